@@ -1,0 +1,757 @@
+// api.cu -- the extern "C" boundary (include/strugatzki_b200.h).  Unity build: all kernels are
+// included here so that one nvcc invocation produces libsgz_b200.so.
+#include "common.cuh"
+#include "corr.cuh"
+#include "corr_kernel.cuh"
+#include "db.cuh"
+#include "peaks.cuh"
+#include "punchout.cuh"
+#include "segm.cuh"
+#include "select.cuh"
+#include "selfsim.cuh"
+
+using namespace sgz;
+
+extern "C" {
+
+int sgz_abi_version(void) { return SGZ_ABI_VERSION; }
+
+const char *sgz_last_error(void) { return err_slot().c_str(); }
+
+int sgz_device_count(int32_t *count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceCount -> %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    if (count) *count = 0;
+    return SGZ_ERR_CUDA;
+  }
+  int usable = 0;
+  for (int d = 0; d < n; d++) {
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, d) == cudaSuccess && pr.major == 10) usable++;
+  }
+  if (count) *count = usable;
+  return SGZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+int sgz_ctx_create(int32_t device, sgz_ctx **out) {
+  SGZ_REQUIRE(out != nullptr, "sgz_ctx_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error("no CUDA device available (%s); strugatzki_b200 has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return SGZ_ERR_CUDA;
+  }
+  SGZ_REQUIRE(device >= 0 && device < n, "sgz_ctx_create: device %d out of range [0,%d)", device, n);
+  cudaDeviceProp pr;
+  SGZ_CUDA(cudaGetDeviceProperties(&pr, device));
+  if (pr.major != 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, pr.major, pr.minor);
+    return SGZ_ERR_CUDA;
+  }
+  sgz_ctx *c = new sgz_ctx();
+  c->device = device;
+  c->smCount = pr.multiProcessorCount;
+  c->smemOptin = pr.sharedMemPerBlockOptin;
+  SGZ_CUDA(cudaSetDevice(device));
+  SGZ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  SGZ_CUDA(cudaEventCreate(&c->ev0));
+  SGZ_CUDA(cudaEventCreate(&c->ev1));
+  *out = c;
+  return SGZ_OK;
+}
+
+int sgz_ctx_destroy(sgz_ctx *ctx) {
+  if (!ctx) return SGZ_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return SGZ_OK;
+}
+
+int sgz_ctx_synchronize(sgz_ctx *ctx) {
+  SGZ_REQUIRE(ctx, "ctx is NULL");
+  SGZ_TRY(ctx->bind());
+  SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SGZ_OK;
+}
+
+void *sgz_ctx_stream(sgz_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int sgz_ctx_last_timing(sgz_ctx *ctx, float *ms, int64_t *launches) {
+  SGZ_REQUIRE(ctx, "ctx is NULL");
+  if (ms) *ms = ctx->lastMs;
+  if (launches) *launches = ctx->lastLaunches;
+  return SGZ_OK;
+}
+
+int64_t sgz_ctx_launch_count(sgz_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int sgz_measure_peak(sgz_ctx *ctx, int32_t which, double *value) {
+  SGZ_REQUIRE(ctx && value, "sgz_measure_peak: NULL argument");
+  return measure_peak(ctx, which, value);
+}
+
+// ---------------------------------------------------------------------------------------------
+// database
+// ---------------------------------------------------------------------------------------------
+int sgz_db_create(sgz_ctx *ctx, int32_t numCh, const float *norm, sgz_db **out) {
+  SGZ_REQUIRE(ctx && out, "sgz_db_create: NULL argument");
+  SGZ_REQUIRE(numCh >= 2 && numCh <= 48, "numCh = numCoeffs + 1 must be in [2,48], got %d", numCh);
+  SGZ_TRY(ctx->bind());
+  sgz_db *db = new sgz_db();
+  db->ctx = ctx;
+  db->numCh = numCh;
+  db->hasNorm = norm != nullptr;
+  db->norm.resize((size_t)numCh * 2);
+  for (int c = 0; c < numCh; c++) {
+    db->norm[2 * c] = norm ? norm[2 * c] : 0.f;
+    db->norm[2 * c + 1] = norm ? norm[2 * c + 1] : 1.f;   // (f - 0) / (1 - 0) == f exactly
+  }
+  int rc = db->dNorm.alloc((size_t)numCh * 2);
+  if (rc < 0) { delete db; return rc; }
+  SGZ_CUDA(cudaMemcpyAsync(db->dNorm.p, db->norm.data(), db->norm.size() * sizeof(float), cudaMemcpyHostToDevice,
+                           ctx->stream));
+  SGZ_CUDA(cudaStreamCreateWithFlags(&db->copyStream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    SGZ_CUDA(cudaEventCreateWithFlags(&db->stageFull[i], cudaEventDisableTiming));
+    SGZ_CUDA(cudaEventCreateWithFlags(&db->stageFree[i], cudaEventDisableTiming));
+  }
+  db->fileStart.push_back(0);
+  *out = db;
+  return SGZ_OK;
+}
+
+int sgz_db_destroy(sgz_db *db) {
+  if (!db) return SGZ_OK;
+  cudaSetDevice(db->ctx->device);
+  cudaStreamSynchronize(db->ctx->stream);
+  cudaStreamSynchronize(db->copyStream);
+  for (int i = 0; i < 2; i++) {
+    cudaEventDestroy(db->stageFull[i]);
+    cudaEventDestroy(db->stageFree[i]);
+  }
+  cudaStreamDestroy(db->copyStream);
+  delete db;
+  return SGZ_OK;
+}
+
+int sgz_db_reserve(sgz_db *db, int64_t totalFrames, int32_t numFiles) {
+  SGZ_REQUIRE(db, "db is NULL");
+  SGZ_REQUIRE(!db->finalized, "sgz_db_reserve after finalize");
+  SGZ_TRY(db->ctx->bind());
+  if (numFiles > 0) db->fileStart.reserve((size_t)numFiles + 1);
+  return db_grow(db, totalFrames);
+}
+
+static int db_begin_file(sgz_db *db, int64_t nFrames, int64_t *dstFrame) {
+  SGZ_REQUIRE(db, "db is NULL");
+  if (db->finalized) {
+    set_error("database already finalized");
+    return SGZ_ERR_STATE;
+  }
+  SGZ_REQUIRE(nFrames >= 0, "negative frame count");
+  SGZ_TRY(db->ctx->bind());
+  SGZ_TRY(db_grow(db, db->usedFrames + nFrames));
+  *dstFrame = db->usedFrames;
+  return SGZ_OK;
+}
+
+static int db_commit_file(sgz_db *db, int64_t nFrames) {
+  db->usedFrames += nFrames;
+  db->fileStart.push_back(db->usedFrames);
+  return db->numFiles() - 1;
+}
+
+int sgz_db_add_file(sgz_db *db, const void *frames, int64_t nFrames, int32_t layout) {
+  int64_t dst = 0;
+  SGZ_TRY(db_begin_file(db, nFrames, &dst));
+  SGZ_REQUIRE(frames || nFrames == 0, "frames is NULL");
+  SGZ_REQUIRE(layout >= 0 && layout <= 2, "unknown layout %d", layout);
+  if (nFrames > 0) {
+    const size_t bytes = (size_t)nFrames * db->numCh * sizeof(float);
+    const int s = db->stageIdx;
+    db->stageIdx ^= 1;
+    if (db->dStage[s].n < bytes) {
+      // staging buffer may still be read by an earlier prepare kernel
+      if (db->stageUsed[s]) SGZ_CUDA(cudaEventSynchronize(db->stageFree[s]));
+      SGZ_TRY(db->dStage[s].alloc(bytes + bytes / 4));
+      db->stageUsed[s] = false;
+    }
+    if (db->stageUsed[s]) SGZ_CUDA(cudaStreamWaitEvent(db->copyStream, db->stageFree[s], 0));
+    SGZ_CUDA(cudaMemcpyAsync(db->dStage[s].p, frames, bytes, cudaMemcpyHostToDevice, db->copyStream));
+    SGZ_CUDA(cudaEventRecord(db->stageFull[s], db->copyStream));
+    SGZ_CUDA(cudaStreamWaitEvent(db->ctx->stream, db->stageFull[s], 0));
+    SGZ_TRY(db_launch_prepare(db, (const float *)db->dStage[s].p, layout, nFrames, dst));
+    SGZ_CUDA(cudaEventRecord(db->stageFree[s], db->ctx->stream));
+    db->stageUsed[s] = true;
+    // the host buffer may be freed on return: pageable copies are staged by the driver before
+    // cudaMemcpyAsync returns, pinned copies need the explicit wait
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, frames) == cudaSuccess && attr.type == cudaMemoryTypeHost)
+      SGZ_CUDA(cudaEventSynchronize(db->stageFull[s]));
+  }
+  return db_commit_file(db, nFrames);
+}
+
+int sgz_db_add_file_device(sgz_db *db, const void *dFrames, int64_t nFrames) {
+  int64_t dst = 0;
+  SGZ_TRY(db_begin_file(db, nFrames, &dst));
+  SGZ_REQUIRE(dFrames || nFrames == 0, "dFrames is NULL");
+  SGZ_TRY(db_launch_prepare(db, (const float *)dFrames, SGZ_LAYOUT_INTERLEAVED_LE, nFrames, dst));
+  return db_commit_file(db, nFrames);
+}
+
+int sgz_db_add_synth(sgz_db *db, uint64_t seed, uint32_t stream, int64_t nFrames, const float *mu,
+                     const float *sigma, float floor0) {
+  int64_t dst = 0;
+  SGZ_TRY(db_begin_file(db, nFrames, &dst));
+  SGZ_REQUIRE(mu && sigma, "mu / sigma is NULL");
+  if (nFrames > 0) {
+    DevBuf<float> ms;
+    SGZ_TRY(ms.alloc((size_t)db->numCh * 2));
+    SGZ_CUDA(cudaMemcpyAsync(ms.p, mu, db->numCh * sizeof(float), cudaMemcpyHostToDevice, db->ctx->stream));
+    SGZ_CUDA(cudaMemcpyAsync(ms.p + db->numCh, sigma, db->numCh * sizeof(float), cudaMemcpyHostToDevice,
+                             db->ctx->stream));
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div<int64_t>(nFrames, 256), 4096), (unsigned)db->numCh);
+    k_db_synth<<<grid, 256, 0, db->ctx->stream>>>(db->dData.p, db->capFrames, dst, nFrames, db->numCh, seed, stream,
+                                                  ms.p, ms.p + db->numCh, floor0, db->dNorm.p);
+    SGZ_LAUNCH_CHECK(db->ctx);
+    SGZ_CUDA(cudaStreamSynchronize(db->ctx->stream));  // ms goes out of scope
+  }
+  return db_commit_file(db, nFrames);
+}
+
+int sgz_db_patch(sgz_db *db, int32_t file, int64_t frameOff, const float *frames, int64_t n) {
+  SGZ_REQUIRE(db && frames, "NULL argument");
+  SGZ_REQUIRE(file >= 0 && file < db->numFiles(), "file index %d out of range", file);
+  int64_t len = db->fileStart[file + 1] - db->fileStart[file];
+  SGZ_REQUIRE(frameOff >= 0 && n >= 0 && frameOff + n <= len, "patch [%lld,+%lld) outside file of %lld frames",
+              (long long)frameOff, (long long)n, (long long)len);
+  SGZ_TRY(db->ctx->bind());
+  if (n == 0) return SGZ_OK;
+  DevBuf<float> tmp;
+  SGZ_TRY(tmp.alloc((size_t)n * db->numCh));
+  SGZ_CUDA(cudaMemcpyAsync(tmp.p, frames, (size_t)n * db->numCh * sizeof(float), cudaMemcpyHostToDevice,
+                           db->ctx->stream));
+  SGZ_TRY(db_launch_prepare(db, tmp.p, SGZ_LAYOUT_INTERLEAVED_LE, n, db->fileStart[file] + frameOff));
+  SGZ_CUDA(cudaStreamSynchronize(db->ctx->stream));
+  return SGZ_OK;
+}
+
+int sgz_db_finalize(sgz_db *db) {
+  SGZ_REQUIRE(db, "db is NULL");
+  SGZ_TRY(db->ctx->bind());
+  if (db->finalized) return SGZ_OK;
+  SGZ_TRY(db_grow(db, db->usedFrames));  // guarantees the zero slack even for an empty DB
+  SGZ_TRY(db->dFileStart.alloc(db->fileStart.size()));
+  SGZ_CUDA(cudaMemcpyAsync(db->dFileStart.p, db->fileStart.data(), db->fileStart.size() * sizeof(int64_t),
+                           cudaMemcpyHostToDevice, db->ctx->stream));
+  SGZ_CUDA(cudaStreamSynchronize(db->copyStream));
+  SGZ_CUDA(cudaStreamSynchronize(db->ctx->stream));
+  db->dStage[0].release();
+  db->dStage[1].release();
+  db->finalized = true;
+  return SGZ_OK;
+}
+
+int sgz_db_info(sgz_db *db, int32_t *numFiles, int64_t *totalFrames, int32_t *numCh) {
+  SGZ_REQUIRE(db, "db is NULL");
+  if (numFiles) *numFiles = db->numFiles();
+  if (totalFrames) *totalFrames = db->usedFrames;
+  if (numCh) *numCh = db->numCh;
+  return SGZ_OK;
+}
+
+int sgz_db_file_frames(sgz_db *db, int32_t file, int64_t *nFrames) {
+  SGZ_REQUIRE(db && nFrames, "NULL argument");
+  SGZ_REQUIRE(file >= 0 && file < db->numFiles(), "file index %d out of range", file);
+  *nFrames = db->fileStart[file + 1] - db->fileStart[file];
+  return SGZ_OK;
+}
+
+int sgz_db_read(sgz_db *db, int32_t file, int64_t frameOff, int64_t n, float *out) {
+  SGZ_REQUIRE(db && out, "NULL argument");
+  SGZ_REQUIRE(file >= 0 && file < db->numFiles(), "file index %d out of range", file);
+  int64_t len = db->fileStart[file + 1] - db->fileStart[file];
+  SGZ_REQUIRE(frameOff >= 0 && n >= 0 && frameOff + n <= len, "read outside file");
+  SGZ_TRY(db->ctx->bind());
+  if (n == 0) return SGZ_OK;
+  DevBuf<float> tmp;
+  SGZ_TRY(tmp.alloc((size_t)n * db->numCh));
+  k_db_gather<<<(unsigned)ceil_div<int64_t>(n * db->numCh, 256), 256, 0, db->ctx->stream>>>(
+      db->dData.p, db->capFrames, db->fileStart[file] + frameOff, n, db->numCh, tmp.p);
+  SGZ_LAUNCH_CHECK(db->ctx);
+  SGZ_CUDA(cudaMemcpyAsync(out, tmp.p, (size_t)n * db->numCh * sizeof(float), cudaMemcpyDeviceToHost,
+                           db->ctx->stream));
+  SGZ_CUDA(cudaStreamSynchronize(db->ctx->stream));
+  return SGZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FeatureCorrelation
+// ---------------------------------------------------------------------------------------------
+static void to_planar(const void *src, int64_t nFrames, int numCh, int layout, std::vector<float> &out) {
+  out.resize((size_t)nFrames * numCh);
+  const float *s = (const float *)src;
+  if (layout == SGZ_LAYOUT_PLANAR_LE) {
+    memcpy(out.data(), s, out.size() * sizeof(float));
+    return;
+  }
+  for (int64_t t = 0; t < nFrames; t++)
+    for (int c = 0; c < numCh; c++) {
+      float v = s[t * numCh + c];
+      if (layout == SGZ_LAYOUT_INTERLEAVED_BE) {
+        uint32_t b;
+        memcpy(&b, &v, 4);
+        b = __builtin_bswap32(b);
+        memcpy(&v, &b, 4);
+      }
+      out[(size_t)c * nFrames + t] = v;
+    }
+}
+
+int sgz_corr_create(sgz_db *db, const sgz_corr_config *cfg, const void *input, int64_t inputFrames, int32_t layout,
+                    sgz_corr **out) {
+  SGZ_REQUIRE(db && cfg && input && out, "sgz_corr_create: NULL argument");
+  *out = nullptr;
+  if (!db->finalized) {
+    set_error("sgz_corr_create: database not finalized");
+    return SGZ_ERR_STATE;
+  }
+  SGZ_REQUIRE(cfg->stepSize > 0, "stepSize must be > 0");
+  SGZ_REQUIRE(layout >= 0 && layout <= 2, "unknown layout %d", layout);
+  SGZ_TRY(db->ctx->bind());
+  sgz_corr *job = new sgz_corr();
+  job->db = db;
+  job->ctx = db->ctx;
+  job->cfg = *cfg;
+  job->step = cfg->stepSize;
+  job->hasOut = cfg->hasPunchOut != 0;
+  job->minPunchF = full_to_feat(cfg->minPunch, job->step);
+  job->maxPunchF = full_to_feat(cfg->maxPunch, job->step);
+  std::vector<float> planar;
+  to_planar(input, inputFrames, db->numCh, layout, planar);
+  int rc = prepare_query(db, planar.data(), inputFrames, cfg->punchInStart, cfg->punchInStop, cfg->punchInWeight,
+                         job->step, job->qin);
+  if (rc == SGZ_OK && job->hasOut)
+    rc = prepare_query(db, planar.data(), inputFrames, cfg->punchOutStart, cfg->punchOutStop, cfg->punchOutWeight,
+                       job->step, job->qout);
+  if (rc == SGZ_OK) {
+    int wq = std::max(job->qin.Wq, job->hasOut ? job->qout.Wq : 0);
+    job->ntg = pick_ntg(job->ctx, db->numCh, wq);
+    if (job->ntg == 0) {
+      set_error("punch window of %d feature frames does not fit the shared-memory tile", wq);
+      rc = SGZ_ERR_INVALID;
+    }
+  }
+  if (rc != SGZ_OK) { delete job; return rc; }
+  job->numTiles = ceil_div<int64_t>(std::max<int64_t>(db->usedFrames, 1), (int64_t)kR * job->ntg);
+  job->numOffsets = valid_offsets(db, job->qin.W, job->hasOut ? job->minPunchF : 0);
+  *out = job;
+  return SGZ_OK;
+}
+
+int sgz_corr_destroy(sgz_corr *job) {
+  if (!job) return SGZ_OK;
+  if (job->worker.joinable()) {
+    job->abortFlag = 1;
+    job->worker.join();
+  }
+  cudaSetDevice(job->ctx->device);
+  cudaStreamSynchronize(job->ctx->stream);
+  delete job;
+  return SGZ_OK;
+}
+
+int sgz_corr_scan(sgz_corr *job) {
+  SGZ_REQUIRE(job, "job is NULL");
+  sgz_ctx *ctx = job->ctx;
+  sgz_db *db = job->db;
+  SGZ_TRY(ctx->bind());
+  if (job->abortFlag) return SGZ_ERR_ABORTED;
+  const size_t n = (size_t)job->numTiles * kR * job->ntg;
+  SGZ_TRY(job->simIn.alloc(n));
+  SGZ_TRY(job->boostIn.alloc(n));
+  SGZ_TRY(job->dFileMax.alloc((size_t)std::max(db->numFiles(), 1)));
+  if (job->hasOut) {
+    SGZ_TRY(job->simOut.alloc(n));
+    SGZ_TRY(job->boostOut.alloc(n));
+  }
+  SGZ_TRY(ctx->begin_call());
+  SGZ_CUDA(cudaMemsetAsync(job->dFileMax.p, 0, job->dFileMax.n * sizeof(unsigned long long), ctx->stream));
+  if (db->usedFrames > 0) {
+    SGZ_TRY(run_scan_one(job, job->qin, job->hasOut ? job->minPunchF : 0, job->simIn.p, job->boostIn.p,
+                         job->dFileMax.p));
+    if (job->hasOut) SGZ_TRY(run_scan_one(job, job->qout, 0, job->simOut.p, job->boostOut.p, nullptr));
+  }
+  SGZ_TRY(ctx->end_call());
+  job->scanMs = ctx->lastMs;
+  job->scanLaunches = ctx->lastLaunches;
+  job->scanned = true;
+  job->progress = 0.8f;
+  // reset selection state
+  job->allPrio.clear();
+  job->nextFile = 0;
+  job->finished = false;
+  job->globalSet = false;
+  job->selectMs = 0.f;
+  return SGZ_OK;
+}
+
+int sgz_corr_local_summary(sgz_corr *job, sgz_file_summary *out, int32_t cap, int32_t *n) {
+  SGZ_REQUIRE(job && n, "NULL argument");
+  if (!job->scanned) { set_error("sgz_corr_local_summary before scan"); return SGZ_ERR_STATE; }
+  sgz_db *db = job->db;
+  SGZ_TRY(job->ctx->bind());
+  const int nf = db->numFiles();
+  *n = nf;
+  if (!out) return SGZ_OK;
+  SGZ_REQUIRE(cap >= nf, "summary buffer too small (%d < %d)", cap, nf);
+  std::vector<unsigned long long> keys((size_t)std::max(nf, 1));
+  if (nf > 0) {
+    SGZ_CUDA(cudaMemcpyAsync(keys.data(), job->dFileMax.p, nf * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                             job->ctx->stream));
+    SGZ_CUDA(cudaStreamSynchronize(job->ctx->stream));
+  }
+  const int tail = job->hasOut ? job->minPunchF : 0;
+  for (int f = 0; f < nf; f++) {
+    int64_t nv = (db->fileStart[f + 1] - db->fileStart[f]) - tail - job->qin.W + 1;
+    out[f].numOffsets = (int32_t)std::max<int64_t>(nv, 0);
+    out[f].maxSim = keys[f] ? float_from_order_key((uint32_t)(keys[f] >> 32)) : -INFINITY;
+  }
+  return SGZ_OK;
+}
+
+int sgz_corr_set_global(sgz_corr *job, const sgz_file_summary *all, int32_t nFilesGlobal, int32_t myFirstFile) {
+  SGZ_REQUIRE(job && (all || nFilesGlobal == 0), "NULL argument");
+  if (!job->scanned) { set_error("sgz_corr_set_global before scan"); return SGZ_ERR_STATE; }
+  SGZ_REQUIRE(myFirstFile >= 0 && myFirstFile + job->db->numFiles() <= nFilesGlobal,
+              "local shard [%d,+%d) outside the global file list of %d", myFirstFile, job->db->numFiles(),
+              nFilesGlobal);
+  job->globalSummary.assign(all, all + nFilesGlobal);
+  job->nFilesGlobal = nFilesGlobal;
+  job->myFirst = myFirstFile;
+  job->globalSet = true;
+  job->allPrio.clear();
+  job->nextFile = 0;
+  job->finished = nFilesGlobal == 0 || job->cfg.numMatches <= 0 || job->cfg.numPerFile <= 0;
+  return SGZ_OK;
+}
+
+// One selection round on the local shard.  See the protocol in strugatzki_b200.h.
+int sgz_corr_select(sgz_corr *job, int32_t *nRecords) {
+  SGZ_REQUIRE(job && nRecords, "NULL argument");
+  if (!job->globalSet) { set_error("sgz_corr_select before set_global"); return SGZ_ERR_STATE; }
+  if (job->abortFlag) return SGZ_ERR_ABORTED;
+  sgz_ctx *ctx = job->ctx;
+  sgz_db *db = job->db;
+  SGZ_TRY(ctx->bind());
+  job->localRecords.clear();
+  *nRecords = 0;
+  if (job->finished) return SGZ_OK;
+  if (job->hasOut) return corr_select_punchout(job, nRecords);
+  const int K = job->cfg.numMatches, npf = job->cfg.numPerFile;
+  const int room = K - (int)job->allPrio.size();
+  const int myLo = job->myFirst, myHi = job->myFirst + db->numFiles();
+  const int tail = 0;
+  if (room > 0) {
+    // ---- filling round: files whose maxEntrySz is known without looking at their results ----
+    const int nb = room >= npf ? room / npf : 1;
+    const int m = room >= npf ? npf : room;
+    job->roundKind = 0;
+    job->roundFirst = job->nextFile;
+    job->roundCount = std::min(nb, job->nFilesGlobal - job->nextFile);
+    job->roundMaxEntrySz = m;
+    std::vector<int32_t> files;
+    for (int g = job->roundFirst; g < job->roundFirst + job->roundCount; g++)
+      if (g >= myLo && g < myHi) files.push_back(g - myLo);
+    if (!files.empty()) {
+      const int nj = (int)files.size();
+      SGZ_TRY(job->dFiles.alloc(nj));
+      SGZ_TRY(job->dCounts.alloc(nj));
+      SGZ_TRY(job->dEntries.alloc((size_t)nj * (npf + 1)));
+      SGZ_CUDA(cudaMemcpyAsync(job->dFiles.p, files.data(), nj * sizeof(int32_t), cudaMemcpyHostToDevice,
+                               ctx->stream));
+      FillParams fp{};
+      fp.sim = job->simIn.p; fp.boost = job->boostIn.p; fp.fileStart = db->dFileStart.p;
+      fp.files = job->dFiles.p; fp.numJobs = nj; fp.W = job->qin.W; fp.tailExtra = tail;
+      fp.numPerFile = npf; fp.maxEntrySz = m; fp.minSpacing = job->cfg.minSpacing; fp.step = job->step;
+      fp.entries = job->dEntries.p; fp.counts = job->dCounts.p;
+      SGZ_TRY(ctx->begin_call());
+      k_replay_fill<<<(unsigned)ceil_div(nj, 4), 128, 0, ctx->stream>>>(fp);
+      SGZ_LAUNCH_CHECK(ctx);
+      SGZ_TRY(ctx->end_call());
+      job->selectMs += ctx->lastMs;
+      std::vector<int32_t> counts(nj);
+      std::vector<EntryRec> ents((size_t)nj * (npf + 1));
+      SGZ_CUDA(cudaMemcpyAsync(counts.data(), job->dCounts.p, nj * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                               ctx->stream));
+      SGZ_CUDA(cudaMemcpyAsync(ents.data(), job->dEntries.p, ents.size() * sizeof(EntryRec), cudaMemcpyDeviceToHost,
+                               ctx->stream));
+      SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+      for (int j = 0; j < nj; j++)
+        for (int k = 0; k < counts[j]; k++) {
+          const EntryRec &e = ents[(size_t)j * (npf + 1) + k];
+          sgz_record r{myLo + files[j], 1, e.piOff, -1, e.sim, e.boostIn, e.boostOut, 0};
+          job->localRecords.push_back(r);
+        }
+    }
+  } else {
+    // ---- full round: allPrio is full; candidates above a provable lower bound of allPrio.last ----
+    job->roundKind = 1;
+    job->roundFirst = job->nextFile;
+    job->roundCount = job->nFilesGlobal - job->nextFile;
+    // running K-th largest DISTINCT value of (allPrio sims U file maxima so far): ascending vector
+    std::vector<float> top;
+    for (const sgz_match &mm : job->allPrio)
+      if (mm.sim == mm.sim) top.push_back(mm.sim);
+    std::sort(top.begin(), top.end());
+    top.erase(std::unique(top.begin(), top.end()), top.end());
+    const float theta0 = job->allPrio.back().sim;   // may be NaN only if every element is NaN
+    std::vector<int32_t> files;
+    std::vector<float> thr;
+    for (int g = job->roundFirst; g < job->nFilesGlobal; g++) {
+      float bound = theta0;
+      if ((int)top.size() >= K && top[top.size() - K] > bound) bound = top[top.size() - K];
+      if (!(bound == bound)) break;  // allPrio.last is NaN: `sim > NaN` never holds -> nothing more is accepted
+      const float mx = job->globalSummary[g].maxSim;
+      if (mx > bound) {
+        if (g >= myLo && g < myHi) { files.push_back(g - myLo); thr.push_back(bound); }
+        auto it = std::lower_bound(top.begin(), top.end(), mx);
+        if (it == top.end() || *it != mx) top.insert(it, mx);
+        if ((int)top.size() > K) top.erase(top.begin());
+      }
+    }
+    if (!files.empty()) {
+      const int nj = (int)files.size();
+      SGZ_TRY(job->dFiles.alloc(nj));
+      SGZ_TRY(job->dThr.alloc(nj));
+      SGZ_TRY(job->dCounter.alloc(1));
+      SGZ_CUDA(cudaMemcpyAsync(job->dFiles.p, files.data(), nj * sizeof(int32_t), cudaMemcpyHostToDevice,
+                               ctx->stream));
+      SGZ_CUDA(cudaMemcpyAsync(job->dThr.p, thr.data(), nj * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+      int cap = std::max(1 << 14, (int)job->dRecs.n);
+      for (;;) {
+        SGZ_TRY(job->dRecs.alloc(cap));
+        SGZ_CUDA(cudaMemsetAsync(job->dCounter.p, 0, sizeof(int), ctx->stream));
+        CandParams cp{};
+        cp.sim = job->simIn.p; cp.boost = job->boostIn.p; cp.fileStart = db->dFileStart.p;
+        cp.files = job->dFiles.p; cp.thresholds = job->dThr.p; cp.numJobs = nj; cp.W = job->qin.W;
+        cp.tailExtra = tail; cp.fileBase = myLo; cp.out = job->dRecs.p; cp.cap = cap; cp.counter = job->dCounter.p;
+        SGZ_TRY(ctx->begin_call());
+        k_candidates<<<dim3((unsigned)nj, 8), 256, 0, ctx->stream>>>(cp);
+        SGZ_LAUNCH_CHECK(ctx);
+        SGZ_TRY(ctx->end_call());
+        job->selectMs += ctx->lastMs;
+        int count = 0;
+        SGZ_CUDA(cudaMemcpyAsync(&count, job->dCounter.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (count <= cap) {
+          job->localRecords.resize(count);
+          if (count > 0) {
+            SGZ_CUDA(cudaMemcpyAsync(job->localRecords.data(), job->dRecs.p, (size_t)count * sizeof(sgz_record),
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+            SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+          }
+          break;
+        }
+        cap = count + count / 2;
+      }
+    }
+  }
+  *nRecords = (int32_t)job->localRecords.size();
+  return SGZ_OK;
+}
+
+int sgz_corr_records(sgz_corr *job, sgz_record *out, int32_t cap, int32_t *n) {
+  SGZ_REQUIRE(job && n, "NULL argument");
+  *n = (int32_t)job->localRecords.size();
+  if (!out) return SGZ_OK;
+  SGZ_REQUIRE(cap >= *n, "record buffer too small (%d < %d)", cap, *n);
+  if (*n > 0) memcpy(out, job->localRecords.data(), (size_t)*n * sizeof(sgz_record));
+  return SGZ_OK;
+}
+
+int sgz_corr_merge(sgz_corr *job, const sgz_record *all, int32_t nAll, int32_t *done) {
+  SGZ_REQUIRE(job && done && (all || nAll == 0), "NULL argument");
+  if (!job->globalSet) { set_error("sgz_corr_merge before set_global"); return SGZ_ERR_STATE; }
+  if (job->finished) { *done = 1; return SGZ_OK; }
+  if (job->hasOut) return corr_merge_punchout(job, all, nAll, done);
+  const int K = job->cfg.numMatches, npf = job->cfg.numPerFile, step = job->step, W = job->qin.W;
+  std::vector<sgz_record> recs(all, all + nAll);
+  auto to_match = [&](const EntryRec &e, int file) {
+    sgz_match m;
+    m.sim = e.sim; m.file = file;
+    m.start = feat_to_full(e.piOff, step);
+    m.stop = feat_to_full(e.stopOff, step);
+    m.boostIn = e.boostIn; m.boostOut = e.boostOut;
+    return m;
+  };
+  auto merge_entry = [&](const EntryRec *e, int n, int file) {  // allPrio ++= entryPrio; take(numMatches)
+    for (int i = 0; i < n; i++) allprio_add(job->allPrio, to_match(e[i], file));
+    if ((int)job->allPrio.size() > K) job->allPrio.resize(K);
+  };
+  if (job->roundKind == 0) {
+    std::stable_sort(recs.begin(), recs.end(), [](const sgz_record &a, const sgz_record &b) { return a.file < b.file; });
+    size_t i = 0;
+    std::vector<EntryRec> ent;
+    for (int g = job->roundFirst; g < job->roundFirst + job->roundCount; g++) {
+      ent.clear();
+      while (i < recs.size() && recs[i].file < g) i++;
+      while (i < recs.size() && recs[i].file == g) {
+        if (recs[i].kind == 1) ent.push_back(EntryRec{recs[i].sim, recs[i].piOff, recs[i].piOff + W, recs[i].boostIn, recs[i].boostOut});
+        i++;
+      }
+      merge_entry(ent.data(), (int)ent.size(), g);
+    }
+    job->nextFile = job->roundFirst + job->roundCount;
+  } else {
+    std::sort(recs.begin(), recs.end(), [](const sgz_record &a, const sgz_record &b) {
+      return a.file != b.file ? a.file < b.file : a.piOff < b.piOff;
+    });
+    std::vector<EntryRec> store((size_t)npf + 1);
+    size_t i = 0;
+    while (i < recs.size()) {
+      const int g = recs[i].file;
+      Machine mc;
+      const int allSize = (int)job->allPrio.size();
+      mc.reset(store.data(), npf, std::min(K - allSize, npf), allSize > 0, allSize > 0 ? job->allPrio.back().sim : 0.f,
+               job->cfg.minSpacing, step);
+      for (; i < recs.size() && recs[i].file == g; i++) {
+        const sgz_record &r = recs[i];
+        if (mc.has_space() || r.sim > mc.lowest())
+          mc.add(EntryRec{r.sim, r.piOff, r.piOff + W, r.boostIn, r.boostOut});
+      }
+      merge_entry(mc.e, mc.n, g);
+    }
+    job->nextFile = job->nFilesGlobal;
+  }
+  if (job->nextFile >= job->nFilesGlobal) job->finished = true;
+  *done = job->finished ? 1 : 0;
+  if (job->finished) job->progress = 1.0f;
+  return SGZ_OK;
+}
+
+static int corr_run_body(sgz_corr *job) {
+  SGZ_TRY(sgz_corr_scan(job));
+  int32_t nf = 0;
+  SGZ_TRY(sgz_corr_local_summary(job, nullptr, 0, &nf));
+  std::vector<sgz_file_summary> sum((size_t)std::max(nf, 1));
+  SGZ_TRY(sgz_corr_local_summary(job, sum.data(), nf, &nf));
+  SGZ_TRY(sgz_corr_set_global(job, sum.data(), nf, 0));
+  int32_t done = job->finished ? 1 : 0;
+  while (!done) {
+    if (job->abortFlag) return SGZ_ERR_ABORTED;
+    int32_t nrec = 0;
+    SGZ_TRY(sgz_corr_select(job, &nrec));
+    SGZ_TRY(sgz_corr_merge(job, job->localRecords.data(), nrec, &done));
+    if (job->nFilesGlobal > 0)
+      job->progress = 0.8f + 0.2f * (float)job->nextFile / (float)job->nFilesGlobal;
+  }
+  job->progress = 1.0f;
+  return SGZ_OK;
+}
+
+int sgz_corr_run(sgz_corr *job) {
+  SGZ_REQUIRE(job, "job is NULL");
+  job->abortFlag = 0;
+  return corr_run_body(job);
+}
+
+int sgz_corr_start(sgz_corr *job) {
+  SGZ_REQUIRE(job, "job is NULL");
+  if (job->worker.joinable()) {
+    if (!job->doneFlag) { set_error("job already running"); return SGZ_ERR_STATE; }
+    job->worker.join();
+  }
+  job->abortFlag = 0;
+  job->doneFlag = 0;
+  job->status = 0;
+  job->progress = 0.f;
+  job->worker = std::thread([job]() {
+    int rc = corr_run_body(job);
+    job->status = rc;
+    job->doneFlag = 1;
+  });
+  return SGZ_OK;
+}
+
+int sgz_corr_poll(sgz_corr *job, float *progress, int32_t *done, int32_t *status) {
+  SGZ_REQUIRE(job, "job is NULL");
+  if (progress) *progress = job->progress.load();
+  if (done) *done = job->doneFlag.load();
+  if (status) *status = job->status.load();
+  return SGZ_OK;
+}
+
+int sgz_corr_abort(sgz_corr *job) {
+  SGZ_REQUIRE(job, "job is NULL");
+  job->abortFlag = 1;
+  return SGZ_OK;
+}
+
+int sgz_corr_wait(sgz_corr *job) {
+  SGZ_REQUIRE(job, "job is NULL");
+  if (job->worker.joinable()) job->worker.join();
+  return job->status.load();
+}
+
+int sgz_corr_result(sgz_corr *job, sgz_match *out, int32_t cap, int32_t *n) {
+  SGZ_REQUIRE(job && n, "NULL argument");
+  *n = (int32_t)job->allPrio.size();
+  if (!out) return SGZ_OK;
+  SGZ_REQUIRE(cap >= *n, "result buffer too small (%d < %d)", cap, *n);
+  for (int i = 0; i < *n; i++) out[i] = job->allPrio[i];
+  return SGZ_OK;
+}
+
+int sgz_corr_num_offsets(sgz_corr *job, int64_t *n) {
+  SGZ_REQUIRE(job && n, "NULL argument");
+  *n = job->numOffsets;
+  return SGZ_OK;
+}
+
+int sgz_corr_timing(sgz_corr *job, float *scanMs, float *selectMs, int64_t *scanLaunches) {
+  SGZ_REQUIRE(job, "job is NULL");
+  if (scanMs) *scanMs = job->scanMs;
+  if (selectMs) *selectMs = job->selectMs;
+  if (scanLaunches) *scanLaunches = job->scanLaunches;
+  return SGZ_OK;
+}
+
+int sgz_corr_curve(sgz_corr *job, int32_t which, int32_t file, int64_t first, int64_t n, float *sim, float *boost) {
+  SGZ_REQUIRE(job, "job is NULL");
+  if (!job->scanned) { set_error("sgz_corr_curve before scan"); return SGZ_ERR_STATE; }
+  sgz_db *db = job->db;
+  SGZ_REQUIRE(which == 0 || (which == 1 && job->hasOut), "curve %d not available", which);
+  SGZ_REQUIRE(file >= 0 && file < db->numFiles(), "file index %d out of range", file);
+  const int W = which == 0 ? job->qin.W : job->qout.W;
+  const int tail = (which == 0 && job->hasOut) ? job->minPunchF : 0;
+  const int64_t nValid = (db->fileStart[file + 1] - db->fileStart[file]) - tail - W + 1;
+  SGZ_REQUIRE(first >= 0 && n >= 0 && first + n <= std::max<int64_t>(nValid, 0),
+              "curve range [%lld,+%lld) outside the %lld evaluated offsets", (long long)first, (long long)n,
+              (long long)nValid);
+  SGZ_TRY(job->ctx->bind());
+  const float *s = (which == 0 ? job->simIn.p : job->simOut.p) + db->fileStart[file] + first;
+  const float *b = (which == 0 ? job->boostIn.p : job->boostOut.p) + db->fileStart[file] + first;
+  if (n > 0) {
+    if (sim) SGZ_CUDA(cudaMemcpyAsync(sim, s, n * sizeof(float), cudaMemcpyDeviceToHost, job->ctx->stream));
+    if (boost) SGZ_CUDA(cudaMemcpyAsync(boost, b, n * sizeof(float), cudaMemcpyDeviceToHost, job->ctx->stream));
+    SGZ_CUDA(cudaStreamSynchronize(job->ctx->stream));
+  }
+  return SGZ_OK;
+}
+
+}  // extern "C"
+
+#include "api_segself.cuh"

@@ -1,0 +1,253 @@
+// api_segself.cuh -- extern "C" entry points of FeatureSegmentation and SelfSimilarity
+// (included by api.cu; unity build).
+#pragma once
+#include "common.cuh"
+#include "db.cuh"
+#include "segm.cuh"
+#include "selfsim.cuh"
+
+namespace sgz {
+
+// raw frames (any layout) [first, first+n) -> normalised planar device buffer [numCh][stride]
+inline int upload_features(sgz_ctx *ctx, int numCh, const float *norm, const void *frames, int64_t nFrames,
+                           int layout, int64_t first, int64_t n, DevBuf<float> &out, int64_t &stride) {
+  SGZ_REQUIRE(numCh >= 2 && numCh <= 48, "numCh = numCoeffs + 1 must be in [2,48], got %d", numCh);
+  SGZ_REQUIRE(layout >= 0 && layout <= 2, "unknown layout %d", layout);
+  SGZ_REQUIRE(first >= 0 && n >= 0 && first + n <= nFrames, "frame range outside the file");
+  stride = std::max<int64_t>((n + 3) / 4 * 4, 4);
+  SGZ_TRY(out.alloc((size_t)stride * numCh));
+  SGZ_CUDA(cudaMemsetAsync(out.p, 0, (size_t)stride * numCh * sizeof(float), ctx->stream));
+  if (n == 0) return SGZ_OK;
+  std::vector<float> nm((size_t)numCh * 2);
+  for (int c = 0; c < numCh; c++) { nm[2 * c] = norm ? norm[2 * c] : 0.f; nm[2 * c + 1] = norm ? norm[2 * c + 1] : 1.f; }
+  DevBuf<float> dNorm, stage;
+  SGZ_TRY(dNorm.alloc(nm.size()));
+  SGZ_CUDA(cudaMemcpyAsync(dNorm.p, nm.data(), nm.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  SGZ_TRY(stage.alloc((size_t)n * numCh));
+  const float *src = (const float *)frames;
+  if (layout == SGZ_LAYOUT_PLANAR_LE) {
+    SGZ_CUDA(cudaMemcpy2DAsync(stage.p, (size_t)n * sizeof(float), src + first, (size_t)nFrames * sizeof(float),
+                               (size_t)n * sizeof(float), (size_t)numCh, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    SGZ_CUDA(cudaMemcpyAsync(stage.p, src + first * numCh, (size_t)n * numCh * sizeof(float), cudaMemcpyHostToDevice,
+                             ctx->stream));
+  }
+  int blocks = (int)ceil_div<int64_t>(n, kPrepFrames);
+  k_db_prepare<<<blocks, 256, (size_t)kPrepFrames * numCh * sizeof(float), ctx->stream>>>(
+      stage.p, layout, n, out.p, stride, 0, numCh, dNorm.p);
+  SGZ_LAUNCH_CHECK(ctx);
+  SGZ_CUDA(cudaStreamSynchronize(ctx->stream));  // stage / dNorm go out of scope
+  return SGZ_OK;
+}
+
+inline void span_to_feat(int hasStart, int hasStop, int64_t spanStart, int64_t spanStop, int step, int64_t nFrames,
+                         int &afStart, int &afStop) {
+  afStart = 0;
+  if (hasStart) afStart = std::max(0, full_to_feat(spanStart, step));
+  afStop = (int)nFrames;
+  if (hasStop) afStop = std::min((int)nFrames, full_to_feat(spanStop, step));
+}
+
+inline int self_geometry(const sgz_self_config *cfg, int64_t n1, int64_t n2, sgz_self_geometry *g, int *Hout) {
+  SGZ_REQUIRE(cfg->stepSize > 0, "stepSize must be > 0");
+  const int H = full_to_feat(cfg->corrLen, cfg->stepSize);
+  SGZ_REQUIRE(H > 0, "corrLen rounds to an empty window");
+  SGZ_REQUIRE(cfg->decimation >= 1, "Illegal decimation setting of %d", cfg->decimation);
+  const int64_t afNum = std::min(n1, n2);
+  int afStart, afStop;
+  span_to_feat(cfg->hasStart, cfg->hasStop, cfg->spanStart, cfg->spanStop, cfg->stepSize, afNum, afStart, afStop);
+  const int afLen = afStop - afStart;
+  const int64_t n = std::max<int64_t>(0, (int64_t)afLen - 2 * H + 1);
+  const int numCorrs = (int)n;
+  int d = cfg->decimation, ext = numCorrs / d;
+  if (ext > 0xB504) {                                   // SelfSimilarityImpl.scala:85-90
+    d = (numCorrs + 0xB503) / 0xB504;
+    ext = numCorrs / d;
+  }
+  g->imgExt = ext;
+  g->decim = d;
+  g->numCorrs = numCorrs;
+  g->afStart = afStart;
+  g->numCells = (int64_t)ext * (ext + 1) / 2;
+  if (Hout) *Hout = H;
+  return SGZ_OK;
+}
+
+}  // namespace sgz
+
+extern "C" {
+
+int sgz_segm_run(sgz_ctx *ctx, const sgz_segm_config *cfg, int32_t numCh, const float *norm, const void *frames,
+                 int64_t nFrames, int32_t layout, sgz_break *out, int32_t cap, int32_t *n, float *curve,
+                 int64_t curveCap, int64_t *numOffsets) {
+  using namespace sgz;
+  SGZ_REQUIRE(ctx && cfg && frames && n, "sgz_segm_run: NULL argument");
+  SGZ_REQUIRE(cfg->stepSize > 0, "stepSize must be > 0");
+  SGZ_TRY(ctx->bind());
+  const int step = cfg->stepSize;
+  const int H = full_to_feat(cfg->corrLen, step);
+  SGZ_REQUIRE(H > 0, "corrLen rounds to an empty window");
+  int afStart, afStop;
+  span_to_feat(cfg->hasStart, cfg->hasStop, cfg->spanStart, cfg->spanStop, step, nFrames, afStart, afStop);
+  const int afLen = afStop - afStart;
+  *n = 0;
+  if (numOffsets) *numOffsets = 0;
+  if (afLen <= 0) return SGZ_OK;
+  // reference loop count (:107-133): one iteration for the first (possibly short) read, then one per frame
+  const int nOff = afLen >= 2 * H ? afLen - 2 * H + 1 : 1;
+  DevBuf<float> x, dCurve;
+  int64_t stride = 0;
+  SGZ_TRY(upload_features(ctx, numCh, norm, frames, nFrames, layout, afStart, afLen, x, stride));
+  SGZ_TRY(dCurve.alloc(nOff));
+  DevBuf<sgz_break> dOut;
+  DevBuf<int> dCount;
+  const int nb = std::max(cfg->numBreaks, 0);
+  SGZ_TRY(dOut.alloc((size_t)nb + 1));
+  SGZ_TRY(dCount.alloc(1));
+  SegmParams sp{x.p, stride, afLen, numCh, H, nOff, cfg->temporalWeight, dCurve.p};
+  PickParams pp{dCurve.p, nOff, afStart, H, step, nb, cfg->minSpacing, dOut.p, dCount.p};
+  SGZ_TRY(ctx->begin_call());
+  k_segm_curve<<<ceil_div(nOff, 128), 128, 0, ctx->stream>>>(sp);
+  SGZ_LAUNCH_CHECK(ctx);
+  k_segm_pick<<<1, 32, 0, ctx->stream>>>(pp);
+  SGZ_LAUNCH_CHECK(ctx);
+  SGZ_TRY(ctx->end_call());
+  int count = 0;
+  SGZ_CUDA(cudaMemcpyAsync(&count, dCount.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<sgz_break> br((size_t)std::max(count, 1));
+  if (count > 0) {
+    SGZ_CUDA(cudaMemcpyAsync(br.data(), dOut.p, count * sizeof(sgz_break), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (curve && curveCap > 0) {
+    SGZ_CUDA(cudaMemcpyAsync(curve, dCurve.p, (size_t)std::min<int64_t>(curveCap, nOff) * sizeof(float),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  *n = count;
+  if (numOffsets) *numOffsets = nOff;
+  if (out) {
+    SGZ_REQUIRE(cap >= count, "break buffer too small (%d < %d)", cap, count);
+    for (int i = 0; i < count; i++) out[i] = br[i];
+  }
+  return SGZ_OK;
+}
+
+int sgz_self_geometry_of(const sgz_self_config *cfg, int64_t nFrames1, int64_t nFrames2, sgz_self_geometry *out) {
+  using namespace sgz;
+  SGZ_REQUIRE(cfg && out, "NULL argument");
+  return self_geometry(cfg, nFrames1, nFrames2, out, nullptr);
+}
+
+static int self_prepare(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh, const float *norm,
+                        const void *frames1, int64_t n1, const void *frames2, int64_t n2, int32_t layout,
+                        sgz_self_geometry &g, int &H, DevBuf<float> &x1, DevBuf<float> &x2, DevBuf<int32_t> &dLut,
+                        sgz::SelfParams &p) {
+  using namespace sgz;
+  SGZ_REQUIRE(cfg->colorWarp > 0, "Illegal color warp setting. Must be > 0, but is %g", cfg->colorWarp);
+  SGZ_REQUIRE(cfg->colorCeil > 0, "Illegal color ceil setting. Must be > 0, but is %g", cfg->colorCeil);
+  if (!frames2) n2 = n1;
+  SGZ_TRY(self_geometry(cfg, n1, n2, &g, &H));
+  // frames needed: [afStart, afStart + numCorrs - 1 + H] of both files (rightOff + H <= afLen - H)
+  const int64_t need = g.numCorrs > 0 ? (int64_t)g.numCorrs - 1 + H : 0;
+  int64_t s1 = 0, s2 = 0;
+  SGZ_TRY(upload_features(ctx, numCh, norm, frames1, n1, layout, g.afStart, need, x1, s1));
+  if (frames2) SGZ_TRY(upload_features(ctx, numCh, norm, frames2, n2, layout, g.afStart, need, x2, s2));
+  if (cfg->lut) {
+    SGZ_REQUIRE(cfg->lutSize >= 2, "lutSize must be >= 2");
+    SGZ_TRY(dLut.alloc(cfg->lutSize));
+    SGZ_CUDA(cudaMemcpyAsync(dLut.p, cfg->lut, cfg->lutSize * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  p = SelfParams{};
+  p.x1 = x1.p;
+  p.x2 = frames2 ? x2.p : x1.p;
+  p.stride1 = s1;
+  p.stride2 = frames2 ? s2 : s1;
+  p.numCh = numCh; p.H = H; p.decim = g.decim; p.imgExt = g.imgExt;
+  p.weight = cfg->temporalWeight;
+  p.colorInv = cfg->colorInv;
+  p.colorWarp = cfg->colorWarp;
+  p.colorScale = 1.0f / cfg->colorCeil;
+  p.lut = cfg->lut ? dLut.p : nullptr;
+  p.lutSize = cfg->lutSize;
+  return SGZ_OK;
+}
+
+int sgz_self_run(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh, const float *norm, const void *frames1,
+                 int64_t nFrames1, const void *frames2, int64_t nFrames2, int32_t layout, int32_t rowBegin,
+                 int32_t rowEnd, int32_t *rgb, int64_t rgbCap, sgz_self_geometry *geom) {
+  using namespace sgz;
+  SGZ_REQUIRE(ctx && cfg && frames1, "sgz_self_run: NULL argument");
+  SGZ_TRY(ctx->bind());
+  sgz_self_geometry g{};
+  int H = 0;
+  DevBuf<float> x1, x2;
+  DevBuf<int32_t> dLut, dRgb;
+  DevBuf<int2> dTiles;
+  SelfParams p;
+  SGZ_TRY(self_prepare(ctx, cfg, numCh, norm, frames1, nFrames1, frames2, nFrames2, layout, g, H, x1, x2, dLut, p));
+  if (geom) *geom = g;
+  const int ext = g.imgExt;
+  if (rowEnd <= 0 || rowEnd > ext) rowEnd = ext;
+  if (rowBegin < 0) rowBegin = 0;
+  if (ext == 0 || rowBegin >= rowEnd) return SGZ_OK;
+  SGZ_REQUIRE(!rgb || rgbCap >= (int64_t)ext * ext, "rgb buffer too small for %d x %d pixels", ext, ext);
+  SGZ_TRY(dRgb.alloc((size_t)ext * ext));
+  SGZ_CUDA(cudaMemsetAsync(dRgb.p, 0, (size_t)ext * ext * sizeof(int32_t), ctx->stream));
+  std::vector<int2> tiles;
+  for (int a0 = rowBegin / kSelfTile * kSelfTile; a0 < rowEnd; a0 += kSelfTile)
+    for (int b0 = a0 / kSelfTile * kSelfTile; b0 < ext; b0 += kSelfTile) tiles.push_back(make_int2(a0, b0));
+  SGZ_TRY(dTiles.alloc(tiles.size()));
+  SGZ_CUDA(cudaMemcpyAsync(dTiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+  p.colBegin = rowBegin;
+  p.colEnd = rowEnd;
+  p.rgb = dRgb.p;
+  const size_t smem = (size_t)2 * numCh * (g.decim * (kSelfTile - 1) + H) * sizeof(float);
+  SGZ_REQUIRE(smem <= ctx->smemOptin, "self-similarity tile needs %zu bytes of shared memory", smem);
+  SGZ_CUDA(cudaFuncSetAttribute(k_self_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemOptin));
+  SGZ_TRY(ctx->begin_call());
+  k_self_tiles<<<(unsigned)tiles.size(), kSelfTile * kSelfTile, smem, ctx->stream>>>(p, dTiles.p);
+  SGZ_LAUNCH_CHECK(ctx);
+  SGZ_TRY(ctx->end_call());
+  if (rgb) {
+    SGZ_CUDA(cudaMemcpyAsync(rgb, dRgb.p, (size_t)ext * ext * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return SGZ_OK;
+}
+
+int sgz_self_cells(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh, const float *norm, const void *frames1,
+                   int64_t nFrames1, const void *frames2, int64_t nFrames2, int32_t layout, int64_t nCells,
+                   const int32_t *leftIdx, const int32_t *rightIdx, float *sim, int32_t *rgb) {
+  using namespace sgz;
+  SGZ_REQUIRE(ctx && cfg && frames1 && leftIdx && rightIdx, "sgz_self_cells: NULL argument");
+  SGZ_TRY(ctx->bind());
+  sgz_self_geometry g{};
+  int H = 0;
+  DevBuf<float> x1, x2, dSim;
+  DevBuf<int32_t> dLut, dL, dR, dRgb;
+  SelfParams p;
+  SGZ_TRY(self_prepare(ctx, cfg, numCh, norm, frames1, nFrames1, frames2, nFrames2, layout, g, H, x1, x2, dLut, p));
+  if (nCells <= 0) return SGZ_OK;
+  for (int64_t k = 0; k < nCells; k++)
+    SGZ_REQUIRE(leftIdx[k] >= 0 && leftIdx[k] < g.imgExt && rightIdx[k] >= 0 && rightIdx[k] < g.imgExt,
+                "cell %lld = (%d,%d) outside the %d x %d image", (long long)k, leftIdx[k], rightIdx[k], g.imgExt,
+                g.imgExt);
+  SGZ_TRY(dL.alloc(nCells));
+  SGZ_TRY(dR.alloc(nCells));
+  SGZ_TRY(dSim.alloc(nCells));
+  SGZ_TRY(dRgb.alloc(nCells));
+  SGZ_CUDA(cudaMemcpyAsync(dL.p, leftIdx, nCells * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  SGZ_CUDA(cudaMemcpyAsync(dR.p, rightIdx, nCells * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  p.leftIdx = dL.p; p.rightIdx = dR.p; p.nCells = nCells; p.simOut = dSim.p; p.rgbOut = dRgb.p;
+  SGZ_TRY(ctx->begin_call());
+  k_self_cells<<<(unsigned)ceil_div<int64_t>(nCells, 128), 128, 0, ctx->stream>>>(p);
+  SGZ_LAUNCH_CHECK(ctx);
+  SGZ_TRY(ctx->end_call());
+  if (sim) SGZ_CUDA(cudaMemcpyAsync(sim, dSim.p, nCells * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  if (rgb) SGZ_CUDA(cudaMemcpyAsync(rgb, dRgb.p, nCells * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SGZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,205 @@
+// corr.cuh -- host side of one FeatureCorrelation search: query preparation
+// (readInBuffer, FeatureCorrelationImpl.scala:83-98), K1 launches, and the round-based
+// select/merge protocol that reproduces allPrio / entryPrio exactly (see select.cuh).
+#pragma once
+#include "common.cuh"
+#include "corr_kernel.cuh"
+#include "db.cuh"
+#include "select.cuh"
+
+struct PunchQuery {
+  int W = 0, Wq = 0;
+  float weight = 0.5f;
+  std::vector<float> taps;  // [numCh][Wq]
+  double stdT = 0, stdS = 0, rhoT = 0, rhoS = 0, lnAvg = 0;
+  DevBuf<float> dTaps;
+};
+
+struct sgz_corr {
+  sgz_db *db = nullptr;
+  sgz_ctx *ctx = nullptr;
+  sgz_corr_config cfg{};
+  int step = 1, minPunchF = 0, maxPunchF = 0;
+  bool hasOut = false;
+  PunchQuery qin, qout;
+  int ntg = 128;
+  int64_t numTiles = 0;
+  int64_t numOffsets = 0;
+  DevBuf<float> simIn, boostIn, simOut, boostOut;
+  DevBuf<unsigned long long> dFileMax;
+  bool scanned = false;
+
+  // global (all ranks) view
+  std::vector<sgz_file_summary> globalSummary;
+  int nFilesGlobal = 0, myFirst = 0;
+  bool globalSet = false;
+
+  // replicated selection state
+  std::vector<sgz_match> allPrio;  // descending Float.compare order, unique sims
+  int nextFile = 0;
+  bool finished = false;
+  // current round
+  int roundKind = -1;  // 0 = filling, 1 = full
+  int roundFirst = 0, roundCount = 0, roundMaxEntrySz = 0;
+  std::vector<sgz_record> localRecords;
+
+  // device scratch for the selection kernels
+  DevBuf<int32_t> dFiles, dCounts;
+  DevBuf<float> dThr;
+  DevBuf<sgz::EntryRec> dEntries;
+  DevBuf<sgz_record> dRecs;
+  DevBuf<int> dCounter;
+
+  // timing (device ms of the last scan / accumulated select kernels)
+  float scanMs = 0.f, selectMs = 0.f;
+  int64_t scanLaunches = 0;
+
+  // async
+  std::thread worker;
+  std::atomic<int> abortFlag{0}, doneFlag{0}, status{0};
+  std::atomic<float> progress{0.f};
+};
+
+namespace sgz {
+
+// readInBuffer (FeatureCorrelationImpl.scala:83-98): cut [start,stop) feature frames, normalise,
+// matrix-wide stats of the temporal (ch 0) and spectral (ch 1..) groups, ln of the loudness average.
+inline int prepare_query(const sgz_db *db, const float *inputPlanar /*[numCh][inputFrames]*/, int64_t inputFrames,
+                         int64_t spanStart, int64_t spanStop, float weight, int step, PunchQuery &q) {
+  const int numCh = db->numCh;
+  const int start = full_to_feat(spanStart, step), stop = full_to_feat(spanStop, step);
+  const int W = stop - start;
+  SGZ_REQUIRE(W > 0, "punch span [%lld,%lld) is empty after rounding to feature frames", (long long)spanStart,
+              (long long)spanStop);
+  if (start < 0 || stop > inputFrames) {
+    set_error("punch span reads feature frames [%d,%d) but the input has %lld frames (reference: EOFException)",
+              start, stop, (long long)inputFrames);
+    return SGZ_ERR_IO;
+  }
+  q.W = W;
+  q.Wq = (W + 3) / 4 * 4;
+  q.weight = weight;
+  std::vector<float> a((size_t)numCh * W);
+  for (int c = 0; c < numCh; c++) {
+    float mn = 0.f, d = 1.f;
+    if (db->hasNorm) { mn = db->norm[2 * c]; d = db->norm[2 * c + 1] - mn; }
+    for (int i = 0; i < W; i++) {
+      float f = inputPlanar[(size_t)c * inputFrames + start + i];
+      a[(size_t)c * W + i] = db->hasNorm ? (f - mn) / d : f;   // MathUtil.normalize
+    }
+  }
+  auto stat = [&](int c0, int c1, double &mean, double &sd) {  // MathUtil.stat, same loop order
+    double sum = 0.0;
+    for (int c = c0; c < c1; c++) for (int i = 0; i < W; i++) sum += a[(size_t)c * W + i];
+    int matSize = W * (c1 - c0);
+    mean = sum / matSize;
+    sum = 0.0;
+    for (int c = c0; c < c1; c++) for (int i = 0; i < W; i++) { double dd = a[(size_t)c * W + i] - mean; sum += dd * dd; }
+    sd = sqrt(sum / matSize);
+  };
+  double meanT, meanS;
+  stat(0, 1, meanT, q.stdT);
+  stat(1, numCh, meanS, q.stdS);
+  {
+    double sum = 0.0;  // MathUtil.avg -> Float, then math.log
+    for (int i = 0; i < W; i++) sum += a[i];
+    float avg = (float)(sum / W);
+    q.lnAvg = log((double)avg);
+  }
+  q.taps.assign((size_t)numCh * q.Wq, 0.f);
+  q.rhoT = q.rhoS = 0.0;
+  for (int c = 0; c < numCh; c++) {
+    double mean = c == 0 ? meanT : meanS;
+    for (int i = 0; i < W; i++) {
+      float tp = (float)((double)a[(size_t)c * W + i] - mean);
+      q.taps[(size_t)c * q.Wq + i] = tp;
+      (c == 0 ? q.rhoT : q.rhoS) += (double)tp;
+    }
+  }
+  SGZ_TRY(q.dTaps.alloc(q.taps.size()));
+  SGZ_CUDA(cudaMemcpyAsync(q.dTaps.p, q.taps.data(), q.taps.size() * sizeof(float), cudaMemcpyHostToDevice,
+                           db->ctx->stream));
+  return SGZ_OK;
+}
+
+template <int NTG>
+inline int launch_corr_ntg(sgz_ctx *ctx, const CorrParams &p, size_t smemBytes, int64_t tileBegin, int64_t tileEnd) {
+  static thread_local int configuredDevice = -1;
+  static thread_local size_t configuredSmem = 0;
+  if (configuredDevice != ctx->device || configuredSmem < smemBytes) {
+    SGZ_CUDA(cudaFuncSetAttribute(k_corr<NTG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemOptin));
+    configuredDevice = ctx->device;
+    configuredSmem = ctx->smemOptin;
+  }
+  (void)tileBegin;
+  k_corr<NTG><<<(unsigned)(tileEnd - tileBegin), 2 * NTG, smemBytes, ctx->stream>>>(p);
+  SGZ_LAUNCH_CHECK(ctx);
+  return SGZ_OK;
+}
+
+inline int pick_ntg(const sgz_ctx *ctx, int numCh, int Wq) {
+  const int opts[3] = {128, 64, 32};
+  for (int k = 0; k < 3; k++)
+    if (corr_smem_layout(opts[k], numCh, Wq).total <= ctx->smemOptin) return opts[k];
+  return 0;
+}
+
+inline int64_t valid_offsets(const sgz_db *db, int W, int tailExtra) {
+  int64_t total = 0;
+  for (int f = 0; f < db->numFiles(); f++) {
+    int64_t n = (db->fileStart[f + 1] - db->fileStart[f]) - tailExtra - W + 1;
+    if (n > 0) total += n;
+  }
+  return total;
+}
+
+inline int run_scan_one(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim, float *boost,
+                        unsigned long long *fileMax) {
+  sgz_db *db = job->db;
+  CorrParams p{};
+  p.data = db->dData.p;
+  p.chanStride = db->capFrames;
+  p.usedFrames = db->usedFrames;
+  p.numCh = db->numCh;
+  p.csplit = (db->numCh + 1) / 2;
+  p.W = q.W;
+  p.Wq = q.Wq;
+  p.taps = q.dTaps.p;
+  p.stdT = q.stdT; p.stdS = q.stdS; p.rhoT = q.rhoT; p.rhoS = q.rhoS;
+  p.lnAvgIn = q.lnAvg;
+  p.weight = q.weight;
+  p.maxBoost = job->cfg.maxBoost;
+  p.fileStart = db->dFileStart.p;
+  p.numFiles = db->numFiles();
+  p.tailExtra = tailExtra;
+  p.sim = sim;
+  p.boost = boost;
+  p.fileMax = fileMax;
+  CorrSmemLayout L = corr_smem_layout(job->ntg, db->numCh, q.Wq);
+  int rc;
+  switch (job->ntg) {
+    case 128: rc = launch_corr_ntg<128>(job->ctx, p, L.total, 0, job->numTiles); break;
+    case 64: rc = launch_corr_ntg<64>(job->ctx, p, L.total, 0, job->numTiles); break;
+    default: rc = launch_corr_ntg<32>(job->ctx, p, L.total, 0, job->numTiles); break;
+  }
+  return rc;
+}
+
+// ---- allPrio helpers (host): SortedSet[Match](MatchMinOrd) ----
+inline int allprio_find(const std::vector<sgz_match> &s, float sim, bool &found) {
+  found = false;
+  size_t i = 0;
+  for (; i < s.size(); i++) {
+    int c = jfloat_compare(s[i].sim, sim);
+    if (c == 0) { found = true; return (int)i; }
+    if (c < 0) return (int)i;
+  }
+  return (int)i;
+}
+inline void allprio_add(std::vector<sgz_match> &s, const sgz_match &m) {
+  bool found;
+  int i = allprio_find(s, m.sim, found);
+  if (!found) s.insert(s.begin() + i, m);
+}
+
+}  // namespace sgz

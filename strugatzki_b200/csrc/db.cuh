@@ -1,0 +1,152 @@
+// db.cuh -- the feature database resident in HBM.
+//
+// Replaces the reference's per-offset feature I/O: `afExtr.read(eInBuf, readOff, 1)` +
+// `MathUtil.normalize` once per frame-offset (FeatureCorrelationImpl.scala:195-197,
+// MathUtil.scala:132-152).  Every DB file is uploaded once, normalised with the same float
+// expression `(f - min) / (max - min)` (IEEE division, bit-identical to the JVM), and kept as
+// ONE planar stream  data[channel][globalFrame]  in which the files follow each other without
+// padding.  K1 tiles that stream; a file table maps global frames back to (file, local frame).
+#pragma once
+#include "common.cuh"
+
+struct sgz_db {
+  sgz_ctx *ctx = nullptr;
+  int numCh = 0;
+  bool hasNorm = false;
+  std::vector<float> norm;              // [numCh][2] host copy
+  DevBuf<float> dNorm;                  // [numCh][2]; {0,1} per channel when normalize=false
+  DevBuf<float> dData;                  // planar [numCh][capFrames]
+  int64_t capFrames = 0;                // channel stride (multiple of 4)
+  int64_t usedFrames = 0;
+  std::vector<int64_t> fileStart;       // size numFiles+1 (last = usedFrames)
+  DevBuf<int64_t> dFileStart;
+  bool finalized = false;
+  // double-buffered upload staging
+  DevBuf<unsigned char> dStage[2];
+  cudaStream_t copyStream = nullptr;
+  cudaEvent_t stageFull[2] = {nullptr, nullptr}, stageFree[2] = {nullptr, nullptr};
+  int stageIdx = 0;
+  bool stageUsed[2] = {false, false};
+
+  int numFiles() const { return (int)fileStart.size() - 1; }
+};
+
+namespace sgz {
+
+constexpr int64_t kDbSlack = 4096;  // readable zero frames behind the last file (tile halo)
+
+// ---- synthetic features.  Integer hash -> exact integer sum of 8
+// consecutive 24-bit values -> ONE float scale, so numpy (strugatzki_b200/synth.py) and this
+// kernel produce bit-identical floats. --------------------------------------------------------
+__host__ __device__ inline uint32_t synth_u24(uint64_t seed, uint32_t stream, uint32_t c, uint64_t t) {
+  uint64_t z = seed + (uint64_t)stream * 0xD1B54A32D192ED03ULL + (uint64_t)c * 0x9E3779B97F4A7C15ULL +
+               t * 0xBF58476D1CE4E5B9ULL;
+  z ^= z >> 30;
+  z *= 0xBF58476D1CE4E5B9ULL;
+  z ^= z >> 27;
+  z *= 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 40);
+}
+
+__device__ inline float synth_value(uint64_t seed, uint32_t stream, uint32_t c, uint64_t t, float mu,
+                                    float sigma) {
+  int32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += (int32_t)synth_u24(seed, stream, c, t + k);
+  float g = __fmul_rn((float)(s - 67108860), __int_as_float(0x339cc471));  // * sqrt(1.5)/2^24
+  return __fadd_rn(mu, __fmul_rn(sigma, g));
+}
+
+__device__ inline float normalize_value(float f, float mn, float mx) {
+  return __fdiv_rn(__fsub_rn(f, mn), __fsub_rn(mx, mn));  // MathUtil.scala:140-147
+}
+
+__global__ void k_db_synth(float *__restrict__ data, int64_t chanStride, int64_t dstFrame, int64_t nFrames,
+                           int numCh, uint64_t seed, uint32_t stream, const float *__restrict__ mu,
+                           const float *__restrict__ sigma, float floor0, const float *__restrict__ norm) {
+  int c = blockIdx.y;
+  float m = mu[c], s = sigma[c], mn = norm[2 * c], mx = norm[2 * c + 1];
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nFrames;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    float x = synth_value(seed, stream, (uint32_t)c, (uint64_t)t, m, s);
+    if (c == 0) x = fmaxf(x, floor0);
+    data[(int64_t)c * chanStride + dstFrame + t] = normalize_value(x, mn, mx);
+  }
+}
+
+__device__ inline float load_be(const float *p) {
+  uint32_t v = *reinterpret_cast<const uint32_t *>(p);
+  return __int_as_float((int)__byte_perm(v, 0, 0x0123));
+}
+
+// K0: interleaved (LE or BE) / planar staging -> normalised planar store.  One block converts
+// kFr frames; the interleaved source is read with fully coalesced 4-byte loads into shared memory
+// and written back as numCh coalesced rows.
+constexpr int kPrepFrames = 256;
+__global__ void k_db_prepare(const float *__restrict__ src, int layout, int64_t srcFrames,
+                             float *__restrict__ data, int64_t chanStride, int64_t dstFrame, int numCh,
+                             const float *__restrict__ norm) {
+  extern __shared__ float sh[];  // [kPrepFrames * numCh]
+  int64_t f0 = (int64_t)blockIdx.x * kPrepFrames;
+  int nf = (int)min((int64_t)kPrepFrames, srcFrames - f0);
+  if (nf <= 0) return;
+  if (layout == SGZ_LAYOUT_PLANAR_LE) {
+    for (int i = threadIdx.x; i < nf * numCh; i += blockDim.x) {
+      int c = i / nf, t = i - c * nf;
+      float v = src[(int64_t)c * srcFrames + f0 + t];
+      data[(int64_t)c * chanStride + dstFrame + f0 + t] = normalize_value(v, norm[2 * c], norm[2 * c + 1]);
+    }
+    return;
+  }
+  const float *s = src + f0 * numCh;
+  for (int i = threadIdx.x; i < nf * numCh; i += blockDim.x)
+    sh[i] = layout == SGZ_LAYOUT_INTERLEAVED_BE ? load_be(s + i) : s[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < nf * numCh; i += blockDim.x) {
+    int c = i / nf, t = i - c * nf;
+    float v = sh[t * numCh + c];
+    data[(int64_t)c * chanStride + dstFrame + f0 + t] = normalize_value(v, norm[2 * c], norm[2 * c + 1]);
+  }
+}
+
+__global__ void k_db_gather(const float *__restrict__ data, int64_t chanStride, int64_t srcFrame, int64_t n,
+                            int numCh, float *__restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * numCh) return;
+  int c = (int)(i / n);
+  int64_t t = i - (int64_t)c * n;
+  out[i] = data[(int64_t)c * chanStride + srcFrame + t];
+}
+
+inline int db_grow(sgz_db *db, int64_t needFrames) {
+  if (needFrames + kDbSlack <= db->capFrames) return SGZ_OK;
+  int64_t newCap = std::max<int64_t>(needFrames + kDbSlack, db->capFrames * 2);
+  newCap = (newCap + 1023) / 1024 * 1024;
+  DevBuf<float> nd;
+  SGZ_TRY(nd.alloc((size_t)newCap * db->numCh));
+  cudaStream_t st = db->ctx->stream;
+  SGZ_CUDA(cudaMemsetAsync(nd.p, 0, (size_t)newCap * db->numCh * sizeof(float), st));
+  if (db->usedFrames > 0) {
+    SGZ_CUDA(cudaMemcpy2DAsync(nd.p, (size_t)newCap * sizeof(float), db->dData.p,
+                               (size_t)db->capFrames * sizeof(float), (size_t)db->usedFrames * sizeof(float),
+                               (size_t)db->numCh, cudaMemcpyDeviceToDevice, st));
+  }
+  SGZ_CUDA(cudaStreamSynchronize(st));
+  std::swap(db->dData.p, nd.p);
+  std::swap(db->dData.n, nd.n);
+  db->capFrames = newCap;
+  return SGZ_OK;
+}
+
+inline int db_launch_prepare(sgz_db *db, const float *dSrc, int layout, int64_t nFrames, int64_t dstFrame) {
+  if (nFrames <= 0) return SGZ_OK;
+  int blocks = (int)ceil_div<int64_t>(nFrames, kPrepFrames);
+  size_t sm = (size_t)kPrepFrames * db->numCh * sizeof(float);
+  k_db_prepare<<<blocks, 256, sm, db->ctx->stream>>>(dSrc, layout, nFrames, db->dData.p, db->capFrames,
+                                                     dstFrame, db->numCh, db->dNorm.p);
+  SGZ_LAUNCH_CHECK(db->ctx);
+  return SGZ_OK;
+}
+
+}  // namespace sgz

@@ -1,0 +1,190 @@
+// segm.cuh -- K3: FeatureSegmentation (FeatureSegmentationImpl.scala:31-142).
+//
+// north_star asks for BIT-IDENTICAL break frames.  B200 has a full-rate FP64 pipe
+// (64 DFMA lanes / SM / clk), and the whole job is 51 595 offsets x 3 passes x 86 x 14 cells
+// = 1.9e8 FP64 operations, i.e. microseconds of pipe time -- so instead of a fast FP32 curve plus a
+// tie analysis, the curve kernel replays the reference's Double arithmetic operation by operation
+// (MathUtil.stat two-pass in PHYSICAL ring-buffer order, MathUtil.correlateHalf in logical order,
+// no FMA contraction: __dadd_rn/__dmul_rn), which makes every sim bit-identical to the JVM's and
+// the break picking a pure replay of addBreak (:68-83).
+#pragma once
+#include "common.cuh"
+
+namespace sgz {
+
+struct SegmParams {
+  const float *x;       // normalised planar [numCh][stride] frames of the analysed span (index 0 = afStart)
+  int64_t stride;
+  int afLen;            // frames available in the span
+  int numCh;
+  int H;                // halfWinLen
+  int nOff;             // number of offsets
+  float weight;
+  float *curve;         // [nOff]
+};
+
+__device__ __forceinline__ float segm_load(const SegmParams &p, int c, int e) {
+  // frames the reference never read stay 0.0f in its freshly allocated ring buffer (afLen < 2H case)
+  return e < p.afLen ? p.x[(int64_t)c * p.stride + e] : 0.0f;
+}
+
+// MathUtil.correlateHalf(numChannels, H, ring, frameOff = t % 2H, chanOff) for window start t
+__device__ float segm_correlate_half(const SegmParams &p, int t, int chanOff, int numChannels) {
+  const int H = p.H, win = 2 * H;
+  const int phase = t % win;
+  const int matFull = win * numChannels;
+  // stat pass 1: sum over PHYSICAL ring index phi = 0..2H-1; logical frame = t + ((phi - t) mod 2H)
+  double sum = 0.0;
+  for (int ch = 0; ch < numChannels; ch++) {
+    const int c = ch + chanOff;
+    for (int phi = 0; phi < win; phi++) {
+      int k = phi - phase; if (k < 0) k += win;
+      sum = __dadd_rn(sum, (double)segm_load(p, c, t + k));
+    }
+  }
+  const double mean = __ddiv_rn(sum, (double)matFull);
+  sum = 0.0;
+  for (int ch = 0; ch < numChannels; ch++) {
+    const int c = ch + chanOff;
+    for (int phi = 0; phi < win; phi++) {
+      int k = phi - phase; if (k < 0) k += win;
+      double d = __dsub_rn((double)segm_load(p, c, t + k), mean);
+      sum = __dadd_rn(sum, __dmul_rn(d, d));
+    }
+  }
+  const double stdDev = __dsqrt_rn(__ddiv_rn(sum, (double)matFull));
+  const double add = -mean;
+  const int matSize = numChannels * H;
+  sum = 0.0;
+  for (int ch = 0; ch < numChannels; ch++) {
+    const int c = ch + chanOff;
+    for (int i = 0; i < H; i++) {
+      double a = __dadd_rn((double)segm_load(p, c, t + i), add);
+      double b = __dadd_rn((double)segm_load(p, c, t + H + i), add);
+      sum = __dadd_rn(sum, __dmul_rn(a, b));
+    }
+  }
+  return (float)__ddiv_rn(sum, __dmul_rn(__dmul_rn(stdDev, stdDev), (double)matSize));
+}
+
+__global__ void k_segm_curve(const SegmParams p) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.nOff) return;
+  const float temporal = p.weight > 0.f ? segm_correlate_half(p, t, 0, 1) : 0.f;
+  const float spectral = p.weight < 1.f ? segm_correlate_half(p, t, 1, p.numCh - 1) : 0.f;
+  p.curve[t] = __fadd_rn(__fmul_rn(temporal, p.weight), __fmul_rn(spectral, __fsub_rn(1.0f, p.weight)));
+}
+
+// SortedSet[Break](BreakMaxOrd) + addBreak
+struct BreakMachine {
+  sgz_break *e;     // ascending Float.compare order on sim, unique sims
+  int n, numBreaks;
+  int hasLast;
+  sgz_break last;
+  int64_t minSpacing;
+
+  __host__ __device__ void reset(sgz_break *store, int nb, int64_t ms) {
+    e = store; n = 0; numBreaks = nb; hasLast = 0; minSpacing = ms;
+    last = sgz_break{0.f, 0, 0};
+  }
+  __host__ __device__ bool has_space() const { return n < numBreaks; }                  // :58
+  __host__ __device__ float highest() const { return n > 0 ? e[n - 1].sim : 0.f; }     // :60-62
+  __host__ __device__ int find(float sim, bool &found) const {
+    found = false;
+    int i = 0;
+    for (; i < n; i++) {
+      int c = jfloat_compare(sim, e[i].sim);
+      if (c == 0) { found = true; return i; }
+      if (c < 0) return i;
+    }
+    return i;
+  }
+  __host__ __device__ void set_add(const sgz_break &b) {
+    bool found;
+    int i = find(b.sim, found);
+    if (found) return;
+    for (int k = n; k > i; k--) e[k] = e[k - 1];
+    e[i] = b;
+    n++;
+  }
+  __host__ __device__ void set_remove(float sim) {
+    bool found;
+    int i = find(sim, found);
+    if (!found) return;
+    for (int k = i; k + 1 < n; k++) e[k] = e[k + 1];
+    n--;
+  }
+  __host__ __device__ void add(const sgz_break &b) {                                    // :68-83
+    if (hasLast && (b.pos - last.pos) < minSpacing) {
+      if (last.sim > b.sim) {
+        set_remove(last.sim);
+        set_add(b);
+        last = b;
+      }
+    } else {
+      set_add(b);
+      if (n > numBreaks) n--;
+      last = b;
+      hasLast = 1;
+    }
+  }
+};
+
+struct PickParams {
+  const float *curve;
+  int nOff;
+  int afStart, H, step;
+  int numBreaks;
+  int64_t minSpacing;
+  sgz_break *out;   // [numBreaks + 1]
+  int *count;
+};
+
+// one warp walks the curve; lanes test 32 offsets per step and jump to the first state change
+__global__ void k_segm_pick(const PickParams p) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  BreakMachine mc;
+  mc.reset(p.out, p.numBreaks, p.minSpacing);
+  bool hs = mc.has_space();
+  float high = mc.highest();
+  int hasLast = 0;
+  float lastSim = 0.f;
+  int64_t lastPos = 0;
+  int pos = 0;
+  while (pos < p.nOff) {
+    const int t = pos + lane;
+    const bool active = t < p.nOff;
+    const float s = active ? p.curve[t] : 0.f;
+    bool change = false;
+    if (active) {
+      const bool accept = hs || s < high;
+      const int64_t bpos = (int64_t)(p.afStart + t + p.H) * p.step;
+      const bool collapse = hasLast && (bpos - lastPos) < p.minSpacing;
+      change = accept && (collapse ? (lastSim > s) : true);
+    }
+    const unsigned mask = __ballot_sync(full, change);
+    if (mask == 0u) { pos += 32; continue; }
+    const int l = __ffs(mask) - 1;
+    const int ts = pos + l;
+    const float ss = __shfl_sync(full, s, l);
+    if (lane == 0) {
+      sgz_break b{ss, 0, (int64_t)(p.afStart + ts + p.H) * p.step};
+      mc.add(b);
+      hs = mc.has_space();
+      high = mc.highest();
+      hasLast = mc.hasLast;
+      lastSim = mc.last.sim;
+      lastPos = mc.last.pos;
+    }
+    hs = __shfl_sync(full, (int)hs, 0) != 0;
+    high = __shfl_sync(full, high, 0);
+    hasLast = __shfl_sync(full, hasLast, 0);
+    lastSim = __shfl_sync(full, lastSim, 0);
+    lastPos = __shfl_sync(full, lastPos, 0);
+    pos = ts + 1;
+  }
+  if (lane == 0) *p.count = mc.n;
+}
+
+}  // namespace sgz

@@ -1,0 +1,204 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (north_star): correlation scores within 1e-5 relative; identical match file/offset positions;
+bit-identical segmentation breaks; (this round) pixel-identical self-similarity images.
+"""
+import numpy as np
+import pytest
+
+from util import (N, O, STEP, assert_matches_equal, assert_sims_close, build_db, corr_cfgs, make_db, make_input,
+                  plant_needles, synth)
+
+pytestmark = pytest.mark.gpu
+
+
+def test_library_reports_b200(ctx):
+    from strugatzki_b200 import engine
+    assert engine.device_count() >= 1
+    assert N.lib().sgz_abi_version() == 1
+
+
+def test_synth_device_equals_numpy(ctx):
+    """device generator == numpy generator, bit for bit, after the reference's normalisation."""
+    from strugatzki_b200 import engine
+    mu, sigma, floor0, norm = synth.default_profile(14)
+    db = engine.Database(ctx, 14, norm)
+    for stream, n in ((3, 1000), (4, 777)):
+        db.add_synth(synth.BASE_SEED, stream, n, mu, sigma, float(floor0))
+    db.finalize()
+    for idx, (stream, n) in enumerate(((3, 1000), (4, 777))):
+        raw = synth.synth_file(synth.BASE_SEED, stream, n, mu, sigma, floor0)
+        want = ((raw - norm[:, 0]) / (norm[:, 1] - norm[:, 0])).astype(np.float32).T
+        got = db.read(idx, 0, n)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_db_layouts_and_patch(ctx):
+    from strugatzki_b200 import engine
+    files, norm = make_db(1, 600)
+    f = files[0]
+    db = engine.Database(ctx, 14, norm)
+    db.add_file(f, N.LAYOUT_INTERLEAVED_LE)
+    db.add_file(f.astype(">f4"), N.LAYOUT_INTERLEAVED_BE)
+    db.add_file(np.ascontiguousarray(f.T), N.LAYOUT_PLANAR_LE)
+    db.add_file(np.zeros((0, 14), np.float32))          # empty file is legal
+    patch = make_input(50)
+    db.patch(0, 100, patch)
+    db.finalize()
+    assert db.info() == (4, 1800, 14)
+    want = ((f - norm[:, 0]) / (norm[:, 1] - norm[:, 0])).astype(np.float32).T
+    a, b, c = db.read(0, 0, 600), db.read(1, 0, 600), db.read(2, 0, 600)
+    assert np.array_equal(b, want) and np.array_equal(c, want)
+    assert np.array_equal(a[:, :100], want[:, :100]) and np.array_equal(a[:, 150:], want[:, 150:])
+    wp = ((patch - norm[:, 0]) / (norm[:, 1] - norm[:, 0])).astype(np.float32).T
+    assert np.array_equal(a[:, 100:150], wp)
+    # normalize = false keeps the raw values
+    db2 = engine.Database(ctx, 14, None)
+    db2.add_file(f)
+    db2.finalize()
+    assert np.array_equal(db2.read(0, 0, 600), f.T)
+
+
+@pytest.mark.parametrize("w_in,weight,num_ch", [(88200, 0.5, 14), (88200, 0.0, 14), (88200, 1.0, 14),
+                                                  (22050, 0.3, 14), (50000, 0.5, 5), (100000, 0.7, 21)])
+def test_corr_curve_matches_oracle(ctx, w_in, weight, num_ch):
+    """every punch-in offset: sim within 1e-5 relative, boost within 1e-6 relative"""
+    from strugatzki_b200 import engine
+    files, norm = make_db(3, [2600, 400, 3100], num_ch)
+    inp = make_input(900, num_ch)
+    W = (w_in + STEP // 2) // STEP
+    plant_needles(files, inp[:W], [(0, 1000), (2, 37)])
+    op, nc = corr_cfgs(inp, norm, punch_in=(0, w_in), w_in=weight, num_matches=3)
+    db = build_db(ctx, files, norm)
+    job = engine.CorrelationJob(db, nc, inp)
+    job.scan()
+    total = 0
+    for i, f in enumerate(files):
+        want_sim, want_boost = O.corr_curve(op, f, 0, 0)
+        n = len(want_sim)
+        assert n == max(0, f.shape[0] - W + 1)
+        total += n
+        if n == 0:
+            continue
+        sim, boost = job.curve(i, 0, 0, n)
+        assert_sims_close(sim, want_sim, rel=1e-5, abs_tol=2e-6, what=f"file {i} sim")
+        assert_sims_close(boost, want_boost, rel=2e-6, abs_tol=0, what=f"file {i} boost")
+    assert job.num_offsets == total == O.corr_num_offsets(op, [f.shape[0] for f in files])
+
+
+@pytest.mark.parametrize("num_matches,num_per_file,min_spacing", [
+    (1, 1, 0), (5, 1, 0), (5, 2, 0), (8, 3, 22050), (20, 4, 44100), (40, 1, 0), (7, 100, 0), (3, 2, -10 ** 9),
+])
+def test_corr_search_matches_oracle(ctx, num_matches, num_per_file, min_spacing):
+    """FeatureCorrelation punch-in search: identical files / spans, sims within 1e-5"""
+    from strugatzki_b200 import engine
+    files, norm = make_db(12, [3000, 2500, 4100, 180, 2900, 3300, 2000, 5000, 172, 2600, 3100, 2800])
+    inp = make_input(900)
+    W = 172
+    plant_needles(files, inp[:W], [(2, 1500), (7, 10), (7, 3000), (9, 2400), (11, 100)])
+    op, nc = corr_cfgs(inp, norm, num_matches=num_matches, num_per_file=num_per_file, min_spacing=min_spacing)
+    db = build_db(ctx, files, norm)
+    job = engine.CorrelationJob(db, nc, inp)
+    got = job.run()
+    want = O.corr_search(op, files)
+    assert_matches_equal(got, want)
+
+
+def test_corr_search_boost_gate_and_no_norm(ctx):
+    from strugatzki_b200 import engine
+    files, _ = make_db(5, 2500)
+    inp = make_input(900)
+    files[1][:, 0] *= np.float32(0.05)        # very quiet file -> boost > maxBoost -> sim forced to 0f
+    plant_needles(files, inp[:172], [(3, 700)])
+    op, nc = corr_cfgs(inp, None, num_matches=4, num_per_file=1, max_boost=2.0)
+    db = build_db(ctx, files, None)
+    job = engine.CorrelationJob(db, nc, inp)
+    got = job.run()
+    want = O.corr_search(op, files)
+    assert_matches_equal(got, want)
+    sim, boost = job.curve(1, 0, 0, 100)
+    assert np.all(sim == 0.0) and np.all(boost > 2.0)
+
+
+def test_corr_async_poll_and_abort(ctx):
+    from strugatzki_b200 import engine, Aborted
+    files, norm = make_db(4, 4000)
+    inp = make_input(900)
+    op, nc = corr_cfgs(inp, norm, num_matches=3)
+    db = build_db(ctx, files, norm)
+    job = engine.CorrelationJob(db, nc, inp)
+    job.start()
+    job.wait()
+    p, done, status = job.poll()
+    assert done and status == 0 and p == 1.0
+    assert_matches_equal(job.result(), O.corr_search(op, files))
+    job.abort()
+    with pytest.raises(Aborted):
+        job.scan()
+
+
+def test_corr_errors(ctx):
+    from strugatzki_b200 import engine, NativeError
+    files, norm = make_db(1, 1000)
+    inp = make_input(100)
+    db = engine.Database(ctx, 14, norm)
+    db.add_file(files[0])
+    _, nc = corr_cfgs(inp, norm)
+    with pytest.raises(NativeError):          # not finalized
+        engine.CorrelationJob(db, nc, inp)
+    db.finalize()
+    with pytest.raises(NativeError) as ei:    # punch span beyond the input file (reference: EOFException)
+        engine.CorrelationJob(db, nc, inp)
+    assert ei.value.code == N.ERR_IO
+    with pytest.raises(NativeError):
+        db.add_file(files[0])
+
+
+@pytest.mark.parametrize("corr_len,weight,num_breaks,min_spacing,span", [
+    (22050, 0.5, 20, 22050, (None, None)), (11025, 0.0, 5, 0, (None, None)), (44100, 1.0, 8, 88200, (None, None)),
+    (22050, 0.25, 6, 22050, (300 * 512, 2500 * 512)), (22050, 0.5, 3, 22050, (None, 40 * 512)),
+])
+def test_segmentation_bit_identical(ctx, corr_len, weight, num_breaks, min_spacing, span):
+    from strugatzki_b200 import engine
+    f, cuts = synth.regime_file(synth.BASE_SEED, 5, 4000, 14, 12)
+    _, _, _, norm = synth.default_profile(14)
+    op = O.SegmParams(step_size=STEP, corr_len=corr_len, temporal_weight=weight, norm=norm, num_breaks=num_breaks,
+                      min_spacing=min_spacing, span_start=span[0], span_stop=span[1])
+    want, want_curve = O.segm_run(op, f, want_curve=True)
+    cfg = N.SegmConfig(STEP, int(span[0] is not None), int(span[1] is not None), span[0] or 0, span[1] or 0,
+                       corr_len, weight, num_breaks, min_spacing)
+    got, curve, noff = engine.segm_run(ctx, cfg, f, norm, want_curve=True)
+    assert np.array_equal(curve.view(np.uint32), want_curve[:noff].view(np.uint32)), "curve is not bit-identical"
+    assert [(b["pos"], np.float32(b["sim"]).tobytes()) for b in got] == \
+           [(b["pos"], np.float32(b["sim"]).tobytes()) for b in want]
+
+
+@pytest.mark.parametrize("decim,weight,warp,ceil,inv,cross", [
+    (1, 0.5, 1.0, 1.0, False, False), (3, 0.2, 0.5, 0.8, True, False), (2, 1.0, 2.0, 1.0, False, True),
+])
+def test_selfsimilarity_image_identical(ctx, decim, weight, warp, ceil, inv, cross):
+    from strugatzki_b200 import engine
+    f1, _ = synth.regime_file(synth.BASE_SEED, 6, 420, 14, 5)
+    f2 = synth.regime_file(synth.BASE_SEED, 7, 400, 14, 4)[0] if cross else None
+    _, _, _, norm = synth.default_profile(14)
+    op = O.SelfParams(step_size=STEP, corr_len=20480, decimation=decim, temporal_weight=weight, norm=norm,
+                      color_inv=inv, color_warp=warp, color_ceil=ceil)
+    want = O.self_image(op, f1, f2)
+    cfg = N.SelfConfig(STEP, 0, 0, 0, 0, 20480, decim, weight, int(inv), warp, ceil, None, 0)
+    got, g = engine.self_run(ctx, cfg, f1, f2, norm)
+    assert got.shape == want.shape and g["imgExt"] == want.shape[0]
+    assert np.array_equal(got, want)
+    # cell-list entry point
+    rng = np.random.default_rng(1)
+    l = rng.integers(0, g["imgExt"], 64)
+    r = rng.integers(0, g["imgExt"], 64)
+    sim, rgb = engine.self_cells(ctx, cfg, f1, f2, l, r, norm)
+    wsim, wrgb = O.self_cells(op, f1, f2, l, r)
+    assert np.array_equal(sim.view(np.uint32), wsim.view(np.uint32)) and np.array_equal(rgb, wrgb)
+
+
+def test_measured_peaks_are_plausible(ctx):
+    ffma = ctx.measure_peak(0)
+    hbm = ctx.measure_peak(3)
+    assert 30.0 < ffma < 100.0, ffma       # B200: 148 SMs x 128 lanes x 2 flop x ~1.9 GHz ~ 72 TFLOP/s
+    assert 3000.0 < hbm < 9000.0, hbm
