@@ -124,13 +124,7 @@ inline int prepare_query(const sgz_db *db, const float *inputPlanar /*[numCh][in
 
 template <int NTG>
 inline int launch_corr_ntg(sgz_ctx *ctx, const CorrParams &p, size_t smemBytes, int64_t tileBegin, int64_t tileEnd) {
-  static thread_local int configuredDevice = -1;
-  static thread_local size_t configuredSmem = 0;
-  if (configuredDevice != ctx->device || configuredSmem < smemBytes) {
-    SGZ_CUDA(cudaFuncSetAttribute(k_corr<NTG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemOptin));
-    configuredDevice = ctx->device;
-    configuredSmem = ctx->smemOptin;
-  }
+  SGZ_CUDA(cudaFuncSetAttribute(k_corr<NTG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemOptin));
   (void)tileBegin;
   k_corr<NTG><<<(unsigned)(tileEnd - tileBegin), 2 * NTG, smemBytes, ctx->stream>>>(p);
   SGZ_LAUNCH_CHECK(ctx);
@@ -138,7 +132,11 @@ inline int launch_corr_ntg(sgz_ctx *ctx, const CorrParams &p, size_t smemBytes, 
 }
 
 inline int pick_ntg(const sgz_ctx *ctx, int numCh, int Wq) {
-  const int opts[3] = {128, 64, 32};
+  // prefer two resident CTAs per SM (one CTA's load / prefix / epilogue phases overlap the other's FFMA loop)
+  const int opts[3] = {96, 64, 32};
+  const size_t perSm = 228 * 1024, reserved = 1024;
+  for (int k = 0; k < 3; k++)
+    if (2 * (corr_smem_layout(opts[k], numCh, Wq).total + reserved) <= perSm) return opts[k];
   for (int k = 0; k < 3; k++)
     if (corr_smem_layout(opts[k], numCh, Wq).total <= ctx->smemOptin) return opts[k];
   return 0;
@@ -178,7 +176,7 @@ inline int run_scan_one(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim,
   CorrSmemLayout L = corr_smem_layout(job->ntg, db->numCh, q.Wq);
   int rc;
   switch (job->ntg) {
-    case 128: rc = launch_corr_ntg<128>(job->ctx, p, L.total, 0, job->numTiles); break;
+    case 96: rc = launch_corr_ntg<96>(job->ctx, p, L.total, 0, job->numTiles); break;
     case 64: rc = launch_corr_ntg<64>(job->ctx, p, L.total, 0, job->numTiles); break;
     default: rc = launch_corr_ntg<32>(job->ctx, p, L.total, 0, job->numTiles); break;
   }

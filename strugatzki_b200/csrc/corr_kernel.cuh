@@ -73,15 +73,64 @@ inline CorrSmemLayout corr_smem_layout(int ntg, int numCh, int Wq) {
   L.offF = (L.offTaps + taps + 15) / 16 * 16;
   L.offCP = (L.offF + F + 31) / 32 * 32;
   L.offFile = L.offCP + CP;
-  L.total = L.offFile + 16;
+  L.total = L.offFile + 32;
   return L;
 }
 
 __device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 
-// 12 offsets x Wq taps of one channel; brow = &tile[c][o], arow = &taps[c][0]
+// ---- TMA (bulk async copy) + mbarrier primitives; SASS: UBLKCP / SYNCS ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_LOOP_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// One sub-step = 4 taps x 12 offsets = 48 FFMA fed by one LDS.128 of DB values and one broadcast
+// LDS.128 of taps, both prefetched one sub-step ahead (software pipelining: with 2-3 warps per
+// scheduler the 30-cycle LDS latency must not sit between the load and its first FFMA).
+#define SGZ_SUBSTEP(S, NEXT)                                                   \
+  {                                                                            \
+    bw[(12 + 4 * (S)) & 15] = nb.x;                                            \
+    bw[(13 + 4 * (S)) & 15] = nb.y;                                            \
+    bw[(14 + 4 * (S)) & 15] = nb.z;                                            \
+    bw[(15 + 4 * (S)) & 15] = nb.w;                                            \
+    const float av0 = a.x, av1 = a.y, av2 = a.z, av3 = a.w;                    \
+    nb = lds4(brow + 4 * (NEXT) + 12);                                         \
+    a = lds4(arow + 4 * (NEXT));                                               \
+    _Pragma("unroll") for (int r = 0; r < kR; r++) acc[r] = fmaf(av0, bw[(4 * (S) + 0 + r) & 15], acc[r]); \
+    _Pragma("unroll") for (int r = 0; r < kR; r++) acc[r] = fmaf(av1, bw[(4 * (S) + 1 + r) & 15], acc[r]); \
+    _Pragma("unroll") for (int r = 0; r < kR; r++) acc[r] = fmaf(av2, bw[(4 * (S) + 2 + r) & 15], acc[r]); \
+    _Pragma("unroll") for (int r = 0; r < kR; r++) acc[r] = fmaf(av3, bw[(4 * (S) + 3 + r) & 15], acc[r]); \
+  }
+
+// 12 offsets x Wq taps of one channel; brow = &tile[c][o], arow = &taps[c][0]; nSub = Wq / 4.
+// The prefetch of the sub-step after the last one reads <= 16 B past the row (inside the smem
+// allocation, value unused).
 __device__ __forceinline__ void conv_channel(float (&acc)[kR], const float *__restrict__ brow,
-                                             const float *__restrict__ arow, int Wq) {
+                                             const float *__restrict__ arow, int nSub) {
   float bw[16];
   {
     float4 v0 = lds4(brow), v1 = lds4(brow + 4), v2 = lds4(brow + 8);
@@ -89,24 +138,20 @@ __device__ __forceinline__ void conv_channel(float (&acc)[kR], const float *__re
     bw[4] = v1.x; bw[5] = v1.y; bw[6] = v1.z; bw[7] = v1.w;
     bw[8] = v2.x; bw[9] = v2.y; bw[10] = v2.z; bw[11] = v2.w;
   }
+  float4 nb = lds4(brow + 12), a = lds4(arow);
+  int sub = 0;
 #pragma unroll 1
-  for (int i0 = 0; i0 < Wq; i0 += 16) {
-#pragma unroll
-    for (int s = 0; s < 4; s++) {
-      if (i0 + 4 * s < Wq) {
-        float4 nb = lds4(brow + i0 + 4 * s + 12);
-        bw[(12 + 4 * s) & 15] = nb.x;
-        bw[(13 + 4 * s) & 15] = nb.y;
-        bw[(14 + 4 * s) & 15] = nb.z;
-        bw[(15 + 4 * s) & 15] = nb.w;
-        float4 a = lds4(arow + i0 + 4 * s);
-        float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-#pragma unroll
-          for (int r = 0; r < kR; r++) acc[r] = fmaf(av[u], bw[(4 * s + u + r) & 15], acc[r]);
-        }
-      }
+  for (; sub + 4 <= nSub; sub += 4) {
+    SGZ_SUBSTEP(0, sub + 1)
+    SGZ_SUBSTEP(1, sub + 2)
+    SGZ_SUBSTEP(2, sub + 3)
+    SGZ_SUBSTEP(3, sub + 4)
+  }
+  if (sub < nSub) {
+    SGZ_SUBSTEP(0, sub + 1)
+    if (sub + 1 < nSub) {
+      SGZ_SUBSTEP(1, sub + 2)
+      if (sub + 2 < nSub) { SGZ_SUBSTEP(2, sub + 3) }
     }
   }
 }
@@ -114,14 +159,12 @@ __device__ __forceinline__ void conv_channel(float (&acc)[kR], const float *__re
 struct D4 {
   double t1, t2, s1, s2;
 };
-__device__ __forceinline__ D4 d4_add(D4 a, D4 b) { return {a.t1 + b.t1, a.t2 + b.t2, a.s1 + b.s1, a.s2 + b.s2}; }
-__device__ __forceinline__ D4 d4_sub(D4 a, D4 b) { return {a.t1 - b.t1, a.t2 - b.t2, a.s1 - b.s1, a.s2 - b.s2}; }
 
 template <int NTG>
-__global__ void __launch_bounds__(2 * NTG, 1) k_corr(const CorrParams p) {
+__global__ void __launch_bounds__(2 * NTG, 2) k_corr(const CorrParams p) {
   constexpr int T = kR * NTG;
   constexpr int NT = 2 * NTG;
-  extern __shared__ __align__(32) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   const int Wq = p.Wq;
   const int tileFrames = T + Wq;
   const int pitch = tileFrames;
@@ -135,43 +178,36 @@ __global__ void __launch_bounds__(2 * NTG, 1) k_corr(const CorrParams p) {
   size_t offFile = offCP + (size_t)(numChunks + 1) * 4 * sizeof(double);
   float *taps = reinterpret_cast<float *>(smem + offTaps);
   float2 *F = reinterpret_cast<float2 *>(smem + offF);
-  double *CP = reinterpret_cast<double *>(smem + offCP);  // [numChunks+1][4]
-  int *shFile = reinterpret_cast<int *>(smem + offFile);  // [0]=file of t0, [1]=file of last frame
+  double *CP = reinterpret_cast<double *>(smem + offCP);      // [numChunks+1][4]
+  int *shFile = reinterpret_cast<int *>(smem + offFile);      // [0]=file of t0, [1]=file of last frame
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + offFile + 8);
 
   const int tid = threadIdx.x;
   const int64_t t0 = (int64_t)blockIdx.x * T;
 
-  // ---- file range of this tile (two threads, overlaps with the tile load) ----
-  if (tid < 2) {
-    int64_t g = tid == 0 ? t0 : min(t0 + T - 1, p.usedFrames - 1);
-    int lo = 0, hi = p.numFiles;  // find f with fileStart[f] <= g < fileStart[f+1] (skipping empty files)
+  // ---- stage taps + tile with TMA bulk copies: one elected thread, 1 + numCh copies, one mbarrier ----
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    const uint32_t rowBytes = (uint32_t)tileFrames * sizeof(float);
+    const uint32_t tapBytes = (uint32_t)(p.numCh * Wq) * sizeof(float);
+    mbar_expect_tx(bar, rowBytes * p.numCh + tapBytes);
+    bulk_g2s(taps, p.taps, tapBytes, bar);
+    for (int c = 0; c < p.numCh; c++) bulk_g2s(tile + c * pitch, p.data + (int64_t)c * p.chanStride + t0, rowBytes, bar);
+  }
+  // ---- file range of this tile (two threads, overlaps with the copies) ----
+  if (tid >= 32 && tid < 34) {
+    int64_t g = tid == 32 ? t0 : min(t0 + T - 1, p.usedFrames - 1);
+    int lo = 0, hi = p.numFiles;  // f with fileStart[f] <= g < fileStart[f+1]
     while (hi - lo > 1) {
       int mid = (lo + hi) >> 1;
       if (p.fileStart[mid] <= g) lo = mid; else hi = mid;
     }
-    shFile[tid] = lo;
+    shFile[tid - 32] = lo;
   }
-
-  // ---- stage taps and the tile (coalesced 16 B loads, read-once data -> no L1 allocation) ----
-  for (int i = tid; i < p.numCh * Wq; i += NT) taps[i] = p.taps[i];
-  {
-    const int tf4 = tileFrames >> 2;
-    for (int c = 0; c < p.numCh; c++) {
-      const float *src = p.data + (int64_t)c * p.chanStride + t0;
-      float *dst = tile + c * pitch;
-      for (int v = tid; v < tf4; v += NT) {
-        int64_t g = t0 + 4 * (int64_t)v;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g + 3 < p.chanStride) {
-          asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                       : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
-                       : "l"(src + 4 * v));
-        }
-        *reinterpret_cast<float4 *>(dst + 4 * v) = x;
-      }
-    }
-  }
-  __syncthreads();
+  if (tid < 4) CP[tid] = 0.0;
+  __syncthreads();          // barrier init visible to the waiters
+  mbar_wait(bar, 0);
 
   // ---- per-frame spectral sums (float) ----
   for (int e = tid; e < tileFrames; e += NT) {
@@ -199,7 +235,6 @@ __global__ void __launch_bounds__(2 * NTG, 1) k_corr(const CorrParams p) {
     double *o = CP + 4 * (size_t)(j + 1);
     o[0] = a1; o[1] = a2; o[2] = a3; o[3] = a4;
   }
-  if (tid < 4) CP[tid] = 0.0;
   __syncthreads();
   {
     // warp w scans component w: lane l owns entries [l*per, (l+1)*per) of CP[1..numChunks]
@@ -228,14 +263,15 @@ __global__ void __launch_bounds__(2 * NTG, 1) k_corr(const CorrParams p) {
   const int grp = tid / NTG;       // warp-uniform (NTG % 32 == 0)
   const int lt = tid - grp * NTG;
   const int o = lt * kR;
+  const int nSub = Wq >> 2;
   float accT[kR], accS[kR];
 #pragma unroll
   for (int r = 0; r < kR; r++) { accT[r] = 0.f; accS[r] = 0.f; }
   if (grp == 0) {
-    conv_channel(accT, tile + o, taps, Wq);
-    for (int c = 1; c < p.csplit; c++) conv_channel(accS, tile + c * pitch + o, taps + c * Wq, Wq);
+    conv_channel(accT, tile + o, taps, nSub);
+    for (int c = 1; c < p.csplit; c++) conv_channel(accS, tile + c * pitch + o, taps + c * Wq, nSub);
   } else {
-    for (int c = p.csplit; c < p.numCh; c++) conv_channel(accS, tile + c * pitch + o, taps + c * Wq, Wq);
+    for (int c = p.csplit; c < p.numCh; c++) conv_channel(accS, tile + c * pitch + o, taps + c * Wq, nSub);
   }
   __syncthreads();  // everybody is done with the taps; CP is complete
 
@@ -264,7 +300,7 @@ __global__ void __launch_bounds__(2 * NTG, 1) k_corr(const CorrParams p) {
     }
   }
 
-  // ---- window sums: start chunk aligned at o + 4*grp, slide to o + 6*grp ----
+  // ---- window sums (FP64): start chunk aligned at o + 4*grp, slide to o + 6*grp ----
   const int W = p.W;
   const int nq = W >> 2, rem = W & 3;
   int ws = o + 4 * grp;  // window start (tile-local frame), multiple of 4
@@ -276,7 +312,7 @@ __global__ void __launch_bounds__(2 * NTG, 1) k_corr(const CorrParams p) {
       int e = ws + 4 * nq + k;
       double b0 = (double)tile[e];
       float2 f = F[e];
-      win = d4_add(win, D4{b0, b0 * b0, (double)f.x, (double)f.y});
+      win.t1 += b0; win.t2 += b0 * b0; win.s1 += (double)f.x; win.s2 += (double)f.y;
     }
   }
   auto slide = [&](int start) {  // window [start, start+W) -> [start+1, start+1+W)
@@ -289,7 +325,7 @@ __global__ void __launch_bounds__(2 * NTG, 1) k_corr(const CorrParams p) {
   };
   if (grp == 1) { slide(ws); slide(ws + 1); ws += 2; }
 
-  // ---- epilogue ----
+  // ---- epilogue: FP64 only where cancellation demands it (variance), FP32 elsewhere ----
   const int fLo = shFile[0], fHi = shFile[1];
   const int64_t g0 = t0 + ws;
   int f = fLo;
@@ -302,8 +338,11 @@ __global__ void __launch_bounds__(2 * NTG, 1) k_corr(const CorrParams p) {
     f = lo;
   }
   int64_t fStart = p.fileStart[f], fEnd = p.fileStart[f + 1];
-  const double dW = (double)W, dNS = (double)(p.numCh - 1) * (double)W;
+  const double invW = 1.0 / (double)W, invNS = 1.0 / ((double)(p.numCh - 1) * (double)W);
+  const float cT = (float)(invW / p.stdT), cS = (float)(invNS / p.stdS);
+  const float rhoT = (float)p.rhoT, rhoS = (float)p.rhoS, lnIn = (float)p.lnAvgIn;
   const bool useT = p.weight > 0.f, useS = p.weight < 1.f;
+  const float qnan = __int_as_float(0x7fc00000);
   float simv[6], boostv[6];
   unsigned long long best = 0ull;
   int bestFile = -1;
@@ -320,28 +359,25 @@ __global__ void __launch_bounds__(2 * NTG, 1) k_corr(const CorrParams p) {
     }
     const int64_t tl = g - fStart;
     const int64_t nValid = (fEnd - fStart) - p.tailExtra - W + 1;
-    float sim = __int_as_float(0x7fc00000), boost = __int_as_float(0x7fc00000);
+    float sim = qnan, boost = qnan;
     if (g < p.usedFrames && tl < nValid) {
-      double mT = win.t1 / dW;
-      float avgB = (float)mT;                                   // MathUtil.avg
-      double lnB = log((double)avgB);
-      boost = (float)exp((p.lnAvgIn - lnB) / 0.6);              // calcBoost
+      const double mT = win.t1 * invW;
+      const float avgB = (float)mT;                              // MathUtil.avg -> Float
+      boost = expf((lnIn - logf(avgB)) / 0.6f);                  // calcBoost
       if (boost <= p.maxBoost) {
         float temporal = 0.f, spectral = 0.f;
         if (useT) {
-          double q = win.t2 / dW;
-          double var = q - mT * mT;
-          double sd = (var > 1e-13 * q) ? sqrt(var) : 0.0;
-          double cr = (double)crossT[k] - mT * p.rhoT;
-          temporal = sd > 0.0 ? (float)(cr / (p.stdT * sd * dW)) : __int_as_float(0x7fc00000);
+          const double q = win.t2 * invW;
+          const double var = q - mT * mT;
+          const float cr = crossT[k] - (float)mT * rhoT;
+          temporal = (var > 1e-13 * q) ? (cr * cT) / sqrtf((float)var) : qnan;
         }
         if (useS) {
-          double mS = win.s1 / dNS;
-          double q = win.s2 / dNS;
-          double var = q - mS * mS;
-          double sd = (var > 1e-13 * q) ? sqrt(var) : 0.0;
-          double cr = (double)crossS[k] - mS * p.rhoS;
-          spectral = sd > 0.0 ? (float)(cr / (p.stdS * sd * dNS)) : __int_as_float(0x7fc00000);
+          const double mS = win.s1 * invNS;
+          const double q = win.s2 * invNS;
+          const double var = q - mS * mS;
+          const float cr = crossS[k] - (float)mS * rhoS;
+          spectral = (var > 1e-13 * q) ? (cr * cS) / sqrtf((float)var) : qnan;
         }
         sim = __fadd_rn(__fmul_rn(temporal, p.weight), __fmul_rn(spectral, __fsub_rn(1.0f, p.weight)));
       } else {
@@ -368,10 +404,10 @@ __global__ void __launch_bounds__(2 * NTG, 1) k_corr(const CorrParams p) {
     }
   }
   if (p.fileMax) {
-    // warp-aggregate when the whole warp sits in one file
+    // warp-aggregate when every lane that found something sits in the same file
     const unsigned full = 0xffffffffu;
-    int f0 = __shfl_sync(full, bestFile, 0);
-    bool uniform = __all_sync(full, (bestFile == f0 || best == 0ull) && !straddle) && f0 >= 0;
+    const int f0 = __reduce_max_sync(full, bestFile);
+    const bool uniform = __all_sync(full, (bestFile == f0 || best == 0ull) && !straddle) && f0 >= 0;
     if (uniform) {
       unsigned long long m = best;
 #pragma unroll

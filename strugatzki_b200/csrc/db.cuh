@@ -33,7 +33,7 @@ struct sgz_db {
 
 namespace sgz {
 
-constexpr int64_t kDbSlack = 4096;  // readable zero frames behind the last file (tile halo)
+constexpr int64_t kDbSlack = 16384;  // readable zero frames behind the last file (tile halo)
 
 // ---- synthetic features.  Integer hash -> exact integer sum of 8
 // consecutive 24-bit values -> ONE float scale, so numpy (strugatzki_b200/synth.py) and this

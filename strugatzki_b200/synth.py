@@ -82,7 +82,8 @@ def regime_file(seed: int, stream: int, n_frames: int, num_ch: int = 14, n_regim
     mu, sigma, floor0, _ = default_profile(num_ch)
     base = synth_file(seed, stream, n_frames, np.zeros(num_ch, np.float32), sigma, -1e9)
     rng = np.random.default_rng(seed + 7919 * stream)
-    cuts = np.sort(rng.choice(np.arange(400, n_frames - 400), n_regimes - 1, replace=False))
+    margin = min(400, n_frames // 8)
+    cuts = np.sort(rng.choice(np.arange(margin, n_frames - margin), n_regimes - 1, replace=False))
     bounds = np.concatenate(([0], cuts, [n_frames]))
     out = np.empty_like(base)
     for k in range(len(bounds) - 1):
