@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- FeatureCorrelation DB frame-offsets/s on B200 (BASELINE.json config 5).
+
+  python bench.py --gpus 1 --steps K --warmup W            own arm (CUDA path through the C ABI)
+  torchrun ... bench.py --gpus N --steps K --warmup W      one rank per GPU, weak scaling
+  python bench.py --impl reference ...                     the reference's CPU algorithm (oracle port)
+
+A step is ONE complete search (K1 scan + K2 selection + ordered merge) of the 2 s punch-in window over
+the database resident in HBM: 6000 synthetic feature files x 51 680 frames (1000 h, 13 MFCC + loudness,
+fft 1024 / step 512 @ 44.1 kHz) PER GPU, numMatches 100, numPerFile 1, minSpacing 0.5 s.  `value` is
+evaluated frame-offsets of all ranks / max-over-ranks device time.  `e2e` is the same search through the
+same C-ABI calls starting from HOST buffers (pinned): DB upload + normalise/transpose + search + result
+download inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAMES_PER_FILE = 51680
+STEP = 512
+W_IN_SAMPLES = 88200
+FLOP_PER_OFFSET = 2 * 14 * 172 + 4 * 14 + 32   # 4904
+BYTES_PER_OFFSET = 56 + 8                      # 56 B DB frame read + (sim, boost) curve written
+
+
+def corr_config(N, num_matches=100, num_per_file=1, min_spacing=22050):
+    return N.CorrConfig(STEP, 0, W_IN_SAMPLES, 0.5, 0, 0, 0, 0.5, 44100, 352800, 8.0, num_matches, num_per_file,
+                        min_spacing)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def reference_arm(args):
+    """The reference's own CPU algorithm (oracle port: no JVM exists on the box), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    from strugatzki_b200 import synth
+    cores = host_threads()
+    mu, sigma, floor0, norm = synth.default_profile(14)
+    files_per_thread = 2
+    files = [synth.synth_file(synth.BASE_SEED, 1 + i, FRAMES_PER_FILE, mu, sigma, floor0)
+             for i in range(files_per_thread)]
+    inp = synth.synth_file(synth.BASE_SEED, 0, 900, mu, sigma, floor0)
+    p = O.CorrParams(step_size=STEP, input=inp, punch_in=(0, W_IN_SAMPLES), norm=norm, num_matches=100,
+                     num_per_file=1, min_spacing=22050)
+    offsets_per_thread = O.corr_num_offsets(p, [f.shape[0] for f in files])
+    O.lib()
+
+    def one(_):
+        return O.corr_search(O.CorrParams(**{k: getattr(p, k) for k in (
+            "step_size", "input", "punch_in", "punch_in_weight", "punch_out", "punch_out_weight", "min_punch",
+            "max_punch", "norm", "max_boost", "num_matches", "num_per_file", "min_spacing")}), files)
+
+    times = []
+    with ThreadPoolExecutor(cores) as ex:
+        for it in range(args.warmup + args.steps):
+            t = time.perf_counter()
+            list(ex.map(one, range(cores)))
+            dt = time.perf_counter() - t
+            if it >= args.warmup:
+                times.append(dt)
+    total = offsets_per_thread * cores
+    ms = 1e3 * float(np.mean(times))
+    value = total / (ms * 1e-3)
+    sample = (f"{cores} threads x {files_per_thread} files x {FRAMES_PER_FILE} frames "
+              f"({total} offsets per step); data pre-loaded in RAM (the reference's 1-frame AudioFile.read per "
+              f"offset is excluded)")
+    line = {"impl": "reference", "metric": "FeatureCorrelation DB frame-offsets/sec", "value": value,
+            "unit": "offsets/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config_block(args.gpus, note="bounded sample of the same workload"),
+            "cpu_baseline": {"value": value, "unit": "offsets/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "offsets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def config_block(n_gpus, files=6000, note=None):
+    c = {"workload": "FeatureCorrelation punch-in 2 s (W=172 frames) over 1000 h synthetic feature DB per GPU "
+                     "(BASELINE.json configs[4])",
+         "files_per_gpu": files, "frames_per_file": FRAMES_PER_FILE, "channels": 14, "temporalWeight": 0.5,
+         "numMatches": 100, "numPerFile": 1, "minSpacing": 22050, "sharding": f"file-range x{n_gpus}",
+         "cache": "DB per GPU (17.4 GB) >> 126 MB L2, no reuse between steps"}
+    if note:
+        c["note"] = note
+    return c
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--files", type=int, default=6000, help="DB files per GPU (default = 1000 h)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from strugatzki_b200 import _native as N, engine, synth
+    from strugatzki_b200.distributed import sharded_search
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    ctx = engine.Context(local_rank)
+    ext_stream = torch.cuda.ExternalStream(ctx.stream, device=device)
+
+    # ---- live roofline denominators on this GPU ----
+    ffma_peak = ctx.measure_peak(0)
+    peaks_file = {}
+    try:
+        peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks_file.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks_file else "fallback (B200_PROFILING.md)"
+
+    # ---- database: generated on the device, then the normal prepare path ----
+    mu, sigma, floor0, norm = synth.default_profile(14)
+    files = args.files
+    db = engine.Database(ctx, 14, norm)
+    db.reserve(files * FRAMES_PER_FILE, files)
+    for i in range(files):
+        db.add_synth(synth.BASE_SEED, 1 + rank * files + i, FRAMES_PER_FILE, mu, sigma, float(floor0))
+    inp = synth.synth_file(synth.BASE_SEED, 0, 900, mu, sigma, floor0)
+    rng = np.random.default_rng(1234 + rank)
+    needles = []
+    for k in range(8):  # planted noisy copies of the query at known places
+        f, off = int(rng.integers(0, files)), int(rng.integers(0, FRAMES_PER_FILE - 172))
+        db.patch(f, off, synth.plant(inp[:172], 77 + rank, k))
+        needles.append((rank * files + f, off * STEP))
+    db.finalize()
+    cfg = corr_config(N)
+    job = engine.CorrelationJob(db, cfg, inp)
+    n_off_local = job.num_offsets
+
+    def step():
+        return sharded_search(job, device, None) if world > 1 else job.run()
+
+    def sync_all():
+        ctx.synchronize()
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    for _ in range(args.warmup):
+        res = step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scan_ms, select_ms = [], []
+    t_wall = time.perf_counter()
+    ev0.record(ext_stream)
+    for _ in range(args.steps):
+        res = step()
+        tm = job.timing()
+        scan_ms.append(tm["scan_ms"])
+        select_ms.append(tm["select_ms"])
+    ev1.record(ext_stream)
+    sync_all()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall)
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([dev_ms, wall_ms, float(n_off_local), float(np.mean(scan_ms))], dtype=torch.float64, device=device)
+    if world > 1:
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms_max, total_off, scan_ms_max = float(mx[0]), float(sm[2]), float(mx[3])
+    else:
+        dev_ms_max, total_off, scan_ms_max = dev_ms, float(n_off_local), float(np.mean(scan_ms))
+    ms_per_step = dev_ms_max / args.steps
+    value = total_off / (ms_per_step * 1e-3)
+
+    # sanity inside the bench: every planted needle of this rank must be found where it was planted
+    found = {(m["file"], m["start"]) for m in res}
+    missing = [nd for nd in needles if nd not in found] if world == 1 else []
+
+    # ---- end to end from HOST buffers through the same C-ABI calls ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, torch, device, ctx, engine, N, synth, rank, files, mu, sigma, floor0, norm, inp, cfg, world,
+                      dist)
+
+    # ---- CPU baseline: the oracle port, one host thread (the reference is single-threaded) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(args, synth, norm, inp)
+
+    if rank == 0:
+        scan_s = float(np.mean(scan_ms)) * 1e-3
+        flops = n_off_local * FLOP_PER_OFFSET / scan_s / 1e12
+        line = {
+            "metric": "FeatureCorrelation DB frame-offsets/sec", "value": value, "unit": "offsets/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 window sums)",
+            "data": "synthetic (device-generated integer-hash features, planted needles)",
+            "config": config_block(world, files),
+            "roofline": {"kernel": "sgz::k_corr (K1 sliding-window Pearson correlation)", "bound": "fp32_ffma",
+                         "achieved": flops, "peak": ffma_peak, "unit": "TFLOP/s", "frac": flops / ffma_peak,
+                         "peak_source": "FP32 FFMA micro-benchmark run live by this process "
+                                        "(MEASURED_PEAKS.json has no FP32 figure; SURVEY.md 8d)",
+                         "algorithmic_flop_per_offset": FLOP_PER_OFFSET, "offsets_per_launch": n_off_local,
+                         "launch_ms": float(np.mean(scan_ms)), "traffic": None,
+                         "hbm": {"achieved": n_off_local * BYTES_PER_OFFSET / scan_s / 1e9, "peak": hbm_peak,
+                                 "unit": "GB/s", "frac": n_off_local * BYTES_PER_OFFSET / scan_s / 1e9 / hbm_peak,
+                                 "peak_source": hbm_src, "algorithmic_bytes_per_offset": BYTES_PER_OFFSET}},
+            "breakdown_ms": {"k1_scan": float(np.mean(scan_ms)), "k2_select_kernels": float(np.mean(select_ms)),
+                             "wall_per_step": wall_ms / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": e2e, "cpu_baseline": cpu,
+            "matches": len(res), "needles_missing": len(missing), "top_sim": res[0]["sim"] if res else None,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(args, torch, device, ctx, engine, N, synth, rank, files, mu, sigma, floor0, norm, inp, cfg, world, dist):
+    import psutil
+    bytes_per_file = FRAMES_PER_FILE * 14 * 4
+    avail = psutil.virtual_memory().available
+    e2e_files = files
+    while e2e_files * bytes_per_file * 1.3 * max(world, 1) > avail * 0.6 and e2e_files > 60:
+        e2e_files //= 2
+    # raw (un-normalised) features of this rank's first e2e_files files -> pinned host memory, planar per file
+    host = torch.empty((e2e_files, 14, FRAMES_PER_FILE), dtype=torch.float32, pin_memory=True)
+    raw = engine.Database(ctx, 14, None)
+    chunk = 200
+    hnp = host.numpy()
+    for c0 in range(0, e2e_files, chunk):
+        raw = engine.Database(ctx, 14, None)
+        for i in range(c0, min(c0 + chunk, e2e_files)):
+            raw.add_synth(synth.BASE_SEED, 1 + rank * files + i, FRAMES_PER_FILE, mu, sigma, float(floor0))
+        raw.finalize()
+        for i in range(c0, min(c0 + chunk, e2e_files)):
+            hnp[i] = raw.read(i - c0, 0, FRAMES_PER_FILE)
+        raw.close()
+    base = host.data_ptr()
+
+    def e2e_step():
+        db2 = engine.Database(ctx, 14, norm)
+        db2.reserve(e2e_files * FRAMES_PER_FILE, e2e_files)
+        for i in range(e2e_files):
+            db2.add_file_ptr(base + i * bytes_per_file, FRAMES_PER_FILE, N.LAYOUT_PLANAR_LE)
+        db2.finalize()
+        job2 = engine.CorrelationJob(db2, cfg, inp)
+        if world > 1:
+            from strugatzki_b200.distributed import sharded_search
+            r = sharded_search(job2, device, None)
+        else:
+            r = job2.run()
+        n = job2.num_offsets
+        job2.close()
+        db2.close()
+        return r, n
+
+    e2e_step()
+    ctx.synchronize()
+    if world > 1:
+        dist.barrier()
+    times = []
+    n_off = 0
+    for _ in range(max(args.e2e_steps, 1)):
+        ctx.synchronize()
+        t = time.perf_counter()
+        r, n_off = e2e_step()
+        ctx.synchronize()
+        times.append(time.perf_counter() - t)
+    t_loc = torch.tensor([float(np.mean(times)), float(n_off)], dtype=torch.float64, device=device)
+    if world > 1:
+        mx = t_loc.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t_loc.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        sec, tot = float(mx[0]), float(sm[1])
+    else:
+        sec, tot = float(t_loc[0]), float(t_loc[1])
+    del host
+    return {"value": tot / sec, "unit": "offsets/s", "ms_per_step": sec * 1e3,
+            "h2d_bytes_per_step": int(e2e_files * bytes_per_file + inp.nbytes + 14 * 172 * 4),
+            "d2h_bytes_per_step": int(100 * 32 + e2e_files * 8 + 100 * 32),
+            "files_per_gpu": e2e_files,
+            "note": "DB upload from pinned host memory (planar float32) + normalise + search + result download, "
+                    "through sgz_db_add_file / sgz_db_finalize / sgz_corr_run; PCIe-bound"}
+
+
+def cpu_baseline(args, synth, norm, inp):
+    from oracle import oracle as O
+    mu, sigma, floor0, _ = synth.default_profile(14)
+    p = O.CorrParams(step_size=STEP, input=inp, punch_in=(0, W_IN_SAMPLES), norm=norm, num_matches=100,
+                     num_per_file=1, min_spacing=22050)
+    f0 = synth.synth_file(synth.BASE_SEED, 1, FRAMES_PER_FILE, mu, sigma, floor0)
+    t = time.perf_counter()
+    O.corr_search(p, [f0])
+    per_file = time.perf_counter() - t
+    n_files = int(max(2, min(60, round(args.cpu_seconds / max(per_file, 1e-3)))))
+    files = [f0] + [synth.synth_file(synth.BASE_SEED, 1 + i, FRAMES_PER_FILE, mu, sigma, floor0)
+                    for i in range(1, n_files)]
+    n = O.corr_num_offsets(p, [f.shape[0] for f in files])
+    t = time.perf_counter()
+    O.corr_search(p, files)
+    dt = time.perf_counter() - t
+    return {"value": n / dt, "unit": "offsets/s", "cores": 1, "kind": "port",
+            "sample": f"first {n_files} of the 6000 DB files ({n} offsets, {dt:.1f} s), C restatement of the "
+                      f"reference's single-threaded Double loops, features pre-loaded in RAM"}
+
+
+if __name__ == "__main__":
+    sys.exit(main())
