@@ -1,0 +1,92 @@
+"""The reference-facing surface end to end: feature AIFFs + meta XML + feat_norms.aif on disk ->
+FeatureCorrelation / FeatureSegmentation / SelfSimilarity processors -> results equal the oracle's."""
+import os
+
+import numpy as np
+import pytest
+
+from util import O, STEP, make_db, make_input, plant_needles, synth
+from strugatzki_b200 import feature_correlation as fc
+from strugatzki_b200 import feature_segmentation as fs
+from strugatzki_b200 import self_similarity as ss
+from strugatzki_b200.io import FeatureExtractionConfig, Span, write_aiff, write_norm_file
+from strugatzki_b200.processor import Progress, Result, Success
+
+pytestmark = pytest.mark.gpu
+
+
+def write_feature_file(folder, name, frames):
+    feat = os.path.join(folder, f"{name}_feat.aif")
+    write_aiff(feat, frames, 44100.0 / STEP)
+    FeatureExtractionConfig(os.path.join(folder, f"{name}.aif"), feat, None, frames.shape[1] - 1, 1024, 2).write(
+        os.path.join(folder, f"{name}_feat.xml"))
+    return os.path.join(folder, f"{name}_feat.xml")
+
+
+@pytest.fixture()
+def database(tmp_path):
+    folder = str(tmp_path / "db")
+    os.makedirs(folder)
+    files, norm = make_db(5, [2600, 3000, 2200, 2800, 2400])
+    inp = make_input(900)
+    plant_needles(files, inp[:172], [(1, 640), (3, 2000)])
+    for i, f in enumerate(files):
+        write_feature_file(folder, f"file{i:02d}", f)
+    meta_in = write_feature_file(str(tmp_path), "query", inp)
+    write_norm_file(folder, norm)
+    return folder, meta_in, files, inp, norm
+
+
+def test_feature_correlation_processor(ctx, database):
+    folder, meta_in, files, inp, norm = database
+    b = fc.ConfigBuilder()
+    b.databaseFolder, b.metaInput = folder, meta_in
+    b.punchIn = fc.Punch(Span(0, 88200), 0.5)
+    b.numMatches, b.numPerFile, b.minSpacing = 4, 2, 22050
+    events = []
+    proc = fc.FeatureCorrelation.run(b.build(), events.append)
+    got = proc.await_result(60)
+    want = O.corr_search(O.CorrParams(step_size=STEP, input=inp, punch_in=(0, 88200), norm=norm, num_matches=4,
+                                      num_per_file=2, min_spacing=22050), files)
+    assert len(got) == len(want) == 4
+    for g, w in zip(got, want):
+        assert g.file == os.path.join(folder, f"file{w['file']:02d}.aif")
+        assert (g.punch.start, g.punch.stop) == (w["start"], w["stop"])
+        assert abs(g.sim - w["sim"]) <= 1e-5 * abs(w["sim"]) + 2e-6
+        assert abs(g.boostIn - w["boostIn"]) <= 1e-5 * abs(w["boostIn"])
+    assert (got[0].file, got[0].punch.start) in ((os.path.join(folder, "file01.aif"), 640 * STEP),
+                                                 (os.path.join(folder, "file03.aif"), 2000 * STEP))
+    prog = [e.amount for e in events if isinstance(e, Progress)]
+    assert prog == sorted(prog) and prog[-1] == 1.0
+    assert isinstance(events[-1], Result) and isinstance(events[-1].value, Success)
+    # normalize = true without feat_norms.aif -> failure surfaces through the processor, like the reference
+    os.remove(os.path.join(folder, "feat_norms.aif"))
+    with pytest.raises(IOError):
+        fc.FeatureCorrelation.run(b.build()).await_result(60)
+
+
+def test_segmentation_and_selfsimilarity_processors(ctx, tmp_path):
+    folder = str(tmp_path)
+    f, _ = synth.regime_file(synth.BASE_SEED, 21, 1500, 14, 7)
+    _, _, _, norm = synth.default_profile(14)
+    meta = write_feature_file(folder, "song", f)
+    write_norm_file(folder, norm)
+    cfg = fs.Config(folder, meta, Span.all(), 22050, 0.5, True, 6, 22050)
+    got = fs.FeatureSegmentation.run(cfg).await_result(60)
+    want = O.segm_run(O.SegmParams(step_size=STEP, norm=norm, num_breaks=6), f)
+    assert [(b.pos, np.float32(b.sim).tobytes()) for b in got] == \
+           [(b["pos"], np.float32(b["sim"]).tobytes()) for b in want]
+
+    png = os.path.join(folder, "out.png")
+    scfg = ss.Config(folder, meta, None, png, Span.until(400 * STEP), 20480, 2, 0.5, ss.GrayScale, 1.0, 1.0, False,
+                     True)
+    assert ss.SelfSimilarity.run(scfg).await_result(120) is None
+    from PIL import Image
+    img = np.asarray(Image.open(png).convert("RGB")).astype(np.int32)
+    packed = (img[..., 0] << 16) | (img[..., 1] << 8) | img[..., 2]
+    want_img = O.self_image(O.SelfParams(step_size=STEP, corr_len=20480, decimation=2, norm=norm,
+                                         span_stop=400 * STEP), f)
+    assert packed.shape == want_img.shape and np.array_equal(packed, want_img)
+    with pytest.raises(RuntimeError):   # PsychoOptical without the third-party palette table
+        ss.SelfSimilarity.run(ss.Config(folder, meta, None, png, Span.until(400 * STEP), 20480, 2, 0.5,
+                                        ss.PsychoOptical)).await_result(60)
