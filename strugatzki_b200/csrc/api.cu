@@ -111,6 +111,7 @@ int sgz_db_create(sgz_ctx *ctx, int32_t numCh, const float *norm, sgz_db **out) 
   sgz_db *db = new sgz_db();
   db->ctx = ctx;
   db->numCh = numCh;
+  db->numPairs = (numCh + 1) / 2;
   db->hasNorm = norm != nullptr;
   db->norm.resize((size_t)numCh * 2);
   for (int c = 0; c < numCh; c++) {
@@ -222,7 +223,7 @@ int sgz_db_add_synth(sgz_db *db, uint64_t seed, uint32_t stream, int64_t nFrames
     SGZ_CUDA(cudaMemcpyAsync(ms.p, mu, db->numCh * sizeof(float), cudaMemcpyHostToDevice, db->ctx->stream));
     SGZ_CUDA(cudaMemcpyAsync(ms.p + db->numCh, sigma, db->numCh * sizeof(float), cudaMemcpyHostToDevice,
                              db->ctx->stream));
-    dim3 grid((unsigned)std::min<int64_t>(ceil_div<int64_t>(nFrames, 256), 4096), (unsigned)db->numCh);
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div<int64_t>(nFrames, 256), 4096), (unsigned)db->numPairs);
     k_db_synth<<<grid, 256, 0, db->ctx->stream>>>(db->dData.p, db->capFrames, dst, nFrames, db->numCh, seed, stream,
                                                   ms.p, ms.p + db->numCh, floor0, db->dNorm.p);
     SGZ_LAUNCH_CHECK(db->ctx);
@@ -348,7 +349,7 @@ int sgz_corr_create(sgz_db *db, const sgz_corr_config *cfg, const void *input, i
                        job->step, job->qout);
   if (rc == SGZ_OK) {
     int wq = std::max(job->qin.Wq, job->hasOut ? job->qout.Wq : 0);
-    job->ntg = pick_ntg(job->ctx, db->numCh, wq);
+    job->ntg = pick_ntg(job->ctx, db->numPairs, wq);
     if (job->ntg == 0) {
       set_error("punch window of %d feature frames does not fit the shared-memory tile", wq);
       rc = SGZ_ERR_INVALID;

@@ -34,7 +34,7 @@ inline int upload_features(sgz_ctx *ctx, int numCh, const float *norm, const voi
   }
   int blocks = (int)ceil_div<int64_t>(n, kPrepFrames);
   k_db_prepare<<<blocks, 256, (size_t)kPrepFrames * numCh * sizeof(float), ctx->stream>>>(
-      stage.p, layout, n, out.p, stride, 0, numCh, dNorm.p);
+      stage.p, layout, n, out.p, stride, 0, numCh, dNorm.p, 0);
   SGZ_LAUNCH_CHECK(ctx);
   SGZ_CUDA(cudaStreamSynchronize(ctx->stream));  // stage / dNorm go out of scope
   return SGZ_OK;

@@ -106,13 +106,14 @@ inline int prepare_query(const sgz_db *db, const float *inputPlanar /*[numCh][in
     float avg = (float)(sum / W);
     q.lnAvg = log((double)avg);
   }
-  q.taps.assign((size_t)numCh * q.Wq, 0.f);
+  // taps in the kernel's pair layout: [pair p][tap i] = float2(channel 2p, channel 2p+1), zero padded
+  q.taps.assign((size_t)db->numPairs * q.Wq * 2, 0.f);
   q.rhoT = q.rhoS = 0.0;
   for (int c = 0; c < numCh; c++) {
     double mean = c == 0 ? meanT : meanS;
     for (int i = 0; i < W; i++) {
       float tp = (float)((double)a[(size_t)c * W + i] - mean);
-      q.taps[(size_t)c * q.Wq + i] = tp;
+      q.taps[((size_t)(c >> 1) * q.Wq + i) * 2 + (c & 1)] = tp;
       (c == 0 ? q.rhoT : q.rhoS) += (double)tp;
     }
   }
@@ -122,23 +123,11 @@ inline int prepare_query(const sgz_db *db, const float *inputPlanar /*[numCh][in
   return SGZ_OK;
 }
 
-template <int NTG>
-inline int launch_corr_ntg(sgz_ctx *ctx, const CorrParams &p, size_t smemBytes, int64_t tileBegin, int64_t tileEnd) {
-  SGZ_CUDA(cudaFuncSetAttribute(k_corr<NTG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemOptin));
-  (void)tileBegin;
-  k_corr<NTG><<<(unsigned)(tileEnd - tileBegin), 2 * NTG, smemBytes, ctx->stream>>>(p);
-  SGZ_LAUNCH_CHECK(ctx);
-  return SGZ_OK;
-}
-
-inline int pick_ntg(const sgz_ctx *ctx, int numCh, int Wq) {
-  // prefer two resident CTAs per SM (one CTA's load / prefix / epilogue phases overlap the other's FFMA loop)
-  const int opts[3] = {96, 64, 32};
-  const size_t perSm = 228 * 1024, reserved = 1024;
-  for (int k = 0; k < 3; k++)
-    if (2 * (corr_smem_layout(opts[k], numCh, Wq).total + reserved) <= perSm) return opts[k];
-  for (int k = 0; k < 3; k++)
-    if (corr_smem_layout(opts[k], numCh, Wq).total <= ctx->smemOptin) return opts[k];
+// consumer threads per CTA: the largest configuration whose ring + stats buffers fit in shared memory
+inline int pick_ntg(const sgz_ctx *ctx, int numPairs, int Wq) {
+  const int opts[5] = {256, 192, 128, 64, 32};
+  for (int k = 0; k < 5; k++)
+    if (corr_smem_layout(opts[k], numPairs, Wq).total <= ctx->smemOptin) return opts[k];
   return 0;
 }
 
@@ -156,13 +145,13 @@ inline int run_scan_one(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim,
   sgz_db *db = job->db;
   CorrParams p{};
   p.data = db->dData.p;
-  p.chanStride = db->capFrames;
+  p.rowStride = db->capFrames;
   p.usedFrames = db->usedFrames;
   p.numCh = db->numCh;
-  p.csplit = (db->numCh + 1) / 2;
+  p.numPairs = db->numPairs;
   p.W = q.W;
   p.Wq = q.Wq;
-  p.taps = q.dTaps.p;
+  p.taps = reinterpret_cast<const float2 *>(q.dTaps.p);
   p.stdT = q.stdT; p.stdS = q.stdS; p.rhoT = q.rhoT; p.rhoS = q.rhoS;
   p.lnAvgIn = q.lnAvg;
   p.weight = q.weight;
@@ -173,14 +162,15 @@ inline int run_scan_one(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim,
   p.sim = sim;
   p.boost = boost;
   p.fileMax = fileMax;
-  CorrSmemLayout L = corr_smem_layout(job->ntg, db->numCh, q.Wq);
-  int rc;
-  switch (job->ntg) {
-    case 96: rc = launch_corr_ntg<96>(job->ctx, p, L.total, 0, job->numTiles); break;
-    case 64: rc = launch_corr_ntg<64>(job->ctx, p, L.total, 0, job->numTiles); break;
-    default: rc = launch_corr_ntg<32>(job->ctx, p, L.total, 0, job->numTiles); break;
-  }
-  return rc;
+  p.numTiles = job->numTiles;
+  CorrSmemLayout L = corr_smem_layout(job->ntg, db->numPairs, q.Wq);
+  sgz_ctx *ctx = job->ctx;
+  SGZ_CUDA(cudaFuncSetAttribute(k_corr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemOptin));
+  // persistent: one CTA per SM, tiles are striped over the CTAs
+  const unsigned grid = (unsigned)std::min<int64_t>(job->numTiles, ctx->smCount);
+  k_corr<<<grid, job->ntg + 64, L.total, ctx->stream>>>(p);
+  SGZ_LAUNCH_CHECK(ctx);
+  return SGZ_OK;
 }
 
 // ---- allPrio helpers (host): SortedSet[Match](MatchMinOrd) ----

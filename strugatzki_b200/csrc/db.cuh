@@ -3,20 +3,26 @@
 // Replaces the reference's per-offset feature I/O: `afExtr.read(eInBuf, readOff, 1)` +
 // `MathUtil.normalize` once per frame-offset (FeatureCorrelationImpl.scala:195-197,
 // MathUtil.scala:132-152).  Every DB file is uploaded once, normalised with the same float
-// expression `(f - min) / (max - min)` (IEEE division, bit-identical to the JVM), and kept as
-// ONE planar stream  data[channel][globalFrame]  in which the files follow each other without
-// padding.  K1 tiles that stream; a file table maps global frames back to (file, local frame).
+// expression `(f - min) / (max - min)` (IEEE division, bit-identical to the JVM), and kept as ONE
+// stream in which the files follow each other without padding.
+//
+// HBM layout ("pair rows"): data[pair p][global frame g] is a float2 holding channels (2p, 2p+1);
+// an odd channel count is padded with a zero channel.  K1 streams one pair row per TMA bulk copy and
+// feeds it to packed FFMA2 (fma.rn.f32x2) whose operands are exactly these naturally aligned
+// pairs -- measured on B200, scalar FFMA with live register operands tops out near 51 TFLOP/s while
+// FFMA2 reaches the full 73 TFLOP/s (tools/peaks_probe.py).
 #pragma once
 #include "common.cuh"
 
 struct sgz_db {
   sgz_ctx *ctx = nullptr;
   int numCh = 0;
+  int numPairs = 0;
   bool hasNorm = false;
   std::vector<float> norm;              // [numCh][2] host copy
   DevBuf<float> dNorm;                  // [numCh][2]; {0,1} per channel when normalize=false
-  DevBuf<float> dData;                  // planar [numCh][capFrames]
-  int64_t capFrames = 0;                // channel stride (multiple of 4)
+  DevBuf<float2> dData;                 // pair rows [numPairs][capFrames]
+  int64_t capFrames = 0;                // row stride in frames (multiple of 1024)
   int64_t usedFrames = 0;
   std::vector<int64_t> fileStart;       // size numFiles+1 (last = usedFrames)
   DevBuf<int64_t> dFileStart;
@@ -62,16 +68,23 @@ __device__ inline float normalize_value(float f, float mn, float mx) {
   return __fdiv_rn(__fsub_rn(f, mn), __fsub_rn(mx, mn));  // MathUtil.scala:140-147
 }
 
-__global__ void k_db_synth(float *__restrict__ data, int64_t chanStride, int64_t dstFrame, int64_t nFrames,
+// one thread = one frame of one channel pair -> coalesced float2 stores
+__global__ void k_db_synth(float2 *__restrict__ data, int64_t rowStride, int64_t dstFrame, int64_t nFrames,
                            int numCh, uint64_t seed, uint32_t stream, const float *__restrict__ mu,
                            const float *__restrict__ sigma, float floor0, const float *__restrict__ norm) {
-  int c = blockIdx.y;
-  float m = mu[c], s = sigma[c], mn = norm[2 * c], mx = norm[2 * c + 1];
+  const int p = blockIdx.y, c0 = 2 * p, c1 = 2 * p + 1;
+  const bool has1 = c1 < numCh;
+  const float m0 = mu[c0], s0 = sigma[c0], mn0 = norm[2 * c0], mx0 = norm[2 * c0 + 1];
+  const float m1 = has1 ? mu[c1] : 0.f, s1 = has1 ? sigma[c1] : 0.f;
+  const float mn1 = has1 ? norm[2 * c1] : 0.f, mx1 = has1 ? norm[2 * c1 + 1] : 1.f;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nFrames;
        t += (int64_t)gridDim.x * blockDim.x) {
-    float x = synth_value(seed, stream, (uint32_t)c, (uint64_t)t, m, s);
-    if (c == 0) x = fmaxf(x, floor0);
-    data[(int64_t)c * chanStride + dstFrame + t] = normalize_value(x, mn, mx);
+    float x = synth_value(seed, stream, (uint32_t)c0, (uint64_t)t, m0, s0);
+    if (c0 == 0) x = fmaxf(x, floor0);
+    float2 v;
+    v.x = normalize_value(x, mn0, mx0);
+    v.y = has1 ? normalize_value(synth_value(seed, stream, (uint32_t)c1, (uint64_t)t, m1, s1), mn1, mx1) : 0.f;
+    data[(int64_t)p * rowStride + dstFrame + t] = v;
   }
 }
 
@@ -80,13 +93,17 @@ __device__ inline float load_be(const float *p) {
   return __int_as_float((int)__byte_perm(v, 0, 0x0123));
 }
 
-// K0: interleaved (LE or BE) / planar staging -> normalised planar store.  One block converts
-// kFr frames; the interleaved source is read with fully coalesced 4-byte loads into shared memory
-// and written back as numCh coalesced rows.
+// destination index of (channel c, frame t): pair rows (DB) or plain planar rows (segm / selfsim)
+__device__ __forceinline__ int64_t dst_index(int pairRows, int c, int64_t t, int64_t rowStride) {
+  return pairRows ? ((int64_t)(c >> 1) * rowStride + t) * 2 + (c & 1) : (int64_t)c * rowStride + t;
+}
+
+// K0: interleaved (LE or BE) / planar staging -> normalised rows.  One block converts kPrepFrames
+// frames; the interleaved source is read with fully coalesced 4-byte loads into shared memory.
 constexpr int kPrepFrames = 256;
 __global__ void k_db_prepare(const float *__restrict__ src, int layout, int64_t srcFrames,
-                             float *__restrict__ data, int64_t chanStride, int64_t dstFrame, int numCh,
-                             const float *__restrict__ norm) {
+                             float *__restrict__ data, int64_t rowStride, int64_t dstFrame, int numCh,
+                             const float *__restrict__ norm, int pairRows) {
   extern __shared__ float sh[];  // [kPrepFrames * numCh]
   int64_t f0 = (int64_t)blockIdx.x * kPrepFrames;
   int nf = (int)min((int64_t)kPrepFrames, srcFrames - f0);
@@ -95,7 +112,7 @@ __global__ void k_db_prepare(const float *__restrict__ src, int layout, int64_t 
     for (int i = threadIdx.x; i < nf * numCh; i += blockDim.x) {
       int c = i / nf, t = i - c * nf;
       float v = src[(int64_t)c * srcFrames + f0 + t];
-      data[(int64_t)c * chanStride + dstFrame + f0 + t] = normalize_value(v, norm[2 * c], norm[2 * c + 1]);
+      data[dst_index(pairRows, c, dstFrame + f0 + t, rowStride)] = normalize_value(v, norm[2 * c], norm[2 * c + 1]);
     }
     return;
   }
@@ -103,34 +120,47 @@ __global__ void k_db_prepare(const float *__restrict__ src, int layout, int64_t 
   for (int i = threadIdx.x; i < nf * numCh; i += blockDim.x)
     sh[i] = layout == SGZ_LAYOUT_INTERLEAVED_BE ? load_be(s + i) : s[i];
   __syncthreads();
-  for (int i = threadIdx.x; i < nf * numCh; i += blockDim.x) {
-    int c = i / nf, t = i - c * nf;
-    float v = sh[t * numCh + c];
-    data[(int64_t)c * chanStride + dstFrame + f0 + t] = normalize_value(v, norm[2 * c], norm[2 * c + 1]);
+  if (pairRows) {
+    const int np = (numCh + 1) >> 1;
+    for (int i = threadIdx.x; i < nf * np; i += blockDim.x) {   // one float2 per thread, coalesced
+      int p = i / nf, t = i - p * nf;
+      int c0 = 2 * p, c1 = 2 * p + 1;
+      float2 v;
+      v.x = normalize_value(sh[t * numCh + c0], norm[2 * c0], norm[2 * c0 + 1]);
+      v.y = c1 < numCh ? normalize_value(sh[t * numCh + c1], norm[2 * c1], norm[2 * c1 + 1]) : 0.f;
+      reinterpret_cast<float2 *>(data)[(int64_t)p * rowStride + dstFrame + f0 + t] = v;
+    }
+  } else {
+    for (int i = threadIdx.x; i < nf * numCh; i += blockDim.x) {
+      int c = i / nf, t = i - c * nf;
+      data[(int64_t)c * rowStride + dstFrame + f0 + t] = normalize_value(sh[t * numCh + c], norm[2 * c], norm[2 * c + 1]);
+    }
   }
 }
 
-__global__ void k_db_gather(const float *__restrict__ data, int64_t chanStride, int64_t srcFrame, int64_t n,
+// planar [numCh][n] read-back of normalised frames from the pair rows
+__global__ void k_db_gather(const float2 *__restrict__ data, int64_t rowStride, int64_t srcFrame, int64_t n,
                             int numCh, float *__restrict__ out) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n * numCh) return;
   int c = (int)(i / n);
   int64_t t = i - (int64_t)c * n;
-  out[i] = data[(int64_t)c * chanStride + srcFrame + t];
+  float2 v = data[(int64_t)(c >> 1) * rowStride + srcFrame + t];
+  out[i] = (c & 1) ? v.y : v.x;
 }
 
 inline int db_grow(sgz_db *db, int64_t needFrames) {
   if (needFrames + kDbSlack <= db->capFrames) return SGZ_OK;
   int64_t newCap = std::max<int64_t>(needFrames + kDbSlack, db->capFrames * 2);
   newCap = (newCap + 1023) / 1024 * 1024;
-  DevBuf<float> nd;
-  SGZ_TRY(nd.alloc((size_t)newCap * db->numCh));
+  DevBuf<float2> nd;
+  SGZ_TRY(nd.alloc((size_t)newCap * db->numPairs));
   cudaStream_t st = db->ctx->stream;
-  SGZ_CUDA(cudaMemsetAsync(nd.p, 0, (size_t)newCap * db->numCh * sizeof(float), st));
+  SGZ_CUDA(cudaMemsetAsync(nd.p, 0, (size_t)newCap * db->numPairs * sizeof(float2), st));
   if (db->usedFrames > 0) {
-    SGZ_CUDA(cudaMemcpy2DAsync(nd.p, (size_t)newCap * sizeof(float), db->dData.p,
-                               (size_t)db->capFrames * sizeof(float), (size_t)db->usedFrames * sizeof(float),
-                               (size_t)db->numCh, cudaMemcpyDeviceToDevice, st));
+    SGZ_CUDA(cudaMemcpy2DAsync(nd.p, (size_t)newCap * sizeof(float2), db->dData.p,
+                               (size_t)db->capFrames * sizeof(float2), (size_t)db->usedFrames * sizeof(float2),
+                               (size_t)db->numPairs, cudaMemcpyDeviceToDevice, st));
   }
   SGZ_CUDA(cudaStreamSynchronize(st));
   std::swap(db->dData.p, nd.p);
@@ -143,8 +173,8 @@ inline int db_launch_prepare(sgz_db *db, const float *dSrc, int layout, int64_t 
   if (nFrames <= 0) return SGZ_OK;
   int blocks = (int)ceil_div<int64_t>(nFrames, kPrepFrames);
   size_t sm = (size_t)kPrepFrames * db->numCh * sizeof(float);
-  k_db_prepare<<<blocks, 256, sm, db->ctx->stream>>>(dSrc, layout, nFrames, db->dData.p, db->capFrames,
-                                                     dstFrame, db->numCh, db->dNorm.p);
+  k_db_prepare<<<blocks, 256, sm, db->ctx->stream>>>(dSrc, layout, nFrames, reinterpret_cast<float *>(db->dData.p),
+                                                     db->capFrames, dstFrame, db->numCh, db->dNorm.p, 1);
   SGZ_LAUNCH_CHECK(db->ctx);
   return SGZ_OK;
 }

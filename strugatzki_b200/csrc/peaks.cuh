@@ -61,6 +61,72 @@ __global__ void k_peak_dfma(double *out, int iters, double b, double c) {
   if (s == 12345.678) out[0] = s;
 }
 
+// Register-operand bound patterns (what a register-tiled FP32 kernel really issues): an 8x8 outer
+// product c[i][j] += a[i] * b[j] where a is reused across a row (reuse cache) but b[j] and c[i][j] are
+// fresh register-file reads for every FFMA.
+__global__ void k_peak_ffma_outer(float *out, int iters, float seed) {
+  float a[8], b[8], c[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    a[i] = out[8 + i] + seed;      // runtime values: nothing folds into immediates
+    b[i] = out[16 + i] - seed;
+#pragma unroll
+    for (int j = 0; j < 8; j++) c[i][j] = 0.f;
+  }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) c[i][j] = fmaf(a[i], b[j], c[i][j]);
+    }
+    // keep a/b live and changing without adding arithmetic to the measured pattern's ratio
+    a[it & 7] += 1e-6f;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) s += c[i][j];
+  }
+  if (s == 12345.678f) out[0] = s;
+}
+
+// same outer product with packed FFMA2: c2[i][j] (pair along j) += (a[i], a[i]) * (b[2j], b[2j+1])
+__global__ void k_peak_ffma2_outer(float *out, int iters, float seed) {
+  unsigned long long a2[8], b2[4], c2[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    float x = out[8 + i] + seed;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a2[i]) : "f"(x), "f"(x));
+#pragma unroll
+    for (int j = 0; j < 4; j++) asm("mov.b64 %0, {%1, %2};" : "=l"(c2[i][j]) : "f"(0.f), "f"(0.f));
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    float y = out[16 + 2 * j] - seed, y2 = out[17 + 2 * j] - seed;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b2[j]) : "f"(y), "f"(y2));
+  }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c2[i][j]) : "l"(a2[i]), "l"(b2[j]));
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float lo, hi;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(c2[i][j]));
+      s += lo + hi;
+    }
+  }
+  if (s == 12345.678f) out[0] = s;
+}
+
 __global__ void k_peak_copy(const float4 *__restrict__ src, float4 *__restrict__ dst, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = src[i];
@@ -105,6 +171,19 @@ inline int measure_peak(sgz_ctx *ctx, int which, double *value) {
       SGZ_CUDA(cudaEventSynchronize(e1));
       SGZ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
       double flops = 2.0 * (double)blocks * threads * iters * ILP * (which == 1 ? 2.0 : 1.0);
+      if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+  } else if (which == 5 || which == 6) {
+    const int iters = 2048;
+    for (int rep = 0; rep < 4; rep++) {
+      SGZ_CUDA(cudaEventRecord(e0, st));
+      if (which == 5) k_peak_ffma_outer<<<blocks, threads, 0, st>>>(sink.p, iters, 0.5f);
+      else k_peak_ffma2_outer<<<blocks, threads, 0, st>>>(sink.p, iters, 0.5f);
+      SGZ_LAUNCH_CHECK(ctx);
+      SGZ_CUDA(cudaEventRecord(e1, st));
+      SGZ_CUDA(cudaEventSynchronize(e1));
+      SGZ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      double flops = 2.0 * (double)blocks * threads * iters * 64.0;
       if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
     }
   } else if (which == 3) {
