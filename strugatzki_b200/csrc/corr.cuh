@@ -125,10 +125,19 @@ inline int prepare_query(const sgz_db *db, const float *inputPlanar /*[numCh][in
 
 // consumer threads per CTA: the largest configuration whose ring + stats buffers fit in shared memory
 inline int pick_ntg(const sgz_ctx *ctx, int numPairs, int Wq) {
+  // preferred: 128 consumers per CTA and TWO persistent CTAs per SM -- the CTAs drift out of phase, so one
+  // CTA's epilogue / row prologue / stats wait overlaps the other's FFMA2 loop
+  const size_t perSm = 228 * 1024, reserved = 1024;
+  if (2 * (corr_smem_layout(128, numPairs, Wq).total + reserved) <= perSm) return 128;
   const int opts[5] = {256, 192, 128, 64, 32};
   for (int k = 0; k < 5; k++)
     if (corr_smem_layout(opts[k], numPairs, Wq).total <= ctx->smemOptin) return opts[k];
   return 0;
+}
+
+inline int corr_ctas_per_sm(int ntg, int numPairs, int Wq) {
+  const size_t perSm = 228 * 1024, reserved = 1024;
+  return (ntg <= 128 && 2 * (corr_smem_layout(ntg, numPairs, Wq).total + reserved) <= perSm) ? 2 : 1;
 }
 
 inline int64_t valid_offsets(const sgz_db *db, int W, int tailExtra) {
@@ -166,8 +175,9 @@ inline int run_scan_one(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim,
   CorrSmemLayout L = corr_smem_layout(job->ntg, db->numPairs, q.Wq);
   sgz_ctx *ctx = job->ctx;
   SGZ_CUDA(cudaFuncSetAttribute(k_corr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemOptin));
-  // persistent: one CTA per SM, tiles are striped over the CTAs
-  const unsigned grid = (unsigned)std::min<int64_t>(job->numTiles, ctx->smCount);
+  // persistent: one or two CTAs per SM, tiles are striped over the CTAs
+  const int perSm = corr_ctas_per_sm(job->ntg, db->numPairs, q.Wq);
+  const unsigned grid = (unsigned)std::min<int64_t>(job->numTiles, (int64_t)ctx->smCount * perSm);
   k_corr<<<grid, job->ntg + 64, L.total, ctx->stream>>>(p);
   SGZ_LAUNCH_CHECK(ctx);
   return SGZ_OK;

@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(384, 1) k_corr(const CorrParams p) {
             *reinterpret_cast<float4 *>(F + 2 * v) = make_float4(x.y, x.y * x.y, x.w, x.w * x.w);
           }
         } else {
+#pragma unroll 4
           for (int v = lane; v < nv; v += 32) {
             const float4 x = lds4(row + 2 * v);
             float4 f = *reinterpret_cast<float4 *>(F + 2 * v);
@@ -292,11 +293,33 @@ __global__ void __launch_bounds__(384, 1) k_corr(const CorrParams p) {
       double r1 = 0, r2 = 0, r3 = 0, r4 = 0;
       for (int j = jb; j < je; j++) {
         double a1 = 0, a2 = 0, a3 = 0, a4 = 0;
-        const int e1 = min(kR * (j + 1), rowFrames);
-        for (int e = kR * j; e < e1; e++) {
-          const double b0 = (double)T0[e];
-          const float2 f = F[e];
-          a1 += b0; a2 += b0 * b0; a3 += (double)f.x; a4 += (double)f.y;
+        const int e0 = kR * j, e1 = min(kR * (j + 1), rowFrames);
+        if (e1 - e0 == kR) {
+          // full chunk: all loads first, then a pairwise tree (depth 4 instead of a 14-long FP64 chain)
+          double d1[kR], d2[kR], d3[kR], d4[kR];
+#pragma unroll
+          for (int k = 0; k < kR; k += 2) {
+            const float2 t = *reinterpret_cast<const float2 *>(T0 + e0 + k);
+            const float4 f = *reinterpret_cast<const float4 *>(F + e0 + k);
+            d1[k] = (double)t.x; d1[k + 1] = (double)t.y;
+            d3[k] = (double)f.x; d4[k] = (double)f.y; d3[k + 1] = (double)f.z; d4[k + 1] = (double)f.w;
+          }
+#pragma unroll
+          for (int k = 0; k < kR; k++) d2[k] = d1[k] * d1[k];
+#pragma unroll
+          for (int w = 1; w < kR; w <<= 1) {
+#pragma unroll
+            for (int k = 0; k + w < kR; k += 2 * w) {
+              d1[k] += d1[k + w]; d2[k] += d2[k + w]; d3[k] += d3[k + w]; d4[k] += d4[k + w];
+            }
+          }
+          a1 = d1[0]; a2 = d2[0]; a3 = d3[0]; a4 = d4[0];
+        } else {
+          for (int e = e0; e < e1; e++) {
+            const double b0 = (double)T0[e];
+            const float2 f = F[e];
+            a1 += b0; a2 += b0 * b0; a3 += (double)f.x; a4 += (double)f.y;
+          }
         }
         r1 += a1; r2 += a2; r3 += a3; r4 += a4;
         double *o = CP + 4 * (size_t)(j + 1);
@@ -324,7 +347,7 @@ __global__ void __launch_bounds__(384, 1) k_corr(const CorrParams p) {
     const int nSub = Wq >> 2;
     const double invW = 1.0 / (double)W, invNS = 1.0 / ((double)(p.numCh - 1) * (double)W);
     const float cT = (float)(invW / p.stdT), cS = (float)(invNS / p.stdS);
-    const float rhoT = (float)p.rhoT, rhoS = (float)p.rhoS, lnIn = (float)p.lnAvgIn;
+    const float rhoT = (float)p.rhoT, rhoS = (float)p.rhoS, l2In = (float)(p.lnAvgIn * 1.4426950408889634);
     const bool useT = p.weight > 0.f, useS = p.weight < 1.f;
     const float qnan = __int_as_float(0x7fc00000);
     const int nq = W / kR, remW = W - nq * kR;
@@ -375,53 +398,30 @@ __global__ void __launch_bounds__(384, 1) k_corr(const CorrParams p) {
         f = lo;
       }
       int64_t fStart = p.fileStart[f], fEnd = p.fileStart[f + 1];
+      // pass A: straight-line arithmetic for all 14 offsets (no file logic in here, so the 14 chains overlap).
+      // FP64 only for the window variance; boost via MUFU lg2/ex2 (|rel err| < 1e-6); rsqrt instead of sqrt+div.
       float simv[kR], boostv[kR];
-      unsigned long long best = 0ull;
-      int bestFile = -1;
-      bool straddle = false;
 #pragma unroll
       for (int k = 0; k < kR; k++) {
-        const int64_t g = g0 + k;
-        while (g >= fEnd && f + 1 < p.numFiles) {
-          if (best != 0ull && p.fileMax) { atomicMax(p.fileMax + bestFile, best); straddle = true; }
-          best = 0ull;
-          f++;
-          fStart = fEnd;
-          fEnd = p.fileStart[f + 1];
+        const double mT = win.t1 * invW;
+        const float avgB = (float)mT;                                          // MathUtil.avg -> Float
+        const float boost = exp2f((l2In - __log2f(avgB)) * (1.0f / 0.6f));     // calcBoost
+        float temporal = 0.f, spectral = 0.f;
+        if (useT) {
+          const double q = win.t2 * invW;
+          const double var = q - mT * mT;
+          const float cr = accT[k] - (float)mT * rhoT;
+          temporal = (var > 1e-13 * q) ? (cr * cT) * rsqrtf((float)var) : qnan;
         }
-        const int64_t tl = g - fStart;
-        const int64_t nValid = (fEnd - fStart) - p.tailExtra - W + 1;
-        float sim = qnan, boost = qnan;
-        if (g < p.usedFrames && tl < nValid) {
-          const double mT = win.t1 * invW;
-          const float avgB = (float)mT;                              // MathUtil.avg -> Float
-          boost = expf((lnIn - logf(avgB)) / 0.6f);                  // calcBoost
-          if (boost <= p.maxBoost) {
-            float temporal = 0.f, spectral = 0.f;
-            if (useT) {
-              const double q = win.t2 * invW;
-              const double var = q - mT * mT;
-              const float cr = accT[k] - (float)mT * rhoT;
-              temporal = (var > 1e-13 * q) ? (cr * cT) / sqrtf((float)var) : qnan;
-            }
-            if (useS) {
-              const double mS = win.s1 * invNS;
-              const double q = win.s2 * invNS;
-              const double var = q - mS * mS;
-              const float cr = (acc[k].x + acc[k].y) - (float)mS * rhoS;
-              spectral = (var > 1e-13 * q) ? (cr * cS) / sqrtf((float)var) : qnan;
-            }
-            sim = __fadd_rn(__fmul_rn(temporal, p.weight), __fmul_rn(spectral, __fsub_rn(1.0f, p.weight)));
-          } else {
-            sim = 0.f;
-          }
-          if (sim == sim) {
-            const unsigned long long key = ((unsigned long long)float_order_key(sim) << 32) |
-                                           (unsigned long long)(0xffffffffu - (uint32_t)tl);
-            if (key > best) { best = key; bestFile = f; }
-          }
+        if (useS) {
+          const double mS = win.s1 * invNS;
+          const double q = win.s2 * invNS;
+          const double var = q - mS * mS;
+          const float cr = (acc[k].x + acc[k].y) - (float)mS * rhoS;
+          spectral = (var > 1e-13 * q) ? (cr * cS) * rsqrtf((float)var) : qnan;
         }
-        simv[k] = sim;
+        const float blend = __fadd_rn(__fmul_rn(temporal, p.weight), __fmul_rn(spectral, __fsub_rn(1.0f, p.weight)));
+        simv[k] = boost <= p.maxBoost ? blend : 0.f;
         boostv[k] = boost;
         if (k < kR - 1) {  // slide the window by one frame
           const int e = o + k;
@@ -431,6 +431,49 @@ __global__ void __launch_bounds__(384, 1) k_corr(const CorrParams p) {
           win.t2 += bn * bn - bo * bo;
           win.s1 += (double)fn.x - (double)fo.x;
           win.s2 += (double)fn.y - (double)fo.y;
+        }
+      }
+      // pass B: which offsets exist (window inside its file), per-file maximum (first occurrence)
+      unsigned long long best = 0ull;
+      int bestFile = -1;
+      bool straddle = false;
+      if (g0 + kR <= fEnd || f + 1 >= p.numFiles) {
+        // common case: all 14 offsets belong to one file
+        const int64_t lim = fEnd - p.tailExtra - W + 1 - g0;          // offsets k < lim are evaluated
+        const int nOk = lim < 0 ? 0 : (lim > kR ? kR : (int)lim);
+        const uint32_t tl0 = (uint32_t)(g0 - fStart);
+#pragma unroll
+        for (int k = 0; k < kR; k++) {
+          if (k >= nOk) { simv[k] = qnan; boostv[k] = qnan; }
+          else if (simv[k] == simv[k]) {
+            const unsigned long long key = ((unsigned long long)float_order_key(simv[k]) << 32) |
+                                           (unsigned long long)(0xffffffffu - (tl0 + (uint32_t)k));
+            if (key > best) { best = key; bestFile = f; }
+          }
+        }
+      } else {
+        for (int k = 0; k < kR; k++) {
+          const int64_t g = g0 + k;
+          while (g >= fEnd && f + 1 < p.numFiles) {
+            if (best != 0ull && p.fileMax) { atomicMax(p.fileMax + bestFile, best); straddle = true; }
+            best = 0ull;
+            f++;
+            fStart = fEnd;
+            fEnd = p.fileStart[f + 1];
+          }
+          const int64_t tl = g - fStart;
+          const int64_t nValid = (fEnd - fStart) - p.tailExtra - W + 1;
+          float sv = qnan, bv = qnan;
+#pragma unroll
+          for (int kk = 0; kk < kR; kk++) if (kk == k) { sv = simv[kk]; bv = boostv[kk]; }
+          if (!(g < p.usedFrames && tl < nValid)) { sv = qnan; bv = qnan; }
+          else if (sv == sv) {
+            const unsigned long long key = ((unsigned long long)float_order_key(sv) << 32) |
+                                           (unsigned long long)(0xffffffffu - (uint32_t)tl);
+            if (key > best) { best = key; bestFile = f; }
+          }
+#pragma unroll
+          for (int kk = 0; kk < kR; kk++) if (kk == k) { simv[kk] = sv; boostv[kk] = bv; }
         }
       }
       __syncwarp();

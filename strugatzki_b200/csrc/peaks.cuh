@@ -186,6 +186,20 @@ inline int measure_peak(sgz_ctx *ctx, int which, double *value) {
       double flops = 2.0 * (double)blocks * threads * iters * 64.0;
       if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
     }
+  } else if (which >= 10 && which < 20) {
+    // FFMA2 outer product with (which - 9) warps per scheduler (one CTA per SM): issue-interval probe
+    const int warpsPerSmsp = which - 9;
+    const int iters = 8192;
+    for (int rep = 0; rep < 4; rep++) {
+      SGZ_CUDA(cudaEventRecord(e0, st));
+      k_peak_ffma2_outer<<<ctx->smCount, 128 * warpsPerSmsp, 0, st>>>(sink.p, iters, 0.5f);
+      SGZ_LAUNCH_CHECK(ctx);
+      SGZ_CUDA(cudaEventRecord(e1, st));
+      SGZ_CUDA(cudaEventSynchronize(e1));
+      SGZ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      double flops = 2.0 * (double)ctx->smCount * 128 * warpsPerSmsp * iters * 64.0;
+      if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
   } else if (which == 3) {
     const size_t n = (size_t)1 << 27;  // 2 GiB per buffer as float4
     DevBuf<float4> a, b;
