@@ -216,8 +216,10 @@ int sgz_corr_curve(sgz_corr *job, int32_t which, int32_t file, int64_t first, in
  *   sgz_corr_result(job, ...)                   identical on every rank; Match.file is GLOBAL
  */
 typedef struct {
-  float   maxSim;       /* Float.compare-maximum of the file's punch-in curve (first offset) */
+  float   maxSim;       /* largest non-NaN sim of the file's punch-in curve (-inf if none)   */
   int32_t numOffsets;   /* evaluated punch-in offsets of the file                            */
+  float   maxSimOut;    /* same for the punch-out curve (punch-out mode only, else -inf)     */
+  int32_t _pad;
 } sgz_file_summary;
 
 typedef struct {

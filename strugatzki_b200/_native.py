@@ -81,7 +81,7 @@ class SelfGeometry(C.Structure):
 
 
 class FileSummary(C.Structure):
-    _fields_ = [("maxSim", C.c_float), ("numOffsets", C.c_int32)]
+    _fields_ = [("maxSim", C.c_float), ("numOffsets", C.c_int32), ("maxSimOut", C.c_float), ("_pad", C.c_int32)]
 
 
 class Record(C.Structure):
@@ -89,7 +89,8 @@ class Record(C.Structure):
                 ("sim", C.c_float), ("boostIn", C.c_float), ("boostOut", C.c_float), ("aux", C.c_int32)]
 
 
-SUMMARY_DTYPE = np.dtype([("maxSim", np.float32), ("numOffsets", np.int32)])
+SUMMARY_DTYPE = np.dtype([("maxSim", np.float32), ("numOffsets", np.int32), ("maxSimOut", np.float32),
+                          ("_pad", np.int32)])
 RECORD_DTYPE = np.dtype([("file", np.int32), ("kind", np.int32), ("piOff", np.int32), ("poOff", np.int32),
                          ("sim", np.float32), ("boostIn", np.float32), ("boostOut", np.float32),
                          ("aux", np.int32)])

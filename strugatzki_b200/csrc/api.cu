@@ -387,13 +387,16 @@ int sgz_corr_scan(sgz_corr *job) {
   if (job->hasOut) {
     SGZ_TRY(job->simOut.alloc(n));
     SGZ_TRY(job->boostOut.alloc(n));
+    SGZ_TRY(job->dFileMaxOut.alloc((size_t)std::max(db->numFiles(), 1)));
   }
   SGZ_TRY(ctx->begin_call());
   SGZ_CUDA(cudaMemsetAsync(job->dFileMax.p, 0, job->dFileMax.n * sizeof(unsigned long long), ctx->stream));
+  if (job->hasOut)
+    SGZ_CUDA(cudaMemsetAsync(job->dFileMaxOut.p, 0, job->dFileMaxOut.n * sizeof(unsigned long long), ctx->stream));
   if (db->usedFrames > 0) {
     SGZ_TRY(run_scan_one(job, job->qin, job->hasOut ? job->minPunchF : 0, job->simIn.p, job->boostIn.p,
                          job->dFileMax.p));
-    if (job->hasOut) SGZ_TRY(run_scan_one(job, job->qout, 0, job->simOut.p, job->boostOut.p, nullptr));
+    if (job->hasOut) SGZ_TRY(run_scan_one(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p));
   }
   SGZ_TRY(ctx->end_call());
   job->scanMs = ctx->lastMs;
@@ -424,11 +427,19 @@ int sgz_corr_local_summary(sgz_corr *job, sgz_file_summary *out, int32_t cap, in
                              job->ctx->stream));
     SGZ_CUDA(cudaStreamSynchronize(job->ctx->stream));
   }
+  std::vector<unsigned long long> keysOut((size_t)std::max(nf, 1), 0ull);
+  if (nf > 0 && job->hasOut) {
+    SGZ_CUDA(cudaMemcpyAsync(keysOut.data(), job->dFileMaxOut.p, nf * sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, job->ctx->stream));
+    SGZ_CUDA(cudaStreamSynchronize(job->ctx->stream));
+  }
   const int tail = job->hasOut ? job->minPunchF : 0;
   for (int f = 0; f < nf; f++) {
     int64_t nv = (db->fileStart[f + 1] - db->fileStart[f]) - tail - job->qin.W + 1;
     out[f].numOffsets = (int32_t)std::max<int64_t>(nv, 0);
     out[f].maxSim = keys[f] ? float_from_order_key((uint32_t)(keys[f] >> 32)) : -INFINITY;
+    out[f].maxSimOut = keysOut[f] ? float_from_order_key((uint32_t)(keysOut[f] >> 32)) : -INFINITY;
+    out[f]._pad = 0;
   }
   return SGZ_OK;
 }

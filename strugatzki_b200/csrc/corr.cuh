@@ -26,7 +26,7 @@ struct sgz_corr {
   int64_t numTiles = 0;
   int64_t numOffsets = 0;
   DevBuf<float> simIn, boostIn, simOut, boostOut;
-  DevBuf<unsigned long long> dFileMax;
+  DevBuf<unsigned long long> dFileMax, dFileMaxOut;
   bool scanned = false;
 
   // global (all ranks) view

@@ -37,7 +37,7 @@ def test_every_declared_symbol_is_exported():
 def test_struct_layouts_match_header():
     # sizes the Scala/JNI or ctypes side relies on
     assert C.sizeof(N.Match) == 32 and C.sizeof(N.Break) == 16 and C.sizeof(N.Record) == 32
-    assert C.sizeof(N.FileSummary) == 8 and C.sizeof(N.SelfGeometry) == 24
+    assert C.sizeof(N.FileSummary) == 16 and C.sizeof(N.SelfGeometry) == 24
     assert C.sizeof(N.CorrConfig) == 96 and C.sizeof(N.SegmConfig) == 56
 
 

@@ -1,0 +1,77 @@
+"""Punch-in + punch-out search (FeatureCorrelationImpl.scala:250-393) against the oracle."""
+import numpy as np
+import pytest
+
+from util import N, O, STEP, assert_matches_equal, assert_sims_close, build_db, corr_cfgs, make_db, make_input, synth
+
+pytestmark = pytest.mark.gpu
+
+W = 172
+
+
+def planted_db(n_files=14, n_frames=4200, pairs=((2, 500, 900), (5, 100, 260), (5, 3000, 3500), (9, 1500, 2100),
+                                                  (12, 2000, 2300))):
+    files, norm = make_db(n_files, n_frames)
+    inp = make_input(900)
+    for k, (f, a, b) in enumerate(pairs):
+        files[f][a:a + W] = synth.plant(inp[:W], 31, 2 * k)
+        files[f][b:b + W] = synth.plant(inp[345:345 + W], 31, 2 * k + 1)
+    return files, norm, inp
+
+
+def test_out_curve_matches_oracle(ctx):
+    from strugatzki_b200 import engine
+    files, norm, inp = planted_db(3, 2500, ((1, 400, 800),))
+    op, nc = corr_cfgs(inp, norm, punch_out=(345 * STEP, (345 + W) * STEP), min_punch=86 * STEP, max_punch=689 * STEP,
+                       w_out=0.3, num_matches=3)
+    db = build_db(ctx, files, norm)
+    job = engine.CorrelationJob(db, nc, inp)
+    job.scan()
+    for i, f in enumerate(files):
+        # loop A range: N - minPunch - W_in + 1 offsets; loop B curve: every frame with a full window
+        want_in, _ = O.corr_curve(op, f, 0, 0)
+        n_in = f.shape[0] - 86 - W + 1
+        sim, _ = job.curve(i, 0, 0, n_in)
+        assert_sims_close(sim, want_in[:n_in], what="in")
+        want_out, want_bo = O.corr_curve(op, f, 1, 0)
+        n_out = f.shape[0] - W + 1
+        so, bo = job.curve(i, 1, 0, n_out)
+        assert_sims_close(so, want_out, what="out")
+        assert_sims_close(bo, want_bo, rel=1e-5, abs_tol=0, what="boost out")
+    assert job.num_offsets == O.corr_num_offsets(op, [f.shape[0] for f in files])
+
+
+@pytest.mark.parametrize("num_matches,num_per_file,min_spacing,min_punch,max_punch", [
+    (20, 2, 22050, 86, 689), (4, 1, 0, 86, 689), (6, 3, 44100, 40, 300), (30, 5, 0, 86, 689), (2, 2, 22050, 200, 450),
+    (50, 1, 22050, 86, 689),
+])
+def test_punch_out_search_matches_oracle(ctx, num_matches, num_per_file, min_spacing, min_punch, max_punch):
+    from strugatzki_b200 import engine
+    files, norm, inp = planted_db()
+    op, nc = corr_cfgs(inp, norm, punch_out=(345 * STEP, (345 + W) * STEP), min_punch=min_punch * STEP,
+                       max_punch=max_punch * STEP, num_matches=num_matches, num_per_file=num_per_file,
+                       min_spacing=min_spacing)
+    db = build_db(ctx, files, norm)
+    got = engine.CorrelationJob(db, nc, inp).run()
+    want = O.corr_search(op, files)
+    assert_matches_equal(got, want)
+    assert (got[0]["file"], got[0]["start"], got[0]["stop"]) in {(2, 500 * STEP, 900 * STEP), (5, 100 * STEP, 260 * STEP),
+                                                                 (5, 3000 * STEP, 3500 * STEP), (9, 1500 * STEP, 2100 * STEP),
+                                                                 (12, 2000 * STEP, 2300 * STEP)} or min_punch > 160
+
+
+def test_punch_out_short_files_and_many_rounds(ctx):
+    """files shorter than minPunch + windows contribute nothing; > 64 files exercises several full rounds"""
+    from strugatzki_b200 import engine
+    lens = [900 + 37 * (i % 11) for i in range(90)]
+    lens[3], lens[40], lens[77] = 120, 300, 430
+    files, norm = make_db(90, lens)
+    inp = make_input(900)
+    for k, (f, a, b) in enumerate(((10, 100, 400), (50, 200, 350), (85, 50, 700))):
+        files[f][a:a + W] = synth.plant(inp[:W], 33, 2 * k)
+        files[f][b:b + W] = synth.plant(inp[345:345 + W], 33, 2 * k + 1)
+    op, nc = corr_cfgs(inp, norm, punch_out=(345 * STEP, (345 + W) * STEP), min_punch=86 * STEP, max_punch=689 * STEP,
+                       num_matches=12, num_per_file=2, min_spacing=22050)
+    db = build_db(ctx, files, norm)
+    got = engine.CorrelationJob(db, nc, inp).run()
+    assert_matches_equal(got, O.corr_search(op, files))
