@@ -326,7 +326,7 @@ def run_e2e(args, torch, device, ctx, engine, N, synth, rank, files, mu, sigma, 
         db2 = engine.Database(ctx, 14, norm)
         db2.reserve(e2e_files * FRAMES_PER_FILE, e2e_files)
         for i in range(e2e_files):
-            db2.add_file_ptr(base + i * bytes_per_file, FRAMES_PER_FILE, N.LAYOUT_PLANAR_LE)
+            db2.add_file_ptr(base + i * bytes_per_file, FRAMES_PER_FILE, N.LAYOUT_PLANAR_LE | N.LAYOUT_HOST_STABLE)
         db2.finalize()
         job2 = engine.CorrelationJob(db2, cfg, inp)
         if world > 1:

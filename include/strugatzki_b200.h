@@ -46,6 +46,10 @@ extern "C" {
 #define SGZ_LAYOUT_INTERLEAVED_LE 0  /* [frame][channel] float32 host order                    */
 #define SGZ_LAYOUT_INTERLEAVED_BE 1  /* [frame][channel] float32 big endian = raw AIFF SSND    */
 #define SGZ_LAYOUT_PLANAR_LE      2  /* [channel][frame] float32 = AudioFile.buffer layout     */
+/* OR-ed into the layout of sgz_db_add_file: the (pinned) host buffer stays valid and unchanged until
+ * sgz_db_finalize returns, so the call need not wait for the upload -> H2D copies of consecutive files
+ * pipeline with the prepare kernels. */
+#define SGZ_LAYOUT_HOST_STABLE    0x100
 
 typedef struct sgz_ctx  sgz_ctx;   /* one GPU + one stream */
 typedef struct sgz_db   sgz_db;    /* feature database resident in HBM */

@@ -18,6 +18,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_ABORTED, ERR_STATE, ERR_IO = 0, -1, -2, -3, -4, -5, -6
 LAYOUT_INTERLEAVED_LE, LAYOUT_INTERLEAVED_BE, LAYOUT_PLANAR_LE = 0, 1, 2
+LAYOUT_HOST_STABLE = 0x100   # OR-ed in: host buffer stays valid until finalize (pipelined upload)
 
 # every symbol include/strugatzki_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [

@@ -177,6 +177,8 @@ int sgz_db_add_file(sgz_db *db, const void *frames, int64_t nFrames, int32_t lay
   int64_t dst = 0;
   SGZ_TRY(db_begin_file(db, nFrames, &dst));
   SGZ_REQUIRE(frames || nFrames == 0, "frames is NULL");
+  const bool hostStable = (layout & SGZ_LAYOUT_HOST_STABLE) != 0;
+  layout &= 0xff;
   SGZ_REQUIRE(layout >= 0 && layout <= 2, "unknown layout %d", layout);
   if (nFrames > 0) {
     const size_t bytes = (size_t)nFrames * db->numCh * sizeof(float);
@@ -198,7 +200,7 @@ int sgz_db_add_file(sgz_db *db, const void *frames, int64_t nFrames, int32_t lay
     // the host buffer may be freed on return: pageable copies are staged by the driver before
     // cudaMemcpyAsync returns, pinned copies need the explicit wait
     cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, frames) == cudaSuccess && attr.type == cudaMemoryTypeHost)
+    if (!hostStable && cudaPointerGetAttributes(&attr, frames) == cudaSuccess && attr.type == cudaMemoryTypeHost)
       SGZ_CUDA(cudaEventSynchronize(db->stageFull[s]));
   }
   return db_commit_file(db, nFrames);

@@ -140,22 +140,37 @@ __global__ void k_replay_fill(const FillParams p) {
   float lastSim = 0.f;
   int lastPi = 0;
 
+  // 128 offsets per step: lane l tests offsets pos + 4l .. pos + 4l + 3 (one 16-byte load when aligned);
+  // the step is only taken apart when some offset can change the machine state.
   int64_t pos = 0;
   while (pos < nValid) {
-    const int64_t t = pos + lane;
-    const bool active = t < nValid;
-    const float s = active ? sim[t] : 0.f;
-    bool change = false;
-    if (active) {
-      const bool accept = hs || s > low;
-      const bool collapse = hasLast && ((t - (int64_t)lastPi - p.W) * p.step < p.minSpacing);
-      change = accept && (collapse ? (lastSim < s) : true);
+    const int64_t tb = pos + 4 * lane;
+    float sv[4];
+    if ((((fs + tb) & 3) == 0) && tb + 3 < nValid) {
+      const float4 v = *reinterpret_cast<const float4 *>(sim + tb);
+      sv[0] = v.x; sv[1] = v.y; sv[2] = v.z; sv[3] = v.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++) sv[j] = tb + j < nValid ? sim[tb + j] : 0.f;
     }
-    const unsigned mask = __ballot_sync(full, change);
-    if (mask == 0u) { pos += 32; continue; }
-    const int l = __ffs(mask) - 1;
-    const int64_t ts = pos + l;
-    const float ss = __shfl_sync(full, s, l);
+    int first = 1 << 30;
+#pragma unroll
+    for (int j = 3; j >= 0; j--) {
+      const int64_t t = tb + j;
+      if (t < nValid) {
+        const float s = sv[j];
+        const bool accept = hs || s > low;
+        const bool collapse = hasLast && ((t - (int64_t)lastPi - p.W) * p.step < p.minSpacing);
+        if (accept && (collapse ? (lastSim < s) : true)) first = 4 * lane + j;
+      }
+    }
+    const int hit = __reduce_min_sync(full, first);
+    if (hit == (1 << 30)) { pos += 128; continue; }
+    const int64_t ts = pos + hit;
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) if ((hit & 3) == j) ss = sv[j];
+    ss = __shfl_sync(full, ss, hit >> 2);
     if (lane == 0) {
       EntryRec m{ss, (int32_t)ts, (int32_t)(ts + p.W), boost[ts], 1.0f};
       mc.add(m);

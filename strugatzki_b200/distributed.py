@@ -7,17 +7,23 @@ reference's sequential coupling between files, `(allPrio.size, allPrio.last.sim)
 per selection round, moved with all_gather (NCCL over NVLink on GPUs, gloo in the CPU tests).  Every rank
 then runs the same deterministic replay (sgz_corr_merge), so all ranks end with the identical result and no
 broadcast is needed.
+
+The payloads are KBs, so the cost is collective LATENCY: every exchange is ONE fixed-capacity all_gather
+whose first 8 bytes carry the true length (a second, larger collective only when some rank overflowed; the
+capacity then grows for the following searches -- identically on every rank).
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import Dict, List
 
 import numpy as np
 
+_caps: Dict[str, int] = {}
 
-def allgather_bytes(arr: np.ndarray, device=None, group=None) -> np.ndarray:
-    """All-gather a 1-D structured/POD numpy array of rank-dependent length; returns the concatenation in
-    rank order.  Works with NCCL (device tensors) and gloo (CPU tensors)."""
+
+def allgather_bytes(arr: np.ndarray, device=None, group=None, tag: str = "default", initial_cap: int = 1 << 16):
+    """All-gather a 1-D structured/POD numpy array of rank-dependent length.  Returns (concatenation in rank
+    order, list of per-rank element counts).  Works with NCCL (device tensors) and gloo (CPU tensors)."""
     import torch
     import torch.distributed as dist
 
@@ -25,21 +31,27 @@ def allgather_bytes(arr: np.ndarray, device=None, group=None) -> np.ndarray:
     dtype = arr.dtype
     raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
     dev = device if device is not None else torch.device("cpu")
-    n = torch.tensor([raw.shape[0]], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    mx = max(max(sizes), 1)
-    buf = torch.zeros(mx, dtype=torch.uint8, device=dev)
-    if raw.shape[0]:
-        buf[:raw.shape[0]] = torch.from_numpy(raw.copy()).to(dev)
-    out = torch.zeros(world * mx, dtype=torch.uint8, device=dev)
-    dist.all_gather_into_tensor(out, buf, group=group) if dev.type == "cuda" else \
-        dist.all_gather(list(out.view(world, mx).unbind(0)), buf, group=group)
-    host = out.cpu().numpy().reshape(world, mx)
-    parts = [host[r, :sizes[r]] for r in range(world)]
+    cap = _caps.get(tag, initial_cap)
+    while True:
+        msg = np.zeros(8 + cap, np.uint8)
+        msg[:8] = np.frombuffer(np.int64(raw.shape[0]).tobytes(), np.uint8)
+        n_send = min(raw.shape[0], cap)
+        msg[8:8 + n_send] = raw[:n_send]
+        buf = torch.from_numpy(msg).to(dev)
+        out = torch.empty(world * (8 + cap), dtype=torch.uint8, device=dev)
+        if dev.type == "cuda":
+            dist.all_gather_into_tensor(out, buf, group=group)
+        else:
+            dist.all_gather(list(out.view(world, 8 + cap).unbind(0)), buf, group=group)
+        host = out.cpu().numpy().reshape(world, 8 + cap)
+        sizes = [int(np.frombuffer(host[r, :8].tobytes(), np.int64)[0]) for r in range(world)]
+        if max(sizes) <= cap:
+            break
+        cap = 2 * max(sizes)          # same decision on every rank
+        _caps[tag] = cap
+    parts = [host[r, 8:8 + sizes[r]] for r in range(world)]
     cat = np.concatenate(parts) if parts else np.zeros(0, np.uint8)
-    return cat.view(dtype)
+    return cat.view(dtype), [s // dtype.itemsize for s in sizes]
 
 
 def sharded_search(job, device=None, group=None) -> List[dict]:
@@ -49,16 +61,13 @@ def sharded_search(job, device=None, group=None) -> List[dict]:
 
     rank = dist.get_rank(group)
     job.scan()
-    local = job.local_summary()
-    counts = allgather_bytes(np.array([local.shape[0]], np.int64), device, group)
-    my_first = int(counts[:rank].sum())
-    everything = allgather_bytes(local, device, group)
-    job.set_global(everything, my_first)
+    everything, counts = allgather_bytes(job.local_summary(), device, group, tag="summary", initial_cap=1 << 17)
+    job.set_global(everything, int(sum(counts[:rank])))
     done = False
     rounds = 0
     while not done:
         recs = job.select()
-        all_recs = allgather_bytes(recs, device, group)
+        all_recs, _ = allgather_bytes(recs, device, group, tag="records", initial_cap=1 << 16)
         done = job.merge(all_recs)
         rounds += 1
         if rounds > 1_000_000:

@@ -22,9 +22,12 @@ def _worker(rank, world, port, out_q):
         mine = np.zeros(3 * rank, N.RECORD_DTYPE)
         mine["file"] = rank
         mine["piOff"] = np.arange(3 * rank)
-        got = allgather_bytes(mine)
-        assert got.dtype == N.RECORD_DTYPE and got.shape[0] == sum(3 * r for r in range(world))
-        assert list(got["file"]) == [r for r in range(world) for _ in range(3 * r)]
+        for _ in range(2):   # 1st call overflows the tiny capacity (two collectives), 2nd fits in one
+            got, cnt = allgather_bytes(mine, tag="t1", initial_cap=32)
+            assert got.dtype == N.RECORD_DTYPE and got.shape[0] == sum(3 * r for r in range(world))
+            assert cnt == [3 * r for r in range(world)]
+            assert list(got["file"]) == [r for r in range(world) for _ in range(3 * r)]
+            assert list(got["piOff"]) == [i for r in range(world) for i in range(3 * r)]
 
         # 2. protocol driver with a stand-in job: each rank owns (rank + 2) files whose maximum is known
         class FakeJob:
