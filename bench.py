@@ -272,6 +272,13 @@ def main():
     if rank == 0:
         scan_s = float(np.mean(scan_ms)) * 1e-3
         flops = n_off_local * FLOP_PER_OFFSET / scan_s / 1e12
+        traffic = None   # dram__bytes_read + dram__bytes_write of one k_corr launch, from the committed ncu capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k_corr_traffic.json")))
+            if int(tj["offsets_per_launch"]) == int(n_off_local):
+                traffic = float(tj["dram_bytes_per_launch"])
+        except Exception:
+            pass
         line = {
             "metric": "FeatureCorrelation DB frame-offsets/sec", "value": value, "unit": "offsets/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -283,7 +290,9 @@ def main():
                          "peak_source": "FP32 FFMA micro-benchmark run live by this process "
                                         "(MEASURED_PEAKS.json has no FP32 figure; SURVEY.md 8d)",
                          "algorithmic_flop_per_offset": FLOP_PER_OFFSET, "offsets_per_launch": n_off_local,
-                         "launch_ms": float(np.mean(scan_ms)), "traffic": None,
+                         "launch_ms": float(np.mean(scan_ms)), "traffic": traffic,
+                         "traffic_source": "profiles/r01_k_corr_traffic.json (ncu --set full of this command)",
+                         "algorithmic_bytes_per_launch": n_off_local * BYTES_PER_OFFSET,
                          "hbm": {"achieved": n_off_local * BYTES_PER_OFFSET / scan_s / 1e9, "peak": hbm_peak,
                                  "unit": "GB/s", "frac": n_off_local * BYTES_PER_OFFSET / scan_s / 1e9 / hbm_peak,
                                  "peak_source": hbm_src, "algorithmic_bytes_per_offset": BYTES_PER_OFFSET}},

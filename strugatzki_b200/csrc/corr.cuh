@@ -128,6 +128,10 @@ inline int pick_ntg(const sgz_ctx *ctx, int numPairs, int Wq) {
   // preferred: 128 consumers per CTA and TWO persistent CTAs per SM -- the CTAs drift out of phase, so one
   // CTA's epilogue / row prologue / stats wait overlaps the other's FFMA2 loop
   const size_t perSm = 228 * 1024, reserved = 1024;
+  if (const char *e = getenv("SGZ_CORR_NC")) {   // tuning override (developer knob)
+    const int nc = atoi(e);
+    if (nc >= 32 && nc <= 320 && nc % 32 == 0 && corr_smem_layout(nc, numPairs, Wq).total <= ctx->smemOptin) return nc;
+  }
   if (2 * (corr_smem_layout(128, numPairs, Wq).total + reserved) <= perSm) return 128;
   const int opts[5] = {256, 192, 128, 64, 32};
   for (int k = 0; k < 5; k++)
@@ -137,6 +141,7 @@ inline int pick_ntg(const sgz_ctx *ctx, int numPairs, int Wq) {
 
 inline int corr_ctas_per_sm(int ntg, int numPairs, int Wq) {
   const size_t perSm = 228 * 1024, reserved = 1024;
+  if (const char *e = getenv("SGZ_CORR_CTAS")) return atoi(e) == 2 ? 2 : 1;
   return (ntg <= 128 && 2 * (corr_smem_layout(ntg, numPairs, Wq).total + reserved) <= perSm) ? 2 : 1;
 }
 
