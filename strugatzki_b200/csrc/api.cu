@@ -352,6 +352,9 @@ int sgz_corr_create(sgz_db *db, const sgz_corr_config *cfg, const void *input, i
   if (rc == SGZ_OK) {
     int wq = std::max(job->qin.Wq, job->hasOut ? job->qout.Wq : 0);
     job->ntg = pick_ntg(job->ctx, db->numPairs, wq);
+    if (const char *e = getenv("SGZ_CORR_NSLOT")) job->nslot = atoi(e) == 2 ? 2 : 3;   // tuning override
+    if (job->ntg > 0 && corr_smem_layout(job->ntg, db->numPairs, wq, job->nslot).total > job->ctx->smemOptin) job->nslot = 2;
+    if (job->ntg > 0 && corr_smem_layout(job->ntg, db->numPairs, wq, job->nslot).total > job->ctx->smemOptin) job->ntg = 0;
     if (job->ntg == 0) {
       set_error("punch window of %d feature frames does not fit the shared-memory tile", wq);
       rc = SGZ_ERR_INVALID;

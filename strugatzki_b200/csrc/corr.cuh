@@ -23,6 +23,7 @@ struct sgz_corr {
   bool hasOut = false;
   PunchQuery qin, qout;
   int ntg = 128;
+  int nslot = 3;
   int64_t numTiles = 0;
   int64_t numOffsets = 0;
   DevBuf<float> simIn, boostIn, simOut, boostOut;
@@ -132,6 +133,9 @@ inline int pick_ntg(const sgz_ctx *ctx, int numPairs, int Wq) {
     const int nc = atoi(e);
     if (nc >= 32 && nc <= 320 && nc % 32 == 0 && corr_smem_layout(nc, numPairs, Wq).total <= ctx->smemOptin) return nc;
   }
+  // measured on B200 (600 x 51 680 frames, W = 172): 256 x 1 CTA/SM 10.2e9 offsets/s, 128 x 2 CTAs/SM 9.8e9,
+  // 192 x 1 8.7e9, 128 x 1 9.0e9, 96 x 2 7.6e9
+  if (corr_smem_layout(256, numPairs, Wq).total <= ctx->smemOptin) return 256;
   if (2 * (corr_smem_layout(128, numPairs, Wq).total + reserved) <= perSm) return 128;
   const int opts[5] = {256, 192, 128, 64, 32};
   for (int k = 0; k < 5; k++)
@@ -177,13 +181,14 @@ inline int run_scan_one(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim,
   p.boost = boost;
   p.fileMax = fileMax;
   p.numTiles = job->numTiles;
-  CorrSmemLayout L = corr_smem_layout(job->ntg, db->numPairs, q.Wq);
+  CorrSmemLayout L = corr_smem_layout(job->ntg, db->numPairs, q.Wq, job->nslot);
   sgz_ctx *ctx = job->ctx;
-  SGZ_CUDA(cudaFuncSetAttribute(k_corr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemOptin));
+  auto kern = job->nslot == 2 ? k_corr<2> : k_corr<3>;
+  SGZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemOptin));
   // persistent: one or two CTAs per SM, tiles are striped over the CTAs
   const int perSm = corr_ctas_per_sm(job->ntg, db->numPairs, q.Wq);
   const unsigned grid = (unsigned)std::min<int64_t>(job->numTiles, (int64_t)ctx->smCount * perSm);
-  k_corr<<<grid, job->ntg + 64, L.total, ctx->stream>>>(p);
+  kern<<<grid, job->ntg + 64, L.total, ctx->stream>>>(p);
   SGZ_LAUNCH_CHECK(ctx);
   return SGZ_OK;
 }

@@ -73,14 +73,14 @@ struct CorrSmemLayout {
 };
 
 // shared memory: [ring: kNSlot pair rows][taps][2 x stats{T0, F, CP, fileLoHi}][mbarriers]
-__host__ __device__ inline CorrSmemLayout corr_smem_layout(int nc, int numPairs, int Wq) {
+__host__ __device__ inline CorrSmemLayout corr_smem_layout(int nc, int numPairs, int Wq, int nslot = kNSlot) {
   CorrSmemLayout L;
   L.NC = nc;
   L.T = kR * nc;
   L.rowFrames = L.T + Wq;
   L.rowPitch = L.rowFrames + kRowPad;
   L.numChunks = (L.rowFrames + kR - 1) / kR;
-  size_t ring = (size_t)kNSlot * L.rowPitch * sizeof(float2);
+  size_t ring = (size_t)nslot * L.rowPitch * sizeof(float2);
   size_t taps = ((size_t)numPairs * Wq + kRowPad) * sizeof(float2);
   L.offTaps = ring;
   L.offStats = (L.offTaps + taps + 31) / 32 * 32;
@@ -191,18 +191,19 @@ struct D4 {
 };
 
 // blockDim.x = NC + 64: warps [0, NC/32) consumers, warp NC/32 = TMA issuer, warp NC/32+1 = stats.
+template <int NSLOT>
 __global__ void __launch_bounds__(384, 1) k_corr(const CorrParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int NC = (int)blockDim.x - 64;
   const int NCW = NC >> 5;
   const int Wq = p.Wq, W = p.W;
-  const CorrSmemLayout L = corr_smem_layout(NC, p.numPairs, Wq);
+  const CorrSmemLayout L = corr_smem_layout(NC, p.numPairs, Wq, NSLOT);
   const int T = L.T, rowFrames = L.rowFrames, rowPitch = L.rowPitch, numChunks = L.numChunks;
 
   float2 *ring = reinterpret_cast<float2 *>(smem);
   float2 *taps = reinterpret_cast<float2 *>(smem + L.offTaps);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.offBars);
-  uint64_t *full = bars, *empty = bars + kNSlot, *statsReady = bars + 2 * kNSlot, *statsFree = bars + 2 * kNSlot + 2;
+  uint64_t *full = bars, *empty = bars + NSLOT, *statsReady = bars + 2 * NSLOT, *statsFree = bars + 2 * NSLOT + 2;
   auto stats_T0 = [&](int b) { return reinterpret_cast<float *>(smem + L.offStats + b * L.statsBytes); };
   auto stats_F = [&](int b) { return reinterpret_cast<float2 *>(smem + L.offStats + b * L.statsBytes + L.t0Bytes); };
   auto stats_CP = [&](int b) {
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(384, 1) k_corr(const CorrParams p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < kNSlot; s++) {
+    for (int s = 0; s < NSLOT; s++) {
       mbar_init(full + s, 1);
       mbar_init(empty + s, NCW + 1);
     }
@@ -237,8 +238,8 @@ __global__ void __launch_bounds__(384, 1) k_corr(const CorrParams p) {
       for (int64_t tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
         const int64_t t0 = tile * T;
         for (int c = 0; c < p.numPairs; c++, rc++) {
-          const int slot = rc % kNSlot;
-          mbar_wait(empty + slot, ((rc / kNSlot) & 1) ^ 1);
+          const int slot = rc % NSLOT;
+          mbar_wait(empty + slot, ((rc / NSLOT) & 1) ^ 1);
           mbar_expect_tx(full + slot, rowBytes);
           bulk_g2s(ring + (size_t)slot * rowPitch, p.data + (int64_t)c * p.rowStride + t0, rowBytes, full + slot);
         }
@@ -265,8 +266,8 @@ __global__ void __launch_bounds__(384, 1) k_corr(const CorrParams p) {
       }
       const int nv = rowFrames >> 1;  // two frames (one LDS.128) per iteration; rowFrames is even
       for (int c = 0; c < p.numPairs; c++, rc++) {
-        const int slot = rc % kNSlot;
-        mbar_wait(full + slot, (rc / kNSlot) & 1);
+        const int slot = rc % NSLOT;
+        mbar_wait(full + slot, (rc / NSLOT) & 1);
         const float2 *row = ring + (size_t)slot * rowPitch;
         if (c == 0) {   // pair 0 = (loudness, first spectral channel)
           for (int v = lane; v < nv; v += 32) {
@@ -359,8 +360,8 @@ __global__ void __launch_bounds__(384, 1) k_corr(const CorrParams p) {
 #pragma unroll
       for (int r = 0; r < kR; r++) acc[r] = make_float2(0.f, 0.f);
       for (int c = 0; c < p.numPairs; c++, rc++) {
-        const int slot = rc % kNSlot;
-        mbar_wait(full + slot, (rc / kNSlot) & 1);
+        const int slot = rc % NSLOT;
+        mbar_wait(full + slot, (rc / NSLOT) & 1);
         conv_pair(acc, ring + (size_t)slot * rowPitch + o, taps + c * Wq, nSub);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + slot);
