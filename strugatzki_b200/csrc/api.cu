@@ -401,7 +401,14 @@ int sgz_corr_scan(sgz_corr *job) {
   if (db->usedFrames > 0) {
     SGZ_TRY(run_scan_one(job, job->qin, job->hasOut ? job->minPunchF : 0, job->simIn.p, job->boostIn.p,
                          job->dFileMax.p));
-    if (job->hasOut) SGZ_TRY(run_scan_one(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p));
+    if (job->hasOut) {
+      SGZ_TRY(run_scan_one(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p));
+      SGZ_TRY(job->rowMaxOut.alloc((size_t)db->usedFrames));
+      k_row_max_out<<<(unsigned)ceil_div<int64_t>(db->usedFrames, 256), 256, 0, ctx->stream>>>(
+          job->simOut.p, db->dFileStart.p, db->numFiles(), db->usedFrames, job->qin.W, job->qout.W, job->minPunchF,
+          job->maxPunchF, job->rowMaxOut.p);
+      SGZ_LAUNCH_CHECK(ctx);
+    }
   }
   SGZ_TRY(ctx->end_call());
   job->scanMs = ctx->lastMs;

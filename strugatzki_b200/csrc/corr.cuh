@@ -26,7 +26,7 @@ struct sgz_corr {
   int nslot = 3;
   int64_t numTiles = 0;
   int64_t numOffsets = 0;
-  DevBuf<float> simIn, boostIn, simOut, boostOut;
+  DevBuf<float> simIn, boostIn, simOut, boostOut, rowMaxOut;
   DevBuf<unsigned long long> dFileMax, dFileMaxOut;
   bool scanned = false;
 

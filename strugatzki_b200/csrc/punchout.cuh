@@ -24,7 +24,7 @@
 namespace sgz {
 
 struct FillPoParams {
-  const float *simIn, *boostIn, *simOut, *boostOut;
+  const float *simIn, *boostIn, *simOut, *boostOut, *rowMax;
   const int64_t *fileStart;
   const int32_t *files;
   int numJobs;
@@ -40,6 +40,31 @@ __host__ __device__ __forceinline__ int64_t i64min(int64_t a, int64_t b) { retur
 
 __device__ __forceinline__ float cell_sim(float inSim, float outSim) {
   return (float)sqrt((double)__fmul_rn(inSim, outSim));   // math.sqrt(inSim * outSim).toFloat, Float product
+}
+
+// rowMax[g] = max over the grid row of punch-in offset g of simOut (NaN ignored, -inf if the row has no cell).
+// cell_sim(in, out) is monotone in `out` for in > 0, so cell_sim(in, rowMax) is the exact row maximum: when it
+// cannot beat `low` (and the entry has no space) no cell of the row can be accepted -> the row is skipped.
+// This is the pruning the reference notes as missing (FeatureCorrelationImpl.scala:345-349), done exactly.
+__global__ void k_row_max_out(const float *__restrict__ simOut, const int64_t *__restrict__ fileStart, int numFiles,
+                              int64_t usedFrames, int Win, int Wout, int minPunchF, int maxPunchF,
+                              float *__restrict__ rowMax) {
+  const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= usedFrames) return;
+  int lo = 0, hi = numFiles;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (fileStart[mid] <= g) lo = mid; else hi = mid;
+  }
+  const int64_t fs = fileStart[lo], N = fileStart[lo + 1] - fs, pi = g - fs;
+  const int64_t nA = N - minPunchF - Win + 1;
+  float m = -INFINITY;
+  if (pi < nA) {
+    const int64_t p0 = pi + minPunchF, p1 = i64min(pi + maxPunchF, N - Wout);
+    const float *s = simOut + fs;
+    for (int64_t po = p0; po <= p1; po++) m = fmaxf(m, s[po]);
+  }
+  rowMax[g] = m;
 }
 
 __global__ void k_replay_fill_po(const FillPoParams p) {
@@ -69,7 +94,9 @@ __global__ void k_replay_fill_po(const FillPoParams p) {
     const int64_t r = pi + lane;
     const float in = r < nA ? p.simIn[fs + r] : 0.f;
     const int64_t cellsR = i64min(poMax - (r + p.minPunchF) + 1, (int64_t)span);
-    const bool gate = r < nA && cellsR > 0 && in > __fmul_rn(low, low);
+    bool gate = r < nA && cellsR > 0 && in > __fmul_rn(low, low);
+    // exact pruning: without space in the entry a row only matters if its best cell beats `low`
+    if (gate && !hs) gate = cell_sim(in, p.rowMax[fs + r]) > low;
     const unsigned rmask = __ballot_sync(full, gate);
     if (rmask == 0u) { pi += 32; continue; }
     const int rl = __ffs(rmask) - 1;
@@ -116,7 +143,7 @@ __global__ void k_replay_fill_po(const FillPoParams p) {
 }
 
 struct CandPoParams {
-  const float *simIn, *boostIn, *simOut, *boostOut;
+  const float *simIn, *boostIn, *simOut, *boostOut, *rowMax;
   const int64_t *fileStart;
   const int32_t *files;
   const float *thresholds;
@@ -166,7 +193,7 @@ __global__ void k_candidates_po(const CandPoParams p) {
   for (int64_t rbase = (int64_t)warp * 32; rbase < nA; rbase += (int64_t)nWarps * 32) {
     const int64_t r = rbase + lane;
     const float in = r < nA ? p.simIn[fs + r] : 0.f;
-    unsigned rmask = __ballot_sync(full, r < nA && in > thr2);
+    unsigned rmask = __ballot_sync(full, r < nA && in > thr2 && cell_sim(in, p.rowMax[fs + r]) > thr);
     while (rmask) {
       const int rl = __ffs(rmask) - 1;
       rmask &= rmask - 1;
@@ -215,6 +242,7 @@ inline int corr_select_punchout(sgz_corr *job, int32_t *nRecords) {
       SGZ_CUDA(cudaMemcpyAsync(job->dFiles.p, files.data(), nj * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
       FillPoParams fp{};
       fp.simIn = job->simIn.p; fp.boostIn = job->boostIn.p; fp.simOut = job->simOut.p; fp.boostOut = job->boostOut.p;
+      fp.rowMax = job->rowMaxOut.p;
       fp.fileStart = db->dFileStart.p; fp.files = job->dFiles.p; fp.numJobs = nj;
       fp.Win = job->qin.W; fp.Wout = job->qout.W; fp.minPunchF = job->minPunchF; fp.maxPunchF = job->maxPunchF;
       fp.numPerFile = npf; fp.maxEntrySz = m; fp.minSpacing = job->cfg.minSpacing; fp.step = job->step;
@@ -270,6 +298,7 @@ inline int corr_select_punchout(sgz_corr *job, int32_t *nRecords) {
         SGZ_CUDA(cudaMemsetAsync(job->dCounter.p, 0, sizeof(int), ctx->stream));
         CandPoParams cp{};
         cp.simIn = job->simIn.p; cp.boostIn = job->boostIn.p; cp.simOut = job->simOut.p; cp.boostOut = job->boostOut.p;
+        cp.rowMax = job->rowMaxOut.p;
         cp.fileStart = db->dFileStart.p; cp.files = job->dFiles.p; cp.thresholds = job->dThr.p; cp.numJobs = nj;
         cp.Win = job->qin.W; cp.Wout = job->qout.W; cp.minPunchF = job->minPunchF; cp.maxPunchF = job->maxPunchF;
         cp.fileBase = myLo; cp.out = job->dRecs.p; cp.cap = cap; cp.counter = job->dCounter.p;

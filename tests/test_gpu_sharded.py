@@ -1,0 +1,91 @@
+"""The sharded-search protocol on ONE GPU: two (or three) database shards driven through
+scan -> local_summary -> set_global -> (select -> records -> merge)* exactly like strugatzki_b200/distributed.py
+does across ranks, and compared with the single-database result.  (The real 2-GPU run is tools/multi_gpu_check.py.)"""
+import numpy as np
+import pytest
+
+from util import N, O, STEP, assert_matches_equal, corr_cfgs, make_input, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def drive(jobs):
+    for j in jobs:
+        j.scan()
+    sums = [j.local_summary() for j in jobs]
+    everything = np.concatenate(sums)
+    first = np.cumsum([0] + [s.shape[0] for s in sums])
+    for j, f0 in zip(jobs, first):
+        j.set_global(everything, int(f0))
+    done, rounds = False, 0
+    while not done:
+        recs = np.concatenate([j.select() for j in jobs])
+        flags = [j.merge(recs) for j in jobs]
+        assert len(set(flags)) == 1
+        done = flags[0]
+        rounds += 1
+        assert rounds < 1000
+    res = [j.result() for j in jobs]
+    assert all(r == res[0] for r in res), "replicated merge must give identical results on every shard"
+    return res[0], rounds
+
+
+@pytest.mark.parametrize("punch_out,num_matches,num_per_file,split", [
+    (False, 100, 1, (70, 140)), (False, 9, 3, (5, 100)), (True, 20, 2, (60, 150)), (True, 40, 1, (100,)),
+])
+def test_sharded_equals_single(ctx, punch_out, num_matches, num_per_file, split):
+    from strugatzki_b200 import engine
+    mu, sigma, floor0, norm = synth.default_profile(14)
+    n_files, frames = 200, 6000
+    inp = make_input(900)
+    rng = np.random.default_rng(11)
+    plants = [(int(rng.integers(0, n_files)), int(rng.integers(0, frames - 800))) for _ in range(15)]
+    po = (345 * STEP, 517 * STEP) if punch_out else None
+    _, cfg = corr_cfgs(inp, norm, punch_out=po, num_matches=num_matches, num_per_file=num_per_file, min_spacing=22050)
+
+    def build(lo, hi):
+        db = engine.Database(ctx, 14, norm)
+        for g in range(lo, hi):
+            db.add_synth(synth.BASE_SEED, 1 + g, frames, mu, sigma, float(floor0))
+        for k, (f, off) in enumerate(plants):
+            if lo <= f < hi:
+                db.patch(f - lo, off, synth.plant(inp[:172], 3, 2 * k))
+                db.patch(f - lo, off + 300, synth.plant(inp[345:517], 3, 2 * k + 1))
+        db.finalize()
+        return db
+
+    single = engine.CorrelationJob(build(0, n_files), cfg, inp).run()
+    bounds = (0,) + tuple(split) + (n_files,)
+    shards = [build(a, b) for a, b in zip(bounds, bounds[1:])]
+    jobs = [engine.CorrelationJob(s, cfg, inp) for s in shards]
+    sharded, rounds = drive(jobs)
+    assert sharded == single
+    assert rounds >= 2
+    found = {(m["file"], m["start"]) for m in sharded}
+    if not punch_out and num_matches >= 100:
+        assert all((f, off * STEP) in found for f, off in plants)   # every planted needle is recovered
+
+
+def test_search_is_idempotent_and_order_sensitive(ctx):
+    """same job run twice -> identical result; the DB order is part of the semantics (Q3): reversing it may change
+    which equal-rank matches survive, but never the best match"""
+    from strugatzki_b200 import engine
+    mu, sigma, floor0, norm = synth.default_profile(14)
+    inp = make_input(900)
+    files = [synth.synth_file(synth.BASE_SEED, 1 + i, 3000, mu, sigma, floor0) for i in range(20)]
+    files[7][500:672] = synth.plant(inp[:172], 9, 1)
+    _, cfg = corr_cfgs(inp, norm, num_matches=5, num_per_file=2)
+
+    def run(fs):
+        db = engine.Database(ctx, 14, norm)
+        for f in fs:
+            db.add_file(f)
+        db.finalize()
+        job = engine.CorrelationJob(db, cfg, inp)
+        a, b = job.run(), job.run()
+        assert a == b
+        return a
+
+    fwd, rev = run(files), run(files[::-1])
+    assert fwd[0]["file"] == 7 and rev[0]["file"] == 12 and fwd[0]["sim"] == rev[0]["sim"]
+    assert fwd[0]["start"] == rev[0]["start"] == 500 * STEP
