@@ -110,6 +110,9 @@ typedef struct {
   float   colorWarp, colorCeil;
   const int32_t *lut;                   /* NULL = GrayScale; else PsychoOptical-style LUT  */
   int32_t lutSize;                      /* (IntensityPalette is third-party: host passes it) */
+  int32_t precise;                      /* 0 = tiled FP32 Gram (sims within 1e-5 of the reference, grey within
+                                           1 LSB); 1 = per-cell FP64 replay of the reference's arithmetic
+                                           (bit-identical sims, pixel-identical image, ~30x slower) */
 } sgz_self_config;
 
 typedef struct {

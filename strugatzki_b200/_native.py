@@ -73,7 +73,8 @@ class SelfConfig(C.Structure):
     _fields_ = [("stepSize", C.c_int32), ("hasStart", C.c_int32), ("hasStop", C.c_int32),
                 ("spanStart", C.c_int64), ("spanStop", C.c_int64), ("corrLen", C.c_int64),
                 ("decimation", C.c_int32), ("temporalWeight", C.c_float), ("colorInv", C.c_int32),
-                ("colorWarp", C.c_float), ("colorCeil", C.c_float), ("lut", C.c_void_p), ("lutSize", C.c_int32)]
+                ("colorWarp", C.c_float), ("colorCeil", C.c_float), ("lut", C.c_void_p), ("lutSize", C.c_int32),
+                ("precise", C.c_int32)]
 
 
 class SelfGeometry(C.Structure):

@@ -5,6 +5,7 @@
 #include "db.cuh"
 #include "segm.cuh"
 #include "selfsim.cuh"
+#include "selfsim_fast.cuh"
 
 namespace sgz {
 
@@ -195,13 +196,60 @@ int sgz_self_run(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh, const 
   SGZ_TRY(dRgb.alloc((size_t)ext * ext));
   SGZ_CUDA(cudaMemsetAsync(dRgb.p, 0, (size_t)ext * ext * sizeof(int32_t), ctx->stream));
   std::vector<int2> tiles;
-  for (int a0 = rowBegin / kSelfTile * kSelfTile; a0 < rowEnd; a0 += kSelfTile)
-    for (int b0 = a0 / kSelfTile * kSelfTile; b0 < ext; b0 += kSelfTile) tiles.push_back(make_int2(a0, b0));
-  SGZ_TRY(dTiles.alloc(tiles.size()));
-  SGZ_CUDA(cudaMemcpyAsync(dTiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+  if (cfg->precise) {
+    for (int a0 = rowBegin / kSelfTile * kSelfTile; a0 < rowEnd; a0 += kSelfTile)
+      for (int b0 = a0 / kSelfTile * kSelfTile; b0 < ext; b0 += kSelfTile) tiles.push_back(make_int2(a0, b0));
+    SGZ_TRY(dTiles.alloc(tiles.size()));
+    SGZ_CUDA(cudaMemcpyAsync(dTiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+  }
   p.colBegin = rowBegin;
   p.colEnd = rowEnd;
   p.rgb = dRgb.p;
+  if (!cfg->precise) {
+    // ---- fast path: centred FP32 Gram tiles + FP64 closed-form epilogue (selfsim_fast.cuh) ----
+    const int64_t need = (int64_t)g.numCorrs - 1 + H;
+    DevBuf<double> dMeans;
+    DevBuf<double2> ws1, ws2;
+    SGZ_TRY(dMeans.alloc(2));
+    SGZ_CUDA(cudaMemsetAsync(dMeans.p, 0, 2 * sizeof(double), ctx->stream));
+    SGZ_TRY(ctx->begin_call());
+    k_self_means<<<ctx->smCount * 4, 256, 0, ctx->stream>>>(p.x1, p.stride1, need, numCh, dMeans.p);
+    SGZ_LAUNCH_CHECK(ctx);
+    double means[2];
+    SGZ_CUDA(cudaMemcpyAsync(means, dMeans.p, sizeof means, cudaMemcpyDeviceToHost, ctx->stream));
+    SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    SelfFastParams fp{};
+    fp.base = p;
+    fp.shiftT = (float)(means[0] / (double)need);
+    fp.shiftS = (float)(means[1] / ((double)need * (numCh - 1)));
+    fp.cross = frames2 != nullptr;
+    SGZ_TRY(ws1.alloc((size_t)2 * ext));
+    k_self_wsums<<<ceil_div(ext, 128), 128, 0, ctx->stream>>>(p.x1, p.stride1, numCh, H, g.decim, ext, fp.shiftT, fp.shiftS,
+                                                             ws1.p);
+    SGZ_LAUNCH_CHECK(ctx);
+    fp.ws1 = ws1.p;
+    fp.ws2 = ws1.p;
+    if (frames2) {
+      SGZ_TRY(ws2.alloc((size_t)2 * ext));
+      k_self_wsums<<<ceil_div(ext, 128), 128, 0, ctx->stream>>>(p.x2, p.stride2, numCh, H, g.decim, ext, fp.shiftT,
+                                                               fp.shiftS, ws2.p);
+      SGZ_LAUNCH_CHECK(ctx);
+      fp.ws2 = ws2.p;
+    }
+    std::vector<int2> gt;
+    for (int a0 = rowBegin / kGT * kGT; a0 < rowEnd; a0 += kGT)
+      for (int b0 = a0; b0 < ext; b0 += kGT) gt.push_back(make_int2(a0, b0));
+    SGZ_TRY(dTiles.alloc(gt.size()));
+    SGZ_CUDA(cudaMemcpyAsync(dTiles.p, gt.data(), gt.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    k_self_gram<<<(unsigned)gt.size(), 256, 0, ctx->stream>>>(fp, dTiles.p);
+    SGZ_LAUNCH_CHECK(ctx);
+    SGZ_TRY(ctx->end_call());
+    if (rgb) {
+      SGZ_CUDA(cudaMemcpyAsync(rgb, dRgb.p, (size_t)ext * ext * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return SGZ_OK;
+  }
   const size_t smem = (size_t)2 * numCh * (g.decim * (kSelfTile - 1) + H) * sizeof(float);
   SGZ_REQUIRE(smem <= ctx->smemOptin, "self-similarity tile needs %zu bytes of shared memory", smem);
   SGZ_CUDA(cudaFuncSetAttribute(k_self_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemOptin));
@@ -241,8 +289,26 @@ int sgz_self_cells(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh, cons
   SGZ_CUDA(cudaMemcpyAsync(dR.p, rightIdx, nCells * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
   p.leftIdx = dL.p; p.rightIdx = dR.p; p.nCells = nCells; p.simOut = dSim.p; p.rgbOut = dRgb.p;
   SGZ_TRY(ctx->begin_call());
-  k_self_cells<<<(unsigned)ceil_div<int64_t>(nCells, 128), 128, 0, ctx->stream>>>(p);
-  SGZ_LAUNCH_CHECK(ctx);
+  if (cfg->precise) {
+    k_self_cells<<<(unsigned)ceil_div<int64_t>(nCells, 128), 128, 0, ctx->stream>>>(p);
+    SGZ_LAUNCH_CHECK(ctx);
+  } else {
+    const int64_t need = (int64_t)g.numCorrs - 1 + H;
+    DevBuf<double> dMeans;
+    SGZ_TRY(dMeans.alloc(2));
+    SGZ_CUDA(cudaMemsetAsync(dMeans.p, 0, 2 * sizeof(double), ctx->stream));
+    k_self_means<<<ctx->smCount * 4, 256, 0, ctx->stream>>>(p.x1, p.stride1, need, numCh, dMeans.p);
+    SGZ_LAUNCH_CHECK(ctx);
+    double means[2];
+    SGZ_CUDA(cudaMemcpyAsync(means, dMeans.p, sizeof means, cudaMemcpyDeviceToHost, ctx->stream));
+    SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    SelfFastParams fp{};
+    fp.base = p;
+    fp.shiftT = (float)(means[0] / (double)need);
+    fp.shiftS = (float)(means[1] / ((double)need * (numCh - 1)));
+    k_self_cells_fast<<<(unsigned)ceil_div<int64_t>(nCells, 128), 128, 0, ctx->stream>>>(fp);
+    SGZ_LAUNCH_CHECK(ctx);
+  }
   SGZ_TRY(ctx->end_call());
   if (sim) SGZ_CUDA(cudaMemcpyAsync(sim, dSim.p, nCells * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   if (rgb) SGZ_CUDA(cudaMemcpyAsync(rgb, dRgb.p, nCells * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));

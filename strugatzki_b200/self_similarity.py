@@ -22,6 +22,9 @@ from .io import FeatureExtractionConfig, Span, read_aiff, read_norm_file
 from .processor import Aborted, ProcessorFactory, ProcessorImpl
 
 verbose = False
+# Engine knob without counterpart in the reference Config: False = tiled FP32 Gram kernel (sims within 1e-5 of
+# the reference, grey levels within 1 LSB), True = per-cell FP64 replay (pixel-identical image, ~30x slower).
+precise = False
 
 GrayScale = "gray"
 PsychoOptical = "psycho"
@@ -129,7 +132,8 @@ def write_png(path: str, rgb: np.ndarray) -> None:
 def native_config(c: Config, step_size: int, lut: Optional[np.ndarray]) -> N.SelfConfig:
     return N.SelfConfig(step_size, int(c.span.has_start), int(c.span.has_stop), c.span.start or 0, c.span.stop or 0,
                         c.corrLen, c.decimation, c.temporalWeight, int(c.colorInv), c.colorWarp, c.colorCeil,
-                        None if lut is None else lut.ctypes.data, 0 if lut is None else int(lut.shape[0]))
+                        None if lut is None else lut.ctypes.data, 0 if lut is None else int(lut.shape[0]),
+                        int(bool(precise)))
 
 
 class SelfSimilarityImpl(ProcessorImpl):

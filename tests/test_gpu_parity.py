@@ -184,7 +184,7 @@ def test_selfsimilarity_image_identical(ctx, decim, weight, warp, ceil, inv, cro
     op = O.SelfParams(step_size=STEP, corr_len=20480, decimation=decim, temporal_weight=weight, norm=norm,
                       color_inv=inv, color_warp=warp, color_ceil=ceil)
     want = O.self_image(op, f1, f2)
-    cfg = N.SelfConfig(STEP, 0, 0, 0, 0, 20480, decim, weight, int(inv), warp, ceil, None, 0)
+    cfg = N.SelfConfig(STEP, 0, 0, 0, 0, 20480, decim, weight, int(inv), warp, ceil, None, 0, 1)   # precise = 1
     got, g = engine.self_run(ctx, cfg, f1, f2, norm)
     assert got.shape == want.shape and g["imgExt"] == want.shape[0]
     assert np.array_equal(got, want)
@@ -195,6 +195,34 @@ def test_selfsimilarity_image_identical(ctx, decim, weight, warp, ceil, inv, cro
     sim, rgb = engine.self_cells(ctx, cfg, f1, f2, l, r, norm)
     wsim, wrgb = O.self_cells(op, f1, f2, l, r)
     assert np.array_equal(sim.view(np.uint32), wsim.view(np.uint32)) and np.array_equal(rgb, wrgb)
+
+
+@pytest.mark.parametrize("frames,corr_len,decim,weight,warp,inv,cross", [
+    (900, 44100, 1, 0.5, 1.0, False, False), (1500, 20480, 3, 0.3, 1.0, True, False), (700, 44100, 2, 1.0, 0.5, False, True),
+    (650, 10240, 1, 0.0, 1.0, False, False),
+])
+def test_selfsimilarity_fast_gram_within_tolerance(ctx, frames, corr_len, decim, weight, warp, inv, cross):
+    """default (fast) path: FP32 Gram tiles + FP64 closed form: sims within 1e-5 relative, grey level within 1 LSB"""
+    from strugatzki_b200 import engine
+    f1, _ = synth.regime_file(synth.BASE_SEED, 16, frames, 14, 6)
+    f2 = synth.regime_file(synth.BASE_SEED, 17, frames - 30, 14, 5)[0] if cross else None
+    _, _, _, norm = synth.default_profile(14)
+    op = O.SelfParams(step_size=STEP, corr_len=corr_len, decimation=decim, temporal_weight=weight, norm=norm,
+                      color_inv=inv, color_warp=warp)
+    want = O.self_image(op, f1, f2)
+    cfg = N.SelfConfig(STEP, 0, 0, 0, 0, corr_len, decim, weight, int(inv), warp, 1.0, None, 0, 0)   # precise = 0
+    got, g = engine.self_run(ctx, cfg, f1, f2, norm)
+    assert got.shape == want.shape and g["imgExt"] == want.shape[0] > 128      # several 128 x 128 tiles
+    assert np.array_equal(got, got[::-1, ::-1].T)                              # mirrored like the reference
+    dg = np.abs((got & 0xFF).astype(np.int64) - (want & 0xFF).astype(np.int64))
+    assert dg.max() <= 1, f"grey level differs by {dg.max()}"
+    assert (dg > 0).mean() < 0.01                                              # rounding-boundary flips only
+    rng = np.random.default_rng(3)
+    l = rng.integers(0, g["imgExt"], 4000)
+    r = rng.integers(0, g["imgExt"], 4000)
+    sim, _ = engine.self_cells(ctx, cfg, f1, f2, l, r, norm)
+    wsim, _ = O.self_cells(op, f1, f2, l, r)
+    assert_sims_close(sim, wsim, rel=1e-5, abs_tol=2e-6, what="selfsim cell")
 
 
 def test_measured_peaks_are_plausible(ctx):
