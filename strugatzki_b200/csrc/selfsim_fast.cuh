@@ -61,31 +61,43 @@ __global__ void k_self_wsums(const float *__restrict__ x, int64_t stride, int nu
   ws[imgExt + a] = make_double2(s, q);
 }
 
-// gathers one k-chunk of the Hankel operand: element (kk, i) = x[c][decim*(t0+i) + h] - shift, k = k0 + kk = c*H + h.
-// 16 x 128 elements, 256 threads, 8 per thread; split in a register stage (global loads in flight during the
-// FFMA2 loop of the current chunk) and a shared-memory store.
-__device__ __forceinline__ void gram_fetch(float (&r)[8], const float *__restrict__ x, int64_t stride, int decim, int t0,
-                                           int imgExt, int c0, int H, int k0, int K, float shift, int tid) {
+// Gather of the Hankel operand: thread t always fetches row i = t & 127 of the tile and the k values
+// (t >> 7), (t >> 7) + 2, (t >> 7) + 4, ... of the group -- 8 per 16-wide chunk.  k = c*H + h walks through the
+// planar feature rows, so the thread keeps a cursor (pointer, h, k) and steps it: one load, one subtract and a few
+// integer ops per element, no division, no 64-bit index arithmetic.
+struct GramCursor {
+  const float *ptr;   // &x[c][decim*a + h]
+  int64_t wrap;       // stride - H : jump to the next channel row when h wraps
+  int h, k, H, K;
+  bool rowOk;
+  float shift;
+};
+__device__ __forceinline__ GramCursor gram_cursor(const float *__restrict__ x, int64_t stride, int decim, int a, int imgExt,
+                                                  int c0, int H, int K, float shift, int tid) {
+  GramCursor c;
+  c.H = H; c.K = K; c.shift = shift;
+  c.rowOk = a < imgExt;
+  c.k = tid >> 7;
+  int cc = c.k / H;                 // once per group (H may be 1)
+  c.h = c.k - cc * H;
+  c.ptr = x + (int64_t)(c0 + cc) * stride + (int64_t)decim * (c.rowOk ? a : 0) + c.h;
+  c.wrap = stride - H;
+  return c;
+}
+__device__ __forceinline__ void gram_fetch(float (&r)[8], GramCursor &c) {
 #pragma unroll
   for (int e = 0; e < 8; e++) {
-    const int idx = tid + 256 * e;        // 0..2047
-    const int kk = idx >> 7, i = idx & 127;
-    const int k = k0 + kk;
     float v = 0.f;
-    const int a = t0 + i;
-    if (k < K && a < imgExt) {
-      const int c = k / H, h = k - c * H;
-      v = __fsub_rn(x[(int64_t)(c0 + c) * stride + (int64_t)decim * a + h], shift);
-    }
+    if (c.rowOk && c.k < c.K) v = __fsub_rn(*c.ptr, c.shift);
     r[e] = v;
+    c.k += 2; c.h += 2; c.ptr += 2;
+    if (c.h >= c.H) { c.h -= c.H; c.ptr += c.wrap; }
+    if (c.h >= c.H) { c.h -= c.H; c.ptr += c.wrap; }   // H == 1
   }
 }
 __device__ __forceinline__ void gram_store(float *dst, const float (&r)[8], int tid) {
 #pragma unroll
-  for (int e = 0; e < 8; e++) {
-    const int idx = tid + 256 * e;
-    dst[(idx >> 7) * kGP + (idx & 127)] = r[e];
-  }
+  for (int e = 0; e < 8; e++) dst[((tid >> 7) + 2 * e) * kGP + (tid & 127)] = r[e];
 }
 
 // acc[i][j] (j = column pair) += A-frag x B-frag over one group
@@ -98,18 +110,20 @@ __device__ __forceinline__ void gram_group(float2 (&acc)[8][4], const SelfFastPa
   for (int i = 0; i < 8; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j] = make_float2(0.f, 0.f);
+  GramCursor ca = gram_cursor(b.x1, b.stride1, b.decim, ta + (tid & 127), b.imgExt, c0, b.H, K, shift, tid);
+  GramCursor cb = gram_cursor(b.x2, b.stride2, b.decim, tb + (tid & 127), b.imgExt, c0, b.H, K, shift, tid);
   float ra[8], rb[8];
-  gram_fetch(ra, b.x1, b.stride1, b.decim, ta, b.imgExt, c0, b.H, 0, K, shift, tid);
-  gram_fetch(rb, b.x2, b.stride2, b.decim, tb, b.imgExt, c0, b.H, 0, K, shift, tid);
+  gram_fetch(ra, ca);
+  gram_fetch(rb, cb);
   gram_store(sA, ra, tid);
   gram_store(sB, rb, tid);
   __syncthreads();
   for (int ch = 0; ch < nChunks; ch++) {
-    float *cA = sA + (ch & 1) * kGK * kGP, *cB = sB + (ch & 1) * kGK * kGP;
+    const float *cA = sA + (ch & 1) * kGK * kGP, *cB = sB + (ch & 1) * kGK * kGP;
     const bool more = ch + 1 < nChunks;
     if (more) {   // global loads of the next chunk stay in flight during this chunk's FFMA2 loop
-      gram_fetch(ra, b.x1, b.stride1, b.decim, ta, b.imgExt, c0, b.H, (ch + 1) * kGK, K, shift, tid);
-      gram_fetch(rb, b.x2, b.stride2, b.decim, tb, b.imgExt, c0, b.H, (ch + 1) * kGK, K, shift, tid);
+      gram_fetch(ra, ca);
+      gram_fetch(rb, cb);
     }
 #pragma unroll
     for (int kk = 0; kk < kGK; kk++) {
@@ -137,11 +151,13 @@ __device__ __forceinline__ void gram_group(float2 (&acc)[8][4], const SelfFastPa
 }
 
 __device__ __forceinline__ float gram_coeff(float G, double2 wa, double2 wb, double N) {
+  // N arrives as 1 / (4 N): no FP64 division here; the one division is FP32 (num and den are already well
+  // conditioned after centring)
   const double S = wa.x + wb.x;
-  const double T = S * S / (4.0 * N);
+  const double T = S * S * N;
   const double den = 0.5 * (wa.y + wb.y) - T;
   const double num = (double)G - T;
-  return (float)(num / den);   // 0/0 -> NaN like the reference (constant windows)
+  return __fdiv_rn((float)num, (float)den);   // 0/0 -> NaN like the reference (constant windows)
 }
 
 // cell-list twin of the tile kernel (parity checks): same centred FP32 Gram + FP64 closed form, one thread per cell
@@ -164,7 +180,7 @@ __global__ void k_self_cells_fast(const SelfFastParams p) {
         G = fmaf(u, v, G);
         sa += (double)u; qa += (double)u * (double)u; sb += (double)v; qb += (double)v * (double)v;
       }
-    corr[g] = gram_coeff(G, make_double2(sa, qa), make_double2(sb, qb), (double)(c1 - c0) * (double)b.H);
+    corr[g] = gram_coeff(G, make_double2(sa, qa), make_double2(sb, qb), 1.0 / (4.0 * (double)(c1 - c0) * (double)b.H));
   }
   const float sim = __fadd_rn(__fmul_rn(corr[0], b.weight), __fmul_rn(corr[1], __fsub_rn(1.0f, b.weight)));
   if (b.simOut) b.simOut[k] = sim;
@@ -193,7 +209,7 @@ __global__ void __launch_bounds__(256, 1) k_self_gram(const SelfFastParams p, co
     for (int j = 0; j < 8; j++) corrT[i][j] = 0.f;
   if (useT) {
     gram_group(acc, p, sA, sB, ta, tb, 0, 1, p.shiftT, tid, ty, tx);
-    const double N = (double)b.H;
+    const double N = 1.0 / (4.0 * (double)b.H);
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       const double2 wa = rowsA[i] < ext ? p.ws1[rowsA[i]] : make_double2(0, 0);
@@ -206,7 +222,7 @@ __global__ void __launch_bounds__(256, 1) k_self_gram(const SelfFastParams p, co
     }
   }
   if (useS) gram_group(acc, p, sA, sB, ta, tb, 1, b.numCh - 1, p.shiftS, tid, ty, tx);
-  const double NS = (double)(b.numCh - 1) * (double)b.H;
+  const double NS = 1.0 / (4.0 * (double)(b.numCh - 1) * (double)b.H);
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     const int a = rowsA[i];
