@@ -209,7 +209,7 @@ int sgz_self_run(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh, const 
     // ---- fast path: centred FP32 Gram tiles + FP64 closed-form epilogue (selfsim_fast.cuh) ----
     const int64_t need = (int64_t)g.numCorrs - 1 + H;
     DevBuf<double> dMeans;
-    DevBuf<double2> ws1, ws2;
+    DevBuf<float2> ws1, ws2;
     SGZ_TRY(dMeans.alloc(2));
     SGZ_CUDA(cudaMemsetAsync(dMeans.p, 0, 2 * sizeof(double), ctx->stream));
     SGZ_TRY(ctx->begin_call());

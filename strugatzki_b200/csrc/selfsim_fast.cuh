@@ -27,8 +27,8 @@ constexpr int kGP = kGT + 4;  // smem row pitch (floats)
 struct SelfFastParams {
   SelfParams base;         // x1/x2 planar normalised rows, geometry, colours, rgb
   float shiftT, shiftS;    // centring constants (file-1 group means)
-  const double2 *ws1;      // [2][imgExt] (S, Q) of window a of file 1: group 0 = temporal, 1 = spectral
-  const double2 *ws2;      // same for file 2 (== ws1 for plain self similarity)
+  const float2 *ws1;       // [2][imgExt] (S, Q) of window a of file 1: group 0 = temporal, 1 = spectral
+  const float2 *ws2;      // same for file 2 (== ws1 for plain self similarity)
   int cross;               // file 2 differs from file 1
 };
 
@@ -48,56 +48,55 @@ __global__ void k_self_means(const float *__restrict__ x, int64_t stride, int64_
 
 // (S, Q) of every decimated window, centred data, FP64
 __global__ void k_self_wsums(const float *__restrict__ x, int64_t stride, int numCh, int H, int decim, int imgExt,
-                             float shiftT, float shiftS, double2 *__restrict__ ws) {
+                             float shiftT, float shiftS, float2 *__restrict__ ws) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= imgExt) return;
   const int64_t f0 = (int64_t)decim * a;
   double s = 0, q = 0;
   for (int h = 0; h < H; h++) { const double v = (double)__fsub_rn(x[f0 + h], shiftT); s += v; q += v * v; }
-  ws[a] = make_double2(s, q);
+  ws[a] = make_float2((float)s, (float)q);
   s = 0; q = 0;
   for (int c = 1; c < numCh; c++)
     for (int h = 0; h < H; h++) { const double v = (double)__fsub_rn(x[(int64_t)c * stride + f0 + h], shiftS); s += v; q += v * v; }
-  ws[imgExt + a] = make_double2(s, q);
+  ws[imgExt + a] = make_float2((float)s, (float)q);
 }
 
-// Gather of the Hankel operand: thread t always fetches row i = t & 127 of the tile and the k values
-// (t >> 7), (t >> 7) + 2, (t >> 7) + 4, ... of the group -- 8 per 16-wide chunk.  k = c*H + h walks through the
-// planar feature rows, so the thread keeps a cursor (pointer, h, k) and steps it: one load, one subtract and a few
-// integer ops per element, no division, no 64-bit index arithmetic.
+// Gather of the Hankel operand, one 16 x 128 chunk per call: thread t fetches the 8 rows i = 8*(t & 15) .. +7 at
+// ONE k = k0 + (t >> 4), i.e. one (channel, frame) pair -> the 8 addresses differ by `decim` floats, there is no
+// wrap logic per element, rows past the image are clamped (their cells are never stored) instead of predicated,
+// and the 8 values go to shared memory as two 16-byte stores.  The (channel, frame) cursor advances by 16 per chunk.
 struct GramCursor {
-  const float *ptr;   // &x[c][decim*a + h]
+  const float *ptr;   // &x[c][decim*a0 + h] of this thread's k in the current chunk
   int64_t wrap;       // stride - H : jump to the next channel row when h wraps
+  int64_t rstep[8];   // decim * (row offset), clamped at the image edge
   int h, k, H, K;
-  bool rowOk;
   float shift;
 };
-__device__ __forceinline__ GramCursor gram_cursor(const float *__restrict__ x, int64_t stride, int decim, int a, int imgExt,
+__device__ __forceinline__ GramCursor gram_cursor(const float *__restrict__ x, int64_t stride, int decim, int t0, int imgExt,
                                                   int c0, int H, int K, float shift, int tid) {
   GramCursor c;
   c.H = H; c.K = K; c.shift = shift;
-  c.rowOk = a < imgExt;
-  c.k = tid >> 7;
-  int cc = c.k / H;                 // once per group (H may be 1)
+  c.k = tid >> 4;
+  const int cc = c.k / H;           // once per group
   c.h = c.k - cc * H;
-  c.ptr = x + (int64_t)(c0 + cc) * stride + (int64_t)decim * (c.rowOk ? a : 0) + c.h;
+  const int i0 = 8 * (tid & 15);
+#pragma unroll
+  for (int j = 0; j < 8; j++) c.rstep[j] = (int64_t)decim * min(t0 + i0 + j, imgExt - 1);
+  c.ptr = x + (int64_t)(c0 + cc) * stride + c.h;
   c.wrap = stride - H;
   return c;
 }
 __device__ __forceinline__ void gram_fetch(float (&r)[8], GramCursor &c) {
+  const bool ok = c.k < c.K;
 #pragma unroll
-  for (int e = 0; e < 8; e++) {
-    float v = 0.f;
-    if (c.rowOk && c.k < c.K) v = __fsub_rn(*c.ptr, c.shift);
-    r[e] = v;
-    c.k += 2; c.h += 2; c.ptr += 2;
-    if (c.h >= c.H) { c.h -= c.H; c.ptr += c.wrap; }
-    if (c.h >= c.H) { c.h -= c.H; c.ptr += c.wrap; }   // H == 1
-  }
+  for (int j = 0; j < 8; j++) r[j] = ok ? __fsub_rn(c.ptr[c.rstep[j]], c.shift) : 0.f;
+  c.k += kGK; c.h += kGK; c.ptr += kGK;
+  while (c.h >= c.H) { c.h -= c.H; c.ptr += c.wrap; }
 }
 __device__ __forceinline__ void gram_store(float *dst, const float (&r)[8], int tid) {
-#pragma unroll
-  for (int e = 0; e < 8; e++) dst[((tid >> 7) + 2 * e) * kGP + (tid & 127)] = r[e];
+  float4 *d = reinterpret_cast<float4 *>(dst + (tid >> 4) * kGP + 8 * (tid & 15));
+  d[0] = make_float4(r[0], r[1], r[2], r[3]);
+  d[1] = make_float4(r[4], r[5], r[6], r[7]);
 }
 
 // acc[i][j] (j = column pair) += A-frag x B-frag over one group
@@ -110,8 +109,8 @@ __device__ __forceinline__ void gram_group(float2 (&acc)[8][4], const SelfFastPa
   for (int i = 0; i < 8; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j] = make_float2(0.f, 0.f);
-  GramCursor ca = gram_cursor(b.x1, b.stride1, b.decim, ta + (tid & 127), b.imgExt, c0, b.H, K, shift, tid);
-  GramCursor cb = gram_cursor(b.x2, b.stride2, b.decim, tb + (tid & 127), b.imgExt, c0, b.H, K, shift, tid);
+  GramCursor ca = gram_cursor(b.x1, b.stride1, b.decim, ta, b.imgExt, c0, b.H, K, shift, tid);
+  GramCursor cb = gram_cursor(b.x2, b.stride2, b.decim, tb, b.imgExt, c0, b.H, K, shift, tid);
   float ra[8], rb[8];
   gram_fetch(ra, ca);
   gram_fetch(rb, cb);
@@ -150,14 +149,13 @@ __device__ __forceinline__ void gram_group(float2 (&acc)[8][4], const SelfFastPa
   }
 }
 
-__device__ __forceinline__ float gram_coeff(float G, double2 wa, double2 wb, double N) {
-  // N arrives as 1 / (4 N): no FP64 division here; the one division is FP32 (num and den are already well
-  // conditioned after centring)
-  const double S = wa.x + wb.x;
-  const double T = S * S * N;
-  const double den = 0.5 * (wa.y + wb.y) - T;
-  const double num = (double)G - T;
-  return __fdiv_rn((float)num, (float)den);   // 0/0 -> NaN like the reference (constant windows)
+// inv4N = 1 / (4 N).  After centring, T is small against G and Q, so FP32 is enough here (error ~2e-7);
+// the window sums S, Q themselves are accumulated in FP64 (k_self_wsums) and rounded once.
+__device__ __forceinline__ float gram_coeff(float G, float2 wa, float2 wb, float inv4N) {
+  const float S = wa.x + wb.x;
+  const float T = S * S * inv4N;
+  const float den = fmaf(0.5f, wa.y + wb.y, -T);
+  return __fdiv_rn(G - T, den);   // 0/0 -> NaN like the reference (constant windows)
 }
 
 // cell-list twin of the tile kernel (parity checks): same centred FP32 Gram + FP64 closed form, one thread per cell
@@ -180,7 +178,8 @@ __global__ void k_self_cells_fast(const SelfFastParams p) {
         G = fmaf(u, v, G);
         sa += (double)u; qa += (double)u * (double)u; sb += (double)v; qb += (double)v * (double)v;
       }
-    corr[g] = gram_coeff(G, make_double2(sa, qa), make_double2(sb, qb), 1.0 / (4.0 * (double)(c1 - c0) * (double)b.H));
+    corr[g] = gram_coeff(G, make_float2((float)sa, (float)qa), make_float2((float)sb, (float)qb),
+                         (float)(1.0 / (4.0 * (double)(c1 - c0) * (double)b.H)));
   }
   const float sim = __fadd_rn(__fmul_rn(corr[0], b.weight), __fmul_rn(corr[1], __fsub_rn(1.0f, b.weight)));
   if (b.simOut) b.simOut[k] = sim;
@@ -209,25 +208,25 @@ __global__ void __launch_bounds__(256, 1) k_self_gram(const SelfFastParams p, co
     for (int j = 0; j < 8; j++) corrT[i][j] = 0.f;
   if (useT) {
     gram_group(acc, p, sA, sB, ta, tb, 0, 1, p.shiftT, tid, ty, tx);
-    const double N = 1.0 / (4.0 * (double)b.H);
+    const float N = (float)(1.0 / (4.0 * (double)b.H));
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      const double2 wa = rowsA[i] < ext ? p.ws1[rowsA[i]] : make_double2(0, 0);
+      const float2 wa = rowsA[i] < ext ? p.ws1[rowsA[i]] : make_float2(0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < 8; j++) {
-        const double2 wb = colsB[j] < ext ? p.ws2[colsB[j]] : make_double2(0, 0);
+        const float2 wb = colsB[j] < ext ? p.ws2[colsB[j]] : make_float2(0.f, 0.f);
         const float G = (j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x;
         corrT[i][j] = gram_coeff(G, wa, wb, N);
       }
     }
   }
   if (useS) gram_group(acc, p, sA, sB, ta, tb, 1, b.numCh - 1, p.shiftS, tid, ty, tx);
-  const double NS = 1.0 / (4.0 * (double)(b.numCh - 1) * (double)b.H);
+  const float NS = (float)(1.0 / (4.0 * (double)(b.numCh - 1) * (double)b.H));
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     const int a = rowsA[i];
     if (a >= ext || a < b.colBegin || a >= b.colEnd) continue;
-    const double2 wa = p.ws1[ext + a];
+    const float2 wa = p.ws1[ext + a];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       const int c = colsB[j];
