@@ -264,6 +264,11 @@ def main():
         e2e = run_e2e(args, torch, device, ctx, engine, N, synth, rank, files, mu, sigma, floor0, norm, inp, cfg, world,
                       dist)
 
+    # ---- secondary metric of BASELINE.json: SelfSimilarity cells/s (+ segmentation), bounded workloads ----
+    secondary = None
+    if rank == 0 and world == 1:
+        secondary = run_secondary(ctx, engine, N, synth, norm)
+
     # ---- CPU baseline: the oracle port, one host thread (the reference is single-threaded) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -299,7 +304,7 @@ def main():
             "breakdown_ms": {"k1_scan": float(np.mean(scan_ms)), "k2_select_kernels": float(np.mean(select_ms)),
                              "wall_per_step": wall_ms / args.steps},
             "gpu_launches": int(launches), "clocks": clocks,
-            "e2e": e2e, "cpu_baseline": cpu,
+            "e2e": e2e, "cpu_baseline": cpu, "secondary": secondary,
             "matches": len(res), "needles_missing": len(missing), "top_sim": res[0]["sim"] if res else None,
         }
         print(json.dumps(line), flush=True)
@@ -376,6 +381,37 @@ def run_e2e(args, torch, device, ctx, engine, N, synth, rank, files, mu, sigma, 
             "files_per_gpu": e2e_files,
             "note": "DB upload from pinned host memory (planar float32) + normalise + search + result download, "
                     "through sgz_db_add_file / sgz_db_finalize / sgz_corr_run; PCIe-bound"}
+
+
+def run_secondary(ctx, engine, N, synth, norm):
+    """SelfSimilarity cells/s (fast FP32 Gram path and the exact FP64 replay) and segmentation offsets/s."""
+    out = {}
+    try:
+        f, _ = synth.regime_file(synth.BASE_SEED, 4, 30000, 14, 15)
+        for name, precise in (("selfsimilarity_gram_fp32", 0), ("selfsimilarity_exact_fp64", 1)):
+            cfg = N.SelfConfig(STEP, 0, 0, 0, 0, 44100, 1 if not precise else 3, 0.5, 0, 1.0, 1.0, None, 0, precise)
+            engine.self_run(ctx, cfg, f, None, norm, download=False)
+            _, g = engine.self_run(ctx, cfg, f, None, norm, download=False)
+            ms, launches = ctx.last_timing()
+            cells = g["numCells"]
+            flop = cells * 2408.0 / (ms * 1e-3) / 1e12      # SURVEY 8d: 2*(C+1)*H flop per cell at H = 86
+            out[name] = {"metric": "SelfSimilarity cells/sec", "value": cells / (ms * 1e-3), "unit": "cells/s",
+                         "cells": cells, "imgExt": g["imgExt"], "decim": g["decim"], "kernel_ms": ms,
+                         "algorithmic_tflops": flop,
+                         "workload": "30 000-frame synthetic feature file, corrLen 44100 (H = 86), GrayScale; "
+                                     "matrix only (PNG encode and image download excluded)"}
+        seg, _ = synth.regime_file(synth.BASE_SEED, 31, FRAMES_PER_FILE, 14, 26)
+        scfg = N.SegmConfig(STEP, 0, 0, 0, 0, 22050, 0.5, 20, 22050)
+        engine.segm_run(ctx, scfg, seg, norm)
+        _, _, noff = engine.segm_run(ctx, scfg, seg, norm, want_curve=True)
+        ms, _ = ctx.last_timing()
+        out["segmentation_exact_fp64"] = {"metric": "FeatureSegmentation offsets/sec", "value": noff / (ms * 1e-3),
+                                          "unit": "offsets/s", "offsets": int(noff), "kernel_ms": ms,
+                                          "workload": "10 min synthetic file, corrLen 0.5 s, 20 breaks "
+                                                      "(BASELINE.json configs[1])"}
+    except Exception as e:   # secondary numbers must never break the headline line
+        out["error"] = repr(e)
+    return out
 
 
 def cpu_baseline(args, synth, norm, inp):

@@ -110,5 +110,14 @@ c_s = time.perf_counter() - t
 print(json.dumps(dict(config="configs[3] SelfSimilarity ~155k frames", frames=n, imgExt=g["imgExt"], decim=g["decim"],
                       cells=g["numCells"], gpu_kernel_ms=round(kms, 2), gpu_wall_ms=round(wall * 1e3, 1),
                       gpu_cells_per_s=round(g["numCells"] / (kms * 1e-3), 1), cpu_oracle_cells_per_s=round(2000 / c_s, 1),
+                      mode="fast FP32 Gram (default)",
+                      sample_max_rel_err=float(np.max(np.abs(gs - ws) / np.maximum(np.abs(ws), 1e-3))),
+                      sample_max_grey_diff=int(np.max(np.abs((grgb & 255) - (wrgb & 255)))))), flush=True)
+pcfg = N.SelfConfig(STEP, 0, 0, 0, 0, 44100, 1, 0.5, 0, 1.0, 1.0, None, 0, 1)
+t = time.perf_counter(); _, g = engine.self_run(ctx, pcfg, sf, None, norm, download=False); wall = time.perf_counter() - t
+kms, _ = ctx.last_timing()
+gs, grgb = engine.self_cells(ctx, pcfg, sf, None, l, r, norm)
+print(json.dumps(dict(config="configs[3] SelfSimilarity ~155k frames", mode="precise FP64 replay", cells=g["numCells"],
+                      gpu_kernel_ms=round(kms, 2), gpu_cells_per_s=round(g["numCells"] / (kms * 1e-3), 1),
                       sample_cells_bit_identical=bool(np.array_equal(gs.view(np.uint32), ws.view(np.uint32))
                                                       and np.array_equal(grgb, wrgb)))), flush=True)
