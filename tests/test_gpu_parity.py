@@ -230,3 +230,47 @@ def test_measured_peaks_are_plausible(ctx):
     hbm = ctx.measure_peak(3)
     assert 30.0 < ffma < 100.0, ffma       # B200: 148 SMs x 128 lanes x 2 flop x ~1.9 GHz ~ 72 TFLOP/s
     assert 3000.0 < hbm < 9000.0, hbm
+
+
+def test_corr_edge_cases(ctx):
+    """empty DB, files shorter than the window, numMatches / numPerFile = 0, and an 8 s window (smaller CTA config)"""
+    from strugatzki_b200 import engine
+    files, norm = make_db(3, [900, 100, 60])
+    inp = make_input(900)
+    for kw in (dict(num_matches=0), dict(num_matches=3, num_per_file=0)):
+        op, nc = corr_cfgs(inp, norm, **kw)
+        assert engine.CorrelationJob(build_db(ctx, files, norm), nc, inp).run() == [] == O.corr_search(op, files)
+    op, nc = corr_cfgs(inp, norm, num_matches=3)
+    assert engine.CorrelationJob(build_db(ctx, [], norm), nc, inp).run() == []
+    short = [f[:150] for f in files]                                      # every file shorter than W = 172
+    assert engine.CorrelationJob(build_db(ctx, short, norm), nc, inp).run() == [] == O.corr_search(op, short)
+    # 8 s punch window: W = 689 frames
+    files, norm = make_db(2, [2500, 1800])
+    plant_needles(files, inp[:689], [(1, 300)])
+    op, nc = corr_cfgs(inp, norm, punch_in=(0, 352800), num_matches=2)
+    job = engine.CorrelationJob(build_db(ctx, files, norm), nc, inp)
+    got = job.run()
+    assert_matches_equal(got, O.corr_search(op, files))
+    assert (got[0]["file"], got[0]["start"]) == (1, 300 * STEP)
+    want, _ = O.corr_curve(op, files[0])
+    sim, _ = job.curve(0, 0, 0, len(want))
+    assert_sims_close(sim, want, what="W=689 curve")
+
+
+def test_corr_digital_silence_gives_nan_like_the_reference(ctx):
+    """a constant loudness stretch has zero variance: the reference returns NaN sims (0/0) and, while the result
+    list still has space, inserts them at the head; the engine must do the same"""
+    from strugatzki_b200 import engine
+    files, norm = make_db(4, 2200)
+    inp = make_input(900)
+    files[1][600:1100, 0] = np.float32(0.4)                               # > W frames of constant loudness
+    plant_needles(files, inp[:172], [(2, 900)])
+    op, nc = corr_cfgs(inp, norm, num_matches=6, num_per_file=2)
+    job = engine.CorrelationJob(build_db(ctx, files, norm), nc, inp)
+    got = job.run()
+    want = O.corr_search(op, files)
+    wc, _ = O.corr_curve(op, files[1])
+    gc, _ = job.curve(1, 0, 0, len(wc))
+    assert np.isnan(wc).sum() > 300 and np.array_equal(np.isnan(wc), np.isnan(gc))
+    assert_matches_equal(got, want)
+    assert any(np.isnan(m["sim"]) for m in want)
