@@ -67,14 +67,22 @@ int sgz_ctx_create(int32_t device, sgz_ctx **out) {
   return SGZ_OK;
 }
 
-int sgz_ctx_destroy(sgz_ctx *ctx) {
-  if (!ctx) return SGZ_OK;
+static void ctx_free(sgz_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
+}
+
+int sgz_ctx_destroy(sgz_ctx *ctx) {
+  if (!ctx) return SGZ_OK;
+  if (ctx->refs.load() > 0) {   // databases still alive: released by the last sgz_db_destroy
+    ctx->zombie = true;
+    return SGZ_OK;
+  }
+  ctx_free(ctx);
   return SGZ_OK;
 }
 
@@ -128,14 +136,15 @@ int sgz_db_create(sgz_ctx *ctx, int32_t numCh, const float *norm, sgz_db **out) 
     SGZ_CUDA(cudaEventCreateWithFlags(&db->stageFree[i], cudaEventDisableTiming));
   }
   db->fileStart.push_back(0);
+  ctx->refs++;
   *out = db;
   return SGZ_OK;
 }
 
-int sgz_db_destroy(sgz_db *db) {
-  if (!db) return SGZ_OK;
-  cudaSetDevice(db->ctx->device);
-  cudaStreamSynchronize(db->ctx->stream);
+static void db_free(sgz_db *db) {
+  sgz_ctx *ctx = db->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(db->copyStream);
   for (int i = 0; i < 2; i++) {
     cudaEventDestroy(db->stageFull[i]);
@@ -143,6 +152,16 @@ int sgz_db_destroy(sgz_db *db) {
   }
   cudaStreamDestroy(db->copyStream);
   delete db;
+  if (--ctx->refs == 0 && ctx->zombie) ctx_free(ctx);
+}
+
+int sgz_db_destroy(sgz_db *db) {
+  if (!db) return SGZ_OK;
+  if (db->refs.load() > 0) {   // jobs still alive: released by the last sgz_corr_destroy
+    db->zombie = true;
+    return SGZ_OK;
+  }
+  db_free(db);
   return SGZ_OK;
 }
 
@@ -333,6 +352,9 @@ int sgz_corr_create(sgz_db *db, const sgz_corr_config *cfg, const void *input, i
   }
   SGZ_REQUIRE(cfg->stepSize > 0, "stepSize must be > 0");
   SGZ_REQUIRE(layout >= 0 && layout <= 2, "unknown layout %d", layout);
+  // numPerFile = 0 is degenerate in the reference (addMatch's collapse branch has no size check, so matches leak
+  // into a queue that is supposed to hold none, FeatureCorrelationImpl.scala:136-143); rejected instead of emulated
+  SGZ_REQUIRE(cfg->numPerFile >= 1, "numPerFile must be >= 1, got %d", cfg->numPerFile);
   SGZ_TRY(db->ctx->bind());
   sgz_corr *job = new sgz_corr();
   job->db = db;
@@ -363,6 +385,7 @@ int sgz_corr_create(sgz_db *db, const sgz_corr_config *cfg, const void *input, i
   if (rc != SGZ_OK) { delete job; return rc; }
   job->numTiles = ceil_div<int64_t>(std::max<int64_t>(db->usedFrames, 1), (int64_t)kR * job->ntg);
   job->numOffsets = valid_offsets(db, job->qin.W, job->hasOut ? job->minPunchF : 0);
+  db->refs++;
   *out = job;
   return SGZ_OK;
 }
@@ -373,9 +396,11 @@ int sgz_corr_destroy(sgz_corr *job) {
     job->abortFlag = 1;
     job->worker.join();
   }
+  sgz_db *db = job->db;
   cudaSetDevice(job->ctx->device);
   cudaStreamSynchronize(job->ctx->stream);
   delete job;
+  if (--db->refs == 0 && db->zombie) db_free(db);
   return SGZ_OK;
 }
 

@@ -108,6 +108,11 @@ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
 // opaque handle types
 // ---------------------------------------------------------------------------------------------
 struct sgz_ctx {
+  // lifetime: databases hold a reference to their context and jobs to their database; a destroy call on a
+  // handle that is still referenced only marks it, the last child releases it (hosts with garbage collection
+  // destroy handles in arbitrary order)
+  std::atomic<int> refs{0};
+  bool zombie = false;
   int device = 0;
   int smCount = 0;
   size_t smemOptin = 0;

