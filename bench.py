@@ -209,8 +209,10 @@ def main():
     job = engine.CorrelationJob(db, cfg, inp)
     n_off_local = job.num_offsets
 
+    phases = {}
+
     def step():
-        return sharded_search(job, device, None) if world > 1 else job.run()
+        return sharded_search(job, device, None, trace=phases) if world > 1 else job.run()
 
     def sync_all():
         ctx.synchronize()
@@ -226,6 +228,7 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = ctx.launch_count
+    phases.clear()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ms, select_ms = [], []
     t_wall = time.perf_counter()
@@ -302,7 +305,9 @@ def main():
                                  "unit": "GB/s", "frac": n_off_local * BYTES_PER_OFFSET / scan_s / 1e9 / hbm_peak,
                                  "peak_source": hbm_src, "algorithmic_bytes_per_offset": BYTES_PER_OFFSET}},
             "breakdown_ms": {"k1_scan": float(np.mean(scan_ms)), "k2_select_kernels": float(np.mean(select_ms)),
-                             "wall_per_step": wall_ms / args.steps},
+                             "wall_per_step": wall_ms / args.steps,
+                             "rank0_host_phases": {k: (v / args.steps if k == "rounds" else 1e3 * v / args.steps)
+                                                   for k, v in phases.items()} if world > 1 else None},
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": e2e, "cpu_baseline": cpu, "secondary": secondary,
             "matches": len(res), "needles_missing": len(missing), "top_sim": res[0]["sim"] if res else None,

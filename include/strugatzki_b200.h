@@ -140,6 +140,11 @@ void *sgz_ctx_stream(sgz_ctx *ctx);
 int sgz_ctx_last_timing(sgz_ctx *ctx, float *ms, int64_t *launches);
 /* total kernels launched on this context so far */
 int64_t sgz_ctx_launch_count(sgz_ctx *ctx);
+/* Device buffers released by destroy calls are parked in a per-device pool and reused by the next
+ * database / job of a similar size (a search re-created per query does not pay cudaMalloc/cudaFree of
+ * multi-GB buffers again).  sgz_ctx_trim hands the parked memory of this context's device back to the
+ * driver; freedBytes may be NULL.  Pool size limit: environment SGZ_POOL_MAX_GB (default 64). */
+int sgz_ctx_trim(sgz_ctx *ctx, int64_t *freedBytes);
 
 /* ------------------------------------------------------------------------------------------
  * feature database  (replaces: DB discovery + per-offset AudioFile.read + MathUtil.normalize,

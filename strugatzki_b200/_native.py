@@ -25,6 +25,7 @@ SYMBOLS = [
     "sgz_abi_version", "sgz_last_error", "sgz_device_count",
     "sgz_ctx_create", "sgz_ctx_destroy", "sgz_ctx_synchronize", "sgz_ctx_stream", "sgz_ctx_last_timing",
     "sgz_ctx_launch_count",
+    "sgz_ctx_trim",
     "sgz_db_create", "sgz_db_destroy", "sgz_db_reserve", "sgz_db_add_file", "sgz_db_add_file_device",
     "sgz_db_add_synth", "sgz_db_patch", "sgz_db_finalize", "sgz_db_info", "sgz_db_file_frames", "sgz_db_read",
     "sgz_corr_create", "sgz_corr_destroy", "sgz_corr_run", "sgz_corr_start", "sgz_corr_poll", "sgz_corr_abort",
@@ -124,6 +125,7 @@ def lib() -> C.CDLL:
         L.sgz_last_error.restype = C.c_char_p
         L.sgz_ctx_stream.restype = C.c_void_p
         L.sgz_ctx_launch_count.restype = C.c_int64
+        L.sgz_ctx_trim.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         for name in SYMBOLS:
             getattr(L, name)  # AttributeError if the header and the library disagree
         _lib = L

@@ -104,6 +104,15 @@ int sgz_ctx_last_timing(sgz_ctx *ctx, float *ms, int64_t *launches) {
 
 int64_t sgz_ctx_launch_count(sgz_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int sgz_ctx_trim(sgz_ctx *ctx, int64_t *freedBytes) {
+  SGZ_REQUIRE(ctx, "ctx is NULL");
+  SGZ_TRY(ctx->bind());
+  SGZ_CUDA(cudaDeviceSynchronize());
+  size_t n = DevicePool::of(ctx->device).trim();
+  if (freedBytes) *freedBytes = (int64_t)n;
+  return SGZ_OK;
+}
+
 int sgz_measure_peak(sgz_ctx *ctx, int32_t which, double *value) {
   SGZ_REQUIRE(ctx && value, "sgz_measure_peak: NULL argument");
   return measure_peak(ctx, which, value);
@@ -274,7 +283,9 @@ int sgz_db_finalize(sgz_db *db) {
   SGZ_REQUIRE(db, "db is NULL");
   SGZ_TRY(db->ctx->bind());
   if (db->finalized) return SGZ_OK;
-  SGZ_TRY(db_grow(db, db->usedFrames));  // guarantees the zero slack even for an empty DB
+  SGZ_TRY(db_grow(db, db->usedFrames));  // guarantees the slack even for an empty DB
+  SGZ_CUDA(cudaMemset2DAsync(db->dData.p + db->usedFrames, (size_t)db->capFrames * sizeof(float2), 0,
+                             (size_t)kDbSlack * sizeof(float2), (size_t)db->numPairs, db->ctx->stream));
   SGZ_TRY(db->dFileStart.alloc(db->fileStart.size()));
   SGZ_CUDA(cudaMemcpyAsync(db->dFileStart.p, db->fileStart.data(), db->fileStart.size() * sizeof(int64_t),
                            cudaMemcpyHostToDevice, db->ctx->stream));

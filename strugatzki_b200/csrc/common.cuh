@@ -7,6 +7,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -151,29 +152,126 @@ struct sgz_ctx {
     }                                                                                       \
   } while (0)
 
-// simple owning device buffer
+// ---------------------------------------------------------------------------------------------
+// Device memory pool.  cudaMalloc / cudaFree of the multi-GB database and curve buffers cost 10-100 ms
+// each and serialise the whole device (measured with tools/e2e_probe.py), which a search that is
+// re-created per query pays every time.  Freed blocks are therefore parked per device and handed out
+// again to requests of a similar size; sgz_ctx_trim (or memory pressure) returns them to the driver.
+// Blocks enter the pool only after a device-wide synchronisation, the guarantee cudaFree gave before.
+// ---------------------------------------------------------------------------------------------
+#include <map>
+#include <mutex>
+
+namespace sgz {
+
+class DevicePool {
+ public:
+  static DevicePool &of(int device) {
+    static std::mutex m;
+    static std::map<int, DevicePool *> pools;
+    std::lock_guard<std::mutex> g(m);
+    DevicePool *&p = pools[device];
+    if (!p) p = new DevicePool();   // lives as long as the process, like the CUDA primary context
+    return *p;
+  }
+  static size_t round_up(size_t bytes) {
+    const size_t q = bytes >= (1u << 20) ? (size_t)2 << 20 : 512;
+    return (bytes + q - 1) / q * q;
+  }
+  cudaError_t get(size_t bytes, void **out, size_t *got) {
+    const size_t want = round_up(bytes);
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      auto it = free_.lower_bound(want);
+      if (it != free_.end() && it->first <= want + want / 4) {   // at most 25 % internal waste
+        *out = it->second;
+        *got = it->first;
+        cached_ -= it->first;
+        free_.erase(it);
+        return cudaSuccess;
+      }
+    }
+    cudaError_t e = cudaMalloc(out, want);
+    if (e == cudaErrorMemoryAllocation) {
+      (void)cudaGetLastError();
+      trim();
+      e = cudaMalloc(out, want);
+    }
+    *got = want;
+    return e;
+  }
+  void put(void *p, size_t bytes) {
+    cudaDeviceSynchronize();   // nothing in flight may still touch the block
+    std::lock_guard<std::mutex> g(mu_);
+    if (cached_ + bytes > limit_) {
+      cudaFree(p);
+      return;
+    }
+    free_.emplace(bytes, p);
+    cached_ += bytes;
+  }
+  size_t trim() {
+    std::lock_guard<std::mutex> g(mu_);
+    size_t n = cached_;
+    for (auto &kv : free_) cudaFree(kv.second);
+    free_.clear();
+    cached_ = 0;
+    return n;
+  }
+  size_t cached() {
+    std::lock_guard<std::mutex> g(mu_);
+    return cached_;
+  }
+
+ private:
+  DevicePool() {
+    if (const char *e = getenv("SGZ_POOL_MAX_GB")) limit_ = (size_t)(atof(e) * (double)(1ull << 30));
+  }
+  std::mutex mu_;
+  std::multimap<size_t, void *> free_;
+  size_t cached_ = 0;
+  size_t limit_ = (size_t)64 << 30;   // of 180 GB; the 1000 h database + its curves are 20 GB
+};
+
+}  // namespace sgz
+
+// simple owning device buffer (pool backed)
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
-  size_t n = 0;
+  size_t n = 0;          // elements requested
+  size_t bytes = 0;      // size of the pool block
+  int dev = -1;
   int alloc(size_t count) {
     if (count <= n && p) return SGZ_OK;
     release();
     if (count == 0) return SGZ_OK;
-    cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+    cudaGetDevice(&dev);
+    void *q = nullptr;
+    cudaError_t e = ::sgz::DevicePool::of(dev).get(count * sizeof(T), &q, &bytes);
     if (e != cudaSuccess) {
       p = nullptr;
       n = 0;
+      bytes = 0;
       ::sgz::set_error("cudaMalloc(%zu bytes) -> %s", count * sizeof(T), cudaGetErrorString(e));
+      (void)cudaGetLastError();
       return e == cudaErrorMemoryAllocation ? SGZ_ERR_NOMEM : SGZ_ERR_CUDA;
     }
+    p = (T *)q;
     n = count;
+    // test hook: hand out NaN-patterned memory so that a kernel relying on zero-initialised buffers shows up
+    static const bool poison = getenv("SGZ_POOL_POISON") != nullptr;
+    if (poison) {
+      cudaMemset(q, 0xFF, bytes);
+      cudaDeviceSynchronize();   // the NULL-stream memset is not ordered with the non-blocking streams
+    }
     return SGZ_OK;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) ::sgz::DevicePool::of(dev).put(p, bytes);
     p = nullptr;
     n = 0;
+    bytes = 0;
   }
   ~DevBuf() { release(); }
   DevBuf() = default;

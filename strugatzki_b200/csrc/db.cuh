@@ -158,7 +158,8 @@ inline int db_grow(sgz_db *db, int64_t needFrames) {
   DevBuf<float2> nd;
   SGZ_TRY(nd.alloc((size_t)newCap * db->numPairs));
   cudaStream_t st = db->ctx->stream;
-  SGZ_CUDA(cudaMemsetAsync(nd.p, 0, (size_t)newCap * db->numPairs * sizeof(float2), st));
+  // no full memset: every frame below usedFrames is written by a prepare / synth kernel, and the slack
+  // behind the last file is zeroed by sgz_db_finalize (pool blocks are handed out dirty)
   if (db->usedFrames > 0) {
     SGZ_CUDA(cudaMemcpy2DAsync(nd.p, (size_t)newCap * sizeof(float2), db->dData.p,
                                (size_t)db->capFrames * sizeof(float2), (size_t)db->usedFrames * sizeof(float2),
@@ -167,6 +168,8 @@ inline int db_grow(sgz_db *db, int64_t needFrames) {
   SGZ_CUDA(cudaStreamSynchronize(st));
   std::swap(db->dData.p, nd.p);
   std::swap(db->dData.n, nd.n);
+  std::swap(db->dData.bytes, nd.bytes);
+  std::swap(db->dData.dev, nd.dev);
   db->capFrames = newCap;
   return SGZ_OK;
 }

@@ -14,7 +14,8 @@ capacity then grows for the following searches -- identically on every rank).
 """
 from __future__ import annotations
 
-from typing import Dict, List
+import time
+from typing import Dict, List, Optional
 
 import numpy as np
 
@@ -54,22 +55,44 @@ def allgather_bytes(arr: np.ndarray, device=None, group=None, tag: str = "defaul
     return cat.view(dtype), [s // dtype.itemsize for s in sizes]
 
 
-def sharded_search(job, device=None, group=None) -> List[dict]:
+def sharded_search(job, device=None, group=None, trace: Optional[dict] = None) -> List[dict]:
     """Run one search over a database sharded across the ranks of `group`; `job` is this rank's
-    CorrelationJob (or any object with the same scan/summary/select/merge surface)."""
+    CorrelationJob (or any object with the same scan/summary/select/merge surface).  `trace`, when given,
+    accumulates host wall seconds per phase (every phase ends with a device synchronisation)."""
     import torch.distributed as dist
+
+    t_last = time.perf_counter()
+
+    def mark(phase):
+        nonlocal t_last
+        if trace is not None:
+            now = time.perf_counter()
+            trace[phase] = trace.get(phase, 0.0) + (now - t_last)
+            t_last = now
 
     rank = dist.get_rank(group)
     job.scan()
-    everything, counts = allgather_bytes(job.local_summary(), device, group, tag="summary", initial_cap=1 << 17)
+    mark("scan")
+    summary = job.local_summary()
+    mark("summary_download")
+    everything, counts = allgather_bytes(summary, device, group, tag="summary", initial_cap=1 << 17)
+    mark("summary_allgather")
     job.set_global(everything, int(sum(counts[:rank])))
+    mark("set_global")
     done = False
     rounds = 0
     while not done:
         recs = job.select()
+        mark("select")
         all_recs, _ = allgather_bytes(recs, device, group, tag="records", initial_cap=1 << 16)
+        mark("records_allgather")
         done = job.merge(all_recs)
+        mark("merge")
         rounds += 1
         if rounds > 1_000_000:
             raise RuntimeError("selection protocol did not terminate")
-    return job.result()
+    if trace is not None:
+        trace["rounds"] = trace.get("rounds", 0) + rounds
+    res = job.result()
+    mark("result")
+    return res

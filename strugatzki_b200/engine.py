@@ -55,6 +55,12 @@ class Context:
     def launch_count(self) -> int:
         return int(N.lib().sgz_ctx_launch_count(self._h))
 
+    def trim(self) -> int:
+        """Return the device memory parked by destroyed databases / jobs to the driver; bytes freed."""
+        n = C.c_int64()
+        N.check(N.lib().sgz_ctx_trim(self._h, C.byref(n)))
+        return n.value
+
     def measure_peak(self, which: int) -> float:
         v = C.c_double()
         N.check(N.lib().sgz_measure_peak(self._h, int(which), C.byref(v)))

@@ -289,3 +289,22 @@ def test_corr_digital_silence_gives_nan_like_the_reference(ctx):
     assert np.isnan(wc).sum() > 300 and np.array_equal(np.isnan(wc), np.isnan(gc))
     assert_matches_equal(got, want)
     assert any(np.isnan(m["sim"]) for m in want)
+
+
+def test_memory_pool_reuses_and_trims(ctx):
+    """destroyed databases park their buffers; a new database of the same size gets them back dirty and must still
+    produce the same result (slack zeroing at finalize); trim returns the memory to the driver"""
+    from strugatzki_b200 import engine
+    files, norm = make_db(3, 2500)
+    inp = make_input(900)
+    op, nc = corr_cfgs(inp, norm, num_matches=4, num_per_file=2)
+    want = O.corr_search(op, files)
+    ctx.trim()
+    for _ in range(3):
+        db = build_db(ctx, files, norm)
+        job = engine.CorrelationJob(db, nc, inp)
+        assert_matches_equal(job.run(), want)
+        job.close()
+        db.close()
+    assert ctx.trim() > 0
+    assert ctx.trim() == 0
