@@ -346,7 +346,7 @@ def run_e2e(args, torch, device, ctx, engine, N, synth, rank, files, mu, sigma, 
         db2.reserve(e2e_files * FRAMES_PER_FILE, e2e_files)
         for i in range(e2e_files):
             db2.add_file_ptr(base + i * bytes_per_file, FRAMES_PER_FILE, N.LAYOUT_PLANAR_LE | N.LAYOUT_HOST_STABLE)
-        db2.finalize()
+        db2.finalize(wait=False)     # the search streams behind the uploads still in flight
         job2 = engine.CorrelationJob(db2, cfg, inp)
         if world > 1:
             from strugatzki_b200.distributed import sharded_search
@@ -385,7 +385,7 @@ def run_e2e(args, torch, device, ctx, engine, N, synth, rank, files, mu, sigma, 
             "d2h_bytes_per_step": int(100 * 32 + e2e_files * 8 + 100 * 32),
             "files_per_gpu": e2e_files,
             "note": "DB upload from pinned host memory (planar float32) + normalise + search + result download, "
-                    "through sgz_db_add_file / sgz_db_finalize / sgz_corr_run; PCIe-bound"}
+                    "through sgz_db_add_file / sgz_db_finalize_async / sgz_corr_run (K1 streams behind the upload); PCIe-bound"}
 
 
 def run_secondary(ctx, engine, N, synth, norm):

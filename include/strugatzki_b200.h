@@ -47,8 +47,9 @@ extern "C" {
 #define SGZ_LAYOUT_INTERLEAVED_BE 1  /* [frame][channel] float32 big endian = raw AIFF SSND    */
 #define SGZ_LAYOUT_PLANAR_LE      2  /* [channel][frame] float32 = AudioFile.buffer layout     */
 /* OR-ed into the layout of sgz_db_add_file: the (pinned) host buffer stays valid and unchanged until
- * sgz_db_finalize returns, so the call need not wait for the upload -> H2D copies of consecutive files
- * pipeline with the prepare kernels. */
+ * sgz_db_finalize returns (after sgz_db_finalize_async: until the first sgz_corr_scan / sgz_corr_run on the
+ * database, or a later sgz_db_finalize, returns), so the call need not wait for the upload -> H2D copies of
+ * consecutive files pipeline with the prepare kernels. */
 #define SGZ_LAYOUT_HOST_STABLE    0x100
 
 typedef struct sgz_ctx  sgz_ctx;   /* one GPU + one stream */
@@ -171,6 +172,11 @@ int sgz_db_add_synth(sgz_db *db, uint64_t seed, uint32_t stream, int64_t nFrames
 int sgz_db_patch(sgz_db *db, int32_t file, int64_t frameOff, const float *frames, int64_t n);
 /* Ends the add phase: everything is normalised, planar and resident in HBM afterwards. */
 int sgz_db_finalize(sgz_db *db);
+/* Ends the add phase WITHOUT waiting for uploads still in flight (SGZ_LAYOUT_HOST_STABLE files).  The first
+ * search on the database then streams: the correlation kernel runs range by range behind the upload, like the
+ * reference's loop that reads one file and correlates it (FeatureCorrelationImpl.scala:161-199), so the scan
+ * hides behind the PCIe transfer.  Calling sgz_db_finalize afterwards is the explicit wait. */
+int sgz_db_finalize_async(sgz_db *db);
 int sgz_db_info(sgz_db *db, int32_t *numFiles, int64_t *totalFrames, int32_t *numCh);
 int sgz_db_file_frames(sgz_db *db, int32_t file, int64_t *nFrames);
 /* Reads back NORMALISED frames [frameOff, frameOff+n) of a file as planar [numCh][n]. */

@@ -61,6 +61,7 @@ int sgz_ctx_create(int32_t device, sgz_ctx **out) {
   c->smemOptin = pr.sharedMemPerBlockOptin;
   SGZ_CUDA(cudaSetDevice(device));
   SGZ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  SGZ_CUDA(cudaStreamCreateWithFlags(&c->scanStream, cudaStreamNonBlocking));
   SGZ_CUDA(cudaEventCreate(&c->ev0));
   SGZ_CUDA(cudaEventCreate(&c->ev1));
   *out = c;
@@ -70,9 +71,11 @@ int sgz_ctx_create(int32_t device, sgz_ctx **out) {
 static void ctx_free(sgz_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->scanStream);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->scanStream);
   delete ctx;
 }
 
@@ -140,7 +143,7 @@ int sgz_db_create(sgz_ctx *ctx, int32_t numCh, const float *norm, sgz_db **out) 
   SGZ_CUDA(cudaMemcpyAsync(db->dNorm.p, db->norm.data(), db->norm.size() * sizeof(float), cudaMemcpyHostToDevice,
                            ctx->stream));
   SGZ_CUDA(cudaStreamCreateWithFlags(&db->copyStream, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < sgz_db::kStageSlots; i++) {
     SGZ_CUDA(cudaEventCreateWithFlags(&db->stageFull[i], cudaEventDisableTiming));
     SGZ_CUDA(cudaEventCreateWithFlags(&db->stageFree[i], cudaEventDisableTiming));
   }
@@ -153,12 +156,14 @@ int sgz_db_create(sgz_ctx *ctx, int32_t numCh, const float *norm, sgz_db **out) 
 static void db_free(sgz_db *db) {
   sgz_ctx *ctx = db->ctx;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(db->copyStream);
-  for (int i = 0; i < 2; i++) {
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->scanStream);
+  for (int i = 0; i < sgz_db::kStageSlots; i++) {
     cudaEventDestroy(db->stageFull[i]);
     cudaEventDestroy(db->stageFree[i]);
   }
+  for (auto &c : db->chunks) cudaEventDestroy(c.ev);
   cudaStreamDestroy(db->copyStream);
   delete db;
   if (--ctx->refs == 0 && ctx->zombie) ctx_free(ctx);
@@ -195,9 +200,20 @@ static int db_begin_file(sgz_db *db, int64_t nFrames, int64_t *dstFrame) {
   return SGZ_OK;
 }
 
+static int db_mark_chunk(sgz_db *db, int64_t uptoFrame) {
+  sgz_db::Chunk c{uptoFrame, nullptr};
+  SGZ_CUDA(cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming));
+  SGZ_CUDA(cudaEventRecord(c.ev, db->ctx->stream));
+  db->chunks.push_back(c);
+  db->chunkMark = db->usedFrames;
+  return SGZ_OK;
+}
+
 static int db_commit_file(sgz_db *db, int64_t nFrames) {
   db->usedFrames += nFrames;
   db->fileStart.push_back(db->usedFrames);
+  // every writer of the pair rows runs on ctx->stream, so an event recorded now covers all frames so far
+  if (db->usedFrames - db->chunkMark >= chunk_frames()) SGZ_TRY(db_mark_chunk(db, db->usedFrames));
   return db->numFiles() - 1;
 }
 
@@ -211,7 +227,7 @@ int sgz_db_add_file(sgz_db *db, const void *frames, int64_t nFrames, int32_t lay
   if (nFrames > 0) {
     const size_t bytes = (size_t)nFrames * db->numCh * sizeof(float);
     const int s = db->stageIdx;
-    db->stageIdx ^= 1;
+    db->stageIdx = (s + 1) % sgz_db::kStageSlots;
     if (db->dStage[s].n < bytes) {
       // staging buffer may still be read by an earlier prepare kernel
       if (db->stageUsed[s]) SGZ_CUDA(cudaEventSynchronize(db->stageFree[s]));
@@ -279,21 +295,45 @@ int sgz_db_patch(sgz_db *db, int32_t file, int64_t frameOff, const float *frames
   return SGZ_OK;
 }
 
-int sgz_db_finalize(sgz_db *db) {
-  SGZ_REQUIRE(db, "db is NULL");
-  SGZ_TRY(db->ctx->bind());
-  if (db->finalized) return SGZ_OK;
+// everything of finalize that is stream ordered: no host wait for the uploads
+static int db_finalize_enqueue(sgz_db *db) {
   SGZ_TRY(db_grow(db, db->usedFrames));  // guarantees the slack even for an empty DB
   SGZ_CUDA(cudaMemset2DAsync(db->dData.p + db->usedFrames, (size_t)db->capFrames * sizeof(float2), 0,
                              (size_t)kDbSlack * sizeof(float2), (size_t)db->numPairs, db->ctx->stream));
   SGZ_TRY(db->dFileStart.alloc(db->fileStart.size()));
+  // the file table goes through the (idle) scan stream so that it does not queue behind uploads in flight
   SGZ_CUDA(cudaMemcpyAsync(db->dFileStart.p, db->fileStart.data(), db->fileStart.size() * sizeof(int64_t),
-                           cudaMemcpyHostToDevice, db->ctx->stream));
+                           cudaMemcpyHostToDevice, db->ctx->scanStream));
+  SGZ_CUDA(cudaStreamSynchronize(db->ctx->scanStream));
+  SGZ_TRY(db_mark_chunk(db, INT64_MAX));   // "everything, including the slack"
+  db->finalized = true;
+  return SGZ_OK;
+}
+
+// host wait until every upload has landed; drops the progress markers and the staging ring
+static int db_wait_resident(sgz_db *db) {
   SGZ_CUDA(cudaStreamSynchronize(db->copyStream));
   SGZ_CUDA(cudaStreamSynchronize(db->ctx->stream));
-  db->dStage[0].release();
-  db->dStage[1].release();
-  db->finalized = true;
+  for (auto &c : db->chunks) cudaEventDestroy(c.ev);
+  db->chunks.clear();
+  for (int i = 0; i < sgz_db::kStageSlots; i++) {
+    db->dStage[i].release();
+    db->stageUsed[i] = false;
+  }
+  return SGZ_OK;
+}
+
+int sgz_db_finalize(sgz_db *db) {
+  SGZ_REQUIRE(db, "db is NULL");
+  SGZ_TRY(db->ctx->bind());
+  if (!db->finalized) SGZ_TRY(db_finalize_enqueue(db));
+  return db_wait_resident(db);   // also the explicit wait after sgz_db_finalize_async
+}
+
+int sgz_db_finalize_async(sgz_db *db) {
+  SGZ_REQUIRE(db, "db is NULL");
+  SGZ_TRY(db->ctx->bind());
+  if (!db->finalized) SGZ_TRY(db_finalize_enqueue(db));
   return SGZ_OK;
 }
 
@@ -377,11 +417,18 @@ int sgz_corr_create(sgz_db *db, const sgz_corr_config *cfg, const void *input, i
   job->maxPunchF = full_to_feat(cfg->maxPunch, job->step);
   std::vector<float> planar;
   to_planar(input, inputFrames, db->numCh, layout, planar);
+  // uploads still in flight (sgz_db_finalize_async): the taps must not queue behind them on the context stream
+  const bool streaming = !db->chunks.empty();
+  cudaStream_t tapStream = streaming ? db->ctx->scanStream : db->ctx->stream;
   int rc = prepare_query(db, planar.data(), inputFrames, cfg->punchInStart, cfg->punchInStop, cfg->punchInWeight,
-                         job->step, job->qin);
+                         job->step, job->qin, tapStream);
   if (rc == SGZ_OK && job->hasOut)
     rc = prepare_query(db, planar.data(), inputFrames, cfg->punchOutStart, cfg->punchOutStop, cfg->punchOutWeight,
-                       job->step, job->qout);
+                       job->step, job->qout, tapStream);
+  if (rc == SGZ_OK && streaming && cudaStreamSynchronize(tapStream) != cudaSuccess) {
+    set_error("taps upload failed");
+    rc = SGZ_ERR_CUDA;
+  }
   if (rc == SGZ_OK) {
     int wq = std::max(job->qin.Wq, job->hasOut ? job->qout.Wq : 0);
     job->ntg = pick_ntg(job->ctx, db->numPairs, wq);
@@ -430,23 +477,65 @@ int sgz_corr_scan(sgz_corr *job) {
     SGZ_TRY(job->boostOut.alloc(n));
     SGZ_TRY(job->dFileMaxOut.alloc((size_t)std::max(db->numFiles(), 1)));
   }
-  SGZ_TRY(ctx->begin_call());
-  SGZ_CUDA(cudaMemsetAsync(job->dFileMax.p, 0, job->dFileMax.n * sizeof(unsigned long long), ctx->stream));
-  if (job->hasOut)
-    SGZ_CUDA(cudaMemsetAsync(job->dFileMaxOut.p, 0, job->dFileMaxOut.n * sizeof(unsigned long long), ctx->stream));
-  if (db->usedFrames > 0) {
-    SGZ_TRY(run_scan_one(job, job->qin, job->hasOut ? job->minPunchF : 0, job->simIn.p, job->boostIn.p,
-                         job->dFileMax.p));
-    if (job->hasOut) {
-      SGZ_TRY(run_scan_one(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p));
+  const int tailIn = job->hasOut ? job->minPunchF : 0;
+  if (!db->chunks.empty()) {
+    // ---- streaming scan: the database is still being uploaded (sgz_db_finalize_async).  K1 runs on its own
+    // stream, range by range behind the upload markers, and leaves a few SMs to the prepare kernels. ----
+    cudaStream_t ss = ctx->scanStream;
+    const int64_t launches0 = ctx->launches;
+    const int64_t T = (int64_t)kR * job->ntg;
+    const int wqMax = std::max(job->qin.Wq, job->hasOut ? job->qout.Wq : 0);
+    const int spare = ctx->smCount > 32 ? 8 : 0;
+    SGZ_CUDA(cudaEventRecord(ctx->ev0, ss));
+    SGZ_CUDA(cudaMemsetAsync(job->dFileMax.p, 0, job->dFileMax.n * sizeof(unsigned long long), ss));
+    if (job->hasOut)
+      SGZ_CUDA(cudaMemsetAsync(job->dFileMaxOut.p, 0, job->dFileMaxOut.n * sizeof(unsigned long long), ss));
+    int64_t done = 0;
+    for (const auto &c : db->chunks) {
+      // a tile reads frames [tile*T, (tile+1)*T + Wq)
+      const int64_t end = c.uptoFrame == INT64_MAX ? job->numTiles
+                                                   : std::min<int64_t>(job->numTiles, std::max<int64_t>(c.uptoFrame - wqMax, 0) / T);
+      if (end <= done || db->usedFrames == 0) continue;
+      SGZ_CUDA(cudaStreamWaitEvent(ss, c.ev, 0));
+      SGZ_TRY(run_scan_one(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, done, end, ss, spare));
+      if (job->hasOut)
+        SGZ_TRY(run_scan_one(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, done, end, ss, spare));
+      done = end;
+    }
+    SGZ_CUDA(cudaStreamWaitEvent(ss, db->chunks.back().ev, 0));   // file table for the row maxima / later kernels
+    if (job->hasOut && db->usedFrames > 0) {
       SGZ_TRY(job->rowMaxOut.alloc((size_t)db->usedFrames));
-      k_row_max_out<<<(unsigned)ceil_div<int64_t>(db->usedFrames, 256), 256, 0, ctx->stream>>>(
+      k_row_max_out<<<(unsigned)ceil_div<int64_t>(db->usedFrames, 256), 256, 0, ss>>>(
           job->simOut.p, db->dFileStart.p, db->numFiles(), db->usedFrames, job->qin.W, job->qout.W, job->minPunchF,
           job->maxPunchF, job->rowMaxOut.p);
       SGZ_LAUNCH_CHECK(ctx);
     }
+    SGZ_CUDA(cudaEventRecord(ctx->ev1, ss));
+    SGZ_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev1, 0));
+    SGZ_CUDA(cudaEventSynchronize(ctx->ev1));
+    SGZ_CUDA(cudaEventElapsedTime(&ctx->lastMs, ctx->ev0, ctx->ev1));
+    ctx->lastLaunches = ctx->launches - launches0;
+    SGZ_TRY(db_wait_resident(db));
+  } else {
+    SGZ_TRY(ctx->begin_call());
+    SGZ_CUDA(cudaMemsetAsync(job->dFileMax.p, 0, job->dFileMax.n * sizeof(unsigned long long), ctx->stream));
+    if (job->hasOut)
+      SGZ_CUDA(cudaMemsetAsync(job->dFileMaxOut.p, 0, job->dFileMaxOut.n * sizeof(unsigned long long), ctx->stream));
+    if (db->usedFrames > 0) {
+      SGZ_TRY(run_scan_one(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, 0, job->numTiles,
+                           ctx->stream, 0));
+      if (job->hasOut) {
+        SGZ_TRY(run_scan_one(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, 0, job->numTiles,
+                             ctx->stream, 0));
+        SGZ_TRY(job->rowMaxOut.alloc((size_t)db->usedFrames));
+        k_row_max_out<<<(unsigned)ceil_div<int64_t>(db->usedFrames, 256), 256, 0, ctx->stream>>>(
+            job->simOut.p, db->dFileStart.p, db->numFiles(), db->usedFrames, job->qin.W, job->qout.W, job->minPunchF,
+            job->maxPunchF, job->rowMaxOut.p);
+        SGZ_LAUNCH_CHECK(ctx);
+      }
+    }
+    SGZ_TRY(ctx->end_call());
   }
-  SGZ_TRY(ctx->end_call());
   job->scanMs = ctx->lastMs;
   job->scanLaunches = ctx->lastLaunches;
   job->scanned = true;

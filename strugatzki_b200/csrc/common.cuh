@@ -118,6 +118,7 @@ struct sgz_ctx {
   int smCount = 0;
   size_t smemOptin = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t scanStream = nullptr;   // K1 launches of a streaming scan (overlaps the uploads queued on `stream`)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;        // total kernels launched on this context
   int64_t callLaunches0 = 0;   // snapshot at begin_call

@@ -66,7 +66,7 @@ namespace sgz {
 // readInBuffer (FeatureCorrelationImpl.scala:83-98): cut [start,stop) feature frames, normalise,
 // matrix-wide stats of the temporal (ch 0) and spectral (ch 1..) groups, ln of the loudness average.
 inline int prepare_query(const sgz_db *db, const float *inputPlanar /*[numCh][inputFrames]*/, int64_t inputFrames,
-                         int64_t spanStart, int64_t spanStop, float weight, int step, PunchQuery &q) {
+                         int64_t spanStart, int64_t spanStop, float weight, int step, PunchQuery &q, cudaStream_t st) {
   const int numCh = db->numCh;
   const int start = full_to_feat(spanStart, step), stop = full_to_feat(spanStop, step);
   const int W = stop - start;
@@ -119,8 +119,7 @@ inline int prepare_query(const sgz_db *db, const float *inputPlanar /*[numCh][in
     }
   }
   SGZ_TRY(q.dTaps.alloc(q.taps.size()));
-  SGZ_CUDA(cudaMemcpyAsync(q.dTaps.p, q.taps.data(), q.taps.size() * sizeof(float), cudaMemcpyHostToDevice,
-                           db->ctx->stream));
+  SGZ_CUDA(cudaMemcpyAsync(q.dTaps.p, q.taps.data(), q.taps.size() * sizeof(float), cudaMemcpyHostToDevice, st));
   return SGZ_OK;
 }
 
@@ -158,8 +157,12 @@ inline int64_t valid_offsets(const sgz_db *db, int W, int tailExtra) {
   return total;
 }
 
+// one K1 launch over tiles [tileBegin, tileEnd) on `st`; `spareSMs` SMs are left to other streams (the prepare
+// kernels of uploads still in flight during a streaming scan)
 inline int run_scan_one(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim, float *boost,
-                        unsigned long long *fileMax) {
+                        unsigned long long *fileMax, int64_t tileBegin, int64_t tileEnd, cudaStream_t st,
+                        int spareSMs) {
+  if (tileEnd <= tileBegin) return SGZ_OK;
   sgz_db *db = job->db;
   CorrParams p{};
   p.data = db->dData.p;
@@ -180,15 +183,17 @@ inline int run_scan_one(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim,
   p.sim = sim;
   p.boost = boost;
   p.fileMax = fileMax;
-  p.numTiles = job->numTiles;
+  p.tileBegin = tileBegin;
+  p.tileEnd = tileEnd;
   CorrSmemLayout L = corr_smem_layout(job->ntg, db->numPairs, q.Wq, job->nslot);
   sgz_ctx *ctx = job->ctx;
   auto kern = job->nslot == 2 ? k_corr<2> : k_corr<3>;
   SGZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemOptin));
   // persistent: one or two CTAs per SM, tiles are striped over the CTAs
   const int perSm = corr_ctas_per_sm(job->ntg, db->numPairs, q.Wq);
-  const unsigned grid = (unsigned)std::min<int64_t>(job->numTiles, (int64_t)ctx->smCount * perSm);
-  kern<<<grid, job->ntg + 64, L.total, ctx->stream>>>(p);
+  const int sms = std::max(ctx->smCount - spareSMs, 1);
+  const unsigned grid = (unsigned)std::min<int64_t>(tileEnd - tileBegin, (int64_t)sms * perSm);
+  kern<<<grid, job->ntg + 64, L.total, st>>>(p);
   SGZ_LAUNCH_CHECK(ctx);
   return SGZ_OK;
 }

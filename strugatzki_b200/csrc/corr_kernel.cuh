@@ -61,8 +61,8 @@ struct CorrParams {
   const int64_t *fileStart; // [numFiles+1] global start frame of each file
   int numFiles;
   int tailExtra;            // frames excluded at each file end (minPunch in punch-out mode)
-  int64_t numTiles;
-  float *sim;               // [>= numTiles*T]
+  int64_t tileBegin, tileEnd;   // tiles [tileBegin, tileEnd) of this launch (a streaming scan launches ranges)
+  float *sim;               // [>= tileEnd*T]
   float *boost;
   unsigned long long *fileMax;  // [numFiles] packed (order_key(sim) << 32 | ~offset), or nullptr
 };
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(384, 1) k_corr(const CorrParams p) {
     // =========================== TMA issuer ===========================
     if (lane == 0) {
       uint32_t rc = 0;  // rows issued so far by this CTA
-      for (int64_t tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+      for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x) {
         const int64_t t0 = tile * T;
         for (int c = 0; c < p.numPairs; c++, rc++) {
           const int slot = rc % NSLOT;
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(384, 1) k_corr(const CorrParams p) {
   } else if (warp == NCW + 1) {
     // =========================== stats warp ===========================
     uint32_t rc = 0, it = 0;
-    for (int64_t tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x, it++) {
+    for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, it++) {
       const int b = it & 1;
       float *T0 = stats_T0(b);
       float2 *F = stats_F(b);
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(384, 1) k_corr(const CorrParams p) {
     const float qnan = __int_as_float(0x7fc00000);
     const int nq = W / kR, remW = W - nq * kR;
     uint32_t rc = 0, it = 0;
-    for (int64_t tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x, it++) {
+    for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, it++) {
       const int64_t t0 = tile * T;
       float2 acc[kR];
       float accT[kR];

@@ -29,12 +29,19 @@ struct sgz_db {
   std::vector<int64_t> fileStart;       // size numFiles+1 (last = usedFrames)
   DevBuf<int64_t> dFileStart;
   bool finalized = false;
-  // double-buffered upload staging
-  DevBuf<unsigned char> dStage[2];
+  // upload staging ring: H2D copies on copyStream run ahead of the prepare kernels on ctx->stream.  The ring is
+  // deep enough to keep PCIe busy while prepare kernels queue behind a K1 launch of a streaming scan.
+  static constexpr int kStageSlots = 32;
+  DevBuf<unsigned char> dStage[kStageSlots];
   cudaStream_t copyStream = nullptr;
-  cudaEvent_t stageFull[2] = {nullptr, nullptr}, stageFree[2] = {nullptr, nullptr};
+  cudaEvent_t stageFull[kStageSlots] = {}, stageFree[kStageSlots] = {};
   int stageIdx = 0;
-  bool stageUsed[2] = {false, false};
+  bool stageUsed[kStageSlots] = {};
+  // upload progress markers on ctx->stream: every frame below `uptoFrame` is resident once `ev` has fired.
+  // A scan that finds markers (sgz_db_finalize_async) launches K1 range by range behind them.
+  struct Chunk { int64_t uptoFrame; cudaEvent_t ev; };
+  std::vector<Chunk> chunks;
+  int64_t chunkMark = 0;
 
   int numFiles() const { return (int)fileStart.size() - 1; }
 };
@@ -42,6 +49,14 @@ struct sgz_db {
 namespace sgz {
 
 constexpr int64_t kDbSlack = 16384;  // readable zero frames behind the last file (tile halo)
+// upload marker granularity (~80 files of 10 min, 4 ms of PCIe); SGZ_CHUNK_FRAMES overrides it (tests)
+inline int64_t chunk_frames() {
+  static const int64_t v = [] {
+    const char *e = getenv("SGZ_CHUNK_FRAMES");
+    return e && atoll(e) > 0 ? (int64_t)atoll(e) : (int64_t)(4 << 20);
+  }();
+  return v;
+}
 
 // ---- synthetic features.  Integer hash -> exact integer sum of 8
 // consecutive 24-bit values -> ONE float scale, so numpy (strugatzki_b200/synth.py) and this

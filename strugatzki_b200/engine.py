@@ -127,8 +127,9 @@ class Database:
         a = _frames(frames)
         N.check(N.lib().sgz_db_patch(self._h, int(file), C.c_int64(frame_off), N.fptr(a), C.c_int64(a.shape[0])))
 
-    def finalize(self):
-        N.check(N.lib().sgz_db_finalize(self._h))
+    def finalize(self, wait: bool = True):
+        """wait=False: do not wait for HOST_STABLE uploads in flight; the first search streams behind them."""
+        N.check((N.lib().sgz_db_finalize if wait else N.lib().sgz_db_finalize_async)(self._h))
 
     def info(self) -> Tuple[int, int, int]:
         nf, tf, nc = C.c_int32(), C.c_int64(), C.c_int32()

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# small upload markers so that the streaming scan (sgz_db_finalize_async) sees many ranges on the small test DBs;
+# read once by the library, before the first database is built
+os.environ.setdefault("SGZ_CHUNK_FRAMES", "3000")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -308,3 +308,38 @@ def test_memory_pool_reuses_and_trims(ctx):
         db.close()
     assert ctx.trim() > 0
     assert ctx.trim() == 0
+
+
+@pytest.mark.parametrize("punch_out", [False, True])
+def test_streaming_scan_behind_async_upload(ctx, punch_out):
+    """sgz_db_finalize_async: the search starts while HOST_STABLE uploads are still in flight and K1 runs range by
+    range behind the upload markers -- same matches as the resident database and the oracle"""
+    import torch
+    from strugatzki_b200 import engine
+    lens = [3000, 2500, 4100, 180, 2900, 3300, 2000, 5000, 172, 2600, 3100, 2800] * 3
+    files, norm = make_db(len(lens), lens)
+    inp = make_input(900)
+    plant_needles(files, inp[:172], [(2, 1500), (7, 10), (19, 3000), (33, 2400)])
+    kw = dict(num_matches=9, num_per_file=2, min_spacing=22050)
+    if punch_out:
+        kw.update(punch_in=(0, 44100), punch_out=(200 * 512, 200 * 512 + 44100), min_punch=22050, max_punch=88200)
+    op, nc = corr_cfgs(inp, norm, **kw)
+    want = O.corr_search(op, files)
+    pinned = [torch.from_numpy(f).pin_memory() for f in files]     # must outlive the search (HOST_STABLE)
+    for rep in range(2):                                           # second round reuses pooled (dirty) buffers
+        db = engine.Database(ctx, 14, norm)
+        for t in pinned:
+            db.add_file_ptr(t.data_ptr(), t.shape[0], N.LAYOUT_INTERLEAVED_LE | N.LAYOUT_HOST_STABLE)
+        db.finalize(wait=False)
+        job = engine.CorrelationJob(db, nc, inp)
+        got = job.run()
+        assert_matches_equal(got, want)
+        assert job.num_offsets == O.corr_num_offsets(op, lens)
+        # the database is fully resident afterwards: a second (monolithic) scan gives the same curves
+        sim_a, _ = job.curve(2, 0, 0, 1000)
+        job.scan()
+        sim_b, _ = job.curve(2, 0, 0, 1000)
+        assert np.array_equal(sim_a.view(np.uint32), sim_b.view(np.uint32))
+        db.finalize()                                              # explicit wait is a no-op now
+        job.close()
+        db.close()

@@ -11,6 +11,7 @@ import bench  # noqa: E402
 from strugatzki_b200 import _native as N, engine, synth  # noqa: E402
 
 files = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
+STREAM = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 F = bench.FRAMES_PER_FILE
 ctx = engine.Context(0)
 mu, sigma, floor0, norm = synth.default_profile(14)
@@ -38,16 +39,17 @@ for rep in range(3):
     for i in range(files):
         db.add_file_ptr(base + i * bpf, F, N.LAYOUT_PLANAR_LE | N.LAYOUT_HOST_STABLE)
     mark("add_issue", sync=False)
-    mark("add_drain")
-    db.finalize()
-    mark("finalize")
+    if STREAM == 0:
+        mark("add_drain")
+    db.finalize(wait=STREAM == 0)
+    mark("finalize", sync=STREAM == 0)
     job = engine.CorrelationJob(db, cfg, inp)
-    mark("job_create")
+    mark("job_create", sync=STREAM == 0)
     job.run()
     mark("run")
     job.close()
     db.close()
     mark("close")
     ph["total"] = 1e3 * (time.perf_counter() - t0)
-    ph["upload_GBps"] = files * bpf / 1e6 / (ph["add_issue"] + ph["add_drain"])
+    ph["upload_GBps"] = files * bpf / 1e6 / (ph["add_issue"] + ph.get("add_drain", ph["run"]))
     print(json.dumps(ph))

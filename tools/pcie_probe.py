@@ -29,6 +29,19 @@ with torch.cuda.stream(s2):
     dst[half:].copy_(big[half:], non_blocking=True)
 torch.cuda.synchronize()
 out["two_streams"] = {"GB/s": (2 << 30) / (time.perf_counter() - t) / 1e9}
+# file-sized copies alternating over two streams (does the second stream hide the per-copy gap?)
+chunk = 51680 * 56
+n = (2 << 30) // chunk
+s3 = torch.cuda.Stream()
+for rep in range(3):
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    for i in range(n):
+        with torch.cuda.stream(s2 if i & 1 else s3):
+            dst[i * chunk:(i + 1) * chunk].copy_(big[i * chunk:(i + 1) * chunk], non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t
+out["copies_of_2.9MB_two_streams"] = {"GB/s": n * chunk / dt / 1e9}
 # d2h
 torch.cuda.synchronize()
 t = time.perf_counter()
