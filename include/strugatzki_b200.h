@@ -290,6 +290,32 @@ int sgz_self_cells(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh, cons
                    const int32_t *rightIdx, float *sim, int32_t *rgb);
 
 /* ------------------------------------------------------------------------------------------
+ * CrossSimilarity  (replaces CrossSimilarityImpl.body(), Impl/CrossSimilarityImpl.scala:32-187)
+ * The shorter span is the template, slid over the longer one; one sim per step -- the values the reference
+ * writes into its 1-channel output audio file.  The reference's ring-buffer behaviour (8192-frame buffer whose
+ * first read takes min(len, 8192) frames, write index wrapping at the template length, read index wrapping
+ * at 8192) is reproduced as it is: 1 + len2 - min(len2, 8192) values, bit-identical Double arithmetic.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t stepSize;
+  int32_t has1Start, has1Stop;   /* span1: Span.All when both are 0 */
+  int32_t has2Start, has2Stop;   /* span2 */
+  int32_t _pad;
+  int64_t span1Start, span1Stop; /* sample frames */
+  int64_t span2Start, span2Stop;
+  float   temporalWeight;
+  float   maxBoost;
+} sgz_cross_config;
+
+/* number of values a run writes; SGZ_ERR_INVALID where the reference throws (shorter span > 8192 feature
+ * frames: ArrayIndexOutOfBounds; shorter span empty: ArithmeticException) */
+int sgz_cross_num_outputs(const sgz_cross_config *cfg, int64_t nFrames1, int64_t nFrames2, int64_t *nOut);
+/* frames1 / frames2: raw feature frames of metaInput1 / metaInput2 in `layout`; sim[simCap] may be NULL */
+int sgz_cross_run(sgz_ctx *ctx, const sgz_cross_config *cfg, int32_t numCh, const float *norm,
+                  const void *frames1, int64_t nFrames1, const void *frames2, int64_t nFrames2,
+                  int32_t layout, float *sim, int64_t simCap, int64_t *nOut);
+
+/* ------------------------------------------------------------------------------------------
  * measurement helpers (bench.py): live peaks of the pipes the kernels are bound by
  * ---------------------------------------------------------------------------------------- */
 /* which: 0 = FP32 FFMA TFLOP/s, 1 = packed FFMA2 TFLOP/s, 2 = FP64 DFMA TFLOP/s,

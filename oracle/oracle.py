@@ -65,6 +65,15 @@ class _SelfCfg(C.Structure):
                 ("colorWarp", C.c_float), ("colorCeil", C.c_float)]
 
 
+class _CrossCfg(C.Structure):
+    _fields_ = [("numCh", C.c_int32), ("stepSize", C.c_int32), ("norm", C.c_void_p),
+                ("has1Start", C.c_int32), ("has1Stop", C.c_int32),
+                ("span1Start", C.c_int64), ("span1Stop", C.c_int64),
+                ("has2Start", C.c_int32), ("has2Stop", C.c_int32),
+                ("span2Start", C.c_int64), ("span2Stop", C.c_int64),
+                ("temporalWeight", C.c_float), ("maxBoost", C.c_float)]
+
+
 _lib = None
 
 
@@ -79,6 +88,7 @@ def lib():
         _lib.sgz_o_self_geometry.restype = C.c_int
         _lib.sgz_o_self_image.restype = C.c_int
         _lib.sgz_o_self_cells.restype = C.c_int
+        _lib.sgz_o_cross_run.restype = C.c_int64
         _lib.sgz_o_avg.restype = C.c_float
         _lib.sgz_o_correlate_half.restype = C.c_float
         _lib.sgz_o_correlate.restype = C.c_float
@@ -251,3 +261,29 @@ def self_cells(p: SelfParams, file1: np.ndarray, file2: Optional[np.ndarray], le
     if k < 0:
         raise RuntimeError(f"oracle self_cells failed: {k}")
     return sim, rgb
+
+
+@dataclass
+class CrossParams:
+    step_size: int
+    temporal_weight: float = 0.5
+    norm: Optional[np.ndarray] = None
+    max_boost: float = 8.0
+    span1: tuple = (None, None)      # (start, stop) in sample frames; None = open end (Span.All / HasStart / HasStop)
+    span2: tuple = (None, None)
+
+
+def cross_run(p: CrossParams, file1: np.ndarray, file2: np.ndarray) -> np.ndarray:
+    """CrossSimilarityImpl.body(): the sim curve the reference writes to its 1-channel output file."""
+    f1, f2 = _f32(file1), _f32(file2)
+    nrm = None if p.norm is None else _f32(p.norm)
+    (a1, b1), (a2, b2) = p.span1, p.span2
+    cfg = _CrossCfg(f1.shape[1], p.step_size, _ptr(nrm), int(a1 is not None), int(b1 is not None), a1 or 0, b1 or 0,
+                    int(a2 is not None), int(b2 is not None), a2 or 0, b2 or 0, p.temporal_weight, p.max_boost)
+    cap = max(f1.shape[0], f2.shape[0], 1) + 1
+    out = np.zeros(cap, np.float32)
+    n = lib().sgz_o_cross_run(C.byref(cfg), _ptr(f1), C.c_int64(f1.shape[0]), _ptr(f2), C.c_int64(f2.shape[0]),
+                              _ptr(out), C.c_int64(cap))
+    if n < 0:
+        raise RuntimeError(f"oracle cross_run failed: {n}")
+    return out[:n].copy()

@@ -762,3 +762,79 @@ int sgz_o_self_cells(const sgz_o_self_cfg *cfg, const float *file1, int64_t nFra
   free_planar(eInBuf, cfg->numCh);
   return imgExt;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * CrossSimilarityImpl.body(), Impl/CrossSimilarityImpl.scala:32-187
+ * ---------------------------------------------------------------------------------------- */
+
+/* openInput, :69-82 -> start frame and length of the span inside a file of numFrames */
+static void cross_open(int step, int hasStart, int hasStop, int64_t spStart, int64_t spStop, int64_t numFrames,
+                       int64_t *start_out, int64_t *len_out) {
+  int64_t s = hasStart ? full_to_feat(spStart, step) : 0;
+  int64_t e = hasStop ? full_to_feat(spStop, step) : numFrames;
+  int64_t stop = numFrames < e ? numFrames : e;
+  int64_t start = stop < s ? stop : s;
+  if (start < 0) start = 0;
+  *start_out = start;
+  *len_out = stop - start;
+}
+
+int64_t sgz_o_cross_run(const sgz_o_cross_cfg *cfg, const float *file1, int64_t nFrames1,
+                        const float *file2, int64_t nFrames2, float *sim_out, int64_t cap) {
+  const int step = cfg->stepSize, numCh = cfg->numCh;
+  int64_t st1, l1, st2, l2;
+  cross_open(step, cfg->has1Start, cfg->has1Stop, cfg->span1Start, cfg->span1Stop, nFrames1, &st1, &l1);
+  cross_open(step, cfg->has2Start, cfg->has2Stop, cfg->span2Start, cfg->span2Stop, nFrames2, &st2, &l2);
+  /* shorter file -> afIn1 (read completely), longer -> afIn2 (piecewise), :93-95 */
+  const float *fIn1, *fIn2;
+  int64_t pos1, len1, pos2, len2;
+  if (l1 < l2) { fIn1 = file1; pos1 = st1; len1 = l1; fIn2 = file2; pos2 = st2; len2 = l2; }
+  else         { fIn1 = file2; pos1 = st2; len1 = l2; fIn2 = file1; pos2 = st1; len2 = l1; }
+  const int bufSz = 8192;
+  if (len1 > bufSz) return -2;          /* ArrayIndexOutOfBoundsException in the reference */
+  if (len1 <= 0) return len2 > 0 ? -3 : 0;   /* `% len1i` -> ArithmeticException; nothing to do if both are empty */
+  const int len1i = (int)len1;
+
+  input_matrix in;                      /* matrixIn, :100-116 */
+  memset(&in, 0, sizeof in);
+  in.all = alloc_planar(numCh, len1i);
+  read_frames(fIn1, numCh, pos1, in.all, 0, len1i);
+  sgz_o_normalize(cfg->norm, in.all, numCh, 0, len1i);
+  in.numFrames = len1i;
+  in.temporal.mat = in.all; in.temporal.numChannels = 1; in.temporal.numFrames = len1i;
+  sgz_o_stat((const float *const *)in.temporal.mat, 0, len1i, 0, 1, &in.temporal.mean, &in.temporal.stdDev);
+  in.spectral.mat = in.all + 1; in.spectral.numChannels = numCh - 1; in.spectral.numFrames = len1i;
+  sgz_o_stat((const float *const *)in.spectral.mat, 0, len1i, 0, numCh - 1, &in.spectral.mean, &in.spectral.stdDev);
+  in.lnAvgLoudness = calc_ln_avg_loud(in.all[0], 0, len1i);
+
+  const float w = cfg->temporalWeight;
+  float **eInBuf = alloc_planar(numCh, bufSz);
+  int64_t left = len2, filePos = pos2, nOut = 0;
+  int readSz = bufSz, readOff = 0, logicalOff = 0;
+  while (left > 0) {                    /* :135-171 */
+    int chunkLen = (int)(left < readSz ? left : readSz);
+    read_frames(fIn2, numCh, filePos, eInBuf, readOff, chunkLen);
+    filePos += chunkLen;
+    int eInBufOff = logicalOff % len1i;
+    sgz_o_normalize(cfg->norm, eInBuf, numCh, readOff, chunkLen);
+    float boost = calc_boost(&in, eInBuf[0]);
+    float sim;
+    if (boost <= cfg->maxBoost) {
+      /* private correlate (:177-185): stat over b[0, numFrames), MathUtil.correlate wraps % b.length = 8192 */
+      float temporal = (w > 0.0f) ? corr_wrap(&in.temporal, (const float *const *)eInBuf, bufSz, eInBufOff, 0) : 0.0f;
+      float spectral = (w < 1.0f) ? corr_wrap(&in.spectral, (const float *const *)eInBuf, bufSz, eInBufOff, 1) : 0.0f;
+      sim = temporal * w + spectral * (1.0f - w);
+    } else {
+      sim = 0.0f;
+    }
+    if (nOut < cap) sim_out[nOut] = sim;
+    nOut++;
+    left -= chunkLen;
+    readOff = (readOff + chunkLen) % len1i;
+    logicalOff += 1;
+    readSz = 1;
+  }
+  free_planar(eInBuf, numCh);
+  free_planar(in.all, numCh);
+  return nOut;
+}

@@ -13,6 +13,7 @@
  *   Impl/FeatureCorrelationImpl.scala:32-421
  *   Impl/FeatureSegmentationImpl.scala:31-142
  *   Impl/SelfSimilarityImpl.scala:31-180
+ *   Impl/CrossSimilarityImpl.scala:32-187
  *   Impl/SpanUtil.scala:38-43, Api/FeatureCorrelation.scala:75-77,
  *   Api/FeatureSegmentation.scala:60-62
  *
@@ -141,6 +142,31 @@ int sgz_o_self_image(const sgz_o_self_cfg *cfg, const float *file1, int64_t nFra
 int sgz_o_self_cells(const sgz_o_self_cfg *cfg, const float *file1, int64_t nFrames1,
                      const float *file2, int64_t nFrames2, int64_t nCells,
                      const int32_t *leftIdx, const int32_t *rightIdx, float *sim, int32_t *rgb);
+
+/* ---- CrossSimilarityImpl.body(), Impl/CrossSimilarityImpl.scala:32-187 ----
+ * The reference is restated AS IT BEHAVES, including its ring-buffer quirks:
+ *  - the buffer has 8192 frames; the FIRST read takes min(len2, 8192) frames, every later read one
+ *    frame, written at readOff which wraps modulo len1 (:140-141,165);
+ *  - MathUtil.correlate wraps its read index modulo the BUFFER length 8192 (MathUtil.scala:189), not
+ *    modulo len1, so logical frame i of output k is buffer position (i + k % len1) % 8192;
+ *  - mean / std-dev / loudness average of "b" always come from buffer positions [0, len1) (:181-185);
+ *  - hence 1 + len2 - min(len2, 8192) output values.
+ * len1 > 8192 fails in the reference with ArrayIndexOutOfBounds -> returns -2 here. */
+typedef struct {
+  int32_t numCh;
+  int32_t stepSize;
+  const float *norm;
+  int32_t has1Start, has1Stop;           /* span1 */
+  int64_t span1Start, span1Stop;
+  int32_t has2Start, has2Stop;           /* span2 */
+  int64_t span2Start, span2Stop;
+  float   temporalWeight;
+  float   maxBoost;
+} sgz_o_cross_cfg;
+
+/* returns the number of output values (written up to cap), <0 on error */
+int64_t sgz_o_cross_run(const sgz_o_cross_cfg *cfg, const float *file1, int64_t nFrames1,
+                        const float *file2, int64_t nFrames2, float *sim, int64_t cap);
 
 #ifdef __cplusplus
 }

@@ -32,7 +32,8 @@ SYMBOLS = [
     "sgz_corr_wait", "sgz_corr_result", "sgz_corr_num_offsets", "sgz_corr_timing", "sgz_corr_curve",
     "sgz_corr_scan", "sgz_corr_local_summary", "sgz_corr_set_global", "sgz_corr_select", "sgz_corr_records",
     "sgz_corr_merge",
-    "sgz_segm_run", "sgz_self_geometry_of", "sgz_self_run", "sgz_self_cells", "sgz_measure_peak",
+    "sgz_segm_run", "sgz_self_geometry_of", "sgz_self_run", "sgz_self_cells", "sgz_cross_num_outputs",
+    "sgz_cross_run", "sgz_measure_peak",
 ]
 
 
@@ -68,6 +69,14 @@ class SegmConfig(C.Structure):
     _fields_ = [("stepSize", C.c_int32), ("hasStart", C.c_int32), ("hasStop", C.c_int32),
                 ("spanStart", C.c_int64), ("spanStop", C.c_int64), ("corrLen", C.c_int64),
                 ("temporalWeight", C.c_float), ("numBreaks", C.c_int32), ("minSpacing", C.c_int64)]
+
+
+class CrossConfig(C.Structure):
+    _fields_ = [("stepSize", C.c_int32), ("has1Start", C.c_int32), ("has1Stop", C.c_int32),
+                ("has2Start", C.c_int32), ("has2Stop", C.c_int32), ("_pad", C.c_int32),
+                ("span1Start", C.c_int64), ("span1Stop", C.c_int64),
+                ("span2Start", C.c_int64), ("span2Stop", C.c_int64),
+                ("temporalWeight", C.c_float), ("maxBoost", C.c_float)]
 
 
 class SelfConfig(C.Structure):

@@ -6,6 +6,7 @@
 #include "segm.cuh"
 #include "selfsim.cuh"
 #include "selfsim_fast.cuh"
+#include "cross.cuh"
 
 namespace sgz {
 
@@ -312,6 +313,102 @@ int sgz_self_cells(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh, cons
   SGZ_TRY(ctx->end_call());
   if (sim) SGZ_CUDA(cudaMemcpyAsync(sim, dSim.p, nCells * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   if (rgb) SGZ_CUDA(cudaMemcpyAsync(rgb, dRgb.p, nCells * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SGZ_OK;
+}
+
+// openInput, CrossSimilarityImpl.scala:69-82
+static void cross_open(int step, int hasStart, int hasStop, int64_t spStart, int64_t spStop, int64_t numFrames,
+                       int64_t &start, int64_t &len) {
+  const int64_t s = hasStart ? sgz::full_to_feat(spStart, step) : 0;
+  const int64_t e = hasStop ? sgz::full_to_feat(spStop, step) : numFrames;
+  const int64_t stop = std::min(numFrames, e);
+  start = std::max<int64_t>(0, std::min(stop, s));
+  len = stop - start;
+}
+
+int sgz_cross_num_outputs(const sgz_cross_config *cfg, int64_t nFrames1, int64_t nFrames2, int64_t *nOut) {
+  SGZ_REQUIRE(cfg && nOut, "sgz_cross_num_outputs: NULL argument");
+  SGZ_REQUIRE(cfg->stepSize > 0, "stepSize must be > 0");
+  int64_t st1, l1, st2, l2;
+  cross_open(cfg->stepSize, cfg->has1Start, cfg->has1Stop, cfg->span1Start, cfg->span1Stop, nFrames1, st1, l1);
+  cross_open(cfg->stepSize, cfg->has2Start, cfg->has2Stop, cfg->span2Start, cfg->span2Stop, nFrames2, st2, l2);
+  const int64_t lenA = std::min(l1, l2), lenB = std::max(l1, l2);
+  SGZ_REQUIRE(lenA <= sgz::kCrossBuf, "shorter input has %lld feature frames; the reference's 8192-frame buffer "
+              "overflows (ArrayIndexOutOfBoundsException)", (long long)lenA);
+  SGZ_REQUIRE(lenA > 0 || lenB == 0, "shorter input span is empty (reference: ArithmeticException, % 0)");
+  *nOut = lenB > 0 ? 1 + lenB - std::min<int64_t>(lenB, sgz::kCrossBuf) : 0;
+  return SGZ_OK;
+}
+
+int sgz_cross_run(sgz_ctx *ctx, const sgz_cross_config *cfg, int32_t numCh, const float *norm, const void *frames1,
+                  int64_t nFrames1, const void *frames2, int64_t nFrames2, int32_t layout, float *sim, int64_t simCap,
+                  int64_t *nOut) {
+  using namespace sgz;
+  SGZ_REQUIRE(ctx && cfg && frames1 && frames2 && nOut, "sgz_cross_run: NULL argument");
+  SGZ_REQUIRE(numCh >= 2 && numCh <= 48, "numCh = numCoeffs + 1 must be in [2,48], got %d", numCh);
+  SGZ_REQUIRE(layout >= 0 && layout <= 2, "unknown layout %d", layout);
+  SGZ_TRY(ctx->bind());
+  int64_t n = 0;
+  SGZ_TRY(sgz_cross_num_outputs(cfg, nFrames1, nFrames2, &n));
+  *nOut = n;
+  if (n == 0) return SGZ_OK;
+  SGZ_REQUIRE(!sim || simCap >= n, "sim buffer too small (%lld < %lld)", (long long)simCap, (long long)n);
+  int64_t st1, l1, st2, l2;
+  cross_open(cfg->stepSize, cfg->has1Start, cfg->has1Stop, cfg->span1Start, cfg->span1Stop, nFrames1, st1, l1);
+  cross_open(cfg->stepSize, cfg->has2Start, cfg->has2Stop, cfg->span2Start, cfg->span2Stop, nFrames2, st2, l2);
+  // shorter span -> template (afIn1, read completely), longer -> slid over (afIn2); ties go to file 2 (:93-95)
+  const bool firstIsTemplate = l1 < l2;
+  const void *fA = firstIsTemplate ? frames1 : frames2, *fB = firstIsTemplate ? frames2 : frames1;
+  const int64_t nA = firstIsTemplate ? nFrames1 : nFrames2, nB = firstIsTemplate ? nFrames2 : nFrames1;
+  const int64_t posA = firstIsTemplate ? st1 : st2, posB = firstIsTemplate ? st2 : st1;
+  const int L = (int)(firstIsTemplate ? l1 : l2);
+  const int64_t lenB = firstIsTemplate ? l2 : l1;
+
+  // matrixIn (:100-116): normalise, MathUtil.stat per group, ln of the loudness average -- host side, Double
+  std::vector<float> planar;
+  to_planar(fA, nA, numCh, layout, planar);
+  std::vector<float> a((size_t)numCh * L);
+  for (int c = 0; c < numCh; c++) {
+    const float mn = norm ? norm[2 * c] : 0.f, d = norm ? norm[2 * c + 1] - mn : 1.f;
+    for (int i = 0; i < L; i++) {
+      const float f = planar[(size_t)c * nA + posA + i];
+      a[(size_t)c * L + i] = norm ? (f - mn) / d : f;
+    }
+  }
+  auto stat = [&](int c0, int c1, double &mean, double &sd) {
+    double sum = 0.0;
+    for (int c = c0; c < c1; c++) for (int i = 0; i < L; i++) sum += a[(size_t)c * L + i];
+    const int matSize = L * (c1 - c0);
+    mean = sum / matSize;
+    sum = 0.0;
+    for (int c = c0; c < c1; c++) for (int i = 0; i < L; i++) { double dd = a[(size_t)c * L + i] - mean; sum += dd * dd; }
+    sd = sqrt(sum / matSize);
+  };
+  CrossParams p{};
+  stat(0, 1, p.meanT, p.stdT);
+  stat(1, numCh, p.meanS, p.stdS);
+  {
+    double sum = 0.0;
+    for (int i = 0; i < L; i++) sum += a[i];
+    p.lnAvgIn = log((double)(float)(sum / L));
+  }
+  DevBuf<float> x, dA, dSim;
+  int64_t stride = 0;
+  SGZ_TRY(upload_features(ctx, numCh, norm, fB, nB, layout, posB, lenB, x, stride));
+  SGZ_TRY(dA.alloc(a.size()));
+  SGZ_TRY(dSim.alloc((size_t)n));
+  SGZ_CUDA(cudaMemcpyAsync(dA.p, a.data(), a.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  p.x = x.p; p.stride = stride; p.a = dA.p; p.numCh = numCh; p.L = L;
+  p.c0 = (int)std::min<int64_t>(lenB, kCrossBuf);
+  p.nOut = n;
+  p.weight = cfg->temporalWeight; p.maxBoost = cfg->maxBoost;
+  p.sim = dSim.p;
+  SGZ_TRY(ctx->begin_call());
+  k_cross<<<(unsigned)ceil_div<int64_t>(n, 64), 64, 0, ctx->stream>>>(p);
+  SGZ_LAUNCH_CHECK(ctx);
+  SGZ_TRY(ctx->end_call());
+  if (sim) SGZ_CUDA(cudaMemcpyAsync(sim, dSim.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
   return SGZ_OK;
 }

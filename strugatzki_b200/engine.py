@@ -269,6 +269,20 @@ def segm_run(ctx: Context, cfg: N.SegmConfig, frames: np.ndarray, norm: Optional
     return breaks
 
 
+def cross_run(ctx: Context, cfg: N.CrossConfig, frames1: np.ndarray, frames2: np.ndarray,
+              norm: Optional[np.ndarray] = None) -> np.ndarray:
+    """CrossSimilarity: the sim curve the reference writes into its 1-channel output file."""
+    a1, a2 = _frames(frames1), _frames(frames2)
+    nrm = None if norm is None else np.ascontiguousarray(norm, np.float32)
+    n = C.c_int64()
+    N.check(N.lib().sgz_cross_num_outputs(C.byref(cfg), C.c_int64(a1.shape[0]), C.c_int64(a2.shape[0]), C.byref(n)))
+    sim = np.zeros(max(n.value, 1), np.float32)
+    N.check(N.lib().sgz_cross_run(ctx._h, C.byref(cfg), a1.shape[1], None if nrm is None else N.fptr(nrm),
+                                  N.fptr(a1), C.c_int64(a1.shape[0]), N.fptr(a2), C.c_int64(a2.shape[0]),
+                                  N.LAYOUT_INTERLEAVED_LE, N.fptr(sim), C.c_int64(sim.shape[0]), C.byref(n)))
+    return sim[:n.value]
+
+
 def self_geometry(cfg: N.SelfConfig, n1: int, n2: int) -> dict:
     g = N.SelfGeometry()
     N.check(N.lib().sgz_self_geometry_of(C.byref(cfg), C.c_int64(n1), C.c_int64(n2), C.byref(g)))

@@ -38,7 +38,7 @@ def test_struct_layouts_match_header():
     # sizes the Scala/JNI or ctypes side relies on
     assert C.sizeof(N.Match) == 32 and C.sizeof(N.Break) == 16 and C.sizeof(N.Record) == 32
     assert C.sizeof(N.FileSummary) == 16 and C.sizeof(N.SelfGeometry) == 24
-    assert C.sizeof(N.CorrConfig) == 96 and C.sizeof(N.SegmConfig) == 56
+    assert C.sizeof(N.CorrConfig) == 96 and C.sizeof(N.SegmConfig) == 56 and C.sizeof(N.CrossConfig) == 64
 
 
 def test_built_for_sm_100a_only():
@@ -70,3 +70,20 @@ def test_geometry_needs_no_gpu():
     assert g == dict(imgExt=38707, decim=4, numCorrs=154829, afStart=0, numCells=38707 * 38708 // 2)
     g = engine.self_geometry(cfg, 1000, 900)
     assert (g["imgExt"], g["decim"], g["numCorrs"]) == (729, 1, 729)
+
+
+def test_cross_output_count_needs_no_gpu():
+    # CrossSimilarityImpl.scala:127-171: the first read swallows min(len2, 8192) frames, then one value per frame
+    n = C.c_int64()
+    cfg = N.CrossConfig(512, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.5, 8.0)
+    for n1, n2, want in ((300, 9000, 809), (9000, 300, 809), (300, 8192, 1), (300, 500, 1), (0, 0, 0)):
+        assert N.lib().sgz_cross_num_outputs(C.byref(cfg), C.c_int64(n1), C.c_int64(n2), C.byref(n)) == 0
+        assert n.value == want, (n1, n2, n.value)
+    # spans: [100*512, 400*512) of file 1 -> 300 frames
+    cfg = N.CrossConfig(512, 1, 1, 0, 0, 0, 100 * 512, 400 * 512, 0, 0, 0.5, 8.0)
+    assert N.lib().sgz_cross_num_outputs(C.byref(cfg), C.c_int64(5000), C.c_int64(10000), C.byref(n)) == 0
+    assert n.value == 1 + 10000 - 8192
+    cfg = N.CrossConfig(512, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.5, 8.0)
+    assert N.lib().sgz_cross_num_outputs(C.byref(cfg), C.c_int64(9000), C.c_int64(10000), C.byref(n)) == N.ERR_INVALID
+    assert b"8192" in N.lib().sgz_last_error()
+    assert N.lib().sgz_cross_num_outputs(C.byref(cfg), C.c_int64(0), C.c_int64(100), C.byref(n)) == N.ERR_INVALID

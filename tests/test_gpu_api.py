@@ -9,7 +9,8 @@ from util import O, STEP, make_db, make_input, plant_needles, synth
 from strugatzki_b200 import feature_correlation as fc
 from strugatzki_b200 import feature_segmentation as fs
 from strugatzki_b200 import self_similarity as ss
-from strugatzki_b200.io import FeatureExtractionConfig, Span, write_aiff, write_norm_file
+from strugatzki_b200 import cross_similarity as cs
+from strugatzki_b200.io import FeatureExtractionConfig, Span, read_aiff, write_aiff, write_norm_file
 from strugatzki_b200.processor import Progress, Result, Success
 
 pytestmark = pytest.mark.gpu
@@ -99,3 +100,19 @@ def test_segmentation_and_selfsimilarity_processors(ctx, tmp_path):
     with pytest.raises(RuntimeError):   # PsychoOptical without the third-party palette table
         ss.SelfSimilarity.run(ss.Config(folder, meta, None, png, Span.until(400 * STEP), 20480, 2, 0.5,
                                         ss.PsychoOptical)).await_result(60)
+
+
+def test_cross_similarity_processor(ctx, tmp_path):
+    folder = str(tmp_path)
+    files, norm = make_db(2, [260, 8900])
+    m1 = write_feature_file(folder, "short", files[0])
+    m2 = write_feature_file(folder, "long", files[1])
+    write_norm_file(folder, norm)
+    out = os.path.join(folder, "cross.aif")
+    cfg = cs.Config(folder, m1, m2, out, "aiff", Span.all(), Span.from_(100 * STEP), 0.5, True, 8.0)
+    assert cs.Config.from_xml(cfg.to_xml()) == cfg
+    assert cs.CrossSimilarity.run(cfg).await_result(60) is None
+    got, spec = read_aiff(out)
+    want = O.cross_run(O.CrossParams(step_size=STEP, norm=norm, span2=(100 * STEP, None)), files[0], files[1])
+    assert spec.num_channels == 1 and abs(spec.sample_rate - 44100.0 / STEP) < 1e-9
+    assert np.array_equal(got[:, 0].view(np.uint32), want.view(np.uint32))

@@ -343,3 +343,40 @@ def test_streaming_scan_behind_async_upload(ctx, punch_out):
         db.finalize()                                              # explicit wait is a no-op now
         job.close()
         db.close()
+
+
+@pytest.mark.parametrize("n1,n2,w,use_norm,span1,span2", [
+    (300, 9000, 0.5, True, (None, None), (None, None)),
+    (9300, 172, 0.3, True, (None, None), (None, None)),          # template is the SECOND file
+    (300, 8192, 0.5, False, (None, None), (None, None)),         # first read swallows everything: one value
+    (2000, 12000, 0.0, True, (100 * 512, 350 * 512), (None, 11000 * 512)),
+    (400, 9500, 1.0, True, (None, None), (700 * 512, None)),
+    (5000, 8700, 0.5, True, (None, None), (None, None)),         # L > 4096: the read index wraps at 8192
+])
+def test_cross_similarity_bit_identical(ctx, n1, n2, w, use_norm, span1, span2):
+    """CrossSimilarity curve: the engine replays the reference's ring buffer exactly"""
+    from strugatzki_b200 import engine
+    files, norm = make_db(2, [n1, n2])
+    norm = norm if use_norm else None
+    want = O.cross_run(O.CrossParams(step_size=STEP, norm=norm, temporal_weight=w, span1=span1, span2=span2),
+                       files[0], files[1])
+    cfg = N.CrossConfig(STEP, int(span1[0] is not None), int(span1[1] is not None), int(span2[0] is not None),
+                        int(span2[1] is not None), 0, span1[0] or 0, span1[1] or 0, span2[0] or 0, span2[1] or 0, w, 8.0)
+    got = engine.cross_run(ctx, cfg, files[0], files[1], norm)
+    assert got.shape == want.shape and got.shape[0] >= 1
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_cross_similarity_boost_gate_and_errors(ctx):
+    from strugatzki_b200 import engine, NativeError
+    files, norm = make_db(2, [300, 9000])
+    quiet = files[1].copy()
+    quiet[:, 0] *= np.float32(0.02)                   # boost > maxBoost -> sim forced to 0f
+    cfg = N.CrossConfig(STEP, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.5, 2.0)
+    got = engine.cross_run(ctx, cfg, files[0], quiet, None)
+    want = O.cross_run(O.CrossParams(step_size=STEP, norm=None, max_boost=2.0), files[0], quiet)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)) and np.all(got == 0.0)
+    big, _ = make_db(2, [9000, 9100])
+    with pytest.raises(NativeError) as ei:            # reference: ArrayIndexOutOfBoundsException
+        engine.cross_run(ctx, cfg, big[0], big[1], None)
+    assert ei.value.code == N.ERR_INVALID

@@ -166,3 +166,38 @@ def test_golden_fixtures():
             want = data[f"{name}.{key}"]
             assert np.array_equal(np.asarray(val).view(np.uint8), want.view(np.uint8)), f"{name}.{key} changed"
     assert sorted(meta["cases"]) == sorted(cases().keys())
+
+
+def _cross_numpy(f1, f2, norm, w, step=512):
+    """independent formulation of CrossSimilarityImpl's ring (see strugatzki_b200/csrc/cross.cuh): simulate the
+    8192-frame buffer with plain numpy writes, correlate with float64 numpy reductions"""
+    nz = lambda f: ((f - norm[:, 0]) / (norm[:, 1] - norm[:, 0])).astype(np.float32) if norm is not None else f
+    a, b = (f1, f2) if f1.shape[0] < f2.shape[0] else (f2, f1)
+    a, b = nz(a), nz(b)
+    L, len2 = a.shape[0], b.shape[0]
+    c0 = min(len2, 8192)
+    buf = np.zeros((8192, a.shape[1]), np.float32)
+    buf[:c0] = b[:c0]
+    out = []
+
+    def corr(x, bstat, bwin):
+        x = x.astype(np.float64)
+        return ((x - x.mean()) * (bwin.astype(np.float64) - bstat.astype(np.float64).mean())).sum() / (
+            x.std() * bstat.astype(np.float64).std() * x.size)
+    for k in range(1 + len2 - c0):
+        if k >= 1:
+            buf[(c0 + k - 1) % L] = b[c0 + k - 1]
+        idx = (np.arange(L) + k % L) % 8192
+        t = np.float32(corr(a[:, :1], buf[:L, :1], buf[idx][:, :1]))
+        s = np.float32(corr(a[:, 1:], buf[:L, 1:], buf[idx][:, 1:]))
+        out.append(t * np.float32(w) + s * (np.float32(1) - np.float32(w)))
+    return np.array(out, np.float32)
+
+
+@pytest.mark.parametrize("n1,n2,w", [(300, 8700, 0.5), (8600, 172, 0.3), (200, 500, 0.5)])
+def test_cross_similarity_ring_semantics(n1, n2, w):
+    files, norm = make_db(2, [n1, n2])
+    got = O.cross_run(O.CrossParams(step_size=512, norm=norm, temporal_weight=w), files[0], files[1])
+    want = _cross_numpy(files[0], files[1], norm, w)
+    assert got.shape == want.shape == (1 + max(n1, n2) - min(max(n1, n2), 8192),)
+    assert np.allclose(got, want, rtol=2e-6, atol=2e-7)
