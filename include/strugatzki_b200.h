@@ -177,6 +177,12 @@ int sgz_db_finalize(sgz_db *db);
  * reference's loop that reads one file and correlates it (FeatureCorrelationImpl.scala:161-199), so the scan
  * hides behind the PCIe transfer.  Calling sgz_db_finalize afterwards is the explicit wait. */
 int sgz_db_finalize_async(sgz_db *db);
+/* FeatureStats (replaces FeatureStatsImpl.body(), Impl/FeatureStatsImpl.scala:30-135; the producer of
+ * feat_norms.aif, Strugatzki.scala:411-430).  The database must hold RAW features (norm = NULL at create).
+ * out[numCh][2] = per channel (min over files of the file's 1st percentile, max over files of its 99th) as
+ * Doubles -- the host narrows them to Float when it writes the norm file; perFile (optional) =
+ * [numFiles][numCh][2]. */
+int sgz_db_stats(sgz_db *db, double *out, double *perFile);
 int sgz_db_info(sgz_db *db, int32_t *numFiles, int64_t *totalFrames, int32_t *numCh);
 int sgz_db_file_frames(sgz_db *db, int32_t file, int64_t *nFrames);
 /* Reads back NORMALISED frames [frameOff, frameOff+n) of a file as planar [numCh][n]. */

@@ -287,3 +287,16 @@ def cross_run(p: CrossParams, file1: np.ndarray, file2: np.ndarray) -> np.ndarra
     if n < 0:
         raise RuntimeError(f"oracle cross_run failed: {n}")
     return out[:n].copy()
+
+
+def stats_run(files: Sequence[np.ndarray], want_per_file: bool = False):
+    """FeatureStatsImpl.body(): [numCh][2] doubles = (min of the files' 1st percentiles, max of their 99th)."""
+    fs = [_f32(f) for f in files]
+    num_ch = fs[0].shape[1]
+    ptrs = (C.c_void_p * len(fs))(*[f.ctypes.data for f in fs])
+    nfr = (C.c_int64 * len(fs))(*[f.shape[0] for f in fs])
+    out = np.zeros((num_ch, 2), np.float64)
+    per = np.zeros((len(fs), num_ch, 2), np.float64) if want_per_file else None
+    lib().sgz_o_stats_run(num_ch, len(fs), ptrs, nfr, out.ctypes.data_as(C.c_void_p),
+                          None if per is None else per.ctypes.data_as(C.c_void_p))
+    return (out, per) if want_per_file else out

@@ -838,3 +838,78 @@ int64_t sgz_o_cross_run(const sgz_o_cross_cfg *cfg, const float *file1, int64_t 
   free_planar(in.all, numCh);
   return nOut;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * FeatureStatsImpl, Impl/FeatureStatsImpl.scala:30-135
+ * ---------------------------------------------------------------------------------------- */
+
+static double j_min(double a, double b) { return (a != a || b != b) ? NAN : (a < b ? a : b); }   /* math.min */
+static double j_max(double a, double b) { return (a != a || b != b) ? NAN : (a > b ? a : b); }   /* math.max */
+
+/* body1, :55-135: (p01[ch], p99[ch]) of one file */
+static void stats_body1(int numCh, const float *file, int64_t numFrames, double *p01, double *p99) {
+  float *maxs = (float *)malloc(sizeof(float) * (size_t)numCh);
+  float *mins = (float *)malloc(sizeof(float) * (size_t)numCh);
+  double *sums = (double *)calloc((size_t)numCh, sizeof(double));
+  double *skews = (double *)calloc((size_t)numCh, sizeof(double));
+  int32_t *pctils = (int32_t *)calloc((size_t)numCh * 2048, sizeof(int32_t));
+  for (int ch = 0; ch < numCh; ch++) { maxs[ch] = -INFINITY; mins[ch] = INFINITY; }
+  /* first pass (:70-84); the 8192-frame chunking does not change the per-channel order */
+  for (int ch = 0; ch < numCh; ch++) {
+    for (int64_t i = 0; i < numFrames; i++) {
+      float f = file[i * numCh + ch];
+      if (f < mins[ch]) mins[ch] = f;
+      if (f > maxs[ch]) maxs[ch] = f;
+      sums[ch] += f;
+    }
+  }
+  const double log05 = log(0.5);
+  for (int ch = 0; ch < numCh; ch++) {       /* :86-92 */
+    double mean = sums[ch] / (double)numFrames;
+    float d = maxs[ch] - mins[ch];
+    double mn = (mean - mins[ch]) / d;
+    skews[ch] = log05 / log(mn);
+  }
+  for (int ch = 0; ch < numCh; ch++) {       /* second pass, :94-113 */
+    int32_t *cp = pctils + (size_t)ch * 2048;
+    float mn = mins[ch];
+    float d = maxs[ch] - mn;
+    double skew = skews[ch];
+    for (int64_t i = 0; i < numFrames; i++) {
+      float f = file[i * numCh + ch];
+      int32_t norm = j_d2i(pow((double)((f - mn) / d), skew) * 2047 + 0.5);
+      if (norm >= 0 && norm < 2048) cp[norm] += 1;   /* outside: ArrayIndexOutOfBounds upstream; cannot happen for finite data */
+    }
+  }
+  for (int ch = 0; ch < numCh; ch++) {       /* :115-131 */
+    const int32_t *cp = pctils + (size_t)ch * 2048;
+    int32_t p01n = j_d2i((double)numFrames * 0.01);
+    int32_t p99n = j_d2i((double)numFrames * 0.99);
+    double skewr = 1.0 / skews[ch];
+    float mn = mins[ch];
+    float d = maxs[ch] - mn;
+    int32_t cnt = 0;
+    int i = 0;
+    while (cnt < p01n && i < 2048) { cnt += cp[i]; i++; }
+    p01[ch] = pow((double)i / 2048, skewr) * d + mn;
+    while (cnt < p99n && i < 2048) { cnt += cp[i]; i++; }
+    p99[ch] = pow((double)i / 2048, skewr) * d + mn;
+  }
+  free(maxs); free(mins); free(sums); free(skews); free(pctils);
+}
+
+int sgz_o_stats_run(int numCh, int numFiles, const float *const *files, const int64_t *nFrames, double *out,
+                    double *perFile) {
+  double *p01 = (double *)malloc(sizeof(double) * (size_t)numCh);
+  double *p99 = (double *)malloc(sizeof(double) * (size_t)numCh);
+  for (int f = 0; f < numFiles; f++) {       /* body, :30-53 */
+    stats_body1(numCh, files[f], nFrames[f], p01, p99);
+    for (int ch = 0; ch < numCh; ch++) {
+      if (perFile) { perFile[((size_t)f * numCh + ch) * 2] = p01[ch]; perFile[((size_t)f * numCh + ch) * 2 + 1] = p99[ch]; }
+      if (f == 0) { out[2 * ch] = p01[ch]; out[2 * ch + 1] = p99[ch]; }
+      else { out[2 * ch] = j_min(out[2 * ch], p01[ch]); out[2 * ch + 1] = j_max(out[2 * ch + 1], p99[ch]); }
+    }
+  }
+  free(p01); free(p99);
+  return numFiles;
+}

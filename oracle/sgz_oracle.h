@@ -14,6 +14,7 @@
  *   Impl/FeatureSegmentationImpl.scala:31-142
  *   Impl/SelfSimilarityImpl.scala:31-180
  *   Impl/CrossSimilarityImpl.scala:32-187
+ *   Impl/FeatureStatsImpl.scala:30-135
  *   Impl/SpanUtil.scala:38-43, Api/FeatureCorrelation.scala:75-77,
  *   Api/FeatureSegmentation.scala:60-62
  *
@@ -167,6 +168,15 @@ typedef struct {
 /* returns the number of output values (written up to cap), <0 on error */
 int64_t sgz_o_cross_run(const sgz_o_cross_cfg *cfg, const float *file1, int64_t nFrames1,
                         const float *file2, int64_t nFrames2, float *sim, int64_t cap);
+
+/* ---- FeatureStatsImpl.body(), Impl/FeatureStatsImpl.scala:30-135 ----
+ * Per channel: (min over files of the file's 1st percentile, max over files of its 99th), the percentiles taken
+ * from a 2048-bin histogram of the skew-warped values.  files[i] = interleaved RAW frames.  out = [numCh][2]
+ * doubles (the reference narrows them to Float when it writes feat_norms.aif, Strugatzki.scala:417-426);
+ * perFile (optional) = [numFiles][numCh][2].  math.pow / math.log are libm's here (Java's are within 1 ulp of
+ * them, not bit-identical: parity unpinned like the rest). */
+int sgz_o_stats_run(int numCh, int numFiles, const float *const *files, const int64_t *nFrames, double *out,
+                    double *perFile);
 
 #ifdef __cplusplus
 }

@@ -9,6 +9,7 @@
 #include "segm.cuh"
 #include "select.cuh"
 #include "selfsim.cuh"
+#include "stats.cuh"
 
 using namespace sgz;
 
@@ -334,6 +335,62 @@ int sgz_db_finalize_async(sgz_db *db) {
   SGZ_REQUIRE(db, "db is NULL");
   SGZ_TRY(db->ctx->bind());
   if (!db->finalized) SGZ_TRY(db_finalize_enqueue(db));
+  return SGZ_OK;
+}
+
+int sgz_db_stats(sgz_db *db, double *out, double *perFileOut) {
+  SGZ_REQUIRE(db && out, "sgz_db_stats: NULL argument");
+  if (!db->finalized) { set_error("sgz_db_stats: database not finalized"); return SGZ_ERR_STATE; }
+  SGZ_REQUIRE(!db->hasNorm, "sgz_db_stats works on RAW features: create the database with norm = NULL");
+  sgz_ctx *ctx = db->ctx;
+  SGZ_TRY(ctx->bind());
+  SGZ_TRY(db_wait_resident(db));
+  const int nf = db->numFiles(), nc = db->numCh;
+  SGZ_REQUIRE(nf > 0, "sgz_db_stats: empty database");
+  DevBuf<float> dMins, dMaxs;
+  DevBuf<double> dSkews, dPer;
+  DevBuf<int32_t> dHist;
+  SGZ_TRY(dMins.alloc((size_t)nf * nc));
+  SGZ_TRY(dMaxs.alloc((size_t)nf * nc));
+  SGZ_TRY(dSkews.alloc((size_t)nf * nc));
+  SGZ_TRY(dPer.alloc((size_t)nf * nc * 2));
+  const int batch = std::min(nf, 1024);
+  SGZ_TRY(dHist.alloc((size_t)batch * nc * kStatBins));
+  StatsParams p{};
+  p.data = db->dData.p; p.rowStride = db->capFrames; p.fileStart = db->dFileStart.p;
+  p.numFiles = nf; p.numCh = nc; p.numPairs = db->numPairs;
+  p.mins = dMins.p; p.maxs = dMaxs.p; p.skews = dSkews.p; p.hist = dHist.p; p.perFile = dPer.p;
+  SGZ_TRY(ctx->begin_call());
+  k_stats_minmax<<<ceil_div(nf * db->numPairs, 64), 64, 0, ctx->stream>>>(p);
+  SGZ_LAUNCH_CHECK(ctx);
+  for (int f0 = 0; f0 < nf; f0 += batch) {
+    p.file0 = f0;
+    p.fileCount = std::min(batch, nf - f0);
+    int64_t longest = 0;
+    for (int f = f0; f < f0 + p.fileCount; f++) longest = std::max(longest, db->fileStart[f + 1] - db->fileStart[f]);
+    SGZ_CUDA(cudaMemsetAsync(dHist.p, 0, (size_t)p.fileCount * nc * kStatBins * sizeof(int32_t), ctx->stream));
+    if (longest > 0) {
+      dim3 grid((unsigned)ceil_div<int64_t>(longest, kStatSeg), (unsigned)db->numPairs, (unsigned)p.fileCount);
+      k_stats_hist<<<grid, 256, 0, ctx->stream>>>(p);
+      SGZ_LAUNCH_CHECK(ctx);
+    }
+    k_stats_pctl<<<ceil_div(p.fileCount * nc, 128), 128, 0, ctx->stream>>>(p);
+    SGZ_LAUNCH_CHECK(ctx);
+  }
+  SGZ_TRY(ctx->end_call());
+  std::vector<double> per((size_t)nf * nc * 2);
+  SGZ_CUDA(cudaMemcpyAsync(per.data(), dPer.p, per.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  // body(), FeatureStatsImpl.scala:30-53: math.min / math.max over the files, in order (NaN propagates)
+  auto jmin = [](double a, double b) { return (a != a || b != b) ? (double)NAN : (a < b ? a : b); };
+  auto jmax = [](double a, double b) { return (a != a || b != b) ? (double)NAN : (a > b ? a : b); };
+  for (int f = 0; f < nf; f++)
+    for (int c = 0; c < nc; c++) {
+      const double lo = per[((size_t)f * nc + c) * 2], hi = per[((size_t)f * nc + c) * 2 + 1];
+      out[2 * c] = f == 0 ? lo : jmin(out[2 * c], lo);
+      out[2 * c + 1] = f == 0 ? hi : jmax(out[2 * c + 1], hi);
+    }
+  if (perFileOut) memcpy(perFileOut, per.data(), per.size() * sizeof(double));
   return SGZ_OK;
 }
 

@@ -131,6 +131,15 @@ class Database:
         """wait=False: do not wait for HOST_STABLE uploads in flight; the first search streams behind them."""
         N.check((N.lib().sgz_db_finalize if wait else N.lib().sgz_db_finalize_async)(self._h))
 
+    def stats(self, want_per_file: bool = False):
+        """FeatureStats over a RAW database (norm=None): [numCh][2] float64 (p01 min, p99 max)."""
+        nf = self.info()[0]
+        out = np.zeros((self.num_ch, 2), np.float64)
+        per = np.zeros((max(nf, 1), self.num_ch, 2), np.float64) if want_per_file else None
+        N.check(N.lib().sgz_db_stats(self._h, out.ctypes.data_as(C.c_void_p),
+                                     None if per is None else per.ctypes.data_as(C.c_void_p)))
+        return (out, per[:nf]) if want_per_file else out
+
     def info(self) -> Tuple[int, int, int]:
         nf, tf, nc = C.c_int32(), C.c_int64(), C.c_int32()
         N.check(N.lib().sgz_db_info(self._h, C.byref(nf), C.byref(tf), C.byref(nc)))

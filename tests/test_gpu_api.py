@@ -10,6 +10,7 @@ from strugatzki_b200 import feature_correlation as fc
 from strugatzki_b200 import feature_segmentation as fs
 from strugatzki_b200 import self_similarity as ss
 from strugatzki_b200 import cross_similarity as cs
+from strugatzki_b200 import feature_stats as fst
 from strugatzki_b200.io import FeatureExtractionConfig, Span, read_aiff, write_aiff, write_norm_file
 from strugatzki_b200.processor import Progress, Result, Success
 
@@ -116,3 +117,16 @@ def test_cross_similarity_processor(ctx, tmp_path):
     want = O.cross_run(O.CrossParams(step_size=STEP, norm=norm, span2=(100 * STEP, None)), files[0], files[1])
     assert spec.num_channels == 1 and abs(spec.sample_rate - 44100.0 / STEP) < 1e-9
     assert np.array_equal(got[:, 0].view(np.uint32), want.view(np.uint32))
+
+
+def test_feature_stats_processor_writes_norm_file(ctx, tmp_path):
+    folder = str(tmp_path)
+    files, _ = make_db(4, [2600, 3000, 2200, 2800])
+    for i, f in enumerate(files):
+        write_feature_file(folder, f"file{i:02d}", f)
+    res = fst.stats_of_folder(folder)
+    want = O.stats_run(files)
+    assert len(res) == 14 and np.allclose(np.array(res), want, rtol=1e-9)
+    from strugatzki_b200.io import read_norm_file
+    norm = read_norm_file(folder, 14)
+    assert np.array_equal(norm.view(np.uint32), want.astype(np.float32).view(np.uint32))

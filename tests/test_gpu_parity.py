@@ -380,3 +380,39 @@ def test_cross_similarity_boost_gate_and_errors(ctx):
     with pytest.raises(NativeError) as ei:            # reference: ArrayIndexOutOfBoundsException
         engine.cross_run(ctx, cfg, big[0], big[1], None)
     assert ei.value.code == N.ERR_INVALID
+
+
+def test_feature_stats_matches_oracle(ctx):
+    """FeatureStats: per-file percentiles and the database-wide (p01 min, p99 max) spans.
+    Counts are integers and the Double sum keeps the reference's order, so only libm-vs-CUDA pow/log ulps differ."""
+    from strugatzki_b200 import engine
+    files, _ = make_db(6, [3000, 52, 9000, 20000, 4100, 777])
+    files[2][:, 3] = np.float32(0.25)                    # constant channel: d == 0 -> NaN like the reference
+    files[3][:, 5] *= np.float32(-3.0)                   # negative values
+    want, want_per = O.stats_run(files, want_per_file=True)
+    db = engine.Database(ctx, 14, None)
+    for i, f in enumerate(files):
+        db.add_file(f.astype(">f4"), N.LAYOUT_INTERLEAVED_BE) if i % 2 else db.add_file(f)
+    db.finalize()
+    got, got_per = db.stats(want_per_file=True)
+    assert np.array_equal(np.isnan(got_per), np.isnan(want_per))
+    assert np.allclose(got_per, want_per, rtol=1e-9, atol=0, equal_nan=True)
+    assert np.allclose(got, want, rtol=1e-9, atol=0, equal_nan=True)
+    assert np.isnan(got[3]).all() and not np.isnan(got[[0, 1, 2, 4]]).any()
+    # what ends up in feat_norms.aif is the Float narrowing: identical bits
+    ok = ~np.isnan(want)
+    assert np.array_equal(got.astype(np.float32)[ok].view(np.uint32), want.astype(np.float32)[ok].view(np.uint32))
+    # a one-frame file has d == 0 in every channel: its NaNs poison all spans through math.min / math.max
+    tiny, _ = make_db(3, [500, 1, 600])
+    dbt = engine.Database(ctx, 14, None)
+    for f in tiny:
+        dbt.add_file(f)
+    dbt.finalize()
+    assert np.isnan(dbt.stats()).all() and np.isnan(O.stats_run(tiny)).all()
+    from strugatzki_b200 import NativeError
+    _, norm = make_db(1, 10)
+    dbn = engine.Database(ctx, 14, norm)
+    dbn.add_file(files[0])
+    dbn.finalize()
+    with pytest.raises(NativeError):                     # normalised database: stats need the raw values
+        dbn.stats()
