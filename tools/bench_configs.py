@@ -111,7 +111,8 @@ print(json.dumps(dict(config="configs[3] SelfSimilarity ~155k frames", frames=n,
                       cells=g["numCells"], gpu_kernel_ms=round(kms, 2), gpu_wall_ms=round(wall * 1e3, 1),
                       gpu_cells_per_s=round(g["numCells"] / (kms * 1e-3), 1), cpu_oracle_cells_per_s=round(2000 / c_s, 1),
                       mode="fast FP32 Gram (default)",
-                      sample_max_rel_err=float(np.max(np.abs(gs - ws) / np.maximum(np.abs(ws), 1e-3))),
+                      sample_max_abs_err=float(np.max(np.abs(gs - ws))),
+                      sample_max_rel_err_where_abs_sim_gt_0p05=float(np.max((np.abs(gs - ws) / np.abs(ws))[np.abs(ws) > 0.05])),
                       sample_max_grey_diff=int(np.max(np.abs((grgb & 255) - (wrgb & 255)))))), flush=True)
 pcfg = N.SelfConfig(STEP, 0, 0, 0, 0, 44100, 1, 0.5, 0, 1.0, 1.0, None, 0, 1)
 t = time.perf_counter(); _, g = engine.self_run(ctx, pcfg, sf, None, norm, download=False); wall = time.perf_counter() - t
@@ -121,3 +122,40 @@ print(json.dumps(dict(config="configs[3] SelfSimilarity ~155k frames", mode="pre
                       gpu_kernel_ms=round(kms, 2), gpu_cells_per_s=round(g["numCells"] / (kms * 1e-3), 1),
                       sample_cells_bit_identical=bool(np.array_equal(gs.view(np.uint32), ws.view(np.uint32))
                                                       and np.array_equal(grgb, wrgb)))), flush=True)
+
+
+# ---- section 8(f) rows: CrossSimilarity and FeatureStats ----
+cf = [synth.synth_file(synth.BASE_SEED, 900, 172, mu, sigma, floor0),
+      synth.synth_file(synth.BASE_SEED, 901, 310078 if not quick else 20000, mu, sigma, floor0)]
+ccfg = N.CrossConfig(STEP, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.5, 8.0)
+engine.cross_run(ctx, ccfg, cf[0], cf[1], norm)
+t = time.perf_counter(); gc = engine.cross_run(ctx, ccfg, cf[0], cf[1], norm); wall = time.perf_counter() - t
+kms, _ = ctx.last_timing()
+sub = cf[1][:8192 + 20000]
+t = time.perf_counter(); wc = O.cross_run(O.CrossParams(step_size=STEP, norm=norm), cf[0], sub); c_s = time.perf_counter() - t
+print(json.dumps(dict(config="8(f) CrossSimilarity: 2 s template over a 1 h feature file", outputs=int(gc.shape[0]),
+                      gpu_kernel_ms=round(kms, 3), gpu_wall_ms=round(wall * 1e3, 1),
+                      gpu_outputs_per_s=round(gc.shape[0] / (kms * 1e-3), 1),
+                      cpu_oracle_outputs_per_s=round(wc.shape[0] / c_s, 1),
+                      prefix_bit_identical=bool(np.array_equal(gc[:wc.shape[0]].view(np.uint32), wc.view(np.uint32))))),
+      flush=True)
+
+nst = 600 if not quick else 20
+raw = engine.Database(ctx, 14, None)
+raw.reserve(nst * 51680, nst)
+for i in range(nst):
+    raw.add_synth(synth.BASE_SEED, 5000 + i, 51680, mu, sigma, float(floor0))
+raw.finalize()
+raw.stats()
+t = time.perf_counter(); gst, gper = raw.stats(want_per_file=True); wall = time.perf_counter() - t
+kms, _ = ctx.last_timing()
+ncpu = 6
+fl = [synth.synth_file(synth.BASE_SEED, 5000 + i, 51680, mu, sigma, floor0) for i in range(ncpu)]
+t = time.perf_counter(); _, wper = O.stats_run(fl, want_per_file=True); c_s = time.perf_counter() - t
+frames = nst * 51680
+print(json.dumps(dict(config="8(f) FeatureStats over a 100 h raw feature database", files=nst, frames=frames,
+                      gpu_kernels_ms=round(kms, 3), gpu_wall_ms=round(wall * 1e3, 1),
+                      gpu_frames_per_s=round(frames / (kms * 1e-3), 1),
+                      algorithmic_GBps=round(frames * 112 / (kms * 1e-3) / 1e9, 1),
+                      cpu_oracle_frames_per_s=round(ncpu * 51680 / c_s, 1),
+                      per_file_max_rel_err=float(np.max(np.abs(gper[:ncpu] - wper) / np.abs(wper))))), flush=True)
