@@ -499,6 +499,12 @@ int sgz_corr_create(sgz_db *db, const sgz_corr_config *cfg, const void *input, i
   }
   if (rc != SGZ_OK) { delete job; return rc; }
   job->numTiles = ceil_div<int64_t>(std::max<int64_t>(db->usedFrames, 1), (int64_t)kR * job->ntg);
+  job->numTilesTc = ceil_div<int64_t>(std::max<int64_t>(db->usedFrames, 1), (int64_t)kTcTile);
+  {
+    // K1 on the tensor cores: opt-in while it is being qualified (SGZ_CORR_TC=1)
+    const char *e = getenv("SGZ_CORR_TC");
+    job->useTc = e && atoi(e) == 1 && job->qin.dTcTaps.p && (!job->hasOut || job->qout.dTcTaps.p);
+  }
   job->numOffsets = valid_offsets(db, job->qin.W, job->hasOut ? job->minPunchF : 0);
   db->refs++;
   *out = job;
@@ -525,7 +531,15 @@ int sgz_corr_scan(sgz_corr *job) {
   sgz_db *db = job->db;
   SGZ_TRY(ctx->bind());
   if (job->abortFlag) return SGZ_ERR_ABORTED;
-  const size_t n = (size_t)job->numTiles * kR * job->ntg;
+  size_t n = (size_t)job->numTiles * kR * job->ntg;
+  const bool tc = job->useTc && db->chunks.empty();   // a streaming scan hides K1 behind PCIe anyway: FFMA path
+  if (tc) {
+    n = std::max(n, (size_t)ceil_div<int64_t>(job->numTilesTc * kTcTile, kStatT) * kStatT);
+    SGZ_TRY(job->stAT.alloc(n));
+    SGZ_TRY(job->stBT.alloc(n));
+    SGZ_TRY(job->stAS.alloc(n));
+    SGZ_TRY(job->stBS.alloc(n));
+  }
   SGZ_TRY(job->simIn.alloc(n));
   SGZ_TRY(job->boostIn.alloc(n));
   SGZ_TRY(job->dFileMax.alloc((size_t)std::max(db->numFiles(), 1)));
@@ -579,11 +593,15 @@ int sgz_corr_scan(sgz_corr *job) {
     if (job->hasOut)
       SGZ_CUDA(cudaMemsetAsync(job->dFileMaxOut.p, 0, job->dFileMaxOut.n * sizeof(unsigned long long), ctx->stream));
     if (db->usedFrames > 0) {
-      SGZ_TRY(run_scan_one(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, 0, job->numTiles,
-                           ctx->stream, 0));
-      if (job->hasOut) {
-        SGZ_TRY(run_scan_one(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, 0, job->numTiles,
+      if (tc) SGZ_TRY(run_scan_tc(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, ctx->stream));
+      else
+        SGZ_TRY(run_scan_one(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, 0, job->numTiles,
                              ctx->stream, 0));
+      if (job->hasOut) {
+        if (tc) SGZ_TRY(run_scan_tc(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, ctx->stream));
+        else
+          SGZ_TRY(run_scan_one(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, 0, job->numTiles,
+                               ctx->stream, 0));
         SGZ_TRY(job->rowMaxOut.alloc((size_t)db->usedFrames));
         k_row_max_out<<<(unsigned)ceil_div<int64_t>(db->usedFrames, 256), 256, 0, ctx->stream>>>(
             job->simOut.p, db->dFileStart.p, db->numFiles(), db->usedFrames, job->qin.W, job->qout.W, job->minPunchF,

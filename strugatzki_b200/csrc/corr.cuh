@@ -4,6 +4,7 @@
 #pragma once
 #include "common.cuh"
 #include "corr_kernel.cuh"
+#include "corr_tc.cuh"
 #include "db.cuh"
 #include "select.cuh"
 
@@ -13,6 +14,8 @@ struct PunchQuery {
   std::vector<float> taps;  // [numCh][Wq]
   double stdT = 0, stdS = 0, rhoT = 0, rhoS = 0, lnAvg = 0;
   DevBuf<float> dTaps;
+  std::vector<float> tcTaps;
+  DevBuf<float> dTcTaps;    // tensor-core path: hi/lo Toeplitz atoms (corr_tc.cuh), empty when not applicable
 };
 
 struct sgz_corr {
@@ -24,6 +27,9 @@ struct sgz_corr {
   PunchQuery qin, qout;
   int ntg = 128;
   int nslot = 3;
+  bool useTc = false;       // K1 on the tensor cores (corr_tc.cuh) for resident scans
+  int64_t numTilesTc = 0;
+  DevBuf<float> stAT, stBT, stAS, stBS;   // window statistics of the tensor-core path
   int64_t numTiles = 0;
   int64_t numOffsets = 0;
   DevBuf<float> simIn, boostIn, simOut, boostOut, rowMaxOut;
@@ -62,6 +68,11 @@ struct sgz_corr {
 };
 
 namespace sgz {
+
+// the tensor-core K1 handles up to 14 channels (16 TMEM accumulators) and windows whose operands fit shared memory
+inline bool tc_applicable(const sgz_ctx *ctx, int numCh, int W) {
+  return numCh >= 2 && numCh <= 14 && W >= 1 && W <= 512 && tc_geom(W).smemBytes <= ctx->smemOptin;
+}
 
 // readInBuffer (FeatureCorrelationImpl.scala:83-98): cut [start,stop) feature frames, normalise,
 // matrix-wide stats of the temporal (ch 0) and spectral (ch 1..) groups, ln of the loudness average.
@@ -120,6 +131,11 @@ inline int prepare_query(const sgz_db *db, const float *inputPlanar /*[numCh][in
   }
   SGZ_TRY(q.dTaps.alloc(q.taps.size()));
   SGZ_CUDA(cudaMemcpyAsync(q.dTaps.p, q.taps.data(), q.taps.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (tc_applicable(db->ctx, numCh, W)) {
+    tc_build_taps(q.taps, db->numPairs, q.Wq, W, q.tcTaps);
+    SGZ_TRY(q.dTcTaps.alloc(q.tcTaps.size()));
+    SGZ_CUDA(cudaMemcpyAsync(q.dTcTaps.p, q.tcTaps.data(), q.tcTaps.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
   return SGZ_OK;
 }
 
@@ -195,6 +211,40 @@ inline int run_scan_one(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim,
   const unsigned grid = (unsigned)std::min<int64_t>(tileEnd - tileBegin, (int64_t)sms * perSm);
   kern<<<grid, job->ntg + 64, L.total, st>>>(p);
   SGZ_LAUNCH_CHECK(ctx);
+  return SGZ_OK;
+}
+
+// tensor-core variant of run_scan_one over the whole database: window statistics, cross terms + sim, file maxima
+inline int run_scan_tc(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim, float *boost,
+                       unsigned long long *fileMax, cudaStream_t st) {
+  sgz_db *db = job->db;
+  sgz_ctx *ctx = job->ctx;
+  const TcGeom G = tc_geom(q.W);
+  CorrStatsParams sp{};
+  sp.data = db->dData.p; sp.rowStride = db->capFrames; sp.usedFrames = db->usedFrames;
+  sp.numCh = db->numCh; sp.numPairs = db->numPairs; sp.W = q.W;
+  sp.stdT = q.stdT; sp.stdS = q.stdS; sp.rhoT = q.rhoT; sp.rhoS = q.rhoS; sp.lnAvgIn = q.lnAvg;
+  sp.fileStart = db->dFileStart.p; sp.numFiles = db->numFiles(); sp.tailExtra = tailExtra;
+  sp.numTiles = ceil_div<int64_t>(job->numTilesTc * kTcTile, kStatT);
+  sp.aT = job->stAT.p; sp.bT = job->stBT.p; sp.aS = job->stAS.p; sp.bS = job->stBS.p; sp.boost = boost;
+  const int rowFrames = kStatT + q.W, numChunks = (rowFrames + kR - 1) / kR;
+  const size_t smS = (((size_t)rowFrames * 4 + 15) / 16) * 16 + (((size_t)rowFrames * 8 + 15) / 16) * 16 +
+                     (size_t)(numChunks + 1) * 32;
+  SGZ_CUDA(cudaFuncSetAttribute(k_corr_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smS));
+  k_corr_stats<<<(unsigned)std::min<int64_t>(sp.numTiles, (int64_t)ctx->smCount * 2), kStatThreads, smS, st>>>(sp);
+  SGZ_LAUNCH_CHECK(ctx);
+  CorrTcParams tp{};
+  tp.data = db->dData.p; tp.rowStride = db->capFrames; tp.numCh = db->numCh; tp.numPairs = db->numPairs; tp.W = q.W;
+  tp.taps = q.dTcTaps.p; tp.weight = q.weight; tp.maxBoost = job->cfg.maxBoost;
+  tp.tileBegin = 0; tp.tileEnd = job->numTilesTc;
+  tp.aT = job->stAT.p; tp.bT = job->stBT.p; tp.aS = job->stAS.p; tp.bS = job->stBS.p; tp.boost = boost; tp.sim = sim;
+  SGZ_CUDA(cudaFuncSetAttribute(k_corr_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));
+  k_corr_tc<<<(unsigned)std::min<int64_t>(job->numTilesTc, ctx->smCount), kTcThreads, G.smemBytes, st>>>(tp);
+  SGZ_LAUNCH_CHECK(ctx);
+  if (fileMax && db->numFiles() > 0) {
+    k_file_max<<<db->numFiles(), 256, 0, st>>>(sim, db->dFileStart.p, db->numFiles(), q.W, tailExtra, fileMax);
+    SGZ_LAUNCH_CHECK(ctx);
+  }
   return SGZ_OK;
 }
 

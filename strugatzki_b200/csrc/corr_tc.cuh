@@ -1,0 +1,517 @@
+// corr_tc.cuh -- K1 on the tensor cores (tcgen05 / TMEM), the 3xTF32 variant of corr_kernel.cuh.
+//
+//   cross(t) = sum_c sum_i q~[c][i] * b[c][t + i]            (FeatureCorrelationImpl.scala:198-210 via MathUtil.correlate)
+//
+// as a GEMM whose operands are never materialised in global memory:
+//   A (M = 128, K-major, SWIZZLE_128B)  A[r][k] = b[c][t0 + 32 r + k]  -- a Hankel view of the channel row: the row pitch
+//        of the swizzle atom (128 B = 32 frames) IS the shift between consecutive rows, a K step of 8 is +32 B, and K
+//        blocks beyond one atom row simply run on into the next row (tools/umma_probe.cu: works with base_offset 0,
+//        the hardware swizzles on absolute address bits);
+//   B (N = 32, K-major, SWIZZLE_32B)    banded Toeplitz taps T[k][c'] = q~[k - (31 - c')], column order reversed so that
+//        the 8x8 blocks of consecutive K steps alias each other: block (step s, row group g') = atom s + g';
+//   D[r][c'] = cross(t0 + 32 r + 31 - c'),  K = 32 + W  (+19 % MACs at W = 172), one tile = 4096 offsets.
+// Precision (tools/tf32x3_probe.py, profiles/r01_tf32x3_precision.json): a single TF32 product misses the 1e-5 bar, so
+// every product is split   a*t = a_hi*t_hi + (a_lo*t_hi + a_hi*t_lo)   with the big term accumulated PER CHANNEL (chains of
+// K/8 = 26 MMAs; the tensor core truncates when it aligns addends, long chains drift) and the small terms in a
+// separate accumulator per group; the FP32 sums of the channel accumulators happen in the epilogue.
+// 16 accumulators x 32 columns = all 512 TMEM columns: [T main, T corr, S corr, 13 spectral mains].
+//
+// The window statistics (mean / variance / loudness boost), which the FFMA kernel builds on the fly, come from a
+// separate HBM-bound pass (k_corr_stats) and the per-file maxima from a third (k_file_max).
+#pragma once
+#include "corr_kernel.cuh"
+
+namespace sgz {
+
+constexpr int kTcP = 32, kTcM = 128, kTcTile = kTcP * kTcM;
+
+struct TcGeom {
+  int W, KS, natom, rows;
+  uint32_t chanBytes;      // one operand buffer (hi or lo) of one channel: rows x 128 B, multiple of 1024
+  uint32_t tapsChanBytes;  // taps atoms of one channel: hi then lo, natom x 256 B each
+  uint32_t tapsPairBytes;  // two channels, rounded up to 1024
+  size_t smemBytes;
+};
+
+__host__ __device__ inline TcGeom tc_geom(int W) {
+  TcGeom g;
+  g.W = W;
+  g.KS = (kTcP + W + 7) / 8;
+  g.natom = g.KS + 3;
+  g.rows = kTcM + (g.KS * 8 + 31) / 32 + 1;
+  g.chanBytes = (uint32_t)((g.rows * 128 + 1023) / 1024 * 1024);
+  g.tapsChanBytes = (uint32_t)(g.natom * 256 * 2);
+  g.tapsPairBytes = (uint32_t)((2 * g.tapsChanBytes + 1023) / 1024 * 1024);
+  g.smemBytes = (size_t)8 * g.chanBytes + (size_t)2 * g.tapsPairBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  return g;
+}
+
+inline float tf32_trunc_host(float x) {
+  uint32_t b;
+  memcpy(&b, &x, 4);
+  b &= ~0x1FFFu;
+  memcpy(&x, &b, 4);
+  return x;
+}
+
+// taps of all channel pairs in the exact shared-memory image the kernel bulk-copies: per pair [chan x][chan y],
+// per channel [hi atoms][lo atoms], atom a = 8 rows (cc) x 8 k (kk) with SWIZZLE_32B chunk flip on rows 4..7
+inline void tc_build_taps(const std::vector<float> &pairTaps /*[numPairs][Wq] float2*/, int numPairs, int Wq, int W,
+                          std::vector<float> &out) {
+  const TcGeom g = tc_geom(W);
+  out.assign((size_t)numPairs * g.tapsPairBytes / 4, 0.f);
+  for (int p = 0; p < numPairs; p++)
+    for (int h = 0; h < 2; h++)
+      for (int part = 0; part < 2; part++)
+        for (int a = 0; a < g.natom; a++)
+          for (int cc = 0; cc < 8; cc++)
+            for (int kk = 0; kk < 8; kk++) {
+              const int q = 8 * a + kk + cc - 31;
+              float v = 0.f;
+              if (q >= 0 && q < W) {
+                const float tp = pairTaps[((size_t)p * Wq + q) * 2 + h];
+                const float hi = tf32_trunc_host(tp);
+                v = part == 0 ? hi : tf32_trunc_host(tp - hi);
+              }
+              const size_t byteOff = (size_t)p * g.tapsPairBytes + (size_t)h * g.tapsChanBytes +
+                                     (size_t)part * g.natom * 256 + (size_t)a * 256 + (size_t)cc * 32 +
+                                     (size_t)(((kk >> 2) ^ ((cc >> 2) & 1)) << 4) + (size_t)(kk & 3) * 4;
+              out[byteOff / 4] = v;
+            }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 1: window statistics per offset (HBM-bound: 56 B read, 20 B written per offset)
+//   temporal = (crossT - bT) * aT,  spectral = (crossS - bS) * aS;  invalid offsets: all NaN
+// ---------------------------------------------------------------------------------------------
+struct CorrStatsParams {
+  const float2 *data;
+  int64_t rowStride, usedFrames;
+  int numCh, numPairs, W;
+  double stdT, stdS, rhoT, rhoS, lnAvgIn;
+  const int64_t *fileStart;
+  int numFiles, tailExtra;
+  int64_t numTiles;          // tiles of kR * 256 offsets
+  float *aT, *bT, *aS, *bS, *boost;
+};
+
+constexpr int kStatThreads = 256, kStatT = kR * kStatThreads;
+
+__global__ void __launch_bounds__(kStatThreads, 2) k_corr_stats(const CorrStatsParams p) {
+  extern __shared__ __align__(128) unsigned char smemStat[];
+  const int W = p.W, rowFrames = kStatT + W, numChunks = (rowFrames + kR - 1) / kR;
+  float *T0 = reinterpret_cast<float *>(smemStat);
+  float2 *F = reinterpret_cast<float2 *>(smemStat + (((size_t)rowFrames * 4 + 15) / 16) * 16);
+  double *CP = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(F) + (((size_t)rowFrames * 8 + 15) / 16) * 16);
+  __shared__ int fileLoHi[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double invW = 1.0 / (double)W, invNS = 1.0 / ((double)(p.numCh - 1) * (double)W);
+  const float cT = (float)(invW / p.stdT), cS = (float)(invNS / p.stdS);
+  const float rhoT = (float)p.rhoT, rhoS = (float)p.rhoS, l2In = (float)(p.lnAvgIn * 1.4426950408889634);
+  const float qnan = __int_as_float(0x7fc00000);
+  const int nq = W / kR, remW = W - nq * kR;
+  constexpr int kPer = 16;   // frames per thread: ceil((kStatT + W) / 256) for W <= 512
+
+  for (int64_t tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+    const int64_t t0 = tile * kStatT;
+    if (tid < 2) {
+      int64_t g = tid == 0 ? t0 : min(t0 + kStatT - 1, p.usedFrames - 1);
+      int lo = 0, hi = p.numFiles;
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (p.fileStart[mid] <= g) lo = mid; else hi = mid;
+      }
+      fileLoHi[tid] = lo;
+    }
+    // per-frame sums over the channels, kept in registers until all pair rows went by
+    float b0[kPer], s1[kPer], s2[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; k++) { b0[k] = 0.f; s1[k] = 0.f; s2[k] = 0.f; }
+    for (int c = 0; c < p.numPairs; c++) {
+      const float2 *row = p.data + (int64_t)c * p.rowStride + t0;
+      float2 v[kPer];
+#pragma unroll
+      for (int k = 0; k < kPer; k++) {
+        const int j = tid + k * kStatThreads;
+        v[k] = j < rowFrames ? __ldg(row + j) : make_float2(0.f, 0.f);
+      }
+      if (c == 0) {
+#pragma unroll
+        for (int k = 0; k < kPer; k++) { b0[k] = v[k].x; s1[k] = v[k].y; s2[k] = v[k].y * v[k].y; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < kPer; k++) {
+          s1[k] += v[k].x + v[k].y;
+          s2[k] = fmaf(v[k].x, v[k].x, fmaf(v[k].y, v[k].y, s2[k]));
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; k++) {
+      const int j = tid + k * kStatThreads;
+      if (j < rowFrames) { T0[j] = b0[k]; F[j] = make_float2(s1[k], s2[k]); }
+    }
+    __syncthreads();
+    // FP64 chunk sums (14 frames), then an exclusive prefix over the chunks
+    for (int j = tid; j < numChunks; j += kStatThreads) {
+      double a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+      const int e0 = kR * j, e1 = min(kR * (j + 1), rowFrames);
+      for (int e = e0; e < e1; e++) {
+        const double x = (double)T0[e];
+        const float2 f = F[e];
+        a1 += x; a2 += x * x; a3 += (double)f.x; a4 += (double)f.y;
+      }
+      double *o = CP + 4 * (size_t)(j + 1);
+      o[0] = a1; o[1] = a2; o[2] = a3; o[3] = a4;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int per = (numChunks + 31) / 32;
+      const int jb = min(lane * per, numChunks), je = min(jb + per, numChunks);
+      double r1 = 0, r2 = 0, r3 = 0, r4 = 0;
+      for (int j = jb; j < je; j++) {
+        double *o = CP + 4 * (size_t)(j + 1);
+        r1 += o[0]; r2 += o[1]; r3 += o[2]; r4 += o[3];
+        o[0] = r1; o[1] = r2; o[2] = r3; o[3] = r4;
+      }
+      double i1 = r1, i2 = r2, i3 = r3, i4 = r4;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double o1 = __shfl_up_sync(0xffffffffu, i1, d), o2 = __shfl_up_sync(0xffffffffu, i2, d);
+        const double o3 = __shfl_up_sync(0xffffffffu, i3, d), o4 = __shfl_up_sync(0xffffffffu, i4, d);
+        if (lane >= d) { i1 += o1; i2 += o2; i3 += o3; i4 += o4; }
+      }
+      const double x1 = i1 - r1, x2 = i2 - r2, x3 = i3 - r3, x4 = i4 - r4;
+      for (int j = jb; j < je; j++) {
+        double *o = CP + 4 * (size_t)(j + 1);
+        o[0] += x1; o[1] += x2; o[2] += x3; o[3] += x4;
+      }
+      if (lane == 0) { CP[0] = 0; CP[1] = 0; CP[2] = 0; CP[3] = 0; }
+    }
+    __syncthreads();
+    // per thread: 14 consecutive offsets, window sums slid in FP64 (same arithmetic as the FFMA kernel's epilogue)
+    const int o = tid * kR;
+    D4 win;
+    {
+      const double *c0 = CP + 4 * (size_t)tid, *c1 = CP + 4 * (size_t)(tid + nq);
+      win = {c1[0] - c0[0], c1[1] - c0[1], c1[2] - c0[2], c1[3] - c0[3]};
+      for (int k = 0; k < remW; k++) {
+        const int e = o + kR * nq + k;
+        const double x = (double)T0[e];
+        const float2 f = F[e];
+        win.t1 += x; win.t2 += x * x; win.s1 += (double)f.x; win.s2 += (double)f.y;
+      }
+    }
+    const int64_t g0 = t0 + o;
+    int f = fileLoHi[0];
+    {
+      int lo = fileLoHi[0], hi = fileLoHi[1] + 1;
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (p.fileStart[mid] <= g0) lo = mid; else hi = mid;
+      }
+      f = lo;
+    }
+    int64_t fStart = p.fileStart[f], fEnd = p.fileStart[f + 1];
+    for (int k = 0; k < kR; k++) {
+      const double mT = win.t1 * invW;
+      const float avgB = (float)mT;                                          // MathUtil.avg -> Float
+      float boost = exp2f((l2In - __log2f(avgB)) * (1.0f / 0.6f));           // calcBoost
+      float aT, bT, aS, bS;
+      {
+        const double q = win.t2 * invW;
+        const double var = q - mT * mT;
+        bT = (float)mT * rhoT;
+        aT = (var > 1e-13 * q) ? cT * rsqrtf((float)var) : qnan;
+      }
+      {
+        const double mS = win.s1 * invNS;
+        const double q = win.s2 * invNS;
+        const double var = q - mS * mS;
+        bS = (float)mS * rhoS;
+        aS = (var > 1e-13 * q) ? cS * rsqrtf((float)var) : qnan;
+      }
+      const int64_t g = g0 + k;
+      while (g >= fEnd && f + 1 < p.numFiles) { f++; fStart = fEnd; fEnd = p.fileStart[f + 1]; }
+      const int64_t nValid = (fEnd - fStart) - p.tailExtra - W + 1;
+      if (!(g < p.usedFrames && g - fStart < nValid)) { aT = bT = aS = bS = boost = qnan; }
+      p.aT[g] = aT; p.bT[g] = bT; p.aS[g] = aS; p.bS[g] = bS; p.boost[g] = boost;
+      if (k < kR - 1) {
+        const int e = o + k;
+        const double bo = (double)T0[e], bn = (double)T0[e + W];
+        const float2 fo = F[e], fn = F[e + W];
+        win.t1 += bn - bo;
+        win.t2 += bn * bn - bo * bo;
+        win.s1 += (double)fn.x - (double)fo.x;
+        win.s2 += (double)fn.y - (double)fo.y;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 3: per-file maximum of the sim curve, first occurrence (same packed key as the FFMA kernel)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_file_max(const float *__restrict__ sim, const int64_t *__restrict__ fileStart,
+                                                  int numFiles, int W, int tailExtra,
+                                                  unsigned long long *__restrict__ fileMax) {
+  const int f = blockIdx.x;
+  const int64_t g0 = fileStart[f];
+  const int64_t nValid = (fileStart[f + 1] - g0) - tailExtra - W + 1;
+  unsigned long long best = 0ull;
+  for (int64_t t = threadIdx.x; t < nValid; t += blockDim.x) {
+    const float s = sim[g0 + t];
+    if (s == s) {
+      const unsigned long long key =
+          ((unsigned long long)float_order_key(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)t);
+      if (key > best) best = key;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
+    if (o > best) best = o;
+  }
+  __shared__ unsigned long long wbest[8];
+  if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++) if (wbest[w] > best) best = wbest[w];
+    fileMax[f] = best;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 2: cross terms on the tensor cores + final sim
+// ---------------------------------------------------------------------------------------------
+struct CorrTcParams {
+  const float2 *data;
+  int64_t rowStride;
+  int numCh, numPairs, W;
+  const float *taps;        // tc_build_taps image, numPairs x tapsPairBytes
+  float weight, maxBoost;
+  int64_t tileBegin, tileEnd;   // tiles of 4096 offsets
+  const float *aT, *bT, *aS, *bS, *boost;
+  float *sim;
+};
+
+__device__ __forceinline__ uint64_t tc_desc(uint32_t addr, uint32_t sbo, uint32_t layout) {
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)layout << 61);
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmemD, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmemD),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+// bounded wait: a protocol error must end in a trap (visible CUDA error), not in a hung GPU box
+__device__ __forceinline__ void tc_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 26) && !done; it++) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+  if (!done) __trap();
+}
+
+// warps 0..7: split workers (global pair row -> swizzled hi / lo operand buffers), warp 8: MMA issuer (one lane),
+// warps 9..12: epilogue (TMEM lane quarter = warp % 4)
+constexpr int kTcSplit = 256, kTcThreads = kTcSplit + 32 + 128;
+
+__global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p) {
+  extern __shared__ __align__(1024) unsigned char smemRaw[];
+  const TcGeom G = tc_geom(p.W);
+  unsigned char *base = smemRaw + ((1024 - (smem_u32(smemRaw) & 1023)) & 1023);
+  // operand buffers: [buf 0/1][channel x/y][hi/lo]
+  auto ops = [&](int buf, int h, int part) { return base + (size_t)((buf * 2 + h) * 2 + part) * G.chanBytes; };
+  unsigned char *tapsBase = base + (size_t)8 * G.chanBytes;
+  auto tapsBuf = [&](int buf) { return tapsBase + (size_t)buf * G.tapsPairBytes; };
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tapsBase + (size_t)2 * G.tapsPairBytes);
+  uint64_t *opFree = bars, *opFull = bars + 2, *tapsFull = bars + 4, *accFull = bars + 6, *accEmpty = bars + 7;
+  uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(bars + 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(opFree, 1); mbar_init(opFree + 1, 1);
+    mbar_init(opFull, kTcSplit / 32); mbar_init(opFull + 1, kTcSplit / 32);
+    mbar_init(tapsFull, 1); mbar_init(tapsFull + 1, 1);
+    mbar_init(accFull, 1);
+    mbar_init(accEmpty, 4);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmemSlot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = *tmemSlot;
+  const int nFrames = G.rows * 32;                      // frames of a tile that the A operand can touch
+
+  if (warp < kTcSplit / 32) {
+    // =========================== split workers ===========================
+    constexpr int kPer = 20;                            // >= ceil(nFrames / 256) for W <= 512
+    uint32_t pc = 0;
+    for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x) {
+      const int64_t t0 = tile * kTcTile;
+      for (int pr = 0; pr < p.numPairs; pr++, pc++) {
+        const int buf = pc & 1;
+        const uint32_t use = pc >> 1;
+        const float2 *row = p.data + (int64_t)pr * p.rowStride + t0;
+        float2 v[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; k++) {                // all loads of the pair row in flight before the wait
+          const int L = tid + k * kTcSplit;
+          v[k] = L < nFrames ? __ldg(row + L) : make_float2(0.f, 0.f);
+        }
+        if (use > 0) tc_wait(opFree + buf, (use - 1) & 1);   // MMAs of the pair that last used this buffer are done
+        unsigned char *xh = ops(buf, 0, 0), *xl = ops(buf, 0, 1), *yh = ops(buf, 1, 0), *yl = ops(buf, 1, 1);
+#pragma unroll
+        for (int k = 0; k < kPer; k++) {
+          const int L = tid + k * kTcSplit;
+          if (L < nFrames) {
+            const int r = L >> 5, ch = (L & 31) >> 2, w = L & 3;
+            const uint32_t off = (uint32_t)(r * 128 + ((ch ^ (r & 7)) << 4) + w * 4);
+            const float xhi = __uint_as_float(__float_as_uint(v[k].x) & ~0x1FFFu);
+            const float yhi = __uint_as_float(__float_as_uint(v[k].y) & ~0x1FFFu);
+            *reinterpret_cast<float *>(xh + off) = xhi;
+            *reinterpret_cast<float *>(xl + off) = v[k].x - xhi;
+            *reinterpret_cast<float *>(yh + off) = yhi;
+            *reinterpret_cast<float *>(yl + off) = v[k].y - yhi;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (MMA)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(opFull + buf);
+      }
+    }
+  } else if (warp == kTcSplit / 32) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t idesc =
+          (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcP >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+      uint32_t pc = 0, tileIt = 0;
+      for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, tileIt++) {
+        bool corrStartedT = false, corrStartedS = false;
+        for (int pr = 0; pr < p.numPairs; pr++, pc++) {
+          const int buf = pc & 1;
+          const uint32_t use = pc >> 1;
+          if (use > 0) tc_wait(opFree + buf, (use - 1) & 1);
+          mbar_expect_tx(tapsFull + buf, G.tapsPairBytes);
+          bulk_g2s(tapsBuf(buf), reinterpret_cast<const unsigned char *>(p.taps) + (size_t)pr * G.tapsPairBytes,
+                   G.tapsPairBytes, tapsFull + buf);
+          if (pr == 0 && tileIt > 0) tc_wait(accEmpty, (tileIt - 1) & 1);   // epilogue has drained the accumulators
+          tc_wait(opFull + buf, use & 1);
+          tc_wait(tapsFull + buf, use & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          for (int h = 0; h < 2; h++) {
+            const int c = 2 * pr + h;
+            if (c >= p.numCh) break;
+            const uint32_t dMain = tmem + 32u * (c == 0 ? 0u : (uint32_t)(2 + c));
+            const uint32_t dCorr = tmem + 32u * (c == 0 ? 1u : 2u);
+            const uint32_t tHiA = smem_u32(tapsBuf(buf)) + (uint32_t)h * G.tapsChanBytes;
+            const uint64_t aHi = tc_desc(smem_u32(ops(buf, h, 0)), 1024, 2), aLo = tc_desc(smem_u32(ops(buf, h, 1)), 1024, 2);
+            const uint64_t tHi = tc_desc(tHiA, 256, 6), tLo = tc_desc(tHiA + (uint32_t)G.natom * 256u, 256, 6);
+            bool &started = c == 0 ? corrStartedT : corrStartedS;
+            // one K step: A start +32 B (2 descriptor units), taps start +256 B (16 units)
+            for (int s = 0; s < G.KS; s++) tc_mma(dMain, aHi + 2u * s, tHi + 16u * s, idesc, s > 0);
+            for (int s = 0; s < G.KS; s++) tc_mma(dCorr, aLo + 2u * s, tHi + 16u * s, idesc, started || s > 0);
+            started = true;
+            for (int s = 0; s < G.KS; s++) tc_mma(dCorr, aHi + 2u * s, tLo + 16u * s, idesc, 1);
+          }
+          tc_commit(opFree + buf);
+          if (pr == p.numPairs - 1) tc_commit(accFull);
+        }
+      }
+    }
+  } else {
+    // =========================== epilogue ===========================
+    // TMEM lanes 32 q .. 32 q + 31 (q = warp % 4) = rows r; row r = offsets t0 + 32 r + (31 - column)
+    const int quarter = warp & 3;
+    const bool useT = p.weight > 0.f, useS = p.weight < 1.f;
+    const float qnan = __int_as_float(0x7fc00000);
+    uint32_t tileIt = 0;
+    for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, tileIt++) {
+      const int64_t t0 = tile * kTcTile;
+      tc_wait(accFull, tileIt & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      const int r = quarter * 32 + lane;
+      const uint32_t laneAddr = tmem + ((uint32_t)(quarter * 32) << 16);
+      const int64_t gRow = t0 + 32 * (int64_t)r;
+      float accT[32], accS[32];
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        float v[16];
+        tc_ld16(laneAddr + 0 * 32 + 16 * half, v);
+#pragma unroll
+        for (int i = 0; i < 16; i++) accT[16 * half + i] = v[i];
+        tc_ld16(laneAddr + 1 * 32 + 16 * half, v);
+#pragma unroll
+        for (int i = 0; i < 16; i++) accT[16 * half + i] += v[i];
+        tc_ld16(laneAddr + 2 * 32 + 16 * half, v);
+#pragma unroll
+        for (int i = 0; i < 16; i++) accS[16 * half + i] = v[i];
+        for (int c = 1; c < p.numCh; c++) {
+          tc_ld16(laneAddr + (uint32_t)(2 + c) * 32 + 16 * half, v);
+#pragma unroll
+          for (int i = 0; i < 16; i++) accS[16 * half + i] += v[i];
+        }
+      }
+      // the accumulators are in registers: hand TMEM back to the issuer before the global-memory part
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(accEmpty);
+#pragma unroll
+      for (int q4 = 0; q4 < 8; q4++) {                   // offsets 4 q4 .. 4 q4 + 3 of the row <-> columns 31 - offset
+        const int64_t g = gRow + 4 * q4;
+        const float4 cAT = __ldg(reinterpret_cast<const float4 *>(p.aT + g));
+        const float4 cBT = __ldg(reinterpret_cast<const float4 *>(p.bT + g));
+        const float4 cAS = __ldg(reinterpret_cast<const float4 *>(p.aS + g));
+        const float4 cBS = __ldg(reinterpret_cast<const float4 *>(p.bS + g));
+        const float4 cBo = __ldg(reinterpret_cast<const float4 *>(p.boost + g));
+        const float kat[4] = {cAT.x, cAT.y, cAT.z, cAT.w}, kbt[4] = {cBT.x, cBT.y, cBT.z, cBT.w};
+        const float kas[4] = {cAS.x, cAS.y, cAS.z, cAS.w}, kbs[4] = {cBS.x, cBS.y, cBS.z, cBS.w};
+        const float kbo[4] = {cBo.x, cBo.y, cBo.z, cBo.w};
+        float out[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int col = 31 - (4 * q4 + e);
+          const float temporal = useT ? (accT[col] - kbt[e]) * kat[e] : 0.f;
+          const float spectral = useS ? (accS[col] - kbs[e]) * kas[e] : 0.f;
+          const float blend = __fadd_rn(__fmul_rn(temporal, p.weight), __fmul_rn(spectral, __fsub_rn(1.0f, p.weight)));
+          const bool invalid = (kbt[e] != kbt[e]) && (kbs[e] != kbs[e]);
+          out[e] = invalid ? qnan : (kbo[e] <= p.maxBoost ? blend : 0.f);
+        }
+        *reinterpret_cast<float4 *>(p.sim + g) = make_float4(out[0], out[1], out[2], out[3]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+}  // namespace sgz

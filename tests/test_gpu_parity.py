@@ -416,3 +416,34 @@ def test_feature_stats_matches_oracle(ctx):
     dbn.finalize()
     with pytest.raises(NativeError):                     # normalised database: stats need the raw values
         dbn.stats()
+
+
+@pytest.mark.parametrize("w_in,weight", [(88200, 0.5), (22050, 0.3), (100000, 1.0)])
+def test_corr_tensor_core_path_matches_oracle(ctx, w_in, weight, monkeypatch):
+    """K1 on the tensor cores (SGZ_CORR_TC=1: tcgen05 3xTF32 on a Hankel view of the channel rows, corr_tc.cuh) --
+    opt-in alternative to the FFMA2 kernel, same tolerance; also checks it against the FFMA2 curves"""
+    from strugatzki_b200 import engine
+    files, norm = make_db(4, [9000, 400, 5100, 7000])
+    inp = make_input(900)
+    W = (w_in + STEP // 2) // STEP
+    plant_needles(files, inp[:W], [(0, 4090), (2, 37), (3, 6000)])
+    op, nc = corr_cfgs(inp, norm, punch_in=(0, w_in), w_in=weight, num_matches=5, num_per_file=2)
+    db = build_db(ctx, files, norm)
+    ref_job = engine.CorrelationJob(db, nc, inp)
+    ref_job.scan()
+    monkeypatch.setenv("SGZ_CORR_TC", "1")
+    job = engine.CorrelationJob(db, nc, inp)
+    monkeypatch.delenv("SGZ_CORR_TC")
+    got = job.run()
+    assert job.timing()["scan_launches"] == 3            # stats pass, tensor-core pass, file maxima
+    assert_matches_equal(got, O.corr_search(op, files))
+    for i, f in enumerate(files):
+        want_sim, want_boost = O.corr_curve(op, f, 0, 0)
+        n = len(want_sim)
+        if n == 0:
+            continue
+        sim, boost = job.curve(i, 0, 0, n)
+        assert_sims_close(sim, want_sim, rel=1e-5, abs_tol=2e-6, what=f"file {i} sim (tensor cores)")
+        assert_sims_close(boost, want_boost, rel=1e-5, abs_tol=0, what=f"file {i} boost")
+        sim_f, _ = ref_job.curve(i, 0, 0, n)
+        assert np.nanmax(np.abs(sim - sim_f)) < 4e-6
