@@ -14,8 +14,8 @@ struct PunchQuery {
   std::vector<float> taps;  // [numCh][Wq]
   double stdT = 0, stdS = 0, rhoT = 0, rhoS = 0, lnAvg = 0;
   DevBuf<float> dTaps;
-  std::vector<float> tcTaps;
-  DevBuf<float> dTcTaps;    // tensor-core path: hi/lo Toeplitz atoms (corr_tc.cuh), empty when not applicable
+  std::vector<uint16_t> tcTaps;
+  DevBuf<uint16_t> dTcTaps;    // tensor-core path: hi/lo Toeplitz atoms (corr_tc.cuh), empty when not applicable
 };
 
 struct sgz_corr {
@@ -134,7 +134,7 @@ inline int prepare_query(const sgz_db *db, const float *inputPlanar /*[numCh][in
   if (tc_applicable(db->ctx, numCh, W)) {
     tc_build_taps(q.taps, db->numPairs, q.Wq, W, q.tcTaps);
     SGZ_TRY(q.dTcTaps.alloc(q.tcTaps.size()));
-    SGZ_CUDA(cudaMemcpyAsync(q.dTcTaps.p, q.tcTaps.data(), q.tcTaps.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    SGZ_CUDA(cudaMemcpyAsync(q.dTcTaps.p, q.tcTaps.data(), q.tcTaps.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
   }
   return SGZ_OK;
 }
@@ -239,8 +239,26 @@ inline int run_scan_tc(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim, 
   tp.tileBegin = 0; tp.tileEnd = job->numTilesTc;
   tp.aT = job->stAT.p; tp.bT = job->stBT.p; tp.aS = job->stAS.p; tp.bS = job->stBS.p; tp.boost = boost; tp.sim = sim;
   SGZ_CUDA(cudaFuncSetAttribute(k_corr_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));
-  k_corr_tc<<<(unsigned)std::min<int64_t>(job->numTilesTc, ctx->smCount), kTcThreads, G.smemBytes, st>>>(tp);
+  const unsigned gridTc = (unsigned)std::min<int64_t>(job->numTilesTc, ctx->smCount);
+  DevBuf<long long> dProf;
+  const bool prof = getenv("SGZ_CORR_TC_PROF") != nullptr;   // developer probe: where does the issuer lane wait?
+  if (prof) {
+    SGZ_TRY(dProf.alloc((size_t)gridTc * 8));
+    SGZ_CUDA(cudaMemsetAsync(dProf.p, 0, (size_t)gridTc * 8 * sizeof(long long), st));
+    tp.prof = dProf.p;
+  }
+  k_corr_tc<<<gridTc, kTcThreads, G.smemBytes, st>>>(tp);
   SGZ_LAUNCH_CHECK(ctx);
+  if (prof) {
+    std::vector<long long> h((size_t)gridTc * 8);
+    SGZ_CUDA(cudaMemcpyAsync(h.data(), dProf.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    SGZ_CUDA(cudaStreamSynchronize(st));
+    double a[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (unsigned b = 0; b < gridTc; b++) for (int k = 0; k < 7; k++) a[k] += (double)h[(size_t)b * 8 + k];
+    const double tiles = a[6] > 0 ? a[6] : 1;
+    fprintf(stderr, "k_corr_tc issuer cycles per tile: total %.0f | wait opFree %.0f, accEmpty %.0f, opFull %.0f, taps %.0f, "
+                    "issue %.0f\n", a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles, a[4] / tiles, a[5] / tiles);
+  }
   if (fileMax && db->numFiles() > 0) {
     k_file_max<<<db->numFiles(), 256, 0, st>>>(sim, db->dFileStart.p, db->numFiles(), q.W, tailExtra, fileMax);
     SGZ_LAUNCH_CHECK(ctx);

@@ -1,24 +1,28 @@
-// corr_tc.cuh -- K1 on the tensor cores (tcgen05 / TMEM), the 3xTF32 variant of corr_kernel.cuh.
+// corr_tc.cuh -- K1 on the tensor cores (tcgen05 / TMEM): split-FP16 ("FP16x3") variant of corr_kernel.cuh.
 //
 //   cross(t) = sum_c sum_i q~[c][i] * b[c][t + i]            (FeatureCorrelationImpl.scala:198-210 via MathUtil.correlate)
 //
 // as a GEMM whose operands are never materialised in global memory:
-//   A (M = 128, K-major, SWIZZLE_128B)  A[r][k] = b[c][t0 + 32 r + k]  -- a Hankel view of the channel row: the row pitch
-//        of the swizzle atom (128 B = 32 frames) IS the shift between consecutive rows, a K step of 8 is +32 B, and K
-//        blocks beyond one atom row simply run on into the next row (tools/umma_probe.cu: works with base_offset 0,
+//   A (M = 128, K-major, FP16, SWIZZLE_64B)  A[r][k] = b[c][t0 + 32 r + k]  -- a Hankel view of the channel row: the row
+//        pitch of the swizzle atom (64 B = 32 halves) IS the shift between consecutive rows, a K step of 16 is +32 B, and
+//        K blocks beyond one atom row simply run on into the next row (tools/umma_probe.cu: works with base_offset 0,
 //        the hardware swizzles on absolute address bits);
-//   B (N = 32, K-major, SWIZZLE_32B)    banded Toeplitz taps T[k][c'] = q~[k - (31 - c')], column order reversed so that
-//        the 8x8 blocks of consecutive K steps alias each other: block (step s, row group g') = atom s + g';
+//   B (N = 32, K-major, FP16, SWIZZLE_32B)   banded Toeplitz taps T[k][c'] = q~[k - (31 - c')], column order reversed so
+//        that the 8x16 blocks of consecutive K steps alias each other: block (step s, row group g') = atom 2 s + g';
 //   D[r][c'] = cross(t0 + 32 r + 31 - c'),  K = 32 + W  (+19 % MACs at W = 172), one tile = 4096 offsets.
-// Precision (tools/tf32x3_probe.py, profiles/r01_tf32x3_precision.json): a single TF32 product misses the 1e-5 bar, so
-// every product is split   a*t = a_hi*t_hi + (a_lo*t_hi + a_hi*t_lo)   with the big term accumulated PER CHANNEL (chains of
-// K/8 = 26 MMAs; the tensor core truncates when it aligns addends, long chains drift) and the small terms in a
-// separate accumulator per group; the FP32 sums of the channel accumulators happen in the epilogue.
+// Precision (tools/tf32x3_probe.py, profiles/r01_tf32x3_precision.json): a single reduced-precision product misses the
+// 1e-5 bar, so both operands are split into two FP16 numbers (22 significant bits, the data are normalised features of
+// order 1) and   a*t = a1*t1 + (a2*t1 + a1*t2)   with the big term accumulated PER CHANNEL (chains of K/16 = 13 MMAs;
+// the tensor core truncates when it aligns addends, long chains drift) and the small terms in a separate accumulator
+// per group; the FP32 sums of the channel accumulators happen in the epilogue.  FP16 instead of TF32 halves the number of
+// MMAs (K = 16 per instruction at 44 cycles vs K = 8 at 50 -- the A-operand fetch bounds small-N MMAs either way).
 // 16 accumulators x 32 columns = all 512 TMEM columns: [T main, T corr, S corr, 13 spectral mains].
 //
 // The window statistics (mean / variance / loudness boost), which the FFMA kernel builds on the fly, come from a
 // separate HBM-bound pass (k_corr_stats) and the per-file maxima from a third (k_file_max).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "corr_kernel.cuh"
 
 namespace sgz {
@@ -27,8 +31,8 @@ constexpr int kTcP = 32, kTcM = 128, kTcTile = kTcP * kTcM;
 
 struct TcGeom {
   int W, KS, natom, rows;
-  uint32_t chanBytes;      // one operand buffer (hi or lo) of one channel: rows x 128 B, multiple of 1024
-  uint32_t tapsChanBytes;  // taps atoms of one channel: hi then lo, natom x 256 B each
+  uint32_t chanBytes;      // one FP16 operand buffer (first or second part) of one channel: rows x 64 B, multiple of 1024
+  uint32_t tapsChanBytes;  // taps atoms of one channel: first then second FP16 part, natom x 256 B each
   uint32_t tapsPairBytes;  // two channels, rounded up to 1024
   size_t smemBytes;
 };
@@ -36,47 +40,42 @@ struct TcGeom {
 __host__ __device__ inline TcGeom tc_geom(int W) {
   TcGeom g;
   g.W = W;
-  g.KS = (kTcP + W + 7) / 8;
-  g.natom = g.KS + 3;
-  g.rows = kTcM + (g.KS * 8 + 31) / 32 + 1;
-  g.chanBytes = (uint32_t)((g.rows * 128 + 1023) / 1024 * 1024);
+  g.KS = (kTcP + W + 15) / 16;
+  g.natom = 2 * g.KS + 2;
+  g.rows = kTcM + (g.KS * 16 + 31) / 32 + 1;
+  g.chanBytes = (uint32_t)((g.rows * 64 + 1023) / 1024 * 1024);
   g.tapsChanBytes = (uint32_t)(g.natom * 256 * 2);
   g.tapsPairBytes = (uint32_t)((2 * g.tapsChanBytes + 1023) / 1024 * 1024);
   g.smemBytes = (size_t)8 * g.chanBytes + (size_t)2 * g.tapsPairBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
   return g;
 }
 
-inline float tf32_trunc_host(float x) {
-  uint32_t b;
-  memcpy(&b, &x, 4);
-  b &= ~0x1FFFu;
-  memcpy(&x, &b, 4);
-  return x;
-}
-
 // taps of all channel pairs in the exact shared-memory image the kernel bulk-copies: per pair [chan x][chan y],
-// per channel [hi atoms][lo atoms], atom a = 8 rows (cc) x 8 k (kk) with SWIZZLE_32B chunk flip on rows 4..7
+// per channel [first-part atoms][second-part atoms], atom a = 8 rows (cc) x 16 k (kk) halves with the SWIZZLE_32B
+// chunk flip on rows 4..7
 inline void tc_build_taps(const std::vector<float> &pairTaps /*[numPairs][Wq] float2*/, int numPairs, int Wq, int W,
-                          std::vector<float> &out) {
+                          std::vector<uint16_t> &out) {
   const TcGeom g = tc_geom(W);
-  out.assign((size_t)numPairs * g.tapsPairBytes / 4, 0.f);
+  out.assign((size_t)numPairs * g.tapsPairBytes / 2, 0);
   for (int p = 0; p < numPairs; p++)
     for (int h = 0; h < 2; h++)
       for (int part = 0; part < 2; part++)
         for (int a = 0; a < g.natom; a++)
           for (int cc = 0; cc < 8; cc++)
-            for (int kk = 0; kk < 8; kk++) {
+            for (int kk = 0; kk < 16; kk++) {
               const int q = 8 * a + kk + cc - 31;
-              float v = 0.f;
+              __half v = __float2half_rn(0.f);
               if (q >= 0 && q < W) {
                 const float tp = pairTaps[((size_t)p * Wq + q) * 2 + h];
-                const float hi = tf32_trunc_host(tp);
-                v = part == 0 ? hi : tf32_trunc_host(tp - hi);
+                const __half t1 = __float2half_rn(tp);
+                v = part == 0 ? t1 : __float2half_rn(tp - __half2float(t1));
               }
               const size_t byteOff = (size_t)p * g.tapsPairBytes + (size_t)h * g.tapsChanBytes +
                                      (size_t)part * g.natom * 256 + (size_t)a * 256 + (size_t)cc * 32 +
-                                     (size_t)(((kk >> 2) ^ ((cc >> 2) & 1)) << 4) + (size_t)(kk & 3) * 4;
-              out[byteOff / 4] = v;
+                                     (size_t)(((kk >> 3) ^ ((cc >> 2) & 1)) << 4) + (size_t)(kk & 7) * 2;
+              uint16_t bits;
+              memcpy(&bits, &v, 2);
+              out[byteOff / 2] = bits;
             }
 }
 
@@ -289,11 +288,12 @@ struct CorrTcParams {
   const float2 *data;
   int64_t rowStride;
   int numCh, numPairs, W;
-  const float *taps;        // tc_build_taps image, numPairs x tapsPairBytes
+  const uint16_t *taps;     // tc_build_taps image, numPairs x tapsPairBytes
   float weight, maxBoost;
   int64_t tileBegin, tileEnd;   // tiles of 4096 offsets
   const float *aT, *bT, *aS, *bS, *boost;
   float *sim;
+  long long *prof;          // developer probe (SGZ_CORR_TC_PROF): per CTA 8 cycle counters, or nullptr
 };
 
 __device__ __forceinline__ uint64_t tc_desc(uint32_t addr, uint32_t sbo, uint32_t layout) {
@@ -303,7 +303,7 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t addr, uint32_t sbo, uint32_
 __device__ __forceinline__ void tc_mma(uint32_t tmemD, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmemD),
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmemD),
       "l"(da), "l"(db), "r"(idesc), "r"(acc)
       : "memory");
 }
@@ -322,15 +322,18 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
-// bounded wait: a protocol error must end in a trap (visible CUDA error), not in a hung GPU box
+// bounded wait: a protocol error must end in a trap (visible CUDA error), not in a hung GPU box.  Waiting warps back
+// off with nanosleep: a spinning warp would steal issue slots from the single MMA-issuer lane on its scheduler.
+template <bool kSleep = true>
 __device__ __forceinline__ void tc_wait(uint64_t *bar, uint32_t parity) {
   uint32_t done = 0;
-  for (uint32_t it = 0; it < (1u << 26) && !done; it++) {
+  for (uint32_t it = 0; it < (1u << 24) && !done; it++) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(done)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+    if (kSleep && !done) __nanosleep(100);
   }
   if (!done) __trap();
 }
@@ -343,7 +346,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
   extern __shared__ __align__(1024) unsigned char smemRaw[];
   const TcGeom G = tc_geom(p.W);
   unsigned char *base = smemRaw + ((1024 - (smem_u32(smemRaw) & 1023)) & 1023);
-  // operand buffers: [buf 0/1][channel x/y][hi/lo]
+  // operand buffers: [buf 0/1][channel x/y][first / second FP16 part]
   auto ops = [&](int buf, int h, int part) { return base + (size_t)((buf * 2 + h) * 2 + part) * G.chanBytes; };
   unsigned char *tapsBase = base + (size_t)8 * G.chanBytes;
   auto tapsBuf = [&](int buf) { return tapsBase + (size_t)buf * G.tapsPairBytes; };
@@ -373,34 +376,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
 
   if (warp < kTcSplit / 32) {
     // =========================== split workers ===========================
-    constexpr int kPer = 20;                            // >= ceil(nFrames / 256) for W <= 512
+    constexpr int kPer = 10;                            // >= ceil(nFrames / 512) for W <= 512; two frames per step
     uint32_t pc = 0;
     for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x) {
       const int64_t t0 = tile * kTcTile;
       for (int pr = 0; pr < p.numPairs; pr++, pc++) {
         const int buf = pc & 1;
         const uint32_t use = pc >> 1;
-        const float2 *row = p.data + (int64_t)pr * p.rowStride + t0;
-        float2 v[kPer];
+        const float4 *row = reinterpret_cast<const float4 *>(p.data + (int64_t)pr * p.rowStride + t0);   // t0 % 4096 == 0
+        float4 v[kPer];
 #pragma unroll
         for (int k = 0; k < kPer; k++) {                // all loads of the pair row in flight before the wait
-          const int L = tid + k * kTcSplit;
-          v[k] = L < nFrames ? __ldg(row + L) : make_float2(0.f, 0.f);
+          const int L2 = tid + k * kTcSplit;            // frames 2 L2, 2 L2 + 1
+          v[k] = 2 * L2 < nFrames ? __ldg(row + L2) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (use > 0) tc_wait(opFree + buf, (use - 1) & 1);   // MMAs of the pair that last used this buffer are done
-        unsigned char *xh = ops(buf, 0, 0), *xl = ops(buf, 0, 1), *yh = ops(buf, 1, 0), *yl = ops(buf, 1, 1);
+        unsigned char *x1 = ops(buf, 0, 0), *x2 = ops(buf, 0, 1), *y1 = ops(buf, 1, 0), *y2 = ops(buf, 1, 1);
 #pragma unroll
         for (int k = 0; k < kPer; k++) {
-          const int L = tid + k * kTcSplit;
+          const int L = 2 * (tid + k * kTcSplit);
           if (L < nFrames) {
-            const int r = L >> 5, ch = (L & 31) >> 2, w = L & 3;
-            const uint32_t off = (uint32_t)(r * 128 + ((ch ^ (r & 7)) << 4) + w * 4);
-            const float xhi = __uint_as_float(__float_as_uint(v[k].x) & ~0x1FFFu);
-            const float yhi = __uint_as_float(__float_as_uint(v[k].y) & ~0x1FFFu);
-            *reinterpret_cast<float *>(xh + off) = xhi;
-            *reinterpret_cast<float *>(xl + off) = v[k].x - xhi;
-            *reinterpret_cast<float *>(yh + off) = yhi;
-            *reinterpret_cast<float *>(yl + off) = v[k].y - yhi;
+            // frame L -> row L / 32 (64 B), 16-byte chunk (L % 32) / 8 flipped by (row >> 1) & 3, half (L % 8)
+            const int r = L >> 5, ch = (L & 31) >> 3, w = L & 7;
+            const uint32_t off = (uint32_t)(r * 64 + ((ch ^ ((r >> 1) & 3)) << 4) + w * 2);
+            const __half2 xa = __floats2half2_rn(v[k].x, v[k].z), ya = __floats2half2_rn(v[k].y, v[k].w);
+            const float2 xf = __half22float2(xa), yf = __half22float2(ya);
+            *reinterpret_cast<__half2 *>(x1 + off) = xa;
+            *reinterpret_cast<__half2 *>(x2 + off) = __floats2half2_rn(v[k].x - xf.x, v[k].z - xf.y);
+            *reinterpret_cast<__half2 *>(y1 + off) = ya;
+            *reinterpret_cast<__half2 *>(y2 + off) = __floats2half2_rn(v[k].y - yf.x, v[k].w - yf.y);
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (MMA)
@@ -411,21 +415,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
   } else if (warp == kTcSplit / 32) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      const uint32_t idesc =
-          (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcP >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+      // D = F32, A = B = F16 (format 0), both K-major, N = 32, M = 128
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(kTcP >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
       uint32_t pc = 0, tileIt = 0;
+      long long cFree = 0, cAcc = 0, cFull = 0, cTaps = 0, cIssue = 0, cTotal = clock64(), tA;
       for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, tileIt++) {
         bool corrStartedT = false, corrStartedS = false;
         for (int pr = 0; pr < p.numPairs; pr++, pc++) {
           const int buf = pc & 1;
           const uint32_t use = pc >> 1;
-          if (use > 0) tc_wait(opFree + buf, (use - 1) & 1);
+          tA = clock64();
+          if (use > 0) tc_wait<false>(opFree + buf, (use - 1) & 1);
+          cFree += clock64() - tA;
           mbar_expect_tx(tapsFull + buf, G.tapsPairBytes);
           bulk_g2s(tapsBuf(buf), reinterpret_cast<const unsigned char *>(p.taps) + (size_t)pr * G.tapsPairBytes,
                    G.tapsPairBytes, tapsFull + buf);
-          if (pr == 0 && tileIt > 0) tc_wait(accEmpty, (tileIt - 1) & 1);   // epilogue has drained the accumulators
-          tc_wait(opFull + buf, use & 1);
-          tc_wait(tapsFull + buf, use & 1);
+          tA = clock64();
+          if (pr == 0 && tileIt > 0) tc_wait<false>(accEmpty, (tileIt - 1) & 1);   // epilogue has drained the accumulators
+          cAcc += clock64() - tA;
+          tA = clock64();
+          tc_wait<false>(opFull + buf, use & 1);
+          cFull += clock64() - tA;
+          tA = clock64();
+          tc_wait<false>(tapsFull + buf, use & 1);
+          cTaps += clock64() - tA;
+          tA = clock64();
           asm volatile("tcgen05.fence::after_thread_sync;");
           for (int h = 0; h < 2; h++) {
             const int c = 2 * pr + h;
@@ -433,18 +447,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
             const uint32_t dMain = tmem + 32u * (c == 0 ? 0u : (uint32_t)(2 + c));
             const uint32_t dCorr = tmem + 32u * (c == 0 ? 1u : 2u);
             const uint32_t tHiA = smem_u32(tapsBuf(buf)) + (uint32_t)h * G.tapsChanBytes;
-            const uint64_t aHi = tc_desc(smem_u32(ops(buf, h, 0)), 1024, 2), aLo = tc_desc(smem_u32(ops(buf, h, 1)), 1024, 2);
+            const uint64_t aHi = tc_desc(smem_u32(ops(buf, h, 0)), 512, 4), aLo = tc_desc(smem_u32(ops(buf, h, 1)), 512, 4);
             const uint64_t tHi = tc_desc(tHiA, 256, 6), tLo = tc_desc(tHiA + (uint32_t)G.natom * 256u, 256, 6);
             bool &started = c == 0 ? corrStartedT : corrStartedS;
-            // one K step: A start +32 B (2 descriptor units), taps start +256 B (16 units)
-            for (int s = 0; s < G.KS; s++) tc_mma(dMain, aHi + 2u * s, tHi + 16u * s, idesc, s > 0);
-            for (int s = 0; s < G.KS; s++) tc_mma(dCorr, aLo + 2u * s, tHi + 16u * s, idesc, started || s > 0);
+            // one K step of 16: A start +32 B (2 descriptor units), taps start +2 atoms = 512 B (32 units)
+            for (int s = 0; s < G.KS; s++) tc_mma(dMain, aHi + 2u * s, tHi + 32u * s, idesc, s > 0);
+            for (int s = 0; s < G.KS; s++) tc_mma(dCorr, aLo + 2u * s, tHi + 32u * s, idesc, started || s > 0);
             started = true;
-            for (int s = 0; s < G.KS; s++) tc_mma(dCorr, aHi + 2u * s, tLo + 16u * s, idesc, 1);
+            for (int s = 0; s < G.KS; s++) tc_mma(dCorr, aHi + 2u * s, tLo + 32u * s, idesc, 1);
           }
           tc_commit(opFree + buf);
           if (pr == p.numPairs - 1) tc_commit(accFull);
+          cIssue += clock64() - tA;
         }
+      }
+      if (p.prof) {
+        long long *o = p.prof + 8 * blockIdx.x;
+        o[0] = clock64() - cTotal; o[1] = cFree; o[2] = cAcc; o[3] = cFull; o[4] = cTaps; o[5] = cIssue; o[6] = tileIt;
       }
     }
   } else {

@@ -175,6 +175,96 @@ __global__ void __launch_bounds__(128, 1) k_rate(long long *cyclesOut, int reps,
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
+// ---- the same question for FP16 operands (kind::f16, K = 16): A = Hankel view with SWIZZLE_64B (row pitch 64 B =
+// 32 halves), taps atoms of 8 rows x 16 k (SWIZZLE_32B), atom index a = 2 s + g'
+#include <cuda_fp16.h>
+constexpr int KS16 = (P + W + 15) / 16, NATOM16 = 2 * (KS16 - 1) + 4;
+constexpr int ROWS16 = M + (KS16 * 16 + 31) / 32 + 1;
+
+__global__ void __launch_bounds__(128, 1) k_probe16(const float *__restrict__ sig, const float *__restrict__ taps,
+                                                    float *__restrict__ out, long long *cyc, int reps) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *sA = smem + ((1024 - (smem_u32(smem) & 1023)) & 1023);   // ROWS16 x 64 B, SWIZZLE_64B
+  unsigned char *sB = sA + ((ROWS16 * 64 + 1023) / 1024) * 1024;          // NATOM16 x 256 B, SWIZZLE_32B
+  __shared__ uint32_t tmemBase;
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // linear half index L -> row L/32 (64 B), 16-byte chunk (L%32)/8, swizzled chunk ^ ((row >> 1) & 3)
+  for (int L = tid; L < ROWS16 * 32; L += blockDim.x) {
+    const int row = L >> 5, ch = (L & 31) >> 3, w = L & 7;
+    *reinterpret_cast<__half *>(sA + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4) + w * 2) = __float2half_rn(sig[L]);
+  }
+  // atom a, row cc (0..7), k column kk (0..15): tap index 8 a + kk + cc - 31; SWIZZLE_32B: chunk ^ (cc >> 2 & 1)
+  for (int e = tid; e < NATOM16 * 128; e += blockDim.x) {
+    const int a = e >> 7, cc = (e >> 4) & 7, kk = e & 15;
+    const int q = 8 * a + kk + cc - 31;
+    const float v = (q >= 0 && q < W) ? taps[q] : 0.f;
+    const int ch = kk >> 3, w = kk & 7;
+    *reinterpret_cast<__half *>(sB + a * 256 + cc * 32 + ((ch ^ ((cc >> 2) & 1)) << 4) + w * 2) = __float2half_rn(v);
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(&tmemBase)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = tmemBase;
+  if (tid == 0) {
+    // D = F32, A = B = F16 (format 0), K-major, N = 32, M = 128
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(P >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    const uint64_t da0 = make_desc(smem_u32(sA), 512, 4, 0), db0 = make_desc(smem_u32(sB), 256, 6, 0);
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; r++)
+      for (int s = 0; s < KS16; s++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem),
+            "l"(da0 + 2u * s), "l"(db0 + 32u * s), "r"(idesc), "r"((uint32_t)(s > 0)));
+      }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)));
+    uint32_t done = 0;
+    for (int it = 0; it < (1 << 24) && !done; it++)
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+          : "=r"(done)
+          : "r"(smem_u32(&bar)));
+    cyc[0] = clock64() - t0;
+  } else {
+    uint32_t done = 0;
+    for (int it = 0; it < (1 << 24) && !done; it++)
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+          : "=r"(done)
+          : "r"(smem_u32(&bar)));
+  }
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  uint32_t v[32];
+  const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  const int r = warp * 32 + lane;
+  for (int c = 0; c < 32; c++) out[32 * r + 31 - c] = __uint_as_float(v[c]);
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem));
+}
+
 static float tf32_trunc(float x) {
   uint32_t b;
   memcpy(&b, &x, 4);
@@ -218,6 +308,27 @@ int main() {
   }
   long long *dCyc, hCyc[2];
   cudaMalloc(&dCyc, 16);
+  {
+    const size_t smem16 = ((ROWS16 * 64 + 1023) / 1024) * 1024 + NATOM16 * 256 + 2048;
+    cudaFuncSetAttribute(k_probe16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
+    for (int reps = 1; reps <= 400; reps *= 400) {
+      cudaMemset(dOut, 0xFF, nOut * 4);
+      k_probe16<<<1, 128, smem16>>>(dSig, dTaps, dOut, dCyc, reps);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("{\"f16_error\": \"%s\"}\n", cudaGetErrorString(e)); return 1; }
+      cudaMemcpy(out.data(), dOut, nOut * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(hCyc, dCyc, 8, cudaMemcpyDeviceToHost);
+      double maxErr = 0;
+      for (int t = 0; t < nOut; t++) {
+        double ref = 0;
+        for (int i = 0; i < W; i++) ref += (double)__half2float(__float2half_rn(taps[i])) * (double)__half2float(__float2half_rn(sig[t + i]));
+        double err = fabs((double)out[t] - ref);
+        if (err > maxErr || err != err) maxErr = err;
+      }
+      printf("{\"shape\": \"M128 N32 K16 f16, Hankel A (SWIZZLE_64B)\", \"reps\": %d, \"max_abs_err_vs_fp16_inputs\": %.3e, "
+             "\"cycles_per_mma\": %.1f}\n", reps, maxErr, (double)hCyc[0] / ((double)reps * KS16));
+    }
+  }
   const size_t smemR = ((ROWS * 128 + 1023) / 1024) * 1024 + NATOM * 256 * 4 + 2048;
   cudaFuncSetAttribute(k_rate<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemR);
   cudaFuncSetAttribute(k_rate<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemR);
