@@ -533,13 +533,7 @@ int sgz_corr_scan(sgz_corr *job) {
   if (job->abortFlag) return SGZ_ERR_ABORTED;
   size_t n = (size_t)job->numTiles * kR * job->ntg;
   const bool tc = job->useTc && db->chunks.empty();   // a streaming scan hides K1 behind PCIe anyway: FFMA path
-  if (tc) {
-    n = std::max(n, (size_t)ceil_div<int64_t>(job->numTilesTc * kTcTile, kStatT) * kStatT);
-    SGZ_TRY(job->stAT.alloc(n));
-    SGZ_TRY(job->stBT.alloc(n));
-    SGZ_TRY(job->stAS.alloc(n));
-    SGZ_TRY(job->stBS.alloc(n));
-  }
+  if (tc) n = std::max(n, (size_t)job->numTilesTc * kTcTile);
   SGZ_TRY(job->simIn.alloc(n));
   SGZ_TRY(job->boostIn.alloc(n));
   SGZ_TRY(job->dFileMax.alloc((size_t)std::max(db->numFiles(), 1)));

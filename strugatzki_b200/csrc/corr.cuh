@@ -29,7 +29,6 @@ struct sgz_corr {
   int nslot = 3;
   bool useTc = false;       // K1 on the tensor cores (corr_tc.cuh) for resident scans
   int64_t numTilesTc = 0;
-  DevBuf<float> stAT, stBT, stAS, stBS;   // window statistics of the tensor-core path
   int64_t numTiles = 0;
   int64_t numOffsets = 0;
   DevBuf<float> simIn, boostIn, simOut, boostOut, rowMaxOut;
@@ -214,30 +213,21 @@ inline int run_scan_one(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim,
   return SGZ_OK;
 }
 
-// tensor-core variant of run_scan_one over the whole database: window statistics, cross terms + sim, file maxima
+// tensor-core variant of run_scan_one over the whole database (one fused kernel, see corr_tc.cuh)
 inline int run_scan_tc(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim, float *boost,
                        unsigned long long *fileMax, cudaStream_t st) {
   sgz_db *db = job->db;
   sgz_ctx *ctx = job->ctx;
   const TcGeom G = tc_geom(q.W);
-  CorrStatsParams sp{};
-  sp.data = db->dData.p; sp.rowStride = db->capFrames; sp.usedFrames = db->usedFrames;
-  sp.numCh = db->numCh; sp.numPairs = db->numPairs; sp.W = q.W;
-  sp.stdT = q.stdT; sp.stdS = q.stdS; sp.rhoT = q.rhoT; sp.rhoS = q.rhoS; sp.lnAvgIn = q.lnAvg;
-  sp.fileStart = db->dFileStart.p; sp.numFiles = db->numFiles(); sp.tailExtra = tailExtra;
-  sp.numTiles = ceil_div<int64_t>(job->numTilesTc * kTcTile, kStatT);
-  sp.aT = job->stAT.p; sp.bT = job->stBT.p; sp.aS = job->stAS.p; sp.bS = job->stBS.p; sp.boost = boost;
-  const int rowFrames = kStatT + q.W, numChunks = (rowFrames + kR - 1) / kR;
-  const size_t smS = (((size_t)rowFrames * 4 + 15) / 16) * 16 + (((size_t)rowFrames * 8 + 15) / 16) * 16 +
-                     (size_t)(numChunks + 1) * 32;
-  SGZ_CUDA(cudaFuncSetAttribute(k_corr_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smS));
-  k_corr_stats<<<(unsigned)std::min<int64_t>(sp.numTiles, (int64_t)ctx->smCount * 2), kStatThreads, smS, st>>>(sp);
-  SGZ_LAUNCH_CHECK(ctx);
   CorrTcParams tp{};
-  tp.data = db->dData.p; tp.rowStride = db->capFrames; tp.numCh = db->numCh; tp.numPairs = db->numPairs; tp.W = q.W;
-  tp.taps = q.dTcTaps.p; tp.weight = q.weight; tp.maxBoost = job->cfg.maxBoost;
+  tp.data = db->dData.p; tp.rowStride = db->capFrames; tp.usedFrames = db->usedFrames;
+  tp.numCh = db->numCh; tp.numPairs = db->numPairs; tp.W = q.W;
+  tp.taps = q.dTcTaps.p;
+  tp.stdT = q.stdT; tp.stdS = q.stdS; tp.rhoT = q.rhoT; tp.rhoS = q.rhoS; tp.lnAvgIn = q.lnAvg;
+  tp.weight = q.weight; tp.maxBoost = job->cfg.maxBoost;
+  tp.fileStart = db->dFileStart.p; tp.numFiles = db->numFiles(); tp.tailExtra = tailExtra;
   tp.tileBegin = 0; tp.tileEnd = job->numTilesTc;
-  tp.aT = job->stAT.p; tp.bT = job->stBT.p; tp.aS = job->stAS.p; tp.bS = job->stBS.p; tp.boost = boost; tp.sim = sim;
+  tp.sim = sim; tp.boost = boost; tp.fileMax = fileMax;
   SGZ_CUDA(cudaFuncSetAttribute(k_corr_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));
   const unsigned gridTc = (unsigned)std::min<int64_t>(job->numTilesTc, ctx->smCount);
   DevBuf<long long> dProf;
@@ -258,10 +248,6 @@ inline int run_scan_tc(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim, 
     const double tiles = a[6] > 0 ? a[6] : 1;
     fprintf(stderr, "k_corr_tc issuer cycles per tile: total %.0f | wait opFree %.0f, accEmpty %.0f, opFull %.0f, taps %.0f, "
                     "issue %.0f\n", a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles, a[4] / tiles, a[5] / tiles);
-  }
-  if (fileMax && db->numFiles() > 0) {
-    k_file_max<<<db->numFiles(), 256, 0, st>>>(sim, db->dFileStart.p, db->numFiles(), q.W, tailExtra, fileMax);
-    SGZ_LAUNCH_CHECK(ctx);
   }
   return SGZ_OK;
 }

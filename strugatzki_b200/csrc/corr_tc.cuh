@@ -18,8 +18,8 @@
 // MMAs (K = 16 per instruction at 44 cycles vs K = 8 at 50 -- the A-operand fetch bounds small-N MMAs either way).
 // 16 accumulators x 32 columns = all 512 TMEM columns: [T main, T corr, S corr, 13 spectral mains].
 //
-// The window statistics (mean / variance / loudness boost), which the FFMA kernel builds on the fly, come from a
-// separate HBM-bound pass (k_corr_stats) and the per-file maxima from a third (k_file_max).
+// The split warps, which touch every element anyway, also build the per-frame sums; the epilogue warps turn them into the
+// window statistics (FP64 row sums + sliding, the FFMA kernel's arithmetic), the sim / boost curves and the file maxima.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -34,6 +34,7 @@ struct TcGeom {
   uint32_t chanBytes;      // one FP16 operand buffer (first or second part) of one channel: rows x 64 B, multiple of 1024
   uint32_t tapsChanBytes;  // taps atoms of one channel: first then second FP16 part, natom x 256 B each
   uint32_t tapsPairBytes;  // two channels, rounded up to 1024
+  uint32_t t0Bytes, fBytes, rsBytes;   // per-frame loudness / spectral sums, FP64 row sums
   size_t smemBytes;
 };
 
@@ -46,7 +47,11 @@ __host__ __device__ inline TcGeom tc_geom(int W) {
   g.chanBytes = (uint32_t)((g.rows * 64 + 1023) / 1024 * 1024);
   g.tapsChanBytes = (uint32_t)(g.natom * 256 * 2);
   g.tapsPairBytes = (uint32_t)((2 * g.tapsChanBytes + 1023) / 1024 * 1024);
-  g.smemBytes = (size_t)8 * g.chanBytes + (size_t)2 * g.tapsPairBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  g.t0Bytes = (uint32_t)((g.rows * 32 * 4 + 127) / 128 * 128);
+  g.fBytes = (uint32_t)(g.rows * 32 * 8);
+  g.rsBytes = (uint32_t)(g.rows * 32);
+  g.smemBytes = (size_t)8 * g.chanBytes + (size_t)2 * g.tapsPairBytes + g.t0Bytes + g.fBytes + g.rsBytes +
+                1024 /*alignment slack*/ + 256 /*barriers*/;
   return g;
 }
 
@@ -80,220 +85,21 @@ inline void tc_build_taps(const std::vector<float> &pairTaps /*[numPairs][Wq] fl
 }
 
 // ---------------------------------------------------------------------------------------------
-// pass 1: window statistics per offset (HBM-bound: 56 B read, 20 B written per offset)
-//   temporal = (crossT - bT) * aT,  spectral = (crossS - bS) * aS;  invalid offsets: all NaN
-// ---------------------------------------------------------------------------------------------
-struct CorrStatsParams {
-  const float2 *data;
-  int64_t rowStride, usedFrames;
-  int numCh, numPairs, W;
-  double stdT, stdS, rhoT, rhoS, lnAvgIn;
-  const int64_t *fileStart;
-  int numFiles, tailExtra;
-  int64_t numTiles;          // tiles of kR * 256 offsets
-  float *aT, *bT, *aS, *bS, *boost;
-};
-
-constexpr int kStatThreads = 256, kStatT = kR * kStatThreads;
-
-__global__ void __launch_bounds__(kStatThreads, 2) k_corr_stats(const CorrStatsParams p) {
-  extern __shared__ __align__(128) unsigned char smemStat[];
-  const int W = p.W, rowFrames = kStatT + W, numChunks = (rowFrames + kR - 1) / kR;
-  float *T0 = reinterpret_cast<float *>(smemStat);
-  float2 *F = reinterpret_cast<float2 *>(smemStat + (((size_t)rowFrames * 4 + 15) / 16) * 16);
-  double *CP = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(F) + (((size_t)rowFrames * 8 + 15) / 16) * 16);
-  __shared__ int fileLoHi[2];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const double invW = 1.0 / (double)W, invNS = 1.0 / ((double)(p.numCh - 1) * (double)W);
-  const float cT = (float)(invW / p.stdT), cS = (float)(invNS / p.stdS);
-  const float rhoT = (float)p.rhoT, rhoS = (float)p.rhoS, l2In = (float)(p.lnAvgIn * 1.4426950408889634);
-  const float qnan = __int_as_float(0x7fc00000);
-  const int nq = W / kR, remW = W - nq * kR;
-  constexpr int kPer = 16;   // frames per thread: ceil((kStatT + W) / 256) for W <= 512
-
-  for (int64_t tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
-    const int64_t t0 = tile * kStatT;
-    if (tid < 2) {
-      int64_t g = tid == 0 ? t0 : min(t0 + kStatT - 1, p.usedFrames - 1);
-      int lo = 0, hi = p.numFiles;
-      while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (p.fileStart[mid] <= g) lo = mid; else hi = mid;
-      }
-      fileLoHi[tid] = lo;
-    }
-    // per-frame sums over the channels, kept in registers until all pair rows went by
-    float b0[kPer], s1[kPer], s2[kPer];
-#pragma unroll
-    for (int k = 0; k < kPer; k++) { b0[k] = 0.f; s1[k] = 0.f; s2[k] = 0.f; }
-    for (int c = 0; c < p.numPairs; c++) {
-      const float2 *row = p.data + (int64_t)c * p.rowStride + t0;
-      float2 v[kPer];
-#pragma unroll
-      for (int k = 0; k < kPer; k++) {
-        const int j = tid + k * kStatThreads;
-        v[k] = j < rowFrames ? __ldg(row + j) : make_float2(0.f, 0.f);
-      }
-      if (c == 0) {
-#pragma unroll
-        for (int k = 0; k < kPer; k++) { b0[k] = v[k].x; s1[k] = v[k].y; s2[k] = v[k].y * v[k].y; }
-      } else {
-#pragma unroll
-        for (int k = 0; k < kPer; k++) {
-          s1[k] += v[k].x + v[k].y;
-          s2[k] = fmaf(v[k].x, v[k].x, fmaf(v[k].y, v[k].y, s2[k]));
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < kPer; k++) {
-      const int j = tid + k * kStatThreads;
-      if (j < rowFrames) { T0[j] = b0[k]; F[j] = make_float2(s1[k], s2[k]); }
-    }
-    __syncthreads();
-    // FP64 chunk sums (14 frames), then an exclusive prefix over the chunks
-    for (int j = tid; j < numChunks; j += kStatThreads) {
-      double a1 = 0, a2 = 0, a3 = 0, a4 = 0;
-      const int e0 = kR * j, e1 = min(kR * (j + 1), rowFrames);
-      for (int e = e0; e < e1; e++) {
-        const double x = (double)T0[e];
-        const float2 f = F[e];
-        a1 += x; a2 += x * x; a3 += (double)f.x; a4 += (double)f.y;
-      }
-      double *o = CP + 4 * (size_t)(j + 1);
-      o[0] = a1; o[1] = a2; o[2] = a3; o[3] = a4;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      const int per = (numChunks + 31) / 32;
-      const int jb = min(lane * per, numChunks), je = min(jb + per, numChunks);
-      double r1 = 0, r2 = 0, r3 = 0, r4 = 0;
-      for (int j = jb; j < je; j++) {
-        double *o = CP + 4 * (size_t)(j + 1);
-        r1 += o[0]; r2 += o[1]; r3 += o[2]; r4 += o[3];
-        o[0] = r1; o[1] = r2; o[2] = r3; o[3] = r4;
-      }
-      double i1 = r1, i2 = r2, i3 = r3, i4 = r4;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const double o1 = __shfl_up_sync(0xffffffffu, i1, d), o2 = __shfl_up_sync(0xffffffffu, i2, d);
-        const double o3 = __shfl_up_sync(0xffffffffu, i3, d), o4 = __shfl_up_sync(0xffffffffu, i4, d);
-        if (lane >= d) { i1 += o1; i2 += o2; i3 += o3; i4 += o4; }
-      }
-      const double x1 = i1 - r1, x2 = i2 - r2, x3 = i3 - r3, x4 = i4 - r4;
-      for (int j = jb; j < je; j++) {
-        double *o = CP + 4 * (size_t)(j + 1);
-        o[0] += x1; o[1] += x2; o[2] += x3; o[3] += x4;
-      }
-      if (lane == 0) { CP[0] = 0; CP[1] = 0; CP[2] = 0; CP[3] = 0; }
-    }
-    __syncthreads();
-    // per thread: 14 consecutive offsets, window sums slid in FP64 (same arithmetic as the FFMA kernel's epilogue)
-    const int o = tid * kR;
-    D4 win;
-    {
-      const double *c0 = CP + 4 * (size_t)tid, *c1 = CP + 4 * (size_t)(tid + nq);
-      win = {c1[0] - c0[0], c1[1] - c0[1], c1[2] - c0[2], c1[3] - c0[3]};
-      for (int k = 0; k < remW; k++) {
-        const int e = o + kR * nq + k;
-        const double x = (double)T0[e];
-        const float2 f = F[e];
-        win.t1 += x; win.t2 += x * x; win.s1 += (double)f.x; win.s2 += (double)f.y;
-      }
-    }
-    const int64_t g0 = t0 + o;
-    int f = fileLoHi[0];
-    {
-      int lo = fileLoHi[0], hi = fileLoHi[1] + 1;
-      while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (p.fileStart[mid] <= g0) lo = mid; else hi = mid;
-      }
-      f = lo;
-    }
-    int64_t fStart = p.fileStart[f], fEnd = p.fileStart[f + 1];
-    for (int k = 0; k < kR; k++) {
-      const double mT = win.t1 * invW;
-      const float avgB = (float)mT;                                          // MathUtil.avg -> Float
-      float boost = exp2f((l2In - __log2f(avgB)) * (1.0f / 0.6f));           // calcBoost
-      float aT, bT, aS, bS;
-      {
-        const double q = win.t2 * invW;
-        const double var = q - mT * mT;
-        bT = (float)mT * rhoT;
-        aT = (var > 1e-13 * q) ? cT * rsqrtf((float)var) : qnan;
-      }
-      {
-        const double mS = win.s1 * invNS;
-        const double q = win.s2 * invNS;
-        const double var = q - mS * mS;
-        bS = (float)mS * rhoS;
-        aS = (var > 1e-13 * q) ? cS * rsqrtf((float)var) : qnan;
-      }
-      const int64_t g = g0 + k;
-      while (g >= fEnd && f + 1 < p.numFiles) { f++; fStart = fEnd; fEnd = p.fileStart[f + 1]; }
-      const int64_t nValid = (fEnd - fStart) - p.tailExtra - W + 1;
-      if (!(g < p.usedFrames && g - fStart < nValid)) { aT = bT = aS = bS = boost = qnan; }
-      p.aT[g] = aT; p.bT[g] = bT; p.aS[g] = aS; p.bS[g] = bS; p.boost[g] = boost;
-      if (k < kR - 1) {
-        const int e = o + k;
-        const double bo = (double)T0[e], bn = (double)T0[e + W];
-        const float2 fo = F[e], fn = F[e + W];
-        win.t1 += bn - bo;
-        win.t2 += bn * bn - bo * bo;
-        win.s1 += (double)fn.x - (double)fo.x;
-        win.s2 += (double)fn.y - (double)fo.y;
-      }
-    }
-    __syncthreads();
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// pass 3: per-file maximum of the sim curve, first occurrence (same packed key as the FFMA kernel)
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_file_max(const float *__restrict__ sim, const int64_t *__restrict__ fileStart,
-                                                  int numFiles, int W, int tailExtra,
-                                                  unsigned long long *__restrict__ fileMax) {
-  const int f = blockIdx.x;
-  const int64_t g0 = fileStart[f];
-  const int64_t nValid = (fileStart[f + 1] - g0) - tailExtra - W + 1;
-  unsigned long long best = 0ull;
-  for (int64_t t = threadIdx.x; t < nValid; t += blockDim.x) {
-    const float s = sim[g0 + t];
-    if (s == s) {
-      const unsigned long long key =
-          ((unsigned long long)float_order_key(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)t);
-      if (key > best) best = key;
-    }
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
-    if (o > best) best = o;
-  }
-  __shared__ unsigned long long wbest[8];
-  if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = best;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; w++) if (wbest[w] > best) best = wbest[w];
-    fileMax[f] = best;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// pass 2: cross terms on the tensor cores + final sim
+// the kernel: cross terms on the tensor cores, window statistics and the final sim fused
 // ---------------------------------------------------------------------------------------------
 struct CorrTcParams {
   const float2 *data;
-  int64_t rowStride;
+  int64_t rowStride, usedFrames;
   int numCh, numPairs, W;
   const uint16_t *taps;     // tc_build_taps image, numPairs x tapsPairBytes
+  double stdT, stdS, rhoT, rhoS, lnAvgIn;
   float weight, maxBoost;
+  const int64_t *fileStart;
+  int numFiles, tailExtra;
   int64_t tileBegin, tileEnd;   // tiles of 4096 offsets
-  const float *aT, *bT, *aS, *bS, *boost;
-  float *sim;
-  long long *prof;          // developer probe (SGZ_CORR_TC_PROF): per CTA 8 cycle counters, or nullptr
+  float *sim, *boost;
+  unsigned long long *fileMax;  // [numFiles] packed (order_key(sim) << 32 | ~offset), or nullptr
+  long long *prof;              // developer probe (SGZ_CORR_TC_PROF): per CTA 8 cycle counters, or nullptr
 };
 
 __device__ __forceinline__ uint64_t tc_desc(uint32_t addr, uint32_t sbo, uint32_t layout) {
@@ -322,8 +128,7 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
-// bounded wait: a protocol error must end in a trap (visible CUDA error), not in a hung GPU box.  Waiting warps back
-// off with nanosleep: a spinning warp would steal issue slots from the single MMA-issuer lane on its scheduler.
+// bounded wait: a protocol error must end in a trap (visible CUDA error), not in a hung GPU box
 template <bool kSleep = true>
 __device__ __forceinline__ void tc_wait(uint64_t *bar, uint32_t parity) {
   uint32_t done = 0;
@@ -337,9 +142,10 @@ __device__ __forceinline__ void tc_wait(uint64_t *bar, uint32_t parity) {
   }
   if (!done) __trap();
 }
+__device__ __forceinline__ void tc_epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
 
-// warps 0..7: split workers (global pair row -> swizzled hi / lo operand buffers), warp 8: MMA issuer (one lane),
-// warps 9..12: epilogue (TMEM lane quarter = warp % 4)
+// warps 0..7: split workers (global pair row -> swizzled FP16 operand buffers + per-frame sums), warp 8: MMA issuer
+// (one lane), warps 9..12: epilogue (TMEM lane quarter = warp % 4; window statistics, sim, file maxima)
 constexpr int kTcSplit = 256, kTcThreads = kTcSplit + 32 + 128;
 
 __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p) {
@@ -350,9 +156,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
   auto ops = [&](int buf, int h, int part) { return base + (size_t)((buf * 2 + h) * 2 + part) * G.chanBytes; };
   unsigned char *tapsBase = base + (size_t)8 * G.chanBytes;
   auto tapsBuf = [&](int buf) { return tapsBase + (size_t)buf * G.tapsPairBytes; };
-  uint64_t *bars = reinterpret_cast<uint64_t *>(tapsBase + (size_t)2 * G.tapsPairBytes);
+  float *T0 = reinterpret_cast<float *>(tapsBase + (size_t)2 * G.tapsPairBytes);           // loudness per frame
+  float2 *F = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(T0) + G.t0Bytes);   // (sum_c b, sum_c b^2)
+  double *RS = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(F) + G.fBytes);    // [rows][4] row sums
+  uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(RS) + G.rsBytes);
   uint64_t *opFree = bars, *opFull = bars + 2, *tapsFull = bars + 4, *accFull = bars + 6, *accEmpty = bars + 7;
-  uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(bars + 8);
+  uint64_t *statsFull = bars + 8, *statsFree = bars + 9;
+  uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(bars + 10);
+  int *fileLoHi = reinterpret_cast<int *>(bars + 11);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
@@ -361,6 +172,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
     mbar_init(tapsFull, 1); mbar_init(tapsFull + 1, 1);
     mbar_init(accFull, 1);
     mbar_init(accEmpty, 4);
+    mbar_init(statsFull, kTcSplit / 32);
+    mbar_init(statsFree, 4);
     fence_mbar_init();
   }
   __syncthreads();
@@ -377,9 +190,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
   if (warp < kTcSplit / 32) {
     // =========================== split workers ===========================
     constexpr int kPer = 10;                            // >= ceil(nFrames / 512) for W <= 512; two frames per step
-    uint32_t pc = 0;
-    for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x) {
+    uint32_t pc = 0, tileIt = 0;
+    for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, tileIt++) {
       const int64_t t0 = tile * kTcTile;
+      float b0[2 * kPer], s1[2 * kPer], s2[2 * kPer];   // per-frame sums over the channels of this thread's frames
       for (int pr = 0; pr < p.numPairs; pr++, pc++) {
         const int buf = pc & 1;
         const uint32_t use = pc >> 1;
@@ -389,6 +203,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
         for (int k = 0; k < kPer; k++) {                // all loads of the pair row in flight before the wait
           const int L2 = tid + k * kTcSplit;            // frames 2 L2, 2 L2 + 1
           v[k] = 2 * L2 < nFrames ? __ldg(row + L2) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (pr == 0) {   // pair 0 = (loudness, first spectral channel)
+#pragma unroll
+          for (int k = 0; k < kPer; k++) {
+            b0[2 * k] = v[k].x; s1[2 * k] = v[k].y; s2[2 * k] = v[k].y * v[k].y;
+            b0[2 * k + 1] = v[k].z; s1[2 * k + 1] = v[k].w; s2[2 * k + 1] = v[k].w * v[k].w;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < kPer; k++) {
+            s1[2 * k] += v[k].x + v[k].y; s2[2 * k] = fmaf(v[k].x, v[k].x, fmaf(v[k].y, v[k].y, s2[2 * k]));
+            s1[2 * k + 1] += v[k].z + v[k].w; s2[2 * k + 1] = fmaf(v[k].z, v[k].z, fmaf(v[k].w, v[k].w, s2[2 * k + 1]));
+          }
         }
         if (use > 0) tc_wait(opFree + buf, (use - 1) & 1);   // MMAs of the pair that last used this buffer are done
         unsigned char *x1 = ops(buf, 0, 0), *x2 = ops(buf, 0, 1), *y1 = ops(buf, 1, 0), *y2 = ops(buf, 1, 1);
@@ -411,6 +238,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
         __syncwarp();
         if (lane == 0) mbar_arrive(opFull + buf);
       }
+      // per-frame sums of the tile -> shared memory for the epilogue warps
+      if (tileIt > 0) tc_wait(statsFree, (tileIt - 1) & 1);
+#pragma unroll
+      for (int k = 0; k < kPer; k++) {
+        const int L = 2 * (tid + k * kTcSplit);
+        if (L < nFrames) {
+          *reinterpret_cast<float2 *>(T0 + L) = make_float2(b0[2 * k], b0[2 * k + 1]);
+          *reinterpret_cast<float4 *>(F + L) = make_float4(s1[2 * k], s2[2 * k], s1[2 * k + 1], s2[2 * k + 1]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(statsFull);
     }
   } else if (warp == kTcSplit / 32) {
     // =========================== MMA issuer ===========================
@@ -469,17 +308,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
   } else {
     // =========================== epilogue ===========================
     // TMEM lanes 32 q .. 32 q + 31 (q = warp % 4) = rows r; row r = offsets t0 + 32 r + (31 - column)
-    const int quarter = warp & 3;
+    const int quarter = warp & 3, et = (warp - (kTcSplit / 32 + 1)) * 32 + lane;   // et = 0..127
+    const int W = p.W, nr = W >> 5, rem = W & 31;
     const bool useT = p.weight > 0.f, useS = p.weight < 1.f;
     const float qnan = __int_as_float(0x7fc00000);
+    const double invW = 1.0 / (double)W, invNS = 1.0 / ((double)(p.numCh - 1) * (double)W);
+    const float cT = (float)(invW / p.stdT), cS = (float)(invNS / p.stdS);
+    const float rhoT = (float)p.rhoT, rhoS = (float)p.rhoS, l2In = (float)(p.lnAvgIn * 1.4426950408889634);
     uint32_t tileIt = 0;
     for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, tileIt++) {
       const int64_t t0 = tile * kTcTile;
+      if (et < 2) {   // file range of the tile
+        const int64_t gq = et == 0 ? t0 : min(t0 + kTcTile - 1, p.usedFrames - 1);
+        int lo = 0, hi = p.numFiles;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (p.fileStart[mid] <= gq) lo = mid; else hi = mid;
+        }
+        fileLoHi[et] = lo;
+      }
       tc_wait(accFull, tileIt & 1);
       asm volatile("tcgen05.fence::after_thread_sync;");
       const int r = quarter * 32 + lane;
       const uint32_t laneAddr = tmem + ((uint32_t)(quarter * 32) << 16);
-      const int64_t gRow = t0 + 32 * (int64_t)r;
       float accT[32], accS[32];
 #pragma unroll
       for (int half = 0; half < 2; half++) {
@@ -499,33 +350,108 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
           for (int i = 0; i < 16; i++) accS[16 * half + i] += v[i];
         }
       }
-      // the accumulators are in registers: hand TMEM back to the issuer before the global-memory part
+      // the accumulators are in registers: hand TMEM back to the issuer
       asm volatile("tcgen05.fence::before_thread_sync;");
       __syncwarp();
       if (lane == 0) mbar_arrive(accEmpty);
+
+      // ---- window statistics: FP64 sums of whole 32-frame rows, then slide frame by frame inside the row ----
+      tc_wait(statsFull, tileIt & 1);
+      for (int rr = r; rr < G.rows; rr += 128) {
+        double a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+        const int e0 = 32 * rr;
+#pragma unroll 8
+        for (int k = 0; k < 32; k++) {
+          const double x = (double)T0[e0 + k];
+          const float2 f = F[e0 + k];
+          a1 += x; a2 += x * x; a3 += (double)f.x; a4 += (double)f.y;
+        }
+        double *o = RS + 4 * rr;
+        o[0] = a1; o[1] = a2; o[2] = a3; o[3] = a4;
+      }
+      tc_epi_sync();
+      D4 win = {0, 0, 0, 0};
+      for (int i = 0; i < nr; i++) {
+        const double *o = RS + 4 * (r + i);
+        win.t1 += o[0]; win.t2 += o[1]; win.s1 += o[2]; win.s2 += o[3];
+      }
+      for (int k = 0; k < rem; k++) {
+        const int e = 32 * (r + nr) + k;
+        const double x = (double)T0[e];
+        const float2 f = F[e];
+        win.t1 += x; win.t2 += x * x; win.s1 += (double)f.x; win.s2 += (double)f.y;
+      }
+      const int64_t g0 = t0 + 32 * (int64_t)r;
+      int f = fileLoHi[0];
+      {
+        int lo = fileLoHi[0], hi = fileLoHi[1] + 1;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (p.fileStart[mid] <= g0) lo = mid; else hi = mid;
+        }
+        f = lo;
+      }
+      int64_t fStart = p.fileStart[f], fEnd = p.fileStart[f + 1];
+      unsigned long long best = 0ull;
+      const float *T0r = T0 + 32 * r;
+      const float2 *Fr = F + 32 * r;
 #pragma unroll
-      for (int q4 = 0; q4 < 8; q4++) {                   // offsets 4 q4 .. 4 q4 + 3 of the row <-> columns 31 - offset
-        const int64_t g = gRow + 4 * q4;
-        const float4 cAT = __ldg(reinterpret_cast<const float4 *>(p.aT + g));
-        const float4 cBT = __ldg(reinterpret_cast<const float4 *>(p.bT + g));
-        const float4 cAS = __ldg(reinterpret_cast<const float4 *>(p.aS + g));
-        const float4 cBS = __ldg(reinterpret_cast<const float4 *>(p.bS + g));
-        const float4 cBo = __ldg(reinterpret_cast<const float4 *>(p.boost + g));
-        const float kat[4] = {cAT.x, cAT.y, cAT.z, cAT.w}, kbt[4] = {cBT.x, cBT.y, cBT.z, cBT.w};
-        const float kas[4] = {cAS.x, cAS.y, cAS.z, cAS.w}, kbs[4] = {cBS.x, cBS.y, cBS.z, cBS.w};
-        const float kbo[4] = {cBo.x, cBo.y, cBo.z, cBo.w};
-        float out[4];
+      for (int q4 = 0; q4 < 8; q4++) {
+        float simv[4], boostv[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-          const int col = 31 - (4 * q4 + e);
-          const float temporal = useT ? (accT[col] - kbt[e]) * kat[e] : 0.f;
-          const float spectral = useS ? (accS[col] - kbs[e]) * kas[e] : 0.f;
+          const int j = 4 * q4 + e, col = 31 - j;
+          const double mT = win.t1 * invW;
+          const float avgB = (float)mT;                                          // MathUtil.avg -> Float
+          const float boost = exp2f((l2In - __log2f(avgB)) * (1.0f / 0.6f));     // calcBoost
+          float temporal = 0.f, spectral = 0.f;
+          if (useT) {
+            const double q = win.t2 * invW;
+            const double var = q - mT * mT;
+            const float cr = accT[col] - (float)mT * rhoT;
+            temporal = (var > 1e-13 * q) ? (cr * cT) * rsqrtf((float)var) : qnan;
+          }
+          if (useS) {
+            const double mS = win.s1 * invNS;
+            const double q = win.s2 * invNS;
+            const double var = q - mS * mS;
+            const float cr = accS[col] - (float)mS * rhoS;
+            spectral = (var > 1e-13 * q) ? (cr * cS) * rsqrtf((float)var) : qnan;
+          }
           const float blend = __fadd_rn(__fmul_rn(temporal, p.weight), __fmul_rn(spectral, __fsub_rn(1.0f, p.weight)));
-          const bool invalid = (kbt[e] != kbt[e]) && (kbs[e] != kbs[e]);
-          out[e] = invalid ? qnan : (kbo[e] <= p.maxBoost ? blend : 0.f);
+          float sv = boost <= p.maxBoost ? blend : 0.f, bv = boost;
+          // which offsets exist (window inside its file), per-file maximum (first occurrence)
+          const int64_t g = g0 + j;
+          while (g >= fEnd && f + 1 < p.numFiles) {
+            if (best != 0ull && p.fileMax) atomicMax(p.fileMax + f, best);
+            best = 0ull;
+            f++;
+            fStart = fEnd;
+            fEnd = p.fileStart[f + 1];
+          }
+          const int64_t tl = g - fStart;
+          if (!(g < p.usedFrames && tl < (fEnd - fStart) - p.tailExtra - W + 1)) { sv = qnan; bv = qnan; }
+          else if (sv == sv) {
+            const unsigned long long key = ((unsigned long long)float_order_key(sv) << 32) |
+                                           (unsigned long long)(0xffffffffu - (uint32_t)tl);
+            if (key > best) best = key;
+          }
+          simv[e] = sv; boostv[e] = bv;
+          if (j < 31) {   // slide the window by one frame
+            const double bo = (double)T0r[j], bn = (double)T0r[j + W];
+            const float2 fo = Fr[j], fn = Fr[j + W];
+            win.t1 += bn - bo;
+            win.t2 += bn * bn - bo * bo;
+            win.s1 += (double)fn.x - (double)fo.x;
+            win.s2 += (double)fn.y - (double)fo.y;
+          }
         }
-        *reinterpret_cast<float4 *>(p.sim + g) = make_float4(out[0], out[1], out[2], out[3]);
+        *reinterpret_cast<float4 *>(p.sim + g0 + 4 * q4) = make_float4(simv[0], simv[1], simv[2], simv[3]);
+        *reinterpret_cast<float4 *>(p.boost + g0 + 4 * q4) = make_float4(boostv[0], boostv[1], boostv[2], boostv[3]);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(statsFree);   // T0 / F / RS may be rebuilt
+      if (best != 0ull && p.fileMax) atomicMax(p.fileMax + f, best);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
