@@ -533,7 +533,21 @@ int sgz_corr_scan(sgz_corr *job) {
   if (job->abortFlag) return SGZ_ERR_ABORTED;
   size_t n = (size_t)job->numTiles * kR * job->ntg;
   const bool tc = job->useTc && db->chunks.empty();   // a streaming scan hides K1 behind PCIe anyway: FFMA path
-  if (tc) n = std::max(n, (size_t)job->numTilesTc * kTcTile);
+  if (tc) {
+    n = std::max(n, (size_t)job->numTilesTc * kTcTile);
+    if (!job->dTileFile.p) {
+      std::vector<int32_t> tf((size_t)job->numTilesTc + 1);
+      int f = 0;
+      const int nf = db->numFiles();
+      for (int64_t t = 0; t <= job->numTilesTc; t++) {
+        const int64_t g = std::min<int64_t>(t * kTcTile, std::max<int64_t>(db->usedFrames - 1, 0));
+        while (f + 1 < nf && db->fileStart[f + 1] <= g) f++;
+        tf[(size_t)t] = f;
+      }
+      SGZ_TRY(job->dTileFile.alloc(tf.size()));
+      SGZ_CUDA(cudaMemcpy(job->dTileFile.p, tf.data(), tf.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+  }
   SGZ_TRY(job->simIn.alloc(n));
   SGZ_TRY(job->boostIn.alloc(n));
   SGZ_TRY(job->dFileMax.alloc((size_t)std::max(db->numFiles(), 1)));

@@ -29,6 +29,7 @@ struct sgz_corr {
   int nslot = 3;
   bool useTc = false;       // K1 on the tensor cores (corr_tc.cuh) for resident scans
   int64_t numTilesTc = 0;
+  DevBuf<int32_t> dTileFile;   // [numTilesTc + 1] file holding the first frame of each tensor-core tile
   int64_t numTiles = 0;
   int64_t numOffsets = 0;
   DevBuf<float> simIn, boostIn, simOut, boostOut, rowMaxOut;
@@ -225,7 +226,7 @@ inline int run_scan_tc(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim, 
   tp.taps = q.dTcTaps.p;
   tp.stdT = q.stdT; tp.stdS = q.stdS; tp.rhoT = q.rhoT; tp.rhoS = q.rhoS; tp.lnAvgIn = q.lnAvg;
   tp.weight = q.weight; tp.maxBoost = job->cfg.maxBoost;
-  tp.fileStart = db->dFileStart.p; tp.numFiles = db->numFiles(); tp.tailExtra = tailExtra;
+  tp.fileStart = db->dFileStart.p; tp.tileFile = job->dTileFile.p; tp.numFiles = db->numFiles(); tp.tailExtra = tailExtra;
   tp.tileBegin = 0; tp.tileEnd = job->numTilesTc;
   tp.sim = sim; tp.boost = boost; tp.fileMax = fileMax;
   SGZ_CUDA(cudaFuncSetAttribute(k_corr_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));
@@ -233,21 +234,23 @@ inline int run_scan_tc(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim, 
   DevBuf<long long> dProf;
   const bool prof = getenv("SGZ_CORR_TC_PROF") != nullptr;   // developer probe: where does the issuer lane wait?
   if (prof) {
-    SGZ_TRY(dProf.alloc((size_t)gridTc * 8));
-    SGZ_CUDA(cudaMemsetAsync(dProf.p, 0, (size_t)gridTc * 8 * sizeof(long long), st));
+    SGZ_TRY(dProf.alloc((size_t)gridTc * 16));
+    SGZ_CUDA(cudaMemsetAsync(dProf.p, 0, (size_t)gridTc * 16 * sizeof(long long), st));
     tp.prof = dProf.p;
   }
   k_corr_tc<<<gridTc, kTcThreads, G.smemBytes, st>>>(tp);
   SGZ_LAUNCH_CHECK(ctx);
   if (prof) {
-    std::vector<long long> h((size_t)gridTc * 8);
+    std::vector<long long> h((size_t)gridTc * 16);
     SGZ_CUDA(cudaMemcpyAsync(h.data(), dProf.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
     SGZ_CUDA(cudaStreamSynchronize(st));
-    double a[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (unsigned b = 0; b < gridTc; b++) for (int k = 0; k < 7; k++) a[k] += (double)h[(size_t)b * 8 + k];
+    double a[16] = {0};
+    for (unsigned b = 0; b < gridTc; b++) for (int k = 0; k < 16; k++) a[k] += (double)h[(size_t)b * 16 + k];
     const double tiles = a[6] > 0 ? a[6] : 1;
-    fprintf(stderr, "k_corr_tc issuer cycles per tile: total %.0f | wait opFree %.0f, accEmpty %.0f, opFull %.0f, taps %.0f, "
-                    "issue %.0f\n", a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles, a[4] / tiles, a[5] / tiles);
+    fprintf(stderr, "k_corr_tc cycles per tile: issuer total %.0f | wait opFree %.0f, accEmpty %.0f, opFull %.0f, taps %.0f, "
+                    "issue %.0f || epilogue wait accFull %.0f, tmem read %.0f, wait stats %.0f, row sums %.0f, init %.0f, loop %.0f\n",
+            a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles, a[4] / tiles, a[5] / tiles, a[8] / tiles, a[9] / tiles,
+            a[10] / tiles, a[12] / tiles, a[13] / tiles, a[11] / tiles);
   }
   return SGZ_OK;
 }

@@ -47,8 +47,8 @@ __host__ __device__ inline TcGeom tc_geom(int W) {
   g.chanBytes = (uint32_t)((g.rows * 64 + 1023) / 1024 * 1024);
   g.tapsChanBytes = (uint32_t)(g.natom * 256 * 2);
   g.tapsPairBytes = (uint32_t)((2 * g.tapsChanBytes + 1023) / 1024 * 1024);
-  g.t0Bytes = (uint32_t)((g.rows * 32 * 4 + 127) / 128 * 128);
-  g.fBytes = (uint32_t)(g.rows * 32 * 8);
+  g.t0Bytes = (uint32_t)((g.rows * 33 * 4 + 127) / 128 * 128);   // skewed: frame e at index e + e / 32
+  g.fBytes = (uint32_t)((g.rows * 33 * 8 + 127) / 128 * 128);
   g.rsBytes = (uint32_t)(g.rows * 32);
   g.smemBytes = (size_t)8 * g.chanBytes + (size_t)2 * g.tapsPairBytes + g.t0Bytes + g.fBytes + g.rsBytes +
                 1024 /*alignment slack*/ + 256 /*barriers*/;
@@ -95,11 +95,12 @@ struct CorrTcParams {
   double stdT, stdS, rhoT, rhoS, lnAvgIn;
   float weight, maxBoost;
   const int64_t *fileStart;
+  const int32_t *tileFile;      // [numTiles + 1] file that holds frame 4096 * tile (clamped to the last file)
   int numFiles, tailExtra;
   int64_t tileBegin, tileEnd;   // tiles of 4096 offsets
   float *sim, *boost;
   unsigned long long *fileMax;  // [numFiles] packed (order_key(sim) << 32 | ~offset), or nullptr
-  long long *prof;              // developer probe (SGZ_CORR_TC_PROF): per CTA 8 cycle counters, or nullptr
+  long long *prof;              // developer probe (SGZ_CORR_TC_PROF): per CTA 16 cycle counters, or nullptr
 };
 
 __device__ __forceinline__ uint64_t tc_desc(uint32_t addr, uint32_t sbo, uint32_t layout) {
@@ -117,17 +118,14 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // bounded wait: a protocol error must end in a trap (visible CUDA error), not in a hung GPU box
 template <bool kSleep = true>
 __device__ __forceinline__ void tc_wait(uint64_t *bar, uint32_t parity) {
@@ -141,6 +139,11 @@ __device__ __forceinline__ void tc_wait(uint64_t *bar, uint32_t parity) {
     if (kSleep && !done) __nanosleep(100);
   }
   if (!done) __trap();
+}
+__device__ __forceinline__ bool tc_elect() {   // one lane of a converged warp
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
 
@@ -163,7 +166,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
   uint64_t *opFree = bars, *opFull = bars + 2, *tapsFull = bars + 4, *accFull = bars + 6, *accEmpty = bars + 7;
   uint64_t *statsFull = bars + 8, *statsFree = bars + 9;
   uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(bars + 10);
-  int *fileLoHi = reinterpret_cast<int *>(bars + 11);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
@@ -243,9 +245,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
 #pragma unroll
       for (int k = 0; k < kPer; k++) {
         const int L = 2 * (tid + k * kTcSplit);
-        if (L < nFrames) {
-          *reinterpret_cast<float2 *>(T0 + L) = make_float2(b0[2 * k], b0[2 * k + 1]);
-          *reinterpret_cast<float4 *>(F + L) = make_float4(s1[2 * k], s2[2 * k], s1[2 * k + 1], s2[2 * k + 1]);
+        if (L < nFrames) {   // skewed by one element per 32-frame row: the epilogue lanes walk rows, not frames
+          const int i = L + (L >> 5);
+          T0[i] = b0[2 * k]; T0[i + 1] = b0[2 * k + 1];
+          F[i] = make_float2(s1[2 * k], s2[2 * k]); F[i + 1] = make_float2(s1[2 * k + 1], s2[2 * k + 1]);
         }
       }
       __syncwarp();
@@ -253,57 +256,67 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
     }
   } else if (warp == kTcSplit / 32) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      // D = F32, A = B = F16 (format 0), both K-major, N = 32, M = 128
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(kTcP >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
-      uint32_t pc = 0, tileIt = 0;
-      long long cFree = 0, cAcc = 0, cFull = 0, cTaps = 0, cIssue = 0, cTotal = clock64(), tA;
-      for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, tileIt++) {
-        bool corrStartedT = false, corrStartedS = false;
-        for (int pr = 0; pr < p.numPairs; pr++, pc++) {
-          const int buf = pc & 1;
-          const uint32_t use = pc >> 1;
-          tA = clock64();
-          if (use > 0) tc_wait<false>(opFree + buf, (use - 1) & 1);
-          cFree += clock64() - tA;
+    // The whole warp runs the (uniform) control flow and one elected lane issues: descriptors and loop counters then
+    // live in uniform registers and each tcgen05.mma costs a handful of instructions.
+    // D = F32, A = B = F16 (format 0), both K-major, N = 32, M = 128
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(kTcP >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+    uint32_t pc = 0, tileIt = 0;
+    long long cFree = 0, cAcc = 0, cFull = 0, cTaps = 0, cIssue = 0, cTotal = clock64(), tA;
+    for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, tileIt++) {
+      bool corrStartedT = false, corrStartedS = false;
+      for (int pr = 0; pr < p.numPairs; pr++, pc++) {
+        const int buf = pc & 1;
+        const uint32_t use = pc >> 1;
+        tA = clock64();
+        if (use > 0) tc_wait<false>(opFree + buf, (use - 1) & 1);
+        cFree += clock64() - tA;
+        if (tc_elect()) {
           mbar_expect_tx(tapsFull + buf, G.tapsPairBytes);
           bulk_g2s(tapsBuf(buf), reinterpret_cast<const unsigned char *>(p.taps) + (size_t)pr * G.tapsPairBytes,
                    G.tapsPairBytes, tapsFull + buf);
-          tA = clock64();
-          if (pr == 0 && tileIt > 0) tc_wait<false>(accEmpty, (tileIt - 1) & 1);   // epilogue has drained the accumulators
-          cAcc += clock64() - tA;
-          tA = clock64();
-          tc_wait<false>(opFull + buf, use & 1);
-          cFull += clock64() - tA;
-          tA = clock64();
-          tc_wait<false>(tapsFull + buf, use & 1);
-          cTaps += clock64() - tA;
-          tA = clock64();
-          asm volatile("tcgen05.fence::after_thread_sync;");
-          for (int h = 0; h < 2; h++) {
-            const int c = 2 * pr + h;
-            if (c >= p.numCh) break;
-            const uint32_t dMain = tmem + 32u * (c == 0 ? 0u : (uint32_t)(2 + c));
-            const uint32_t dCorr = tmem + 32u * (c == 0 ? 1u : 2u);
-            const uint32_t tHiA = smem_u32(tapsBuf(buf)) + (uint32_t)h * G.tapsChanBytes;
-            const uint64_t aHi = tc_desc(smem_u32(ops(buf, h, 0)), 512, 4), aLo = tc_desc(smem_u32(ops(buf, h, 1)), 512, 4);
-            const uint64_t tHi = tc_desc(tHiA, 256, 6), tLo = tc_desc(tHiA + (uint32_t)G.natom * 256u, 256, 6);
-            bool &started = c == 0 ? corrStartedT : corrStartedS;
+        }
+        tA = clock64();
+        if (pr == 0 && tileIt > 0) tc_wait<false>(accEmpty, (tileIt - 1) & 1);   // epilogue has drained the accumulators
+        cAcc += clock64() - tA;
+        tA = clock64();
+        tc_wait<false>(opFull + buf, use & 1);
+        cFull += clock64() - tA;
+        tA = clock64();
+        tc_wait<false>(tapsFull + buf, use & 1);
+        cTaps += clock64() - tA;
+        tA = clock64();
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        for (int h = 0; h < 2; h++) {
+          const int c = 2 * pr + h;
+          if (c >= p.numCh) break;
+          const uint32_t dMain = tmem + 32u * (c == 0 ? 0u : (uint32_t)(2 + c));
+          const uint32_t dCorr = tmem + 32u * (c == 0 ? 1u : 2u);
+          const uint32_t tHiA = smem_u32(tapsBuf(buf)) + (uint32_t)h * G.tapsChanBytes;
+          const uint64_t aHi = tc_desc(smem_u32(ops(buf, h, 0)), 512, 4), aLo = tc_desc(smem_u32(ops(buf, h, 1)), 512, 4);
+          const uint64_t tHi = tc_desc(tHiA, 256, 6), tLo = tc_desc(tHiA + (uint32_t)G.natom * 256u, 256, 6);
+          const bool started = c == 0 ? corrStartedT : corrStartedS;
+          if (c == 0) corrStartedT = true; else corrStartedS = true;
+          if (tc_elect()) {
             // one K step of 16: A start +32 B (2 descriptor units), taps start +2 atoms = 512 B (32 units)
-            for (int s = 0; s < G.KS; s++) tc_mma(dMain, aHi + 2u * s, tHi + 32u * s, idesc, s > 0);
-            for (int s = 0; s < G.KS; s++) tc_mma(dCorr, aLo + 2u * s, tHi + 32u * s, idesc, started || s > 0);
-            started = true;
-            for (int s = 0; s < G.KS; s++) tc_mma(dCorr, aHi + 2u * s, tLo + 32u * s, idesc, 1);
+            uint64_t da = aHi, db = tHi;
+            for (int s = 0; s < G.KS; s++, da += 2, db += 32) tc_mma(dMain, da, db, idesc, s > 0);
+            da = aLo; db = tHi;
+            for (int s = 0; s < G.KS; s++, da += 2, db += 32) tc_mma(dCorr, da, db, idesc, started || s > 0);
+            da = aHi; db = tLo;
+            for (int s = 0; s < G.KS; s++, da += 2, db += 32) tc_mma(dCorr, da, db, idesc, 1);
           }
+        }
+        if (tc_elect()) {
           tc_commit(opFree + buf);
           if (pr == p.numPairs - 1) tc_commit(accFull);
-          cIssue += clock64() - tA;
         }
+        __syncwarp();
+        cIssue += clock64() - tA;
       }
-      if (p.prof) {
-        long long *o = p.prof + 8 * blockIdx.x;
-        o[0] = clock64() - cTotal; o[1] = cFree; o[2] = cAcc; o[3] = cFull; o[4] = cTaps; o[5] = cIssue; o[6] = tileIt;
-      }
+    }
+    if (p.prof && lane == 0) {
+      long long *o = p.prof + 16 * blockIdx.x;
+      o[0] = clock64() - cTotal; o[1] = cFree; o[2] = cAcc; o[3] = cFull; o[4] = cTaps; o[5] = cIssue; o[6] = tileIt;
     }
   } else {
     // =========================== epilogue ===========================
@@ -316,50 +329,62 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
     const float cT = (float)(invW / p.stdT), cS = (float)(invNS / p.stdS);
     const float rhoT = (float)p.rhoT, rhoS = (float)p.rhoS, l2In = (float)(p.lnAvgIn * 1.4426950408889634);
     uint32_t tileIt = 0;
+    long long eAcc = 0, eLd = 0, eSt = 0, eMain = 0, eRow = 0, eInit = 0;
     for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, tileIt++) {
       const int64_t t0 = tile * kTcTile;
-      if (et < 2) {   // file range of the tile
-        const int64_t gq = et == 0 ? t0 : min(t0 + kTcTile - 1, p.usedFrames - 1);
-        int lo = 0, hi = p.numFiles;
+      // file of this thread's first offset: the tile spans files [tileFile[tile], tileFile[tile + 1]] (host table)
+      const int r = quarter * 32 + lane;
+      const int64_t g0 = t0 + 32 * (int64_t)r;
+      int f;
+      {
+        int lo = p.tileFile[tile], hi = p.tileFile[tile + 1] + 1;
         while (hi - lo > 1) {
           const int mid = (lo + hi) >> 1;
-          if (p.fileStart[mid] <= gq) lo = mid; else hi = mid;
+          if (p.fileStart[mid] <= g0) lo = mid; else hi = mid;
         }
-        fileLoHi[et] = lo;
+        f = lo;
       }
+      int64_t fStart = p.fileStart[f], fEnd = p.fileStart[f + 1];
+      long long tE = clock64();
       tc_wait(accFull, tileIt & 1);
+      eAcc += clock64() - tE; tE = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;");
-      const int r = quarter * 32 + lane;
       const uint32_t laneAddr = tmem + ((uint32_t)(quarter * 32) << 16);
       float accT[32], accS[32];
 #pragma unroll
       for (int half = 0; half < 2; half++) {
-        float v[16];
-        tc_ld16(laneAddr + 0 * 32 + 16 * half, v);
+        uint32_t u[16], w[16];
+        tc_ld16_nowait(laneAddr + 0 * 32 + 16 * half, u);
+        tc_ld16_nowait(laneAddr + 1 * 32 + 16 * half, w);
+        tc_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; i++) accT[16 * half + i] = v[i];
-        tc_ld16(laneAddr + 1 * 32 + 16 * half, v);
+        for (int i = 0; i < 16; i++) accT[16 * half + i] = __uint_as_float(u[i]) + __uint_as_float(w[i]);
+        tc_ld16_nowait(laneAddr + 2 * 32 + 16 * half, u);
+        tc_ld16_nowait(laneAddr + 3 * 32 + 16 * half, w);
+        tc_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; i++) accT[16 * half + i] += v[i];
-        tc_ld16(laneAddr + 2 * 32 + 16 * half, v);
+        for (int i = 0; i < 16; i++) accS[16 * half + i] = __uint_as_float(u[i]) + __uint_as_float(w[i]);
+        for (int c = 2; c < p.numCh; c += 2) {     // two accumulators per wait; an odd tail reads one
+          tc_ld16_nowait(laneAddr + (uint32_t)(2 + c) * 32 + 16 * half, u);
+          if (c + 1 < p.numCh) tc_ld16_nowait(laneAddr + (uint32_t)(3 + c) * 32 + 16 * half, w);
+          tc_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; i++) accS[16 * half + i] = v[i];
-        for (int c = 1; c < p.numCh; c++) {
-          tc_ld16(laneAddr + (uint32_t)(2 + c) * 32 + 16 * half, v);
-#pragma unroll
-          for (int i = 0; i < 16; i++) accS[16 * half + i] += v[i];
+          for (int i = 0; i < 16; i++)
+            accS[16 * half + i] += __uint_as_float(u[i]) + (c + 1 < p.numCh ? __uint_as_float(w[i]) : 0.f);
         }
       }
       // the accumulators are in registers: hand TMEM back to the issuer
       asm volatile("tcgen05.fence::before_thread_sync;");
       __syncwarp();
       if (lane == 0) mbar_arrive(accEmpty);
+      eLd += clock64() - tE; tE = clock64();
 
       // ---- window statistics: FP64 sums of whole 32-frame rows, then slide frame by frame inside the row ----
       tc_wait(statsFull, tileIt & 1);
+      eSt += clock64() - tE; tE = clock64();
       for (int rr = r; rr < G.rows; rr += 128) {
         double a1 = 0, a2 = 0, a3 = 0, a4 = 0;
-        const int e0 = 32 * rr;
+        const int e0 = 33 * rr;
 #pragma unroll 8
         for (int k = 0; k < 32; k++) {
           const double x = (double)T0[e0 + k];
@@ -370,37 +395,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
         o[0] = a1; o[1] = a2; o[2] = a3; o[3] = a4;
       }
       tc_epi_sync();
+      eRow += clock64() - tE; tE = clock64();
       D4 win = {0, 0, 0, 0};
       for (int i = 0; i < nr; i++) {
         const double *o = RS + 4 * (r + i);
         win.t1 += o[0]; win.t2 += o[1]; win.s1 += o[2]; win.s2 += o[3];
       }
       for (int k = 0; k < rem; k++) {
-        const int e = 32 * (r + nr) + k;
+        const int e = 33 * (r + nr) + k;
         const double x = (double)T0[e];
         const float2 f = F[e];
         win.t1 += x; win.t2 += x * x; win.s1 += (double)f.x; win.s2 += (double)f.y;
       }
-      const int64_t g0 = t0 + 32 * (int64_t)r;
-      int f = fileLoHi[0];
-      {
-        int lo = fileLoHi[0], hi = fileLoHi[1] + 1;
-        while (hi - lo > 1) {
-          const int mid = (lo + hi) >> 1;
-          if (p.fileStart[mid] <= g0) lo = mid; else hi = mid;
-        }
-        f = lo;
-      }
-      int64_t fStart = p.fileStart[f], fEnd = p.fileStart[f + 1];
+      eInit += clock64() - tE; tE = clock64();
       unsigned long long best = 0ull;
-      const float *T0r = T0 + 32 * r;
-      const float2 *Fr = F + 32 * r;
+      const float *T0r = T0 + 33 * r;      // row base in the skewed arrays: frame 32 r + x sits at x + x / 32
+      const float2 *Fr = F + 33 * r;
+      // common case: all 32 offsets of the row are evaluated offsets of ONE file -> no control flow per offset
+      const bool plain = g0 + 32 <= fStart + ((fEnd - fStart) - p.tailExtra - W + 1) && g0 + 32 <= p.usedFrames;
+      const uint32_t tl0 = (uint32_t)(g0 - fStart);
 #pragma unroll
-      for (int q4 = 0; q4 < 8; q4++) {
-        float simv[4], boostv[4];
+      for (int blk = 0; blk < 4; blk++) {
+        // pass A: straight-line arithmetic for 8 offsets, so that the 8 dependency chains overlap (one warp per
+        // scheduler here: no other warp hides the FP64 / MUFU latencies)
+        float simv[8], boostv[8];
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const int j = 4 * q4 + e, col = 31 - j;
+        for (int e = 0; e < 8; e++) {
+          const int j = 8 * blk + e, col = 31 - j;
           const double mT = win.t1 * invW;
           const float avgB = (float)mT;                                          // MathUtil.avg -> Float
           const float boost = exp2f((l2In - __log2f(avgB)) * (1.0f / 0.6f));     // calcBoost
@@ -419,39 +440,68 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
             spectral = (var > 1e-13 * q) ? (cr * cS) * rsqrtf((float)var) : qnan;
           }
           const float blend = __fadd_rn(__fmul_rn(temporal, p.weight), __fmul_rn(spectral, __fsub_rn(1.0f, p.weight)));
-          float sv = boost <= p.maxBoost ? blend : 0.f, bv = boost;
-          // which offsets exist (window inside its file), per-file maximum (first occurrence)
-          const int64_t g = g0 + j;
-          while (g >= fEnd && f + 1 < p.numFiles) {
-            if (best != 0ull && p.fileMax) atomicMax(p.fileMax + f, best);
-            best = 0ull;
-            f++;
-            fStart = fEnd;
-            fEnd = p.fileStart[f + 1];
-          }
-          const int64_t tl = g - fStart;
-          if (!(g < p.usedFrames && tl < (fEnd - fStart) - p.tailExtra - W + 1)) { sv = qnan; bv = qnan; }
-          else if (sv == sv) {
-            const unsigned long long key = ((unsigned long long)float_order_key(sv) << 32) |
-                                           (unsigned long long)(0xffffffffu - (uint32_t)tl);
-            if (key > best) best = key;
-          }
-          simv[e] = sv; boostv[e] = bv;
-          if (j < 31) {   // slide the window by one frame
-            const double bo = (double)T0r[j], bn = (double)T0r[j + W];
-            const float2 fo = Fr[j], fn = Fr[j + W];
-            win.t1 += bn - bo;
-            win.t2 += bn * bn - bo * bo;
-            win.s1 += (double)fn.x - (double)fo.x;
-            win.s2 += (double)fn.y - (double)fo.y;
+          simv[e] = boost <= p.maxBoost ? blend : 0.f;
+          boostv[e] = boost;
+          if (j < 31) {
+            // slide the window by one frame: the deltas in FP32 (their rounding, 6e-8 of one frame's value, is far
+            // below the window sums' own FP32 inputs), the running sums in FP64
+            const int jn = j + W + ((j + W) >> 5);
+            const float bo = T0r[j], bn = T0r[jn];
+            const float2 fo = Fr[j], fn = Fr[jn];
+            win.t1 += (double)(bn - bo);
+            win.t2 += (double)fmaf(bn, bn, -bo * bo);
+            win.s1 += (double)(fn.x - fo.x);
+            win.s2 += (double)(fn.y - fo.y);
           }
         }
-        *reinterpret_cast<float4 *>(p.sim + g0 + 4 * q4) = make_float4(simv[0], simv[1], simv[2], simv[3]);
-        *reinterpret_cast<float4 *>(p.boost + g0 + 4 * q4) = make_float4(boostv[0], boostv[1], boostv[2], boostv[3]);
+        // pass B: which offsets exist (window inside its file), per-file maximum (first occurrence)
+        if (plain) {
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            if (simv[e] == simv[e]) {
+              const unsigned long long key = ((unsigned long long)float_order_key(simv[e]) << 32) |
+                                             (unsigned long long)(0xffffffffu - (tl0 + (uint32_t)(8 * blk + e)));
+              if (key > best) best = key;
+            }
+          }
+        } else {
+          for (int e = 0; e < 8; e++) {
+            const int64_t g = g0 + 8 * blk + e;
+            while (g >= fEnd && f + 1 < p.numFiles) {
+              if (best != 0ull && p.fileMax) atomicMax(p.fileMax + f, best);
+              best = 0ull;
+              f++;
+              fStart = fEnd;
+              fEnd = p.fileStart[f + 1];
+            }
+            const int64_t tl = g - fStart;
+            float sv = qnan, bv = qnan;
+#pragma unroll
+            for (int kk = 0; kk < 8; kk++) if (kk == e) { sv = simv[kk]; bv = boostv[kk]; }
+            if (!(g < p.usedFrames && tl < (fEnd - fStart) - p.tailExtra - W + 1)) { sv = qnan; bv = qnan; }
+            else if (sv == sv) {
+              const unsigned long long key = ((unsigned long long)float_order_key(sv) << 32) |
+                                             (unsigned long long)(0xffffffffu - (uint32_t)tl);
+              if (key > best) best = key;
+            }
+#pragma unroll
+            for (int kk = 0; kk < 8; kk++) if (kk == e) { simv[kk] = sv; boostv[kk] = bv; }
+          }
+        }
+        float4 *so = reinterpret_cast<float4 *>(p.sim + g0 + 8 * blk), *bo = reinterpret_cast<float4 *>(p.boost + g0 + 8 * blk);
+        so[0] = make_float4(simv[0], simv[1], simv[2], simv[3]);
+        so[1] = make_float4(simv[4], simv[5], simv[6], simv[7]);
+        bo[0] = make_float4(boostv[0], boostv[1], boostv[2], boostv[3]);
+        bo[1] = make_float4(boostv[4], boostv[5], boostv[6], boostv[7]);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(statsFree);   // T0 / F / RS may be rebuilt
       if (best != 0ull && p.fileMax) atomicMax(p.fileMax + f, best);
+      eMain += clock64() - tE;
+    }
+    if (p.prof && et == 0) {
+      long long *o = p.prof + 16 * blockIdx.x + 8;
+      o[0] = eAcc; o[1] = eLd; o[2] = eSt; o[3] = eMain; o[4] = eRow; o[5] = eInit;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
