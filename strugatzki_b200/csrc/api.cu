@@ -501,9 +501,10 @@ int sgz_corr_create(sgz_db *db, const sgz_corr_config *cfg, const void *input, i
   job->numTiles = ceil_div<int64_t>(std::max<int64_t>(db->usedFrames, 1), (int64_t)kR * job->ntg);
   job->numTilesTc = ceil_div<int64_t>(std::max<int64_t>(db->usedFrames, 1), (int64_t)kTcTile);
   {
-    // K1 on the tensor cores: opt-in while it is being qualified (SGZ_CORR_TC=1)
+    // K1 on the tensor cores (corr_tc.cuh) wherever it applies (<= 14 channels, window <= 256 frames); the FFMA2
+    // kernel covers the rest and streaming scans.  SGZ_CORR_TC=0 forces the FFMA2 kernel.
     const char *e = getenv("SGZ_CORR_TC");
-    job->useTc = e && atoi(e) == 1 && job->qin.dTcTaps.p && (!job->hasOut || job->qout.dTcTaps.p);
+    job->useTc = !(e && atoi(e) == 0) && job->qin.dTcTaps.p && (!job->hasOut || job->qout.dTcTaps.p);
   }
   job->numOffsets = valid_offsets(db, job->qin.W, job->hasOut ? job->minPunchF : 0);
   db->refs++;

@@ -71,7 +71,7 @@ namespace sgz {
 
 // the tensor-core K1 handles up to 14 channels (16 TMEM accumulators) and windows whose operands fit shared memory
 inline bool tc_applicable(const sgz_ctx *ctx, int numCh, int W) {
-  return numCh >= 2 && numCh <= 14 && W >= 1 && W <= 512 && tc_geom(W).smemBytes <= ctx->smemOptin;
+  return numCh >= 2 && numCh <= 14 && W >= 1 && W <= 256 && tc_geom(W).smemBytes <= ctx->smemOptin;
 }
 
 // readInBuffer (FeatureCorrelationImpl.scala:83-98): cut [start,stop) feature frames, normalise,

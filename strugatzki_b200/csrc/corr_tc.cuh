@@ -28,6 +28,9 @@
 namespace sgz {
 
 constexpr int kTcP = 32, kTcM = 128, kTcTile = kTcP * kTcM;
+// the second FP16 parts (residuals, 2^-11 of the value) are stored times 2^11 so that they stay FP16 normals; their
+// products go to separate accumulators which the epilogue scales back
+constexpr float kTcLoScale = 2048.f;
 
 struct TcGeom {
   int W, KS, natom, rows;
@@ -49,7 +52,7 @@ __host__ __device__ inline TcGeom tc_geom(int W) {
   g.tapsPairBytes = (uint32_t)((2 * g.tapsChanBytes + 1023) / 1024 * 1024);
   g.t0Bytes = (uint32_t)((g.rows * 33 * 4 + 127) / 128 * 128);   // skewed: frame e at index e + e / 32
   g.fBytes = (uint32_t)((g.rows * 33 * 8 + 127) / 128 * 128);
-  g.rsBytes = (uint32_t)(g.rows * 32);
+  g.rsBytes = (uint32_t)(g.rows * 32 + g.rows * 4 * 32);   // FP64 sums of whole rows + of 8-frame quarters
   g.smemBytes = (size_t)8 * g.chanBytes + (size_t)2 * g.tapsPairBytes + g.t0Bytes + g.fBytes + g.rsBytes +
                 1024 /*alignment slack*/ + 256 /*barriers*/;
   return g;
@@ -73,7 +76,7 @@ inline void tc_build_taps(const std::vector<float> &pairTaps /*[numPairs][Wq] fl
               if (q >= 0 && q < W) {
                 const float tp = pairTaps[((size_t)p * Wq + q) * 2 + h];
                 const __half t1 = __float2half_rn(tp);
-                v = part == 0 ? t1 : __float2half_rn(tp - __half2float(t1));
+                v = part == 0 ? t1 : __float2half_rn((tp - __half2float(t1)) * kTcLoScale);
               }
               const size_t byteOff = (size_t)p * g.tapsPairBytes + (size_t)h * g.tapsChanBytes +
                                      (size_t)part * g.natom * 256 + (size_t)a * 256 + (size_t)cc * 32 +
@@ -145,11 +148,12 @@ __device__ __forceinline__ bool tc_elect() {   // one lane of a converged warp
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
   return pred != 0;
 }
-__device__ __forceinline__ void tc_epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+__device__ __forceinline__ void tc_epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
 
-// warps 0..7: split workers (global pair row -> swizzled FP16 operand buffers + per-frame sums), warp 8: MMA issuer
-// (one lane), warps 9..12: epilogue (TMEM lane quarter = warp % 4; window statistics, sim, file maxima)
-constexpr int kTcSplit = 256, kTcThreads = kTcSplit + 32 + 128;
+// warps 0..6: split workers (global pair row -> swizzled FP16 operand buffers + per-frame sums), warp 7: MMA issuer
+// (one elected lane), warps 8..15: epilogue (TMEM lane quarter = warp % 4; window statistics, sim, file maxima)
+// 7 + 1 + 8 = 16 warps: the register file is handed out to groups of 4 warps, 17 warps would cost 128 -> 96 registers
+constexpr int kTcSplit = 224, kTcEpi = 256, kTcThreads = kTcSplit + 32 + kTcEpi;
 
 __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p) {
   extern __shared__ __align__(1024) unsigned char smemRaw[];
@@ -162,6 +166,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
   float *T0 = reinterpret_cast<float *>(tapsBase + (size_t)2 * G.tapsPairBytes);           // loudness per frame
   float2 *F = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(T0) + G.t0Bytes);   // (sum_c b, sum_c b^2)
   double *RS = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(F) + G.fBytes);    // [rows][4] row sums
+  double *RQ = RS + 4 * G.rows;                                                                // [rows][4 quarters][4]
   uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(RS) + G.rsBytes);
   uint64_t *opFree = bars, *opFull = bars + 2, *tapsFull = bars + 4, *accFull = bars + 6, *accEmpty = bars + 7;
   uint64_t *statsFull = bars + 8, *statsFree = bars + 9;
@@ -173,9 +178,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
     mbar_init(opFull, kTcSplit / 32); mbar_init(opFull + 1, kTcSplit / 32);
     mbar_init(tapsFull, 1); mbar_init(tapsFull + 1, 1);
     mbar_init(accFull, 1);
-    mbar_init(accEmpty, 4);
+    mbar_init(accEmpty, kTcEpi / 32);
     mbar_init(statsFull, kTcSplit / 32);
-    mbar_init(statsFree, 4);
+    mbar_init(statsFree, kTcEpi / 32);
     fence_mbar_init();
   }
   __syncthreads();
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
 
   if (warp < kTcSplit / 32) {
     // =========================== split workers ===========================
-    constexpr int kPer = 10;                            // >= ceil(nFrames / 512) for W <= 512; two frames per step
+    constexpr int kPer = 10;                            // >= ceil(nFrames / 448) for W <= 256; two frames per step
     uint32_t pc = 0, tileIt = 0;
     for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, tileIt++) {
       const int64_t t0 = tile * kTcTile;
@@ -200,40 +205,45 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
         const int buf = pc & 1;
         const uint32_t use = pc >> 1;
         const float4 *row = reinterpret_cast<const float4 *>(p.data + (int64_t)pr * p.rowStride + t0);   // t0 % 4096 == 0
-        float4 v[kPer];
-#pragma unroll
-        for (int k = 0; k < kPer; k++) {                // all loads of the pair row in flight before the wait
-          const int L2 = tid + k * kTcSplit;            // frames 2 L2, 2 L2 + 1
-          v[k] = 2 * L2 < nFrames ? __ldg(row + L2) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (pr == 0) {   // pair 0 = (loudness, first spectral channel)
-#pragma unroll
-          for (int k = 0; k < kPer; k++) {
-            b0[2 * k] = v[k].x; s1[2 * k] = v[k].y; s2[2 * k] = v[k].y * v[k].y;
-            b0[2 * k + 1] = v[k].z; s1[2 * k + 1] = v[k].w; s2[2 * k + 1] = v[k].w * v[k].w;
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < kPer; k++) {
-            s1[2 * k] += v[k].x + v[k].y; s2[2 * k] = fmaf(v[k].x, v[k].x, fmaf(v[k].y, v[k].y, s2[2 * k]));
-            s1[2 * k + 1] += v[k].z + v[k].w; s2[2 * k + 1] = fmaf(v[k].z, v[k].z, fmaf(v[k].w, v[k].w, s2[2 * k + 1]));
-          }
-        }
-        if (use > 0) tc_wait(opFree + buf, (use - 1) & 1);   // MMAs of the pair that last used this buffer are done
         unsigned char *x1 = ops(buf, 0, 0), *x2 = ops(buf, 0, 1), *y1 = ops(buf, 1, 0), *y2 = ops(buf, 1, 1);
 #pragma unroll
-        for (int k = 0; k < kPer; k++) {
-          const int L = 2 * (tid + k * kTcSplit);
-          if (L < nFrames) {
-            // frame L -> row L / 32 (64 B), 16-byte chunk (L % 32) / 8 flipped by (row >> 1) & 3, half (L % 8)
-            const int r = L >> 5, ch = (L & 31) >> 3, w = L & 7;
-            const uint32_t off = (uint32_t)(r * 64 + ((ch ^ ((r >> 1) & 3)) << 4) + w * 2);
-            const __half2 xa = __floats2half2_rn(v[k].x, v[k].z), ya = __floats2half2_rn(v[k].y, v[k].w);
-            const float2 xf = __half22float2(xa), yf = __half22float2(ya);
-            *reinterpret_cast<__half2 *>(x1 + off) = xa;
-            *reinterpret_cast<__half2 *>(x2 + off) = __floats2half2_rn(v[k].x - xf.x, v[k].z - xf.y);
-            *reinterpret_cast<__half2 *>(y1 + off) = ya;
-            *reinterpret_cast<__half2 *>(y2 + off) = __floats2half2_rn(v[k].y - yf.x, v[k].w - yf.y);
+        for (int k0 = 0; k0 < kPer; k0 += kPer) {       // all loads of the pair row in flight at once
+          float4 v[kPer];
+#pragma unroll
+          for (int k = 0; k < kPer; k++) {
+            const int L2 = tid + (k0 + k) * kTcSplit;   // frames 2 L2, 2 L2 + 1
+            v[k] = 2 * L2 < nFrames ? __ldg(row + L2) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (pr == 0) {   // pair 0 = (loudness, first spectral channel)
+#pragma unroll
+            for (int k = 0; k < kPer; k++) {
+              const int kk = k0 + k;
+              b0[2 * kk] = v[k].x; s1[2 * kk] = v[k].y; s2[2 * kk] = v[k].y * v[k].y;
+              b0[2 * kk + 1] = v[k].z; s1[2 * kk + 1] = v[k].w; s2[2 * kk + 1] = v[k].w * v[k].w;
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < kPer; k++) {
+              const int kk = k0 + k;
+              s1[2 * kk] += v[k].x + v[k].y; s2[2 * kk] = fmaf(v[k].x, v[k].x, fmaf(v[k].y, v[k].y, s2[2 * kk]));
+              s1[2 * kk + 1] += v[k].z + v[k].w; s2[2 * kk + 1] = fmaf(v[k].z, v[k].z, fmaf(v[k].w, v[k].w, s2[2 * kk + 1]));
+            }
+          }
+          if (k0 == 0 && use > 0) tc_wait<false>(opFree + buf, (use - 1) & 1);   // MMAs that last used this buffer are done
+#pragma unroll
+          for (int k = 0; k < kPer; k++) {
+            const int L = 2 * (tid + (k0 + k) * kTcSplit);
+            if (L < nFrames) {
+              // frame L -> row L / 32 (64 B), 16-byte chunk (L % 32) / 8 flipped by (row >> 1) & 3, half (L % 8)
+              const int r = L >> 5, ch = (L & 31) >> 3, w = L & 7;
+              const uint32_t off = (uint32_t)(r * 64 + ((ch ^ ((r >> 1) & 3)) << 4) + w * 2);
+              const __half2 xa = __floats2half2_rn(v[k].x, v[k].z), ya = __floats2half2_rn(v[k].y, v[k].w);
+              const float2 xf = __half22float2(xa), yf = __half22float2(ya);
+              *reinterpret_cast<__half2 *>(x1 + off) = xa;
+              *reinterpret_cast<__half2 *>(x2 + off) = __floats2half2_rn((v[k].x - xf.x) * kTcLoScale, (v[k].z - xf.y) * kTcLoScale);
+              *reinterpret_cast<__half2 *>(y1 + off) = ya;
+              *reinterpret_cast<__half2 *>(y2 + off) = __floats2half2_rn((v[k].y - yf.x) * kTcLoScale, (v[k].w - yf.y) * kTcLoScale);
+            }
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (MMA)
@@ -267,13 +277,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
       for (int pr = 0; pr < p.numPairs; pr++, pc++) {
         const int buf = pc & 1;
         const uint32_t use = pc >> 1;
-        tA = clock64();
-        if (use > 0) tc_wait<false>(opFree + buf, (use - 1) & 1);
-        cFree += clock64() - tA;
-        if (tc_elect()) {
+        if (pc == 0 && tc_elect()) {   // very first pair: nothing to wait for (later requests are issued one pair ahead)
           mbar_expect_tx(tapsFull + buf, G.tapsPairBytes);
-          bulk_g2s(tapsBuf(buf), reinterpret_cast<const unsigned char *>(p.taps) + (size_t)pr * G.tapsPairBytes,
-                   G.tapsPairBytes, tapsFull + buf);
+          bulk_g2s(tapsBuf(buf), p.taps, G.tapsPairBytes, tapsFull + buf);
         }
         tA = clock64();
         if (pr == 0 && tileIt > 0) tc_wait<false>(accEmpty, (tileIt - 1) & 1);   // epilogue has drained the accumulators
@@ -312,6 +318,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
         }
         __syncwarp();
         cIssue += clock64() - tA;
+        // taps of the NEXT pair, one pair ahead: its buffer is free once the pair before this one has executed, which
+        // (tcgen05 ops run in issue order) happens while the MMAs just issued are still queued
+        {
+          const bool lastPair = pr == p.numPairs - 1;
+          if (!(lastPair && tile + gridDim.x >= p.tileEnd)) {
+            const uint32_t npc = pc + 1, nbuf = npc & 1, nuse = npc >> 1;
+            const int npr = lastPair ? 0 : pr + 1;
+            tA = clock64();
+            if (nuse > 0) tc_wait<false>(opFree + nbuf, (nuse - 1) & 1);
+            cFree += clock64() - tA;
+            if (tc_elect()) {
+              mbar_expect_tx(tapsFull + nbuf, G.tapsPairBytes);
+              bulk_g2s(tapsBuf(nbuf), reinterpret_cast<const unsigned char *>(p.taps) + (size_t)npr * G.tapsPairBytes,
+                       G.tapsPairBytes, tapsFull + nbuf);
+            }
+          }
+        }
       }
     }
     if (p.prof && lane == 0) {
@@ -320,9 +343,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
     }
   } else {
     // =========================== epilogue ===========================
-    // TMEM lanes 32 q .. 32 q + 31 (q = warp % 4) = rows r; row r = offsets t0 + 32 r + (31 - column)
-    const int quarter = warp & 3, et = (warp - (kTcSplit / 32 + 1)) * 32 + lane;   // et = 0..127
-    const int W = p.W, nr = W >> 5, rem = W & 31;
+    // 8 warps: TMEM lane quarter q = warp % 4 (rows r = 32 q + lane), column half hs = (warp - 8) / 4.  A thread owns the
+    // 16 offsets t0 + 32 r + jb .. + 15 (columns 31 - offset), jb = 16 (1 - hs).  Two warps per scheduler: the FP64 /
+    // MUFU latencies of the window statistics need the second warp to hide behind.
+    const int ew = warp - (kTcSplit / 32 + 1), quarter = warp & 3, hs = ew >> 2, et = ew * 32 + lane;   // et = 0..255
+    const int jb = 16 * (1 - hs);
+    const int W = p.W;
     const bool useT = p.weight > 0.f, useS = p.weight < 1.f;
     const float qnan = __int_as_float(0x7fc00000);
     const double invW = 1.0 / (double)W, invNS = 1.0 / ((double)(p.numCh - 1) * (double)W);
@@ -334,7 +360,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
       const int64_t t0 = tile * kTcTile;
       // file of this thread's first offset: the tile spans files [tileFile[tile], tileFile[tile + 1]] (host table)
       const int r = quarter * 32 + lane;
-      const int64_t g0 = t0 + 32 * (int64_t)r;
+      const int64_t g0 = t0 + 32 * (int64_t)r + jb;
       int f;
       {
         int lo = p.tileFile[tile], hi = p.tileFile[tile + 1] + 1;
@@ -349,28 +375,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
       tc_wait(accFull, tileIt & 1);
       eAcc += clock64() - tE; tE = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;");
-      const uint32_t laneAddr = tmem + ((uint32_t)(quarter * 32) << 16);
-      float accT[32], accS[32];
-#pragma unroll
-      for (int half = 0; half < 2; half++) {
+      const uint32_t laneAddr = tmem + ((uint32_t)(quarter * 32) << 16) + 16u * (uint32_t)hs;
+      float accT[16], accS[16];
+      {
         uint32_t u[16], w[16];
-        tc_ld16_nowait(laneAddr + 0 * 32 + 16 * half, u);
-        tc_ld16_nowait(laneAddr + 1 * 32 + 16 * half, w);
+        tc_ld16_nowait(laneAddr + 0 * 32, u);
+        tc_ld16_nowait(laneAddr + 1 * 32, w);
         tc_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; i++) accT[16 * half + i] = __uint_as_float(u[i]) + __uint_as_float(w[i]);
-        tc_ld16_nowait(laneAddr + 2 * 32 + 16 * half, u);
-        tc_ld16_nowait(laneAddr + 3 * 32 + 16 * half, w);
+        for (int i = 0; i < 16; i++) accT[i] = fmaf(__uint_as_float(w[i]), 1.0f / kTcLoScale, __uint_as_float(u[i]));
+        tc_ld16_nowait(laneAddr + 2 * 32, u);
+        tc_ld16_nowait(laneAddr + 3 * 32, w);
         tc_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; i++) accS[16 * half + i] = __uint_as_float(u[i]) + __uint_as_float(w[i]);
+        for (int i = 0; i < 16; i++) accS[i] = fmaf(__uint_as_float(u[i]), 1.0f / kTcLoScale, __uint_as_float(w[i]));
         for (int c = 2; c < p.numCh; c += 2) {     // two accumulators per wait; an odd tail reads one
-          tc_ld16_nowait(laneAddr + (uint32_t)(2 + c) * 32 + 16 * half, u);
-          if (c + 1 < p.numCh) tc_ld16_nowait(laneAddr + (uint32_t)(3 + c) * 32 + 16 * half, w);
+          tc_ld16_nowait(laneAddr + (uint32_t)(2 + c) * 32, u);
+          if (c + 1 < p.numCh) tc_ld16_nowait(laneAddr + (uint32_t)(3 + c) * 32, w);
           tc_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; i++)
-            accS[16 * half + i] += __uint_as_float(u[i]) + (c + 1 < p.numCh ? __uint_as_float(w[i]) : 0.f);
+          for (int i = 0; i < 16; i++) accS[i] += __uint_as_float(u[i]) + (c + 1 < p.numCh ? __uint_as_float(w[i]) : 0.f);
         }
       }
       // the accumulators are in registers: hand TMEM back to the issuer
@@ -379,49 +403,84 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
       if (lane == 0) mbar_arrive(accEmpty);
       eLd += clock64() - tE; tE = clock64();
 
-      // ---- window statistics: FP64 sums of whole 32-frame rows, then slide frame by frame inside the row ----
+      // ---- window statistics: FP64 sums of whole 32-frame rows, then slide frame by frame ----
       tc_wait(statsFull, tileIt & 1);
       eSt += clock64() - tE; tE = clock64();
-      for (int rr = r; rr < G.rows; rr += 128) {
-        double a1 = 0, a2 = 0, a3 = 0, a4 = 0;
-        const int e0 = 33 * rr;
-#pragma unroll 8
-        for (int k = 0; k < 32; k++) {
-          const double x = (double)T0[e0 + k];
-          const float2 f = F[e0 + k];
-          a1 += x; a2 += x * x; a3 += (double)f.x; a4 += (double)f.y;
-        }
-        double *o = RS + 4 * rr;
+      for (int qd = et; qd < 4 * G.rows; qd += kTcEpi) {      // FP64 sums of every 8-frame quarter row
+        const int e0 = 33 * (qd >> 2) + 8 * (qd & 3);
+        double x[8], a1, a2, a3, a4;
+        float2 fq[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { x[k] = (double)T0[e0 + k]; fq[k] = F[e0 + k]; }
+        a1 = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+        a2 = ((x[0] * x[0] + x[1] * x[1]) + (x[2] * x[2] + x[3] * x[3])) + ((x[4] * x[4] + x[5] * x[5]) + (x[6] * x[6] + x[7] * x[7]));
+        a3 = (((double)fq[0].x + (double)fq[1].x) + ((double)fq[2].x + (double)fq[3].x)) +
+             (((double)fq[4].x + (double)fq[5].x) + ((double)fq[6].x + (double)fq[7].x));
+        a4 = (((double)fq[0].y + (double)fq[1].y) + ((double)fq[2].y + (double)fq[3].y)) +
+             (((double)fq[4].y + (double)fq[5].y) + ((double)fq[6].y + (double)fq[7].y));
+        double *o = RQ + 4 * qd;
         o[0] = a1; o[1] = a2; o[2] = a3; o[3] = a4;
       }
       tc_epi_sync();
-      eRow += clock64() - tE; tE = clock64();
-      D4 win = {0, 0, 0, 0};
-      for (int i = 0; i < nr; i++) {
-        const double *o = RS + 4 * (r + i);
-        win.t1 += o[0]; win.t2 += o[1]; win.s1 += o[2]; win.s2 += o[3];
+      if (et < G.rows) {                                      // whole rows from their quarters
+        const double *q = RQ + 16 * et;
+        double *o = RS + 4 * et;
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[k] = (q[k] + q[4 + k]) + (q[8 + k] + q[12 + k]);
       }
-      for (int k = 0; k < rem; k++) {
-        const int e = 33 * (r + nr) + k;
-        const double x = (double)T0[e];
-        const float2 f = F[e];
-        win.t1 += x; win.t2 += x * x; win.s1 += (double)f.x; win.s2 += (double)f.y;
+      tc_epi_sync();
+      eRow += clock64() - tE; tE = clock64();
+      // window of the first offset: frames [32 r + jb, 32 r + jb + W) = quarters up to a row boundary, whole rows,
+      // quarters, and at most 7 single frames (jb is 0 or 16, so the start is quarter aligned)
+      D4 win = {0, 0, 0, 0};
+      {
+        int left = W, fr = 32 * r + jb;                       // fr = next frame (relative to the tile) to add
+        while ((fr & 31) != 0 && left >= 8) {
+          const double *o = RQ + 4 * (fr >> 3);
+          win.t1 += o[0]; win.t2 += o[1]; win.s1 += o[2]; win.s2 += o[3];
+          fr += 8; left -= 8;
+        }
+        D4 w2 = {0, 0, 0, 0};                                 // second chain: halves the dependent FP64 adds
+        for (; left >= 64; left -= 64, fr += 64) {
+          const double *o = RS + 4 * (fr >> 5);
+          win.t1 += o[0]; win.t2 += o[1]; win.s1 += o[2]; win.s2 += o[3];
+          w2.t1 += o[4]; w2.t2 += o[5]; w2.s1 += o[6]; w2.s2 += o[7];
+        }
+        if (left >= 32) {
+          const double *o = RS + 4 * (fr >> 5);
+          win.t1 += o[0]; win.t2 += o[1]; win.s1 += o[2]; win.s2 += o[3];
+          fr += 32; left -= 32;
+        }
+        while (left >= 8) {
+          const double *o = RQ + 4 * (fr >> 3);
+          w2.t1 += o[0]; w2.t2 += o[1]; w2.s1 += o[2]; w2.s2 += o[3];
+          fr += 8; left -= 8;
+        }
+        const int e0 = 33 * (fr >> 5) + (fr & 31);
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+          if (k < left) {
+            const double x = (double)T0[e0 + k];
+            const float2 fq = F[e0 + k];
+            w2.t1 += x; w2.t2 += x * x; w2.s1 += (double)fq.x; w2.s2 += (double)fq.y;
+          }
+        }
+        win.t1 += w2.t1; win.t2 += w2.t2; win.s1 += w2.s1; win.s2 += w2.s2;
       }
       eInit += clock64() - tE; tE = clock64();
       unsigned long long best = 0ull;
       const float *T0r = T0 + 33 * r;      // row base in the skewed arrays: frame 32 r + x sits at x + x / 32
       const float2 *Fr = F + 33 * r;
-      // common case: all 32 offsets of the row are evaluated offsets of ONE file -> no control flow per offset
-      const bool plain = g0 + 32 <= fStart + ((fEnd - fStart) - p.tailExtra - W + 1) && g0 + 32 <= p.usedFrames;
+      // common case: all 16 offsets are evaluated offsets of ONE file -> no control flow per offset
+      const bool plain = g0 + 16 <= fStart + ((fEnd - fStart) - p.tailExtra - W + 1) && g0 + 16 <= p.usedFrames;
       const uint32_t tl0 = (uint32_t)(g0 - fStart);
 #pragma unroll
-      for (int blk = 0; blk < 4; blk++) {
-        // pass A: straight-line arithmetic for 8 offsets, so that the 8 dependency chains overlap (one warp per
-        // scheduler here: no other warp hides the FP64 / MUFU latencies)
+      for (int blk = 0; blk < 2; blk++) {
+        // pass A: straight-line arithmetic for 8 offsets, so that the 8 dependency chains overlap
         float simv[8], boostv[8];
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-          const int j = 8 * blk + e, col = 31 - j;
+          const int jj = 8 * blk + e;           // offset inside the thread's run; accumulator column 15 - jj of its half
           const double mT = win.t1 * invW;
           const float avgB = (float)mT;                                          // MathUtil.avg -> Float
           const float boost = exp2f((l2In - __log2f(avgB)) * (1.0f / 0.6f));     // calcBoost
@@ -429,29 +488,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
           if (useT) {
             const double q = win.t2 * invW;
             const double var = q - mT * mT;
-            const float cr = accT[col] - (float)mT * rhoT;
+            const float cr = accT[15 - jj] - (float)mT * rhoT;
             temporal = (var > 1e-13 * q) ? (cr * cT) * rsqrtf((float)var) : qnan;
           }
           if (useS) {
             const double mS = win.s1 * invNS;
             const double q = win.s2 * invNS;
             const double var = q - mS * mS;
-            const float cr = accS[col] - (float)mS * rhoS;
+            const float cr = accS[15 - jj] - (float)mS * rhoS;
             spectral = (var > 1e-13 * q) ? (cr * cS) * rsqrtf((float)var) : qnan;
           }
           const float blend = __fadd_rn(__fmul_rn(temporal, p.weight), __fmul_rn(spectral, __fsub_rn(1.0f, p.weight)));
           simv[e] = boost <= p.maxBoost ? blend : 0.f;
           boostv[e] = boost;
-          if (j < 31) {
-            // slide the window by one frame: the deltas in FP32 (their rounding, 6e-8 of one frame's value, is far
-            // below the window sums' own FP32 inputs), the running sums in FP64
-            const int jn = j + W + ((j + W) >> 5);
-            const float bo = T0r[j], bn = T0r[jn];
-            const float2 fo = Fr[j], fn = Fr[jn];
-            win.t1 += (double)(bn - bo);
-            win.t2 += (double)fmaf(bn, bn, -bo * bo);
-            win.s1 += (double)(fn.x - fo.x);
-            win.s2 += (double)(fn.y - fo.y);
+          if (jj < 15) {
+            // slide the window by one frame; exact FP64 deltas: a window that has moved onto constant data (digital
+            // silence) must end up with EXACTLY zero variance, the reference yields NaN there
+            const int jo = jb + jj, jn = jo + W;
+            const int io = jo + (jo >> 5), in = jn + (jn >> 5);
+            const double bo = (double)T0r[io], bn = (double)T0r[in];
+            const float2 fo = Fr[io], fn = Fr[in];
+            win.t1 += bn - bo;
+            win.t2 += bn * bn - bo * bo;
+            win.s1 += (double)fn.x - (double)fo.x;
+            win.s2 += (double)fn.y - (double)fo.y;
           }
         }
         // pass B: which offsets exist (window inside its file), per-file maximum (first occurrence)

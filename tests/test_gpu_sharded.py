@@ -87,5 +87,7 @@ def test_search_is_idempotent_and_order_sensitive(ctx):
         return a
 
     fwd, rev = run(files), run(files[::-1])
-    assert fwd[0]["file"] == 7 and rev[0]["file"] == 12 and fwd[0]["sim"] == rev[0]["sim"]
+    # the needle's score does not depend on where its file sits in the database, up to the kernel's rounding (the
+    # tensor-core kernel accumulates an offset's taps in a K order that depends on the offset's position in its tile)
+    assert fwd[0]["file"] == 7 and rev[0]["file"] == 12 and abs(fwd[0]["sim"] - rev[0]["sim"]) < 1e-6
     assert fwd[0]["start"] == rev[0]["start"] == 500 * STEP
