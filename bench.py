@@ -280,30 +280,55 @@ def main():
     if rank == 0:
         scan_s = float(np.mean(scan_ms)) * 1e-3
         flops = n_off_local * FLOP_PER_OFFSET / scan_s / 1e12
-        traffic = None   # dram__bytes_read + dram__bytes_write of one k_corr launch, from the committed ncu capture
+        tc = os.environ.get("SGZ_CORR_TC", "1") != "0"     # K1 on the tensor cores (default) or the FFMA2 kernel
+        traffic = None   # dram__bytes_read + dram__bytes_write of one K1 launch, from the committed ncu capture
+        traffic_file = "r01_k_corr_tc_traffic.json" if tc else "r01_k_corr_traffic.json"
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k_corr_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", traffic_file)))
             if int(tj["offsets_per_launch"]) == int(n_off_local):
                 traffic = float(tj["dram_bytes_per_launch"])
         except Exception:
             pass
+        hbm = {"achieved": n_off_local * BYTES_PER_OFFSET / scan_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+               "frac": n_off_local * BYTES_PER_OFFSET / scan_s / 1e9 / hbm_peak, "peak_source": hbm_src,
+               "algorithmic_bytes_per_offset": BYTES_PER_OFFSET}
+        if tc:
+            # tensor-core K1 (corr_tc.cuh): per tile of 4096 offsets, 14 channels x 3 split-FP16 products x
+            # ceil((32 + W) / 16) MMAs of M128 x N32 x K16; each costs 44.5 cycles back to back (tools/umma_probe.cu: the
+            # A-operand fetch bounds small-N MMAs), which is this design's own floor
+            tensor_peak = float(peaks_file.get("bf16_tflops_sustained", 1399.0))
+            mmas_per_tile = 14 * 3 * ((32 + 172 + 15) // 16)
+            exec_flop_per_offset = mmas_per_tile * 2 * 128 * 32 * 16 / 4096
+            tiles_per_sm = -(-n_off_local // 4096) / 148.0
+            floor_ms = tiles_per_sm * mmas_per_tile * 44.5 / 1.965e6
+            roofline = {"kernel": "sgz::k_corr_tc (K1 sliding-window Pearson correlation on tcgen05, split FP16, fused "
+                                  "window statistics / sim / file maxima)",
+                        "bound": "tensor", "achieved": flops, "peak": tensor_peak, "unit": "TFLOP/s",
+                        "frac": flops / tensor_peak,
+                        "peak_source": "dense bf16 (= fp16) matmul, sustained, MEASURED_PEAKS.json",
+                        "executed_tflops": n_off_local * exec_flop_per_offset / scan_s / 1e12,
+                        "executed_frac": n_off_local * exec_flop_per_offset / scan_s / 1e12 / tensor_peak,
+                        "executed_flop_per_offset": exec_flop_per_offset,
+                        "why_not_higher": "N = 32 MMAs are bound by the 4 KB A-operand fetch (44.5 cycles per M128xN32xK16 "
+                                          "MMA, measured), not by the math; 3 products for FP32-grade precision",
+                        "mma_floor_ms": floor_ms, "frac_of_mma_floor": floor_ms / float(np.mean(scan_ms)),
+                        "fp32_ffma_peak": ffma_peak, "algorithmic_vs_fp32_ffma_peak": flops / ffma_peak}
+        else:
+            roofline = {"kernel": "sgz::k_corr (K1 sliding-window Pearson correlation, FFMA2)", "bound": "fp32_ffma",
+                        "achieved": flops, "peak": ffma_peak, "unit": "TFLOP/s", "frac": flops / ffma_peak,
+                        "peak_source": "FP32 FFMA micro-benchmark run live by this process "
+                                       "(MEASURED_PEAKS.json has no FP32 figure; SURVEY.md 8d)"}
+        roofline.update({"algorithmic_flop_per_offset": FLOP_PER_OFFSET, "offsets_per_launch": n_off_local,
+                         "launch_ms": float(np.mean(scan_ms)), "traffic": traffic,
+                         "traffic_source": f"profiles/{traffic_file} (ncu --set full of this command)",
+                         "algorithmic_bytes_per_launch": n_off_local * BYTES_PER_OFFSET, "hbm": hbm})
         line = {
             "metric": "FeatureCorrelation DB frame-offsets/sec", "value": value, "unit": "offsets/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 window sums)",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16x2 split operands, f32 accumulate, f64 window sums",
             "data": "synthetic (device-generated integer-hash features, planted needles)",
             "config": config_block(world, files),
-            "roofline": {"kernel": "sgz::k_corr (K1 sliding-window Pearson correlation)", "bound": "fp32_ffma",
-                         "achieved": flops, "peak": ffma_peak, "unit": "TFLOP/s", "frac": flops / ffma_peak,
-                         "peak_source": "FP32 FFMA micro-benchmark run live by this process "
-                                        "(MEASURED_PEAKS.json has no FP32 figure; SURVEY.md 8d)",
-                         "algorithmic_flop_per_offset": FLOP_PER_OFFSET, "offsets_per_launch": n_off_local,
-                         "launch_ms": float(np.mean(scan_ms)), "traffic": traffic,
-                         "traffic_source": "profiles/r01_k_corr_traffic.json (ncu --set full of this command)",
-                         "algorithmic_bytes_per_launch": n_off_local * BYTES_PER_OFFSET,
-                         "hbm": {"achieved": n_off_local * BYTES_PER_OFFSET / scan_s / 1e9, "peak": hbm_peak,
-                                 "unit": "GB/s", "frac": n_off_local * BYTES_PER_OFFSET / scan_s / 1e9 / hbm_peak,
-                                 "peak_source": hbm_src, "algorithmic_bytes_per_offset": BYTES_PER_OFFSET}},
+            "roofline": roofline,
             "breakdown_ms": {"k1_scan": float(np.mean(scan_ms)), "k2_select_kernels": float(np.mean(select_ms)),
                              "wall_per_step": wall_ms / args.steps,
                              "rank0_host_phases": {k: (v / args.steps if k == "rounds" else 1e3 * v / args.steps)
