@@ -131,7 +131,9 @@ inline int prepare_query(const sgz_db *db, const float *inputPlanar /*[numCh][in
   }
   SGZ_TRY(q.dTaps.alloc(q.taps.size()));
   SGZ_CUDA(cudaMemcpyAsync(q.dTaps.p, q.taps.data(), q.taps.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-  if (tc_applicable(db->ctx, numCh, W)) {
+  // not while uploads are in flight (streaming scan, FFMA2 kernel): a 200 KB pageable copy would queue behind them in
+  // the H2D copy engine and stall the job creation until the database has landed
+  if (tc_applicable(db->ctx, numCh, W) && db->chunks.empty()) {
     tc_build_taps(q.taps, db->numPairs, q.Wq, W, q.tcTaps);
     SGZ_TRY(q.dTcTaps.alloc(q.tcTaps.size()));
     SGZ_CUDA(cudaMemcpyAsync(q.dTcTaps.p, q.tcTaps.data(), q.tcTaps.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
