@@ -236,23 +236,23 @@ inline int run_scan_tc(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim, 
   DevBuf<long long> dProf;
   const bool prof = getenv("SGZ_CORR_TC_PROF") != nullptr;   // developer probe: where does the issuer lane wait?
   if (prof) {
-    SGZ_TRY(dProf.alloc((size_t)gridTc * 16));
-    SGZ_CUDA(cudaMemsetAsync(dProf.p, 0, (size_t)gridTc * 16 * sizeof(long long), st));
+    SGZ_TRY(dProf.alloc((size_t)gridTc * 24));
+    SGZ_CUDA(cudaMemsetAsync(dProf.p, 0, (size_t)gridTc * 24 * sizeof(long long), st));
     tp.prof = dProf.p;
   }
   k_corr_tc<<<gridTc, kTcThreads, G.smemBytes, st>>>(tp);
   SGZ_LAUNCH_CHECK(ctx);
   if (prof) {
-    std::vector<long long> h((size_t)gridTc * 16);
+    std::vector<long long> h((size_t)gridTc * 24);
     SGZ_CUDA(cudaMemcpyAsync(h.data(), dProf.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
     SGZ_CUDA(cudaStreamSynchronize(st));
-    double a[16] = {0};
-    for (unsigned b = 0; b < gridTc; b++) for (int k = 0; k < 16; k++) a[k] += (double)h[(size_t)b * 16 + k];
+    double a[24] = {0};
+    for (unsigned b = 0; b < gridTc; b++) for (int k = 0; k < 24; k++) a[k] += (double)h[(size_t)b * 24 + k];
     const double tiles = a[6] > 0 ? a[6] : 1;
     fprintf(stderr, "k_corr_tc cycles per tile: issuer total %.0f | wait opFree %.0f, accEmpty %.0f, opFull %.0f, taps %.0f, "
-                    "issue %.0f || epilogue wait accFull %.0f, tmem read %.0f, wait stats %.0f, row sums %.0f, init %.0f, loop %.0f\n",
+                    "issue %.0f || epilogue wait accFull %.0f, tmem read %.0f, wait stats %.0f, row sums %.0f, init %.0f, loop %.0f || split loads+sums %.0f, wait opFree %.0f, store %.0f, stats %.0f\n",
             a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles, a[4] / tiles, a[5] / tiles, a[8] / tiles, a[9] / tiles,
-            a[10] / tiles, a[12] / tiles, a[13] / tiles, a[11] / tiles);
+            a[10] / tiles, a[12] / tiles, a[13] / tiles, a[11] / tiles, a[16] / tiles, a[17] / tiles, a[18] / tiles, a[19] / tiles);
   }
   return SGZ_OK;
 }

@@ -52,7 +52,7 @@ __host__ __device__ inline TcGeom tc_geom(int W) {
   g.tapsPairBytes = (uint32_t)((2 * g.tapsChanBytes + 1023) / 1024 * 1024);
   g.t0Bytes = (uint32_t)((g.rows * 33 * 4 + 127) / 128 * 128);   // skewed: frame e at index e + e / 32
   g.fBytes = (uint32_t)((g.rows * 33 * 8 + 127) / 128 * 128);
-  g.rsBytes = (uint32_t)(g.rows * 32 + g.rows * 4 * 32);   // FP64 sums of whole rows + of 8-frame quarters
+  g.rsBytes = (uint32_t)((g.rows * 5 + g.rows * 17) * 8 + 64);   // FP64 sums of whole rows (stride 5) + of 8-frame quarters (stride 17): padded against bank conflicts
   g.smemBytes = (size_t)8 * g.chanBytes + (size_t)2 * g.tapsPairBytes + g.t0Bytes + g.fBytes + g.rsBytes +
                 1024 /*alignment slack*/ + 256 /*barriers*/;
   return g;
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
   float *T0 = reinterpret_cast<float *>(tapsBase + (size_t)2 * G.tapsPairBytes);           // loudness per frame
   float2 *F = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(T0) + G.t0Bytes);   // (sum_c b, sum_c b^2)
   double *RS = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(F) + G.fBytes);    // [rows][4] row sums
-  double *RQ = RS + 4 * G.rows;                                                                // [rows][4 quarters][4]
+  double *RQ = RS + 5 * G.rows;                                                                // [rows][4 quarters][4] + 1 pad
   uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(RS) + G.rsBytes);
   uint64_t *opFree = bars, *opFull = bars + 2, *tapsFull = bars + 4, *accFull = bars + 6, *accEmpty = bars + 7;
   uint64_t *statsFull = bars + 8, *statsFree = bars + 9;
@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
     // =========================== split workers ===========================
     constexpr int kPer = 10;                            // >= ceil(nFrames / 448) for W <= 256; two frames per step
     uint32_t pc = 0, tileIt = 0;
+    long long sLoad = 0, sWait = 0, sStore = 0, sStats = 0, tS;
     for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, tileIt++) {
       const int64_t t0 = tile * kTcTile;
       float b0[2 * kPer], s1[2 * kPer], s2[2 * kPer];   // per-frame sums over the channels of this thread's frames
@@ -206,6 +207,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
         const uint32_t use = pc >> 1;
         const float4 *row = reinterpret_cast<const float4 *>(p.data + (int64_t)pr * p.rowStride + t0);   // t0 % 4096 == 0
         unsigned char *x1 = ops(buf, 0, 0), *x2 = ops(buf, 0, 1), *y1 = ops(buf, 1, 0), *y2 = ops(buf, 1, 1);
+        tS = clock64();
+        {   // pull the NEXT pair row into L2 now: its loads then see an L2 hit instead of the HBM latency
+          const bool lastPair = pr == p.numPairs - 1;
+          const int64_t nt0 = lastPair ? t0 + (int64_t)gridDim.x * kTcTile : t0;
+          if (!lastPair || tile + gridDim.x < p.tileEnd) {
+            const float4 *nrow = reinterpret_cast<const float4 *>(p.data + (int64_t)(lastPair ? 0 : pr + 1) * p.rowStride + nt0);
+#pragma unroll
+            for (int k = 0; k < kPer; k++) {
+              const int L2 = tid + k * kTcSplit;
+              if ((L2 & 7) == 0 && 2 * L2 < nFrames) asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + L2));
+            }
+          }
+        }
 #pragma unroll
         for (int k0 = 0; k0 < kPer; k0 += kPer) {       // all loads of the pair row in flight at once
           float4 v[kPer];
@@ -229,7 +243,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
               s1[2 * kk + 1] += v[k].z + v[k].w; s2[2 * kk + 1] = fmaf(v[k].z, v[k].z, fmaf(v[k].w, v[k].w, s2[2 * kk + 1]));
             }
           }
+          sLoad += clock64() - tS; tS = clock64();
           if (k0 == 0 && use > 0) tc_wait<false>(opFree + buf, (use - 1) & 1);   // MMAs that last used this buffer are done
+          sWait += clock64() - tS; tS = clock64();
 #pragma unroll
           for (int k = 0; k < kPer; k++) {
             const int L = 2 * (tid + (k0 + k) * kTcSplit);
@@ -249,7 +265,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (MMA)
         __syncwarp();
         if (lane == 0) mbar_arrive(opFull + buf);
+        sStore += clock64() - tS;
       }
+      tS = clock64();
       // per-frame sums of the tile -> shared memory for the epilogue warps
       if (tileIt > 0) tc_wait(statsFree, (tileIt - 1) & 1);
 #pragma unroll
@@ -263,6 +281,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(statsFull);
+      sStats += clock64() - tS;
+    }
+    if (p.prof && tid == 0) {
+      long long *o = p.prof + 24 * blockIdx.x + 16;
+      o[0] = sLoad; o[1] = sWait; o[2] = sStore; o[3] = sStats;
     }
   } else if (warp == kTcSplit / 32) {
     // =========================== MMA issuer ===========================
@@ -338,7 +361,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
       }
     }
     if (p.prof && lane == 0) {
-      long long *o = p.prof + 16 * blockIdx.x;
+      long long *o = p.prof + 24 * blockIdx.x;
       o[0] = clock64() - cTotal; o[1] = cFree; o[2] = cAcc; o[3] = cFull; o[4] = cTaps; o[5] = cIssue; o[6] = tileIt;
     }
   } else {
@@ -418,13 +441,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
              (((double)fq[4].x + (double)fq[5].x) + ((double)fq[6].x + (double)fq[7].x));
         a4 = (((double)fq[0].y + (double)fq[1].y) + ((double)fq[2].y + (double)fq[3].y)) +
              (((double)fq[4].y + (double)fq[5].y) + ((double)fq[6].y + (double)fq[7].y));
-        double *o = RQ + 4 * qd;
+        double *o = RQ + 17 * (qd >> 2) + 4 * (qd & 3);
         o[0] = a1; o[1] = a2; o[2] = a3; o[3] = a4;
       }
       tc_epi_sync();
       if (et < G.rows) {                                      // whole rows from their quarters
-        const double *q = RQ + 16 * et;
-        double *o = RS + 4 * et;
+        const double *q = RQ + 17 * et;
+        double *o = RS + 5 * et;
 #pragma unroll
         for (int k = 0; k < 4; k++) o[k] = (q[k] + q[4 + k]) + (q[8 + k] + q[12 + k]);
       }
@@ -436,23 +459,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
       {
         int left = W, fr = 32 * r + jb;                       // fr = next frame (relative to the tile) to add
         while ((fr & 31) != 0 && left >= 8) {
-          const double *o = RQ + 4 * (fr >> 3);
+          const double *o = RQ + 17 * (fr >> 5) + 4 * ((fr >> 3) & 3);
           win.t1 += o[0]; win.t2 += o[1]; win.s1 += o[2]; win.s2 += o[3];
           fr += 8; left -= 8;
         }
         D4 w2 = {0, 0, 0, 0};                                 // second chain: halves the dependent FP64 adds
         for (; left >= 64; left -= 64, fr += 64) {
-          const double *o = RS + 4 * (fr >> 5);
+          const double *o = RS + 5 * (fr >> 5);
           win.t1 += o[0]; win.t2 += o[1]; win.s1 += o[2]; win.s2 += o[3];
-          w2.t1 += o[4]; w2.t2 += o[5]; w2.s1 += o[6]; w2.s2 += o[7];
+          w2.t1 += o[5]; w2.t2 += o[6]; w2.s1 += o[7]; w2.s2 += o[8];
         }
         if (left >= 32) {
-          const double *o = RS + 4 * (fr >> 5);
+          const double *o = RS + 5 * (fr >> 5);
           win.t1 += o[0]; win.t2 += o[1]; win.s1 += o[2]; win.s2 += o[3];
           fr += 32; left -= 32;
         }
         while (left >= 8) {
-          const double *o = RQ + 4 * (fr >> 3);
+          const double *o = RQ + 17 * (fr >> 5) + 4 * ((fr >> 3) & 3);
           w2.t1 += o[0]; w2.t2 += o[1]; w2.s1 += o[2]; w2.s2 += o[3];
           fr += 8; left -= 8;
         }
@@ -560,7 +583,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
       eMain += clock64() - tE;
     }
     if (p.prof && et == 0) {
-      long long *o = p.prof + 16 * blockIdx.x + 8;
+      long long *o = p.prof + 24 * blockIdx.x + 8;
       o[0] = eAcc; o[1] = eLd; o[2] = eSt; o[3] = eMain; o[4] = eRow; o[5] = eInit;
     }
   }
