@@ -289,7 +289,11 @@ int sgz_self_run(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh, const 
                  const void *frames1, int64_t nFrames1, const void *frames2, int64_t nFrames2,
                  int32_t layout, int32_t rowBegin, int32_t rowEnd, int32_t *rgb, int64_t rgbCap,
                  sgz_self_geometry *geom);
-/* sims of selected cells (decimated image coordinates), for parity checks */
+/* which kernel rendered the last image of this context: 0 none, 1 FP32 FFMA2 Gram tiles (selfsim_fast.cuh),
+ * 2 tensor-core Gram tiles (selfsim_tc.cuh: split-FP16 tcgen05, the default when the geometry fits), 3 FP64 replay */
+int32_t sgz_self_last_kernel(sgz_ctx *ctx);
+/* sims of selected cells (decimated image coordinates), for parity checks; with precise = 0 and imgExt <= 4096 the
+ * cells of the computed triangle are read back from the image kernel itself */
 int sgz_self_cells(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh, const float *norm,
                    const void *frames1, int64_t nFrames1, const void *frames2, int64_t nFrames2,
                    int32_t layout, int64_t nCells, const int32_t *leftIdx,

@@ -24,7 +24,7 @@ LAYOUT_HOST_STABLE = 0x100   # OR-ed in: host buffer stays valid until finalize 
 SYMBOLS = [
     "sgz_abi_version", "sgz_last_error", "sgz_device_count",
     "sgz_ctx_create", "sgz_ctx_destroy", "sgz_ctx_synchronize", "sgz_ctx_stream", "sgz_ctx_last_timing",
-    "sgz_ctx_launch_count",
+    "sgz_ctx_launch_count", "sgz_self_last_kernel",
     "sgz_ctx_trim",
     "sgz_db_create", "sgz_db_destroy", "sgz_db_reserve", "sgz_db_add_file", "sgz_db_add_file_device",
     "sgz_db_add_synth", "sgz_db_patch", "sgz_db_finalize", "sgz_db_finalize_async", "sgz_db_stats", "sgz_db_info", "sgz_db_file_frames", "sgz_db_read",

@@ -108,6 +108,8 @@ int sgz_ctx_last_timing(sgz_ctx *ctx, float *ms, int64_t *launches) {
 
 int64_t sgz_ctx_launch_count(sgz_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int32_t sgz_self_last_kernel(sgz_ctx *ctx) { return ctx ? ctx->lastSelfKernel : 0; }
+
 int sgz_ctx_trim(sgz_ctx *ctx, int64_t *freedBytes) {
   SGZ_REQUIRE(ctx, "ctx is NULL");
   SGZ_TRY(ctx->bind());

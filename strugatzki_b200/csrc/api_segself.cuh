@@ -6,6 +6,7 @@
 #include "segm.cuh"
 #include "selfsim.cuh"
 #include "selfsim_fast.cuh"
+#include "selfsim_tc.cuh"
 #include "cross.cuh"
 
 namespace sgz {
@@ -175,6 +176,151 @@ static int self_prepare(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh,
   return SGZ_OK;
 }
 
+// Default (non-precise) image path on p (p.rgb set by the caller): centred Gram tiles + closed-form epilogue.
+// Tensor-core kernel (selfsim_tc.cuh) when the geometry fits and the data are finite, else the FFMA2 kernel
+// (selfsim_fast.cuh).  simMat (device, [ext][ext], tensor-core kernel only) receives the raw sims of the upper triangle;
+// *usedTc reports which kernel ran.
+static int self_fast_image(sgz_ctx *ctx, const sgz_self_config *cfg, sgz::SelfParams &p, const sgz_self_geometry &g,
+                           int H, int numCh, bool cross, int rowBegin, int rowEnd, float *simMat, int *usedTc) {
+  using namespace sgz;
+  const int ext = g.imgExt;
+  const int64_t need = (int64_t)g.numCorrs - 1 + H;
+  if (usedTc) *usedTc = 0;
+  DevBuf<double> dMeans;
+  DevBuf<unsigned int> dAmax;
+  DevBuf<float2> ws1, ws2;
+  DevBuf<float4> wsA, wsB;
+  DevBuf<uint4> rec1, rec2;
+  DevBuf<int2> dTiles;
+  SGZ_TRY(dMeans.alloc(2));
+  SGZ_TRY(dAmax.alloc(2));
+  SGZ_CUDA(cudaMemsetAsync(dMeans.p, 0, 2 * sizeof(double), ctx->stream));
+  SGZ_CUDA(cudaMemsetAsync(dAmax.p, 0, 2 * sizeof(unsigned int), ctx->stream));
+  SGZ_TRY(ctx->begin_call());
+  k_self_means<<<ctx->smCount * 4, 256, 0, ctx->stream>>>(p.x1, p.stride1, need, numCh, dMeans.p);
+  SGZ_LAUNCH_CHECK(ctx);
+  static const bool tcOff = getenv("SGZ_SELF_TC") && atoi(getenv("SGZ_SELF_TC")) == 0;
+  static const bool aDescOff = getenv("SGZ_SELF_TC_ADESC") && atoi(getenv("SGZ_SELF_TC_ADESC")) == 0;
+  const SelfTcGeom G = self_tc_geom(H, g.decim, ctx->smemOptin, !aDescOff);
+  bool tc = !tcOff && G.ok && numCh >= 2;
+  if (tc) {
+    k_self_absmax<<<ctx->smCount * 4, 256, 0, ctx->stream>>>(p.x1, p.stride1, need, numCh, dAmax.p);
+    SGZ_LAUNCH_CHECK(ctx);
+    if (cross) {
+      k_self_absmax<<<ctx->smCount * 4, 256, 0, ctx->stream>>>(p.x2, p.stride2, need, numCh, dAmax.p);
+      SGZ_LAUNCH_CHECK(ctx);
+    }
+  }
+  double means[2];
+  unsigned int amaxBits[2] = {0, 0};
+  SGZ_CUDA(cudaMemcpyAsync(means, dMeans.p, sizeof means, cudaMemcpyDeviceToHost, ctx->stream));
+  SGZ_CUDA(cudaMemcpyAsync(amaxBits, dAmax.p, sizeof amaxBits, cudaMemcpyDeviceToHost, ctx->stream));
+  SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  SelfFastParams fp{};
+  fp.base = p;
+  fp.shiftT = (float)(means[0] / (double)need);
+  fp.shiftS = (float)(means[1] / ((double)need * (numCh - 1)));
+  fp.cross = cross;
+  std::vector<int2> gt;
+  for (int a0 = rowBegin / kGT * kGT; a0 < rowEnd; a0 += kGT)
+    for (int b0 = a0; b0 < ext; b0 += kGT) gt.push_back(make_int2(a0, b0));
+  SGZ_TRY(dTiles.alloc(gt.size()));
+  SGZ_CUDA(cudaMemcpyAsync(dTiles.p, gt.data(), gt.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+  float scale = 1.0f;
+  if (tc) {
+    // power-of-two scale that brings the centred data to |v| <= 8192 (FP16 range with headroom); Inf / NaN data or
+    // shifts leave the tensor-core path
+    float aT, aS;
+    memcpy(&aT, &amaxBits[0], 4);
+    memcpy(&aS, &amaxBits[1], 4);
+    const double bound = std::max((double)aT + std::fabs((double)fp.shiftT), (double)aS + std::fabs((double)fp.shiftS));
+    if (!std::isfinite(bound)) tc = false;
+    else if (bound > 0) scale = (float)std::ldexp(1.0, std::max(-60, std::min(60, (int)std::floor(std::log2(8192.0 / bound)))));
+  }
+  if (tc) {
+    const int nT = ceil_div(ext, kGT);
+    const int64_t nRec = (int64_t)G.dp * kGT * (nT - 1) + G.span;
+    const int64_t recThreads = (int64_t)numCh * nRec;
+    SGZ_TRY(rec1.alloc((size_t)2 * numCh * nRec));
+    SGZ_TRY(wsA.alloc(ext));
+    k_self_records<<<(unsigned)ceil_div<int64_t>(recThreads, 256), 256, 0, ctx->stream>>>(
+        p.x1, p.stride1, need, numCh, G.g, nRec, fp.shiftT, fp.shiftS, scale, rec1.p);
+    SGZ_LAUNCH_CHECK(ctx);
+    k_self_wsums4<<<ceil_div(ext, 128), 128, 0, ctx->stream>>>(p.x1, p.stride1, numCh, H, g.decim, ext, fp.shiftT, fp.shiftS,
+                                                              scale, wsA.p);
+    SGZ_LAUNCH_CHECK(ctx);
+    if (cross) {
+      SGZ_TRY(rec2.alloc((size_t)2 * numCh * nRec));
+      SGZ_TRY(wsB.alloc(ext));
+      k_self_records<<<(unsigned)ceil_div<int64_t>(recThreads, 256), 256, 0, ctx->stream>>>(
+          p.x2, p.stride2, need, numCh, G.g, nRec, fp.shiftT, fp.shiftS, scale, rec2.p);
+      SGZ_LAUNCH_CHECK(ctx);
+      k_self_wsums4<<<ceil_div(ext, 128), 128, 0, ctx->stream>>>(p.x2, p.stride2, numCh, H, g.decim, ext, fp.shiftT,
+                                                                fp.shiftS, scale, wsB.p);
+      SGZ_LAUNCH_CHECK(ctx);
+    }
+    SelfTcParams tp{};
+    tp.f = fp;
+    tp.rec1 = rec1.p;
+    tp.rec2 = cross ? rec2.p : rec1.p;
+    tp.nRec = nRec;
+    tp.wsA = wsA.p;
+    tp.wsB = cross ? wsB.p : wsA.p;
+    tp.tiles = dTiles.p;
+    tp.nTiles = (int)gt.size();
+    tp.nks = G.nks; tp.nSlab = G.nSlab; tp.slabKs = G.slabKs; tp.dp = G.dp; tp.kcStep = G.kcStep; tp.span = G.span;
+    tp.nStage = G.nStage; tp.matBytes = G.matBytes; tp.stageBytes = G.stageBytes;
+    tp.recPartBytes = G.recPartBytes; tp.recStageBytes = G.recStageBytes;
+    tp.simMat = simMat;
+    tp.aDesc = G.aDesc;
+    SGZ_CUDA(cudaFuncSetAttribute(k_self_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));
+    const unsigned gridTc = (unsigned)std::min<size_t>(gt.size(), (size_t)ctx->smCount);
+    DevBuf<long long> dProf;
+    const bool prof = getenv("SGZ_SELF_TC_PROF") != nullptr;   // developer probe: cycles per role
+    if (prof) {
+      SGZ_TRY(dProf.alloc((size_t)gridTc * 16));
+      SGZ_CUDA(cudaMemsetAsync(dProf.p, 0, (size_t)gridTc * 16 * sizeof(long long), ctx->stream));
+      tp.prof = dProf.p;
+    }
+    k_self_gram_tc<<<gridTc, kSgThreads, G.smemBytes, ctx->stream>>>(tp);
+    SGZ_LAUNCH_CHECK(ctx);
+    SGZ_TRY(ctx->end_call());
+    if (prof) {
+      std::vector<long long> h((size_t)gridTc * 16);
+      SGZ_CUDA(cudaMemcpy(h.data(), dProf.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      double a[16] = {0};
+      for (unsigned bk = 0; bk < gridTc; bk++) for (int k = 0; k < 16; k++) a[k] += (double)h[(size_t)bk * 16 + k];
+      const double tiles = a[5] > 0 ? a[5] : 1;
+      fprintf(stderr, "k_self_gram_tc cycles per tile (aDesc %d, %d stages of %d K steps): issuer total %.0f | records %.0f, wait accEmpty %.0f, "
+                      "wait full %.0f, issue %.0f || builder total %.0f | wait records %.0f, wait empty %.0f, build %.0f || "
+                      "epilogue wait accFull %.0f, main %.0f\n",
+              tp.aDesc, tp.nStage, tp.slabKs, a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles, a[4] / tiles, a[8] / tiles,
+              a[9] / tiles, a[10] / tiles, a[11] / tiles, a[12] / tiles, a[13] / tiles);
+    }
+    if (usedTc) *usedTc = 1;
+    ctx->lastSelfKernel = 2;
+    return SGZ_OK;
+  }
+  SGZ_TRY(ws1.alloc((size_t)2 * ext));
+  k_self_wsums<<<ceil_div(ext, 128), 128, 0, ctx->stream>>>(p.x1, p.stride1, numCh, H, g.decim, ext, fp.shiftT, fp.shiftS,
+                                                           ws1.p);
+  SGZ_LAUNCH_CHECK(ctx);
+  fp.ws1 = ws1.p;
+  fp.ws2 = ws1.p;
+  if (cross) {
+    SGZ_TRY(ws2.alloc((size_t)2 * ext));
+    k_self_wsums<<<ceil_div(ext, 128), 128, 0, ctx->stream>>>(p.x2, p.stride2, numCh, H, g.decim, ext, fp.shiftT,
+                                                             fp.shiftS, ws2.p);
+    SGZ_LAUNCH_CHECK(ctx);
+    fp.ws2 = ws2.p;
+  }
+  k_self_gram<<<(unsigned)gt.size(), 256, 0, ctx->stream>>>(fp, dTiles.p);
+  SGZ_LAUNCH_CHECK(ctx);
+  SGZ_TRY(ctx->end_call());
+  ctx->lastSelfKernel = 1;
+  return SGZ_OK;
+}
+
 int sgz_self_run(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh, const float *norm, const void *frames1,
                  int64_t nFrames1, const void *frames2, int64_t nFrames2, int32_t layout, int32_t rowBegin,
                  int32_t rowEnd, int32_t *rgb, int64_t rgbCap, sgz_self_geometry *geom) {
@@ -197,7 +343,7 @@ int sgz_self_run(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh, const 
   SGZ_TRY(dRgb.alloc((size_t)ext * ext));
   SGZ_CUDA(cudaMemsetAsync(dRgb.p, 0, (size_t)ext * ext * sizeof(int32_t), ctx->stream));
   std::vector<int2> tiles;
-  if (cfg->precise) {
+  if (cfg->precise || H < 16) {
     for (int a0 = rowBegin / kSelfTile * kSelfTile; a0 < rowEnd; a0 += kSelfTile)
       for (int b0 = a0 / kSelfTile * kSelfTile; b0 < ext; b0 += kSelfTile) tiles.push_back(make_int2(a0, b0));
     SGZ_TRY(dTiles.alloc(tiles.size()));
@@ -206,45 +352,11 @@ int sgz_self_run(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh, const 
   p.colBegin = rowBegin;
   p.colEnd = rowEnd;
   p.rgb = dRgb.p;
-  if (!cfg->precise) {
-    // ---- fast path: centred FP32 Gram tiles + FP64 closed-form epilogue (selfsim_fast.cuh) ----
-    const int64_t need = (int64_t)g.numCorrs - 1 + H;
-    DevBuf<double> dMeans;
-    DevBuf<float2> ws1, ws2;
-    SGZ_TRY(dMeans.alloc(2));
-    SGZ_CUDA(cudaMemsetAsync(dMeans.p, 0, 2 * sizeof(double), ctx->stream));
-    SGZ_TRY(ctx->begin_call());
-    k_self_means<<<ctx->smCount * 4, 256, 0, ctx->stream>>>(p.x1, p.stride1, need, numCh, dMeans.p);
-    SGZ_LAUNCH_CHECK(ctx);
-    double means[2];
-    SGZ_CUDA(cudaMemcpyAsync(means, dMeans.p, sizeof means, cudaMemcpyDeviceToHost, ctx->stream));
-    SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
-    SelfFastParams fp{};
-    fp.base = p;
-    fp.shiftT = (float)(means[0] / (double)need);
-    fp.shiftS = (float)(means[1] / ((double)need * (numCh - 1)));
-    fp.cross = frames2 != nullptr;
-    SGZ_TRY(ws1.alloc((size_t)2 * ext));
-    k_self_wsums<<<ceil_div(ext, 128), 128, 0, ctx->stream>>>(p.x1, p.stride1, numCh, H, g.decim, ext, fp.shiftT, fp.shiftS,
-                                                             ws1.p);
-    SGZ_LAUNCH_CHECK(ctx);
-    fp.ws1 = ws1.p;
-    fp.ws2 = ws1.p;
-    if (frames2) {
-      SGZ_TRY(ws2.alloc((size_t)2 * ext));
-      k_self_wsums<<<ceil_div(ext, 128), 128, 0, ctx->stream>>>(p.x2, p.stride2, numCh, H, g.decim, ext, fp.shiftT,
-                                                               fp.shiftS, ws2.p);
-      SGZ_LAUNCH_CHECK(ctx);
-      fp.ws2 = ws2.p;
-    }
-    std::vector<int2> gt;
-    for (int a0 = rowBegin / kGT * kGT; a0 < rowEnd; a0 += kGT)
-      for (int b0 = a0; b0 < ext; b0 += kGT) gt.push_back(make_int2(a0, b0));
-    SGZ_TRY(dTiles.alloc(gt.size()));
-    SGZ_CUDA(cudaMemcpyAsync(dTiles.p, gt.data(), gt.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
-    k_self_gram<<<(unsigned)gt.size(), 256, 0, ctx->stream>>>(fp, dTiles.p);
-    SGZ_LAUNCH_CHECK(ctx);
-    SGZ_TRY(ctx->end_call());
+  // Very short windows (H < 16 frames) go to the exact path: the closed form cancels badly when a window's mean is far from
+  // the file mean relative to its own spread, and the exact replay costs O(H) per cell anyway.
+  const bool precise = cfg->precise || H < 16;
+  if (!precise) {
+    SGZ_TRY(self_fast_image(ctx, cfg, p, g, H, numCh, frames2 != nullptr, rowBegin, rowEnd, nullptr, nullptr));
     if (rgb) {
       SGZ_CUDA(cudaMemcpyAsync(rgb, dRgb.p, (size_t)ext * ext * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
       SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -258,6 +370,7 @@ int sgz_self_run(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh, const 
   k_self_tiles<<<(unsigned)tiles.size(), kSelfTile * kSelfTile, smem, ctx->stream>>>(p, dTiles.p);
   SGZ_LAUNCH_CHECK(ctx);
   SGZ_TRY(ctx->end_call());
+  ctx->lastSelfKernel = 3;
   if (rgb) {
     SGZ_CUDA(cudaMemcpyAsync(rgb, dRgb.p, (size_t)ext * ext * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -290,7 +403,7 @@ int sgz_self_cells(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh, cons
   SGZ_CUDA(cudaMemcpyAsync(dR.p, rightIdx, nCells * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
   p.leftIdx = dL.p; p.rightIdx = dR.p; p.nCells = nCells; p.simOut = dSim.p; p.rgbOut = dRgb.p;
   SGZ_TRY(ctx->begin_call());
-  if (cfg->precise) {
+  if (cfg->precise || H < 16) {
     k_self_cells<<<(unsigned)ceil_div<int64_t>(nCells, 128), 128, 0, ctx->stream>>>(p);
     SGZ_LAUNCH_CHECK(ctx);
   } else {
@@ -314,6 +427,36 @@ int sgz_self_cells(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh, cons
   if (sim) SGZ_CUDA(cudaMemcpyAsync(sim, dSim.p, nCells * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   if (rgb) SGZ_CUDA(cudaMemcpyAsync(rgb, dRgb.p, nCells * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (!cfg->precise && H >= 16 && g.imgExt <= 4096) {
+    // Images of this geometry come from the tile kernel (tensor cores when eligible): report ITS values for every cell
+    // of the computed triangle, so that the parity checks on cells exercise the kernel that renders the image.
+    const int ext = g.imgExt;
+    DevBuf<int32_t> dImg;
+    DevBuf<float> dMat;
+    SGZ_TRY(dImg.alloc((size_t)ext * ext));
+    SGZ_TRY(dMat.alloc((size_t)ext * ext));
+    p.colBegin = 0;
+    p.colEnd = ext;
+    p.rgb = dImg.p;
+    int usedTc = 0;
+    SGZ_TRY(self_fast_image(ctx, cfg, p, g, H, numCh, frames2 != nullptr, 0, ext, dMat.p, &usedTc));
+    if (usedTc) {
+      std::vector<float> hm((size_t)ext * ext);
+      std::vector<int32_t> hi((size_t)ext * ext);
+      SGZ_CUDA(cudaMemcpyAsync(hm.data(), dMat.p, hm.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+      SGZ_CUDA(cudaMemcpyAsync(hi.data(), dImg.p, hi.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+      for (int64_t k = 0; k < nCells; k++) {
+        int l = leftIdx[k], r = rightIdx[k];
+        if (l > r) {
+          if (frames2) continue;          // cross mode: the image holds (left <= right) only
+          std::swap(l, r);
+        }
+        if (sim) sim[k] = hm[(size_t)l * ext + r];
+        if (rgb) rgb[k] = hi[(size_t)(ext - 1 - r) * ext + l];
+      }
+    }
+  }
   return SGZ_OK;
 }
 

@@ -124,6 +124,7 @@ struct sgz_ctx {
   int64_t callLaunches0 = 0;   // snapshot at begin_call
   float lastMs = 0.f;
   int64_t lastLaunches = 0;
+  int lastSelfKernel = 0;      // which kernel rendered the last SelfSimilarity image (sgz_self_last_kernel)
 
   int bind() const {
     SGZ_CUDA(cudaSetDevice(device));

@@ -1,0 +1,487 @@
+// selfsim_tc.cuh -- K4 on the tensor cores (tcgen05 / TMEM): the SelfSimilarity Gram matrix of selfsim_fast.cuh with
+// split-FP16 operands.
+//
+//   G[a][b] = sum_c sum_h x1[c][d a + h] * x2[c][d b + h]      (closed form of MathUtil.correlateHalf, SURVEY.md 3.3;
+//                                                               SelfSimilarityImpl.scala:127-155)
+// per 128 x 128 cell tile of the upper triangle: M = 128 windows of file 1, N = 128 windows of file 2, K = channels x H.
+// Precision: the centred data are scaled by a power of two into the FP16 range and split into two FP16 numbers
+// (22 significant bits), a*b = a1*b1 + (a2*b1 + a1*b2).  The tensor core truncates when it aligns addends, so the number
+// of accumulations into a LARGE accumulator bounds the bias: the main products of the spectral group get their own TMEM
+// region (6 x 13 = 78 MMAs at H = 86), the small correction products another, the temporal group (18 MMAs) a third.
+//
+// Operands are windows of ONE signal (Hankel matrices), so nothing is materialised in global memory except a "record"
+// array R[part][c][rho] = the 8 FP16 values of frames g rho .. g rho + 7 (g = gcd(decim, 8)): any 16-byte chunk
+// (window a, k = 8 kc .. 8 kc + 7) of an operand tile is then ONE aligned record, rho = (decim / g) a + (8 / g) kc.
+// Per (tile, channel) the few KB of records both operands need arrive by bulk copy; 7 builder warps expand them into
+// no-swizzle K-major core matrices (one LDS.128 + one STS.128 per chunk, conflict free), zeroing k >= H, in a ring of
+// slabs of two K steps; one issuer warp (elected lane) feeds tcgen05.mma M128 x N128 x K16 (kind::f16, FP32
+// accumulate); 8 epilogue warps read TMEM, apply the closed form with the FP64-accumulated window sums, blend, map to
+// a colour and store the pixel and its mirror (the mirror goes through a small shared-memory transpose so that both
+// stores are coalesced).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "corr_tc.cuh"
+#include "selfsim_fast.cuh"
+
+namespace sgz {
+
+constexpr int kSgBuildWarps = 7, kSgEpiWarps = 8;
+constexpr int kSgThreads = (kSgBuildWarps + 1 + kSgEpiWarps) * 32;   // 512: the register file is handed out per 4 warps
+constexpr int kSgPPitch = 17;                                        // transpose buffer: 32 rows x 16 pixels, padded
+
+struct SelfTcGeom {
+  int H, nks, nSlab, slabKs;  // K steps of 16; a ring stage ("slab") holds slabKs of them
+  int g, dp, kcStep, span;    // record grid (see above); span = records one operand stage holds
+  int nStage;                 // ring depth (slabs)
+  int aDesc;                  // decim | 8: A is read in place from the record stage, the ring holds B only
+  uint32_t matBytes, stageBytes;
+  uint32_t recPartBytes, recStageBytes;
+  size_t smemBytes;
+  bool ok;
+};
+
+inline SelfTcGeom self_tc_geom(int H, int decim, size_t smemLimit, bool allowADesc) {
+  SelfTcGeom G{};
+  G.H = H;
+  G.nks = (H + 15) / 16;
+  G.g = decim & -decim;
+  if (G.g > 8) G.g = 8;
+  G.dp = decim / G.g;
+  G.kcStep = 8 / G.g;
+  G.span = G.dp * 127 + G.kcStep * (2 * G.nks - 1) + 1;
+  G.recPartBytes = (uint32_t)G.span * 16u;
+  G.recStageBytes = (4u * G.recPartBytes + 127u) / 128u * 128u;
+  G.aDesc = allowADesc && G.dp == 1;
+  G.ok = false;
+  const size_t fixed = 2 * (size_t)G.recStageBytes + (size_t)kSgEpiWarps * 32 * kSgPPitch * 4 + 128 * 16 + 256 + 1024;
+  // large stages mean few barrier round trips and fences; at least 3 stages if they fit, else smaller slabs
+  for (int ks = std::min(G.nks, G.aDesc ? 8 : 4); ks >= 1 && !G.ok; ks = ks > 2 ? ks - 1 : ks - 1) {
+    const uint32_t matBytes = (uint32_t)ks * 4096u, stageBytes = (G.aDesc ? 2u : 4u) * matBytes;
+    for (int ns = 4; ns >= (ks > 2 ? 3 : 2); ns--) {
+      if (fixed + (size_t)ns * stageBytes <= smemLimit) {
+        G.slabKs = ks; G.nSlab = (G.nks + ks - 1) / ks; G.nStage = ns;
+        G.matBytes = matBytes; G.stageBytes = stageBytes;
+        G.smemBytes = fixed + (size_t)ns * stageBytes;
+        G.ok = true;
+        break;
+      }
+    }
+  }
+  return G;
+}
+
+struct SelfTcParams {
+  SelfFastParams f;          // geometry, colours, rgb, shifts; ws1 / ws2 are NOT used (the scaled sums below are)
+  const uint4 *rec1, *rec2;  // records [part][channel][nRec] of file 1 / file 2
+  int64_t nRec;
+  const float4 *wsA, *wsB;   // per window (S_T, Q_T, S_S, Q_S) of the scaled centred data (file 1 / file 2)
+  const int2 *tiles;
+  int nTiles;
+  int nks, nSlab, slabKs, dp, kcStep, span, nStage;
+  uint32_t matBytes, stageBytes, recPartBytes, recStageBytes;
+  float *simMat;             // optional [imgExt][imgExt] raw sims at (a, b >= a) (parity checks), or nullptr
+  int aDesc;                 // decim | 8: the A operand is read straight from the record stage (see the issuer)
+  long long *prof;           // developer probe (SGZ_SELF_TC_PROF): per CTA 16 cycle counters, or nullptr
+};
+
+// max |x| per group (as float bits; |NaN| compares above everything) next to the means of k_self_means
+__global__ void k_self_absmax(const float *__restrict__ x, int64_t stride, int64_t n, int numCh, unsigned int *out) {
+  unsigned int mT = 0, mS = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    mT = max(mT, __float_as_uint(x[i]) & 0x7fffffffu);
+    for (int c = 1; c < numCh; c++) mS = max(mS, __float_as_uint(x[(int64_t)c * stride + i]) & 0x7fffffffu);
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    mT = max(mT, __shfl_xor_sync(0xffffffffu, mT, d));
+    mS = max(mS, __shfl_xor_sync(0xffffffffu, mS, d));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMax(out, mT); atomicMax(out + 1, mS); }
+}
+
+// records: rec[part][c][rho] = FP16 first / second part of scale * (x[c][g rho + j] - shift_group), j = 0..7; zero past nValid
+__global__ void k_self_records(const float *__restrict__ x, int64_t stride, int64_t nValid, int numCh, int g, int64_t nRec,
+                               float shiftT, float shiftS, float scale, uint4 *__restrict__ rec) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)numCh * nRec) return;
+  const int c = (int)(idx / nRec);
+  const int64_t rho = idx - (int64_t)c * nRec;
+  const float sh = c == 0 ? shiftT : shiftS;
+  __half hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int64_t fr = (int64_t)g * rho + j;
+    const float v = fr < nValid ? __fmul_rn(__fsub_rn(x[(int64_t)c * stride + fr], sh), scale) : 0.f;
+    hi[j] = __float2half_rn(v);
+    lo[j] = __float2half_rn(v - __half2float(hi[j]));
+  }
+  rec[idx] = *reinterpret_cast<const uint4 *>(hi);
+  rec[(int64_t)numCh * nRec + idx] = *reinterpret_cast<const uint4 *>(lo);
+}
+
+// (S, Q) of every decimated window of the scaled centred data, FP64 accumulation, both groups in one float4
+__global__ void k_self_wsums4(const float *__restrict__ x, int64_t stride, int numCh, int H, int decim, int imgExt,
+                              float shiftT, float shiftS, float scale, float4 *__restrict__ ws) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= imgExt) return;
+  const int64_t f0 = (int64_t)decim * a;
+  double s = 0, q = 0;
+  for (int h = 0; h < H; h++) { const double v = (double)__fmul_rn(__fsub_rn(x[f0 + h], shiftT), scale); s += v; q += v * v; }
+  float4 o;
+  o.x = (float)s; o.y = (float)q;
+  s = 0; q = 0;
+  for (int c = 1; c < numCh; c++)
+    for (int h = 0; h < H; h++) {
+      const double v = (double)__fmul_rn(__fsub_rn(x[(int64_t)c * stride + f0 + h], shiftS), scale);
+      s += v; q += v * v;
+    }
+  o.z = (float)s; o.w = (float)q;
+  ws[a] = o;
+}
+
+// no-swizzle K-major operand: rows of a core matrix 16 B apart, 8-row groups SBO apart, the two 8-element K chunks of
+// one K step LBO apart
+__device__ __forceinline__ uint64_t sg_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void sg_epi_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+
+__device__ __forceinline__ float sg_coeff(float G, float Sa, float Qa, float Sb, float Qb, float inv4N) {
+  const float S = Sa + Sb;
+  const float T = S * S * inv4N;
+  const float den = fmaf(0.5f, Qa + Qb, -T);
+  return __fdividef(G - T, den);   // 0/0 -> NaN like the reference (constant windows)
+}
+
+// the same with halved sums of squares: hQ = Q / 2
+__device__ __forceinline__ float sg_coeff_h(float G, float Sa, float hQa, float Sb, float hQb, float inv4N) {
+  const float S = Sa + Sb;
+  const float t1 = S * inv4N;
+  const float den = fmaf(-t1, S, hQa + hQb);
+  return __fdividef(fmaf(-t1, S, G), den);   // 0/0 -> NaN like the reference (constant windows)
+}
+
+// GrayScale with colorWarp = 1 without FP64: clamp(floor(s * 255 + 0.5), 0, 255) computed exactly -- s * 255 = k + fr with
+// k = trunc, fr = exact remainder, so the reference's (int)((double) f + 0.5) is k + (fr >= 0.5); NaN -> 0 like d2i_java
+__device__ __forceinline__ int32_t sg_grey(float sim, float colorScale, int colorInv) {
+  const float v = __fmul_rn(fmaxf(sim, 0.f), colorScale);
+  const float s = colorInv ? __fsub_rn(1.0f, v) : v;
+  const float f = fminf(fmaxf(__fmul_rn(s, 255.0f), 0.f), 256.f);
+  int k = __float2int_rz(f);
+  k += (f - (float)k) >= 0.5f ? 1 : 0;
+  k = (sim != sim) ? 0 : min(k, 255);
+  return k * 0x010101;
+}
+
+// colour of one cell; identical to self_color() except that pow(m, 1.0) is skipped (it returns m exactly)
+__device__ __forceinline__ int32_t sg_color(const SelfParams &p, float sim, bool warpOne) {
+  if (!warpOne || p.lut != nullptr) return self_color(p, sim);
+  float m = (sim != sim) ? sim : fmaxf(0.0f, sim);
+  if (sim == 0.0f) m = 0.0f;
+  const float v = __fmul_rn(m, p.colorScale);
+  const float s = p.colorInv ? __fsub_rn(1.0f, v) : v;
+  int32_t i = d2i_java(__dadd_rn((double)__fmul_rn(s, 255.0f), 0.5));
+  i = max(0, min(255, i));
+  return i * 0x010101;
+}
+
+__global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcParams p) {
+  extern __shared__ __align__(1024) unsigned char smemRaw[];
+  const SelfParams &b = p.f.base;
+  unsigned char *base = smemRaw + ((1024 - (smem_u32(smemRaw) & 1023)) & 1023);
+  unsigned char *ring = base;                                               // [nStage][mats][2 slabKs chunks][128 rows][16 B]
+  unsigned char *recBase = ring + (size_t)p.nStage * p.stageBytes;          // [2][A1, A2, B1, B2][span] records
+  int32_t *P = reinterpret_cast<int32_t *>(recBase + 2 * (size_t)p.recStageBytes);   // [8 warps][32][17]
+  float4 *colW = reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(P) + (size_t)kSgEpiWarps * 32 * kSgPPitch * 4);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(colW) + 128 * 16);
+  uint64_t *full = bars, *empty = bars + 4, *recFull = bars + 8, *recEmpty = bars + 10, *accFull = bars + 12,
+           *accEmpty = bars + 13;
+  uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(bars + 14);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < 4; s++) { mbar_init(full + s, kSgBuildWarps); mbar_init(empty + s, 1); }
+    mbar_init(recFull, 1); mbar_init(recFull + 1, 1);
+    mbar_init(recEmpty, kSgBuildWarps + (p.aDesc ? 1 : 0)); mbar_init(recEmpty + 1, kSgBuildWarps + (p.aDesc ? 1 : 0));
+    mbar_init(accFull, 1);
+    mbar_init(accEmpty, kSgEpiWarps);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmemSlot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = *tmemSlot;
+
+  const bool useT = b.weight > 0.f, useS = b.weight < 1.f;
+  const int cBegin = useT ? 0 : 1, cEnd = useS ? b.numCh : 1;
+  const int H = b.H;
+  const int firstMat = p.aDesc ? 2 : 0;                 // ring stages hold [A1, A2, B1, B2] or, with aDesc, [B1, B2]
+  const uint32_t matUnits = p.matBytes / 16;
+
+  if (warp < kSgBuildWarps) {
+    // =========================== builders ===========================
+    uint32_t slabCtr = 0, chCtr = 0;
+    long long bRec = 0, bEmpty = 0, bBuild = 0, bTot = clock64(), tB;
+    for (int t = blockIdx.x; t < p.nTiles; t += gridDim.x) {
+      for (int c = cBegin; c < cEnd; c++, chCtr++) {
+        const int rs = chCtr & 1;
+        tB = clock64();
+        tc_wait(recFull + rs, (chCtr >> 1) & 1);
+        bRec += clock64() - tB;
+        const uint4 *recS = reinterpret_cast<const uint4 *>(recBase + (size_t)rs * p.recStageBytes);
+        for (int slab = 0; slab < p.nSlab; slab++, slabCtr++) {
+          const int st = slabCtr % p.nStage;
+          const uint32_t use = slabCtr / p.nStage;
+          tB = clock64();
+          if (use > 0) tc_wait(empty + st, (use - 1) & 1);   // the MMAs that read this stage are done
+          bEmpty += clock64() - tB; tB = clock64();
+          uint4 *dstS = reinterpret_cast<uint4 *>(ring + (size_t)st * p.stageBytes);
+          const int kc0 = 2 * p.slabKs * slab;
+          const int nkcl = 2 * min(p.slabKs, p.nks - p.slabKs * slab);     // 8-element chunks of this stage
+          const int nPairs = (4 - firstMat) * nkcl;                       // (operand part, chunk) pairs x 4 row groups
+          // one pair per step and warp: the four row groups are four independent 16-byte copies per lane
+          for (int pi = warp; pi < nPairs; pi += kSgBuildWarps) {
+            int mi = 0, kcl = pi;
+            while (kcl >= nkcl) { kcl -= nkcl; mi++; }
+            const int kc = kc0 + kcl;
+            const uint4 *src = recS + (size_t)(firstMat + mi) * p.span + (size_t)p.kcStep * kc + (size_t)p.dp * lane;
+            uint4 *dst = dstS + (size_t)mi * matUnits + (size_t)kcl * 128 + lane;
+            const int step = 32 * p.dp;
+            uint4 v0 = src[0], v1 = src[step], v2 = src[2 * step], v3 = src[3 * step];
+            const int nv = H - 8 * kc;                       // valid k of this chunk; beyond H the window has ended
+            if (nv < 8) {
+              const uint32_t mx = nv >= 2 ? 0xffffffffu : (nv == 1 ? 0xffffu : 0u), my = nv >= 4 ? 0xffffffffu : (nv == 3 ? 0xffffu : 0u);
+              const uint32_t mz = nv >= 6 ? 0xffffffffu : (nv == 5 ? 0xffffu : 0u), mw = nv == 7 ? 0xffffu : 0u;
+              v0.x &= mx; v0.y &= my; v0.z &= mz; v0.w &= mw;
+              v1.x &= mx; v1.y &= my; v1.z &= mz; v1.w &= mw;
+              v2.x &= mx; v2.y &= my; v2.z &= mz; v2.w &= mw;
+              v3.x &= mx; v3.y &= my; v3.z &= mz; v3.w &= mw;
+            }
+            dst[0] = v0; dst[32] = v1; dst[64] = v2; dst[96] = v3;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (MMA)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full + st);
+          bBuild += clock64() - tB;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(recEmpty + rs);
+      }
+    }
+    if (p.prof && tid == 0) {
+      long long *o = p.prof + 16 * blockIdx.x + 8;
+      o[0] = clock64() - bTot; o[1] = bRec; o[2] = bEmpty; o[3] = bBuild;
+    }
+  } else if (warp == kSgBuildWarps) {
+    // =========================== record producer + MMA issuer ===========================
+    // D = F32, A = B = F16, both K-major, M = 128, N = 128
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const int64_t chanRecs = p.nRec, partRecs = (int64_t)b.numCh * p.nRec;
+    auto request = [&](int rs, int t, int c) {   // the records both operands of (tile t, channel c) need
+      if (tc_elect()) {
+        const int2 tl = p.tiles[t];
+        unsigned char *dst = recBase + (size_t)rs * p.recStageBytes;
+        mbar_expect_tx(recFull + rs, 4u * p.recPartBytes);
+        const uint4 *a0 = p.rec1 + (int64_t)c * chanRecs + (int64_t)p.dp * tl.x;
+        const uint4 *b0 = p.rec2 + (int64_t)c * chanRecs + (int64_t)p.dp * tl.y;
+        bulk_g2s(dst, a0, p.recPartBytes, recFull + rs);
+        bulk_g2s(dst + p.recPartBytes, a0 + partRecs, p.recPartBytes, recFull + rs);
+        bulk_g2s(dst + 2 * p.recPartBytes, b0, p.recPartBytes, recFull + rs);
+        bulk_g2s(dst + 3 * p.recPartBytes, b0 + partRecs, p.recPartBytes, recFull + rs);
+      }
+      __syncwarp();
+    };
+    uint32_t slabCtr = 0, chCtr = 0, tileIt = 0;
+    long long iRec = 0, iAcc = 0, iFull = 0, iIssue = 0, iTot = clock64(), tI;
+    for (int t = blockIdx.x; t < p.nTiles; t += gridDim.x, tileIt++) {
+      for (int c = cBegin; c < cEnd; c++, chCtr++) {
+        tI = clock64();
+        if (chCtr == 0) request(0, t, c);
+        {   // records of the next (tile, channel), one channel ahead
+          const bool lastC = c + 1 == cEnd;
+          const int nt = lastC ? t + (int)gridDim.x : t, nc = lastC ? cBegin : c + 1;
+          if (nt < p.nTiles) {
+            const uint32_t n = chCtr + 1;
+            if (n >= 2) tc_wait<false>(recEmpty + (n & 1), ((n >> 1) - 1) & 1);
+            request((int)(n & 1), nt, nc);
+          }
+        }
+        iRec += clock64() - tI; tI = clock64();
+        if (c == cBegin && tileIt > 0) tc_wait<false>(accEmpty, (tileIt - 1) & 1);   // the epilogue has drained TMEM
+        iAcc += clock64() - tI;
+        const uint32_t dMain = tmem + (c == 0 ? 0u : 128u), dCorr = tmem + (c == 0 ? 0u : 256u);
+        for (int slab = 0; slab < p.nSlab; slab++, slabCtr++) {
+          const int st = slabCtr % p.nStage;
+          const uint32_t use = slabCtr / p.nStage;
+          tI = clock64();
+          tc_wait<false>(full + st, use & 1);
+          iFull += clock64() - tI; tI = clock64();
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          if (tc_elect()) {
+            const uint32_t sb = smem_u32(ring + (size_t)st * p.stageBytes);
+            const int nksHere = min(p.slabKs, p.nks - p.slabKs * slab);
+            for (int ks = 0; ks < nksHere; ks++) {
+              const uint32_t o = (uint32_t)ks * 2u * 2048u;
+              uint64_t a1, a2, b1, b2;
+              if (p.aDesc) {
+                // decim | 8: a window starts every record (dp = 1), so the 8 rows of a core matrix ARE 8 consecutive
+                // records (16 B apart), row groups are 128 B apart and chunk kc of a row lies kcStep records further:
+                // the record stage itself is the K-major operand, with overlapping core matrices (LBO = kcStep * 16 B)
+                const uint32_t ra = smem_u32(recBase + (size_t)(chCtr & 1) * p.recStageBytes) +
+                                    (uint32_t)(p.slabKs * slab + ks) * 2u * (uint32_t)p.kcStep * 16u;
+                a1 = sg_desc(ra, (uint32_t)p.kcStep * 16u, 128);
+                a2 = sg_desc(ra + p.recPartBytes, (uint32_t)p.kcStep * 16u, 128);
+                b1 = sg_desc(sb + o, 2048, 128);
+                b2 = sg_desc(sb + p.matBytes + o, 2048, 128);
+              } else {
+                a1 = sg_desc(sb + o, 2048, 128);
+                a2 = sg_desc(sb + p.matBytes + o, 2048, 128);
+                b1 = sg_desc(sb + 2 * p.matBytes + o, 2048, 128);
+                b2 = sg_desc(sb + 3 * p.matBytes + o, 2048, 128);
+              }
+              const bool first = slab == 0 && ks == 0 && (c == 0 || c == 1);   // first MMA into this group's regions
+              tc_mma(dMain, a1, b1, idesc, !first);
+              tc_mma(dCorr, a2, b1, idesc, c == 0 ? 1u : !first);
+              tc_mma(dCorr, a1, b2, idesc, 1);
+            }
+            tc_commit(empty + st);
+            if (p.aDesc && slab + 1 == p.nSlab) tc_commit(recEmpty + (chCtr & 1));   // the MMAs read the record stage
+            if (c + 1 == cEnd && slab + 1 == p.nSlab) tc_commit(accFull);
+          }
+          __syncwarp();
+          iIssue += clock64() - tI;
+        }
+      }
+    }
+    if (p.prof && lane == 0) {
+      long long *o = p.prof + 16 * blockIdx.x;
+      o[0] = clock64() - iTot; o[1] = iRec; o[2] = iAcc; o[3] = iFull; o[4] = iIssue; o[5] = tileIt;
+    }
+  } else {
+    // =========================== epilogue ===========================
+    // warp -> TMEM lane quarter (rows of the tile) and column half; thread = one row a, 64 columns in batches of 16
+    const int ew = warp - (kSgBuildWarps + 1), quarter = warp & 3, half = ew >> 2, et = ew * 32 + lane;
+    int32_t *Pw = P + (size_t)ew * 32 * kSgPPitch;
+    const int ext = b.imgExt;
+    const float invNT = (float)(1.0 / (4.0 * (double)H)), invNS = (float)(1.0 / (4.0 * (double)(b.numCh - 1) * (double)H));
+    const bool warpOne = b.colorWarp == 1.0f;
+    const float wT = b.weight, wS = __fsub_rn(1.0f, b.weight);
+    uint32_t tileIt = 0;
+    long long eAcc = 0, eMain = 0, tE;
+    for (int t = blockIdx.x; t < p.nTiles; t += gridDim.x, tileIt++) {
+      const int2 tl = p.tiles[t];
+      const int ta = tl.x, tb = tl.y;
+      sg_epi_sync();                                       // everybody is done with the previous tile's column sums
+      if (et < 128) {                                      // column sums as (S_T, Q_T / 2, S_S, Q_S / 2)
+        float4 w = tb + et < ext ? p.wsB[tb + et] : make_float4(0.f, 0.f, 0.f, 0.f);
+        w.y *= 0.5f; w.w *= 0.5f;
+        colW[et] = w;
+      }
+      sg_epi_sync();
+      const int a = ta + quarter * 32 + lane;
+      float4 wa = a < ext ? p.wsA[a] : make_float4(0.f, 0.f, 0.f, 0.f);
+      wa.y *= 0.5f; wa.w *= 0.5f;
+      const bool rowOk = a < ext && a >= b.colBegin && a < b.colEnd;
+      // interior tile (all 128 x 128 cells exist, strictly above the diagonal) with the plain grey scale: no per-cell
+      // predicates, 32-bit pixel offsets (imgExt <= 0xB504, so imgExt^2 < 2^31)
+      const bool fast = ta + 128 <= ext && tb + 128 <= ext && tb >= ta + 128 && ta >= b.colBegin && ta + 128 <= b.colEnd &&
+                        warpOne && b.lut == nullptr && p.simMat == nullptr;
+      tE = clock64();
+      tc_wait(accFull, tileIt & 1);
+      eAcc += clock64() - tE; tE = clock64();
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      const uint32_t laneAddr = tmem + ((uint32_t)(quarter * 32) << 16) + 64u * (uint32_t)half;
+#pragma unroll 1
+      for (int bt = 0; bt < 4; bt++) {
+        uint32_t uT[16], uM[16], uC[16];
+        if (useT) tc_ld16_nowait(laneAddr + 16u * bt, uT);
+        if (useS) {
+          tc_ld16_nowait(laneAddr + 128u + 16u * bt, uM);
+          tc_ld16_nowait(laneAddr + 256u + 16u * bt, uC);
+        }
+        tc_ld_wait();
+        if (bt == 3) {   // all accumulators of this warp are in registers: hand TMEM back to the issuer
+          asm volatile("tcgen05.fence::before_thread_sync;");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(accEmpty);
+        }
+        const int c0 = tb + 64 * half + 16 * bt;
+        const float4 *cw = colW + 64 * half + 16 * bt;
+        int32_t colr[16];
+        if (fast) {
+          // pass 1: 16 independent cells in registers
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            const float4 wb = cw[i];
+            float temporal = 0.f, spectral = 0.f;
+            if (useT) temporal = sg_coeff_h(__uint_as_float(uT[i]), wa.x, wa.y, wb.x, wb.y, invNT);
+            if (useS) spectral = sg_coeff_h(__uint_as_float(uM[i]) + __uint_as_float(uC[i]), wa.z, wa.w, wb.z, wb.w, invNS);
+            const float sim = __fadd_rn(__fmul_rn(temporal, wT), __fmul_rn(spectral, wS));
+            colr[i] = sg_grey(sim, b.colorScale, b.colorInv);
+          }
+          // pass 2: the pixel (image row ext-1-c, x = a: coalesced over the lanes) and the transpose buffer
+          const uint32_t offD = (uint32_t)(ext - 1 - c0) * (uint32_t)ext + (uint32_t)a;
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            Pw[lane * kSgPPitch + i] = colr[i];
+            b.rgb[offD - (uint32_t)i * (uint32_t)ext] = colr[i];
+          }
+          __syncwarp();
+          // the mirrored pixels: image row ext-1-a', x = c: 16 consecutive pixels per row of this batch
+          int32_t m[16];
+#pragma unroll
+          for (int it = 0; it < 16; it++) m[it] = Pw[(2 * it + (lane >> 4)) * kSgPPitch + (lane & 15)];
+          const uint32_t offM = (uint32_t)(ext - 1 - (ta + quarter * 32 + (lane >> 4))) * (uint32_t)ext + (uint32_t)(c0 + (lane & 15));
+#pragma unroll
+          for (int it = 0; it < 16; it++) b.rgb[offM - (uint32_t)(2 * it) * (uint32_t)ext] = m[it];
+          __syncwarp();
+          continue;
+        }
+        // generic path: image edges, the diagonal, colour tables, colorWarp != 1, sim matrix output
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const float4 wb = cw[i];
+          float temporal = 0.f, spectral = 0.f;
+          if (useT) temporal = sg_coeff_h(__uint_as_float(uT[i]), wa.x, wa.y, wb.x, wb.y, invNT);
+          if (useS) spectral = sg_coeff_h(__uint_as_float(uM[i]) + __uint_as_float(uC[i]), wa.z, wa.w, wb.z, wb.w, invNS);
+          const float sim = __fadd_rn(__fmul_rn(temporal, wT), __fmul_rn(spectral, wS));
+          colr[i] = sg_color(b, sim, warpOne);
+          if (p.simMat && rowOk && c0 + i < ext && c0 + i >= a) p.simMat[(int64_t)a * ext + c0 + i] = sim;
+        }
+        int32_t *row0 = b.rgb + (int64_t)(ext - 1 - c0) * ext + a;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          Pw[lane * kSgPPitch + i] = colr[i];
+          if (rowOk && c0 + i < ext && c0 + i >= a) row0[-(int64_t)i * ext] = colr[i];   // upper triangle only
+        }
+        __syncwarp();
+        {
+          const int a2 = ta + quarter * 32 + (lane >> 4), c2 = c0 + (lane & 15);
+          int32_t *mrow = b.rgb + (int64_t)(ext - 1 - a2) * ext + c2;
+#pragma unroll 4
+          for (int it = 0; it < 16; it++) {
+            const int a3 = a2 + 2 * it;
+            const int32_t mv = Pw[(2 * it + (lane >> 4)) * kSgPPitch + (lane & 15)];
+            if (a3 < ext && a3 >= b.colBegin && a3 < b.colEnd && c2 < ext && c2 >= a3) mrow[-(int64_t)(2 * it) * ext] = mv;
+          }
+        }
+        __syncwarp();
+      }
+      eMain += clock64() - tE;
+    }
+    if (p.prof && et == 0) {
+      long long *o = p.prof + 16 * blockIdx.x + 12;
+      o[0] = eAcc; o[1] = eMain;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+}  // namespace sgz

@@ -298,6 +298,14 @@ def self_geometry(cfg: N.SelfConfig, n1: int, n2: int) -> dict:
     return dict(imgExt=g.imgExt, decim=g.decim, numCorrs=g.numCorrs, afStart=g.afStart, numCells=g.numCells)
 
 
+SELF_KERNELS = {0: "none", 1: "ffma2_gram", 2: "tc_gram", 3: "fp64_replay"}
+
+
+def self_last_kernel(ctx: Context) -> str:
+    """Which kernel rendered the last SelfSimilarity image of this context (sgz_self_last_kernel)."""
+    return SELF_KERNELS[int(N.lib().sgz_self_last_kernel(ctx._h))]
+
+
 def self_run(ctx: Context, cfg: N.SelfConfig, frames1: np.ndarray, frames2: Optional[np.ndarray] = None,
              norm: Optional[np.ndarray] = None, col_begin: int = 0, col_end: int = 0, download: bool = True):
     a1 = _frames(frames1)

@@ -200,9 +200,15 @@ def test_selfsimilarity_image_identical(ctx, decim, weight, warp, ceil, inv, cro
 @pytest.mark.parametrize("frames,corr_len,decim,weight,warp,inv,cross", [
     (900, 44100, 1, 0.5, 1.0, False, False), (1500, 20480, 3, 0.3, 1.0, True, False), (700, 44100, 2, 1.0, 0.5, False, True),
     (650, 10240, 1, 0.0, 1.0, False, False),
+    # record grids of the tensor-core kernel: g = gcd(decim, 8), window stride decim / g records (odd strides, strides of
+    # 8 frames and more), an H that is a multiple of 16, an H of exactly one K step
+    (2300, 44100, 4, 0.5, 1.0, False, False), (3300, 44100, 7, 0.5, 1.0, False, True), (3600, 16384, 8, 0.25, 1.0, False, False),
+    (2500, 44100, 5, 0.5, 1.0, True, False), (1900, 44100, 6, 0.7, 1.0, False, False), (700, 8192, 1, 0.5, 1.0, False, False),
+    (6000, 44100, 16, 0.5, 1.0, False, False),
 ])
 def test_selfsimilarity_fast_gram_within_tolerance(ctx, frames, corr_len, decim, weight, warp, inv, cross):
-    """default (fast) path: FP32 Gram tiles + FP64 closed form: sims within 1e-5 relative, grey level within 1 LSB"""
+    """default (fast) path: Gram tiles (tensor cores, split FP16) + closed form with FP64-accumulated window sums: sims
+    within 1e-5 relative, grey level within 1 LSB"""
     from strugatzki_b200 import engine
     f1, _ = synth.regime_file(synth.BASE_SEED, 16, frames, 14, 6)
     f2 = synth.regime_file(synth.BASE_SEED, 17, frames - 30, 14, 5)[0] if cross else None
@@ -212,6 +218,7 @@ def test_selfsimilarity_fast_gram_within_tolerance(ctx, frames, corr_len, decim,
     want = O.self_image(op, f1, f2)
     cfg = N.SelfConfig(STEP, 0, 0, 0, 0, corr_len, decim, weight, int(inv), warp, 1.0, None, 0, 0)   # precise = 0
     got, g = engine.self_run(ctx, cfg, f1, f2, norm)
+    assert engine.self_last_kernel(ctx) == "tc_gram"                           # no silent fall-back to the FFMA2 kernel
     assert got.shape == want.shape and g["imgExt"] == want.shape[0] > 128      # several 128 x 128 tiles
     assert np.array_equal(got, got[::-1, ::-1].T)                              # mirrored like the reference
     dg = np.abs((got & 0xFF).astype(np.int64) - (want & 0xFF).astype(np.int64))

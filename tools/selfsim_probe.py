@@ -19,4 +19,4 @@ for rep in range(2):
     wall = time.time() - t
     ms, launches = ctx.last_timing()
     print(json.dumps(dict(frames=frames, imgExt=g["imgExt"], decim=g["decim"], cells=g["numCells"], kernel_ms=round(ms, 2),
-                          wall_ms=round(wall * 1e3, 1), cells_per_s=round(g["numCells"] / (ms * 1e-3), 1))), flush=True)
+                          wall_ms=round(wall * 1e3, 1), cells_per_s=round(g["numCells"] / (ms * 1e-3), 1), kernel=engine.self_last_kernel(ctx))), flush=True)
