@@ -269,34 +269,54 @@ static int self_fast_image(sgz_ctx *ctx, const sgz_self_config *cfg, sgz::SelfPa
     tp.tiles = dTiles.p;
     tp.nTiles = (int)gt.size();
     tp.nks = G.nks; tp.nSlab = G.nSlab; tp.slabKs = G.slabKs; tp.dp = G.dp; tp.kcStep = G.kcStep; tp.span = G.span;
-    tp.nStage = G.nStage; tp.matBytes = G.matBytes; tp.stageBytes = G.stageBytes;
+    tp.nStage = G.nStage; tp.nRecStage = G.nRecStage; tp.matBytes = G.matBytes; tp.stageBytes = G.stageBytes;
     tp.recPartBytes = G.recPartBytes; tp.recStageBytes = G.recStageBytes;
     tp.simMat = simMat;
     tp.aDesc = G.aDesc;
-    SGZ_CUDA(cudaFuncSetAttribute(k_self_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));
+    SGZ_CUDA(cudaFuncSetAttribute(k_self_gram_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));
+    SGZ_CUDA(cudaFuncSetAttribute(k_self_gram_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));
+    SGZ_CUDA(cudaFuncSetAttribute(k_self_gram_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));
     const unsigned gridTc = (unsigned)std::min<size_t>(gt.size(), (size_t)ctx->smCount);
     DevBuf<long long> dProf;
+    DevBuf<float> dCorrT;
     const bool prof = getenv("SGZ_SELF_TC_PROF") != nullptr;   // developer probe: cycles per role
-    if (prof) {
-      SGZ_TRY(dProf.alloc((size_t)gridTc * 16));
-      SGZ_CUDA(cudaMemsetAsync(dProf.p, 0, (size_t)gridTc * 16 * sizeof(long long), ctx->stream));
-      tp.prof = dProf.p;
+    // both groups in play: temporal pass -> corrT, then the spectral pass (see SelfTcParams); SGZ_SELF_TC_PASSES=1 keeps
+    // the one-launch form (three TMEM regions per tile, epilogue not overlapped)
+    static const bool onePass = getenv("SGZ_SELF_TC_PASSES") && atoi(getenv("SGZ_SELF_TC_PASSES")) == 1;
+    const bool useT = p.weight > 0.f, useS = p.weight < 1.f;
+    const int nPass = useT && useS && !onePass ? 2 : 1;
+    if (nPass == 2) {
+      SGZ_TRY(dCorrT.alloc((size_t)ext * ext));
+      tp.corrT = dCorrT.p;
     }
-    k_self_gram_tc<<<gridTc, kSgThreads, G.smemBytes, ctx->stream>>>(tp);
-    SGZ_LAUNCH_CHECK(ctx);
+    for (int pass = 0; pass < nPass; pass++) {
+      const bool doT = nPass == 2 ? pass == 0 : useT, doS = nPass == 2 ? pass == 1 : useS;
+      tp.storeT = nPass == 2 && pass == 0;
+      tp.loadT = nPass == 2 && pass == 1;
+      if (prof) {
+        SGZ_TRY(dProf.alloc((size_t)gridTc * 16));
+        SGZ_CUDA(cudaMemsetAsync(dProf.p, 0, (size_t)gridTc * 16 * sizeof(long long), ctx->stream));
+        tp.prof = dProf.p;
+      }
+      if (doT && doS) k_self_gram_tc<0><<<gridTc, kSgThreads, G.smemBytes, ctx->stream>>>(tp);
+      else if (doT) k_self_gram_tc<1><<<gridTc, kSgThreads, G.smemBytes, ctx->stream>>>(tp);
+      else k_self_gram_tc<2><<<gridTc, kSgThreads, G.smemBytes, ctx->stream>>>(tp);
+      SGZ_LAUNCH_CHECK(ctx);
+      if (prof) {
+        std::vector<long long> h((size_t)gridTc * 16);
+        SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+        SGZ_CUDA(cudaMemcpy(h.data(), dProf.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        double a[16] = {0};
+        for (unsigned bk = 0; bk < gridTc; bk++) for (int k = 0; k < 16; k++) a[k] += (double)h[(size_t)bk * 16 + k];
+        const double tiles = a[5] > 0 ? a[5] : 1;
+        fprintf(stderr, "k_self_gram_tc pass %d/%d cycles per tile (aDesc %d, %d stages of %d K steps, %d record stages): issuer total %.0f | "
+                        "records %.0f, wait accEmpty %.0f, wait full %.0f, issue %.0f || builder total %.0f | wait records %.0f, "
+                        "wait empty %.0f, build %.0f || epilogue wait accFull %.0f, main %.0f\n",
+                pass + 1, nPass, tp.aDesc, tp.nStage, tp.slabKs, tp.nRecStage, a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles,
+                a[4] / tiles, a[8] / tiles, a[9] / tiles, a[10] / tiles, a[11] / tiles, a[12] / tiles, a[13] / tiles);
+      }
+    }
     SGZ_TRY(ctx->end_call());
-    if (prof) {
-      std::vector<long long> h((size_t)gridTc * 16);
-      SGZ_CUDA(cudaMemcpy(h.data(), dProf.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-      double a[16] = {0};
-      for (unsigned bk = 0; bk < gridTc; bk++) for (int k = 0; k < 16; k++) a[k] += (double)h[(size_t)bk * 16 + k];
-      const double tiles = a[5] > 0 ? a[5] : 1;
-      fprintf(stderr, "k_self_gram_tc cycles per tile (aDesc %d, %d stages of %d K steps): issuer total %.0f | records %.0f, wait accEmpty %.0f, "
-                      "wait full %.0f, issue %.0f || builder total %.0f | wait records %.0f, wait empty %.0f, build %.0f || "
-                      "epilogue wait accFull %.0f, main %.0f\n",
-              tp.aDesc, tp.nStage, tp.slabKs, a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles, a[4] / tiles, a[8] / tiles,
-              a[9] / tiles, a[10] / tiles, a[11] / tiles, a[12] / tiles, a[13] / tiles);
-    }
     if (usedTc) *usedTc = 1;
     ctx->lastSelfKernel = 2;
     return SGZ_OK;

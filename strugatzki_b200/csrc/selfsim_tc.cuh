@@ -34,6 +34,7 @@ struct SelfTcGeom {
   int H, nks, nSlab, slabKs;  // K steps of 16; a ring stage ("slab") holds slabKs of them
   int g, dp, kcStep, span;    // record grid (see above); span = records one operand stage holds
   int nStage;                 // ring depth (slabs)
+  int nRecStage;              // record stages (channels requested ahead + 1)
   int aDesc;                  // decim | 8: A is read in place from the record stage, the ring holds B only
   uint32_t matBytes, stageBytes;
   uint32_t recPartBytes, recStageBytes;
@@ -54,17 +55,20 @@ inline SelfTcGeom self_tc_geom(int H, int decim, size_t smemLimit, bool allowADe
   G.recStageBytes = (4u * G.recPartBytes + 127u) / 128u * 128u;
   G.aDesc = allowADesc && G.dp == 1;
   G.ok = false;
-  const size_t fixed = 2 * (size_t)G.recStageBytes + (size_t)kSgEpiWarps * 32 * kSgPPitch * 4 + 128 * 16 + 256 + 1024;
-  // large stages mean few barrier round trips and fences; at least 3 stages if they fit, else smaller slabs
-  for (int ks = std::min(G.nks, G.aDesc ? 8 : 4); ks >= 1 && !G.ok; ks = ks > 2 ? ks - 1 : ks - 1) {
-    const uint32_t matBytes = (uint32_t)ks * 4096u, stageBytes = (G.aDesc ? 2u : 4u) * matBytes;
-    for (int ns = 4; ns >= (ks > 2 ? 3 : 2); ns--) {
-      if (fixed + (size_t)ns * stageBytes <= smemLimit) {
-        G.slabKs = ks; G.nSlab = (G.nks + ks - 1) / ks; G.nStage = ns;
-        G.matBytes = matBytes; G.stageBytes = stageBytes;
-        G.smemBytes = fixed + (size_t)ns * stageBytes;
-        G.ok = true;
-        break;
+  // large stages mean few barrier round trips and fences; at least 3 stages if they fit, else smaller slabs;
+  // four record stages (requests two channels ahead of the MMAs) where they fit
+  for (int nr = 4; nr >= 2 && !G.ok; nr--) {
+    const size_t fixed = (size_t)nr * G.recStageBytes + (size_t)kSgEpiWarps * 32 * kSgPPitch * 4 + 128 * 16 + 256 + 1024;
+    for (int ks = std::min(G.nks, G.aDesc ? 8 : 4); ks >= 1 && !G.ok; ks--) {
+      const uint32_t matBytes = (uint32_t)ks * 4096u, stageBytes = (G.aDesc ? 2u : 4u) * matBytes;
+      for (int ns = 4; ns >= (ks > 2 ? 3 : 2); ns--) {
+        if (fixed + (size_t)ns * stageBytes <= smemLimit) {
+          G.slabKs = ks; G.nSlab = (G.nks + ks - 1) / ks; G.nStage = ns; G.nRecStage = nr;
+          G.matBytes = matBytes; G.stageBytes = stageBytes;
+          G.smemBytes = fixed + (size_t)ns * stageBytes;
+          G.ok = true;
+          break;
+        }
       }
     }
   }
@@ -78,11 +82,19 @@ struct SelfTcParams {
   const float4 *wsA, *wsB;   // per window (S_T, Q_T, S_S, Q_S) of the scaled centred data (file 1 / file 2)
   const int2 *tiles;
   int nTiles;
-  int nks, nSlab, slabKs, dp, kcStep, span, nStage;
+  int nks, nSlab, slabKs, dp, kcStep, span, nStage, nRecStage;
   uint32_t matBytes, stageBytes, recPartBytes, recStageBytes;
   float *simMat;             // optional [imgExt][imgExt] raw sims at (a, b >= a) (parity checks), or nullptr
   int aDesc;                 // decim | 8: the A operand is read straight from the record stage (see the issuer)
   long long *prof;           // developer probe (SGZ_SELF_TC_PROF): per CTA 16 cycle counters, or nullptr
+  // Passes.  With both groups in play (0 < temporalWeight < 1) the image takes two launches so that the accumulators of
+  // a launch fit TMEM twice and the epilogue of tile n overlaps the MMAs of tile n + 1:
+  //   pass 1 (doT, storeT): temporal group only, one 128-column region per tile (4 in flight), writes the temporal
+  //                         coefficient of every cell to corrT[c][a];
+  //   pass 2 (doS, loadT):  spectral group, main + correction regions (2 tiles in flight), reads corrT, writes pixels.
+  // A single group (weight 0 or 1) is one launch with doT or doS alone.
+  int storeT, loadT;         // (which groups a launch computes is the kernel's template argument)
+  float *corrT;              // [imgExt][imgExt], element [c][a] (column-major so that lanes = rows a are coalesced)
 };
 
 // max |x| per group (as float bits; |NaN| compares above everything) next to the means of k_self_means
@@ -144,6 +156,13 @@ __global__ void k_self_wsums4(const float *__restrict__ x, int64_t stride, int n
 __device__ __forceinline__ uint64_t sg_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
 }
+__device__ __forceinline__ void tc_mma_acc(uint32_t tmemD, uint64_t da, uint64_t db, uint32_t idesc) {   // D += A * B
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmemD),
+      "l"(da), "l"(db), "r"(idesc)
+      : "memory");
+}
 __device__ __forceinline__ void sg_epi_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
 __device__ __forceinline__ float sg_coeff(float G, float Sa, float Qa, float Sb, float Qb, float inv4N) {
@@ -185,26 +204,29 @@ __device__ __forceinline__ int32_t sg_color(const SelfParams &p, float sim, bool
   return i * 0x010101;
 }
 
+// kMode: 0 = both groups in one launch, 1 = temporal group only, 2 = spectral group only
+template <int kMode>
 __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcParams p) {
+  constexpr bool kDoT = kMode != 2, kDoS = kMode != 1;
   extern __shared__ __align__(1024) unsigned char smemRaw[];
   const SelfParams &b = p.f.base;
   unsigned char *base = smemRaw + ((1024 - (smem_u32(smemRaw) & 1023)) & 1023);
   unsigned char *ring = base;                                               // [nStage][mats][2 slabKs chunks][128 rows][16 B]
-  unsigned char *recBase = ring + (size_t)p.nStage * p.stageBytes;          // [2][A1, A2, B1, B2][span] records
-  int32_t *P = reinterpret_cast<int32_t *>(recBase + 2 * (size_t)p.recStageBytes);   // [8 warps][32][17]
+  unsigned char *recBase = ring + (size_t)p.nStage * p.stageBytes;          // [nRecStage][A1, A2, B1, B2][span] records
+  int32_t *P = reinterpret_cast<int32_t *>(recBase + (size_t)p.nRecStage * p.recStageBytes);   // [8 warps][32][17]
   float4 *colW = reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(P) + (size_t)kSgEpiWarps * 32 * kSgPPitch * 4);
   uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(colW) + 128 * 16);
-  uint64_t *full = bars, *empty = bars + 4, *recFull = bars + 8, *recEmpty = bars + 10, *accFull = bars + 12,
-           *accEmpty = bars + 13;
-  uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(bars + 14);
+  uint64_t *full = bars, *empty = bars + 4, *recFull = bars + 8, *recEmpty = bars + 12, *accFull = bars + 16,
+           *accEmpty = bars + 20;
+  uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(bars + 24);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int s = 0; s < 4; s++) { mbar_init(full + s, kSgBuildWarps); mbar_init(empty + s, 1); }
-    mbar_init(recFull, 1); mbar_init(recFull + 1, 1);
-    mbar_init(recEmpty, kSgBuildWarps + (p.aDesc ? 1 : 0)); mbar_init(recEmpty + 1, kSgBuildWarps + (p.aDesc ? 1 : 0));
-    mbar_init(accFull, 1);
-    mbar_init(accEmpty, kSgEpiWarps);
+    for (int s = 0; s < 4; s++) {
+      mbar_init(full + s, kSgBuildWarps); mbar_init(empty + s, 1);
+      mbar_init(accFull + s, 1); mbar_init(accEmpty + s, kSgEpiWarps);
+      mbar_init(recFull + s, 1); mbar_init(recEmpty + s, kSgBuildWarps + (p.aDesc ? 1 : 0));
+    }
     fence_mbar_init();
   }
   __syncthreads();
@@ -217,8 +239,10 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem = *tmemSlot;
 
-  const bool useT = b.weight > 0.f, useS = b.weight < 1.f;
-  const int cBegin = useT ? 0 : 1, cEnd = useS ? b.numCh : 1;
+  // channels of this pass and its TMEM staging: temporal = one region per tile, spectral = main + correction regions
+  const int cBegin = kDoT ? 0 : 1, cEnd = kDoS ? b.numCh : 1;
+  const int accStages = kDoS ? (kDoT ? 1 : 2) : 4;
+  const uint32_t accCols = 512u / (uint32_t)accStages;
   const int H = b.H;
   const int firstMat = p.aDesc ? 2 : 0;                 // ring stages hold [A1, A2, B1, B2] or, with aDesc, [B1, B2]
   const uint32_t matUnits = p.matBytes / 16;
@@ -229,9 +253,9 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
     long long bRec = 0, bEmpty = 0, bBuild = 0, bTot = clock64(), tB;
     for (int t = blockIdx.x; t < p.nTiles; t += gridDim.x) {
       for (int c = cBegin; c < cEnd; c++, chCtr++) {
-        const int rs = chCtr & 1;
+        const int rs = chCtr % p.nRecStage;
         tB = clock64();
-        tc_wait(recFull + rs, (chCtr >> 1) & 1);
+        tc_wait(recFull + rs, (chCtr / p.nRecStage) & 1);
         bRec += clock64() - tB;
         const uint4 *recS = reinterpret_cast<const uint4 *>(recBase + (size_t)rs * p.recStageBytes);
         for (int slab = 0; slab < p.nSlab; slab++, slabCtr++) {
@@ -282,7 +306,17 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
     // D = F32, A = B = F16, both K-major, M = 128, N = 128
     const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const int64_t chanRecs = p.nRec, partRecs = (int64_t)b.numCh * p.nRec;
-    auto request = [&](int rs, int t, int c) {   // the records both operands of (tile t, channel c) need
+    const int nCh = cEnd - cBegin;
+    // records both operands of the n-th (tile, channel) of this CTA need.  Requests run `ahead` channels ahead of the
+    // MMAs; with 3+ stages the stage a request recycles was released two channels ago (its MMAs are long done), so the
+    // issuer never waits here
+    const uint32_t ahead = p.nRecStage >= 3 ? (uint32_t)p.nRecStage - 2u : 1u;
+    auto request = [&](uint32_t n) {
+      const int t = blockIdx.x + (int)(n / (uint32_t)nCh) * (int)gridDim.x, c = cBegin + (int)(n % (uint32_t)nCh);
+      if (t >= p.nTiles) return;
+      const int rs = n % p.nRecStage;
+      const uint32_t use = n / p.nRecStage;
+      if (use > 0) tc_wait<false>(recEmpty + rs, (use - 1) & 1);
       if (tc_elect()) {
         const int2 tl = p.tiles[t];
         unsigned char *dst = recBase + (size_t)rs * p.recStageBytes;
@@ -298,23 +332,20 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
     };
     uint32_t slabCtr = 0, chCtr = 0, tileIt = 0;
     long long iRec = 0, iAcc = 0, iFull = 0, iIssue = 0, iTot = clock64(), tI;
+    for (uint32_t n = 0; n < ahead; n++) request(n);
     for (int t = blockIdx.x; t < p.nTiles; t += gridDim.x, tileIt++) {
+      const int as = tileIt % accStages;
+      const uint32_t accBase = tmem + (uint32_t)as * accCols;
       for (int c = cBegin; c < cEnd; c++, chCtr++) {
         tI = clock64();
-        if (chCtr == 0) request(0, t, c);
-        {   // records of the next (tile, channel), one channel ahead
-          const bool lastC = c + 1 == cEnd;
-          const int nt = lastC ? t + (int)gridDim.x : t, nc = lastC ? cBegin : c + 1;
-          if (nt < p.nTiles) {
-            const uint32_t n = chCtr + 1;
-            if (n >= 2) tc_wait<false>(recEmpty + (n & 1), ((n >> 1) - 1) & 1);
-            request((int)(n & 1), nt, nc);
-          }
-        }
+        request(chCtr + ahead);
         iRec += clock64() - tI; tI = clock64();
-        if (c == cBegin && tileIt > 0) tc_wait<false>(accEmpty, (tileIt - 1) & 1);   // the epilogue has drained TMEM
+        if (c == cBegin && tileIt >= (uint32_t)accStages)
+          tc_wait<false>(accEmpty + as, ((tileIt / accStages) - 1) & 1);   // the epilogue has drained this TMEM stage
         iAcc += clock64() - tI;
-        const uint32_t dMain = tmem + (c == 0 ? 0u : 128u), dCorr = tmem + (c == 0 ? 0u : 256u);
+        // regions of the stage: temporal = one region for all three products; spectral = main + correction, after the
+        // temporal region when both groups share a launch
+        const uint32_t dMain = accBase + (c == 0 ? 0u : (kDoT ? 128u : 0u)), dCorr = c == 0 ? dMain : dMain + 128u;
         for (int slab = 0; slab < p.nSlab; slab++, slabCtr++) {
           const int st = slabCtr % p.nStage;
           const uint32_t use = slabCtr / p.nStage;
@@ -323,35 +354,42 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
           iFull += clock64() - tI; tI = clock64();
           asm volatile("tcgen05.fence::after_thread_sync;");
           if (tc_elect()) {
+            // descriptors of the first K step; a K step further is a constant increment of the start-address fields
             const uint32_t sb = smem_u32(ring + (size_t)st * p.stageBytes);
             const int nksHere = min(p.slabKs, p.nks - p.slabKs * slab);
-            for (int ks = 0; ks < nksHere; ks++) {
-              const uint32_t o = (uint32_t)ks * 2u * 2048u;
-              uint64_t a1, a2, b1, b2;
-              if (p.aDesc) {
-                // decim | 8: a window starts every record (dp = 1), so the 8 rows of a core matrix ARE 8 consecutive
-                // records (16 B apart), row groups are 128 B apart and chunk kc of a row lies kcStep records further:
-                // the record stage itself is the K-major operand, with overlapping core matrices (LBO = kcStep * 16 B)
-                const uint32_t ra = smem_u32(recBase + (size_t)(chCtr & 1) * p.recStageBytes) +
-                                    (uint32_t)(p.slabKs * slab + ks) * 2u * (uint32_t)p.kcStep * 16u;
-                a1 = sg_desc(ra, (uint32_t)p.kcStep * 16u, 128);
-                a2 = sg_desc(ra + p.recPartBytes, (uint32_t)p.kcStep * 16u, 128);
-                b1 = sg_desc(sb + o, 2048, 128);
-                b2 = sg_desc(sb + p.matBytes + o, 2048, 128);
-              } else {
-                a1 = sg_desc(sb + o, 2048, 128);
-                a2 = sg_desc(sb + p.matBytes + o, 2048, 128);
-                b1 = sg_desc(sb + 2 * p.matBytes + o, 2048, 128);
-                b2 = sg_desc(sb + 3 * p.matBytes + o, 2048, 128);
-              }
-              const bool first = slab == 0 && ks == 0 && (c == 0 || c == 1);   // first MMA into this group's regions
-              tc_mma(dMain, a1, b1, idesc, !first);
-              tc_mma(dCorr, a2, b1, idesc, c == 0 ? 1u : !first);
-              tc_mma(dCorr, a1, b2, idesc, 1);
+            uint64_t a1, a2, b1, b2, aInc;
+            if (p.aDesc) {
+              // decim | 8: a window starts every record (dp = 1), so the 8 rows of a core matrix ARE 8 consecutive
+              // records (16 B apart), row groups are 128 B apart and chunk kc of a row lies kcStep records further:
+              // the record stage itself is the K-major operand, with overlapping core matrices (LBO = kcStep * 16 B)
+              const uint32_t ra = smem_u32(recBase + (size_t)(chCtr % p.nRecStage) * p.recStageBytes) +
+                                  (uint32_t)(p.slabKs * slab) * 2u * (uint32_t)p.kcStep * 16u;
+              a1 = sg_desc(ra, (uint32_t)p.kcStep * 16u, 128);
+              a2 = sg_desc(ra + p.recPartBytes, (uint32_t)p.kcStep * 16u, 128);
+              b1 = sg_desc(sb, 2048, 128);
+              b2 = sg_desc(sb + p.matBytes, 2048, 128);
+              aInc = 2u * (uint32_t)p.kcStep;               // 2 chunks x kcStep records x 16 B, in 16-byte units
+            } else {
+              a1 = sg_desc(sb, 2048, 128);
+              a2 = sg_desc(sb + p.matBytes, 2048, 128);
+              b1 = sg_desc(sb + 2 * p.matBytes, 2048, 128);
+              b2 = sg_desc(sb + 3 * p.matBytes, 2048, 128);
+              aInc = 256;                                   // 2 chunks x 2048 B
+            }
+            // first MMA into a region of this tile overwrites; the temporal group keeps all three products in one region
+            const bool first = slab == 0 && (c == 0 || c == 1);
+            tc_mma(dMain, a1, b1, idesc, !first);
+            tc_mma(dCorr, a2, b1, idesc, c == 0 ? 1u : !first);
+            tc_mma(dCorr, a1, b2, idesc, 1);
+            for (int ks = 1; ks < nksHere; ks++) {
+              a1 += aInc; a2 += aInc; b1 += 256; b2 += 256;
+              tc_mma_acc(dMain, a1, b1, idesc);
+              tc_mma_acc(dCorr, a2, b1, idesc);
+              tc_mma_acc(dCorr, a1, b2, idesc);
             }
             tc_commit(empty + st);
-            if (p.aDesc && slab + 1 == p.nSlab) tc_commit(recEmpty + (chCtr & 1));   // the MMAs read the record stage
-            if (c + 1 == cEnd && slab + 1 == p.nSlab) tc_commit(accFull);
+            if (p.aDesc && slab + 1 == p.nSlab) tc_commit(recEmpty + (chCtr % p.nRecStage));   // the MMAs read the record stage
+            if (c + 1 == cEnd && slab + 1 == p.nSlab) tc_commit(accFull + as);
           }
           __syncwarp();
           iIssue += clock64() - tI;
@@ -371,9 +409,13 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
     const float invNT = (float)(1.0 / (4.0 * (double)H)), invNS = (float)(1.0 / (4.0 * (double)(b.numCh - 1) * (double)H));
     const bool warpOne = b.colorWarp == 1.0f;
     const float wT = b.weight, wS = __fsub_rn(1.0f, b.weight);
+    const bool useT = kDoT, useS = kDoS;
+    // TMEM columns of the regions inside a stage: one-launch two-group mode [T | S main | S corr], else [main | corr]
+    const uint32_t colT = 0u, colM = kDoT ? 128u : 0u, colC = kDoT ? 256u : 128u;
     uint32_t tileIt = 0;
     long long eAcc = 0, eMain = 0, tE;
     for (int t = blockIdx.x; t < p.nTiles; t += gridDim.x, tileIt++) {
+      const int as = tileIt % accStages;
       const int2 tl = p.tiles[t];
       const int ta = tl.x, tb = tl.y;
       sg_epi_sync();                                       // everybody is done with the previous tile's column sums
@@ -387,44 +429,60 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
       float4 wa = a < ext ? p.wsA[a] : make_float4(0.f, 0.f, 0.f, 0.f);
       wa.y *= 0.5f; wa.w *= 0.5f;
       const bool rowOk = a < ext && a >= b.colBegin && a < b.colEnd;
-      // interior tile (all 128 x 128 cells exist, strictly above the diagonal) with the plain grey scale: no per-cell
-      // predicates, 32-bit pixel offsets (imgExt <= 0xB504, so imgExt^2 < 2^31)
-      const bool fast = ta + 128 <= ext && tb + 128 <= ext && tb >= ta + 128 && ta >= b.colBegin && ta + 128 <= b.colEnd &&
-                        warpOne && b.lut == nullptr && p.simMat == nullptr;
+      // interior tile (all 128 x 128 cells exist, strictly above the diagonal): no per-cell predicates, 32-bit pixel
+      // offsets (imgExt <= 0xB504, so imgExt^2 < 2^31); the pixel path also needs the plain grey scale
+      const bool interior = ta + 128 <= ext && tb + 128 <= ext && tb >= ta + 128 && ta >= b.colBegin && ta + 128 <= b.colEnd;
+      const bool fast = interior && warpOne && b.lut == nullptr && p.simMat == nullptr;
       tE = clock64();
-      tc_wait(accFull, tileIt & 1);
+      tc_wait(accFull + as, (tileIt / accStages) & 1);
       eAcc += clock64() - tE; tE = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;");
-      const uint32_t laneAddr = tmem + ((uint32_t)(quarter * 32) << 16) + 64u * (uint32_t)half;
+      const uint32_t laneAddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * accCols + 64u * (uint32_t)half;
 #pragma unroll 1
       for (int bt = 0; bt < 4; bt++) {
         uint32_t uT[16], uM[16], uC[16];
-        if (useT) tc_ld16_nowait(laneAddr + 16u * bt, uT);
+        if (useT) tc_ld16_nowait(laneAddr + colT + 16u * bt, uT);
         if (useS) {
-          tc_ld16_nowait(laneAddr + 128u + 16u * bt, uM);
-          tc_ld16_nowait(laneAddr + 256u + 16u * bt, uC);
+          tc_ld16_nowait(laneAddr + colM + 16u * bt, uM);
+          tc_ld16_nowait(laneAddr + colC + 16u * bt, uC);
         }
         tc_ld_wait();
-        if (bt == 3) {   // all accumulators of this warp are in registers: hand TMEM back to the issuer
+        if (bt == 3) {   // all accumulators of this warp are in registers: hand the TMEM stage back to the issuer
           asm volatile("tcgen05.fence::before_thread_sync;");
           __syncwarp();
-          if (lane == 0) mbar_arrive(accEmpty);
+          if (lane == 0) mbar_arrive(accEmpty + as);
         }
         const int c0 = tb + 64 * half + 16 * bt;
         const float4 *cw = colW + 64 * half + 16 * bt;
+        if (kMode == 1 && p.storeT) {
+          // pass 1 of 2: the temporal coefficient of every cell of the tile -> corrT[c][a] (lanes = rows a: coalesced)
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            const float4 wb = cw[i];
+            const float temporal = sg_coeff_h(__uint_as_float(uT[i]), wa.x, wa.y, wb.x, wb.y, invNT);
+            if (interior || (a < ext && c0 + i < ext)) p.corrT[(int64_t)(c0 + i) * ext + a] = temporal;
+          }
+          continue;
+        }
+        float tv[16];
+        if (kMode == 2 && p.loadT) {
+#pragma unroll
+          for (int i = 0; i < 16; i++) tv[i] = (interior || (a < ext && c0 + i < ext)) ? __ldcs(p.corrT + (int64_t)(c0 + i) * ext + a) : 0.f;
+        }
         int32_t colr[16];
         if (fast) {
-          // pass 1: 16 independent cells in registers
+          // 16 independent cells in registers
 #pragma unroll
           for (int i = 0; i < 16; i++) {
             const float4 wb = cw[i];
             float temporal = 0.f, spectral = 0.f;
             if (useT) temporal = sg_coeff_h(__uint_as_float(uT[i]), wa.x, wa.y, wb.x, wb.y, invNT);
+            if (kMode == 2 && p.loadT) temporal = tv[i];
             if (useS) spectral = sg_coeff_h(__uint_as_float(uM[i]) + __uint_as_float(uC[i]), wa.z, wa.w, wb.z, wb.w, invNS);
             const float sim = __fadd_rn(__fmul_rn(temporal, wT), __fmul_rn(spectral, wS));
             colr[i] = sg_grey(sim, b.colorScale, b.colorInv);
           }
-          // pass 2: the pixel (image row ext-1-c, x = a: coalesced over the lanes) and the transpose buffer
+          // the pixel (image row ext-1-c, x = a: coalesced over the lanes) and the transpose buffer
           const uint32_t offD = (uint32_t)(ext - 1 - c0) * (uint32_t)ext + (uint32_t)a;
 #pragma unroll
           for (int i = 0; i < 16; i++) {
@@ -448,6 +506,7 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
           const float4 wb = cw[i];
           float temporal = 0.f, spectral = 0.f;
           if (useT) temporal = sg_coeff_h(__uint_as_float(uT[i]), wa.x, wa.y, wb.x, wb.y, invNT);
+          if (kMode == 2 && p.loadT) temporal = tv[i];
           if (useS) spectral = sg_coeff_h(__uint_as_float(uM[i]) + __uint_as_float(uC[i]), wa.z, wa.w, wb.z, wb.w, invNS);
           const float sim = __fadd_rn(__fmul_rn(temporal, wT), __fmul_rn(spectral, wS));
           colr[i] = sg_color(b, sim, warpOne);
