@@ -35,7 +35,7 @@ struct SelfTcGeom {
   int g, dp, kcStep, span;    // record grid (see above); span = records one operand stage holds
   int nStage;                 // ring depth (slabs)
   int nRecStage;              // record stages (channels requested ahead + 1)
-  int aDesc;                  // decim | 8: A is read in place from the record stage, the ring holds B only
+  int aDesc;                  // decim | 8: A and B are read in place from the record stages
   uint32_t matBytes, stageBytes;
   uint32_t recPartBytes, recStageBytes;
   size_t smemBytes;
@@ -55,12 +55,23 @@ inline SelfTcGeom self_tc_geom(int H, int decim, size_t smemLimit, bool allowADe
   G.recStageBytes = (4u * G.recPartBytes + 127u) / 128u * 128u;
   G.aDesc = allowADesc && G.dp == 1;
   G.ok = false;
+  if (G.aDesc) {
+    // decim | 8: both operands are read in place from the record stages; the ring only holds the masked copy of B's last
+    // K step (needed when H is not a multiple of 16), one stage per channel
+    G.slabKs = 1; G.nSlab = 1; G.nStage = 4; G.nRecStage = 4;
+    G.matBytes = 4096; G.stageBytes = 2 * G.matBytes;
+    G.smemBytes = (size_t)G.nRecStage * G.recStageBytes + (size_t)kSgEpiWarps * 32 * kSgPPitch * 4 + 128 * 16 + 256 + 1024 +
+                  (size_t)G.nStage * G.stageBytes;
+    G.ok = G.smemBytes <= smemLimit;
+    if (G.ok) return G;
+    G.aDesc = 0;
+  }
   // large stages mean few barrier round trips and fences; at least 3 stages if they fit, else smaller slabs;
   // four record stages (requests two channels ahead of the MMAs) where they fit
   for (int nr = 4; nr >= 2 && !G.ok; nr--) {
     const size_t fixed = (size_t)nr * G.recStageBytes + (size_t)kSgEpiWarps * 32 * kSgPPitch * 4 + 128 * 16 + 256 + 1024;
-    for (int ks = std::min(G.nks, G.aDesc ? 8 : 4); ks >= 1 && !G.ok; ks--) {
-      const uint32_t matBytes = (uint32_t)ks * 4096u, stageBytes = (G.aDesc ? 2u : 4u) * matBytes;
+    for (int ks = std::min(G.nks, 4); ks >= 1 && !G.ok; ks--) {
+      const uint32_t matBytes = (uint32_t)ks * 4096u, stageBytes = 4u * matBytes;
       for (int ns = 4; ns >= (ks > 2 ? 3 : 2); ns--) {
         if (fixed + (size_t)ns * stageBytes <= smemLimit) {
           G.slabKs = ks; G.nSlab = (G.nks + ks - 1) / ks; G.nStage = ns; G.nRecStage = nr;
@@ -265,8 +276,9 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
           if (use > 0) tc_wait(empty + st, (use - 1) & 1);   // the MMAs that read this stage are done
           bEmpty += clock64() - tB; tB = clock64();
           uint4 *dstS = reinterpret_cast<uint4 *>(ring + (size_t)st * p.stageBytes);
-          const int kc0 = 2 * p.slabKs * slab;
-          const int nkcl = 2 * min(p.slabKs, p.nks - p.slabKs * slab);     // 8-element chunks of this stage
+          // in-place mode: the stage holds B's last K step only, and only if the window ends inside it
+          const int kc0 = p.aDesc ? 2 * (p.nks - 1) : 2 * p.slabKs * slab;
+          const int nkcl = p.aDesc ? ((H & 15) ? 2 : 0) : 2 * min(p.slabKs, p.nks - p.slabKs * slab);   // 8-element chunks
           const int nPairs = (4 - firstMat) * nkcl;                       // (operand part, chunk) pairs x 4 row groups
           // one pair per step and warp: the four row groups are four independent 16-byte copies per lane
           for (int pi = warp; pi < nPairs; pi += kSgBuildWarps) {
@@ -354,38 +366,40 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
           iFull += clock64() - tI; tI = clock64();
           asm volatile("tcgen05.fence::after_thread_sync;");
           if (tc_elect()) {
-            // descriptors of the first K step; a K step further is a constant increment of the start-address fields
             const uint32_t sb = smem_u32(ring + (size_t)st * p.stageBytes);
-            const int nksHere = min(p.slabKs, p.nks - p.slabKs * slab);
-            uint64_t a1, a2, b1, b2, aInc;
+            // first MMA into a region of this tile overwrites; the temporal group keeps all three products in one region
+            const bool first = slab == 0 && (c == 0 || c == 1);
             if (p.aDesc) {
               // decim | 8: a window starts every record (dp = 1), so the 8 rows of a core matrix ARE 8 consecutive
               // records (16 B apart), row groups are 128 B apart and chunk kc of a row lies kcStep records further:
-              // the record stage itself is the K-major operand, with overlapping core matrices (LBO = kcStep * 16 B)
-              const uint32_t ra = smem_u32(recBase + (size_t)(chCtr % p.nRecStage) * p.recStageBytes) +
-                                  (uint32_t)(p.slabKs * slab) * 2u * (uint32_t)p.kcStep * 16u;
-              a1 = sg_desc(ra, (uint32_t)p.kcStep * 16u, 128);
-              a2 = sg_desc(ra + p.recPartBytes, (uint32_t)p.kcStep * 16u, 128);
-              b1 = sg_desc(sb, 2048, 128);
-              b2 = sg_desc(sb + p.matBytes, 2048, 128);
-              aInc = 2u * (uint32_t)p.kcStep;               // 2 chunks x kcStep records x 16 B, in 16-byte units
+              // the record stage itself is the K-major operand of BOTH sides, with overlapping core matrices
+              // (LBO = kcStep * 16 B).  Only B's last K step comes from the ring (masked past the window's end).
+              const uint32_t ra = smem_u32(recBase + (size_t)(chCtr % p.nRecStage) * p.recStageBytes);
+              const uint32_t lbo = (uint32_t)p.kcStep * 16u;
+              const uint64_t a1 = sg_desc(ra, lbo, 128), a2 = sg_desc(ra + p.recPartBytes, lbo, 128);
+              const uint64_t b1 = sg_desc(ra + 2 * p.recPartBytes, lbo, 128), b2 = sg_desc(ra + 3 * p.recPartBytes, lbo, 128);
+              const uint64_t inc = 2u * (uint32_t)p.kcStep;     // 2 chunks x kcStep records x 16 B, in 16-byte units
+              const int nIn = (H & 15) ? p.nks - 1 : p.nks;     // K steps whose B is read in place
+              const uint64_t t1 = sg_desc(sb, 2048, 128), t2 = sg_desc(sb + p.matBytes, 2048, 128);   // masked last K step
+              // Consecutive MMAs into the SAME accumulator run back to back; a change of accumulator costs about two MMA
+              // times (measured), so a channel is issued as one chain of main products and one chain of corrections.
+              for (int ks = 0; ks < p.nks; ks++)
+                tc_mma(dMain, a1 + inc * ks, ks < nIn ? b1 + inc * ks : t1, idesc, !(first && ks == 0));
+              for (int ks = 0; ks < p.nks; ks++) {
+                tc_mma(dCorr, a2 + inc * ks, ks < nIn ? b1 + inc * ks : t1, idesc, c == 0 ? 1u : !(first && ks == 0));
+                tc_mma_acc(dCorr, a1 + inc * ks, ks < nIn ? b2 + inc * ks : t2, idesc);
+              }
             } else {
-              a1 = sg_desc(sb, 2048, 128);
-              a2 = sg_desc(sb + p.matBytes, 2048, 128);
-              b1 = sg_desc(sb + 2 * p.matBytes, 2048, 128);
-              b2 = sg_desc(sb + 3 * p.matBytes, 2048, 128);
-              aInc = 256;                                   // 2 chunks x 2048 B
-            }
-            // first MMA into a region of this tile overwrites; the temporal group keeps all three products in one region
-            const bool first = slab == 0 && (c == 0 || c == 1);
-            tc_mma(dMain, a1, b1, idesc, !first);
-            tc_mma(dCorr, a2, b1, idesc, c == 0 ? 1u : !first);
-            tc_mma(dCorr, a1, b2, idesc, 1);
-            for (int ks = 1; ks < nksHere; ks++) {
-              a1 += aInc; a2 += aInc; b1 += 256; b2 += 256;
-              tc_mma_acc(dMain, a1, b1, idesc);
-              tc_mma_acc(dCorr, a2, b1, idesc);
-              tc_mma_acc(dCorr, a1, b2, idesc);
+              // descriptors of the first K step; a K step further is a constant increment of the start-address fields
+              const int nksHere = min(p.slabKs, p.nks - p.slabKs * slab);
+              const uint64_t a1 = sg_desc(sb, 2048, 128), a2 = sg_desc(sb + p.matBytes, 2048, 128);
+              const uint64_t b1 = sg_desc(sb + 2 * p.matBytes, 2048, 128), b2 = sg_desc(sb + 3 * p.matBytes, 2048, 128);
+              for (int ks = 0; ks < nksHere; ks++)             // 2 chunks x 2048 B = 256 units per K step
+                tc_mma(dMain, a1 + 256u * ks, b1 + 256u * ks, idesc, !(first && ks == 0));
+              for (int ks = 0; ks < nksHere; ks++) {
+                tc_mma(dCorr, a2 + 256u * ks, b1 + 256u * ks, idesc, c == 0 ? 1u : !(first && ks == 0));
+                tc_mma_acc(dCorr, a1 + 256u * ks, b2 + 256u * ks, idesc);
+              }
             }
             tc_commit(empty + st);
             if (p.aDesc && slab + 1 == p.nSlab) tc_commit(recEmpty + (chCtr % p.nRecStage));   // the MMAs read the record stage
