@@ -190,7 +190,7 @@ static int self_fast_image(sgz_ctx *ctx, const sgz_self_config *cfg, sgz::SelfPa
   DevBuf<unsigned int> dAmax;
   DevBuf<float2> ws1, ws2;
   DevBuf<float4> wsA, wsB;
-  DevBuf<uint4> rec1, rec2;
+  DevBuf<uint4> rec1, rec2, tail2;
   DevBuf<int2> dTiles;
   SGZ_TRY(dMeans.alloc(2));
   SGZ_TRY(dAmax.alloc(2));
@@ -270,7 +270,16 @@ static int self_fast_image(sgz_ctx *ctx, const sgz_self_config *cfg, sgz::SelfPa
     tp.nTiles = (int)gt.size();
     tp.nks = G.nks; tp.nSlab = G.nSlab; tp.slabKs = G.slabKs; tp.dp = G.dp; tp.kcStep = G.kcStep; tp.span = G.span;
     tp.nStage = G.nStage; tp.nRecStage = G.nRecStage; tp.matBytes = G.matBytes; tp.stageBytes = G.stageBytes;
-    tp.recPartBytes = G.recPartBytes; tp.recStageBytes = G.recStageBytes;
+    tp.recPartBytes = G.recPartBytes; tp.recStageBytes = G.recStageBytes; tp.tailBytes = G.tailBytes;
+    if (G.tailBytes) {   // in-place mode, H % 16 != 0: B's last K step, cut off at the window's end, for every window row
+      const int64_t nRows = (int64_t)nT * kGT;
+      SGZ_TRY(tail2.alloc((size_t)2 * numCh * 2 * nRows));
+      k_self_tail<<<(unsigned)ceil_div<int64_t>(2 * (int64_t)numCh * 2 * nRows, 256), 256, 0, ctx->stream>>>(
+          tp.rec2, numCh, nRec, G.kcStep, 2 * (G.nks - 1), H, nRows, tail2.p);
+      SGZ_LAUNCH_CHECK(ctx);
+      tp.tail2 = tail2.p;
+      tp.nTailRows = nRows;
+    }
     tp.simMat = simMat;
     tp.aDesc = G.aDesc;
     SGZ_CUDA(cudaFuncSetAttribute(k_self_gram_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));
@@ -280,9 +289,11 @@ static int self_fast_image(sgz_ctx *ctx, const sgz_self_config *cfg, sgz::SelfPa
     DevBuf<long long> dProf;
     DevBuf<float> dCorrT;
     const bool prof = getenv("SGZ_SELF_TC_PROF") != nullptr;   // developer probe: cycles per role
-    // both groups in play: temporal pass -> corrT, then the spectral pass (see SelfTcParams); SGZ_SELF_TC_PASSES=1 keeps
-    // the one-launch form (three TMEM regions per tile, epilogue not overlapped)
-    static const bool onePass = getenv("SGZ_SELF_TC_PASSES") && atoi(getenv("SGZ_SELF_TC_PASSES")) == 1;
+    // Both groups in play: one launch with three TMEM regions per tile (default; the epilogue of a tile is not overlapped
+    // with the next tile's MMAs), or SGZ_SELF_TC_PASSES=2: temporal pass -> corrT, then the spectral pass with two tiles
+    // in TMEM (see SelfTcParams).  Measured on B200 (30 000 frames, decim 1): 1.16e11 vs 1.06e11 cells/s -- the overlapped
+    // epilogue runs at half speed next to the MMAs' shared-memory traffic and the extra pass costs 8 k cycles per tile.
+    static const bool onePass = !(getenv("SGZ_SELF_TC_PASSES") && atoi(getenv("SGZ_SELF_TC_PASSES")) == 2);
     const bool useT = p.weight > 0.f, useS = p.weight < 1.f;
     const int nPass = useT && useS && !onePass ? 2 : 1;
     if (nPass == 2) {

@@ -26,7 +26,8 @@
 
 namespace sgz {
 
-constexpr int kSgBuildWarps = 7, kSgEpiWarps = 8;
+constexpr int kSgBuildWarps = 7, kSgEpiWarps = 8;   // warp 0 = record producer, warps 1..6 = builders (expansion mode only)
+constexpr int kSgBuilders = kSgBuildWarps - 1;
 constexpr int kSgThreads = (kSgBuildWarps + 1 + kSgEpiWarps) * 32;   // 512: the register file is handed out per 4 warps
 constexpr int kSgPPitch = 17;                                        // transpose buffer: 32 rows x 16 pixels, padded
 
@@ -37,7 +38,7 @@ struct SelfTcGeom {
   int nRecStage;              // record stages (channels requested ahead + 1)
   int aDesc;                  // decim | 8: A and B are read in place from the record stages
   uint32_t matBytes, stageBytes;
-  uint32_t recPartBytes, recStageBytes;
+  uint32_t recPartBytes, recStageBytes, tailBytes;
   size_t smemBytes;
   bool ok;
 };
@@ -55,21 +56,27 @@ inline SelfTcGeom self_tc_geom(int H, int decim, size_t smemLimit, bool allowADe
   G.recStageBytes = (4u * G.recPartBytes + 127u) / 128u * 128u;
   G.aDesc = allowADesc && G.dp == 1;
   G.ok = false;
+  G.tailBytes = 0;
   if (G.aDesc) {
-    // decim | 8: both operands are read in place from the record stages; the ring only holds the masked copy of B's last
-    // K step (needed when H is not a multiple of 16), one stage per channel
-    G.slabKs = 1; G.nSlab = 1; G.nStage = 4; G.nRecStage = 4;
-    G.matBytes = 4096; G.stageBytes = 2 * G.matBytes;
-    G.smemBytes = (size_t)G.nRecStage * G.recStageBytes + (size_t)kSgEpiWarps * 32 * kSgPPitch * 4 + 128 * 16 + 256 + 1024 +
-                  (size_t)G.nStage * G.stageBytes;
-    G.ok = G.smemBytes <= smemLimit;
+    // decim | 8: both operands are read in place from the record stages.  When H is not a multiple of 16 the last K step
+    // of B must end at the window's end: its masked copy comes pre-built from global memory (k_self_records) as part of
+    // the record stage, in canonical [chunk][row] order.  No builder warps, no ring.
+    G.tailBytes = (H & 15) ? 4u * 2048u : 0u;                      // B first / second part x 2 chunks x 128 rows x 16 B
+    G.recStageBytes = (4u * G.recPartBytes + G.tailBytes + 127u) / 128u * 128u;
+    G.slabKs = G.nks; G.nSlab = 1; G.nStage = 0; G.matBytes = 0; G.stageBytes = 0;
+    const size_t fixed = (size_t)kSgEpiWarps * 32 * kSgPPitch * 4 + 128 * 16 + 512 + 1024;
+    G.nRecStage = (int)std::min<size_t>(8, (smemLimit - fixed) / G.recStageBytes);
+    G.smemBytes = fixed + (size_t)G.nRecStage * G.recStageBytes;
+    G.ok = G.nRecStage >= 3;
     if (G.ok) return G;
     G.aDesc = 0;
+    G.tailBytes = 0;
+    G.recStageBytes = (4u * G.recPartBytes + 127u) / 128u * 128u;
   }
   // large stages mean few barrier round trips and fences; at least 3 stages if they fit, else smaller slabs;
   // four record stages (requests two channels ahead of the MMAs) where they fit
   for (int nr = 4; nr >= 2 && !G.ok; nr--) {
-    const size_t fixed = (size_t)nr * G.recStageBytes + (size_t)kSgEpiWarps * 32 * kSgPPitch * 4 + 128 * 16 + 256 + 1024;
+    const size_t fixed = (size_t)nr * G.recStageBytes + (size_t)kSgEpiWarps * 32 * kSgPPitch * 4 + 128 * 16 + 512 + 1024;
     for (int ks = std::min(G.nks, 4); ks >= 1 && !G.ok; ks--) {
       const uint32_t matBytes = (uint32_t)ks * 4096u, stageBytes = 4u * matBytes;
       for (int ns = 4; ns >= (ks > 2 ? 3 : 2); ns--) {
@@ -94,7 +101,9 @@ struct SelfTcParams {
   const int2 *tiles;
   int nTiles;
   int nks, nSlab, slabKs, dp, kcStep, span, nStage, nRecStage;
-  uint32_t matBytes, stageBytes, recPartBytes, recStageBytes;
+  uint32_t matBytes, stageBytes, recPartBytes, recStageBytes, tailBytes;
+  const uint4 *tail2;        // pre-masked last K step of file 2's windows: [part][channel][chunk 0/1][nTailRows] (in-place mode)
+  int64_t nTailRows;
   float *simMat;             // optional [imgExt][imgExt] raw sims at (a, b >= a) (parity checks), or nullptr
   int aDesc;                 // decim | 8: the A operand is read straight from the record stage (see the issuer)
   long long *prof;           // developer probe (SGZ_SELF_TC_PROF): per CTA 16 cycle counters, or nullptr
@@ -140,6 +149,27 @@ __global__ void k_self_records(const float *__restrict__ x, int64_t stride, int6
   }
   rec[idx] = *reinterpret_cast<const uint4 *>(hi);
   rec[(int64_t)numCh * nRec + idx] = *reinterpret_cast<const uint4 *>(lo);
+}
+
+// In-place mode, H % 16 != 0: the last K step (chunks kc0 = 2 (nks - 1) and kc0 + 1) of every window row of file 2, cut
+// off at the window's end: tail[part][c][kcl][row] = record (row + kcStep (kc0 + kcl)) with the halves k >= H zeroed
+__global__ void k_self_tail(const uint4 *__restrict__ rec, int numCh, int64_t nRec, int kcStep, int kc0, int H, int64_t nRows,
+                            uint4 *__restrict__ tail) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= 2 * (int64_t)numCh * 2 * nRows) return;
+  const int64_t row = idx % nRows;
+  const int kcl = (int)((idx / nRows) & 1);
+  const int64_t pc = idx / (2 * nRows);               // part * numCh + c
+  const int64_t rho = row + (int64_t)kcStep * (kc0 + kcl);
+  uint4 v = rho < nRec ? rec[pc * nRec + rho] : make_uint4(0, 0, 0, 0);
+  const int nv = H - 8 * (kc0 + kcl);
+  if (nv < 8) {
+    v.x = nv >= 2 ? v.x : (nv == 1 ? v.x & 0xffffu : 0u);
+    v.y = nv >= 4 ? v.y : (nv == 3 ? v.y & 0xffffu : 0u);
+    v.z = nv >= 6 ? v.z : (nv == 5 ? v.z & 0xffffu : 0u);
+    v.w = nv == 7 ? v.w & 0xffffu : 0u;
+  }
+  tail[idx] = v;
 }
 
 // (S, Q) of every decimated window of the scaled centred data, FP64 accumulation, both groups in one float4
@@ -227,17 +257,18 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
   int32_t *P = reinterpret_cast<int32_t *>(recBase + (size_t)p.nRecStage * p.recStageBytes);   // [8 warps][32][17]
   float4 *colW = reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(P) + (size_t)kSgEpiWarps * 32 * kSgPPitch * 4);
   uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(colW) + 128 * 16);
-  uint64_t *full = bars, *empty = bars + 4, *recFull = bars + 8, *recEmpty = bars + 12, *accFull = bars + 16,
-           *accEmpty = bars + 20;
-  uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(bars + 24);
+  uint64_t *full = bars, *empty = bars + 4, *recFull = bars + 8, *recEmpty = bars + 16, *accFull = bars + 24,
+           *accEmpty = bars + 28;
+  uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(bars + 32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int s = 0; s < 4; s++) {
-      mbar_init(full + s, kSgBuildWarps); mbar_init(empty + s, 1);
+      mbar_init(full + s, kSgBuilders); mbar_init(empty + s, 1);
       mbar_init(accFull + s, 1); mbar_init(accEmpty + s, kSgEpiWarps);
-      mbar_init(recFull + s, 1); mbar_init(recEmpty + s, kSgBuildWarps + (p.aDesc ? 1 : 0));
     }
+    // a record stage is released by the MMAs that read it (in-place mode) or by the builders that expanded it
+    for (int s = 0; s < 8; s++) { mbar_init(recFull + s, 1); mbar_init(recEmpty + s, p.aDesc ? 1 : kSgBuilders); }
     fence_mbar_init();
   }
   __syncthreads();
@@ -255,14 +286,46 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
   const int accStages = kDoS ? (kDoT ? 1 : 2) : 4;
   const uint32_t accCols = 512u / (uint32_t)accStages;
   const int H = b.H;
-  const int firstMat = p.aDesc ? 2 : 0;                 // ring stages hold [A1, A2, B1, B2] or, with aDesc, [B1, B2]
   const uint32_t matUnits = p.matBytes / 16;
 
-  if (warp < kSgBuildWarps) {
-    // =========================== builders ===========================
+  if (warp == 0) {
+    // =========================== record producer ===========================
+    // the records both operands of the n-th (tile, channel) of this CTA need (+ B's pre-masked last K step in in-place
+    // mode); runs as far ahead as the record stages allow
+    const int64_t chanRecs = p.nRec, partRecs = (int64_t)b.numCh * p.nRec;
+    uint32_t n = 0;
+    for (int t = blockIdx.x; t < p.nTiles; t += gridDim.x) {
+      const int2 tl = p.tiles[t];
+      for (int c = cBegin; c < cEnd; c++, n++) {
+        const int rs = n % p.nRecStage;
+        const uint32_t use = n / p.nRecStage;
+        if (use > 0) tc_wait(recEmpty + rs, (use - 1) & 1);
+        if (tc_elect()) {
+          unsigned char *dst = recBase + (size_t)rs * p.recStageBytes;
+          mbar_expect_tx(recFull + rs, 4u * p.recPartBytes + p.tailBytes);
+          const uint4 *a0 = p.rec1 + (int64_t)c * chanRecs + (int64_t)p.dp * tl.x;
+          const uint4 *b0 = p.rec2 + (int64_t)c * chanRecs + (int64_t)p.dp * tl.y;
+          bulk_g2s(dst, a0, p.recPartBytes, recFull + rs);
+          bulk_g2s(dst + p.recPartBytes, a0 + partRecs, p.recPartBytes, recFull + rs);
+          bulk_g2s(dst + 2 * p.recPartBytes, b0, p.recPartBytes, recFull + rs);
+          bulk_g2s(dst + 3 * p.recPartBytes, b0 + partRecs, p.recPartBytes, recFull + rs);
+          if (p.tailBytes) {   // [part][chunk][128 rows]
+            unsigned char *td = dst + 4 * p.recPartBytes;
+            for (int part = 0; part < 2; part++)
+              for (int kcl = 0; kcl < 2; kcl++)
+                bulk_g2s(td + (part * 2 + kcl) * 2048,
+                         p.tail2 + (((int64_t)part * b.numCh + c) * 2 + kcl) * p.nTailRows + tl.y, 2048, recFull + rs);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < kSgBuildWarps) {
+    // =========================== builders (expansion mode: decim does not divide 8) ===========================
+    const int bw = warp - 1;
     uint32_t slabCtr = 0, chCtr = 0;
     long long bRec = 0, bEmpty = 0, bBuild = 0, bTot = clock64(), tB;
-    for (int t = blockIdx.x; t < p.nTiles; t += gridDim.x) {
+    for (int t = blockIdx.x; t < p.nTiles && !p.aDesc; t += gridDim.x) {
       for (int c = cBegin; c < cEnd; c++, chCtr++) {
         const int rs = chCtr % p.nRecStage;
         tB = clock64();
@@ -276,16 +339,15 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
           if (use > 0) tc_wait(empty + st, (use - 1) & 1);   // the MMAs that read this stage are done
           bEmpty += clock64() - tB; tB = clock64();
           uint4 *dstS = reinterpret_cast<uint4 *>(ring + (size_t)st * p.stageBytes);
-          // in-place mode: the stage holds B's last K step only, and only if the window ends inside it
-          const int kc0 = p.aDesc ? 2 * (p.nks - 1) : 2 * p.slabKs * slab;
-          const int nkcl = p.aDesc ? ((H & 15) ? 2 : 0) : 2 * min(p.slabKs, p.nks - p.slabKs * slab);   // 8-element chunks
-          const int nPairs = (4 - firstMat) * nkcl;                       // (operand part, chunk) pairs x 4 row groups
+          const int kc0 = 2 * p.slabKs * slab;
+          const int nkcl = 2 * min(p.slabKs, p.nks - p.slabKs * slab);     // 8-element chunks of this stage
+          const int nPairs = 4 * nkcl;                                    // (operand part, chunk) pairs x 4 row groups
           // one pair per step and warp: the four row groups are four independent 16-byte copies per lane
-          for (int pi = warp; pi < nPairs; pi += kSgBuildWarps) {
+          for (int pi = bw; pi < nPairs; pi += kSgBuilders) {
             int mi = 0, kcl = pi;
             while (kcl >= nkcl) { kcl -= nkcl; mi++; }
             const int kc = kc0 + kcl;
-            const uint4 *src = recS + (size_t)(firstMat + mi) * p.span + (size_t)p.kcStep * kc + (size_t)p.dp * lane;
+            const uint4 *src = recS + (size_t)mi * p.span + (size_t)p.kcStep * kc + (size_t)p.dp * lane;
             uint4 *dst = dstS + (size_t)mi * matUnits + (size_t)kcl * 128 + lane;
             const int step = 32 * p.dp;
             uint4 v0 = src[0], v1 = src[step], v2 = src[2 * step], v3 = src[3 * step];
@@ -309,7 +371,7 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
         if (lane == 0) mbar_arrive(recEmpty + rs);
       }
     }
-    if (p.prof && tid == 0) {
+    if (p.prof && warp == 1 && lane == 0) {
       long long *o = p.prof + 16 * blockIdx.x + 8;
       o[0] = clock64() - bTot; o[1] = bRec; o[2] = bEmpty; o[3] = bBuild;
     }
@@ -317,46 +379,68 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
     // =========================== record producer + MMA issuer ===========================
     // D = F32, A = B = F16, both K-major, M = 128, N = 128
     const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const int64_t chanRecs = p.nRec, partRecs = (int64_t)b.numCh * p.nRec;
-    const int nCh = cEnd - cBegin;
-    // records both operands of the n-th (tile, channel) of this CTA need.  Requests run `ahead` channels ahead of the
-    // MMAs; with 3+ stages the stage a request recycles was released two channels ago (its MMAs are long done), so the
-    // issuer never waits here
-    const uint32_t ahead = p.nRecStage >= 3 ? (uint32_t)p.nRecStage - 2u : 1u;
-    auto request = [&](uint32_t n) {
-      const int t = blockIdx.x + (int)(n / (uint32_t)nCh) * (int)gridDim.x, c = cBegin + (int)(n % (uint32_t)nCh);
-      if (t >= p.nTiles) return;
-      const int rs = n % p.nRecStage;
-      const uint32_t use = n / p.nRecStage;
-      if (use > 0) tc_wait<false>(recEmpty + rs, (use - 1) & 1);
-      if (tc_elect()) {
-        const int2 tl = p.tiles[t];
-        unsigned char *dst = recBase + (size_t)rs * p.recStageBytes;
-        mbar_expect_tx(recFull + rs, 4u * p.recPartBytes);
-        const uint4 *a0 = p.rec1 + (int64_t)c * chanRecs + (int64_t)p.dp * tl.x;
-        const uint4 *b0 = p.rec2 + (int64_t)c * chanRecs + (int64_t)p.dp * tl.y;
-        bulk_g2s(dst, a0, p.recPartBytes, recFull + rs);
-        bulk_g2s(dst + p.recPartBytes, a0 + partRecs, p.recPartBytes, recFull + rs);
-        bulk_g2s(dst + 2 * p.recPartBytes, b0, p.recPartBytes, recFull + rs);
-        bulk_g2s(dst + 3 * p.recPartBytes, b0 + partRecs, p.recPartBytes, recFull + rs);
-      }
-      __syncwarp();
-    };
     uint32_t slabCtr = 0, chCtr = 0, tileIt = 0;
-    long long iRec = 0, iAcc = 0, iFull = 0, iIssue = 0, iTot = clock64(), tI;
-    for (uint32_t n = 0; n < ahead; n++) request(n);
-    for (int t = blockIdx.x; t < p.nTiles; t += gridDim.x, tileIt++) {
+    const bool prof = p.prof != nullptr;
+    long long iRec = 0, iAcc = 0, iFull = 0, iIssue = 0, iTot = clock64(), tI = 0;
+    if (p.aDesc) {
+      // ---- in-place mode.  decim | 8: a window starts every record (dp = 1), so the 8 rows of a core matrix ARE 8
+      // consecutive records (16 B apart), row groups are 128 B apart and chunk kc of a row lies kcStep records further:
+      // the record stage itself is the K-major operand of BOTH sides, with overlapping core matrices (LBO = kcStep * 16
+      // B).  Only B's last K step is a separate, pre-masked block of the stage when H is not a multiple of 16.
+      // The queue of issued MMAs is short, so the loop keeps the gap between two channels small: descriptors are stage 0's
+      // plus a stage offset, waits come first, nothing else sits between the MMAs of consecutive channels.
+      const uint32_t lbo = (uint32_t)p.kcStep * 16u, r0 = smem_u32(recBase);
+      const uint64_t partU = p.recPartBytes >> 4, stageU = p.recStageBytes >> 4, inc = 2u * (uint32_t)p.kcStep;
+      const uint64_t A1 = sg_desc(r0, lbo, 128), T1 = sg_desc(r0 + 4 * p.recPartBytes, 2048, 128);
+      const int nks = p.nks, nIn = (H & 15) ? nks - 1 : nks;     // K steps whose B is read in place
+      uint32_t rs = 0, rsPar = 0;
+      for (int t = blockIdx.x; t < p.nTiles; t += gridDim.x, tileIt++) {
+        const int as = tileIt % accStages;
+        const uint32_t accBase = tmem + (uint32_t)as * accCols;
+        for (int c = cBegin; c < cEnd; c++) {
+          if (prof) tI = clock64();
+          tc_wait<false>(recFull + rs, rsPar);
+          if (prof) { iRec += clock64() - tI; tI = clock64(); }
+          if (c == cBegin && tileIt >= (uint32_t)accStages)
+            tc_wait<false>(accEmpty + as, ((tileIt / accStages) - 1) & 1);   // the epilogue has drained this TMEM stage
+          if (prof) { iAcc += clock64() - tI; tI = clock64(); }
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          // regions of the stage: temporal = one region for all three products; spectral = main + correction, after the
+          // temporal region when both groups share a launch
+          const uint32_t dMain = accBase + (c == 0 ? 0u : (kDoT ? 128u : 0u)), dCorr = c == 0 ? dMain : dMain + 128u;
+          const uint64_t a1 = A1 + stageU * rs, a2 = a1 + partU, b1 = a1 + 2 * partU, b2 = a1 + 3 * partU;
+          const uint64_t t1 = T1 + stageU * rs, t2 = t1 + 256;
+          const uint32_t accFirst = (c == 0 || c == 1) ? 0u : 1u;   // first MMA into a region of this tile overwrites
+          if (tc_elect()) {
+            // one chain of main products, one of corrections (the temporal group keeps all products in one region)
+            for (int ks = 0; ks < nIn; ks++) tc_mma(dMain, a1 + inc * ks, b1 + inc * ks, idesc, ks > 0 ? 1u : accFirst);
+            if (nIn < nks) tc_mma(dMain, a1 + inc * nIn, t1, idesc, nIn > 0 ? 1u : accFirst);
+            for (int ks = 0; ks < nIn; ks++) {
+              tc_mma(dCorr, a2 + inc * ks, b1 + inc * ks, idesc, (ks > 0 || c == 0) ? 1u : accFirst);
+              tc_mma_acc(dCorr, a1 + inc * ks, b2 + inc * ks, idesc);
+            }
+            if (nIn < nks) {
+              tc_mma(dCorr, a2 + inc * nIn, t1, idesc, (nIn > 0 || c == 0) ? 1u : accFirst);
+              tc_mma_acc(dCorr, a1 + inc * nIn, t2, idesc);
+            }
+            tc_commit(recEmpty + rs);                              // the MMAs read the record stage
+            if (c + 1 == cEnd) tc_commit(accFull + as);
+          }
+          __syncwarp();
+          if (++rs == (uint32_t)p.nRecStage) { rs = 0; rsPar ^= 1; }
+          if (prof) iIssue += clock64() - tI;
+        }
+      }
+    }
+    for (int t = blockIdx.x; t < p.nTiles && !p.aDesc; t += gridDim.x, tileIt++) {
+      // ---- expansion mode: operands come from the ring the builders fill
       const int as = tileIt % accStages;
       const uint32_t accBase = tmem + (uint32_t)as * accCols;
       for (int c = cBegin; c < cEnd; c++, chCtr++) {
         tI = clock64();
-        request(chCtr + ahead);
-        iRec += clock64() - tI; tI = clock64();
         if (c == cBegin && tileIt >= (uint32_t)accStages)
           tc_wait<false>(accEmpty + as, ((tileIt / accStages) - 1) & 1);   // the epilogue has drained this TMEM stage
         iAcc += clock64() - tI;
-        // regions of the stage: temporal = one region for all three products; spectral = main + correction, after the
-        // temporal region when both groups share a launch
         const uint32_t dMain = accBase + (c == 0 ? 0u : (kDoT ? 128u : 0u)), dCorr = c == 0 ? dMain : dMain + 128u;
         for (int slab = 0; slab < p.nSlab; slab++, slabCtr++) {
           const int st = slabCtr % p.nStage;
@@ -369,40 +453,17 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
             const uint32_t sb = smem_u32(ring + (size_t)st * p.stageBytes);
             // first MMA into a region of this tile overwrites; the temporal group keeps all three products in one region
             const bool first = slab == 0 && (c == 0 || c == 1);
-            if (p.aDesc) {
-              // decim | 8: a window starts every record (dp = 1), so the 8 rows of a core matrix ARE 8 consecutive
-              // records (16 B apart), row groups are 128 B apart and chunk kc of a row lies kcStep records further:
-              // the record stage itself is the K-major operand of BOTH sides, with overlapping core matrices
-              // (LBO = kcStep * 16 B).  Only B's last K step comes from the ring (masked past the window's end).
-              const uint32_t ra = smem_u32(recBase + (size_t)(chCtr % p.nRecStage) * p.recStageBytes);
-              const uint32_t lbo = (uint32_t)p.kcStep * 16u;
-              const uint64_t a1 = sg_desc(ra, lbo, 128), a2 = sg_desc(ra + p.recPartBytes, lbo, 128);
-              const uint64_t b1 = sg_desc(ra + 2 * p.recPartBytes, lbo, 128), b2 = sg_desc(ra + 3 * p.recPartBytes, lbo, 128);
-              const uint64_t inc = 2u * (uint32_t)p.kcStep;     // 2 chunks x kcStep records x 16 B, in 16-byte units
-              const int nIn = (H & 15) ? p.nks - 1 : p.nks;     // K steps whose B is read in place
-              const uint64_t t1 = sg_desc(sb, 2048, 128), t2 = sg_desc(sb + p.matBytes, 2048, 128);   // masked last K step
-              // Consecutive MMAs into the SAME accumulator run back to back; a change of accumulator costs about two MMA
-              // times (measured), so a channel is issued as one chain of main products and one chain of corrections.
-              for (int ks = 0; ks < p.nks; ks++)
-                tc_mma(dMain, a1 + inc * ks, ks < nIn ? b1 + inc * ks : t1, idesc, !(first && ks == 0));
-              for (int ks = 0; ks < p.nks; ks++) {
-                tc_mma(dCorr, a2 + inc * ks, ks < nIn ? b1 + inc * ks : t1, idesc, c == 0 ? 1u : !(first && ks == 0));
-                tc_mma_acc(dCorr, a1 + inc * ks, ks < nIn ? b2 + inc * ks : t2, idesc);
-              }
-            } else {
-              // descriptors of the first K step; a K step further is a constant increment of the start-address fields
-              const int nksHere = min(p.slabKs, p.nks - p.slabKs * slab);
-              const uint64_t a1 = sg_desc(sb, 2048, 128), a2 = sg_desc(sb + p.matBytes, 2048, 128);
-              const uint64_t b1 = sg_desc(sb + 2 * p.matBytes, 2048, 128), b2 = sg_desc(sb + 3 * p.matBytes, 2048, 128);
-              for (int ks = 0; ks < nksHere; ks++)             // 2 chunks x 2048 B = 256 units per K step
-                tc_mma(dMain, a1 + 256u * ks, b1 + 256u * ks, idesc, !(first && ks == 0));
-              for (int ks = 0; ks < nksHere; ks++) {
-                tc_mma(dCorr, a2 + 256u * ks, b1 + 256u * ks, idesc, c == 0 ? 1u : !(first && ks == 0));
-                tc_mma_acc(dCorr, a1 + 256u * ks, b2 + 256u * ks, idesc);
-              }
+            // descriptors of the first K step; a K step further is a constant increment of the start-address fields
+            const int nksHere = min(p.slabKs, p.nks - p.slabKs * slab);
+            const uint64_t a1 = sg_desc(sb, 2048, 128), a2 = sg_desc(sb + p.matBytes, 2048, 128);
+            const uint64_t b1 = sg_desc(sb + 2 * p.matBytes, 2048, 128), b2 = sg_desc(sb + 3 * p.matBytes, 2048, 128);
+            for (int ks = 0; ks < nksHere; ks++)             // 2 chunks x 2048 B = 256 units per K step
+              tc_mma(dMain, a1 + 256u * ks, b1 + 256u * ks, idesc, !(first && ks == 0));
+            for (int ks = 0; ks < nksHere; ks++) {
+              tc_mma(dCorr, a2 + 256u * ks, b1 + 256u * ks, idesc, c == 0 ? 1u : !(first && ks == 0));
+              tc_mma_acc(dCorr, a1 + 256u * ks, b2 + 256u * ks, idesc);
             }
             tc_commit(empty + st);
-            if (p.aDesc && slab + 1 == p.nSlab) tc_commit(recEmpty + (chCtr % p.nRecStage));   // the MMAs read the record stage
             if (c + 1 == cEnd && slab + 1 == p.nSlab) tc_commit(accFull + as);
           }
           __syncwarp();

@@ -23,11 +23,12 @@ __global__ void __launch_bounds__(128, 1) k_rate(int layout, int nAcc, int N, in
   extern __shared__ __align__(1024) unsigned char smemRaw[];
   unsigned char *base = smemRaw + ((1024 - (smem_u32(smemRaw) & 1023)) & 1023);
   __shared__ uint32_t tmemSlot;
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar, bar2;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(base)[i] = 0x3c003c00u;   // FP16 ones
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -60,7 +61,18 @@ __global__ void __launch_bounds__(128, 1) k_rate(int layout, int nAcc, int N, in
                "l"(A), "l"(B), "r"(idesc)                                                                               \
                : "memory")
     const long long t0 = clock64();
-    if (ksteps == 1) {       // change the accumulator after every MMA
+    if (ksteps == 7) {       // the K4 kernel's channel: 6 main products, then 12 corrections (two operand parts), one commit
+      uint64_t da2[6], db2[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) { da2[k] = da[k] + 140; db2[k] = db[k] + 140; }   // second parts 2240 B further
+      for (int i = 0; i < n; i += 18) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) MMA(d0, da[k], db[k]);
+#pragma unroll
+        for (int k = 0; k < 6; k++) { MMA(d1, da2[k], db[k]); MMA(d1, da[k], db2[k]); }
+        if (nAcc == 3) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
+      }
+    } else if (ksteps == 1) {       // change the accumulator after every MMA
       for (int i = 0; i < n; i += 18) {
 #pragma unroll
         for (int k = 0; k < 6; k++) { MMA(d0, da[k], db[k]); MMA(d1, da[k], db[k]); MMA(d2, da[k], db[k]); }
@@ -102,8 +114,9 @@ int main() {
     for (int layout = 0; layout < 4; layout++)
       for (int nAcc : {1, 2, 3}) {
         if (nAcc * N > 512) continue;
-        for (int ksteps : {1, 6}) {
+        for (int ksteps : {1, 6, 7}) {
           if (ksteps == 1 && nAcc > 1 && N != 128) continue;
+          if (ksteps == 7 && (N != 128 || nAcc < 2 || layout > 1)) continue;
           k_rate<<<sms, 128, smem>>>(layout, nAcc, N, n, ksteps, d);
           cudaError_t e = cudaDeviceSynchronize();
           if (e != cudaSuccess) { printf("{\"error\": \"%s\"}\n", cudaGetErrorString(e)); return 1; }
@@ -111,8 +124,8 @@ int main() {
           cudaMemcpy(h, d, sms * sizeof(long long), cudaMemcpyDeviceToHost);
           double s = 0;
           for (int i = 0; i < sms; i++) s += (double)h[i];
-          printf("{\"shape\": \"M128 N%d K16 f16\", \"layout\": \"%s\", \"accumulators\": %d, \"chain\": %d, \"cycles_per_mma\": %.1f}\n", N,
-                 names[layout], nAcc, ksteps, s / sms / n);
+          printf("{\"shape\": \"M128 N%d K16 f16\", \"layout\": \"%s\", \"accumulators\": %d, \"chain\": \"%s\", \"cycles_per_mma\": %.1f}\n", N,
+                 names[layout], nAcc, ksteps == 7 ? (nAcc == 3 ? "K4 channel pattern + commit per 18" : "K4 channel pattern") : (ksteps == 1 ? "1" : "6"), s / sms / n);
         }
       }
   return 0;
