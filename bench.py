@@ -429,12 +429,23 @@ def run_e2e(args, torch, device, ctx, engine, N, synth, rank, files, mu, sigma, 
 
 
 def run_secondary(ctx, engine, N, synth, norm):
-    """SelfSimilarity cells/s (fast FP32 Gram path and the exact FP64 replay) and segmentation offsets/s."""
+    """SelfSimilarity cells/s (tensor-core Gram kernel at two sizes, the FP64 replay) and segmentation offsets/s."""
     out = {}
     try:
-        f, _ = synth.regime_file(synth.BASE_SEED, 4, 30000, 14, 15)
-        for name, precise in (("selfsimilarity_gram_fp32", 0), ("selfsimilarity_exact_fp64", 1)):
-            cfg = N.SelfConfig(STEP, 0, 0, 0, 0, 44100, 1 if not precise else 3, 0.5, 0, 1.0, 1.0, None, 0, precise)
+        try:
+            tensor_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1399.0))
+        except Exception:
+            tensor_peak = 1399.0
+        cases = (("selfsimilarity_gram_tc", 30000, 1, 0, "30 000-frame synthetic feature file"),
+                 ("selfsimilarity_gram_tc_config3", 155000, 1, 0,
+                  "155 000-frame synthetic feature file (BASELINE.json configs[3]; decimation raised to 4 by the 0xB504 rule)"),
+                 ("selfsimilarity_exact_fp64", 30000, 3, 1, "30 000-frame synthetic feature file"))
+        files = {}
+        for name, frames, decim, precise, what in cases:
+            if frames not in files:
+                files[frames] = synth.regime_file(synth.BASE_SEED, 4, frames, 14, max(4, frames // 2000))[0]
+            f = files[frames]
+            cfg = N.SelfConfig(STEP, 0, 0, 0, 0, 44100, decim, 0.5, 0, 1.0, 1.0, None, 0, precise)
             engine.self_run(ctx, cfg, f, None, norm, download=False)
             _, g = engine.self_run(ctx, cfg, f, None, norm, download=False)
             ms, launches = ctx.last_timing()
@@ -442,9 +453,23 @@ def run_secondary(ctx, engine, N, synth, norm):
             flop = cells * 2408.0 / (ms * 1e-3) / 1e12      # 2*(C+1)*H flop per cell at H = 86
             out[name] = {"metric": "SelfSimilarity cells/sec", "value": cells / (ms * 1e-3), "unit": "cells/s",
                          "cells": cells, "imgExt": g["imgExt"], "decim": g["decim"], "kernel_ms": ms,
-                         "algorithmic_tflops": flop,
-                         "workload": "30 000-frame synthetic feature file, corrLen 44100 (H = 86), GrayScale; "
-                                     "matrix only (PNG encode and image download excluded)"}
+                         "kernel": engine.self_last_kernel(ctx), "algorithmic_tflops": flop,
+                         "workload": what + ", corrLen 44100 (H = 86), temporalWeight 0.5, GrayScale; matrix only "
+                                            "(PNG encode and image download excluded)"}
+            if not precise:
+                # executed: 3 split-FP16 products x 14 channels x 6 K steps of M128 x N128 x K16 per 128 x 128 tile
+                tiles = (g["imgExt"] + 127) // 128
+                tiles = tiles * (tiles + 1) // 2
+                exec_flop = tiles * 252 * 2.0 * 128 * 128 * 16
+                out[name]["roofline"] = {
+                    "bound": "tensor", "achieved": flop, "peak": tensor_peak, "unit": "TFLOP/s", "frac": flop / tensor_peak,
+                    "peak_source": "dense bf16 (= fp16) matmul, sustained, MEASURED_PEAKS.json",
+                    "executed_tflops": exec_flop / (ms * 1e-3) / 1e12, "executed_frac": exec_flop / (ms * 1e-3) / 1e12 / tensor_peak,
+                    "mma_floor_ms": tiles / 148.0 * 252 * 64 / 1.965e6,
+                    "frac_of_mma_floor": tiles / 148.0 * 252 * 64 / 1.965e6 / ms,
+                    "note": "FP32-grade result from three FP16 products (a1 b1 + a2 b1 + a1 b2): executed flops are 3.35x "
+                            "the algorithmic ones (x3 products, K padded 86 -> 96); M128 x N128 x K16 runs at its 64-cycle "
+                            "floor in isolation (tools/umma_rate_probe.cu)"}
         seg, _ = synth.regime_file(synth.BASE_SEED, 31, FRAMES_PER_FILE, 14, 26)
         scfg = N.SegmConfig(STEP, 0, 0, 0, 0, 22050, 0.5, 20, 22050)
         engine.segm_run(ctx, scfg, seg, norm)

@@ -218,7 +218,9 @@ __device__ __forceinline__ float sg_coeff_h(float G, float Sa, float hQa, float 
   const float S = Sa + Sb;
   const float t1 = S * inv4N;
   const float den = fmaf(-t1, S, hQa + hQb);
-  return __fdividef(fmaf(-t1, S, G), den);   // 0/0 -> NaN like the reference (constant windows)
+  float r;                                    // MUFU.RCP alone (__fdividef adds range scaling the operands never need):
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));   // den = 0 -> inf, and 0 * inf = NaN like the reference's 0/0
+  return fmaf(-t1, S, G) * r;
 }
 
 // GrayScale with colorWarp = 1 without FP64: clamp(floor(s * 255 + 0.5), 0, 255) computed exactly -- s * 255 = k + fr with
@@ -522,6 +524,10 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
           tc_ld16_nowait(laneAddr + colC + 16u * bt, uC);
         }
         tc_ld_wait();
+        if (useS) {      // spectral Gram = main + correction products
+#pragma unroll
+          for (int i = 0; i < 16; i++) uM[i] = __float_as_uint(__uint_as_float(uM[i]) + __uint_as_float(uC[i]));
+        }
         if (bt == 3) {   // all accumulators of this warp are in registers: hand the TMEM stage back to the issuer
           asm volatile("tcgen05.fence::before_thread_sync;");
           __syncwarp();
@@ -553,7 +559,7 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
             float temporal = 0.f, spectral = 0.f;
             if (useT) temporal = sg_coeff_h(__uint_as_float(uT[i]), wa.x, wa.y, wb.x, wb.y, invNT);
             if (kMode == 2 && p.loadT) temporal = tv[i];
-            if (useS) spectral = sg_coeff_h(__uint_as_float(uM[i]) + __uint_as_float(uC[i]), wa.z, wa.w, wb.z, wb.w, invNS);
+            if (useS) spectral = sg_coeff_h(__uint_as_float(uM[i]), wa.z, wa.w, wb.z, wb.w, invNS);
             const float sim = __fadd_rn(__fmul_rn(temporal, wT), __fmul_rn(spectral, wS));
             colr[i] = sg_grey(sim, b.colorScale, b.colorInv);
           }
@@ -582,7 +588,7 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
           float temporal = 0.f, spectral = 0.f;
           if (useT) temporal = sg_coeff_h(__uint_as_float(uT[i]), wa.x, wa.y, wb.x, wb.y, invNT);
           if (kMode == 2 && p.loadT) temporal = tv[i];
-          if (useS) spectral = sg_coeff_h(__uint_as_float(uM[i]) + __uint_as_float(uC[i]), wa.z, wa.w, wb.z, wb.w, invNS);
+          if (useS) spectral = sg_coeff_h(__uint_as_float(uM[i]), wa.z, wa.w, wb.z, wb.w, invNS);
           const float sim = __fadd_rn(__fmul_rn(temporal, wT), __fmul_rn(spectral, wS));
           colr[i] = sg_color(b, sim, warpOne);
           if (p.simMat && rowOk && c0 + i < ext && c0 + i >= a) p.simMat[(int64_t)a * ext + c0 + i] = sim;
