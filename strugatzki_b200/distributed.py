@@ -96,3 +96,46 @@ def sharded_search(job, device=None, group=None, trace: Optional[dict] = None) -
     res = job.result()
     mark("result")
     return res
+
+
+# ---------------------------------------------------------------------------------------------
+# SelfSimilarity: the matrix shards by blocks of image columns
+# ---------------------------------------------------------------------------------------------
+def selfsim_column_blocks(img_ext: int, world: int, tile: int = 128) -> List[tuple]:
+    """Column blocks [begin, end) of the upper triangle, one per rank, aligned to the kernel's tile size and balanced by
+    CELL count (column a holds img_ext - a cells, so the first blocks are narrower).  Blocks may be empty when the image
+    has fewer tiles than ranks."""
+    n_tiles = (img_ext + tile - 1) // tile
+    cells = np.array([sum(img_ext - a for a in range(t * tile, min((t + 1) * tile, img_ext))) for t in range(n_tiles)], np.float64)
+    cum = np.concatenate([[0.0], np.cumsum(cells)])
+    total = cum[-1]
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r / world
+        k = int(np.searchsorted(cum, target))            # first boundary at or beyond the target
+        if k > 0 and abs(cum[k - 1] - target) <= abs(cum[min(k, n_tiles)] - target):
+            k -= 1
+        cuts.append(min(max(k, cuts[-1]), n_tiles))
+    cuts.append(n_tiles)
+    return [(min(a * tile, img_ext), min(b * tile, img_ext)) for a, b in zip(cuts, cuts[1:])]
+
+
+def sharded_self_similarity(render, img_ext: int, device=None, group=None, dst: int = 0):
+    """One SelfSimilarity image rendered by all ranks of `group`: rank r calls `render(col_begin, col_end)` -- e.g.
+    `lambda b, e: engine.self_run(ctx, cfg, frames1, frames2, norm, b, e)[0]` with the feature file replicated on every
+    GPU -- for its column block and gets an (img_ext, img_ext) int32 image that holds only that block's pixels and their
+    mirrors (everything else 0).  Blocks write disjoint pixels, so the image is the SUM of the partial images: one
+    reduce to rank `dst` (NCCL over NVLink on GPUs, gloo in the CPU tests).  Returns the image on `dst`, None elsewhere.
+    No other communication: the Gram tiles are independent (SelfSimilarityImpl.scala:127-155 has no cross-cell state)."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    b, e = selfsim_column_blocks(img_ext, world)[rank]
+    part = render(b, e) if e > b else np.zeros((img_ext, img_ext), np.int32)
+    part = np.ascontiguousarray(part, np.int32)
+    assert part.shape == (img_ext, img_ext), part.shape
+    dev = device if device is not None else torch.device("cpu")
+    t = torch.from_numpy(part).to(dev)
+    dist.reduce(t, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy() if rank == dst else None

@@ -94,3 +94,59 @@ def test_gloo_world2_sharded_protocol():
     results = dict(q.get(timeout=10) for _ in range(2))
     assert results[0] == results[1]                                          # replicated merge -> identical result
     assert [m["file"] for m in results[0]] == [4, 3, 2]
+
+
+def _selfsim_worker(rank, world, port, q):
+    import os
+    import numpy as np
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from strugatzki_b200.distributed import selfsim_column_blocks, sharded_self_similarity
+    ext = 700
+    full = np.zeros((ext, ext), np.int32)
+    a, c = np.triu_indices(ext)                       # cell (a, c >= a): pixel (ext-1-c, a) and mirror (ext-1-a, c)
+    val = ((a * 131 + c * 7) % 255 + 1).astype(np.int32) * 0x010101
+    full[ext - 1 - c, a] = val
+    full[ext - 1 - a, c] = val
+
+    def render(b, e):                                 # what sgz_self_run(rowBegin = b, rowEnd = e) leaves in the image
+        img = np.zeros((ext, ext), np.int32)
+        m = (a >= b) & (a < e)
+        img[ext - 1 - c[m], a[m]] = val[m]
+        img[ext - 1 - a[m], c[m]] = val[m]
+        return img
+
+    got = sharded_self_similarity(render, ext)
+    blocks = selfsim_column_blocks(ext, world)
+    q.put((rank, None if got is None else bool(np.array_equal(got, full)), blocks))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_self_similarity_world2():
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 17
+    ps = [ctx.Process(target=_selfsim_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[0][1] is True and res[1][1] is None
+    assert res[0][2] == res[1][2]
+
+
+def test_selfsim_column_blocks_balanced():
+    from strugatzki_b200.distributed import selfsim_column_blocks
+    for ext, world in ((38707, 8), (29829, 4), (700, 2), (100, 8), (1, 2), (129, 3)):
+        blocks = selfsim_column_blocks(ext, world)
+        assert len(blocks) == world and blocks[0][0] == 0 and blocks[-1][1] == ext
+        assert all(b0[1] == b1[0] for b0, b1 in zip(blocks, blocks[1:]))
+        assert all(b % 128 == 0 or b == ext for blk in blocks for b in blk)
+        if ext > 128 * 8 * world:
+            cells = [sum(ext - a for a in range(b, e)) for b, e in blocks]
+            assert max(cells) < 1.15 * (sum(cells) / world), (ext, world, cells)

@@ -91,3 +91,25 @@ def test_search_is_idempotent_and_order_sensitive(ctx):
     # tensor-core kernel accumulates an offset's taps in a K order that depends on the offset's position in its tile)
     assert fwd[0]["file"] == 7 and rev[0]["file"] == 12 and abs(fwd[0]["sim"] - rev[0]["sim"]) < 1e-6
     assert fwd[0]["start"] == rev[0]["start"] == 500 * STEP
+
+
+@pytest.mark.parametrize("frames,decim,world", [(2000, 1, 3), (3000, 4, 2), (2400, 3, 4)])
+def test_selfsim_column_blocks_sum_to_full_image(ctx, frames, decim, world):
+    """SelfSimilarity shards by blocks of image columns (strugatzki_b200/distributed.py): the partial images of the
+    blocks hold disjoint pixels and add up to the image rendered in one go."""
+    from strugatzki_b200 import engine
+    from strugatzki_b200.distributed import selfsim_column_blocks
+    f1, _ = synth.regime_file(synth.BASE_SEED, 21, frames, 14, 6)
+    _, _, _, norm = synth.default_profile(14)
+    cfg = N.SelfConfig(STEP, 0, 0, 0, 0, 44100, decim, 0.5, 0, 1.0, 1.0, None, 0, 0)
+    full, g = engine.self_run(ctx, cfg, f1, None, norm)
+    assert engine.self_last_kernel(ctx) == "tc_gram"
+    ext = g["imgExt"]
+    blocks = selfsim_column_blocks(ext, world)
+    total = np.zeros_like(full)
+    for b, e in blocks:
+        if e > b:
+            part, _ = engine.self_run(ctx, cfg, f1, None, norm, b, e)
+            assert not np.any((total != 0) & (part != 0) & (total != part))
+            total += part
+    assert np.array_equal(total, full)

@@ -1,5 +1,6 @@
 """torchrun --nproc-per-node N tools/multi_gpu_check.py : a DB sharded over N GPUs must give EXACTLY the result
-of the same DB on one GPU (file-range sharding + all_gather of summaries / candidate records)."""
+of the same DB on one GPU (file-range sharding + all_gather of summaries / candidate records); a SelfSimilarity image
+rendered as column blocks on N GPUs must equal the image of one GPU."""
 import os
 import sys
 
@@ -11,7 +12,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 from strugatzki_b200 import _native as N, engine, synth  # noqa: E402
-from strugatzki_b200.distributed import sharded_search  # noqa: E402
+from strugatzki_b200.distributed import sharded_search, sharded_self_similarity  # noqa: E402
 
 
 def main():
@@ -53,6 +54,16 @@ def main():
             ok &= same
             print(f"{name}: {len(res)} matches, sharded x{world} == single GPU: {same}; top {res[0]}", flush=True)
             full.close()
+    # SelfSimilarity: column blocks of the image, one per GPU, summed on rank 0 == the image rendered by one GPU
+    seg, _ = synth.regime_file(synth.BASE_SEED, 21, 6000, 14, 8)
+    scfg = N.SelfConfig(512, 0, 0, 0, 0, 44100, 1, 0.5, 0, 1.0, 1.0, None, 0, 0)
+    ext = engine.self_geometry(scfg, seg.shape[0], seg.shape[0])["imgExt"]
+    img = sharded_self_similarity(lambda b, e: engine.self_run(ctx, scfg, seg, None, norm, b, e)[0], ext, dev, None)
+    if rank == 0:
+        ref, _ = engine.self_run(ctx, scfg, seg, None, norm)
+        same = bool(np.array_equal(img, ref))
+        ok &= same
+        print(f"self-similarity {ext} x {ext} ({engine.self_last_kernel(ctx)}): column blocks x{world} == single GPU: {same}", flush=True)
     if rank == 0:
         print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL", flush=True)
     dist.barrier()
