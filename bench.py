@@ -132,7 +132,7 @@ def reference_arm(args):
             "data": "synthetic", "config": config_block(args.gpus, note="bounded sample of the same workload"),
             "cpu_baseline": {"value": value, "unit": "offsets/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "offsets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -147,7 +147,25 @@ def config_block(n_gpus, files=6000, note=None):
     return c
 
 
+_JSON_FD = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of this run, on the real stdout (see main: libraries that print to fd 1 -- NCCL announces its
+    version there -- are pointed at stderr for the whole run)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)              # anything else written to stdout goes to stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -352,7 +370,7 @@ def main():
             "e2e": e2e, "cpu_baseline": cpu, "secondary": secondary,
             "matches": len(res), "needles_missing": len(missing), "top_sim": res[0]["sim"] if res else None,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
