@@ -108,11 +108,13 @@ int sgz_segm_run(sgz_ctx *ctx, const sgz_segm_config *cfg, int32_t numCh, const 
   SGZ_TRY(dOut.alloc((size_t)nb + 1));
   SGZ_TRY(dCount.alloc(1));
   SegmParams sp{x.p, stride, afLen, numCh, H, nOff, cfg->temporalWeight, dCurve.p};
-  PickParams pp{dCurve.p, nOff, afStart, H, step, nb, cfg->minSpacing, dOut.p, dCount.p};
+  const int pickShared = ((size_t)nb + 1) * sizeof(sgz_break) <= 8 * 1024;
+  const size_t pickSmem = kPickChunk * sizeof(float) + (pickShared ? ((size_t)nb + 1) * sizeof(sgz_break) : 0);
+  PickParams pp{dCurve.p, nOff, afStart, H, step, nb, cfg->minSpacing, dOut.p, dCount.p, pickShared};
   SGZ_TRY(ctx->begin_call());
   k_segm_curve<<<ceil_div(nOff, 128), 128, 0, ctx->stream>>>(sp);
   SGZ_LAUNCH_CHECK(ctx);
-  k_segm_pick<<<1, 32, 0, ctx->stream>>>(pp);
+  k_segm_pick<<<1, 32, pickSmem, ctx->stream>>>(pp);
   SGZ_LAUNCH_CHECK(ctx);
   SGZ_TRY(ctx->end_call());
   int count = 0;

@@ -138,51 +138,53 @@ struct PickParams {
   int64_t minSpacing;
   sgz_break *out;   // [numBreaks + 1]
   int *count;
+  int inShared;     // the sorted set lives in shared memory during the replay (numBreaks + 1 entries fit), else in `out`
 };
 
-// one warp walks the curve; lanes test 32 offsets per step and jump to the first state change
+// One warp walks the curve; lanes test 32 offsets per step and jump to the first state change.  The replay is a chain of
+// dependent steps, so what matters is the latency of one step: the curve is staged through shared memory in chunks
+// (coalesced, many loads in flight), the sorted set lives in shared memory, and ALL lanes run the (identical) state
+// machine, so that no state has to be broadcast after a change.
+constexpr int kPickChunk = 8192;
+
 __global__ void k_segm_pick(const PickParams p) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
+  extern __shared__ __align__(16) unsigned char pickSmem[];
+  float *chunk = reinterpret_cast<float *>(pickSmem);                                    // [kPickChunk]
+  sgz_break *store = p.inShared ? reinterpret_cast<sgz_break *>(pickSmem + kPickChunk * sizeof(float)) : p.out;
   BreakMachine mc;
-  mc.reset(p.out, p.numBreaks, p.minSpacing);
-  bool hs = mc.has_space();
-  float high = mc.highest();
-  int hasLast = 0;
-  float lastSim = 0.f;
-  int64_t lastPos = 0;
+  mc.reset(store, p.numBreaks, p.minSpacing);
   int pos = 0;
-  while (pos < p.nOff) {
-    const int t = pos + lane;
-    const bool active = t < p.nOff;
-    const float s = active ? p.curve[t] : 0.f;
-    bool change = false;
-    if (active) {
-      const bool accept = hs || s < high;
-      const int64_t bpos = (int64_t)(p.afStart + t + p.H) * p.step;
-      const bool collapse = hasLast && (bpos - lastPos) < p.minSpacing;
-      change = accept && (collapse ? (lastSim > s) : true);
+  for (int base = 0; base < p.nOff; base += kPickChunk) {
+    const int end = min(base + kPickChunk, p.nOff);
+    __syncwarp();
+    for (int i = base + lane; i < end; i += 32) chunk[i - base] = p.curve[i];
+    __syncwarp();
+    while (pos < end) {
+      const int t = pos + lane;
+      const bool active = t < end;
+      const float s = active ? chunk[t - base] : 0.f;
+      bool change = false;
+      if (active) {
+        const bool accept = mc.has_space() || s < mc.highest();
+        const int64_t bpos = (int64_t)(p.afStart + t + p.H) * p.step;
+        const bool collapse = mc.hasLast && (bpos - mc.last.pos) < p.minSpacing;
+        change = accept && (collapse ? (mc.last.sim > s) : true);
+      }
+      const unsigned mask = __ballot_sync(full, change);
+      if (mask == 0u) { pos += 32; continue; }
+      const int l = __ffs(mask) - 1;
+      const int ts = pos + l;
+      const float ss = __shfl_sync(full, s, l);
+      mc.add(sgz_break{ss, 0, (int64_t)(p.afStart + ts + p.H) * p.step});   // same arguments, same writes on every lane
+      __syncwarp();
+      pos = ts + 1;
     }
-    const unsigned mask = __ballot_sync(full, change);
-    if (mask == 0u) { pos += 32; continue; }
-    const int l = __ffs(mask) - 1;
-    const int ts = pos + l;
-    const float ss = __shfl_sync(full, s, l);
-    if (lane == 0) {
-      sgz_break b{ss, 0, (int64_t)(p.afStart + ts + p.H) * p.step};
-      mc.add(b);
-      hs = mc.has_space();
-      high = mc.highest();
-      hasLast = mc.hasLast;
-      lastSim = mc.last.sim;
-      lastPos = mc.last.pos;
-    }
-    hs = __shfl_sync(full, (int)hs, 0) != 0;
-    high = __shfl_sync(full, high, 0);
-    hasLast = __shfl_sync(full, hasLast, 0);
-    lastSim = __shfl_sync(full, lastSim, 0);
-    lastPos = __shfl_sync(full, lastPos, 0);
-    pos = ts + 1;
+  }
+  if (p.inShared) {
+    __syncwarp();
+    for (int i = lane; i < mc.n; i += 32) p.out[i] = store[i];
   }
   if (lane == 0) *p.count = mc.n;
 }
