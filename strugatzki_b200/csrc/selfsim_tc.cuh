@@ -223,6 +223,18 @@ __device__ __forceinline__ float sg_coeff_h(float G, float Sa, float hQa, float 
   return fmaf(-t1, S, G) * r;
 }
 
+// both groups at once on the packed FP32 pipe (FADD2 / FMUL2 / FFMA2): x = temporal, y = spectral
+__device__ __forceinline__ float2 sg_coeff2(float2 G, float2 Sa, float2 hQa, float2 Sb, float2 hQb, float2 negInv4N) {
+  const float2 S = __fadd2_rn(Sa, Sb);
+  const float2 nt1 = __fmul2_rn(S, negInv4N);                 // -S / 4N
+  const float2 den = __ffma2_rn(nt1, S, __fadd2_rn(hQa, hQb));
+  const float2 num = __ffma2_rn(nt1, S, G);
+  float rx, ry;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rx) : "f"(den.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ry) : "f"(den.y));
+  return __fmul2_rn(num, make_float2(rx, ry));
+}
+
 // GrayScale with colorWarp = 1 without FP64: clamp(floor(s * 255 + 0.5), 0, 255) computed exactly -- s * 255 = k + fr with
 // k = trunc, fr = exact remainder, so the reference's (int)((double) f + 0.5) is k + (fr >= 0.5); NaN -> 0 like d2i_java
 __device__ __forceinline__ int32_t sg_grey(float sim, float colorScale, int colorInv) {
@@ -403,13 +415,18 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
           if (prof) tI = clock64();
           tc_wait<false>(recFull + rs, rsPar);
           if (prof) { iRec += clock64() - tI; tI = clock64(); }
-          if (c == cBegin && tileIt >= (uint32_t)accStages)
+          // One-launch mode with both groups: the temporal region alternates between columns 0 and 384, so the 18 temporal
+          // MMAs of tile n + 1 run while the epilogue still reads tile n (the region they overwrite was drained with tile
+          // n - 1); only the spectral regions wait for the epilogue.
+          const bool waitHere = kMode == 0 ? c == 1 : c == cBegin;
+          if (waitHere && tileIt >= (uint32_t)accStages)
             tc_wait<false>(accEmpty + as, ((tileIt / accStages) - 1) & 1);   // the epilogue has drained this TMEM stage
           if (prof) { iAcc += clock64() - tI; tI = clock64(); }
           asm volatile("tcgen05.fence::after_thread_sync;");
           // regions of the stage: temporal = one region for all three products; spectral = main + correction, after the
           // temporal region when both groups share a launch
-          const uint32_t dMain = accBase + (c == 0 ? 0u : (kDoT ? 128u : 0u)), dCorr = c == 0 ? dMain : dMain + 128u;
+          const uint32_t dMain = accBase + (c == 0 ? ((kMode == 0 && (tileIt & 1)) ? 384u : 0u) : (kDoT ? 128u : 0u));
+          const uint32_t dCorr = c == 0 ? dMain : dMain + 128u;
           const uint64_t a1 = A1 + stageU * rs, a2 = a1 + partU, b1 = a1 + 2 * partU, b2 = a1 + 3 * partU;
           const uint64_t t1 = T1 + stageU * rs, t2 = t1 + 256;
           const uint32_t accFirst = (c == 0 || c == 1) ? 0u : 1u;   // first MMA into a region of this tile overwrites
@@ -443,7 +460,8 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
         if (c == cBegin && tileIt >= (uint32_t)accStages)
           tc_wait<false>(accEmpty + as, ((tileIt / accStages) - 1) & 1);   // the epilogue has drained this TMEM stage
         iAcc += clock64() - tI;
-        const uint32_t dMain = accBase + (c == 0 ? 0u : (kDoT ? 128u : 0u)), dCorr = c == 0 ? dMain : dMain + 128u;
+        const uint32_t dMain = accBase + (c == 0 ? ((kMode == 0 && (tileIt & 1)) ? 384u : 0u) : (kDoT ? 128u : 0u));
+        const uint32_t dCorr = c == 0 ? dMain : dMain + 128u;
         for (int slab = 0; slab < p.nSlab; slab++, slabCtr++) {
           const int st = slabCtr % p.nStage;
           const uint32_t use = slabCtr / p.nStage;
@@ -496,15 +514,19 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
       const int2 tl = p.tiles[t];
       const int ta = tl.x, tb = tl.y;
       sg_epi_sync();                                       // everybody is done with the previous tile's column sums
-      if (et < 128) {                                      // column sums as (S_T, Q_T / 2, S_S, Q_S / 2)
-        float4 w = tb + et < ext ? p.wsB[tb + et] : make_float4(0.f, 0.f, 0.f, 0.f);
-        w.y *= 0.5f; w.w *= 0.5f;
-        colW[et] = w;
+      if (et < 128) {                                      // column sums as (S_T, S_S, Q_T / 2, Q_S / 2)
+        const float4 w = tb + et < ext ? p.wsB[tb + et] : make_float4(0.f, 0.f, 0.f, 0.f);
+        colW[et] = make_float4(w.x, w.z, 0.5f * w.y, 0.5f * w.w);
       }
       sg_epi_sync();
       const int a = ta + quarter * 32 + lane;
-      float4 wa = a < ext ? p.wsA[a] : make_float4(0.f, 0.f, 0.f, 0.f);
-      wa.y *= 0.5f; wa.w *= 0.5f;
+      float4 wa;
+      {
+        const float4 w = a < ext ? p.wsA[a] : make_float4(0.f, 0.f, 0.f, 0.f);
+        wa = make_float4(w.x, w.z, 0.5f * w.y, 0.5f * w.w);
+      }
+      const float2 waS = make_float2(wa.x, wa.y), waQ = make_float2(wa.z, wa.w);
+      const float2 negInv = make_float2(-invNT, -invNS);
       const bool rowOk = a < ext && a >= b.colBegin && a < b.colEnd;
       // interior tile (all 128 x 128 cells exist, strictly above the diagonal): no per-cell predicates, 32-bit pixel
       // offsets (imgExt <= 0xB504, so imgExt^2 < 2^31); the pixel path also needs the plain grey scale
@@ -518,7 +540,7 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
 #pragma unroll 1
       for (int bt = 0; bt < 4; bt++) {
         uint32_t uT[16], uM[16], uC[16];
-        if (useT) tc_ld16_nowait(laneAddr + colT + 16u * bt, uT);
+        if (useT) tc_ld16_nowait(laneAddr + ((kMode == 0 && (tileIt & 1)) ? 384u : colT) + 16u * bt, uT);
         if (useS) {
           tc_ld16_nowait(laneAddr + colM + 16u * bt, uM);
           tc_ld16_nowait(laneAddr + colC + 16u * bt, uC);
@@ -540,7 +562,7 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
 #pragma unroll
           for (int i = 0; i < 16; i++) {
             const float4 wb = cw[i];
-            const float temporal = sg_coeff_h(__uint_as_float(uT[i]), wa.x, wa.y, wb.x, wb.y, invNT);
+            const float temporal = sg_coeff_h(__uint_as_float(uT[i]), wa.x, wa.z, wb.x, wb.z, invNT);
             if (interior || (a < ext && c0 + i < ext)) p.corrT[(int64_t)(c0 + i) * ext + a] = temporal;
           }
           continue;
@@ -556,11 +578,19 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
 #pragma unroll
           for (int i = 0; i < 16; i++) {
             const float4 wb = cw[i];
-            float temporal = 0.f, spectral = 0.f;
-            if (useT) temporal = sg_coeff_h(__uint_as_float(uT[i]), wa.x, wa.y, wb.x, wb.y, invNT);
-            if (kMode == 2 && p.loadT) temporal = tv[i];
-            if (useS) spectral = sg_coeff_h(__uint_as_float(uM[i]), wa.z, wa.w, wb.z, wb.w, invNS);
-            const float sim = __fadd_rn(__fmul_rn(temporal, wT), __fmul_rn(spectral, wS));
+            float sim;
+            if (kMode == 0) {   // both groups from TMEM: one packed evaluation
+              const float2 cf = sg_coeff2(make_float2(__uint_as_float(uT[i]), __uint_as_float(uM[i])), waS, waQ,
+                                          make_float2(wb.x, wb.y), make_float2(wb.z, wb.w), negInv);
+              const float2 bl = __fmul2_rn(cf, make_float2(wT, wS));
+              sim = __fadd_rn(bl.x, bl.y);
+            } else {
+              float temporal = 0.f, spectral = 0.f;
+              if (useT) temporal = sg_coeff_h(__uint_as_float(uT[i]), wa.x, wa.z, wb.x, wb.z, invNT);
+              if (kMode == 2 && p.loadT) temporal = tv[i];
+              if (useS) spectral = sg_coeff_h(__uint_as_float(uM[i]), wa.y, wa.w, wb.y, wb.w, invNS);
+              sim = __fadd_rn(__fmul_rn(temporal, wT), __fmul_rn(spectral, wS));
+            }
             colr[i] = sg_grey(sim, b.colorScale, b.colorInv);
           }
           // the pixel (image row ext-1-c, x = a: coalesced over the lanes) and the transpose buffer
@@ -586,9 +616,9 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
         for (int i = 0; i < 16; i++) {
           const float4 wb = cw[i];
           float temporal = 0.f, spectral = 0.f;
-          if (useT) temporal = sg_coeff_h(__uint_as_float(uT[i]), wa.x, wa.y, wb.x, wb.y, invNT);
+          if (useT) temporal = sg_coeff_h(__uint_as_float(uT[i]), wa.x, wa.z, wb.x, wb.z, invNT);
           if (kMode == 2 && p.loadT) temporal = tv[i];
-          if (useS) spectral = sg_coeff_h(__uint_as_float(uM[i]), wa.z, wa.w, wb.z, wb.w, invNS);
+          if (useS) spectral = sg_coeff_h(__uint_as_float(uM[i]), wa.y, wa.w, wb.y, wb.w, invNS);
           const float sim = __fadd_rn(__fmul_rn(temporal, wT), __fmul_rn(spectral, wS));
           colr[i] = sg_color(b, sim, warpOne);
           if (p.simMat && rowOk && c0 + i < ext && c0 + i >= a) p.simMat[(int64_t)a * ext + c0 + i] = sim;
