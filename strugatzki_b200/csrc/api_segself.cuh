@@ -284,6 +284,8 @@ static int self_fast_image(sgz_ctx *ctx, const sgz_self_config *cfg, sgz::SelfPa
     }
     tp.simMat = simMat;
     tp.aDesc = G.aDesc;
+    static const int dumpEnv = getenv("SGZ_SELF_TC_DUMP") ? atoi(getenv("SGZ_SELF_TC_DUMP")) : -1;
+    tp.dump = dumpEnv >= 0 ? std::min(dumpEnv, G.dump) : G.dump;
     SGZ_CUDA(cudaFuncSetAttribute(k_self_gram_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));
     SGZ_CUDA(cudaFuncSetAttribute(k_self_gram_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));
     SGZ_CUDA(cudaFuncSetAttribute(k_self_gram_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));
@@ -322,10 +324,10 @@ static int self_fast_image(sgz_ctx *ctx, const sgz_self_config *cfg, sgz::SelfPa
         double a[16] = {0};
         for (unsigned bk = 0; bk < gridTc; bk++) for (int k = 0; k < 16; k++) a[k] += (double)h[(size_t)bk * 16 + k];
         const double tiles = a[5] > 0 ? a[5] : 1;
-        fprintf(stderr, "k_self_gram_tc pass %d/%d cycles per tile (aDesc %d, %d stages of %d K steps, %d record stages): issuer total %.0f | "
+        fprintf(stderr, "k_self_gram_tc pass %d/%d cycles per tile (aDesc %d, %d stages of %d K steps, %d record stages, %d parked batches): issuer total %.0f | "
                         "records %.0f, wait accEmpty %.0f, wait full %.0f, issue %.0f || builder total %.0f | wait records %.0f, "
                         "wait empty %.0f, build %.0f || epilogue wait accFull %.0f, main %.0f\n",
-                pass + 1, nPass, tp.aDesc, tp.nStage, tp.slabKs, tp.nRecStage, a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles,
+                pass + 1, nPass, tp.aDesc, tp.nStage, tp.slabKs, tp.nRecStage, tp.dump, a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles,
                 a[4] / tiles, a[8] / tiles, a[9] / tiles, a[10] / tiles, a[11] / tiles, a[12] / tiles, a[13] / tiles);
       }
     }

@@ -36,6 +36,7 @@ struct SelfTcGeom {
   int g, dp, kcStep, span;    // record grid (see above); span = records one operand stage holds
   int nStage;                 // ring depth (slabs)
   int nRecStage;              // record stages (channels requested ahead + 1)
+  int dump;                   // accumulator batches (32 KB each) the epilogue may park in shared memory
   int aDesc;                  // decim | 8: A and B are read in place from the record stages
   uint32_t matBytes, stageBytes;
   uint32_t recPartBytes, recStageBytes, tailBytes;
@@ -65,8 +66,14 @@ inline SelfTcGeom self_tc_geom(int H, int decim, size_t smemLimit, bool allowADe
     G.recStageBytes = (4u * G.recPartBytes + G.tailBytes + 127u) / 128u * 128u;
     G.slabKs = G.nks; G.nSlab = 1; G.nStage = 0; G.matBytes = 0; G.stageBytes = 0;
     const size_t fixed = (size_t)kSgEpiWarps * 32 * kSgPPitch * 4 + 128 * 16 + 512 + 1024;
-    G.nRecStage = (int)std::min<size_t>(8, (smemLimit - fixed) / G.recStageBytes);
-    G.smemBytes = fixed + (size_t)G.nRecStage * G.recStageBytes;
+    // shared memory = record ring + parked accumulators: as many parked batches as leave a ring of >= 5 stages
+    G.dump = 0;
+    for (int d = 3; d >= 0; d--) {
+      const size_t left = smemLimit - fixed - (size_t)d * 32768;
+      if (smemLimit >= fixed + (size_t)d * 32768 && left / G.recStageBytes >= (size_t)(d > 0 ? 5 : 3)) { G.dump = d; break; }
+    }
+    G.nRecStage = (int)std::min<size_t>(8, (smemLimit - fixed - (size_t)G.dump * 32768) / G.recStageBytes);
+    G.smemBytes = fixed + (size_t)G.dump * 32768 + (size_t)G.nRecStage * G.recStageBytes;
     G.ok = G.nRecStage >= 3;
     if (G.ok) return G;
     G.aDesc = 0;
@@ -114,6 +121,7 @@ struct SelfTcParams {
   //   pass 2 (doS, loadT):  spectral group, main + correction regions (2 tiles in flight), reads corrT, writes pixels.
   // A single group (weight 0 or 1) is one launch with doT or doS alone.
   int storeT, loadT;         // (which groups a launch computes is the kernel's template argument)
+  int dump;                  // batches of accumulators the epilogue parks in shared memory to release TMEM early (0..3)
   float *corrT;              // [imgExt][imgExt], element [c][a] (column-major so that lanes = rows a are coalesced)
 };
 
@@ -204,6 +212,22 @@ __device__ __forceinline__ void tc_mma_acc(uint32_t tmemD, uint64_t da, uint64_t
       "l"(da), "l"(db), "r"(idesc)
       : "memory");
 }
+// A-operand collector: `fill` keeps the fetched A in the tensor core's operand buffer, `lastuse` takes it from there
+// instead of shared memory (SASS: UTCHMMA ... .A_KEEP / .A_REUSE).  Shared-memory bandwidth is what bounds this kernel.
+__device__ __forceinline__ void tc_mma_fill(uint32_t tmemD, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmemD),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_lastuse(uint32_t tmemD, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmemD),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void sg_epi_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
 __device__ __forceinline__ float sg_coeff(float G, float Sa, float Qa, float Sb, float Qb, float inv4N) {
@@ -274,6 +298,7 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
   uint64_t *full = bars, *empty = bars + 4, *recFull = bars + 8, *recEmpty = bars + 16, *accFull = bars + 24,
            *accEmpty = bars + 28;
   uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(bars + 32);
+  float *dump = reinterpret_cast<float *>(bars + 64);                        // [dump][16 columns][T, S][256 epilogue threads]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
@@ -431,16 +456,14 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
           const uint64_t t1 = T1 + stageU * rs, t2 = t1 + 256;
           const uint32_t accFirst = (c == 0 || c == 1) ? 0u : 1u;   // first MMA into a region of this tile overwrites
           if (tc_elect()) {
-            // one chain of main products, one of corrections (the temporal group keeps all products in one region)
-            for (int ks = 0; ks < nIn; ks++) tc_mma(dMain, a1 + inc * ks, b1 + inc * ks, idesc, ks > 0 ? 1u : accFirst);
-            if (nIn < nks) tc_mma(dMain, a1 + inc * nIn, t1, idesc, nIn > 0 ? 1u : accFirst);
-            for (int ks = 0; ks < nIn; ks++) {
-              tc_mma(dCorr, a2 + inc * ks, b1 + inc * ks, idesc, (ks > 0 || c == 0) ? 1u : accFirst);
-              tc_mma_acc(dCorr, a1 + inc * ks, b2 + inc * ks, idesc);
-            }
-            if (nIn < nks) {
-              tc_mma(dCorr, a2 + inc * nIn, t1, idesc, (nIn > 0 || c == 0) ? 1u : accFirst);
-              tc_mma_acc(dCorr, a1 + inc * nIn, t2, idesc);
+            // per K step: a1 b1 -> main, a1 b2 -> correction (A taken from the collector, not from shared memory again),
+            // a2 b1 -> correction.  (Changing the accumulator between MMAs costs nothing: tools/umma_rate_probe.cu.)
+            for (int ks = 0; ks < nks; ks++) {
+              const uint64_t x1 = a1 + inc * ks, x2 = a2 + inc * ks;
+              const uint64_t y1 = ks < nIn ? b1 + inc * ks : t1, y2 = ks < nIn ? b2 + inc * ks : t2;
+              tc_mma_fill(dMain, x1, y1, idesc, ks > 0 ? 1u : accFirst);
+              tc_mma_lastuse(dCorr, x1, y2, idesc, (ks > 0 || c == 0) ? 1u : accFirst);
+              tc_mma_acc(dCorr, x2, y1, idesc);
             }
             tc_commit(recEmpty + rs);                              // the MMAs read the record stage
             if (c + 1 == cEnd) tc_commit(accFull + as);
@@ -537,23 +560,54 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
       eAcc += clock64() - tE; tE = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;");
       const uint32_t laneAddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * accCols + 64u * (uint32_t)half;
+      // TMEM holds ONE tile in the one-launch mode, so the next tile's MMAs wait until the last accumulator has been read.
+      // To shorten that, the accumulators of the last `dump` batches are first copied to shared memory (a thread reads
+      // back only what it wrote: no synchronisation), the TMEM stage is released after the load of batch 3 - dump, and
+      // the dumped batches are evaluated from shared memory while the MMAs of the next tile already run.
+      const int D = p.dump;
+      const uint32_t colTt = (kMode == 0 && (tileIt & 1)) ? 384u : colT;
 #pragma unroll 1
-      for (int bt = 0; bt < 4; bt++) {
+      for (int bt = 4 - D; bt < 4; bt++) {
         uint32_t uT[16], uM[16], uC[16];
-        if (useT) tc_ld16_nowait(laneAddr + ((kMode == 0 && (tileIt & 1)) ? 384u : colT) + 16u * bt, uT);
+        if (useT) tc_ld16_nowait(laneAddr + colTt + 16u * bt, uT);
         if (useS) {
           tc_ld16_nowait(laneAddr + colM + 16u * bt, uM);
           tc_ld16_nowait(laneAddr + colC + 16u * bt, uC);
         }
         tc_ld_wait();
-        if (useS) {      // spectral Gram = main + correction products
+        float *dp = dump + (size_t)(bt - (4 - D)) * (2 * 16 * kSgEpiWarps * 32) + et;
 #pragma unroll
-          for (int i = 0; i < 16; i++) uM[i] = __float_as_uint(__uint_as_float(uM[i]) + __uint_as_float(uC[i]));
+        for (int i = 0; i < 16; i++) {
+          if (useT) dp[(2 * i) * (kSgEpiWarps * 32)] = __uint_as_float(uT[i]);
+          if (useS) dp[(2 * i + 1) * (kSgEpiWarps * 32)] = __uint_as_float(uM[i]) + __uint_as_float(uC[i]);
         }
-        if (bt == 3) {   // all accumulators of this warp are in registers: hand the TMEM stage back to the issuer
-          asm volatile("tcgen05.fence::before_thread_sync;");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(accEmpty + as);
+      }
+#pragma unroll 1
+      for (int bt = 0; bt < 4; bt++) {
+        uint32_t uT[16], uM[16], uC[16];
+        if (bt < 4 - D) {
+          if (useT) tc_ld16_nowait(laneAddr + colTt + 16u * bt, uT);
+          if (useS) {
+            tc_ld16_nowait(laneAddr + colM + 16u * bt, uM);
+            tc_ld16_nowait(laneAddr + colC + 16u * bt, uC);
+          }
+          tc_ld_wait();
+          if (useS) {      // spectral Gram = main + correction products
+#pragma unroll
+            for (int i = 0; i < 16; i++) uM[i] = __float_as_uint(__uint_as_float(uM[i]) + __uint_as_float(uC[i]));
+          }
+          if (bt == 3 - D) {   // the last accumulators are out of TMEM: hand the stage back to the issuer
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(accEmpty + as);
+          }
+        } else {
+          const float *dp = dump + (size_t)(bt - (4 - D)) * (2 * 16 * kSgEpiWarps * 32) + et;
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            if (useT) uT[i] = __float_as_uint(dp[(2 * i) * (kSgEpiWarps * 32)]);
+            if (useS) uM[i] = __float_as_uint(dp[(2 * i + 1) * (kSgEpiWarps * 32)]);
+          }
         }
         const int c0 = tb + 64 * half + 16 * bt;
         const float4 *cw = colW + 64 * half + 16 * bt;
