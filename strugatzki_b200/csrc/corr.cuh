@@ -234,6 +234,8 @@ inline int run_scan_tc(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim, 
   SGZ_CUDA(cudaFuncSetAttribute(k_corr_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));
   const unsigned gridTc = (unsigned)std::min<int64_t>(job->numTilesTc, ctx->smCount);
   DevBuf<long long> dProf;
+  static const bool chainOrder = getenv("SGZ_CORR_TC_CHAIN") && atoi(getenv("SGZ_CORR_TC_CHAIN")) == 1;
+  tp.chainOrder = chainOrder;
   const bool prof = getenv("SGZ_CORR_TC_PROF") != nullptr;   // developer probe: where does the issuer lane wait?
   if (prof) {
     SGZ_TRY(dProf.alloc((size_t)gridTc * 24));

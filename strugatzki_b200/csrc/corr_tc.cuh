@@ -104,6 +104,7 @@ struct CorrTcParams {
   float *sim, *boost;
   unsigned long long *fileMax;  // [numFiles] packed (order_key(sim) << 32 | ~offset), or nullptr
   long long *prof;              // developer probe (SGZ_CORR_TC_PROF): per CTA 16 cycle counters, or nullptr
+  int chainOrder;               // developer knob (SGZ_CORR_TC_CHAIN=1): one chain per product instead of the per-K-step order
 };
 
 __device__ __forceinline__ uint64_t tc_desc(uint32_t addr, uint32_t sbo, uint32_t layout) {
@@ -114,6 +115,22 @@ __device__ __forceinline__ void tc_mma(uint32_t tmemD, uint64_t da, uint64_t db,
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmemD),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// A-operand collector: `fill` keeps the fetched A in the tensor core's operand buffer, `lastuse` takes it from there
+// instead of shared memory (SASS: UTCHMMA ... .A_KEEP / .A_REUSE)
+__device__ __forceinline__ void tc_mma_fill(uint32_t tmemD, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmemD),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_lastuse(uint32_t tmemD, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmemD),
       "l"(da), "l"(db), "r"(idesc), "r"(acc)
       : "memory");
 }
@@ -326,13 +343,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_corr_tc(const CorrTcParams p)
           const bool started = c == 0 ? corrStartedT : corrStartedS;
           if (c == 0) corrStartedT = true; else corrStartedS = true;
           if (tc_elect()) {
-            // one K step of 16: A start +32 B (2 descriptor units), taps start +2 atoms = 512 B (32 units)
-            uint64_t da = aHi, db = tHi;
-            for (int s = 0; s < G.KS; s++, da += 2, db += 32) tc_mma(dMain, da, db, idesc, s > 0);
-            da = aLo; db = tHi;
-            for (int s = 0; s < G.KS; s++, da += 2, db += 32) tc_mma(dCorr, da, db, idesc, started || s > 0);
-            da = aHi; db = tLo;
-            for (int s = 0; s < G.KS; s++, da += 2, db += 32) tc_mma(dCorr, da, db, idesc, 1);
+            // one K step of 16: A start +32 B (2 descriptor units), taps start +2 atoms = 512 B (32 units).
+            // N = 32 MMAs are bound by the fetch of the 4 KB A operand: per K step a1 t1 and a1 t2 share A through the
+            // operand collector (.collector::a::fill / lastuse), so two of three MMAs fetch it (changing the
+            // accumulator between MMAs costs nothing, tools/umma_rate_probe.cu).  SGZ_CORR_TC_CHAIN=1: the round-1 order.
+            if (p.chainOrder) {
+              uint64_t da = aHi, db = tHi;
+              for (int s = 0; s < G.KS; s++, da += 2, db += 32) tc_mma(dMain, da, db, idesc, s > 0);
+              da = aLo; db = tHi;
+              for (int s = 0; s < G.KS; s++, da += 2, db += 32) tc_mma(dCorr, da, db, idesc, started || s > 0);
+              da = aHi; db = tLo;
+              for (int s = 0; s < G.KS; s++, da += 2, db += 32) tc_mma(dCorr, da, db, idesc, 1);
+            } else {
+              uint64_t d1 = aHi, d2 = aLo, b1 = tHi, b2 = tLo;
+              for (int s = 0; s < G.KS; s++, d1 += 2, d2 += 2, b1 += 32, b2 += 32) {
+                tc_mma_fill(dMain, d1, b1, idesc, s > 0);
+                tc_mma_lastuse(dCorr, d1, b2, idesc, started || s > 0);
+                tc_mma(dCorr, d2, b1, idesc, 1);
+              }
+            }
           }
         }
         if (tc_elect()) {

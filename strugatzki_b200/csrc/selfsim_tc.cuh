@@ -212,22 +212,6 @@ __device__ __forceinline__ void tc_mma_acc(uint32_t tmemD, uint64_t da, uint64_t
       "l"(da), "l"(db), "r"(idesc)
       : "memory");
 }
-// A-operand collector: `fill` keeps the fetched A in the tensor core's operand buffer, `lastuse` takes it from there
-// instead of shared memory (SASS: UTCHMMA ... .A_KEEP / .A_REUSE).  Shared-memory bandwidth is what bounds this kernel.
-__device__ __forceinline__ void tc_mma_fill(uint32_t tmemD, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmemD),
-      "l"(da), "l"(db), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void tc_mma_lastuse(uint32_t tmemD, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmemD),
-      "l"(da), "l"(db), "r"(idesc), "r"(acc)
-      : "memory");
-}
 __device__ __forceinline__ void sg_epi_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
 __device__ __forceinline__ float sg_coeff(float G, float Sa, float Qa, float Sb, float Qb, float inv4N) {
