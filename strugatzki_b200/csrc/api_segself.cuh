@@ -218,6 +218,11 @@ static int self_fast_image(sgz_ctx *ctx, const sgz_self_config *cfg, sgz::SelfPa
   SGZ_CUDA(cudaMemcpyAsync(means, dMeans.p, sizeof means, cudaMemcpyDeviceToHost, ctx->stream));
   SGZ_CUDA(cudaMemcpyAsync(amaxBits, dAmax.p, sizeof amaxBits, cudaMemcpyDeviceToHost, ctx->stream));
   SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (!std::isfinite(means[0]) || !std::isfinite(means[1])) {   // NaN / Inf features: not for the centred Gram forms
+    SGZ_TRY(ctx->end_call());
+    if (usedTc) *usedTc = -1;
+    return SGZ_OK;
+  }
   SelfFastParams fp{};
   fp.base = p;
   fp.shiftT = (float)(means[0] / (double)need);
@@ -235,8 +240,9 @@ static int self_fast_image(sgz_ctx *ctx, const sgz_self_config *cfg, sgz::SelfPa
     float aT, aS;
     memcpy(&aT, &amaxBits[0], 4);
     memcpy(&aS, &amaxBits[1], 4);
-    const double bound = std::max((double)aT + std::fabs((double)fp.shiftT), (double)aS + std::fabs((double)fp.shiftS));
-    if (!std::isfinite(bound)) tc = false;
+    const double bT = (double)aT + std::fabs((double)fp.shiftT), bS = (double)aS + std::fabs((double)fp.shiftS);
+    const double bound = std::max(bT, bS);
+    if (!std::isfinite(bT) || !std::isfinite(bS)) tc = false;   // (std::max alone would drop a NaN operand)
     else if (bound > 0) scale = (float)std::ldexp(1.0, std::max(-60, std::min(60, (int)std::floor(std::log2(8192.0 / bound)))));
   }
   if (tc) {
@@ -377,13 +383,6 @@ int sgz_self_run(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh, const 
   SGZ_REQUIRE(!rgb || rgbCap >= (int64_t)ext * ext, "rgb buffer too small for %d x %d pixels", ext, ext);
   SGZ_TRY(dRgb.alloc((size_t)ext * ext));
   SGZ_CUDA(cudaMemsetAsync(dRgb.p, 0, (size_t)ext * ext * sizeof(int32_t), ctx->stream));
-  std::vector<int2> tiles;
-  if (cfg->precise || H < 16) {
-    for (int a0 = rowBegin / kSelfTile * kSelfTile; a0 < rowEnd; a0 += kSelfTile)
-      for (int b0 = a0 / kSelfTile * kSelfTile; b0 < ext; b0 += kSelfTile) tiles.push_back(make_int2(a0, b0));
-    SGZ_TRY(dTiles.alloc(tiles.size()));
-    SGZ_CUDA(cudaMemcpyAsync(dTiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
-  }
   p.colBegin = rowBegin;
   p.colEnd = rowEnd;
   p.rgb = dRgb.p;
@@ -391,13 +390,23 @@ int sgz_self_run(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh, const 
   // the file mean relative to its own spread, and the exact replay costs O(H) per cell anyway.
   const bool precise = cfg->precise || H < 16;
   if (!precise) {
-    SGZ_TRY(self_fast_image(ctx, cfg, p, g, H, numCh, frames2 != nullptr, rowBegin, rowEnd, nullptr, nullptr));
-    if (rgb) {
-      SGZ_CUDA(cudaMemcpyAsync(rgb, dRgb.p, (size_t)ext * ext * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-      SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    int used = 0;
+    SGZ_TRY(self_fast_image(ctx, cfg, p, g, H, numCh, frames2 != nullptr, rowBegin, rowEnd, nullptr, &used));
+    if (used >= 0) {
+      if (rgb) {
+        SGZ_CUDA(cudaMemcpyAsync(rgb, dRgb.p, (size_t)ext * ext * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+      }
+      return SGZ_OK;
     }
-    return SGZ_OK;
+    // used < 0: NaN / Inf in the features.  The Gram forms centre the data by the file mean, which would smear one bad
+    // frame over the whole image; the exact replay keeps it local to the windows over that frame, like the reference.
   }
+  std::vector<int2> tiles;
+  for (int a0 = rowBegin / kSelfTile * kSelfTile; a0 < rowEnd; a0 += kSelfTile)
+    for (int b0 = a0 / kSelfTile * kSelfTile; b0 < ext; b0 += kSelfTile) tiles.push_back(make_int2(a0, b0));
+  SGZ_TRY(dTiles.alloc(tiles.size()));
+  SGZ_CUDA(cudaMemcpyAsync(dTiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
   const size_t smem = (size_t)2 * numCh * (g.decim * (kSelfTile - 1) + H) * sizeof(float);
   SGZ_REQUIRE(smem <= ctx->smemOptin, "self-similarity tile needs %zu bytes of shared memory", smem);
   SGZ_CUDA(cudaFuncSetAttribute(k_self_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemOptin));
@@ -451,12 +460,17 @@ int sgz_self_cells(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh, cons
     double means[2];
     SGZ_CUDA(cudaMemcpyAsync(means, dMeans.p, sizeof means, cudaMemcpyDeviceToHost, ctx->stream));
     SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
-    SelfFastParams fp{};
-    fp.base = p;
-    fp.shiftT = (float)(means[0] / (double)need);
-    fp.shiftS = (float)(means[1] / ((double)need * (numCh - 1)));
-    k_self_cells_fast<<<(unsigned)ceil_div<int64_t>(nCells, 128), 128, 0, ctx->stream>>>(fp);
-    SGZ_LAUNCH_CHECK(ctx);
+    if (!std::isfinite(means[0]) || !std::isfinite(means[1])) {   // NaN / Inf features: exact replay (see sgz_self_run)
+      k_self_cells<<<(unsigned)ceil_div<int64_t>(nCells, 128), 128, 0, ctx->stream>>>(p);
+      SGZ_LAUNCH_CHECK(ctx);
+    } else {
+      SelfFastParams fp{};
+      fp.base = p;
+      fp.shiftT = (float)(means[0] / (double)need);
+      fp.shiftS = (float)(means[1] / ((double)need * (numCh - 1)));
+      k_self_cells_fast<<<(unsigned)ceil_div<int64_t>(nCells, 128), 128, 0, ctx->stream>>>(fp);
+      SGZ_LAUNCH_CHECK(ctx);
+    }
   }
   SGZ_TRY(ctx->end_call());
   if (sim) SGZ_CUDA(cudaMemcpyAsync(sim, dSim.p, nCells * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -475,7 +489,7 @@ int sgz_self_cells(sgz_ctx *ctx, const sgz_self_config *cfg, int32_t numCh, cons
     p.rgb = dImg.p;
     int usedTc = 0;
     SGZ_TRY(self_fast_image(ctx, cfg, p, g, H, numCh, frames2 != nullptr, 0, ext, dMat.p, &usedTc));
-    if (usedTc) {
+    if (usedTc > 0) {
       std::vector<float> hm((size_t)ext * ext);
       std::vector<int32_t> hi((size_t)ext * ext);
       SGZ_CUDA(cudaMemcpyAsync(hm.data(), dMat.p, hm.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));

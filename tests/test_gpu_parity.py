@@ -461,3 +461,29 @@ def test_corr_both_k1_kernels_match_oracle(ctx, w_in, weight, monkeypatch):
         assert np.nanmax(np.abs(sims[0] - sims[1])) < 4e-6
         differs |= not np.array_equal(sims[0].view(np.uint32), sims[1].view(np.uint32))
     assert differs                                       # i.e. two different kernels really ran
+
+
+def test_selfsimilarity_small_image_and_nan_fallback(ctx):
+    """An image smaller than one 128 x 128 tile on the tensor-core kernel; non-finite features go to the exact replay
+    (the Gram forms centre by the file mean, which a NaN would smear over the whole image) and give the oracle's image: a
+    NaN frame only touches the windows over it."""
+    from strugatzki_b200 import engine
+    _, _, _, norm = synth.default_profile(14)
+    f1, _ = synth.regime_file(synth.BASE_SEED, 41, 260, 14, 3)
+    op = O.SelfParams(step_size=STEP, corr_len=44100, decimation=1, temporal_weight=0.5, norm=norm)
+    cfg = N.SelfConfig(STEP, 0, 0, 0, 0, 44100, 1, 0.5, 0, 1.0, 1.0, None, 0, 0)
+    want = O.self_image(op, f1, None)
+    got, g = engine.self_run(ctx, cfg, f1, None, norm)
+    assert engine.self_last_kernel(ctx) == "tc_gram" and 0 < g["imgExt"] < 128
+    d = np.abs((got & 0xFF).astype(np.int64) - (want & 0xFF).astype(np.int64))
+    assert got.shape == want.shape and d.max() <= 1
+    f2 = f1.copy()
+    f2[100, 3] = np.nan
+    want = O.self_image(op, f2, None)
+    got, _ = engine.self_run(ctx, cfg, f2, None, norm)
+    assert engine.self_last_kernel(ctx) == "fp64_replay"
+    assert np.array_equal(got, want) and (want == 0).any() and (want != 0).any()
+    # no window at all (file shorter than two half windows): an empty image, no launch
+    short = f1[:100]
+    got, g = engine.self_run(ctx, cfg, short, None, norm)
+    assert g["imgExt"] == 0
