@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _native as N
 from . import engine
-from .io import (FeatureExtractionConfig, Span, list_database, read_aiff, read_norm_file)
+from .io import (FeatureExtractionConfig, Span, list_database, read_aiff, read_aiff_many, read_norm_file)
 from .processor import Aborted, ProcessorFactory, ProcessorImpl
 
 verbose = False
@@ -166,9 +166,9 @@ class FeatureCorrelationImpl(ProcessorImpl):
         ctx = engine.Context(self.device)
         db = engine.Database(ctx, num_ch, norm)
         try:
-            for e in extr_dbs:
+            # reader threads run ahead of the upload; file order = order of extr_dbs (it fixes the file indices)
+            for e, (frames, spec) in zip(extr_dbs, read_aiff_many([e.feature_output for e in extr_dbs], raw=True)):
                 self.check_aborted()
-                frames, spec = read_aiff(e.feature_output, raw=True)
                 if spec.num_channels != num_ch:
                     raise IOError(f"{e.feature_output}: {spec.num_channels} channels, expected {num_ch}")
                 if spec.big_endian_f32:

@@ -10,7 +10,7 @@ import numpy as np
 
 from . import _native as N
 from . import engine
-from .io import read_aiff, write_norm_file
+from .io import read_aiff_many, write_norm_file
 from .processor import Aborted, ProcessorFactory, ProcessorImpl
 
 
@@ -24,9 +24,8 @@ class FeatureStatsImpl(ProcessorImpl):
         ctx = engine.Context(self.device)
         try:
             db = None
-            for i, path in enumerate(paths):
-                self.check_aborted()
-                frames, spec = read_aiff(path, raw=True)          # big-endian payload: the GPU swaps the bytes
+            for i, (frames, spec) in enumerate(read_aiff_many(paths, raw=True)):   # reader threads run ahead of the upload
+                self.check_aborted()                              # (big-endian payload: the GPU swaps the bytes)
                 if db is None:
                     db = engine.Database(ctx, spec.num_channels, None)
                 elif spec.num_channels != db.num_ch:

@@ -168,6 +168,43 @@ def read_aiff(path: str, raw: bool = False):
     raise IOError(f"{path}: unsupported AIFF-C compression {ctype!r}")
 
 
+def read_aiff_many(paths, raw: bool = True, workers: int = 8, window: int = 16):
+    """Ingest pipeline for a database folder: the feature files are read and parsed by a pool
+    of `workers` threads up to `window` files ahead of the consumer (file I/O and numpy's frombuffer release the GIL) and
+    yielded IN THE ORDER of `paths` as (frames, spec) -- the order is what fixes the file indices of the search
+    (FeatureCorrelationImpl.scala:160-165).  The consumer (sgz_db_add_file, which copies into a pinned staging ring and
+    returns while the H2D copy is in flight) therefore overlaps disk, parse and upload.  A failed read raises at the
+    position of its file; closing the generator early (abort) cancels the reads not yet started."""
+    from collections import deque
+    from concurrent.futures import ThreadPoolExecutor
+
+    paths = list(paths)
+    if workers <= 1 or len(paths) <= 1:
+        for path in paths:
+            yield read_aiff(path, raw=raw)
+        return
+    window = max(window, workers)
+    pool = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="sgz-ingest")
+    pending = deque()
+    try:
+        it = iter(paths)
+        for path in it:
+            pending.append(pool.submit(read_aiff, path, raw))
+            if len(pending) >= window:
+                break
+        while pending:
+            fut = pending.popleft()
+            res = fut.result()
+            nxt = next(it, None)
+            if nxt is not None:
+                pending.append(pool.submit(read_aiff, nxt, raw))
+            yield res
+    finally:
+        for fut in pending:
+            fut.cancel()
+        pool.shutdown(wait=True, cancel_futures=True)
+
+
 def read_norm_file(database_folder: str, num_ch: int) -> np.ndarray:
     """feat_norms.aif -> [numCh][2] = {min, max}; same `require` as FeatureCorrelationImpl.scala:61-71."""
     a, spec = read_aiff(os.path.join(database_folder, NORMALIZE_NAME))

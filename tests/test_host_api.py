@@ -147,3 +147,33 @@ def test_processor_contract():
     with pytest.raises(Aborted):
         q.await_result(5)
     assert isinstance(res[-1].value, Failure) and isinstance(res[-1].value.exception, Aborted)
+
+
+def test_read_aiff_many_keeps_order_and_reports_errors(tmp_path):
+    """ingest pipeline: files come back in the order of the list (it fixes the file indices of a search) whatever the
+    readers' completion order; a broken file raises at its position; closing the generator early cancels the rest"""
+    from strugatzki_b200 import io as sio
+    rng = np.random.default_rng(0)
+    paths, datas = [], []
+    for i in range(23):
+        n = int(rng.integers(1, 400)) if i != 7 else 20000      # one big file finishes late
+        d = rng.standard_normal((n, 3)).astype(np.float32)
+        p = str(tmp_path / f"f{i:02d}_feat.aif")
+        sio.write_aiff(p, d)
+        paths.append(p)
+        datas.append(d)
+    got = list(sio.read_aiff_many(paths, raw=False, workers=4, window=6))
+    assert len(got) == len(paths)
+    for (frames, spec), d in zip(got, datas):
+        assert spec.num_channels == 3 and np.array_equal(np.asarray(frames, np.float32), d)
+    raw = list(sio.read_aiff_many(paths[:3], raw=True, workers=2))
+    assert all(np.array_equal(np.asarray(f, np.float32), d) for (f, _), d in zip(raw, datas))
+    bad = paths[:5] + [str(tmp_path / "missing.aif")] + paths[5:]
+    seen = 0
+    with pytest.raises(Exception):
+        for _ in sio.read_aiff_many(bad, workers=3, window=4):
+            seen += 1
+    assert seen == 5
+    gen = sio.read_aiff_many(paths, workers=4, window=4)
+    next(gen)
+    gen.close()          # early abort: no hang, readers shut down
