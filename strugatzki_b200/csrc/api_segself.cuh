@@ -204,7 +204,13 @@ static int self_fast_image(sgz_ctx *ctx, const sgz_self_config *cfg, sgz::SelfPa
   static const bool tcOff = getenv("SGZ_SELF_TC") && atoi(getenv("SGZ_SELF_TC")) == 0;
   static const bool aDescOff = getenv("SGZ_SELF_TC_ADESC") && atoi(getenv("SGZ_SELF_TC_ADESC")) == 0;
   const SelfTcGeom G = self_tc_geom(H, g.decim, ctx->smemOptin, !aDescOff);
-  bool tc = !tcOff && G.ok && numCh >= 2;
+  // The tensor core truncates when it adds a product block to the accumulator, a bias that grows with the number of MMAs
+  // into one (large) accumulator (tools/selfsim_error_probe.py, worst relative deviation from the oracle): 78 MMAs at the
+  // default window (13 spectral channels x 6 K steps) 3.8e-6, 91 MMAs (H = 112) 8.7e-6, 104 MMAs (H = 128) 1.0e-5, 416
+  // (H = 512) 5.7e-5.  Chains of more than 78 MMAs (H > 96 at 14 channels) therefore go to the FFMA2 kernel, whose
+  // round-to-nearest errors average out (8e-7 at H = 192).
+  const bool chainOk = (numCh - 1) * G.nks <= 78 && 3 * G.nks <= 78;
+  bool tc = !tcOff && G.ok && numCh >= 2 && chainOk;
   if (tc) {
     k_self_absmax<<<ctx->smCount * 4, 256, 0, ctx->stream>>>(p.x1, p.stride1, need, numCh, dAmax.p);
     SGZ_LAUNCH_CHECK(ctx);
