@@ -432,7 +432,7 @@ def test_feature_stats_matches_oracle(ctx):
         dbn.stats()
 
 
-@pytest.mark.parametrize("w_in,weight", [(88200, 0.5), (22050, 0.3), (100000, 1.0)])
+@pytest.mark.parametrize("w_in,weight", [(88200, 0.5), (22050, 0.3), (100000, 1.0), (131072, 0.5)])   # last: W = 256, the widest TC window
 def test_corr_both_k1_kernels_match_oracle(ctx, w_in, weight, monkeypatch):
     """K1 exists twice: on the tensor cores (default where it applies: tcgen05 split-FP16 MMAs on a Hankel view of the
     channel rows, corr_tc.cuh) and as the FFMA2 kernel (SGZ_CORR_TC=0; wide windows, > 14 channels, streaming scans).
