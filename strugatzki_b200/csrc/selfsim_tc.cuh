@@ -9,15 +9,24 @@
 // of accumulations into a LARGE accumulator bounds the bias: the main products of the spectral group get their own TMEM
 // region (6 x 13 = 78 MMAs at H = 86), the small correction products another, the temporal group (18 MMAs) a third.
 //
+// (Measured worst deviation from the oracle 3.8e-6 relative at H = 86; the host routes windows whose spectral chain would
+// exceed 78 MMAs to the FFMA2 kernel, see api_segself.cuh and tools/selfsim_error_probe.py.)
+//
 // Operands are windows of ONE signal (Hankel matrices), so nothing is materialised in global memory except a "record"
 // array R[part][c][rho] = the 8 FP16 values of frames g rho .. g rho + 7 (g = gcd(decim, 8)): any 16-byte chunk
 // (window a, k = 8 kc .. 8 kc + 7) of an operand tile is then ONE aligned record, rho = (decim / g) a + (8 / g) kc.
-// Per (tile, channel) the few KB of records both operands need arrive by bulk copy; 7 builder warps expand them into
-// no-swizzle K-major core matrices (one LDS.128 + one STS.128 per chunk, conflict free), zeroing k >= H, in a ring of
-// slabs of two K steps; one issuer warp (elected lane) feeds tcgen05.mma M128 x N128 x K16 (kind::f16, FP32
-// accumulate); 8 epilogue warps read TMEM, apply the closed form with the FP64-accumulated window sums, blend, map to
-// a colour and store the pixel and its mirror (the mirror goes through a small shared-memory transpose so that both
-// stores are coalesced).
+//  * In-place mode (decim | 8): a window starts at every record, so the 8 rows of a no-swizzle K-major core matrix ARE 8
+//    consecutive records and the record stage in shared memory is itself the operand of both sides (SBO = 128 B,
+//    LBO = (8 / g) * 16 B, overlapping core matrices).  Only B's last K step, which must end at the window's end, comes
+//    pre-masked from global memory (k_self_tail) as part of the stage.  Warp 0 streams the stages with bulk copies
+//    through a ring of 5 - 8; nobody touches the operands with generic loads / stores.
+//  * Expansion mode (other decimations): 6 builder warps expand the records of a stage into canonical core matrices
+//    (one LDS.128 + one STS.128 per chunk, conflict free), zeroing k >= H, in a ring of slabs of a few K steps.
+// One issuer warp (elected lane) feeds tcgen05.mma M128 x N128 x K16 (kind::f16, FP32 accumulate; per K step a1 b1,
+// a1 b2 with A from the operand collector, a2 b1).  8 epilogue warps read TMEM (the last column batches are parked in
+// shared memory first so that TMEM is released early), apply the closed form with the FP64-accumulated window sums on
+// the packed FP32 pipe, blend, map to a colour and store the pixel and its mirror (the mirror goes through a small
+// shared-memory transpose so that both stores are coalesced).  DESIGN.md section 4 (K4) has the measurements.
 #pragma once
 #include <cuda_fp16.h>
 
