@@ -89,17 +89,19 @@ inline SelfTcGeom self_tc_geom(int H, int decim, size_t smemLimit, bool allowADe
     G.tailBytes = 0;
     G.recStageBytes = (4u * G.recPartBytes + 127u) / 128u * 128u;
   }
-  // large stages mean few barrier round trips and fences; at least 3 stages if they fit, else smaller slabs;
-  // four record stages (requests two channels ahead of the MMAs) where they fit
-  for (int nr = 4; nr >= 2 && !G.ok; nr--) {
-    const size_t fixed = (size_t)nr * G.recStageBytes + (size_t)kSgEpiWarps * 32 * kSgPPitch * 4 + 128 * 16 + 512 + 1024;
+  // expansion mode: large ring stages mean few barrier round trips and fences (at least 3 stages if they fit, else smaller
+  // slabs); two record stages are enough for the builders, more only if shared memory is left over
+  {
+    const size_t fixed = (size_t)kSgEpiWarps * 32 * kSgPPitch * 4 + 128 * 16 + 512 + 1024;
     for (int ks = std::min(G.nks, 4); ks >= 1 && !G.ok; ks--) {
       const uint32_t matBytes = (uint32_t)ks * 4096u, stageBytes = 4u * matBytes;
       for (int ns = 4; ns >= (ks > 2 ? 3 : 2); ns--) {
-        if (fixed + (size_t)ns * stageBytes <= smemLimit) {
-          G.slabKs = ks; G.nSlab = (G.nks + ks - 1) / ks; G.nStage = ns; G.nRecStage = nr;
+        if (fixed + 2 * (size_t)G.recStageBytes + (size_t)ns * stageBytes <= smemLimit) {
+          G.slabKs = ks; G.nSlab = (G.nks + ks - 1) / ks; G.nStage = ns; G.nRecStage = 2;
           G.matBytes = matBytes; G.stageBytes = stageBytes;
-          G.smemBytes = fixed + (size_t)ns * stageBytes;
+          while (G.nRecStage < 4 && fixed + (size_t)(G.nRecStage + 1) * G.recStageBytes + (size_t)ns * stageBytes <= smemLimit)
+            G.nRecStage++;
+          G.smemBytes = fixed + (size_t)G.nRecStage * G.recStageBytes + (size_t)ns * stageBytes;
           G.ok = true;
           break;
         }

@@ -235,7 +235,10 @@ def test_selfsimilarity_fast_gram_within_tolerance(ctx, frames, corr_len, decim,
     r = rng.integers(0, g["imgExt"], 4000)
     sim, _ = engine.self_cells(ctx, cfg, f1, f2, l, r, norm)
     wsim, _ = O.self_cells(op, f1, f2, l, r)
-    assert_sims_close(sim, wsim, rel=1e-5, abs_tol=2e-6, what="selfsim cell")
+    # relative 1e-5; the absolute floor for sims near zero is 4e-6 (= 0.001 grey levels): the tensor core's truncating
+    # accumulation leaves up to 3.4e-6 at H = 86 (tools/selfsim_error_probe.py), the FFMA2 kernel stays below 1e-6
+    assert_sims_close(sim, wsim, rel=1e-5, abs_tol=4e-6 if engine.self_last_kernel(ctx) == "tc_gram" else 2e-6,
+                      what="selfsim cell")
 
 
 def test_measured_peaks_are_plausible(ctx):
