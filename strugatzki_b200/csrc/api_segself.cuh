@@ -205,11 +205,17 @@ static int self_fast_image(sgz_ctx *ctx, const sgz_self_config *cfg, sgz::SelfPa
   static const bool aDescOff = getenv("SGZ_SELF_TC_ADESC") && atoi(getenv("SGZ_SELF_TC_ADESC")) == 0;
   const SelfTcGeom G = self_tc_geom(H, g.decim, ctx->smemOptin, !aDescOff);
   // The tensor core truncates when it adds a product block to the accumulator, a bias that grows with the number of MMAs
-  // into one (large) accumulator (tools/selfsim_error_probe.py, worst relative deviation from the oracle): 78 MMAs at the
-  // default window (13 spectral channels x 6 K steps) 3.8e-6, 91 MMAs (H = 112) 8.7e-6, 104 MMAs (H = 128) 1.0e-5, 416
-  // (H = 512) 5.7e-5.  Chains of more than 78 MMAs (H > 96 at 14 channels) therefore go to the FFMA2 kernel, whose
-  // round-to-nearest errors average out (8e-7 at H = 192).
-  const bool chainOk = (numCh - 1) * G.nks <= 78 && 3 * G.nks <= 78;
+  // into one (large) accumulator (tools/selfsim_error_probe.py, worst deviation from the oracle): with ONE spectral main
+  // accumulator 78 MMAs (13 channels x 6 K steps, H = 86) give 3.3e-6 absolute / 3.8e-6 relative, H = 96 8.6e-6 relative,
+  // 104 MMAs (H = 128) 1.0e-5, 416 (H = 512) 5.7e-5.  So from 60 MMAs on the main products alternate between TWO TMEM
+  // regions by channel parity (twoMain: half the chain per accumulator -- 1.8e-6 absolute at H = 86, 3.8e-6 at H = 176 --
+  // at the price of the spare region the temporal MMAs of the next tile would otherwise use: -2 % speed), and windows whose
+  // half chain still exceeds 78 MMAs (H > 176 at 14 channels) go to the FFMA2 kernel, whose round-to-nearest errors average
+  // out (8e-7 at H = 192).
+  const int chainAll = (numCh - 1) * G.nks, chainHalf = (numCh / 2) * G.nks;   // numCh / 2 = odd spectral channels
+  static const int oneMainMax = getenv("SGZ_SELF_TC_ONE_MAIN_MAX") ? atoi(getenv("SGZ_SELF_TC_ONE_MAIN_MAX")) : 60;
+  const bool twoMain = chainAll > oneMainMax && numCh >= 3;
+  const bool chainOk = (twoMain ? chainHalf : chainAll) <= 78 && 3 * G.nks <= 78;
   bool tc = !tcOff && G.ok && numCh >= 2 && chainOk;
   if (tc) {
     k_self_absmax<<<ctx->smCount * 4, 256, 0, ctx->stream>>>(p.x1, p.stride1, need, numCh, dAmax.p);
@@ -296,6 +302,7 @@ static int self_fast_image(sgz_ctx *ctx, const sgz_self_config *cfg, sgz::SelfPa
     }
     tp.simMat = simMat;
     tp.aDesc = G.aDesc;
+    tp.twoMain = twoMain;
     static const int dumpEnv = getenv("SGZ_SELF_TC_DUMP") ? atoi(getenv("SGZ_SELF_TC_DUMP")) : -1;
     tp.dump = dumpEnv >= 0 ? std::min(dumpEnv, G.dump) : G.dump;
     SGZ_CUDA(cudaFuncSetAttribute(k_self_gram_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));

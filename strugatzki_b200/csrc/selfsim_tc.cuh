@@ -133,6 +133,8 @@ struct SelfTcParams {
   // A single group (weight 0 or 1) is one launch with doT or doS alone.
   int storeT, loadT;         // (which groups a launch computes is the kernel's template argument)
   int dump;                  // batches of accumulators the epilogue parks in shared memory to release TMEM early (0..3)
+  int twoMain;               // long windows: the spectral main products alternate between two regions by channel parity,
+                             // halving the chain (and the truncation bias) per accumulator; no spare region then
   float *corrT;              // [imgExt][imgExt], element [c][a] (column-major so that lanes = rows a are coalesced)
 };
 
@@ -317,7 +319,11 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
 
   // channels of this pass and its TMEM staging: temporal = one region per tile, spectral = main + correction regions
   const int cBegin = kDoT ? 0 : 1, cEnd = kDoS ? b.numCh : 1;
-  const int accStages = kDoS ? (kDoT ? 1 : 2) : 4;
+  const int accStages = kDoS ? ((kDoT || p.twoMain) ? 1 : 2) : 4;
+  // TMEM columns inside a stage.  Temporal region: column 0 (alternating with the spare region 384 in the one-launch mode,
+  // see the issuer); spectral main products: regMa (and regMb for even channels with twoMain); corrections: regC.
+  const uint32_t regMa = kDoT ? 128u : 0u, regMb = regMa + 128u, regC = regMa + (p.twoMain ? 256u : 128u);
+  const bool spareT = kMode == 0 && !p.twoMain;
   const uint32_t accCols = 512u / (uint32_t)accStages;
   const int H = b.H;
   const uint32_t matUnits = p.matBytes / 16;
@@ -438,18 +444,20 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
           // One-launch mode with both groups: the temporal region alternates between columns 0 and 384, so the 18 temporal
           // MMAs of tile n + 1 run while the epilogue still reads tile n (the region they overwrite was drained with tile
           // n - 1); only the spectral regions wait for the epilogue.
-          const bool waitHere = kMode == 0 ? c == 1 : c == cBegin;
+          const bool waitHere = spareT ? c == 1 : c == cBegin;
           if (waitHere && tileIt >= (uint32_t)accStages)
             tc_wait<false>(accEmpty + as, ((tileIt / accStages) - 1) & 1);   // the epilogue has drained this TMEM stage
           if (prof) { iAcc += clock64() - tI; tI = clock64(); }
           asm volatile("tcgen05.fence::after_thread_sync;");
           // regions of the stage: temporal = one region for all three products; spectral = main + correction, after the
           // temporal region when both groups share a launch
-          const uint32_t dMain = accBase + (c == 0 ? ((kMode == 0 && (tileIt & 1)) ? 384u : 0u) : (kDoT ? 128u : 0u));
-          const uint32_t dCorr = c == 0 ? dMain : dMain + 128u;
+          const uint32_t dMain = accBase + (c == 0 ? ((spareT && (tileIt & 1)) ? 384u : 0u)
+                                                   : ((p.twoMain && (c & 1) == 0) ? regMb : regMa));
+          const uint32_t dCorr = c == 0 ? dMain : accBase + regC;
           const uint64_t a1 = A1 + stageU * rs, a2 = a1 + partU, b1 = a1 + 2 * partU, b2 = a1 + 3 * partU;
           const uint64_t t1 = T1 + stageU * rs, t2 = t1 + 256;
-          const uint32_t accFirst = (c == 0 || c == 1) ? 0u : 1u;   // first MMA into a region of this tile overwrites
+          // first MMA into a region of this tile overwrites
+          const uint32_t accFirst = (c == 0 || c == 1 || (p.twoMain && c == 2)) ? 0u : 1u, accFirstC = c == 1 ? 0u : 1u;
           if (tc_elect()) {
             // per K step: a1 b1 -> main, a1 b2 -> correction (A taken from the collector, not from shared memory again),
             // a2 b1 -> correction.  (Changing the accumulator between MMAs costs nothing: tools/umma_rate_probe.cu.)
@@ -457,7 +465,7 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
               const uint64_t x1 = a1 + inc * ks, x2 = a2 + inc * ks;
               const uint64_t y1 = ks < nIn ? b1 + inc * ks : t1, y2 = ks < nIn ? b2 + inc * ks : t2;
               tc_mma_fill(dMain, x1, y1, idesc, ks > 0 ? 1u : accFirst);
-              tc_mma_lastuse(dCorr, x1, y2, idesc, (ks > 0 || c == 0) ? 1u : accFirst);
+              tc_mma_lastuse(dCorr, x1, y2, idesc, (ks > 0 || c == 0) ? 1u : accFirstC);
               tc_mma_acc(dCorr, x2, y1, idesc);
             }
             tc_commit(recEmpty + rs);                              // the MMAs read the record stage
@@ -478,8 +486,9 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
         if (c == cBegin && tileIt >= (uint32_t)accStages)
           tc_wait<false>(accEmpty + as, ((tileIt / accStages) - 1) & 1);   // the epilogue has drained this TMEM stage
         iAcc += clock64() - tI;
-        const uint32_t dMain = accBase + (c == 0 ? ((kMode == 0 && (tileIt & 1)) ? 384u : 0u) : (kDoT ? 128u : 0u));
-        const uint32_t dCorr = c == 0 ? dMain : dMain + 128u;
+        const uint32_t dMain = accBase + (c == 0 ? ((spareT && (tileIt & 1)) ? 384u : 0u)
+                                                 : ((p.twoMain && (c & 1) == 0) ? regMb : regMa));
+        const uint32_t dCorr = c == 0 ? dMain : accBase + regC;
         for (int slab = 0; slab < p.nSlab; slab++, slabCtr++) {
           const int st = slabCtr % p.nStage;
           const uint32_t use = slabCtr / p.nStage;
@@ -490,7 +499,7 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
           if (tc_elect()) {
             const uint32_t sb = smem_u32(ring + (size_t)st * p.stageBytes);
             // first MMA into a region of this tile overwrites; the temporal group keeps all three products in one region
-            const bool first = slab == 0 && (c == 0 || c == 1);
+            const bool first = slab == 0 && (c == 0 || c == 1 || (p.twoMain && c == 2)), firstC = slab == 0 && c == 1;
             // descriptors of the first K step; a K step further is a constant increment of the start-address fields
             const int nksHere = min(p.slabKs, p.nks - p.slabKs * slab);
             const uint64_t a1 = sg_desc(sb, 2048, 128), a2 = sg_desc(sb + p.matBytes, 2048, 128);
@@ -498,7 +507,7 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
             for (int ks = 0; ks < nksHere; ks++)             // 2 chunks x 2048 B = 256 units per K step
               tc_mma(dMain, a1 + 256u * ks, b1 + 256u * ks, idesc, !(first && ks == 0));
             for (int ks = 0; ks < nksHere; ks++) {
-              tc_mma(dCorr, a2 + 256u * ks, b1 + 256u * ks, idesc, c == 0 ? 1u : !(first && ks == 0));
+              tc_mma(dCorr, a2 + 256u * ks, b1 + 256u * ks, idesc, c == 0 ? 1u : !(firstC && ks == 0));
               tc_mma_acc(dCorr, a1 + 256u * ks, b2 + 256u * ks, idesc);
             }
             tc_commit(empty + st);
@@ -524,7 +533,7 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
     const float wT = b.weight, wS = __fsub_rn(1.0f, b.weight);
     const bool useT = kDoT, useS = kDoS;
     // TMEM columns of the regions inside a stage: one-launch two-group mode [T | S main | S corr], else [main | corr]
-    const uint32_t colT = 0u, colM = kDoT ? 128u : 0u, colC = kDoT ? 256u : 128u;
+    const uint32_t colT = 0u, colM = regMa, colC = regC;
     uint32_t tileIt = 0;
     long long eAcc = 0, eMain = 0, tE;
     for (int t = blockIdx.x; t < p.nTiles; t += gridDim.x, tileIt++) {
@@ -560,7 +569,7 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
       // back only what it wrote: no synchronisation), the TMEM stage is released after the load of batch 3 - dump, and
       // the dumped batches are evaluated from shared memory while the MMAs of the next tile already run.
       const int D = p.dump;
-      const uint32_t colTt = (kMode == 0 && (tileIt & 1)) ? 384u : colT;
+      const uint32_t colTt = (spareT && (tileIt & 1)) ? 384u : colT;
 #pragma unroll 1
       for (int bt = 4 - D; bt < 4; bt++) {
         uint32_t uT[16], uM[16], uC[16];
@@ -570,6 +579,12 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
           tc_ld16_nowait(laneAddr + colC + 16u * bt, uC);
         }
         tc_ld_wait();
+        if (useS && p.twoMain) {   // second main region (even channels)
+#pragma unroll
+          for (int i = 0; i < 16; i++) uM[i] = __float_as_uint(__uint_as_float(uM[i]) + __uint_as_float(uC[i]));
+          tc_ld16_nowait(laneAddr + regMb + 16u * bt, uC);
+          tc_ld_wait();
+        }
         float *dp = dump + (size_t)(bt - (4 - D)) * (2 * 16 * kSgEpiWarps * 32) + et;
 #pragma unroll
         for (int i = 0; i < 16; i++) {
@@ -587,6 +602,12 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
             tc_ld16_nowait(laneAddr + colC + 16u * bt, uC);
           }
           tc_ld_wait();
+          if (useS && p.twoMain) {   // second main region (even channels)
+#pragma unroll
+            for (int i = 0; i < 16; i++) uM[i] = __float_as_uint(__uint_as_float(uM[i]) + __uint_as_float(uC[i]));
+            tc_ld16_nowait(laneAddr + regMb + 16u * bt, uC);
+            tc_ld_wait();
+          }
           if (useS) {      // spectral Gram = main + correction products
 #pragma unroll
             for (int i = 0; i < 16; i++) uM[i] = __float_as_uint(__uint_as_float(uM[i]) + __uint_as_float(uC[i]));

@@ -205,8 +205,10 @@ def test_selfsimilarity_image_identical(ctx, decim, weight, warp, ceil, inv, cro
     (2300, 44100, 4, 0.5, 1.0, False, False), (3300, 44100, 7, 0.5, 1.0, False, True), (3600, 16384, 8, 0.25, 1.0, False, False),
     (2500, 44100, 5, 0.5, 1.0, True, False), (1900, 44100, 6, 0.7, 1.0, False, False), (700, 8192, 1, 0.5, 1.0, False, False),
     (6000, 44100, 16, 0.5, 1.0, False, False),
-    # the longest window the tensor-core kernel takes (H = 96: 13 x 6 = 78 MMAs into the spectral accumulator), and the next
-    (1500, 49152, 1, 0.5, 1.0, False, False), (1500, 57344, 1, 0.5, 1.0, False, False),
+    # H = 96: the longest window with one spectral main accumulator (13 x 6 = 78 MMAs); H = 112 and 160: two accumulators
+    # by channel parity (7 x 7 and 7 x 10 MMAs), also with the spectral group alone and in expansion mode
+    (1500, 49152, 1, 0.5, 1.0, False, False), (1500, 57344, 1, 0.5, 1.0, False, False), (1700, 81920, 1, 0.5, 1.0, False, True),
+    (1700, 81920, 2, 0.0, 1.0, False, False), (2400, 65536, 3, 0.5, 1.0, False, False),
     # long windows (32 and 64 K steps per channel): FFMA2 kernel
     (1600, 262144, 1, 0.5, 1.0, False, False), (2600, 524288, 2, 0.4, 1.0, False, True),
 ])
@@ -223,8 +225,8 @@ def test_selfsimilarity_fast_gram_within_tolerance(ctx, frames, corr_len, decim,
     cfg = N.SelfConfig(STEP, 0, 0, 0, 0, corr_len, decim, weight, int(inv), warp, 1.0, None, 0, 0)   # precise = 0
     got, g = engine.self_run(ctx, cfg, f1, f2, norm)
     # no silent fall-back to the FFMA2 kernel -- except for long windows, where the tensor core's truncating accumulation
-    # would exceed the error budget (chains of more than 78 MMAs into one accumulator)
-    assert engine.self_last_kernel(ctx) == ("tc_gram" if corr_len <= 49152 else "ffma2_gram")
+    # would exceed the error budget (chains of more than 78 MMAs into one accumulator even when split over two)
+    assert engine.self_last_kernel(ctx) == ("tc_gram" if corr_len <= 90112 else "ffma2_gram")
     assert got.shape == want.shape and g["imgExt"] == want.shape[0] > 128      # several 128 x 128 tiles
     assert np.array_equal(got, got[::-1, ::-1].T)                              # mirrored like the reference
     dg = np.abs((got & 0xFF).astype(np.int64) - (want & 0xFF).astype(np.int64))

@@ -12,7 +12,7 @@ from strugatzki_b200 import _native as N, engine, synth  # noqa: E402
 
 ctx = engine.Context(0)
 _, _, _, norm = synth.default_profile(14)
-for corr_len, frames in ((22050, 1200), (44100, 1200), (49152, 1400), (57344, 1500), (98304, 1500)):
+for corr_len, frames in ((22050, 1200), (44100, 1200), (49152, 1400), (57344, 1500), (81920, 1700), (90112, 1800), (98304, 1500)):
     f1, _ = synth.regime_file(synth.BASE_SEED, 16, frames, 14, 6)
     op = O.SelfParams(step_size=512, corr_len=corr_len, decimation=1, temporal_weight=0.5, norm=norm)
     cfg = N.SelfConfig(512, 0, 0, 0, 0, corr_len, 1, 0.5, 0, 1.0, 1.0, None, 0, 0)
