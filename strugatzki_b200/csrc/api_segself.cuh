@@ -114,7 +114,9 @@ int sgz_segm_run(sgz_ctx *ctx, const sgz_segm_config *cfg, int32_t numCh, const 
   SGZ_TRY(ctx->begin_call());
   k_segm_curve<<<ceil_div(nOff, 128), 128, 0, ctx->stream>>>(sp);
   SGZ_LAUNCH_CHECK(ctx);
-  k_segm_pick<<<1, 32, pickSmem, ctx->stream>>>(pp);
+  static const bool pickSmemOnly = getenv("SGZ_SEGM_PICK_SMEM") != nullptr;   // developer knob: the shared-memory replay
+  if (nb <= 31 && !pickSmemOnly) k_segm_pick_warp<<<1, 32, kPickChunk * sizeof(float), ctx->stream>>>(pp);
+  else k_segm_pick<<<1, 32, pickSmem, ctx->stream>>>(pp);
   SGZ_LAUNCH_CHECK(ctx);
   SGZ_TRY(ctx->end_call());
   int count = 0;

@@ -189,4 +189,88 @@ __global__ void k_segm_pick(const PickParams p) {
   if (lane == 0) *p.count = mc.n;
 }
 
+// The same replay with the sorted set held IN REGISTERS, one entry per lane (numBreaks <= 31): find = two ballots over
+// the total-order keys, insert / remove = one shuffle of every field.  A state change then costs a few dozen cycles
+// instead of a chain of dependent shared-memory accesses (about every second offset of a smooth curve is a change).
+__device__ __forceinline__ uint32_t segm_jkey(float x) {   // java.lang.Float.compare as an unsigned key
+  return float_order_key(x != x ? __int_as_float(0x7fc00000) : x);
+}
+
+__global__ void k_segm_pick_warp(const PickParams p) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  extern __shared__ __align__(16) unsigned char pickSmem[];
+  float *chunk = reinterpret_cast<float *>(pickSmem);                                    // [kPickChunk]
+  uint32_t eKey = 0;      // entry `lane` of the set: ascending Float.compare order on sim, unique sims
+  float eSim = 0.f;
+  long long ePos = 0;
+  int n = 0, hasLast = 0;
+  float lastSim = 0.f, high = 0.f;
+  long long lastPos = 0;
+  auto set_add = [&](float sim, long long pos) {
+    const uint32_t k = segm_jkey(sim);
+    const unsigned lt = __ballot_sync(full, lane < n && eKey < k), eq = __ballot_sync(full, lane < n && eKey == k);
+    const uint32_t uKey = __shfl_up_sync(full, eKey, 1);
+    const float uSim = __shfl_up_sync(full, eSim, 1);
+    const long long uPos = __shfl_up_sync(full, ePos, 1);
+    if (eq != 0u) return;                                  // TreeSet.+ keeps the existing element
+    const int idx = __popc(lt);
+    if (lane > idx && lane <= n) { eKey = uKey; eSim = uSim; ePos = uPos; }
+    if (lane == idx) { eKey = k; eSim = sim; ePos = pos; }
+    n++;
+  };
+  auto set_remove = [&](float sim) {
+    const uint32_t k = segm_jkey(sim);
+    const unsigned lt = __ballot_sync(full, lane < n && eKey < k), eq = __ballot_sync(full, lane < n && eKey == k);
+    const uint32_t dKey = __shfl_down_sync(full, eKey, 1);
+    const float dSim = __shfl_down_sync(full, eSim, 1);
+    const long long dPos = __shfl_down_sync(full, ePos, 1);
+    if (eq == 0u) return;
+    const int idx = __popc(lt);
+    if (lane >= idx && lane < n - 1) { eKey = dKey; eSim = dSim; ePos = dPos; }
+    n--;
+  };
+  int pos = 0;
+  for (int base = 0; base < p.nOff; base += kPickChunk) {
+    const int end = min(base + kPickChunk, p.nOff);
+    __syncwarp();
+    for (int i = base + lane; i < end; i += 32) chunk[i - base] = p.curve[i];
+    __syncwarp();
+    while (pos < end) {
+      const int t = pos + lane;
+      const bool active = t < end;
+      const float s = active ? chunk[t - base] : 0.f;
+      bool change = false;
+      if (active) {
+        const bool accept = n < p.numBreaks || s < high;                                  // :58-62, :120
+        const long long bpos = (long long)(p.afStart + t + p.H) * p.step;
+        const bool collapse = hasLast && (bpos - lastPos) < p.minSpacing;
+        change = accept && (collapse ? (lastSim > s) : true);
+      }
+      const unsigned mask = __ballot_sync(full, change);
+      if (mask == 0u) { pos += 32; continue; }
+      const int l = __ffs(mask) - 1;
+      const int ts = pos + l;
+      const float bs = __shfl_sync(full, s, l);
+      const long long bp = (long long)(p.afStart + ts + p.H) * p.step;
+      // addBreak, :68-83
+      if (hasLast && (bp - lastPos) < p.minSpacing) {
+        if (lastSim > bs) {
+          set_remove(lastSim);
+          set_add(bs, bp);
+          lastSim = bs; lastPos = bp;
+        }
+      } else {
+        set_add(bs, bp);
+        if (n > p.numBreaks) n--;
+        lastSim = bs; lastPos = bp; hasLast = 1;
+      }
+      high = n > 0 ? __shfl_sync(full, eSim, n - 1) : 0.f;
+      pos = ts + 1;
+    }
+  }
+  if (lane < n) p.out[lane] = sgz_break{eSim, 0, (int64_t)ePos};
+  if (lane == 0) *p.count = n;
+}
+
 }  // namespace sgz

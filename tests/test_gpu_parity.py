@@ -157,6 +157,9 @@ def test_corr_errors(ctx):
 @pytest.mark.parametrize("corr_len,weight,num_breaks,min_spacing,span", [
     (22050, 0.5, 20, 22050, (None, None)), (11025, 0.0, 5, 0, (None, None)), (44100, 1.0, 8, 88200, (None, None)),
     (22050, 0.25, 6, 22050, (300 * 512, 2500 * 512)), (22050, 0.5, 3, 22050, (None, 40 * 512)),
+    # the break set lives in registers up to 31 breaks (one entry per lane) and in shared memory beyond
+    (22050, 0.5, 31, 11025, (None, None)), (22050, 0.5, 32, 11025, (None, None)), (11025, 0.5, 200, 0, (None, None)),
+    (22050, 0.5, 1, 22050, (None, None)), (22050, 0.5, 0, 22050, (None, None)),
 ])
 def test_segmentation_bit_identical(ctx, corr_len, weight, num_breaks, min_spacing, span):
     from strugatzki_b200 import engine
@@ -498,3 +501,30 @@ def test_selfsimilarity_small_image_and_nan_fallback(ctx):
     short = f1[:100]
     got, g = engine.self_run(ctx, cfg, short, None, norm)
     assert g["imgExt"] == 0
+
+
+@pytest.mark.parametrize("num_breaks", [4, 40])
+def test_segmentation_with_silence_and_ties(ctx, num_breaks):
+    """digital silence gives NaN sims (0/0 in correlateHalf) and repeated material gives exactly equal sims: the replay of
+    the reference's TreeSet (add does not overwrite, NaN greatest) must survive both, in both replay kernels"""
+    from strugatzki_b200 import engine
+    f, _ = synth.regime_file(synth.BASE_SEED, 8, 1500, 14, 5)
+    f[300:520] = f[300]                 # constant stretch: windows inside it have zero variance
+    f[900:1100] = f[600:800]            # repeated material: equal sims at equal relative positions
+    f[1100:1300] = f[600:800]
+    _, _, _, norm = synth.default_profile(14)
+    op = O.SegmParams(step_size=STEP, corr_len=22050, temporal_weight=0.5, norm=norm, num_breaks=num_breaks, min_spacing=22050)
+    want, want_curve = O.segm_run(op, f, want_curve=True)
+    cfg = N.SegmConfig(STEP, 0, 0, 0, 0, 22050, 0.5, num_breaks, 22050)
+    got, curve, noff = engine.segm_run(ctx, cfg, f, norm, want_curve=True)
+    wc = want_curve[:noff]
+    assert np.isnan(wc).any()
+    assert np.array_equal(np.isnan(curve), np.isnan(wc))               # NaN where the reference has NaN (any payload)
+    ok = ~np.isnan(wc)
+    assert np.array_equal(curve[ok].view(np.uint32), wc[ok].view(np.uint32)), "curve is not bit-identical"
+    # a NaN sim can be a break (Float.compare sorts NaN last, so it survives while the set is not full): same position,
+    # NaN on both sides, any payload; every other sim bit for bit
+    def key(b):
+        x = np.float32(b["sim"])
+        return (b["pos"], b"nan" if np.isnan(x) else x.tobytes())
+    assert [key(b) for b in got] == [key(b) for b in want]
