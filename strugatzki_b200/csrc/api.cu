@@ -363,7 +363,7 @@ int sgz_db_stats(sgz_db *db, double *out, double *perFileOut) {
   p.numFiles = nf; p.numCh = nc; p.numPairs = db->numPairs;
   p.mins = dMins.p; p.maxs = dMaxs.p; p.skews = dSkews.p; p.hist = dHist.p; p.perFile = dPer.p;
   SGZ_TRY(ctx->begin_call());
-  k_stats_minmax<<<ceil_div(nf * db->numPairs, 64), 64, 0, ctx->stream>>>(p);
+  k_stats_minmax<<<ceil_div(nf * db->numPairs, kMmWarps), 32 * kMmWarps, 0, ctx->stream>>>(p);
   SGZ_LAUNCH_CHECK(ctx);
   for (int f0 = 0; f0 < nf; f0 += batch) {
     p.file0 = f0;
@@ -587,10 +587,9 @@ int sgz_corr_scan(sgz_corr *job) {
     SGZ_CUDA(cudaStreamWaitEvent(ss, db->chunks.back().ev, 0));   // file table for the row maxima / later kernels
     if (job->hasOut && db->usedFrames > 0) {
       SGZ_TRY(job->rowMaxOut.alloc((size_t)db->usedFrames));
-      k_row_max_out<<<(unsigned)ceil_div<int64_t>(db->usedFrames, 256), 256, 0, ss>>>(
-          job->simOut.p, db->dFileStart.p, db->numFiles(), db->usedFrames, job->qin.W, job->qout.W, job->minPunchF,
-          job->maxPunchF, job->rowMaxOut.p);
-      SGZ_LAUNCH_CHECK(ctx);
+      SGZ_CUDA(launch_row_max_out(ss, job->simOut.p, db->dFileStart.p, db->numFiles(), db->usedFrames, job->qin.W,
+                                  job->qout.W, job->minPunchF, job->maxPunchF, job->rowMaxOut.p));
+      ctx->launches++;
     }
     SGZ_CUDA(cudaEventRecord(ctx->ev1, ss));
     SGZ_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev1, 0));
@@ -614,10 +613,9 @@ int sgz_corr_scan(sgz_corr *job) {
           SGZ_TRY(run_scan_one(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, 0, job->numTiles,
                                ctx->stream, 0));
         SGZ_TRY(job->rowMaxOut.alloc((size_t)db->usedFrames));
-        k_row_max_out<<<(unsigned)ceil_div<int64_t>(db->usedFrames, 256), 256, 0, ctx->stream>>>(
-            job->simOut.p, db->dFileStart.p, db->numFiles(), db->usedFrames, job->qin.W, job->qout.W, job->minPunchF,
-            job->maxPunchF, job->rowMaxOut.p);
-        SGZ_LAUNCH_CHECK(ctx);
+        SGZ_CUDA(launch_row_max_out(ctx->stream, job->simOut.p, db->dFileStart.p, db->numFiles(), db->usedFrames,
+                                    job->qin.W, job->qout.W, job->minPunchF, job->maxPunchF, job->rowMaxOut.p));
+        ctx->launches++;
       }
     }
     SGZ_TRY(ctx->end_call());

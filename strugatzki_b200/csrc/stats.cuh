@@ -5,8 +5,8 @@
 //
 // Works on a database created with norm = NULL (raw values are stored bit-exactly), so the upload path -- big
 // endian AIFF payloads, staging ring, device-side transposition -- is shared with the search.
-//   pass 1  k_stats_minmax : one thread per (file, channel pair) walks the file in frame order, so the Double sum
-//                            has the reference's summation order (:70-84); ends with the skew (:86-92)
+//   pass 1  k_stats_minmax : one warp per (file, channel pair); coalesced loads, per-lane min / max, the Double sum
+//                            in the reference's frame order (:70-84) by one lane per channel; ends with the skew (:86-92)
 //   pass 2  k_stats_hist   : one block per (file, pair, 8192-frame segment); bins in shared memory, integer
 //                            counts merged with atomics (order independent, exact) (:94-113)
 //   pass 3  k_stats_pctl   : one thread per (file, channel) scans its 2048 bins (:115-131)
@@ -34,50 +34,99 @@ struct StatsParams {
 // Double -> Int like the JVM: NaN -> 0, saturating, truncating
 __device__ __forceinline__ int j_d2i(double x) { return x != x ? 0 : __double2int_rz(x); }
 
-__global__ void k_stats_minmax(const StatsParams p) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per (file, channel pair).  The Double sum must keep the reference's frame order (:70-84), so it is a
+// chain of n dependent additions whatever the layout; everything around it is made parallel: the warp fetches 256
+// frames with coalesced loads (the next 256 are in flight while the chain runs), min / max are taken per lane and
+// merged at the end ("first one wins" among equal values, like the sequential scan, so that the sign of a zero
+// extreme is the reference's), and lanes 0 / 1 add the two channels of the pair from shared memory.
+constexpr int kMmWarps = 4;
+constexpr int kMmSteps = 8;                       // 32-frame steps per chunk
+constexpr int kMmChunk = 32 * kMmSteps;
+
+struct StatExt {          // running extreme of one channel: value and the frame it was first seen at
+  float v;
+  int64_t at;
+};
+
+__device__ __forceinline__ void stat_ext_merge(StatExt &a, bool isMin, unsigned full, int delta) {
+  const float ov = __shfl_xor_sync(full, a.v, delta);
+  const int64_t oat = __shfl_xor_sync(full, a.at, delta);
+  const bool better = isMin ? ov < a.v : ov > a.v;
+  if (better || (ov == a.v && oat < a.at)) { a.v = ov; a.at = oat; }
+}
+
+__global__ void __launch_bounds__(32 * kMmWarps) k_stats_minmax(const StatsParams p) {
+  __shared__ double buf[kMmWarps][2][kMmChunk];   // the chunk as Doubles, one plane per channel of the pair
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int idx = blockIdx.x * kMmWarps + warp;
   if (idx >= p.numFiles * p.numPairs) return;
   const int f = idx / p.numPairs, pr = idx - f * p.numPairs;
   const int64_t g0 = p.fileStart[f], n = p.fileStart[f + 1] - g0;
   const float2 *row = p.data + (int64_t)pr * p.rowStride + g0;
-  float mn0 = INFINITY, mn1 = INFINITY, mx0 = -INFINITY, mx1 = -INFINITY;
-  double s0 = 0.0, s1 = 0.0;
-  int64_t i = 0;
-  for (; i + 8 <= n; i += 8) {     // 8 independent loads in flight, the adds stay in frame order
-    float2 v[8];
+  const int64_t never = INT64_MAX;
+  StatExt mn0{INFINITY, never}, mn1{INFINITY, never}, mx0{-INFINITY, never}, mx1{-INFINITY, never};
+  double s = 0.0;                                  // lane 0: channel 2 pr, lane 1: channel 2 pr + 1
+  float2 v[kMmSteps];
 #pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = __ldg(row + i + k);
+  for (int u = 0; u < kMmSteps; u++) {
+    const int64_t i = 32 * u + lane;
+    v[u] = i < n ? __ldg(row + i) : make_float2(0.f, 0.f);
+  }
+  const double *bsum = buf[warp][lane & 1];
+  for (int64_t base = 0; base < n; base += kMmChunk) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-      if (v[k].x < mn0) mn0 = v[k].x;
-      if (v[k].x > mx0) mx0 = v[k].x;
-      s0 = __dadd_rn(s0, (double)v[k].x);
-      if (v[k].y < mn1) mn1 = v[k].y;
-      if (v[k].y > mx1) mx1 = v[k].y;
-      s1 = __dadd_rn(s1, (double)v[k].y);
+    for (int u = 0; u < kMmSteps; u++) {
+      const int64_t i = base + 32 * u + lane;
+      // Float -> Double by all lanes: the conversion unit is narrow, two lanes converting 2 x 256 values would
+      // cost more than the additions themselves
+      buf[warp][0][32 * u + lane] = (double)v[u].x;
+      buf[warp][1][32 * u + lane] = (double)v[u].y;
+      if (i < n) {
+        if (v[u].x < mn0.v) { mn0.v = v[u].x; mn0.at = i; }
+        if (v[u].x > mx0.v) { mx0.v = v[u].x; mx0.at = i; }
+        if (v[u].y < mn1.v) { mn1.v = v[u].y; mn1.at = i; }
+        if (v[u].y > mx1.v) { mx1.v = v[u].y; mx1.at = i; }
+      }
     }
-  }
-  for (; i < n; i++) {
-    const float2 v = __ldg(row + i);
-    if (v.x < mn0) mn0 = v.x;
-    if (v.x > mx0) mx0 = v.x;
-    s0 = __dadd_rn(s0, (double)v.x);
-    if (v.y < mn1) mn1 = v.y;
-    if (v.y > mx1) mx1 = v.y;
-    s1 = __dadd_rn(s1, (double)v.y);
-  }
-  const double log05 = log(0.5);
+    __syncwarp();
 #pragma unroll
-  for (int h = 0; h < 2; h++) {
-    const int c = 2 * pr + h;
-    if (c >= p.numCh) break;
-    const float mn = h ? mn1 : mn0, mx = h ? mx1 : mx0;
-    const double mean = __ddiv_rn(h ? s1 : s0, (double)n);
-    const float d = __fsub_rn(mx, mn);
-    const double m = __ddiv_rn(__dsub_rn(mean, (double)mn), (double)d);
-    p.mins[(int64_t)f * p.numCh + c] = mn;
-    p.maxs[(int64_t)f * p.numCh + c] = mx;
-    p.skews[(int64_t)f * p.numCh + c] = __ddiv_rn(log05, log(m));
+    for (int u = 0; u < kMmSteps; u++) {           // next chunk: in flight during the chain
+      const int64_t i = base + kMmChunk + 32 * u + lane;
+      v[u] = i < n ? __ldg(row + i) : make_float2(0.f, 0.f);
+    }
+    const int cnt = (int)(n - base < kMmChunk ? n - base : kMmChunk);
+    if (lane < 2) {
+      int k = 0;
+      for (; k + 8 <= cnt; k += 8) {
+        double d[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) d[q] = bsum[k + q];
+#pragma unroll
+        for (int q = 0; q < 8; q++) s = __dadd_rn(s, d[q]);
+      }
+      for (; k < cnt; k++) s = __dadd_rn(s, bsum[k]);
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int delta = 16; delta >= 1; delta >>= 1) {
+    stat_ext_merge(mn0, true, full, delta);
+    stat_ext_merge(mn1, true, full, delta);
+    stat_ext_merge(mx0, false, full, delta);
+    stat_ext_merge(mx1, false, full, delta);
+  }
+  if (lane < 2) {
+    const int c = 2 * pr + lane;
+    if (c < p.numCh) {
+      const float mn = lane ? mn1.v : mn0.v, mx = lane ? mx1.v : mx0.v;
+      const double mean = __ddiv_rn(s, (double)n);
+      const float d = __fsub_rn(mx, mn);
+      const double m = __ddiv_rn(__dsub_rn(mean, (double)mn), (double)d);
+      p.mins[(int64_t)f * p.numCh + c] = mn;
+      p.maxs[(int64_t)f * p.numCh + c] = mx;
+      p.skews[(int64_t)f * p.numCh + c] = __ddiv_rn(log(0.5), log(m));
+    }
   }
 }
 
