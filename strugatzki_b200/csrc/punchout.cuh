@@ -141,7 +141,7 @@ inline cudaError_t launch_row_max_out(cudaStream_t st, const float *simOut, cons
   const int span = maxPunchF - minPunchF + 1;
   const unsigned blocks = (unsigned)ceil_div<int64_t>(usedFrames, kRowMaxThreads);
   const size_t smem = span > 0 ? row_max_smem_bytes(span) : 0;
-  if (span > 64 && smem <= 200 * 1024) {
+  if (span > 64 && smem <= 200 * 1024 && getenv("SGZ_PO_GLOBAL") == nullptr) {   // developer knob: the untiled kernels
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(k_row_max_out_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       if (e != cudaSuccess) return e;
@@ -454,9 +454,10 @@ inline int corr_select_punchout(sgz_corr *job, int32_t *nRecords) {
       SGZ_TRY(ctx->begin_call());
       const size_t curveBytes = fill_po_smem_bytes(fp.maxPunchF - fp.minPunchF + 1);
       const size_t entBytes = (size_t)(npf + 1) * sizeof(EntryRec);
-      fp.staged = fp.maxPunchF >= fp.minPunchF && curveBytes <= kFillSmemMax ? 1 : 0;
+      const bool poGlobal = getenv("SGZ_PO_GLOBAL") != nullptr;   // developer knob: curves and entries stay in global memory
+      fp.staged = fp.maxPunchF >= fp.minPunchF && curveBytes <= kFillSmemMax && !poGlobal ? 1 : 0;
       fp.curveFloats = fp.staged ? (int)(curveBytes / sizeof(float)) : 0;
-      fp.entSmem = entBytes <= 16 * 1024 ? 1 : 0;
+      fp.entSmem = entBytes <= 16 * 1024 && !poGlobal ? 1 : 0;
       const size_t fillSmem = (fp.staged ? curveBytes : 0) + (fp.entSmem ? entBytes : 0);
       if (fillSmem > 48 * 1024)
         SGZ_CUDA(cudaFuncSetAttribute(k_replay_fill_po, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -75,3 +75,29 @@ def test_punch_out_short_files_and_many_rounds(ctx):
     db = build_db(ctx, files, norm)
     got = engine.CorrelationJob(db, nc, inp).run()
     assert_matches_equal(got, O.corr_search(op, files))
+
+
+@pytest.mark.parametrize("global_path", [False, True])
+@pytest.mark.parametrize("num_matches,num_per_file,min_spacing", [(12, 3, 22050), (6, 2, 0), (40, 4, 11025)])
+def test_punch_out_silence_ties_and_unstaged_path(ctx, monkeypatch, global_path, num_matches, num_per_file, min_spacing):
+    """digital silence (NaN sims in both curves) and repeated material (exactly equal cell sims: a collapse onto an equal
+    key shrinks entryPrio, the replay's row marks must be dropped) in the filling and in the full rounds; the same through
+    the kernels that keep the curves in global memory (grids too wide for shared memory, SGZ_PO_GLOBAL)"""
+    from strugatzki_b200 import engine
+    if global_path:
+        monkeypatch.setenv("SGZ_PO_GLOBAL", "1")
+    files, norm = make_db(10, 4700)
+    inp = make_input(900)
+    for k, (f, a, b) in enumerate(((1, 500, 900), (4, 2100, 2500), (7, 4000, 4350))):
+        files[f][a:a + W] = synth.plant(inp[:W], 35, 2 * k)
+        files[f][b:b + W] = synth.plant(inp[345:345 + W], 35, 2 * k + 1)
+    for f in (0, 2, 4, 8):
+        files[f][1200:1700] = files[f][1200]                  # constant stretch: zero-variance windows
+        files[f][2600:3300] = files[f][300:1000]              # repeated material: equal sims at equal relative positions
+        files[f][3300:4000] = files[f][300:1000]
+    files[3][:] = files[2]                                    # a whole file twice: every cell ties with the file before
+    op, nc = corr_cfgs(inp, norm, punch_out=(345 * STEP, (345 + W) * STEP), min_punch=86 * STEP, max_punch=689 * STEP,
+                       num_matches=num_matches, num_per_file=num_per_file, min_spacing=min_spacing)
+    db = build_db(ctx, files, norm)
+    got = engine.CorrelationJob(db, nc, inp).run()
+    assert_matches_equal(got, O.corr_search(op, files))
