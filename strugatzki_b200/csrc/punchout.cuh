@@ -244,14 +244,23 @@ __global__ void __launch_bounds__(kFillThreads) k_replay_fill_po(const FillPoPar
     if (p.prof) { t1 = clock64(); tMark += t1 - t0; }
     // ---- warp 0: exact replay over the marked rows ----
     bool marksValid = !hs;
+    static_assert(kFillChunk / 32 == 64, "markedGroups is one 64-bit word");
+    const unsigned long long markedGroups = ((unsigned long long)__ballot_sync(full, marks[32 + lane] != 0u) << 32) |
+                                            __ballot_sync(full, marks[lane] != 0u);
     if (chunk == 0) { tLow = cell_prod_threshold(low); tLowOf = low; tLast = cell_prod_threshold(lastSim); }
     if (pi < chunk) pi = chunk;
     while (pi < chunkEnd) {
-      if (marksValid) {
+      if (marksValid) {                              // jump to the next marked row
         const int o = (int)(pi - chunk);
-        const unsigned m = marks[o >> 5] & (full << (o & 31));
-        if (m == 0u) { pi = chunk + (int64_t)((o >> 5) + 1) * 32; continue; }
-        pi = chunk + (o & ~31) + (__ffs(m) - 1);
+        int g = o >> 5;
+        unsigned m = marks[g] & (full << (o & 31));
+        if (m == 0u) {
+          const unsigned long long later = g < 63 ? markedGroups >> (g + 1) << (g + 1) : 0ull;
+          if (later == 0ull) { pi = chunkEnd; continue; }
+          g = __ffsll((long long)later) - 1;
+          m = marks[g];
+        }
+        pi = chunk + 32 * g + (__ffs(m) - 1);
       }
       // rows pi .. pi+31: the first one whose gate holds (state is constant while nothing is accepted)
       const int64_t r = pi + lane;
@@ -260,8 +269,10 @@ __global__ void __launch_bounds__(kFillThreads) k_replay_fill_po(const FillPoPar
       const float rm = inChunk ? (staged ? sRm[r - chunk] : p.rowMax[fs + r]) : 0.f;
       const int64_t cellsR = i64min(poMax - (r + p.minPunchF) + 1, (int64_t)span);
       bool gate = inChunk && cellsR > 0 && in > __fmul_rn(low, low);
-      // exact pruning: without space in the entry a row only matters if its best cell beats `low`
+      // exact pruning: without space in the entry a row only matters if its best cell beats `low`, and a row that
+      // collapses into the last match only if its best cell beats that match
       if (gate && !hs) gate = __fmul_rn(in, rm) >= tLow;
+      if (gate && hasLast && ((r - (int64_t)lastStop) * p.step < p.minSpacing)) gate = __fmul_rn(in, rm) >= tLast;
       const unsigned rmask = __ballot_sync(full, gate);
       nSteps++;
       if (rmask == 0u) { pi = pi + 32 < chunkEnd ? pi + 32 : chunkEnd; continue; }
@@ -304,7 +315,7 @@ __global__ void __launch_bounds__(kFillThreads) k_replay_fill_po(const FillPoPar
         const int cell = c + 32 * qHit + cl;
         const int64_t pos = row + p.minPunchF + cell;
         if (lane == 0) {
-          EntryRec m{ss, (int32_t)row, (int32_t)pos, p.boostIn[fs + row], p.boostOut[fs + pos]};
+          EntryRec m{ss, (int32_t)row, (int32_t)pos, 0.f, 0.f};   // addMatch does not look at the boosts: filled in at the end
           mc.add(m);
           hs = mc.has_space();
           low = mc.lowest();
@@ -331,8 +342,12 @@ __global__ void __launch_bounds__(kFillThreads) k_replay_fill_po(const FillPoPar
   }
   if (warp == 0 && lane == 0) {
     p.counts[job] = mc.n;
-    if (ent != gEnt)
-      for (int i = 0; i < mc.n; i++) gEnt[i] = ent[i];
+    for (int i = 0; i < mc.n; i++) {
+      EntryRec e = ent[i];
+      e.boostIn = p.boostIn[fs + e.piOff];
+      e.boostOut = p.boostOut[fs + e.stopOff];
+      gEnt[i] = e;
+    }
   }
   if (p.prof && warp == 0 && lane == 0)
     printf("k_replay_fill_po file %d: rows %lld, row steps %d, gated rows %d, state changes %d; cycles: marks %lld, walk %lld (cells %lld)\n",

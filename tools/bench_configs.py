@@ -110,7 +110,7 @@ c_s = time.perf_counter() - t
 print(json.dumps(dict(config="configs[3] SelfSimilarity ~155k frames", frames=n, imgExt=g["imgExt"], decim=g["decim"],
                       cells=g["numCells"], gpu_kernel_ms=round(kms, 2), gpu_wall_ms=round(wall * 1e3, 1),
                       gpu_cells_per_s=round(g["numCells"] / (kms * 1e-3), 1), cpu_oracle_cells_per_s=round(2000 / c_s, 1),
-                      mode="fast FP32 Gram (default)",
+                      mode="tensor-core Gram (default)",
                       sample_max_abs_err=float(np.max(np.abs(gs - ws))),
                       sample_max_rel_err_where_abs_sim_gt_0p05=float(np.max((np.abs(gs - ws) / np.abs(ws))[np.abs(ws) > 0.05])),
                       sample_max_grey_diff=int(np.max(np.abs((grgb & 255) - (wrgb & 255)))))), flush=True)
