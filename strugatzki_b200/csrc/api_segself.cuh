@@ -600,12 +600,19 @@ int sgz_cross_run(sgz_ctx *ctx, const sgz_cross_config *cfg, int32_t numCh, cons
     for (int i = 0; i < L; i++) sum += a[i];
     p.lnAvgIn = log((double)(float)(sum / L));
   }
-  DevBuf<float> x, dA, dSim;
+  // first factor of MathUtil.correlate's products (MathUtil.scala:185-191): a(ch)(i) + aAdd, aAdd = -mean of the group
+  std::vector<double> ac(a.size());
+  for (int c = 0; c < numCh; c++) {
+    const double aAdd = c == 0 ? -p.meanT : -p.meanS;
+    for (int i = 0; i < L; i++) ac[(size_t)c * L + i] = (double)a[(size_t)c * L + i] + aAdd;
+  }
+  DevBuf<float> x, dSim;
+  DevBuf<double> dA;
   int64_t stride = 0;
   SGZ_TRY(upload_features(ctx, numCh, norm, fB, nB, layout, posB, lenB, x, stride));
   SGZ_TRY(dA.alloc(a.size()));
   SGZ_TRY(dSim.alloc((size_t)n));
-  SGZ_CUDA(cudaMemcpyAsync(dA.p, a.data(), a.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  SGZ_CUDA(cudaMemcpyAsync(dA.p, ac.data(), ac.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   p.x = x.p; p.stride = stride; p.a = dA.p; p.numCh = numCh; p.L = L;
   p.c0 = (int)std::min<int64_t>(lenB, kCrossBuf);
   p.nOut = n;

@@ -23,7 +23,8 @@ constexpr int kCrossBuf = 8192;
 struct CrossParams {
   const float *x;        // normalised planar [numCh][stride] frames of the LONGER span (afIn2), index 0 = span start
   int64_t stride;
-  const float *a;        // normalised planar [numCh][L] template (afIn1)
+  const double *a;       // centred template [numCh][L]: (double)a[c][i] + (-mean of its group), the first factor of
+                         // MathUtil.correlate's product, formed once on the host (same IEEE addition)
   int numCh;
   int L;                 // len1i
   int c0;                // frames of the first read = min(len2, 8192)
@@ -45,66 +46,91 @@ struct CrossRing {
     a = any ? (k - 1) / L : 0;
     b = any ? (int)((k - 1) % L) : 0;
   }
-  // q = (pos - r) mod L is the first m >= 0 written to position pos
-  __device__ __forceinline__ long long frame_at(int pos, int q) const {
-    if (any) {
-      if (q <= b) return (long long)c0 + q + a * L;
-      if (a >= 1) return (long long)c0 + q + (a - 1) * L;
-    }
-    return pos;   // still the frame of the first read
-  }
+  // with q = (pos - r) mod L the first m >= 0 written to position pos, that position holds frame
+  //   c0 + q + a L        if k >= 1 and q <= b,
+  //   c0 + q + (a - 1) L  if k >= 1, q > b and a >= 1,
+  //   pos                 otherwise (still the frame of the first read)      -> cross_ring_runs
 };
 
-__device__ __forceinline__ float cross_load(const CrossParams &p, int c, long long frame) {
-  return p.x[(int64_t)c * p.stride + frame];
+// Calls f(frame0, n) for the maximal runs of consecutive ring positions pos0, pos0 + 1, ... (count of them, all < L)
+// that hold consecutive source frames frame0, frame0 + 1, ...: at most four runs per sweep (the write pointer and the
+// wrap of q), so the sweeps below are plain linear loops without per-element index arithmetic.
+template <typename F>
+__device__ __forceinline__ void cross_ring_runs(const CrossRing &ring, int pos0, int count, F f) {
+  int pos = pos0, left = count;
+  int q = pos0 - ring.r;                       // q = (pos - r) mod L
+  if (q < 0) q += ring.L;
+  while (left > 0) {
+    int n = min(left, ring.L - q);
+    long long frame;
+    if (ring.any && q <= ring.b) {
+      n = min(n, ring.b + 1 - q);
+      frame = (long long)ring.c0 + q + ring.a * ring.L;
+    } else if (ring.any && ring.a >= 1) {
+      frame = (long long)ring.c0 + q + (ring.a - 1) * ring.L;
+    } else {
+      frame = pos;                             // still the frames of the first read
+    }
+    f(frame, n);
+    pos += n;
+    left -= n;
+    q += n;
+    if (q == ring.L) q = 0;
+  }
 }
 
 // FeatureMatrix a (channels [chanOff, chanOff+numChannels)) against the ring at output k
 __device__ float cross_correlate(const CrossParams &p, const CrossRing &ring, int o, int chanOff, int numChannels,
-                                 double aMean, double aStd) {
+                                 double aStd) {
   const int L = p.L;
   const int matSize = numChannels * L;
-  const int q0 = ((0 - ring.r) % L + L) % L;
   // MathUtil.stat(b, 0, L, chanOff, numChannels): physical positions 0..L-1
   double sum = 0.0;
   for (int ch = 0; ch < numChannels; ch++) {
-    int q = q0;
-    for (int pos = 0; pos < L; pos++) {
-      sum = __dadd_rn(sum, (double)cross_load(p, ch + chanOff, ring.frame_at(pos, q)));
-      if (++q == L) q = 0;
-    }
+    const float *xc = p.x + (int64_t)(ch + chanOff) * p.stride;
+    cross_ring_runs(ring, 0, L, [&](long long frame, int n) {
+      const float *src = xc + frame;
+      for (int j = 0; j < n; j++) sum = __dadd_rn(sum, (double)src[j]);
+    });
   }
   const double bMean = __ddiv_rn(sum, (double)matSize);
   sum = 0.0;
   for (int ch = 0; ch < numChannels; ch++) {
-    int q = q0;
-    for (int pos = 0; pos < L; pos++) {
-      double d = __dsub_rn((double)cross_load(p, ch + chanOff, ring.frame_at(pos, q)), bMean);
-      sum = __dadd_rn(sum, __dmul_rn(d, d));
-      if (++q == L) q = 0;
-    }
+    const float *xc = p.x + (int64_t)(ch + chanOff) * p.stride;
+    cross_ring_runs(ring, 0, L, [&](long long frame, int n) {
+      const float *src = xc + frame;
+      for (int j = 0; j < n; j++) {
+        const double d = __dsub_rn((double)src[j], bMean);
+        sum = __dadd_rn(sum, __dmul_rn(d, d));
+      }
+    });
   }
   const double bStd = __dsqrt_rn(__ddiv_rn(sum, (double)matSize));
-  // MathUtil.correlate: b index (i + o) % 8192
-  const double aAdd = -aMean, bAdd = -bMean;
+  // MathUtil.correlate: b index (i + o) % 8192; positions >= L hold the frames of the first read (or fresh zeros)
+  const double bAdd = -bMean;
   sum = 0.0;
   for (int ch = 0; ch < numChannels; ch++) {
-    const float *ca = p.a + (int64_t)(ch + chanOff) * L;
-    int pos = o;
-    int q = ((o - ring.r) % L + L) % L;
-    for (int i = 0; i < L; i++) {
-      float bv;
+    const double *ca = p.a + (int64_t)(ch + chanOff) * L;
+    const float *xc = p.x + (int64_t)(ch + chanOff) * p.stride;
+    int i = 0, pos = o;
+    while (i < L) {
       if (pos < L) {
-        bv = cross_load(p, ch + chanOff, ring.frame_at(pos, q));
-        if (++q == L) q = 0;
+        const int n = min(L - i, L - pos);
+        cross_ring_runs(ring, pos, n, [&](long long frame, int m) {
+          const float *src = xc + frame;
+          for (int j = 0; j < m; j++, i++)
+            sum = __dadd_rn(sum, __dmul_rn(ca[i], __dadd_rn((double)src[j], bAdd)));
+        });
+        pos += n;
       } else {
-        bv = pos < p.c0 ? cross_load(p, ch + chanOff, pos) : 0.0f;   // beyond the first read: fresh array zeros
+        const int n = min(L - i, kCrossBuf - pos);
+        for (int j = 0; j < n; j++, i++) {
+          const float bv = pos + j < p.c0 ? xc[pos + j] : 0.0f;   // beyond the first read: fresh array zeros
+          sum = __dadd_rn(sum, __dmul_rn(ca[i], __dadd_rn((double)bv, bAdd)));
+        }
+        pos += n;
       }
-      sum = __dadd_rn(sum, __dmul_rn(__dadd_rn((double)ca[i], aAdd), __dadd_rn((double)bv, bAdd)));
-      if (++pos == kCrossBuf) {   // wraps only when L > 4096
-        pos = 0;
-        q = ((0 - ring.r) % L + L) % L;
-      }
+      if (pos == kCrossBuf) pos = 0;           // wraps only when L > 4096
     }
   }
   return (float)__ddiv_rn(sum, __dmul_rn(__dmul_rn(aStd, bStd), (double)matSize));
@@ -118,19 +144,16 @@ __global__ void k_cross(const CrossParams p) {
   const int o = (int)(k % L);
   // calcBoost (:64-67): MathUtil.avg of the loudness channel over positions [0, L)
   double sum = 0.0;
-  {
-    int q = ((0 - ring.r) % L + L) % L;
-    for (int pos = 0; pos < L; pos++) {
-      sum = __dadd_rn(sum, (double)cross_load(p, 0, ring.frame_at(pos, q)));
-      if (++q == L) q = 0;
-    }
-  }
+  cross_ring_runs(ring, 0, L, [&](long long frame, int n) {
+    const float *src = p.x + frame;
+    for (int j = 0; j < n; j++) sum = __dadd_rn(sum, (double)src[j]);
+  });
   const float avgB = (float)__ddiv_rn(sum, (double)L);
   const float boost = (float)exp(__ddiv_rn(__dsub_rn(p.lnAvgIn, log((double)avgB)), 0.6));
   float sim = 0.0f;
   if (boost <= p.maxBoost) {   // false for NaN, like the JVM
-    const float temporal = p.weight > 0.f ? cross_correlate(p, ring, o, 0, 1, p.meanT, p.stdT) : 0.f;
-    const float spectral = p.weight < 1.f ? cross_correlate(p, ring, o, 1, p.numCh - 1, p.meanS, p.stdS) : 0.f;
+    const float temporal = p.weight > 0.f ? cross_correlate(p, ring, o, 0, 1, p.stdT) : 0.f;
+    const float spectral = p.weight < 1.f ? cross_correlate(p, ring, o, 1, p.numCh - 1, p.stdS) : 0.f;
     sim = __fadd_rn(__fmul_rn(temporal, p.weight), __fmul_rn(spectral, __fsub_rn(1.0f, p.weight)));
   }
   p.sim[k] = sim;
