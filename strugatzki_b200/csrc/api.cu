@@ -376,7 +376,7 @@ int sgz_db_stats(sgz_db *db, double *out, double *perFileOut) {
       k_stats_hist<<<grid, 256, 0, ctx->stream>>>(p);
       SGZ_LAUNCH_CHECK(ctx);
     }
-    k_stats_pctl<<<ceil_div(p.fileCount * nc, 128), 128, 0, ctx->stream>>>(p);
+    k_stats_pctl<<<ceil_div(p.fileCount * nc, 4), 128, 0, ctx->stream>>>(p);   // one warp per (file, channel)
     SGZ_LAUNCH_CHECK(ctx);
   }
   SGZ_TRY(ctx->end_call());

@@ -9,7 +9,7 @@
 //                            in the reference's frame order (:70-84) by one lane per channel; ends with the skew (:86-92)
 //   pass 2  k_stats_hist   : one block per (file, pair, 8192-frame segment); bins in shared memory, integer
 //                            counts merged with atomics (order independent, exact) (:94-113)
-//   pass 3  k_stats_pctl   : one thread per (file, channel) scans its 2048 bins (:115-131)
+//   pass 3  k_stats_pctl   : one warp per (file, channel) finds where the bin counts reach 1 % / 99 % (:115-131)
 // HBM-bound by design (2 x 56 B per frame); pass 2 carries one FP64 pow per value.
 #pragma once
 #include "common.cuh"
@@ -164,24 +164,56 @@ __global__ void k_stats_hist(const StatsParams p) {
     if (sh[i]) atomicAdd(h0 + i, sh[i]);
 }
 
+// One warp per (file, channel).  The reference walks the bins until the running count reaches 1 % of the frames and
+// goes on from there to 99 % (:115-131): i = smallest index whose prefix count (bins 0 .. i-1) reaches the target, the
+// second index never below the first.  Lane l owns bins [64 l, 64 l + 64): a warp scan of the lane sums finds the lane
+// in which the target is crossed, that lane walks its 64 bins.
+__device__ __forceinline__ int stat_bins_until(const int32_t *cp, int target, int lane, int laneSum, int laneIncl) {
+  const unsigned full = 0xffffffffu;
+  if (target <= 0) return 0;
+  const unsigned reached = __ballot_sync(full, laneIncl >= target);
+  if (reached == 0u) return kStatBins;
+  const int l = __ffs(reached) - 1;
+  int idx = 0;
+  if (lane == l) {
+    int acc = laneIncl - laneSum;
+    for (int j = 0; j < kStatBins / 32; j++) {
+      acc += cp[l * (kStatBins / 32) + j];
+      if (acc >= target) { idx = l * (kStatBins / 32) + j + 1; break; }
+    }
+  }
+  return __shfl_sync(full, idx, l);
+}
+
 __global__ void k_stats_pctl(const StatsParams p) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (idx >= p.fileCount * p.numCh) return;
   const int fl = idx / p.numCh, c = idx - fl * p.numCh, f = p.file0 + fl;
   const int64_t n = p.fileStart[f + 1] - p.fileStart[f];
   const int32_t *cp = p.hist + ((int64_t)fl * p.numCh + c) * kStatBins;
   const int p01n = j_d2i(__dmul_rn((double)n, 0.01));
   const int p99n = j_d2i(__dmul_rn((double)n, 0.99));
-  const double skewr = __ddiv_rn(1.0, p.skews[(int64_t)f * p.numCh + c]);
-  const float mn = p.mins[(int64_t)f * p.numCh + c];
-  const float d = __fsub_rn(p.maxs[(int64_t)f * p.numCh + c], mn);
-  int cnt = 0, i = 0;
-  while (cnt < p01n && i < kStatBins) { cnt += cp[i]; i++; }
-  p.perFile[((int64_t)f * p.numCh + c) * 2] =
-      __dadd_rn(__dmul_rn(pow(__ddiv_rn((double)i, 2048.0), skewr), (double)d), (double)mn);
-  while (cnt < p99n && i < kStatBins) { cnt += cp[i]; i++; }
-  p.perFile[((int64_t)f * p.numCh + c) * 2 + 1] =
-      __dadd_rn(__dmul_rn(pow(__ddiv_rn((double)i, 2048.0), skewr), (double)d), (double)mn);
+  int laneSum = 0;
+  for (int j = 0; j < kStatBins / 32; j++) laneSum += cp[lane * (kStatBins / 32) + j];
+  int laneIncl = laneSum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(full, laneIncl, d);
+    if (lane >= d) laneIncl += o;
+  }
+  const int i01 = stat_bins_until(cp, p01n, lane, laneSum, laneIncl);
+  const int i99 = max(i01, stat_bins_until(cp, p99n, lane, laneSum, laneIncl));
+  if (lane == 0) {
+    const double skewr = __ddiv_rn(1.0, p.skews[(int64_t)f * p.numCh + c]);
+    const float mn = p.mins[(int64_t)f * p.numCh + c];
+    const float d = __fsub_rn(p.maxs[(int64_t)f * p.numCh + c], mn);
+    p.perFile[((int64_t)f * p.numCh + c) * 2] =
+        __dadd_rn(__dmul_rn(pow(__ddiv_rn((double)i01, 2048.0), skewr), (double)d), (double)mn);
+    p.perFile[((int64_t)f * p.numCh + c) * 2 + 1] =
+        __dadd_rn(__dmul_rn(pow(__ddiv_rn((double)i99, 2048.0), skewr), (double)d), (double)mn);
+  }
 }
 
 }  // namespace sgz
