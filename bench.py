@@ -129,21 +129,19 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": "FeatureCorrelation DB frame-offsets/sec", "value": value,
             "unit": "offsets/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": config_block(args.gpus, note="bounded sample of the same workload"),
+            "data": "synthetic", "config": config_block(args.gpus), "config_note": "bounded sample of the same workload",
             "cpu_baseline": {"value": value, "unit": "offsets/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "offsets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
     return 0
 
 
-def config_block(n_gpus, files=6000, note=None):
+def config_block(n_gpus, files=6000):
     c = {"workload": "FeatureCorrelation punch-in 2 s (W=172 frames) over 1000 h synthetic feature DB per GPU "
                      "(BASELINE.json configs[4])",
          "files_per_gpu": files, "frames_per_file": FRAMES_PER_FILE, "channels": 14, "temporalWeight": 0.5,
          "numMatches": 100, "numPerFile": 1, "minSpacing": 22050, "sharding": f"file-range x{n_gpus}",
          "cache": "DB per GPU (17.4 GB) >> 126 MB L2, no reuse between steps"}
-    if note:
-        c["note"] = note
     return c
 
 
@@ -213,8 +211,7 @@ def main():
     files = args.files
     db = engine.Database(ctx, 14, norm)
     db.reserve(files * FRAMES_PER_FILE, files)
-    for i in range(files):
-        db.add_synth(synth.BASE_SEED, 1 + rank * files + i, FRAMES_PER_FILE, mu, sigma, float(floor0))
+    db.add_synth_many(synth.BASE_SEED, 1 + rank * files, files, FRAMES_PER_FILE, mu, sigma, float(floor0))   # one launch
     inp = synth.synth_file(synth.BASE_SEED, 0, 900, mu, sigma, floor0)
     rng = np.random.default_rng(1234 + rank)
     needles = []
@@ -391,8 +388,8 @@ def run_e2e(args, torch, device, ctx, engine, N, synth, rank, files, mu, sigma, 
     hnp = host.numpy()
     for c0 in range(0, e2e_files, chunk):
         raw = engine.Database(ctx, 14, None)
-        for i in range(c0, min(c0 + chunk, e2e_files)):
-            raw.add_synth(synth.BASE_SEED, 1 + rank * files + i, FRAMES_PER_FILE, mu, sigma, float(floor0))
+        raw.add_synth_many(synth.BASE_SEED, 1 + rank * files + c0, min(chunk, e2e_files - c0), FRAMES_PER_FILE, mu, sigma,
+                           float(floor0))
         raw.finalize()
         for i in range(c0, min(c0 + chunk, e2e_files)):
             hnp[i] = raw.read(i - c0, 0, FRAMES_PER_FILE)

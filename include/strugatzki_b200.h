@@ -167,6 +167,10 @@ int sgz_db_add_file_device(sgz_db *db, const void *dFrames, int64_t nFrames);
  * x[c][t] = mu[c] + sigma[c] * g(seed, stream, c, t), channel 0 clamped to >= floor0. */
 int sgz_db_add_synth(sgz_db *db, uint64_t seed, uint32_t stream, int64_t nFrames,
                      const float *mu, const float *sigma, float floor0);
+/* `numFiles` synthetic files of `nFramesEach` frames (streams firstStream, firstStream + 1, ...) generated by ONE
+ * kernel launch; identical to numFiles calls of sgz_db_add_synth.  Returns the index of the first file added. */
+int sgz_db_add_synth_many(sgz_db *db, uint64_t seed, uint32_t firstStream, int32_t numFiles, int64_t nFramesEach,
+                          const float *mu, const float *sigma, float floor0);
 /* Overwrites frames [frameOff, frameOff+n) of an added file with raw (un-normalised)
  * interleaved LE frames -- used to plant known needles into a synthetic DB. */
 int sgz_db_patch(sgz_db *db, int32_t file, int64_t frameOff, const float *frames, int64_t n);
@@ -249,7 +253,12 @@ typedef struct {
 typedef struct {
   int32_t file;         /* GLOBAL file index                                   */
   int32_t kind;         /* 0 = candidate cell, 1 = resolved entry of a filling-phase file,
-                           2 = end-of-file marker of a resolved file            */
+                           2 = end-of-file marker of a resolved file,
+                           3 = punch-in offset above the round threshold (punch-out mode),
+                           4 = gate interval of a filling-round file in punch-out mode: piOff = first
+                               accepted row (-1: none), sim = its in-sim, boostIn = largest in-sim the row
+                               gate turned away before it; sgz_corr_merge ends the round at the first
+                               file whose interval does not hold allPrio.last.sim^2 of that moment       */
   int32_t piOff;        /* punch-in offset (feature frames, file local)        */
   int32_t poOff;        /* punch-out offset, or -1                              */
   float   sim;

@@ -281,6 +281,31 @@ int sgz_db_add_synth(sgz_db *db, uint64_t seed, uint32_t stream, int64_t nFrames
   return db_commit_file(db, nFrames);
 }
 
+int sgz_db_add_synth_many(sgz_db *db, uint64_t seed, uint32_t firstStream, int32_t numFiles, int64_t nFramesEach,
+                          const float *mu, const float *sigma, float floor0) {
+  SGZ_REQUIRE(numFiles >= 0 && nFramesEach >= 0, "negative file / frame count");
+  int64_t dst = 0;
+  SGZ_TRY(db_begin_file(db, (int64_t)numFiles * nFramesEach, &dst));
+  SGZ_REQUIRE(mu && sigma, "mu / sigma is NULL");
+  const int first = db->numFiles();
+  if (numFiles > 0 && nFramesEach > 0) {
+    DevBuf<float> ms;
+    SGZ_TRY(ms.alloc((size_t)db->numCh * 2));
+    SGZ_CUDA(cudaMemcpyAsync(ms.p, mu, db->numCh * sizeof(float), cudaMemcpyHostToDevice, db->ctx->stream));
+    SGZ_CUDA(cudaMemcpyAsync(ms.p + db->numCh, sigma, db->numCh * sizeof(float), cudaMemcpyHostToDevice,
+                             db->ctx->stream));
+    const int64_t total = (int64_t)numFiles * nFramesEach;
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div<int64_t>(total, 256), (int64_t)db->ctx->smCount * 32),
+              (unsigned)db->numPairs);
+    k_db_synth_many<<<grid, 256, 0, db->ctx->stream>>>(db->dData.p, db->capFrames, dst, nFramesEach, numFiles, db->numCh,
+                                                       seed, firstStream, ms.p, ms.p + db->numCh, floor0, db->dNorm.p);
+    SGZ_LAUNCH_CHECK(db->ctx);
+    SGZ_CUDA(cudaStreamSynchronize(db->ctx->stream));  // ms goes out of scope
+  }
+  for (int f = 0; f < numFiles; f++) SGZ_TRY(db_commit_file(db, nFramesEach));
+  return first;
+}
+
 int sgz_db_patch(sgz_db *db, int32_t file, int64_t frameOff, const float *frames, int64_t n) {
   SGZ_REQUIRE(db && frames, "NULL argument");
   SGZ_REQUIRE(file >= 0 && file < db->numFiles(), "file index %d out of range", file);

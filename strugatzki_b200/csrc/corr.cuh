@@ -54,6 +54,7 @@ struct sgz_corr {
   DevBuf<int32_t> dFiles, dCounts;
   DevBuf<float> dThr;
   DevBuf<sgz::EntryRec> dEntries;
+  DevBuf<float4> dMeta;        // punch-out filling rounds: gate interval per file (punchout.cuh)
   DevBuf<sgz_record> dRecs;
   DevBuf<int> dCounter;
 

@@ -105,6 +105,30 @@ __global__ void k_db_synth(float2 *__restrict__ data, int64_t rowStride, int64_t
   }
 }
 
+// the same for `numFiles` equally long files in ONE launch (streams stream0, stream0 + 1, ...): the 1000 h bench
+// database is 6000 files, and 6000 separate launches made the ncu launch list uncapturable
+__global__ void k_db_synth_many(float2 *__restrict__ data, int64_t rowStride, int64_t dstFrame, int64_t nFrames,
+                                int64_t numFiles, int numCh, uint64_t seed, uint32_t stream0,
+                                const float *__restrict__ mu, const float *__restrict__ sigma, float floor0,
+                                const float *__restrict__ norm) {
+  const int p = blockIdx.y, c0 = 2 * p, c1 = 2 * p + 1;
+  const bool has1 = c1 < numCh;
+  const float m0 = mu[c0], s0 = sigma[c0], mn0 = norm[2 * c0], mx0 = norm[2 * c0 + 1];
+  const float m1 = has1 ? mu[c1] : 0.f, s1 = has1 ? sigma[c1] : 0.f;
+  const float mn1 = has1 ? norm[2 * c1] : 0.f, mx1 = has1 ? norm[2 * c1 + 1] : 1.f;
+  const int64_t total = nFrames * numFiles;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = i / nFrames, t = i - f * nFrames;
+    const uint32_t stream = stream0 + (uint32_t)f;
+    float x = synth_value(seed, stream, (uint32_t)c0, (uint64_t)t, m0, s0);
+    if (c0 == 0) x = fmaxf(x, floor0);
+    float2 v;
+    v.x = normalize_value(x, mn0, mx0);
+    v.y = has1 ? normalize_value(synth_value(seed, stream, (uint32_t)c1, (uint64_t)t, m1, s1), mn1, mx1) : 0.f;
+    data[(int64_t)p * rowStride + dstFrame + i] = v;
+  }
+}
+
 __device__ inline float load_be(const float *p) {
   uint32_t v = *reinterpret_cast<const uint32_t *>(p);
   return __int_as_float((int)__byte_perm(v, 0, 0x0123));

@@ -34,6 +34,14 @@ struct FillPoParams {
   int step;
   EntryRec *entries;   // [numJobs][numPerFile + 1]
   int32_t *counts;
+  // lowestSim falls back to allPrio.last.sim while entryPrio is empty (FeatureCorrelationImpl.scala:125-129), and the row
+  // gate `inSim > low * low` (:342) applies even while the entry has space.  Files of one filling round run in parallel
+  // with the allPrio state of the ROUND START as the guess; `meta` tells the merge whether the guess mattered:
+  // meta[job] = {max in-sim of the rows (with cells) skipped while the entry was empty, in-sim of the first accepted row,
+  // that row (-1: none)}.  The result is the reference's for every allPrio.last whose square lies in [meta.x, meta.y).
+  int allNonEmpty;
+  float allLast;
+  float4 *meta;        // [numJobs]
   int staged;          // the chunk's curves fit the dynamic shared memory of the launch
   int entSmem;         // entryPrio in shared memory, behind the curves
   int curveFloats;     // floats of dynamic shared memory taken by the curves (0 when not staged)
@@ -192,7 +200,10 @@ __global__ void __launch_bounds__(kFillThreads) k_replay_fill_po(const FillPoPar
   EntryRec *gEnt = p.entries + (size_t)job * (p.numPerFile + 1);
   EntryRec *ent = p.entSmem ? reinterpret_cast<EntryRec *>(fillSmem + p.curveFloats) : gEnt;
   Machine mc;
-  mc.reset(ent, p.numPerFile, p.maxEntrySz, 0, 0.f, p.minSpacing, p.step);
+  mc.reset(ent, p.numPerFile, p.maxEntrySz, p.allNonEmpty, p.allLast, p.minSpacing, p.step);
+  bool entEmpty = true;             // entryPrio still empty: `low` is allPrio.last.sim (or 0)
+  float metaM = -INFINITY, metaV = 0.f;
+  int metaRow = -1;
   // filling round: entryHasSpace holds at the file start, so tInOff = 0; loop B needs one full window
   const bool any = nA > 0 && (N - p.minPunchF) >= p.Wout && span > 0 && p.maxEntrySz > 0;
   bool hs = mc.has_space();
@@ -275,10 +286,18 @@ __global__ void __launch_bounds__(kFillThreads) k_replay_fill_po(const FillPoPar
       if (gate && hasLast && ((r - (int64_t)lastStop) * p.step < p.minSpacing)) gate = __fmul_rn(in, rm) >= tLast;
       const unsigned rmask = __ballot_sync(full, gate);
       nSteps++;
+      if (entEmpty) {   // rows the gate turned away before the first match: would a lower allPrio.last have let them in?
+        const bool skipped = inChunk && cellsR > 0 && !gate && (rmask == 0u || lane < __ffs(rmask) - 1);
+        float m = skipped ? in : -INFINITY;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(full, m, d));
+        metaM = fmaxf(metaM, m);
+      }
       if (rmask == 0u) { pi = pi + 32 < chunkEnd ? pi + 32 : chunkEnd; continue; }
       const int rl = __ffs(rmask) - 1;
       const int64_t row = pi + rl;
       const float inS = __shfl_sync(full, in, rl);
+      if (entEmpty) { metaRow = (int)row; metaV = inS; entEmpty = false; }   // hs holds: the row's first cell is accepted
       const int n = (int)__shfl_sync(full, (int)cellsR, rl);
       nGated++;
       const long long tc0 = p.prof ? clock64() : 0;
@@ -342,6 +361,7 @@ __global__ void __launch_bounds__(kFillThreads) k_replay_fill_po(const FillPoPar
   }
   if (warp == 0 && lane == 0) {
     p.counts[job] = mc.n;
+    p.meta[job] = make_float4(metaM, metaV, __int_as_float(metaRow), 0.f);
     for (int i = 0; i < mc.n; i++) {
       EntryRec e = ent[i];
       e.boostIn = p.boostIn[fs + e.piOff];
@@ -464,6 +484,10 @@ inline int corr_select_punchout(sgz_corr *job, int32_t *nRecords) {
       fp.Win = job->qin.W; fp.Wout = job->qout.W; fp.minPunchF = job->minPunchF; fp.maxPunchF = job->maxPunchF;
       fp.numPerFile = npf; fp.maxEntrySz = m; fp.minSpacing = job->cfg.minSpacing; fp.step = job->step;
       fp.entries = job->dEntries.p; fp.counts = job->dCounts.p;
+      SGZ_TRY(job->dMeta.alloc(nj));
+      fp.meta = job->dMeta.p;
+      fp.allNonEmpty = job->allPrio.empty() ? 0 : 1;
+      fp.allLast = job->allPrio.empty() ? 0.f : job->allPrio.back().sim;
       static const bool fillProf = getenv("SGZ_FILL_PROF") != nullptr;
       fp.prof = fillProf ? 1 : 0;
       SGZ_TRY(ctx->begin_call());
@@ -483,15 +507,23 @@ inline int corr_select_punchout(sgz_corr *job, int32_t *nRecords) {
       job->selectMs += ctx->lastMs;
       std::vector<int32_t> counts(nj);
       std::vector<EntryRec> ents((size_t)nj * (npf + 1));
+      std::vector<float4> meta((size_t)nj);
       SGZ_CUDA(cudaMemcpyAsync(counts.data(), job->dCounts.p, nj * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
       SGZ_CUDA(cudaMemcpyAsync(ents.data(), job->dEntries.p, ents.size() * sizeof(EntryRec), cudaMemcpyDeviceToHost,
                                ctx->stream));
+      SGZ_CUDA(cudaMemcpyAsync(meta.data(), job->dMeta.p, nj * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
       SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
-      for (int j = 0; j < nj; j++)
+      for (int j = 0; j < nj; j++) {
+        // kind 4 = "gate interval" of the file (one per file of the round, before its matches): piOff = first accepted
+        // row or -1, sim = its in-sim, boostIn = largest in-sim the gate turned away before it
+        int32_t row;
+        memcpy(&row, &meta[j].z, 4);
+        job->localRecords.push_back(sgz_record{myLo + files[j], 4, row, -1, meta[j].y, meta[j].x, 0.f, 0});
         for (int k = 0; k < counts[j]; k++) {
           const EntryRec &e = ents[(size_t)j * (npf + 1) + k];
           job->localRecords.push_back(sgz_record{myLo + files[j], 1, e.piOff, e.stopOff, e.sim, e.boostIn, e.boostOut, 0});
         }
+      }
     }
   } else {
     // full round over a geometrically growing batch of files; theta = allPrio.last.sim now
@@ -577,8 +609,21 @@ inline int corr_merge_punchout(sgz_corr *job, const sgz_record *all, int32_t nAl
     for (int g = job->roundFirst; g < job->roundFirst + job->roundCount; g++) {
       ent.clear();
       while (i < recs.size() && recs[i].file < g) i++;
-      for (; i < recs.size() && recs[i].file == g; i++)
+      bool valid = true;
+      for (; i < recs.size() && recs[i].file == g; i++) {
         if (recs[i].kind == 1) ent.push_back(EntryRec{recs[i].sim, recs[i].piOff, recs[i].poOff, recs[i].boostIn, recs[i].boostOut});
+        else if (recs[i].kind == 4) {
+          // the file ran with the allPrio of the round start; with the allPrio of NOW (files before g merged) the row
+          // gate `inSim > low * low` must pick the same first row, else the file is replayed as the head of the next round
+          const float low = job->allPrio.empty() ? 0.f : job->allPrio.back().sim;
+          const float thr = low * low;
+          valid = !(recs[i].boostIn > thr) && (recs[i].piOff < 0 || recs[i].sim > thr);
+        }
+      }
+      if (!valid) {   // never the first file of a round: its guess is the true state
+        job->roundCount = g - job->roundFirst;
+        break;
+      }
       merge_entry(ent.data(), (int)ent.size(), g);
     }
   } else {

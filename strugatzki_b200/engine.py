@@ -123,6 +123,15 @@ class Database:
         return N.check(N.lib().sgz_db_add_synth(self._h, C.c_uint64(seed), C.c_uint32(stream), C.c_int64(n_frames),
                                                 N.fptr(mu), N.fptr(sigma), C.c_float(floor0)))
 
+    def add_synth_many(self, seed: int, first_stream: int, num_files: int, n_frames_each: int, mu: np.ndarray,
+                       sigma: np.ndarray, floor0: float) -> int:
+        """`num_files` synthetic files in one kernel launch (streams first_stream, first_stream + 1, ...)."""
+        mu = np.ascontiguousarray(mu, np.float32)
+        sigma = np.ascontiguousarray(sigma, np.float32)
+        return N.check(N.lib().sgz_db_add_synth_many(self._h, C.c_uint64(seed), C.c_uint32(first_stream), int(num_files),
+                                                     C.c_int64(n_frames_each), N.fptr(mu), N.fptr(sigma),
+                                                     C.c_float(floor0)))
+
     def patch(self, file: int, frame_off: int, frames: np.ndarray):
         a = _frames(frames)
         N.check(N.lib().sgz_db_patch(self._h, int(file), C.c_int64(frame_off), N.fptr(a), C.c_int64(a.shape[0])))

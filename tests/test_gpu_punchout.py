@@ -101,3 +101,30 @@ def test_punch_out_silence_ties_and_unstaged_path(ctx, monkeypatch, global_path,
     db = build_db(ctx, files, norm)
     got = engine.CorrelationJob(db, nc, inp).run()
     assert_matches_equal(got, O.corr_search(op, files))
+
+
+def strong_then_weak_db(n_files, n_frames=3000):
+    """file 0 holds a planted in/out pair (cell sim close to 1); every later file is weak random material whose in-curve
+    stays below allPrio.last.sim^2, so the reference's row gate (`inSim > low * low` with low = allPrio.last.sim while
+    entryPrio is empty, FeatureCorrelationImpl.scala:125-129,342) lets nothing of them through"""
+    files, norm = make_db(n_files, n_frames)
+    inp = make_input(900)
+    files[0][400:400 + W] = synth.plant(inp[:W], 41, 0)
+    files[0][900:900 + W] = synth.plant(inp[345:345 + W], 41, 1)
+    return files, norm, inp
+
+
+@pytest.mark.parametrize("n_files,num_matches,num_per_file", [(3, 3, 1), (8, 12, 2), (6, 6, 1), (12, 40, 3)])
+def test_punch_out_filling_round_gate_uses_allprio_last(ctx, n_files, num_matches, num_per_file):
+    """filling rounds (numMatches > numPerFile) in which a strong file precedes weak ones: the weak files must be gated
+    by allPrio.last.sim of the files before them, not by 0 (punchout.cuh)"""
+    from strugatzki_b200 import engine
+    files, norm, inp = strong_then_weak_db(n_files)
+    op, nc = corr_cfgs(inp, norm, punch_out=(345 * STEP, (345 + W) * STEP), min_punch=86 * STEP, max_punch=689 * STEP,
+                       num_matches=num_matches, num_per_file=num_per_file, min_spacing=22050)
+    want = O.corr_search(op, files)
+    if num_per_file == 1:   # with more per file the strong file's second match is weak and opens the gate again
+        assert len(want) == 1, "the scenario must leave allPrio short of full"
+    db = build_db(ctx, files, norm)
+    got = engine.CorrelationJob(db, nc, inp).run()
+    assert_matches_equal(got, want)
