@@ -320,6 +320,7 @@ int sgz_db_patch(sgz_db *db, int32_t file, int64_t frameOff, const float *frames
                            db->ctx->stream));
   SGZ_TRY(db_launch_prepare(db, tmp.p, SGZ_LAYOUT_INTERLEAVED_LE, n, db->fileStart[file] + frameOff));
   SGZ_CUDA(cudaStreamSynchronize(db->ctx->stream));
+  db->planesUpto = 0;   // the FP16 planes of the tensor-core K1 are rebuilt by the next search
   return SGZ_OK;
 }
 
@@ -532,6 +533,11 @@ int sgz_corr_create(sgz_db *db, const sgz_corr_config *cfg, const void *input, i
     // kernel covers the rest and streaming scans.  SGZ_CORR_TC=0 forces the FFMA2 kernel.
     const char *e = getenv("SGZ_CORR_TC");
     job->useTc = !(e && atoi(e) == 0) && job->qin.dTcTaps.p && (!job->hasOut || job->qout.dTcTaps.p);
+    // the N = 64 tensor-core kernel fed by bulk copies (corr_tc2.cuh) is the default for resident AND streaming scans;
+    // SGZ_CORR_TC2=0 falls back to the round-1 kernels above
+    const char *e2 = getenv("SGZ_CORR_TC2");
+    job->useT2 = !(e && atoi(e) == 0) && !(e2 && atoi(e2) == 0) && job->qin.dT2Taps.p && (!job->hasOut || job->qout.dT2Taps.p);
+    job->numTilesT2 = ceil_div<int64_t>(std::max<int64_t>(db->usedFrames, 1), (int64_t)kT2Tile);
   }
   job->numOffsets = valid_offsets(db, job->qin.W, job->hasOut ? job->minPunchF : 0);
   db->refs++;
@@ -560,7 +566,26 @@ int sgz_corr_scan(sgz_corr *job) {
   SGZ_TRY(ctx->bind());
   if (job->abortFlag) return SGZ_ERR_ABORTED;
   size_t n = (size_t)job->numTiles * kR * job->ntg;
-  const bool tc = job->useTc && db->chunks.empty();   // a streaming scan hides K1 behind PCIe anyway: FFMA path
+  const bool t2 = job->useT2;
+  const bool tc = !t2 && job->useTc && db->chunks.empty();   // round-1 kernels: a streaming scan takes the FFMA2 path
+  if (t2) {
+    n = std::max(n, (size_t)job->numTilesT2 * kT2Tile);
+    if (!job->dTileFileT2.p) {
+      std::vector<int32_t> tf((size_t)job->numTilesT2 + 1);
+      int f = 0;
+      const int nf = db->numFiles();
+      for (int64_t t = 0; t <= job->numTilesT2; t++) {
+        const int64_t g = std::min<int64_t>(t * kT2Tile, std::max<int64_t>(db->usedFrames - 1, 0));
+        while (f + 1 < nf && db->fileStart[f + 1] <= g) f++;
+        tf[(size_t)t] = f;
+      }
+      SGZ_TRY(job->dTileFileT2.alloc(tf.size()));
+      // small pageable copy on the scan stream: inline, does not queue behind uploads in flight
+      SGZ_CUDA(cudaMemcpyAsync(job->dTileFileT2.p, tf.data(), tf.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+                               ctx->scanStream));
+      SGZ_CUDA(cudaStreamSynchronize(ctx->scanStream));
+    }
+  }
   if (tc) {
     n = std::max(n, (size_t)job->numTilesTc * kTcTile);
     if (!job->dTileFile.p) {
@@ -599,10 +624,27 @@ int sgz_corr_scan(sgz_corr *job) {
       SGZ_CUDA(cudaMemsetAsync(job->dFileMaxOut.p, 0, job->dFileMaxOut.n * sizeof(unsigned long long), ss));
     int64_t done = 0;
     for (const auto &c : db->chunks) {
+      if (db->usedFrames == 0) continue;
+      if (t2) {
+        // planes of the whole 2048-frame blocks that have landed, then the tiles whose operands (8192 frames + 4 rows) and
+        // window statistics (+ W + 16 frames) lie inside them
+        const bool last = c.uptoFrame == INT64_MAX;
+        const int64_t ready = last ? INT64_MAX : c.uptoFrame / kPlaneFrames * kPlaneFrames;
+        const int64_t end = last ? job->numTilesT2
+                                 : std::min<int64_t>(job->numTilesT2, std::max<int64_t>(ready - std::max(320, wqMax + 32), 0) / kT2Tile);
+        if (end <= done && !last) continue;
+        SGZ_CUDA(cudaStreamWaitEvent(ss, c.ev, 0));
+        SGZ_TRY(db_ensure_planes(db, last ? -1 : c.uptoFrame, ss));
+        SGZ_TRY(run_scan_t2(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, done, end, ss, spare));
+        if (job->hasOut)
+          SGZ_TRY(run_scan_t2(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, done, end, ss, spare));
+        done = std::max(done, end);
+        continue;
+      }
       // a tile reads frames [tile*T, (tile+1)*T + Wq)
       const int64_t end = c.uptoFrame == INT64_MAX ? job->numTiles
                                                    : std::min<int64_t>(job->numTiles, std::max<int64_t>(c.uptoFrame - wqMax, 0) / T);
-      if (end <= done || db->usedFrames == 0) continue;
+      if (end <= done) continue;
       SGZ_CUDA(cudaStreamWaitEvent(ss, c.ev, 0));
       SGZ_TRY(run_scan_one(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, done, end, ss, spare));
       if (job->hasOut)
@@ -623,17 +665,23 @@ int sgz_corr_scan(sgz_corr *job) {
     ctx->lastLaunches = ctx->launches - launches0;
     SGZ_TRY(db_wait_resident(db));
   } else {
+    // once per database (a property of the database like its normalisation, not of the search): FP16 planes + frame sums
+    if (t2 && db->usedFrames > 0) SGZ_TRY(db_ensure_planes(db, -1, ctx->stream));
     SGZ_TRY(ctx->begin_call());
     SGZ_CUDA(cudaMemsetAsync(job->dFileMax.p, 0, job->dFileMax.n * sizeof(unsigned long long), ctx->stream));
     if (job->hasOut)
       SGZ_CUDA(cudaMemsetAsync(job->dFileMaxOut.p, 0, job->dFileMaxOut.n * sizeof(unsigned long long), ctx->stream));
     if (db->usedFrames > 0) {
-      if (tc) SGZ_TRY(run_scan_tc(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, ctx->stream));
+      if (t2) SGZ_TRY(run_scan_t2(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, 0, job->numTilesT2,
+                                  ctx->stream, 0));
+      else if (tc) SGZ_TRY(run_scan_tc(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, ctx->stream));
       else
         SGZ_TRY(run_scan_one(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, 0, job->numTiles,
                              ctx->stream, 0));
       if (job->hasOut) {
-        if (tc) SGZ_TRY(run_scan_tc(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, ctx->stream));
+        if (t2) SGZ_TRY(run_scan_t2(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, 0, job->numTilesT2,
+                                    ctx->stream, 0));
+        else if (tc) SGZ_TRY(run_scan_tc(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, ctx->stream));
         else
           SGZ_TRY(run_scan_one(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, 0, job->numTiles,
                                ctx->stream, 0));

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "corr_kernel.cuh"
 #include "corr_tc.cuh"
+#include "corr_tc2.cuh"
 #include "db.cuh"
 #include "select.cuh"
 
@@ -16,6 +17,7 @@ struct PunchQuery {
   DevBuf<float> dTaps;
   std::vector<uint16_t> tcTaps;
   DevBuf<uint16_t> dTcTaps;    // tensor-core path: hi/lo Toeplitz atoms (corr_tc.cuh), empty when not applicable
+  DevBuf<unsigned char> dT2Taps;   // N = 64 tensor-core path (corr_tc2.cuh), empty when not applicable
 };
 
 struct sgz_corr {
@@ -28,8 +30,10 @@ struct sgz_corr {
   int ntg = 128;
   int nslot = 3;
   bool useTc = false;       // K1 on the tensor cores (corr_tc.cuh) for resident scans
-  int64_t numTilesTc = 0;
+  bool useT2 = false;       // K1 on the tensor cores, N = 64 tiles fed by bulk copies (corr_tc2.cuh): the default
+  int64_t numTilesTc = 0, numTilesT2 = 0;
   DevBuf<int32_t> dTileFile;   // [numTilesTc + 1] file holding the first frame of each tensor-core tile
+  DevBuf<int32_t> dTileFileT2; // the same for the 8192-offset tiles of corr_tc2.cuh
   int64_t numTiles = 0;
   int64_t numOffsets = 0;
   DevBuf<float> simIn, boostIn, simOut, boostOut, rowMaxOut;
@@ -73,6 +77,38 @@ namespace sgz {
 // the tensor-core K1 handles up to 14 channels (16 TMEM accumulators) and windows whose operands fit shared memory
 inline bool tc_applicable(const sgz_ctx *ctx, int numCh, int W) {
   return numCh >= 2 && numCh <= 14 && W >= 1 && W <= 256 && tc_geom(W).smemBytes <= ctx->smemOptin;
+}
+
+// the N = 64 kernel takes any channel count (the spectral channels share five accumulators) and every window whose
+// operand / taps rings fit shared memory (W <~ 900 frames with the minimum of two stages each)
+inline bool t2_applicable(const sgz_ctx *ctx, int numCh, int W) {
+  return numCh >= 2 && W >= 1 && W <= 4096 && t2_geom(W, ctx->smemOptin).smemBytes <= ctx->smemOptin;
+}
+
+// FP16 planes and per-frame sums of the frames [db->planesUpto, upto) -- whole 2048-frame blocks; upto < 0 = everything
+// a tile may touch (the zero slack behind the last file included)
+inline int db_ensure_planes(sgz_db *db, int64_t upto, cudaStream_t st) {
+  const int64_t strideFrames = (db->capFrames + kT2Tile - 1) / kT2Tile * kT2Tile;
+  if (!db->dPlanes.p || db->planeStrideBytes != strideFrames * 2) {
+    db->planeStrideBytes = strideFrames * 2;
+    SGZ_TRY(db->dPlanes.alloc((size_t)db->numCh * 2 * (size_t)db->planeStrideBytes));
+    SGZ_TRY(db->dSide0.alloc((size_t)strideFrames));
+    SGZ_TRY(db->dSide1.alloc((size_t)strideFrames));
+    SGZ_TRY(db->dSide2.alloc((size_t)strideFrames));
+    db->planeRows = strideFrames / kT2P;
+    SGZ_TRY(db->dB16.alloc((size_t)16 * db->planeRows));
+    db->planesUpto = 0;
+  }
+  const int64_t all = std::min(strideFrames, (db->usedFrames + kDbSlack + kPlaneFrames - 1) / kPlaneFrames * kPlaneFrames);
+  const int64_t end = upto < 0 ? all : std::min(all, upto / kPlaneFrames * kPlaneFrames);
+  if (end <= db->planesUpto) return SGZ_OK;
+  const unsigned blocks = (unsigned)((end - db->planesUpto) / kPlaneFrames);
+  k_db_planes<<<blocks, 256, 0, st>>>(db->dData.p, db->capFrames, db->numCh, db->numPairs, db->planesUpto,
+                                      std::min(end, db->capFrames), db->dPlanes.p, db->planeStrideBytes, db->dSide0.p,
+                                      db->dSide1.p, db->dSide2.p, db->dB16.p, db->planeRows);
+  SGZ_LAUNCH_CHECK(db->ctx);
+  db->planesUpto = end;
+  return SGZ_OK;
 }
 
 // readInBuffer (FeatureCorrelationImpl.scala:83-98): cut [start,stop) feature frames, normalise,
@@ -138,6 +174,12 @@ inline int prepare_query(const sgz_db *db, const float *inputPlanar /*[numCh][in
     tc_build_taps(q.taps, db->numPairs, q.Wq, W, q.tcTaps);
     SGZ_TRY(q.dTcTaps.alloc(q.tcTaps.size()));
     SGZ_CUDA(cudaMemcpyAsync(q.dTcTaps.p, q.tcTaps.data(), q.tcTaps.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+  }
+  if (t2_applicable(db->ctx, numCh, W)) {
+    const T2Geom g = t2_geom(W, db->ctx->smemOptin);
+    SGZ_TRY(q.dT2Taps.alloc((size_t)numCh * g.tapsBytes));
+    k_t2_taps<<<numCh, 256, 0, st>>>(reinterpret_cast<const float2 *>(q.dTaps.p), numCh, q.Wq, W, q.dT2Taps.p);
+    SGZ_LAUNCH_CHECK(db->ctx);
   }
   return SGZ_OK;
 }
@@ -256,6 +298,53 @@ inline int run_scan_tc(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim, 
                     "issue %.0f || epilogue wait accFull %.0f, tmem read %.0f, wait stats %.0f, row sums %.0f, init %.0f, loop %.0f || split loads+sums %.0f, wait opFree %.0f, store %.0f, stats %.0f\n",
             a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles, a[4] / tiles, a[5] / tiles, a[8] / tiles, a[9] / tiles,
             a[10] / tiles, a[12] / tiles, a[13] / tiles, a[11] / tiles, a[16] / tiles, a[17] / tiles, a[18] / tiles, a[19] / tiles);
+  }
+  return SGZ_OK;
+}
+
+// N = 64 tensor-core K1 over tiles [tileBegin, tileEnd) of 8192 offsets (corr_tc2.cuh); the planes of every frame the
+// tiles touch must have been enqueued on `st` (db_ensure_planes)
+inline int run_scan_t2(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim, float *boost, unsigned long long *fileMax,
+                       int64_t tileBegin, int64_t tileEnd, cudaStream_t st, int spareSMs) {
+  if (tileEnd <= tileBegin) return SGZ_OK;
+  sgz_db *db = job->db;
+  sgz_ctx *ctx = job->ctx;
+  const T2Geom G = t2_geom(q.W, ctx->smemOptin);
+  CorrT2Params tp{};
+  tp.planes = db->dPlanes.p; tp.planeStrideBytes = db->planeStrideBytes;
+  tp.sb0 = db->dSide0.p; tp.sb1 = db->dSide1.p; tp.sb2 = db->dSide2.p;
+  tp.b16 = db->dB16.p; tp.rowsTotal = db->planeRows;
+  tp.usedFrames = db->usedFrames; tp.numCh = db->numCh; tp.W = q.W;
+  tp.taps = q.dT2Taps.p;
+  tp.stdT = q.stdT; tp.stdS = q.stdS; tp.rhoT = q.rhoT; tp.rhoS = q.rhoS; tp.lnAvgIn = q.lnAvg;
+  tp.weight = q.weight; tp.maxBoost = job->cfg.maxBoost;
+  tp.fileStart = db->dFileStart.p; tp.tileFile = job->dTileFileT2.p; tp.numFiles = db->numFiles(); tp.tailExtra = tailExtra;
+  tp.tileBegin = tileBegin; tp.tileEnd = tileEnd;
+  tp.sim = sim; tp.boost = boost; tp.fileMax = fileMax;
+  tp.smemMax = (int)ctx->smemOptin;
+  const bool prof = getenv("SGZ_CORR_TC_PROF") != nullptr;   // developer probe: cycles per role and phase
+  auto kern = prof ? k_corr_tc2<true> : k_corr_tc2<false>;
+  SGZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));
+  const unsigned grid = (unsigned)std::min<int64_t>(tileEnd - tileBegin, std::max(ctx->smCount - spareSMs, 1));
+  DevBuf<long long> dProf;
+  if (prof) {
+    SGZ_TRY(dProf.alloc((size_t)grid * 24));
+    SGZ_CUDA(cudaMemsetAsync(dProf.p, 0, (size_t)grid * 24 * sizeof(long long), st));
+    tp.prof = dProf.p;
+  }
+  kern<<<grid, kT2Threads, G.smemBytes, st>>>(tp);
+  SGZ_LAUNCH_CHECK(ctx);
+  if (prof) {
+    std::vector<long long> h((size_t)grid * 24);
+    SGZ_CUDA(cudaMemcpyAsync(h.data(), dProf.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    SGZ_CUDA(cudaStreamSynchronize(st));
+    double a[24] = {0};
+    for (unsigned b = 0; b < grid; b++) for (int k = 0; k < 24; k++) a[k] += (double)h[(size_t)b * 24 + k];
+    const double tiles = a[5] > 0 ? a[5] : 1;
+    fprintf(stderr, "k_corr_tc2 cycles per tile (8192 offsets): issuer total %.0f | wait accEmpty %.0f, signal %.0f, taps %.0f, issue %.0f "
+                    "|| epilogue singles + wait sums %.0f, window init %.0f, wait accFull %.0f, tmem read %.0f, 16 offsets %.0f\n",
+            a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles, a[4] / tiles, a[8] / tiles, a[9] / tiles, a[10] / tiles,
+            a[11] / tiles, a[12] / tiles);
   }
   return SGZ_OK;
 }

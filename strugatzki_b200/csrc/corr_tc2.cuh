@@ -1,0 +1,555 @@
+// corr_tc2.cuh -- K1 on the tensor cores, second generation: N = 64 tiles fed by bulk copies (round 2).
+//
+//   cross(t) = sum_c sum_i q~[c][i] * b[c][t + i]            (FeatureCorrelationImpl.scala:198-210 via MathUtil.correlate)
+//
+// Same split-FP16 formulation as corr_tc.cuh (a*t = a1*t1 + (a2*t1 + a1*t2), products accumulated in FP32 in TMEM), but
+//   * the Hankel period is 64: A (M = 128, K-major, SWIZZLE_128B) A[r][k] = b[c][t0 + 64 r + k] -- the 128-byte row of the
+//     swizzle atom IS the shift between rows, so the operand is the FP16 signal itself and one tile is 8192 offsets;
+//     B (N = 64, K-major, SWIZZLE_32B) = banded Toeplitz taps with reversed columns, block (K step s, row group g') =
+//     atom 2 s + g'.  An M128 x N64 x K16 MMA fetches 6 KB from shared memory for 64 columns where N = 32 fetched 5 KB
+//     for 32 (the operand fetch, not the math, bounds small-N MMAs: 48 against 44.5 cycles, tools/umma_rate_probe.cu);
+//   * the FP16 parts of the database are computed ONCE per database (k_db_planes: pre-swizzled planes, 2 x 2 B per value
+//     = the 56 B per frame of the float rows) together with the per-frame sums the window statistics need, so nothing in
+//     this kernel touches the operands with ordinary loads/stores: a producer lane streams them with cp.async.bulk
+//     through a 4-deep ring (UBLKCP), the taps of the channel through a second ring;
+//   * 8 accumulators of 64 columns fill TMEM: [T main, T corr, S corr, 5 spectral mains] -- the spectral channels take
+//     turns on the five main accumulators (chains of <= 3 x KS MMAs; the tensor core truncates when it aligns addends,
+//     so the chain length bounds the bias);
+//   * 16 epilogue warps (window statistics in FP64 from 16-frame block sums + exact slides, boost, blend, file maxima)
+//     work on tile n while the MMAs of tile n + 1 run; the FP64 block sums are part of the prepared database too and
+//     arrive by bulk copy.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "corr_tc.cuh"
+
+namespace sgz {
+
+constexpr int kT2P = 64, kT2M = 128, kT2Tile = kT2P * kT2M;
+constexpr int kT2Mains = 5;               // spectral main accumulators
+constexpr int kT2EpiWarps = 16, kT2Threads = (4 + kT2EpiWarps) * 32;
+
+struct T2Geom {
+  int W, KS, natom, rows, sumRows, sumPitch;
+  uint32_t planeBytes;      // one FP16 part of one channel of one tile (rows x 128 B)
+  uint32_t planeStride;     // placement stride in shared memory (multiple of 1024)
+  uint32_t tapsBytes;       // taps of one channel: first-part atoms then second-part atoms
+  uint32_t tapsStride;
+  uint32_t sumsBytes;
+  int sigStages, tapStages;
+  size_t smemBytes;
+};
+
+__host__ __device__ inline T2Geom t2_geom(int W, size_t smemMax = 232448) {
+  T2Geom g;
+  g.W = W;
+  g.KS = (kT2P - 1 + W + 15) / 16;
+  g.natom = 2 * g.KS + 6;
+  g.rows = kT2M - 1 + (g.KS + 3) / 4;               // row 127 runs on for 16 KS halves
+  g.planeBytes = (uint32_t)g.rows * 128u;
+  g.planeStride = (g.planeBytes + 1023u) / 1024u * 1024u;
+  g.tapsBytes = (uint32_t)g.natom * 256u * 2u;
+  g.tapsStride = (g.tapsBytes + 1023u) / 1024u * 1024u;
+  g.sumRows = kT2M + (W + 63) / 64;                  // 64-frame rows that windows starting in the tile can touch
+  g.sumPitch = (g.sumRows + 1) & ~1;                 // bulk copies move multiples of 16 bytes
+  g.sumsBytes = (uint32_t)(16 * g.sumPitch * 8);     // [4 quantities][4 column blocks][sumPitch] doubles
+  g.sigStages = 4;
+  g.tapStages = 3;
+  for (;;) {
+    g.smemBytes = (size_t)g.sigStages * 2 * g.planeStride + (size_t)g.tapStages * g.tapsStride + g.sumsBytes +
+                  1024 /*alignment slack*/ + 256 /*barriers*/;
+    if (g.smemBytes <= smemMax || (g.sigStages == 2 && g.tapStages == 2)) break;
+    if (g.sigStages > g.tapStages || g.tapStages == 2) g.sigStages--; else g.tapStages--;
+  }
+  return g;
+}
+
+// position of frame g in a pre-swizzled FP16 plane (bytes): SWIZZLE_128B = 16-byte chunk index ^= 128-byte row index mod 8
+__host__ __device__ inline int64_t t2_plane_byte(int64_t g) {
+  const int64_t a = 2 * g;
+  return a ^ (((a >> 7) & 7) << 4);
+}
+// position of frame g in a tile-transposed per-frame array: [tile][frame % 64][frame / 64 % 128]
+__host__ __device__ inline int64_t t2_side_index(int64_t g) {
+  return (g & ~(int64_t)(kT2Tile - 1)) + ((g & 63) << 7) + ((g >> 6) & 127);
+}
+
+// taps image of a taps stage: per channel [first-part atoms][second-part atoms], atom a = 8 rows (cc) x 16 k (kk) halves
+// holding q~[8 a + kk + cc - 63], SWIZZLE_32B chunk flip on rows 4..7.  Built on the device from the float taps (one block
+// per channel): the float taps are a few KB and reach the device as an inline copy even while database uploads occupy
+// the copy engine (streaming scans)
+__global__ void k_t2_taps(const float2 *__restrict__ pairTaps, int numCh, int Wq, int W, unsigned char *__restrict__ out) {
+  const T2Geom g = t2_geom(W);   // natom / tapsBytes do not depend on the shared-memory limit
+  const int c = blockIdx.x;
+  const float *tp = reinterpret_cast<const float *>(pairTaps + (size_t)(c >> 1) * Wq) + (c & 1);
+  for (int i = threadIdx.x; i < 2 * g.natom * 128; i += blockDim.x) {
+    const int part = i / (g.natom * 128), rem = i - part * g.natom * 128;
+    const int a = rem >> 7, cc = (rem >> 4) & 7, kk = rem & 15;
+    const int q = 8 * a + kk + cc - (kT2P - 1);
+    __half v = __float2half_rn(0.f);
+    if (q >= 0 && q < W) {
+      const float t = tp[2 * q];
+      const __half t1 = __float2half_rn(t);
+      v = part == 0 ? t1 : __float2half_rn((t - __half2float(t1)) * kTcLoScale);
+    }
+    const size_t byteOff = (size_t)c * g.tapsBytes + (size_t)part * g.natom * 256 + (size_t)a * 256 + (size_t)cc * 32 +
+                           (size_t)(((kk >> 3) ^ ((cc >> 2) & 1)) << 4) + (size_t)(kk & 7) * 2;
+    *reinterpret_cast<__half *>(out + byteOff) = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0b: FP16 planes + per-frame sums of a frame range of the database (once per database / upload chunk)
+// ---------------------------------------------------------------------------------------------
+// planes[(2 c + part)][planeStrideBytes]: part 0 = fp16(x), part 1 = fp16((x - part0) * 2^11), pre-swizzled (t2_plane_byte);
+// side arrays (tile transposed, t2_side_index): b0 = loudness, s1 = sum over spectral channels, s2 = sum of their squares
+// (the FP32 arithmetic of the round-1 split warps: s1 += x + y, s2 = fma(x, x, fma(y, y, s2)) pair by pair);
+// b16[(4 q + cb)][rowsTotal]: FP64 sums of (b0, b0^2, s1, s2)[q] over the aligned 16-frame block cb of each 64-frame row.
+constexpr int kPlaneFrames = 2048;     // frames per block (256 threads x 8 frames)
+__global__ void __launch_bounds__(256) k_db_planes(const float2 *__restrict__ data, int64_t rowStride, int numCh, int numPairs,
+                                                   int64_t frameBegin, int64_t frameEnd, unsigned char *__restrict__ planes,
+                                                   int64_t planeStrideBytes, float *__restrict__ sb0, float *__restrict__ sb1,
+                                                   float *__restrict__ sb2, double *__restrict__ b16, int64_t rowsTotal) {
+  __shared__ float sh[3][kPlaneFrames + 32];    // +1 per 64 frames against bank conflicts of the transposed read-out
+  const int64_t f0 = frameBegin + (int64_t)blockIdx.x * kPlaneFrames;   // frameBegin is a multiple of 2048
+  const int64_t g0 = f0 + 8 * (int64_t)threadIdx.x;
+  float b0[8], s1[8], s2[8];
+  for (int pr = 0; pr < numPairs; pr++) {
+    const float4 *src = reinterpret_cast<const float4 *>(data + (int64_t)pr * rowStride + g0);
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = g0 + 2 * k < frameEnd ? __ldg(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float x[8], y[8];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { x[2 * k] = v[k].x; y[2 * k] = v[k].y; x[2 * k + 1] = v[k].z; y[2 * k + 1] = v[k].w; }
+    if (pr == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) { b0[k] = x[k]; s1[k] = y[k]; s2[k] = y[k] * y[k]; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) { s1[k] += x[k] + y[k]; s2[k] = fmaf(x[k], x[k], fmaf(y[k], y[k], s2[k])); }
+    }
+    uint32_t xh[4], xl[4], yh[4], yl[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const __half2 xa = __floats2half2_rn(x[2 * k], x[2 * k + 1]), ya = __floats2half2_rn(y[2 * k], y[2 * k + 1]);
+      const float2 xf = __half22float2(xa), yf = __half22float2(ya);
+      const __half2 xb = __floats2half2_rn((x[2 * k] - xf.x) * kTcLoScale, (x[2 * k + 1] - xf.y) * kTcLoScale);
+      const __half2 yb = __floats2half2_rn((y[2 * k] - yf.x) * kTcLoScale, (y[2 * k + 1] - yf.y) * kTcLoScale);
+      xh[k] = *reinterpret_cast<const uint32_t *>(&xa); xl[k] = *reinterpret_cast<const uint32_t *>(&xb);
+      yh[k] = *reinterpret_cast<const uint32_t *>(&ya); yl[k] = *reinterpret_cast<const uint32_t *>(&yb);
+    }
+    const int64_t pos = t2_plane_byte(g0);     // 8 frames = one 16-byte chunk
+    const int c0 = 2 * pr, c1 = 2 * pr + 1;
+    *reinterpret_cast<uint4 *>(planes + (int64_t)(2 * c0) * planeStrideBytes + pos) = make_uint4(xh[0], xh[1], xh[2], xh[3]);
+    *reinterpret_cast<uint4 *>(planes + (int64_t)(2 * c0 + 1) * planeStrideBytes + pos) = make_uint4(xl[0], xl[1], xl[2], xl[3]);
+    if (c1 < numCh) {
+      *reinterpret_cast<uint4 *>(planes + (int64_t)(2 * c1) * planeStrideBytes + pos) = make_uint4(yh[0], yh[1], yh[2], yh[3]);
+      *reinterpret_cast<uint4 *>(planes + (int64_t)(2 * c1 + 1) * planeStrideBytes + pos) = make_uint4(yl[0], yl[1], yl[2], yl[3]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int L = 8 * threadIdx.x + k, i = L + (L >> 6);
+    sh[0][i] = b0[k]; sh[1][i] = s1[k]; sh[2][i] = s2[k];
+  }
+  __syncthreads();
+  // transposed write-out: the block's 2048 frames are 32 rows x 64 columns of one tile; a warp writes 32 consecutive rows
+  // of one column (128 contiguous bytes)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t base = t2_side_index(f0);      // row of f0 within its tile, column 0
+  for (int col = warp; col < 64; col += 8) {
+    const int L = 64 * lane + col, i = L + (L >> 6);
+    const int64_t o = base + ((int64_t)col << 7) + lane;
+    sb0[o] = sh[0][i]; sb1[o] = sh[1][i]; sb2[o] = sh[2][i];
+  }
+  // FP64 sums of the 128 aligned 16-frame blocks: warp cb takes column block cb of the 32 rows, lane = row
+  if (warp < 4) {
+    const int L0 = 64 * lane + 16 * warp, i0 = L0 + (L0 >> 6);
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+    for (int e = 0; e < 16; e += 2) {
+      const double x = (double)sh[0][i0 + e], x2 = (double)sh[0][i0 + e + 1];
+      a0 += x; a1 += x * x; c0 += x2; c1 += x2 * x2;
+      a2 += (double)sh[1][i0 + e]; c2 += (double)sh[1][i0 + e + 1];
+      a3 += (double)sh[2][i0 + e]; c3 += (double)sh[2][i0 + e + 1];
+    }
+    double *dst = b16 + (int64_t)warp * rowsTotal + (f0 >> 6) + lane;
+    dst[0] = a0 + c0; dst[4 * rowsTotal] = a1 + c1; dst[8 * rowsTotal] = a2 + c2; dst[12 * rowsTotal] = a3 + c3;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+struct CorrT2Params {
+  const unsigned char *planes;  // [numCh * 2][planeStrideBytes]
+  int64_t planeStrideBytes;
+  const float *sb0, *sb1, *sb2; // tile-transposed per-frame loudness / spectral sum / spectral sum of squares
+  const double *b16;            // [16][rowsTotal] FP64 sums of aligned 16-frame blocks
+  int64_t rowsTotal;
+  int64_t usedFrames;
+  int numCh, W;
+  const unsigned char *taps;    // k_t2_taps image
+  double stdT, stdS, rhoT, rhoS, lnAvgIn;
+  float weight, maxBoost;
+  const int64_t *fileStart;
+  const int32_t *tileFile;      // [numTiles + 1] file that holds frame 8192 * tile (clamped to the last file)
+  int numFiles, tailExtra;
+  int64_t tileBegin, tileEnd;
+  float *sim, *boost;
+  unsigned long long *fileMax;
+  long long *prof;              // SGZ_CORR_TC_PROF: per CTA 24 cycle counters (k_corr_tc2<true>), or nullptr
+  int smemMax;                  // the geometry (ring depths) is a function of (W, shared memory limit)
+};
+
+__device__ __forceinline__ bool t2_test(uint64_t *bar, uint32_t parity) {   // non-blocking phase test
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
+// one evaluated offset: window sums -> boost and sim (FeatureCorrelationImpl.scala:73-78,198-210)
+struct T2Eval {
+  double invW, invNS;
+  float cT, cS, kT, kS, l2In, wT, wS, maxBoost;
+  bool useT, useS;
+};
+__device__ __forceinline__ void t2_eval(const T2Eval &E, const D4 &win, float accT, float accS, float &sim, float &boost) {
+  const float qnan = __int_as_float(0x7fc00000);
+  const double mT = win.t1 * E.invW;
+  const float avgB = (float)mT;                                            // MathUtil.avg -> Float
+  boost = exp2f((E.l2In - __log2f(avgB)) * (1.0f / 0.6f));                 // calcBoost
+  float temporal = 0.f, spectral = 0.f;
+  if (E.useT) {
+    const double q = win.t2 * E.invW;
+    const double var = q - mT * mT;
+    const float cr = fmaf(accT, E.cT, -(float)mT * E.kT);                  // (acc - mean_b * rho) / (W std_a)
+    temporal = (var > 1e-13 * q) ? cr * rsqrtf((float)var) : qnan;
+  }
+  if (E.useS) {
+    const double mS = win.s1 * E.invNS;
+    const double q = win.s2 * E.invNS;
+    const double var = q - mS * mS;
+    const float cr = fmaf(accS, E.cS, -(float)mS * E.kS);
+    spectral = (var > 1e-13 * q) ? cr * rsqrtf((float)var) : qnan;
+  }
+  const float blend = __fadd_rn(__fmul_rn(temporal, E.wT), __fmul_rn(spectral, E.wS));
+  sim = boost <= E.maxBoost ? blend : 0.f;
+}
+
+// warp 0: producer (bulk copies), warp 1: MMA issuer, warps 2-3: idle (they complete the first warpgroup, which hands most
+// of its registers to the others: setmaxnreg), warps 4..19: epilogue
+template <bool kProf>
+__global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p) {
+  extern __shared__ __align__(1024) unsigned char smemRaw[];
+  const T2Geom G = t2_geom(p.W, (size_t)p.smemMax);
+  unsigned char *base = smemRaw + ((1024 - (smem_u32(smemRaw) & 1023)) & 1023);
+  auto sigBuf = [&](int s, int part) { return base + (size_t)(2 * s + part) * G.planeStride; };
+  unsigned char *tapsBase = base + (size_t)G.sigStages * 2 * G.planeStride;
+  auto tapBuf = [&](int s) { return tapsBase + (size_t)s * G.tapsStride; };
+  double *B16 = reinterpret_cast<double *>(tapsBase + (size_t)G.tapStages * G.tapsStride);   // [q][cb][sumPitch]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(B16) + G.sumsBytes);
+  uint64_t *sigFull = bars, *sigFree = bars + 4, *tapFull = bars + 8, *tapFree = bars + 12;
+  uint64_t *accFull = bars + 16, *accEmpty = bars + 17, *sumsFull = bars + 18, *sumsFree = bars + 19;
+  uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(bars + 20);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < 4; s++) { mbar_init(sigFull + s, 1); mbar_init(sigFree + s, 1); mbar_init(tapFull + s, 1); mbar_init(tapFree + s, 1); }
+    mbar_init(accFull, 1);
+    mbar_init(accEmpty, kT2EpiWarps);
+    mbar_init(sumsFull, 1);
+    mbar_init(sumsFree, kT2EpiWarps);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmemSlot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = *tmemSlot;
+  // 640 threads are launched with 96 registers each; the service warpgroup keeps 64, the epilogue warpgroups take 104 (the pool only holds what was released)
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+  if (warp == 0) {
+    // =========================== producer ===========================
+    if (lane == 0) {
+      uint32_t it = 0, tileIt = 0;
+      for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, tileIt++) {
+        const unsigned char *src = p.planes + tile * (int64_t)(kT2Tile * 2);
+        bool sumsPending = true;     // the block sums of this tile overwrite those of the previous one: once its windows are set up
+        for (int c = 0; c <= p.numCh; c++) {
+          if (sumsPending && (c == p.numCh || tileIt == 0 || t2_test(sumsFree, (tileIt - 1) & 1))) {
+            if (tileIt > 0) tc_wait(sumsFree, (tileIt - 1) & 1);
+            mbar_expect_tx(sumsFull, G.sumsBytes);
+            for (int k = 0; k < 16; k++)
+              bulk_g2s(B16 + k * G.sumPitch, p.b16 + (int64_t)k * p.rowsTotal + tile * kT2M, (uint32_t)G.sumPitch * 8u, sumsFull);
+            sumsPending = false;
+          }
+          if (c == p.numCh) break;
+          const uint32_t s = it % (uint32_t)G.sigStages, u = it / (uint32_t)G.sigStages;
+          if (u > 0) tc_wait(sigFree + s, (u - 1) & 1);
+          mbar_expect_tx(sigFull + s, 2 * G.planeBytes);
+          bulk_g2s(sigBuf(s, 0), src + (int64_t)(2 * c) * p.planeStrideBytes, G.planeBytes, sigFull + s);
+          bulk_g2s(sigBuf(s, 1), src + (int64_t)(2 * c + 1) * p.planeStrideBytes, G.planeBytes, sigFull + s);
+          const uint32_t t = it % (uint32_t)G.tapStages, v = it / (uint32_t)G.tapStages;
+          if (v > 0) tc_wait(tapFree + t, (v - 1) & 1);
+          mbar_expect_tx(tapFull + t, G.tapsBytes);
+          bulk_g2s(tapBuf(t), p.taps + (size_t)c * G.tapsBytes, G.tapsBytes, tapFull + t);
+          it++;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    // D = F32, A = B = F16, both K-major, N = 64, M = 128
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(kT2P >> 3) << 17) | ((uint32_t)(kT2M >> 4) << 24);
+    uint32_t it = 0, tileIt = 0;
+    long long cAcc = 0, cSig = 0, cTap = 0, cIssue = 0, cTotal = 0, tA = 0;
+    if (kProf) cTotal = clock64();
+    for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, tileIt++) {
+      uint32_t started = 0;     // bit i: accumulator i holds a partial sum of this tile
+      if (kProf) tA = clock64();
+      if (tileIt > 0) tc_wait<false>(accEmpty, (tileIt - 1) & 1);   // the epilogue has drained the accumulators
+      if (kProf) cAcc += clock64() - tA;
+      for (int c = 0; c < p.numCh; c++, it++) {
+        const uint32_t s = it % (uint32_t)G.sigStages, u = it / (uint32_t)G.sigStages;
+        const uint32_t t = it % (uint32_t)G.tapStages, v = it / (uint32_t)G.tapStages;
+        if (kProf) tA = clock64();
+        tc_wait<false>(tapFull + t, v & 1);
+        if (kProf) { cTap += clock64() - tA; tA = clock64(); }
+        tc_wait<false>(sigFull + s, u & 1);
+        if (kProf) { cSig += clock64() - tA; tA = clock64(); }
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const uint32_t iMain = c == 0 ? 0u : 3u + (uint32_t)((c - 1) % kT2Mains), iCorr = c == 0 ? 1u : 2u;
+        const uint32_t dMain = tmem + 64u * iMain, dCorr = tmem + 64u * iCorr;
+        const uint32_t accMain = (started >> iMain) & 1u, accCorr = (started >> iCorr) & 1u;
+        started |= (1u << iMain) | (1u << iCorr);
+        const uint64_t aHi = tc_desc(smem_u32(sigBuf(s, 0)), 1024, 2), aLo = tc_desc(smem_u32(sigBuf(s, 1)), 1024, 2);
+        const uint32_t tHiA = smem_u32(tapBuf(t));
+        const uint64_t tHi = tc_desc(tHiA, 256, 6), tLo = tc_desc(tHiA + (uint32_t)G.natom * 256u, 256, 6);
+        if (tc_elect()) {
+          // one K step of 16: A start +32 B (2 descriptor units), taps start +2 atoms = 512 B (32 units); a1 t1 and
+          // a1 t2 share the A operand through the collector
+          uint64_t d1 = aHi, d2 = aLo, b1 = tHi, b2 = tLo;
+          for (int k = 0; k < G.KS; k++, d1 += 2, d2 += 2, b1 += 32, b2 += 32) {
+            tc_mma_fill(dMain, d1, b1, idesc, accMain | (uint32_t)(k > 0));
+            tc_mma_lastuse(dCorr, d1, b2, idesc, accCorr | (uint32_t)(k > 0));
+            tc_mma(dCorr, d2, b1, idesc, 1);
+          }
+          tc_commit(sigFree + s);
+          tc_commit(tapFree + t);
+          if (c == p.numCh - 1) tc_commit(accFull);
+        }
+        __syncwarp();
+        if (kProf) cIssue += clock64() - tA;
+      }
+    }
+    if (kProf && p.prof && lane == 0) {
+      long long *o = p.prof + 24 * blockIdx.x;
+      o[0] = clock64() - cTotal; o[1] = cAcc; o[2] = cSig; o[3] = cTap; o[4] = cIssue; o[5] = tileIt;
+    }
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    // =========================== epilogue ===========================
+    // 16 warps: TMEM lane quarter q = warp % 4 (rows r = 32 q + lane), column group j = (warp - 4) / 4.  A thread owns the
+    // 16 offsets t0 + 64 r + jb .. + 15 (accumulator columns 63 - offset), jb = 16 (3 - j).
+    const int ew = warp - 4, quarter = warp & 3, jg = ew >> 2, et = ew * 32 + lane;
+    const int jb = 16 * (3 - jg);
+    const int W = p.W;
+    T2Eval E;
+    E.invW = 1.0 / (double)W; E.invNS = 1.0 / ((double)(p.numCh - 1) * (double)W);
+    E.cT = (float)(E.invW / p.stdT); E.cS = (float)(E.invNS / p.stdS);
+    E.kT = (float)p.rhoT * E.cT; E.kS = (float)p.rhoS * E.cS;
+    E.l2In = (float)(p.lnAvgIn * 1.4426950408889634);
+    E.wT = p.weight; E.wS = __fsub_rn(1.0f, p.weight); E.maxBoost = p.maxBoost;
+    E.useT = p.weight > 0.f; E.useS = p.weight < 1.f;
+    const float qnan = __int_as_float(0x7fc00000);
+    const int r = quarter * 32 + lane;
+    // window of the thread's first offset = nbk aligned 16-frame blocks, plus (sgn > 0) or minus (sgn < 0) nsg single frames
+    const int nb = W >> 4, left = W & 15;
+    const int nbk = left > 8 ? nb + 1 : nb, nsg = left > 8 ? 16 - left : left, sg0 = left > 8 ? W : nb << 4;
+    const double sgn = left > 8 ? -1.0 : 1.0;
+    uint32_t tileIt = 0;
+    long long eAcc = 0, eLd = 0, eSt = 0, eInit = 0, eMain = 0, tE = 0;
+    for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, tileIt++) {
+      const int64_t t0 = tile * kT2Tile;
+      const int64_t g0 = t0 + 64 * (int64_t)r + jb;
+      {   // pull the per-frame arrays of the NEXT tile into L2: this tile's slides then wait for L2, not for HBM
+        const int64_t nt = tile + gridDim.x;
+        if (nt < p.tileEnd) {
+          for (int l = et; l < 3 * 256; l += kT2EpiWarps * 32) {
+            const float *a = l < 256 ? p.sb0 : (l < 512 ? p.sb1 : p.sb2);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a + nt * kT2Tile + (int64_t)(l & 255) * 32));
+          }
+        }
+      }
+      int f;
+      {
+        int lo = p.tileFile[tile], hi = p.tileFile[tile + 1] + 1;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (p.fileStart[mid] <= g0) lo = mid; else hi = mid;
+        }
+        f = lo;
+      }
+      int64_t fStart = p.fileStart[f], fEnd = p.fileStart[f + 1];
+      if (kProf) tE = clock64();
+
+      // ---- window statistics of the first offset (needs no accumulator) ----
+      D4 win = {0, 0, 0, 0};
+      {
+        // single frames first: their loads are in flight while the block sums arrive
+        D4 w2 = {0, 0, 0, 0};
+        for (int e = 0; e < nsg; e++) {
+          const int w = jb + sg0 + e, rr = r + (w >> 6);
+          const int64_t o = (tile + (rr >> 7)) * (int64_t)kT2Tile + ((int64_t)(w & 63) << 7) + (rr & 127);
+          const double x = (double)__ldg(p.sb0 + o);
+          w2.t1 += x; w2.t2 += x * x; w2.s1 += (double)__ldg(p.sb1 + o); w2.s2 += (double)__ldg(p.sb2 + o);
+        }
+        tc_wait(sumsFull, tileIt & 1);
+        if (kProf) { eSt += clock64() - tE; tE = clock64(); }
+        D4 w3 = {0, 0, 0, 0};
+        int b = jb >> 4;                                      // block index relative to row r: block b -> row r + b / 4, cb b % 4
+        int k = 0;
+        for (; k + 1 < nbk; k += 2, b += 2) {
+          const double *o = B16 + (b & 3) * G.sumPitch + r + (b >> 2);
+          const double *o2 = B16 + ((b + 1) & 3) * G.sumPitch + r + ((b + 1) >> 2);
+          win.t1 += o[0]; win.t2 += o[4 * G.sumPitch]; win.s1 += o[8 * G.sumPitch]; win.s2 += o[12 * G.sumPitch];
+          w3.t1 += o2[0]; w3.t2 += o2[4 * G.sumPitch]; w3.s1 += o2[8 * G.sumPitch]; w3.s2 += o2[12 * G.sumPitch];
+        }
+        if (k < nbk) {
+          const double *o = B16 + (b & 3) * G.sumPitch + r + (b >> 2);
+          win.t1 += o[0]; win.t2 += o[4 * G.sumPitch]; win.s1 += o[8 * G.sumPitch]; win.s2 += o[12 * G.sumPitch];
+        }
+        // the sums are in registers: the producer may fetch the next tile's block sums
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sumsFree);
+        win.t1 = (win.t1 + w3.t1) + sgn * w2.t1; win.t2 = (win.t2 + w3.t2) + sgn * w2.t2;
+        win.s1 = (win.s1 + w3.s1) + sgn * w2.s1; win.s2 = (win.s2 + w3.s2) + sgn * w2.s2;
+      }
+      if (kProf) { eInit += clock64() - tE; tE = clock64(); }
+
+      // ---- accumulators -> registers ----
+      tc_wait(accFull, tileIt & 1);
+      if (kProf) { eAcc += clock64() - tE; tE = clock64(); }
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      const uint32_t laneAddr = tmem + ((uint32_t)(quarter * 32) << 16) + 16u * (uint32_t)jg;
+      float accT[16], accS[16];
+      {
+        uint32_t u[16], w[16];
+        tc_ld16_nowait(laneAddr + 0 * 64, u);
+        tc_ld16_nowait(laneAddr + 1 * 64, w);
+        tc_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; i++) accT[i] = fmaf(__uint_as_float(w[i]), 1.0f / kTcLoScale, __uint_as_float(u[i]));
+        tc_ld16_nowait(laneAddr + 2 * 64, u);
+        tc_ld16_nowait(laneAddr + 3 * 64, w);
+        tc_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; i++) accS[i] = fmaf(__uint_as_float(u[i]), 1.0f / kTcLoScale, __uint_as_float(w[i]));
+        const int nMain = min(p.numCh - 1, kT2Mains);
+        for (int m = 1; m < nMain; m += 2) {
+          tc_ld16_nowait(laneAddr + (uint32_t)(3 + m) * 64, u);
+          if (m + 1 < nMain) tc_ld16_nowait(laneAddr + (uint32_t)(4 + m) * 64, w);
+          tc_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; i++) accS[i] += __uint_as_float(u[i]) + (m + 1 < nMain ? __uint_as_float(w[i]) : 0.f);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(accEmpty);
+      if (kProf) { eLd += clock64() - tE; tE = clock64(); }
+
+      // ---- 16 offsets: evaluate, slide the window by one frame ----
+      unsigned long long best = 0ull;
+      const bool plain = g0 + 16 <= fStart + ((fEnd - fStart) - p.tailExtra - W + 1) && g0 + 16 <= p.usedFrames;
+      const uint32_t tl0 = (uint32_t)(g0 - fStart);
+      const int64_t oOld = t0 + ((int64_t)jb << 7) + r;        // frame 64 r + jb + e sits at + 128 e
+#pragma unroll
+      for (int blk = 0; blk < 4; blk++) {
+        // the frames that leave / enter the window during these four slides
+        float ob[4], os1[4], os2[4], nb0[4], ns1[4], ns2[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int jj = 4 * blk + e;
+          if (jj < 15) {
+            ob[e] = __ldg(p.sb0 + oOld + (jj << 7)); os1[e] = __ldg(p.sb1 + oOld + (jj << 7)); os2[e] = __ldg(p.sb2 + oOld + (jj << 7));
+            const int w = jb + jj + W, rr = r + (w >> 6);
+            const int64_t o = (tile + (rr >> 7)) * (int64_t)kT2Tile + ((int64_t)(w & 63) << 7) + (rr & 127);
+            nb0[e] = __ldg(p.sb0 + o); ns1[e] = __ldg(p.sb1 + o); ns2[e] = __ldg(p.sb2 + o);
+          }
+        }
+        float simv[4], boostv[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int jj = 4 * blk + e;           // offset inside the thread's run; accumulator column 15 - jj of its group
+          t2_eval(E, win, accT[15 - jj], accS[15 - jj], simv[e], boostv[e]);
+          if (jj < 15) {
+            const double bo = (double)ob[e], bn = (double)nb0[e];
+            win.t1 += bn - bo;
+            win.t2 += bn * bn - bo * bo;
+            win.s1 += (double)ns1[e] - (double)os1[e];
+            win.s2 += (double)ns2[e] - (double)os2[e];
+          }
+        }
+        if (plain) {
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            if (simv[e] == simv[e]) {
+              const unsigned long long key = ((unsigned long long)float_order_key(simv[e]) << 32) |
+                                             (unsigned long long)(0xffffffffu - (tl0 + (uint32_t)(4 * blk + e)));
+              if (key > best) best = key;
+            }
+          }
+        } else {
+          for (int e = 0; e < 4; e++) {
+            const int64_t g = g0 + 4 * blk + e;
+            while (g >= fEnd && f + 1 < p.numFiles) {
+              if (best != 0ull && p.fileMax) atomicMax(p.fileMax + f, best);
+              best = 0ull;
+              f++;
+              fStart = fEnd;
+              fEnd = p.fileStart[f + 1];
+            }
+            const int64_t tl = g - fStart;
+            float sv = qnan, bv = qnan;
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) if (kk == e) { sv = simv[kk]; bv = boostv[kk]; }
+            if (!(g < p.usedFrames && tl < (fEnd - fStart) - p.tailExtra - W + 1)) { sv = qnan; bv = qnan; }
+            else if (sv == sv) {
+              const unsigned long long key = ((unsigned long long)float_order_key(sv) << 32) |
+                                             (unsigned long long)(0xffffffffu - (uint32_t)tl);
+              if (key > best) best = key;
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) if (kk == e) { simv[kk] = sv; boostv[kk] = bv; }
+          }
+        }
+        *reinterpret_cast<float4 *>(p.sim + g0 + 4 * blk) = make_float4(simv[0], simv[1], simv[2], simv[3]);
+        *reinterpret_cast<float4 *>(p.boost + g0 + 4 * blk) = make_float4(boostv[0], boostv[1], boostv[2], boostv[3]);
+      }
+      if (best != 0ull && p.fileMax) atomicMax(p.fileMax + f, best);
+      if (kProf) eMain += clock64() - tE;
+    }
+    if (kProf && p.prof && ew == 0 && lane == 0) {
+      long long *o = p.prof + 24 * blockIdx.x + 8;
+      o[0] = eSt; o[1] = eInit; o[2] = eAcc; o[3] = eLd; o[4] = eMain;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+}  // namespace sgz

@@ -43,6 +43,13 @@ struct sgz_db {
   std::vector<Chunk> chunks;
   int64_t chunkMark = 0;
 
+  // tensor-core K1 (corr_tc2.cuh): pre-swizzled FP16 planes [numCh * 2][planeStrideBytes] and the tile-transposed
+  // per-frame sums, built from the pair rows on demand (frames below planesUpto are done; a patch resets it)
+  DevBuf<unsigned char> dPlanes;
+  DevBuf<float> dSide0, dSide1, dSide2;
+  DevBuf<double> dB16;                  // [16][planeRows] FP64 sums of aligned 16-frame blocks
+  int64_t planeStrideBytes = 0, planesUpto = 0, planeRows = 0;
+
   int numFiles() const { return (int)fileStart.size() - 1; }
 };
 
