@@ -82,6 +82,8 @@ inline bool tc_applicable(const sgz_ctx *ctx, int numCh, int W) {
 // the N = 64 kernel takes any channel count (the spectral channels share five accumulators) and every window whose
 // operand / taps rings fit shared memory (W <~ 900 frames with the minimum of two stages each)
 inline bool t2_applicable(const sgz_ctx *ctx, int numCh, int W) {
+  // (32-bit element indices into the per-frame arrays: databases beyond 2^32 - 2^16 frames = 13 000 h per GPU are refused
+  // by db_ensure_planes)
   return numCh >= 2 && W >= 1 && W <= 4096 && t2_geom(W, ctx->smemOptin).smemBytes <= ctx->smemOptin;
 }
 
@@ -89,12 +91,13 @@ inline bool t2_applicable(const sgz_ctx *ctx, int numCh, int W) {
 // a tile may touch (the zero slack behind the last file included)
 inline int db_ensure_planes(sgz_db *db, int64_t upto, cudaStream_t st) {
   const int64_t strideFrames = (db->capFrames + kT2Tile - 1) / kT2Tile * kT2Tile;
+  SGZ_REQUIRE(strideFrames < ((int64_t)1 << 32) - 65536, "database of %lld frames exceeds the 32-bit frame index of the tensor-core scan",
+              (long long)db->usedFrames);
   if (!db->dPlanes.p || db->planeStrideBytes != strideFrames * 2) {
     db->planeStrideBytes = strideFrames * 2;
     SGZ_TRY(db->dPlanes.alloc((size_t)db->numCh * 2 * (size_t)db->planeStrideBytes));
-    SGZ_TRY(db->dSide0.alloc((size_t)strideFrames));
-    SGZ_TRY(db->dSide1.alloc((size_t)strideFrames));
-    SGZ_TRY(db->dSide2.alloc((size_t)strideFrames));
+    SGZ_TRY(db->dSideA.alloc((size_t)strideFrames));
+    SGZ_TRY(db->dSideB.alloc((size_t)strideFrames));
     db->planeRows = strideFrames / kT2P;
     SGZ_TRY(db->dB16.alloc((size_t)16 * db->planeRows));
     db->planesUpto = 0;
@@ -104,8 +107,8 @@ inline int db_ensure_planes(sgz_db *db, int64_t upto, cudaStream_t st) {
   if (end <= db->planesUpto) return SGZ_OK;
   const unsigned blocks = (unsigned)((end - db->planesUpto) / kPlaneFrames);
   k_db_planes<<<blocks, 256, 0, st>>>(db->dData.p, db->capFrames, db->numCh, db->numPairs, db->planesUpto,
-                                      std::min(end, db->capFrames), db->dPlanes.p, db->planeStrideBytes, db->dSide0.p,
-                                      db->dSide1.p, db->dSide2.p, db->dB16.p, db->planeRows);
+                                      std::min(end, db->capFrames), db->dPlanes.p, db->planeStrideBytes, db->dSideA.p,
+                                      db->dSideB.p, db->dB16.p, db->planeRows);
   SGZ_LAUNCH_CHECK(db->ctx);
   db->planesUpto = end;
   return SGZ_OK;
@@ -312,16 +315,28 @@ inline int run_scan_t2(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim, 
   const T2Geom G = t2_geom(q.W, ctx->smemOptin);
   CorrT2Params tp{};
   tp.planes = db->dPlanes.p; tp.planeStrideBytes = db->planeStrideBytes;
-  tp.sb0 = db->dSide0.p; tp.sb1 = db->dSide1.p; tp.sb2 = db->dSide2.p;
+  tp.sideA = db->dSideA.p; tp.sideB = db->dSideB.p;
   tp.b16 = db->dB16.p; tp.rowsTotal = db->planeRows;
   tp.usedFrames = db->usedFrames; tp.numCh = db->numCh; tp.W = q.W;
   tp.taps = q.dT2Taps.p;
-  tp.stdT = q.stdT; tp.stdS = q.stdS; tp.rhoT = q.rhoT; tp.rhoS = q.rhoS; tp.lnAvgIn = q.lnAvg;
-  tp.weight = q.weight; tp.maxBoost = job->cfg.maxBoost;
+  {
+    T2Eval &E = tp.ev;
+    E.invW = 1.0 / (double)q.W; E.invNS = 1.0 / ((double)(db->numCh - 1) * (double)q.W);
+    E.negEps = -1e-13;
+    E.cT = (float)(E.invW / q.stdT); E.cS = (float)(E.invNS / q.stdS);
+    E.kT = (float)q.rhoT * E.cT; E.kS = (float)q.rhoS * E.cS;
+    E.l2In = (float)(q.lnAvg * 1.4426950408889634);
+    E.wT = q.weight; E.wS = 1.0f - q.weight; E.maxBoost = job->cfg.maxBoost;
+    E.useT = q.weight > 0.f; E.useS = q.weight < 1.f;
+  }
   tp.fileStart = db->dFileStart.p; tp.tileFile = job->dTileFileT2.p; tp.numFiles = db->numFiles(); tp.tailExtra = tailExtra;
   tp.tileBegin = tileBegin; tp.tileEnd = tileEnd;
   tp.sim = sim; tp.boost = boost; tp.fileMax = fileMax;
   tp.smemMax = (int)ctx->smemOptin;
+  {
+    static const int ahead = getenv("SGZ_T2_AHEAD") ? atoi(getenv("SGZ_T2_AHEAD")) : kT2Ahead;   // developer knob
+    tp.ahead = ahead;
+  }
   const bool prof = getenv("SGZ_CORR_TC_PROF") != nullptr;   // developer probe: cycles per role and phase
   auto kern = prof ? k_corr_tc2<true> : k_corr_tc2<false>;
   SGZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));

@@ -27,6 +27,7 @@ namespace sgz {
 
 constexpr int kT2P = 64, kT2M = 128, kT2Tile = kT2P * kT2M;
 constexpr int kT2Mains = 5;               // spectral main accumulators
+constexpr int kT2Ahead = 7;               // channels between the L2 prefetch of a signal stage and its bulk copy
 constexpr int kT2EpiWarps = 16, kT2Threads = (4 + kT2EpiWarps) * 32;
 
 struct T2Geom {
@@ -74,6 +75,12 @@ __host__ __device__ inline int64_t t2_side_index(int64_t g) {
   return (g & ~(int64_t)(kT2Tile - 1)) + ((g & 63) << 7) + ((g >> 6) & 127);
 }
 
+// per-frame statistics are kept as the high word of their Double, rounded to nearest (the carry may run into the exponent)
+__device__ __forceinline__ uint32_t t2_dhi(float x) {
+  return (uint32_t)(((unsigned long long)__double_as_longlong((double)x) + 0x80000000ull) >> 32);
+}
+__device__ __forceinline__ double t2_dbl(uint32_t hi) { return __hiloint2double((int)hi, 0); }
+
 // taps image of a taps stage: per channel [first-part atoms][second-part atoms], atom a = 8 rows (cc) x 16 k (kk) halves
 // holding q~[8 a + kk + cc - 63], SWIZZLE_32B chunk flip on rows 4..7.  Built on the device from the float taps (one block
 // per channel): the float taps are a few KB and reach the device as an inline copy even while database uploads occupy
@@ -102,15 +109,19 @@ __global__ void k_t2_taps(const float2 *__restrict__ pairTaps, int numCh, int Wq
 // K0b: FP16 planes + per-frame sums of a frame range of the database (once per database / upload chunk)
 // ---------------------------------------------------------------------------------------------
 // planes[(2 c + part)][planeStrideBytes]: part 0 = fp16(x), part 1 = fp16((x - part0) * 2^11), pre-swizzled (t2_plane_byte);
-// side arrays (tile transposed, t2_side_index): b0 = loudness, s1 = sum over spectral channels, s2 = sum of their squares
-// (the FP32 arithmetic of the round-1 split warps: s1 += x + y, s2 = fma(x, x, fma(y, y, s2)) pair by pair);
-// b16[(4 q + cb)][rowsTotal]: FP64 sums of (b0, b0^2, s1, s2)[q] over the aligned 16-frame block cb of each 64-frame row.
+// side arrays (tile transposed, t2_side_index): per frame b0 = loudness, s1 = sum over the spectral channels, s2 = sum of
+// their squares (FP32: s1 += x + y, s2 = fma(x, x, fma(y, y, s2)) pair by pair), each stored as the HIGH WORD of its
+// Double rounded to 20 mantissa bits -- the window statistics run in FP64, and the kernel gets its Double operand for free
+// (no Float -> Double conversion: 16 lanes per clock per SM, six per slide).  The rounding (2^-21 relative, unbiased) moves
+// a window variance by < 2e-7 relative; sideA = (b0, s1), sideB = s2;
+// b16[(4 q + cb)][rowsTotal]: FP64 sums of (b0, b0^2, s1, s2)[q] of the SAME rounded values over the aligned 16-frame
+// block cb of each 64-frame row.
 constexpr int kPlaneFrames = 2048;     // frames per block (256 threads x 8 frames)
 __global__ void __launch_bounds__(256) k_db_planes(const float2 *__restrict__ data, int64_t rowStride, int numCh, int numPairs,
                                                    int64_t frameBegin, int64_t frameEnd, unsigned char *__restrict__ planes,
-                                                   int64_t planeStrideBytes, float *__restrict__ sb0, float *__restrict__ sb1,
-                                                   float *__restrict__ sb2, double *__restrict__ b16, int64_t rowsTotal) {
-  __shared__ float sh[3][kPlaneFrames + 32];    // +1 per 64 frames against bank conflicts of the transposed read-out
+                                                   int64_t planeStrideBytes, uint2 *__restrict__ sideA,
+                                                   uint32_t *__restrict__ sideB, double *__restrict__ b16, int64_t rowsTotal) {
+  __shared__ uint32_t sh[3][kPlaneFrames + 32];    // +1 per 64 frames against bank conflicts of the transposed read-out
   const int64_t f0 = frameBegin + (int64_t)blockIdx.x * kPlaneFrames;   // frameBegin is a multiple of 2048
   const int64_t g0 = f0 + 8 * (int64_t)threadIdx.x;
   float b0[8], s1[8], s2[8];
@@ -151,7 +162,7 @@ __global__ void __launch_bounds__(256) k_db_planes(const float2 *__restrict__ da
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     const int L = 8 * threadIdx.x + k, i = L + (L >> 6);
-    sh[0][i] = b0[k]; sh[1][i] = s1[k]; sh[2][i] = s2[k];
+    sh[0][i] = t2_dhi(b0[k]); sh[1][i] = t2_dhi(s1[k]); sh[2][i] = t2_dhi(s2[k]);
   }
   __syncthreads();
   // transposed write-out: the block's 2048 frames are 32 rows x 64 columns of one tile; a warp writes 32 consecutive rows
@@ -161,7 +172,7 @@ __global__ void __launch_bounds__(256) k_db_planes(const float2 *__restrict__ da
   for (int col = warp; col < 64; col += 8) {
     const int L = 64 * lane + col, i = L + (L >> 6);
     const int64_t o = base + ((int64_t)col << 7) + lane;
-    sb0[o] = sh[0][i]; sb1[o] = sh[1][i]; sb2[o] = sh[2][i];
+    sideA[o] = make_uint2(sh[0][i], sh[1][i]); sideB[o] = sh[2][i];
   }
   // FP64 sums of the 128 aligned 16-frame blocks: warp cb takes column block cb of the 32 rows, lane = row
   if (warp < 4) {
@@ -169,10 +180,10 @@ __global__ void __launch_bounds__(256) k_db_planes(const float2 *__restrict__ da
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
 #pragma unroll
     for (int e = 0; e < 16; e += 2) {
-      const double x = (double)sh[0][i0 + e], x2 = (double)sh[0][i0 + e + 1];
+      const double x = t2_dbl(sh[0][i0 + e]), x2 = t2_dbl(sh[0][i0 + e + 1]);
       a0 += x; a1 += x * x; c0 += x2; c1 += x2 * x2;
-      a2 += (double)sh[1][i0 + e]; c2 += (double)sh[1][i0 + e + 1];
-      a3 += (double)sh[2][i0 + e]; c3 += (double)sh[2][i0 + e + 1];
+      a2 += t2_dbl(sh[1][i0 + e]); c2 += t2_dbl(sh[1][i0 + e + 1]);
+      a3 += t2_dbl(sh[2][i0 + e]); c3 += t2_dbl(sh[2][i0 + e + 1]);
     }
     double *dst = b16 + (int64_t)warp * rowsTotal + (f0 >> 6) + lane;
     dst[0] = a0 + c0; dst[4 * rowsTotal] = a1 + c1; dst[8 * rowsTotal] = a2 + c2; dst[12 * rowsTotal] = a3 + c3;
@@ -182,17 +193,32 @@ __global__ void __launch_bounds__(256) k_db_planes(const float2 *__restrict__ da
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float t2_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float t2_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float t2_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// constants of one evaluated offset, prepared on the host (kernel parameters = constant bank operands)
+struct T2Eval {
+  double invW, invNS;       // 1 / W, 1 / ((numCh - 1) W)
+  double negEps;            // -1e-13: a window whose variance is below 1e-13 of its mean square counts as constant (-> NaN)
+  float cT, cS;             // 1 / (W std_a) per group, (numCh - 1) folded into cS
+  float kT, kS;             // rho * c: correction for the rounded taps not summing to exactly zero
+  float l2In;               // log2 of the query's average loudness
+  float wT, wS, maxBoost;
+  int useT, useS;
+};
+
 struct CorrT2Params {
   const unsigned char *planes;  // [numCh * 2][planeStrideBytes]
   int64_t planeStrideBytes;
-  const float *sb0, *sb1, *sb2; // tile-transposed per-frame loudness / spectral sum / spectral sum of squares
+  const uint2 *sideA;           // tile-transposed per-frame (loudness, spectral sum) as Double high words
+  const uint32_t *sideB;        // ... spectral sum of squares
   const double *b16;            // [16][rowsTotal] FP64 sums of aligned 16-frame blocks
   int64_t rowsTotal;
   int64_t usedFrames;
   int numCh, W;
   const unsigned char *taps;    // k_t2_taps image
-  double stdT, stdS, rhoT, rhoS, lnAvgIn;
-  float weight, maxBoost;
+  T2Eval ev;
   const int64_t *fileStart;
   const int32_t *tileFile;      // [numTiles + 1] file that holds frame 8192 * tile (clamped to the last file)
   int numFiles, tailExtra;
@@ -201,8 +227,14 @@ struct CorrT2Params {
   unsigned long long *fileMax;
   long long *prof;              // SGZ_CORR_TC_PROF: per CTA 24 cycle counters (k_corr_tc2<true>), or nullptr
   int smemMax;                  // the geometry (ring depths) is a function of (W, shared memory limit)
+  int ahead;                    // channels between the L2 prefetch of a signal stage and its bulk copy (0: no prefetch)
 };
 
+// pull a range into L2 without a destination: the ring in shared memory then waits for L2, not for HBM, so the HBM latency
+// is covered by bytes in flight that need no shared memory
+__device__ __forceinline__ void t2_prefetch_l2(const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ bool t2_test(uint64_t *bar, uint32_t parity) {   // non-blocking phase test
   uint32_t done;
   asm volatile(
@@ -213,31 +245,26 @@ __device__ __forceinline__ bool t2_test(uint64_t *bar, uint32_t parity) {   // n
   return done != 0;
 }
 
-// one evaluated offset: window sums -> boost and sim (FeatureCorrelationImpl.scala:73-78,198-210)
-struct T2Eval {
-  double invW, invNS;
-  float cT, cS, kT, kS, l2In, wT, wS, maxBoost;
-  bool useT, useS;
-};
+// one evaluated offset: window sums -> boost and sim (FeatureCorrelationImpl.scala:73-78,198-210); branch free so that the
+// compiler can interleave the offsets of a thread
 __device__ __forceinline__ void t2_eval(const T2Eval &E, const D4 &win, float accT, float accS, float &sim, float &boost) {
   const float qnan = __int_as_float(0x7fc00000);
   const double mT = win.t1 * E.invW;
-  const float avgB = (float)mT;                                            // MathUtil.avg -> Float
-  boost = exp2f((E.l2In - __log2f(avgB)) * (1.0f / 0.6f));                 // calcBoost
-  float temporal = 0.f, spectral = 0.f;
-  if (E.useT) {
-    const double q = win.t2 * E.invW;
-    const double var = q - mT * mT;
-    const float cr = fmaf(accT, E.cT, -(float)mT * E.kT);                  // (acc - mean_b * rho) / (W std_a)
-    temporal = (var > 1e-13 * q) ? cr * rsqrtf((float)var) : qnan;
-  }
-  if (E.useS) {
-    const double mS = win.s1 * E.invNS;
-    const double q = win.s2 * E.invNS;
-    const double var = q - mS * mS;
-    const float cr = fmaf(accS, E.cS, -(float)mS * E.kS);
-    spectral = (var > 1e-13 * q) ? cr * rsqrtf((float)var) : qnan;
-  }
+  const float mTf = (float)mT;                                             // MathUtil.avg -> Float
+  boost = t2_ex2((E.l2In - t2_lg2(mTf)) * (1.0f / 0.6f));                  // calcBoost
+  const double qT = win.t2 * E.invW;
+  const double varT = fma(-mT, mT, qT);
+  const float crT = fmaf(accT, E.cT, -mTf * E.kT);                         // (acc - mean_b * rho) / (W std_a)
+  float temporal = crT * t2_rsqrt((float)varT);
+  temporal = __double2hiint(fma(qT, E.negEps, varT)) > 0 ? temporal : qnan;   // var > 1e-13 q (positive and not NaN)
+  temporal = E.useT ? temporal : 0.f;
+  const double mS = win.s1 * E.invNS;
+  const double qS = win.s2 * E.invNS;
+  const double varS = fma(-mS, mS, qS);
+  const float crS = fmaf(accS, E.cS, -(float)mS * E.kS);
+  float spectral = crS * t2_rsqrt((float)varS);
+  spectral = __double2hiint(fma(qS, E.negEps, varS)) > 0 ? spectral : qnan;
+  spectral = E.useS ? spectral : 0.f;
   const float blend = __fadd_rn(__fmul_rn(temporal, E.wT), __fmul_rn(spectral, E.wS));
   sim = boost <= E.maxBoost ? blend : 0.f;
 }
@@ -295,6 +322,18 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
             sumsPending = false;
           }
           if (c == p.numCh) break;
+          if (p.ahead > 0) {   // planes of the channel `ahead` steps ahead -> L2
+            const int ca = c + p.ahead;
+            const int64_t ta = tile + (int64_t)gridDim.x * (ca / p.numCh);
+            if (ta < p.tileEnd) {
+              const unsigned char *pa = p.planes + ta * (int64_t)(kT2Tile * 2) + (int64_t)(2 * (ca % p.numCh)) * p.planeStrideBytes;
+              t2_prefetch_l2(pa, G.planeBytes);
+              t2_prefetch_l2(pa + p.planeStrideBytes, G.planeBytes);
+            }
+            if (c == 0 && tile + gridDim.x < p.tileEnd)          // and the block sums of the next tile
+              for (int k = 0; k < 16; k++)
+                t2_prefetch_l2(p.b16 + (int64_t)k * p.rowsTotal + (tile + gridDim.x) * kT2M, (uint32_t)G.sumPitch * 8u);
+          }
           const uint32_t s = it % (uint32_t)G.sigStages, u = it / (uint32_t)G.sigStages;
           if (u > 0) tc_wait(sigFree + s, (u - 1) & 1);
           mbar_expect_tx(sigFull + s, 2 * G.planeBytes);
@@ -366,13 +405,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
     const int ew = warp - 4, quarter = warp & 3, jg = ew >> 2, et = ew * 32 + lane;
     const int jb = 16 * (3 - jg);
     const int W = p.W;
-    T2Eval E;
-    E.invW = 1.0 / (double)W; E.invNS = 1.0 / ((double)(p.numCh - 1) * (double)W);
-    E.cT = (float)(E.invW / p.stdT); E.cS = (float)(E.invNS / p.stdS);
-    E.kT = (float)p.rhoT * E.cT; E.kS = (float)p.rhoS * E.cS;
-    E.l2In = (float)(p.lnAvgIn * 1.4426950408889634);
-    E.wT = p.weight; E.wS = __fsub_rn(1.0f, p.weight); E.maxBoost = p.maxBoost;
-    E.useT = p.weight > 0.f; E.useS = p.weight < 1.f;
+    const T2Eval &E = p.ev;
     const float qnan = __int_as_float(0x7fc00000);
     const int r = quarter * 32 + lane;
     // window of the thread's first offset = nbk aligned 16-frame blocks, plus (sgn > 0) or minus (sgn < 0) nsg single frames
@@ -387,9 +420,10 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
       {   // pull the per-frame arrays of the NEXT tile into L2: this tile's slides then wait for L2, not for HBM
         const int64_t nt = tile + gridDim.x;
         if (nt < p.tileEnd) {
-          for (int l = et; l < 3 * 256; l += kT2EpiWarps * 32) {
-            const float *a = l < 256 ? p.sb0 : (l < 512 ? p.sb1 : p.sb2);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a + nt * kT2Tile + (int64_t)(l & 255) * 32));
+          for (int l = et; l < 3 * 256; l += kT2EpiWarps * 32) {     // 512 lines of sideA, 256 of sideB
+            const void *a = l < 512 ? (const void *)(p.sideA + nt * kT2Tile + (int64_t)l * 16)
+                                    : (const void *)(p.sideB + nt * kT2Tile + (int64_t)(l - 512) * 32);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
           }
         }
       }
@@ -413,8 +447,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
         for (int e = 0; e < nsg; e++) {
           const int w = jb + sg0 + e, rr = r + (w >> 6);
           const int64_t o = (tile + (rr >> 7)) * (int64_t)kT2Tile + ((int64_t)(w & 63) << 7) + (rr & 127);
-          const double x = (double)__ldg(p.sb0 + o);
-          w2.t1 += x; w2.t2 += x * x; w2.s1 += (double)__ldg(p.sb1 + o); w2.s2 += (double)__ldg(p.sb2 + o);
+          const uint2 a = __ldg(p.sideA + o);
+          const double x = t2_dbl(a.x);
+          w2.t1 += x; w2.t2 += x * x; w2.s1 += t2_dbl(a.y); w2.s2 += t2_dbl(__ldg(p.sideB + o));
         }
         tc_wait(sumsFull, tileIt & 1);
         if (kProf) { eSt += clock64() - tE; tE = clock64(); }
@@ -475,19 +510,27 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
       unsigned long long best = 0ull;
       const bool plain = g0 + 16 <= fStart + ((fEnd - fStart) - p.tailExtra - W + 1) && g0 + 16 <= p.usedFrames;
       const uint32_t tl0 = (uint32_t)(g0 - fStart);
-      const int64_t oOld = t0 + ((int64_t)jb << 7) + r;        // frame 64 r + jb + e sits at + 128 e
+      float bestS = -INFINITY;                                 // plain runs: largest sim and its first position
+      int bestJ = -1;
+      // leaving frames 64 r + jb + e sit at + 128 e from the first one; entering frames 64 r + jb + W + e likewise until
+      // the column wraps into the next row (once in 16 frames at most), which may be the first row of the next tile
+      const uint32_t oOld = (uint32_t)(t0 + (jb << 7) + r);    // element indices fit 32 bits (sgz_corr_scan checks)
+      const int wN = jb + W, colN = wN & 63, rowN = r + (wN >> 6);
+      const uint32_t oNew = (uint32_t)((tile + (rowN >> 7)) * (int64_t)kT2Tile + (colN << 7) + (rowN & 127));
+      const int eWrap = 64 - colN;
+      const uint32_t dWrap = (uint32_t)(((rowN & 127) == 127 ? kT2Tile - 127 : 1) - (64 << 7));
 #pragma unroll
       for (int blk = 0; blk < 4; blk++) {
         // the frames that leave / enter the window during these four slides
-        float ob[4], os1[4], os2[4], nb0[4], ns1[4], ns2[4];
+        uint2 oa[4], na[4];
+        uint32_t ob2[4], nb2[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const int jj = 4 * blk + e;
           if (jj < 15) {
-            ob[e] = __ldg(p.sb0 + oOld + (jj << 7)); os1[e] = __ldg(p.sb1 + oOld + (jj << 7)); os2[e] = __ldg(p.sb2 + oOld + (jj << 7));
-            const int w = jb + jj + W, rr = r + (w >> 6);
-            const int64_t o = (tile + (rr >> 7)) * (int64_t)kT2Tile + ((int64_t)(w & 63) << 7) + (rr & 127);
-            nb0[e] = __ldg(p.sb0 + o); ns1[e] = __ldg(p.sb1 + o); ns2[e] = __ldg(p.sb2 + o);
+            oa[e] = __ldg(p.sideA + (oOld + (uint32_t)(jj << 7))); ob2[e] = __ldg(p.sideB + (oOld + (uint32_t)(jj << 7)));
+            const uint32_t d = oNew + (uint32_t)(jj << 7) + (jj >= eWrap ? dWrap : 0u);
+            na[e] = __ldg(p.sideA + d); nb2[e] = __ldg(p.sideB + d);
           }
         }
         float simv[4], boostv[4];
@@ -496,22 +539,17 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
           const int jj = 4 * blk + e;           // offset inside the thread's run; accumulator column 15 - jj of its group
           t2_eval(E, win, accT[15 - jj], accS[15 - jj], simv[e], boostv[e]);
           if (jj < 15) {
-            const double bo = (double)ob[e], bn = (double)nb0[e];
+            const double bo = t2_dbl(oa[e].x), bn = t2_dbl(na[e].x);
             win.t1 += bn - bo;
-            win.t2 += bn * bn - bo * bo;
-            win.s1 += (double)ns1[e] - (double)os1[e];
-            win.s2 += (double)ns2[e] - (double)os2[e];
+            win.t2 += fma(bn, bn, -(bo * bo));
+            win.s1 += t2_dbl(na[e].y) - t2_dbl(oa[e].y);
+            win.s2 += t2_dbl(nb2[e]) - t2_dbl(ob2[e]);
           }
         }
         if (plain) {
 #pragma unroll
-          for (int e = 0; e < 4; e++) {
-            if (simv[e] == simv[e]) {
-              const unsigned long long key = ((unsigned long long)float_order_key(simv[e]) << 32) |
-                                             (unsigned long long)(0xffffffffu - (tl0 + (uint32_t)(4 * blk + e)));
-              if (key > best) best = key;
-            }
-          }
+          for (int e = 0; e < 4; e++)
+            if (simv[e] > bestS) { bestS = simv[e]; bestJ = 4 * blk + e; }      // NaN never wins, ties keep the first
         } else {
           for (int e = 0; e < 4; e++) {
             const int64_t g = g0 + 4 * blk + e;
@@ -539,6 +577,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
         *reinterpret_cast<float4 *>(p.sim + g0 + 4 * blk) = make_float4(simv[0], simv[1], simv[2], simv[3]);
         *reinterpret_cast<float4 *>(p.boost + g0 + 4 * blk) = make_float4(boostv[0], boostv[1], boostv[2], boostv[3]);
       }
+      if (bestJ >= 0)
+        best = ((unsigned long long)float_order_key(bestS) << 32) | (unsigned long long)(0xffffffffu - (tl0 + (uint32_t)bestJ));
       if (best != 0ull && p.fileMax) atomicMax(p.fileMax + f, best);
       if (kProf) eMain += clock64() - tE;
     }

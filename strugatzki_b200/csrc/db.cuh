@@ -46,7 +46,8 @@ struct sgz_db {
   // tensor-core K1 (corr_tc2.cuh): pre-swizzled FP16 planes [numCh * 2][planeStrideBytes] and the tile-transposed
   // per-frame sums, built from the pair rows on demand (frames below planesUpto are done; a patch resets it)
   DevBuf<unsigned char> dPlanes;
-  DevBuf<float> dSide0, dSide1, dSide2;
+  DevBuf<uint2> dSideA;                 // per frame (loudness, spectral sum) as Double high words, tile transposed
+  DevBuf<uint32_t> dSideB;              // per frame spectral sum of squares
   DevBuf<double> dB16;                  // [16][planeRows] FP64 sums of aligned 16-frame blocks
   int64_t planeStrideBytes = 0, planesUpto = 0, planeRows = 0;
 

@@ -44,6 +44,17 @@ for r in data:
         v = int(r[ix[s]])
         if v:
             by[cur][1][s] += v
+if os.environ.get("NCU_LINES_RANGE"):   # stall histogram of a line range of the source file: NCU_LINES_RANGE=474-545
+    lo, hi = map(int, os.environ["NCU_LINES_RANGE"].split("-"))
+    hist, n, ins = defaultdict(int), 0, 0
+    for k, v in by.items():
+        if k and k[0] == os.path.basename(srcfile) and lo <= k[1] <= hi:
+            n += v[0]
+            ins += v[2]
+            for a, b in v[1].items():
+                hist[a] += b
+    print(f"lines {lo}-{hi}: samples {n}, instructions {ins}")
+    print(sorted(hist.items(), key=lambda x: -x[1]))
 src = {}
 tot = sum(v[0] for v in by.values())
 print(f"total samples {tot}")
