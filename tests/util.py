@@ -58,7 +58,9 @@ def build_db(ctx, files, norm):
     return db
 
 
-def assert_sims_close(got, want, rel=1e-5, abs_tol=2e-6, what="sim"):
+def assert_sims_close(got, want, rel=1e-5, abs_tol=2e-6, what="sim") -> int:
+    """|got - want| <= max(rel * |want|, abs_tol) everywhere, identical NaN pattern.  Returns how many cells needed the
+    ABSOLUTE floor, i.e. missed the relative bound (sims close to zero: the contract's 1e-5 is relative)."""
     got = np.asarray(got, np.float64)
     want = np.asarray(want, np.float64)
     assert got.shape == want.shape, (got.shape, want.shape)
@@ -70,6 +72,7 @@ def assert_sims_close(got, want, rel=1e-5, abs_tol=2e-6, what="sim"):
     bad = err > tol
     assert not bad.any(), (f"{what}: {bad.sum()} of {ok.sum()} beyond tolerance; worst abs err "
                            f"{err.max():.3e}, worst rel {np.max(err / np.maximum(np.abs(want[ok]), 1e-30)):.3e}")
+    return int(np.count_nonzero(err > rel * np.abs(want[ok])))
 
 
 def assert_matches_equal(got: List[dict], want: List[dict], rel=1e-5):
