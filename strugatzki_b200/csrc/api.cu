@@ -585,6 +585,9 @@ int sgz_corr_scan(sgz_corr *job) {
                                ctx->scanStream));
       SGZ_CUDA(cudaStreamSynchronize(ctx->scanStream));
     }
+    SGZ_TRY(job->dFixCount.alloc(2));
+    SGZ_TRY(job->dFixList[0].alloc(kFixCap));
+    if (job->hasOut) SGZ_TRY(job->dFixList[1].alloc(kFixCap));
   }
   if (tc) {
     n = std::max(n, (size_t)job->numTilesTc * kTcTile);
@@ -622,6 +625,7 @@ int sgz_corr_scan(sgz_corr *job) {
     SGZ_CUDA(cudaMemsetAsync(job->dFileMax.p, 0, job->dFileMax.n * sizeof(unsigned long long), ss));
     if (job->hasOut)
       SGZ_CUDA(cudaMemsetAsync(job->dFileMaxOut.p, 0, job->dFileMaxOut.n * sizeof(unsigned long long), ss));
+    if (t2) SGZ_CUDA(cudaMemsetAsync(job->dFixCount.p, 0, 2 * sizeof(uint32_t), ss));
     int64_t done = 0;
     for (const auto &c : db->chunks) {
       if (db->usedFrames == 0) continue;
@@ -635,9 +639,9 @@ int sgz_corr_scan(sgz_corr *job) {
         if (end <= done && !last) continue;
         SGZ_CUDA(cudaStreamWaitEvent(ss, c.ev, 0));
         SGZ_TRY(db_ensure_planes(db, last ? -1 : c.uptoFrame, ss));
-        SGZ_TRY(run_scan_t2(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, done, end, ss, spare));
+        SGZ_TRY(run_scan_t2(job, job->qin, 0, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, done, end, ss, spare));
         if (job->hasOut)
-          SGZ_TRY(run_scan_t2(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, done, end, ss, spare));
+          SGZ_TRY(run_scan_t2(job, job->qout, 1, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, done, end, ss, spare));
         done = std::max(done, end);
         continue;
       }
@@ -652,6 +656,10 @@ int sgz_corr_scan(sgz_corr *job) {
       done = end;
     }
     SGZ_CUDA(cudaStreamWaitEvent(ss, db->chunks.back().ev, 0));   // file table for the row maxima / later kernels
+    if (t2 && db->usedFrames > 0) {
+      SGZ_TRY(run_fixup(job, job->qin, 0, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, ss));
+      if (job->hasOut) SGZ_TRY(run_fixup(job, job->qout, 1, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, ss));
+    }
     if (job->hasOut && db->usedFrames > 0) {
       SGZ_TRY(job->rowMaxOut.alloc((size_t)db->usedFrames));
       SGZ_CUDA(launch_row_max_out(ss, job->simOut.p, db->dFileStart.p, db->numFiles(), db->usedFrames, job->qin.W,
@@ -671,17 +679,22 @@ int sgz_corr_scan(sgz_corr *job) {
     SGZ_CUDA(cudaMemsetAsync(job->dFileMax.p, 0, job->dFileMax.n * sizeof(unsigned long long), ctx->stream));
     if (job->hasOut)
       SGZ_CUDA(cudaMemsetAsync(job->dFileMaxOut.p, 0, job->dFileMaxOut.n * sizeof(unsigned long long), ctx->stream));
+    if (t2) SGZ_CUDA(cudaMemsetAsync(job->dFixCount.p, 0, 2 * sizeof(uint32_t), ctx->stream));
     if (db->usedFrames > 0) {
-      if (t2) SGZ_TRY(run_scan_t2(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, 0, job->numTilesT2,
-                                  ctx->stream, 0));
-      else if (tc) SGZ_TRY(run_scan_tc(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, ctx->stream));
+      if (t2) {
+        SGZ_TRY(run_scan_t2(job, job->qin, 0, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, 0, job->numTilesT2,
+                            ctx->stream, 0));
+        SGZ_TRY(run_fixup(job, job->qin, 0, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, ctx->stream));
+      } else if (tc) SGZ_TRY(run_scan_tc(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, ctx->stream));
       else
         SGZ_TRY(run_scan_one(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, 0, job->numTiles,
                              ctx->stream, 0));
       if (job->hasOut) {
-        if (t2) SGZ_TRY(run_scan_t2(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, 0, job->numTilesT2,
-                                    ctx->stream, 0));
-        else if (tc) SGZ_TRY(run_scan_tc(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, ctx->stream));
+        if (t2) {
+          SGZ_TRY(run_scan_t2(job, job->qout, 1, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, 0, job->numTilesT2,
+                              ctx->stream, 0));
+          SGZ_TRY(run_fixup(job, job->qout, 1, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, ctx->stream));
+        } else if (tc) SGZ_TRY(run_scan_tc(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, ctx->stream));
         else
           SGZ_TRY(run_scan_one(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, 0, job->numTiles,
                                ctx->stream, 0));

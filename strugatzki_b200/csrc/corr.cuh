@@ -18,6 +18,8 @@ struct PunchQuery {
   std::vector<uint16_t> tcTaps;
   DevBuf<uint16_t> dTcTaps;    // tensor-core path: hi/lo Toeplitz atoms (corr_tc.cuh), empty when not applicable
   DevBuf<unsigned char> dT2Taps;   // N = 64 tensor-core path (corr_tc2.cuh), empty when not applicable
+  std::vector<double> ac;          // centred query [numCh][W] in Double: a[c][i] + (-group mean), MathUtil.correlate's factor
+  DevBuf<double> dAc;              // ... for the exact re-evaluation of ill-conditioned windows (corr_fix.cuh)
 };
 
 struct sgz_corr {
@@ -34,6 +36,7 @@ struct sgz_corr {
   int64_t numTilesTc = 0, numTilesT2 = 0;
   DevBuf<int32_t> dTileFile;   // [numTilesTc + 1] file holding the first frame of each tensor-core tile
   DevBuf<int32_t> dTileFileT2; // the same for the 8192-offset tiles of corr_tc2.cuh
+  DevBuf<uint32_t> dFixList[2], dFixCount;   // ill-conditioned offsets of the punch-in / punch-out scan (corr_fix.cuh)
   int64_t numTiles = 0;
   int64_t numOffsets = 0;
   DevBuf<float> simIn, boostIn, simOut, boostOut, rowMaxOut;
@@ -179,6 +182,11 @@ inline int prepare_query(const sgz_db *db, const float *inputPlanar /*[numCh][in
     SGZ_CUDA(cudaMemcpyAsync(q.dTcTaps.p, q.tcTaps.data(), q.tcTaps.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
   }
   if (t2_applicable(db->ctx, numCh, W)) {
+    q.ac.resize((size_t)numCh * W);
+    for (int c = 0; c < numCh; c++)
+      for (int i = 0; i < W; i++) q.ac[(size_t)c * W + i] = (double)a[(size_t)c * W + i] + (-(c == 0 ? meanT : meanS));
+    SGZ_TRY(q.dAc.alloc(q.ac.size()));
+    SGZ_CUDA(cudaMemcpyAsync(q.dAc.p, q.ac.data(), q.ac.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     const T2Geom g = t2_geom(W, db->ctx->smemOptin);
     SGZ_TRY(q.dT2Taps.alloc((size_t)numCh * g.tapsBytes));
     k_t2_taps<<<numCh, 256, 0, st>>>(reinterpret_cast<const float2 *>(q.dTaps.p), numCh, q.Wq, W, q.dT2Taps.p);
@@ -307,8 +315,27 @@ inline int run_scan_tc(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim, 
 
 // N = 64 tensor-core K1 over tiles [tileBegin, tileEnd) of 8192 offsets (corr_tc2.cuh); the planes of every frame the
 // tiles touch must have been enqueued on `st` (db_ensure_planes)
-inline int run_scan_t2(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim, float *boost, unsigned long long *fileMax,
-                       int64_t tileBegin, int64_t tileEnd, cudaStream_t st, int spareSMs) {
+constexpr uint32_t kFixCap = 1u << 20;
+
+// exact Double replay of the offsets the tensor-core scan flagged as ill-conditioned (corr_fix.cuh); `which` = 0 punch-in,
+// 1 punch-out curve.  Enqueued behind the K1 launches of that curve; costs one tiny launch when nothing was flagged.
+inline int run_fixup(sgz_corr *job, PunchQuery &q, int which, int tailExtra, float *sim, const float *boost,
+                     unsigned long long *fileMax, cudaStream_t st) {
+  sgz_db *db = job->db;
+  CorrFixParams fp{};
+  fp.data = db->dData.p; fp.rowStride = db->capFrames; fp.usedFrames = db->usedFrames;
+  fp.a = q.dAc.p; fp.numCh = db->numCh; fp.W = q.W; fp.stdT = q.stdT; fp.stdS = q.stdS;
+  fp.weight = q.weight; fp.maxBoost = job->cfg.maxBoost;
+  fp.fileStart = db->dFileStart.p; fp.numFiles = db->numFiles(); fp.tailExtra = tailExtra;
+  fp.list = job->dFixList[which].p; fp.count = job->dFixCount.p + which; fp.cap = kFixCap;
+  fp.sim = sim; fp.boost = boost; fp.fileMax = fileMax;
+  k_corr_fixup<<<(unsigned)job->ctx->smCount * 4, 128, 0, st>>>(fp);
+  SGZ_LAUNCH_CHECK(job->ctx);
+  return SGZ_OK;
+}
+
+inline int run_scan_t2(sgz_corr *job, PunchQuery &q, int which, int tailExtra, float *sim, float *boost,
+                       unsigned long long *fileMax, int64_t tileBegin, int64_t tileEnd, cudaStream_t st, int spareSMs) {
   if (tileEnd <= tileBegin) return SGZ_OK;
   sgz_db *db = job->db;
   sgz_ctx *ctx = job->ctx;
@@ -322,7 +349,7 @@ inline int run_scan_t2(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim, 
   {
     T2Eval &E = tp.ev;
     E.invW = 1.0 / (double)q.W; E.invNS = 1.0 / ((double)(db->numCh - 1) * (double)q.W);
-    E.negEps = -1e-13;
+    E.negEps = -2e-3;
     E.cT = (float)(E.invW / q.stdT); E.cS = (float)(E.invNS / q.stdS);
     E.kT = (float)q.rhoT * E.cT; E.kS = (float)q.rhoS * E.cS;
     E.l2In = (float)(q.lnAvg * 1.4426950408889634);
@@ -332,6 +359,7 @@ inline int run_scan_t2(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim, 
   tp.fileStart = db->dFileStart.p; tp.tileFile = job->dTileFileT2.p; tp.numFiles = db->numFiles(); tp.tailExtra = tailExtra;
   tp.tileBegin = tileBegin; tp.tileEnd = tileEnd;
   tp.sim = sim; tp.boost = boost; tp.fileMax = fileMax;
+  tp.fixList = job->dFixList[which].p; tp.fixCount = job->dFixCount.p + which; tp.fixCap = kFixCap;
   tp.smemMax = (int)ctx->smemOptin;
   {
     static const int ahead = getenv("SGZ_T2_AHEAD") ? atoi(getenv("SGZ_T2_AHEAD")) : kT2Ahead;   // developer knob

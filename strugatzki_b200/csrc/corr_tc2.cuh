@@ -21,6 +21,7 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include "corr_fix.cuh"
 #include "corr_tc.cuh"
 
 namespace sgz {
@@ -200,7 +201,7 @@ __device__ __forceinline__ float t2_lg2(float x) { float y; asm("lg2.approx.ftz.
 // constants of one evaluated offset, prepared on the host (kernel parameters = constant bank operands)
 struct T2Eval {
   double invW, invNS;       // 1 / W, 1 / ((numCh - 1) W)
-  double negEps;            // -1e-13: a window whose variance is below 1e-13 of its mean square counts as constant (-> NaN)
+  double negEps;            // -2e-3: a window whose variance is below 2e-3 of its mean square is re-evaluated exactly (corr_fix.cuh)
   float cT, cS;             // 1 / (W std_a) per group, (numCh - 1) folded into cS
   float kT, kS;             // rho * c: correction for the rounded taps not summing to exactly zero
   float l2In;               // log2 of the query's average loudness
@@ -225,6 +226,8 @@ struct CorrT2Params {
   int64_t tileBegin, tileEnd;
   float *sim, *boost;
   unsigned long long *fileMax;
+  uint32_t *fixList, *fixCount; // offsets whose windows are ill-conditioned (corr_fix.cuh)
+  uint32_t fixCap;
   long long *prof;              // SGZ_CORR_TC_PROF: per CTA 24 cycle counters (k_corr_tc2<true>), or nullptr
   int smemMax;                  // the geometry (ring depths) is a function of (W, shared memory limit)
   int ahead;                    // channels between the L2 prefetch of a signal stage and its bulk copy (0: no prefetch)
@@ -248,7 +251,7 @@ __device__ __forceinline__ bool t2_test(uint64_t *bar, uint32_t parity) {   // n
 // one evaluated offset: window sums -> boost and sim (FeatureCorrelationImpl.scala:73-78,198-210); branch free so that the
 // compiler can interleave the offsets of a thread
 __device__ __forceinline__ void t2_eval(const T2Eval &E, const D4 &win, float accT, float accS, float &sim, float &boost) {
-  const float qnan = __int_as_float(0x7fc00000);
+  const float qnan = __uint_as_float(kFixSentinel);
   const double mT = win.t1 * E.invW;
   const float mTf = (float)mT;                                             // MathUtil.avg -> Float
   boost = t2_ex2((E.l2In - t2_lg2(mTf)) * (1.0f / 0.6f));                  // calcBoost
@@ -256,7 +259,7 @@ __device__ __forceinline__ void t2_eval(const T2Eval &E, const D4 &win, float ac
   const double varT = fma(-mT, mT, qT);
   const float crT = fmaf(accT, E.cT, -mTf * E.kT);                         // (acc - mean_b * rho) / (W std_a)
   float temporal = crT * t2_rsqrt((float)varT);
-  temporal = __double2hiint(fma(qT, E.negEps, varT)) > 0 ? temporal : qnan;   // var > 1e-13 q (positive and not NaN)
+  temporal = __double2hiint(fma(qT, E.negEps, varT)) > 0 ? temporal : qnan;   // var > 2e-3 q (positive and not NaN)
   temporal = E.useT ? temporal : 0.f;
   const double mS = win.s1 * E.invNS;
   const double qS = win.s2 * E.invNS;
@@ -266,7 +269,8 @@ __device__ __forceinline__ void t2_eval(const T2Eval &E, const D4 &win, float ac
   spectral = __double2hiint(fma(qS, E.negEps, varS)) > 0 ? spectral : qnan;
   spectral = E.useS ? spectral : 0.f;
   const float blend = __fadd_rn(__fmul_rn(temporal, E.wT), __fmul_rn(spectral, E.wS));
-  sim = boost <= E.maxBoost ? blend : 0.f;
+  // an ill-conditioned group makes the blend NaN whatever the other group is; it is marked for the exact re-evaluation
+  sim = boost <= E.maxBoost ? (blend == blend ? blend : qnan) : 0.f;
 }
 
 // warp 0: producer (bulk copies), warp 1: MMA issuer, warps 2-3: idle (they complete the first warpgroup, which hands most
@@ -548,8 +552,13 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
         }
         if (plain) {
 #pragma unroll
-          for (int e = 0; e < 4; e++)
+          for (int e = 0; e < 4; e++) {
             if (simv[e] > bestS) { bestS = simv[e]; bestJ = 4 * blk + e; }      // NaN never wins, ties keep the first
+            if (simv[e] != simv[e]) {                                           // rare: ill-conditioned window
+              const uint32_t slot = atomicAdd(p.fixCount, 1u);
+              if (slot < p.fixCap) p.fixList[slot] = (uint32_t)(g0 + 4 * blk + e);
+            }
+          }
         } else {
           for (int e = 0; e < 4; e++) {
             const int64_t g = g0 + 4 * blk + e;
@@ -569,6 +578,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
               const unsigned long long key = ((unsigned long long)float_order_key(sv) << 32) |
                                              (unsigned long long)(0xffffffffu - (uint32_t)tl);
               if (key > best) best = key;
+            } else {
+              const uint32_t slot = atomicAdd(p.fixCount, 1u);
+              if (slot < p.fixCap) p.fixList[slot] = (uint32_t)g;
             }
 #pragma unroll
             for (int kk = 0; kk < 4; kk++) if (kk == e) { simv[kk] = sv; boostv[kk] = bv; }

@@ -312,6 +312,46 @@ def test_corr_digital_silence_gives_nan_like_the_reference(ctx):
     assert any(np.isnan(m["sim"]) for m in want)
 
 
+@pytest.mark.parametrize("weight", [0.5, 0.0, 1.0])
+def test_corr_near_constant_windows_are_the_references(ctx, weight):
+    """the reference returns NaN only for an EXACTLY constant window (0 / 0, MathUtil.scala:195); a window that is constant
+    but for one cell one ulp off, or that carries a dither of 1e-5 of its level, gets a finite sim from its two-pass Double
+    arithmetic.  The tensor-core K1 cannot resolve such windows (variance below 1e-4 of the mean square): it flags them and
+    corr_fix.cuh replays the reference's arithmetic, so NaN pattern AND values are the oracle's, bit for bit"""
+    from strugatzki_b200 import engine
+    files, norm = make_db(3, 4000)
+    inp = make_input(900)
+    f = files[1]
+    f[600:1500] = f[600]                                                   # 900 constant frames, all channels
+    f[1000, 0] = np.nextafter(f[1000, 0], np.float32(2))                   # loudness one ulp off at one frame
+    f[1100, 5] = np.nextafter(f[1100, 5], np.float32(2))                   # one spectral cell one ulp off
+    rng = np.random.default_rng(5)
+    f[2000:2800] = f[2000] * (1 + 1e-5 * rng.standard_normal((800, 14))).astype(np.float32)   # dither
+    files[2][3000:] = files[2][3000]                                       # constant up to the file end
+    plant_needles(files, inp[:172], [(0, 900), (2, 100)])
+    op, nc = corr_cfgs(inp, norm, w_in=weight, num_matches=8, num_per_file=3, min_spacing=22050)
+    job = engine.CorrelationJob(build_db(ctx, files, norm), nc, inp)
+    got = job.run()
+    flagged = 0
+    for i in range(3):
+        wc, wb = O.corr_curve(op, files[i])
+        gc, gb = job.curve(i, 0, 0, len(wc))
+        assert np.array_equal(np.isnan(wc), np.isnan(gc)), f"file {i}: NaN pattern"
+        assert_sims_close(gc, wc, what=f"file {i} sim")
+        if i == 1 and weight > 0:
+            # windows inside the flat stretches have an (almost) constant LOUDNESS channel: flagged and replayed exactly.
+            # (The spectral group is not ill-conditioned there: its 13 channels sit at different levels.)
+            flat = np.zeros(len(wc), bool)
+            flat[600:1500 - 171] = True
+            flat[2000:2800 - 171] = True
+            fin = flat & np.isfinite(wc)          # (NaN patterns were compared above; NaN payloads differ by platform)
+            assert np.array_equal(gc[fin].view(np.uint32), wc[fin].view(np.uint32))        # exact replay: bit identical
+            assert np.isfinite(wc[flat]).any() and np.isnan(wc[flat]).any()
+            flagged = int(flat.sum())
+    assert flagged > 1000 or weight == 0
+    assert_matches_equal(got, O.corr_search(op, files))
+
+
 def test_memory_pool_reuses_and_trims(ctx):
     """destroyed databases park their buffers; a new database of the same size gets them back dirty and must still
     produce the same result (slack zeroing at finalize); trim returns the memory to the driver"""
