@@ -297,7 +297,8 @@ def main():
         flops = n_off_local * FLOP_PER_OFFSET / scan_s / 1e12
         tc = os.environ.get("SGZ_CORR_TC", "1") != "0"     # K1 on the tensor cores (default) or the FFMA2 kernel
         traffic = None   # dram__bytes_read + dram__bytes_write of one K1 launch, from the committed ncu capture
-        traffic_file = "r01_k_corr_tc_traffic.json" if tc else "r01_k_corr_traffic.json"
+        traffic_file = ("r02_k_corr_tc2_traffic.json" if os.environ.get("SGZ_CORR_TC2", "1") != "0" else
+                        "r01_k_corr_tc_traffic.json") if tc else "r01_k_corr_traffic.json"
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", traffic_file)))
             if int(tj["offsets_per_launch"]) == int(n_off_local):
@@ -308,14 +309,25 @@ def main():
                "frac": n_off_local * BYTES_PER_OFFSET / scan_s / 1e9 / hbm_peak, "peak_source": hbm_src,
                "algorithmic_bytes_per_offset": BYTES_PER_OFFSET}
         if tc:
-            # tensor-core K1 (corr_tc.cuh): per tile of 4096 offsets, 14 channels x 3 split-FP16 products x
-            # ceil((32 + W) / 16) MMAs of M128 x N32 x K16; each costs 44.5 cycles back to back (tools/umma_probe.cu: the
-            # A-operand fetch bounds small-N MMAs), which is this design's own floor
+            # tensor-core K1 (corr_tc2.cuh): per tile of 8192 offsets, 14 channels x 3 split-FP16 products x
+            # ceil((63 + W) / 16) MMAs of M128 x N64 x K16.  An MMA reads its operands from shared memory: 6 KB (A 4 KB +
+            # B 2 KB), 2 KB when A comes from the operand collector -> 14 KB per K step of three MMAs, 109 B per clock at the
+            # MMA rate the tensor pipe could sustain.  Together with the bulk copies that fill the ring (731 KB per tile)
+            # and the epilogue's loads / stores the SM's 128 B/clock shared-memory / L1 data pipe is the binding resource
+            # of this formulation ("smem_floor_ms"); see DESIGN.md.
             tensor_peak = float(peaks_file.get("bf16_tflops_sustained", 1399.0))
-            mmas_per_tile = 14 * 3 * ((32 + 172 + 15) // 16)
-            exec_flop_per_offset = mmas_per_tile * 2 * 128 * 32 * 16 / 4096
-            tiles_per_sm = -(-n_off_local // 4096) / 148.0
-            floor_ms = tiles_per_sm * mmas_per_tile * 44.5 / 1.965e6
+            t2 = os.environ.get("SGZ_CORR_TC2", "1") != "0"
+            if t2:
+                ks, tile, ncols, kname = (63 + 172 + 15) // 16, 8192, 64, "sgz::k_corr_tc2"
+                mma_cycles = (48 + 32 + 48) / 3.0
+            else:
+                ks, tile, ncols, kname = (32 + 172 + 15) // 16, 4096, 32, "sgz::k_corr_tc"
+                mma_cycles = 44.5
+            mmas_per_tile = 14 * 3 * ks
+            exec_flop_per_offset = mmas_per_tile * 2 * 128 * ncols * 16 / tile
+            tiles_per_sm = -(-n_off_local // tile) / 148.0
+            floor_ms = tiles_per_sm * mmas_per_tile * mma_cycles / 1.965e6
+            smem_bytes_per_tile = 14 * ks * 14336 + 14 * (2 * 16768 + 18432) + 4096 * 128 + 3000 * 128 if t2 else None
             # Which roof binds?  Algorithmic intensity = 4 904 flop / 64 B = 77 flop/B; with the tensor cores as the math
             # roof the ridge is at tensor_peak / hbm_peak (= 214 flop/B with the measured 1 399 TFLOP/s and 6 549 GB/s):
             # the kernel sits LEFT of the ridge, so the roofline model bounds it by HBM (min(peak, AI x BW) = 502
@@ -329,8 +341,12 @@ def main():
                       "executed_flop_per_offset": exec_flop_per_offset,
                       "mma_floor_ms": floor_ms, "frac_of_mma_floor": floor_ms / float(np.mean(scan_ms)),
                       "fp32_ffma_peak": ffma_peak, "algorithmic_vs_fp32_ffma_peak": flops / ffma_peak}
-            roofline = {"kernel": "sgz::k_corr_tc (K1 sliding-window Pearson correlation on tcgen05, split FP16, fused "
-                                  "window statistics / sim / file maxima)",
+            if smem_bytes_per_tile:
+                tensor["smem_floor_ms"] = tiles_per_sm * smem_bytes_per_tile / 128.0 / 1.965e6
+                tensor["frac_of_smem_floor"] = tensor["smem_floor_ms"] / float(np.mean(scan_ms))
+            roofline = {"kernel": kname + " (K1 sliding-window Pearson correlation on tcgen05: split-FP16 operands from "
+                                          "precomputed planes by bulk copy, N = 64 Hankel tiles, fused window statistics / sim / "
+                                          "file maxima)" if t2 else kname + " (round-1 N = 32 tensor-core kernel)",
                         "bound": "hbm" if intensity < ridge else "tensor",
                         "achieved": hbm["achieved"] if intensity < ridge else flops,
                         "peak": hbm_peak if intensity < ridge else tensor_peak,
@@ -338,10 +354,11 @@ def main():
                         "frac": hbm["frac"] if intensity < ridge else flops / tensor_peak,
                         "peak_source": hbm_src if intensity < ridge else tensor["peak_source"],
                         "intensity_flop_per_byte": intensity, "ridge_flop_per_byte": ridge,
-                        "why_not_higher": "three split-FP16 products for FP32-grade precision, issued as N = 32 MMAs that the "
-                                          "4 KB A-operand fetch bounds (44.5 cycles per M128xN32xK16 MMA, measured), plus the "
-                                          "FP16 split and the FP64 window statistics around them: the MMA floor of this "
-                                          "formulation is 2.1x the HBM time",
+                        "why_not_higher": "three split-FP16 products for FP32-grade precision: 630 M128xN64xK16 MMAs per 8192 "
+                                          "offsets fetch 2.9 MB of operands from shared memory, the ring is filled with 0.73 MB "
+                                          "and the epilogue moves another 0.9 MB -- 4.6 MB per tile through a 128 B/clock data "
+                                          "pipe is 36 k cycles (the measured tile time is 47 k); the HBM time of the same tile is "
+                                          "21 k cycles",
                         "tensor": tensor}
         else:
             roofline = {"kernel": "sgz::k_corr (K1 sliding-window Pearson correlation, FFMA2)", "bound": "fp32_ffma",

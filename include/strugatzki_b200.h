@@ -267,6 +267,21 @@ typedef struct {
   int32_t aux;
 } sgz_record;
 
+/* Punch-in-only searches need far less than one summary per file: a file whose maximum is not among the numMatches largest
+ * maxima of its rank can never raise the threshold of a later file, and whether a file is scanned for candidates is
+ * decided by the rank that holds it.  sgz_corr_local_top returns those (at most numMatches) entries with LOCAL file
+ * indices and the number of local files; after an all_gather the host rebases the indices to the global file list and
+ * hands all entries of all ranks to sgz_corr_set_global_top (in place of local_summary / set_global: 8 B x numMatches
+ * per rank instead of 16 B x files).  Thresholds derived from a subset of the earlier files are lower bounds of the
+ * exact ones, i.e. safe pre-filters (select.cuh); the merge sees the same records on every rank. */
+typedef struct {
+  int32_t file;
+  float   maxSim;
+} sgz_file_entry;
+int sgz_corr_local_top(sgz_corr *job, sgz_file_entry *out, int32_t cap, int32_t *n, int32_t *numFiles);
+int sgz_corr_set_global_top(sgz_corr *job, const sgz_file_entry *all, int32_t nAll, int32_t nFilesGlobal,
+                            int32_t myFirstFile);
+
 int sgz_corr_scan(sgz_corr *job);
 int sgz_corr_local_summary(sgz_corr *job, sgz_file_summary *out, int32_t cap, int32_t *n);
 int sgz_corr_set_global(sgz_corr *job, const sgz_file_summary *all, int32_t nFilesGlobal,

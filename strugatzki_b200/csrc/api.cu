@@ -728,18 +728,16 @@ int sgz_corr_local_summary(sgz_corr *job, sgz_file_summary *out, int32_t cap, in
   *n = nf;
   if (!out) return SGZ_OK;
   SGZ_REQUIRE(cap >= nf, "summary buffer too small (%d < %d)", cap, nf);
-  std::vector<unsigned long long> keys((size_t)std::max(nf, 1));
+  SGZ_TRY(job->pin((size_t)std::max(nf, 1) * 2 * sizeof(unsigned long long)));
+  unsigned long long *keys = reinterpret_cast<unsigned long long *>(job->hPin), *keysOut = keys + std::max(nf, 1);
   if (nf > 0) {
-    SGZ_CUDA(cudaMemcpyAsync(keys.data(), job->dFileMax.p, nf * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                             job->ctx->stream));
+    SGZ_CUDA(cudaMemcpyAsync(keys, job->dFileMax.p, nf * sizeof(unsigned long long), cudaMemcpyDeviceToHost, job->ctx->stream));
+    if (job->hasOut)
+      SGZ_CUDA(cudaMemcpyAsync(keysOut, job->dFileMaxOut.p, nf * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                               job->ctx->stream));
     SGZ_CUDA(cudaStreamSynchronize(job->ctx->stream));
   }
-  std::vector<unsigned long long> keysOut((size_t)std::max(nf, 1), 0ull);
-  if (nf > 0 && job->hasOut) {
-    SGZ_CUDA(cudaMemcpyAsync(keysOut.data(), job->dFileMaxOut.p, nf * sizeof(unsigned long long),
-                             cudaMemcpyDeviceToHost, job->ctx->stream));
-    SGZ_CUDA(cudaStreamSynchronize(job->ctx->stream));
-  }
+  if (!job->hasOut) memset(keysOut, 0, (size_t)std::max(nf, 1) * sizeof(unsigned long long));
   const int tail = job->hasOut ? job->minPunchF : 0;
   for (int f = 0; f < nf; f++) {
     int64_t nv = (db->fileStart[f + 1] - db->fileStart[f]) - tail - job->qin.W + 1;
@@ -765,6 +763,48 @@ int sgz_corr_set_global(sgz_corr *job, const sgz_file_summary *all, int32_t nFil
   job->nextFile = 0;
   job->finished = nFilesGlobal == 0 || job->cfg.numMatches <= 0 || job->cfg.numPerFile <= 0;
   return SGZ_OK;
+}
+
+int sgz_corr_local_top(sgz_corr *job, sgz_file_entry *out, int32_t cap, int32_t *n, int32_t *numFiles) {
+  SGZ_REQUIRE(job && n && numFiles, "NULL argument");
+  if (!job->scanned) { set_error("sgz_corr_local_top before scan"); return SGZ_ERR_STATE; }
+  SGZ_REQUIRE(!job->hasOut, "sgz_corr_local_top is for punch-in-only searches (the punch-out merge needs every file's length)");
+  sgz_db *db = job->db;
+  const int nf = db->numFiles();
+  *numFiles = nf;
+  const int k = std::min(nf, std::max(job->cfg.numMatches, 0));
+  *n = k;
+  if (!out) return SGZ_OK;
+  SGZ_REQUIRE(cap >= k, "entry buffer too small (%d < %d)", cap, k);
+  job->localSummary.resize((size_t)std::max(nf, 1));
+  int32_t got = 0;
+  SGZ_TRY(sgz_corr_local_summary(job, job->localSummary.data(), nf, &got));
+  std::vector<int32_t> idx((size_t)nf);
+  for (int f = 0; f < nf; f++) idx[(size_t)f] = f;
+  auto greater = [&](int32_t a, int32_t b) {
+    const float x = job->localSummary[(size_t)a].maxSim, y = job->localSummary[(size_t)b].maxSim;
+    return x != y ? x > y : a < b;
+  };
+  if (k < nf) std::nth_element(idx.begin(), idx.begin() + k, idx.end(), greater);
+  std::sort(idx.begin(), idx.begin() + k);
+  for (int i = 0; i < k; i++) out[i] = sgz_file_entry{idx[(size_t)i], job->localSummary[(size_t)idx[(size_t)i]].maxSim};
+  return SGZ_OK;
+}
+
+int sgz_corr_set_global_top(sgz_corr *job, const sgz_file_entry *all, int32_t nAll, int32_t nFilesGlobal, int32_t myFirstFile) {
+  SGZ_REQUIRE(job && (all || nAll == 0), "NULL argument");
+  if (!job->scanned) { set_error("sgz_corr_set_global_top before scan"); return SGZ_ERR_STATE; }
+  const int nf = job->db->numFiles();
+  SGZ_REQUIRE((int)job->localSummary.size() >= nf, "sgz_corr_set_global_top before sgz_corr_local_top");
+  SGZ_REQUIRE(myFirstFile >= 0 && myFirstFile + nf <= nFilesGlobal, "local shard [%d,+%d) outside the global file list of %d",
+              myFirstFile, nf, nFilesGlobal);
+  std::vector<sgz_file_summary> g((size_t)nFilesGlobal, sgz_file_summary{-INFINITY, 0, -INFINITY, 0});
+  for (int i = 0; i < nAll; i++) {
+    SGZ_REQUIRE(all[i].file >= 0 && all[i].file < nFilesGlobal, "entry %d names file %d of %d", i, all[i].file, nFilesGlobal);
+    g[(size_t)all[i].file].maxSim = all[i].maxSim;
+  }
+  for (int f = 0; f < nf; f++) g[(size_t)(myFirstFile + f)] = job->localSummary[(size_t)f];   // own files: exact
+  return sgz_corr_set_global(job, g.data(), nFilesGlobal, myFirstFile);
 }
 
 // One selection round on the local shard.  See the protocol in strugatzki_b200.h.
@@ -807,17 +847,18 @@ int sgz_corr_select(sgz_corr *job, int32_t *nRecords) {
       fp.numPerFile = npf; fp.maxEntrySz = m; fp.minSpacing = job->cfg.minSpacing; fp.step = job->step;
       fp.entries = job->dEntries.p; fp.counts = job->dCounts.p;
       SGZ_TRY(ctx->begin_call());
-      k_replay_fill<<<(unsigned)ceil_div(nj, 4), 128, 0, ctx->stream>>>(fp);
+      k_replay_fill<<<(unsigned)nj, kFillPiThreads, 0, ctx->stream>>>(fp);
       SGZ_LAUNCH_CHECK(ctx);
-      SGZ_TRY(ctx->end_call());
-      job->selectMs += ctx->lastMs;
-      std::vector<int32_t> counts(nj);
-      std::vector<EntryRec> ents((size_t)nj * (npf + 1));
-      SGZ_CUDA(cudaMemcpyAsync(counts.data(), job->dCounts.p, nj * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                               ctx->stream));
-      SGZ_CUDA(cudaMemcpyAsync(ents.data(), job->dEntries.p, ents.size() * sizeof(EntryRec), cudaMemcpyDeviceToHost,
-                               ctx->stream));
+      SGZ_TRY(ctx->end_call_async());
+      const size_t entBytes = (size_t)nj * (npf + 1) * sizeof(EntryRec);
+      SGZ_TRY(job->pin(entBytes + (size_t)nj * sizeof(int32_t)));
+      const EntryRec *ents = reinterpret_cast<const EntryRec *>(job->hPin);
+      const int32_t *counts = reinterpret_cast<const int32_t *>(job->hPin + entBytes);
+      SGZ_CUDA(cudaMemcpyAsync(job->hPin, job->dEntries.p, entBytes, cudaMemcpyDeviceToHost, ctx->stream));
+      SGZ_CUDA(cudaMemcpyAsync(job->hPin + entBytes, job->dCounts.p, nj * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
       SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+      SGZ_TRY(ctx->collect_call());
+      job->selectMs += ctx->lastMs;
       for (int j = 0; j < nj; j++)
         for (int k = 0; k < counts[j]; k++) {
           const EntryRec &e = ents[(size_t)j * (npf + 1) + k];
@@ -870,16 +911,23 @@ int sgz_corr_select(sgz_corr *job, int32_t *nRecords) {
         SGZ_TRY(ctx->begin_call());
         k_candidates<<<dim3((unsigned)nj, 8), 256, 0, ctx->stream>>>(cp);
         SGZ_LAUNCH_CHECK(ctx);
-        SGZ_TRY(ctx->end_call());
-        job->selectMs += ctx->lastMs;
-        int count = 0;
-        SGZ_CUDA(cudaMemcpyAsync(&count, job->dCounter.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        SGZ_TRY(ctx->end_call_async());
+        // the counter and the first records in one round trip; more records (rare) in a second one
+        const int first = std::min(cap, 2048);
+        SGZ_TRY(job->pin(16 + (size_t)first * sizeof(sgz_record)));
+        SGZ_CUDA(cudaMemcpyAsync(job->hPin, job->dCounter.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        SGZ_CUDA(cudaMemcpyAsync(job->hPin + 16, job->dRecs.p, (size_t)first * sizeof(sgz_record), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
         SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+        SGZ_TRY(ctx->collect_call());
+        job->selectMs += ctx->lastMs;
+        const int count = *reinterpret_cast<const int *>(job->hPin);
         if (count <= cap) {
           job->localRecords.resize(count);
-          if (count > 0) {
-            SGZ_CUDA(cudaMemcpyAsync(job->localRecords.data(), job->dRecs.p, (size_t)count * sizeof(sgz_record),
-                                     cudaMemcpyDeviceToHost, ctx->stream));
+          if (count > 0) memcpy(job->localRecords.data(), job->hPin + 16, (size_t)std::min(count, first) * sizeof(sgz_record));
+          if (count > first) {
+            SGZ_CUDA(cudaMemcpyAsync(job->localRecords.data() + first, job->dRecs.p + first,
+                                     (size_t)(count - first) * sizeof(sgz_record), cudaMemcpyDeviceToHost, ctx->stream));
             SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
           }
           break;

@@ -135,6 +135,16 @@ struct sgz_ctx {
     SGZ_CUDA(cudaEventRecord(ev0, stream));
     return SGZ_OK;
   }
+  // the same without the host wait: the caller synchronises the stream anyway (a download follows) and then collects
+  int end_call_async() {
+    SGZ_CUDA(cudaEventRecord(ev1, stream));
+    return SGZ_OK;
+  }
+  int collect_call() {
+    SGZ_CUDA(cudaEventElapsedTime(&lastMs, ev0, ev1));
+    lastLaunches = launches - callLaunches0;
+    return SGZ_OK;
+  }
   int end_call() {
     SGZ_CUDA(cudaEventRecord(ev1, stream));
     SGZ_CUDA(cudaEventSynchronize(ev1));

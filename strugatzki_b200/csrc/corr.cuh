@@ -45,6 +45,7 @@ struct sgz_corr {
 
   // global (all ranks) view
   std::vector<sgz_file_summary> globalSummary;
+  std::vector<sgz_file_summary> localSummary;   // cached by sgz_corr_local_top
   int nFilesGlobal = 0, myFirst = 0;
   bool globalSet = false;
 
@@ -64,6 +65,21 @@ struct sgz_corr {
   DevBuf<float4> dMeta;        // punch-out filling rounds: gate interval per file (punchout.cuh)
   DevBuf<sgz_record> dRecs;
   DevBuf<int> dCounter;
+
+  // pinned host scratch for the small downloads of the selection rounds (pageable copies are staged synchronously)
+  unsigned char *hPin = nullptr;
+  size_t hPinBytes = 0;
+  int pin(size_t bytes) {
+    if (bytes <= hPinBytes) return SGZ_OK;
+    if (hPin) cudaFreeHost(hPin);
+    hPin = nullptr;
+    hPinBytes = 0;
+    const size_t want = std::max<size_t>(bytes + bytes / 2, (size_t)1 << 18);
+    SGZ_CUDA(cudaHostAlloc((void **)&hPin, want, cudaHostAllocDefault));
+    hPinBytes = want;
+    return SGZ_OK;
+  }
+  ~sgz_corr() { if (hPin) cudaFreeHost(hPin); }
 
   // timing (device ms of the last scan / accumulated select kernels)
   float scanMs = 0.f, selectMs = 0.f;

@@ -101,7 +101,7 @@ struct Machine {
 };
 
 // ---------------------------------------------------------------------------------------------
-// filling phase, punch-in only: one warp replays one file over its whole curve
+// filling phase, punch-in only: one block replays one file over its whole curve
 // ---------------------------------------------------------------------------------------------
 struct FillParams {
   const float *sim;
@@ -119,11 +119,21 @@ struct FillParams {
   int32_t *counts;          // [numJobs]
 };
 
-__global__ void k_replay_fill(const FillParams p) {
-  const int warpsPerBlock = blockDim.x >> 5;
-  const int job = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
+// One block per file.  The replay itself is sequential (warp 0), but while the entry has no space `lowest` never
+// decreases (addMatch only replaces or drops lower sims), so "sim > low" evaluated with the `low` of the chunk start marks
+// a superset of the offsets that can change the state later in the chunk: all warps stage a chunk of the curve in shared
+// memory and leave one bit per offset, warp 0 visits only the marked 32-offset groups and re-evaluates them exactly.
+// While the entry still has space (the file start, or a collapse onto an equal key) every offset is visited.
+constexpr int kFillPiChunk = 4096, kFillPiThreads = 256;
+
+__global__ void __launch_bounds__(kFillPiThreads) k_replay_fill(const FillParams p) {
+  __shared__ float sSim[kFillPiChunk];
+  __shared__ unsigned marks[kFillPiChunk / 32];
+  __shared__ float sLow;
+  __shared__ int sHs;
+  const int job = blockIdx.x;
   if (job >= p.numJobs) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned full = 0xffffffffu;
   const int f = p.files[job];
   const int64_t fs = p.fileStart[f];
@@ -133,61 +143,66 @@ __global__ void k_replay_fill(const FillParams p) {
 
   Machine mc;
   mc.reset(p.entries + (size_t)job * (p.numPerFile + 1), p.numPerFile, p.maxEntrySz, 0, 0.f, p.minSpacing, p.step);
-  // replicated view of the state every lane needs for its predicate
+  // replicated view of the state every lane of warp 0 needs for its predicate
   bool hs = mc.has_space();
   float low = mc.lowest();
   int hasLast = 0;
   float lastSim = 0.f;
   int lastPi = 0;
-
-  // 128 offsets per step: lane l tests offsets pos + 4l .. pos + 4l + 3 (one 16-byte load when aligned);
-  // the step is only taken apart when some offset can change the machine state.
-  int64_t pos = 0;
-  while (pos < nValid) {
-    const int64_t tb = pos + 4 * lane;
-    float sv[4];
-    if ((((fs + tb) & 3) == 0) && tb + 3 < nValid) {
-      const float4 v = *reinterpret_cast<const float4 *>(sim + tb);
-      sv[0] = v.x; sv[1] = v.y; sv[2] = v.z; sv[3] = v.w;
-    } else {
+  if (threadIdx.x == 0) { sLow = low; sHs = hs ? 1 : 0; }
+  for (int64_t chunk = 0; chunk < nValid; chunk += kFillPiChunk) {
+    __syncthreads();
+    const float lowC = sLow;
+    const bool hsC = sHs != 0;
+    const int n = (int)(nValid - chunk < kFillPiChunk ? nValid - chunk : kFillPiChunk);
 #pragma unroll
-      for (int j = 0; j < 4; j++) sv[j] = tb + j < nValid ? sim[tb + j] : 0.f;
+    for (int j = 0; j < kFillPiChunk / kFillPiThreads; j++) {
+      const int i = j * kFillPiThreads + threadIdx.x;
+      const float s = i < n ? sim[chunk + i] : 0.f;
+      sSim[i] = s;
+      const unsigned m = __ballot_sync(full, i < n && (hsC || s > lowC));
+      if (lane == 0) marks[i >> 5] = m;
     }
-    int first = 1 << 30;
-#pragma unroll
-    for (int j = 3; j >= 0; j--) {
-      const int64_t t = tb + j;
-      if (t < nValid) {
-        const float s = sv[j];
+    __syncthreads();
+    if (warp != 0) continue;
+    bool marksValid = !hs;
+    for (int g = 0; g < (n + 31) / 32; g++) {
+      if (marksValid && marks[g] == 0u) continue;
+      const int i = 32 * g + lane;
+      const int64_t t = chunk + i;
+      const float s = sSim[i];
+      unsigned todo = full;                        // offsets of the group not yet passed by the replay
+      for (;;) {
         const bool accept = hs || s > low;
         const bool collapse = hasLast && ((t - (int64_t)lastPi - p.W) * p.step < p.minSpacing);
-        if (accept && (collapse ? (lastSim < s) : true)) first = 4 * lane + j;
+        const bool change = i < n && accept && (collapse ? (lastSim < s) : true);
+        const unsigned cm = __ballot_sync(full, change) & todo;
+        if (cm == 0u) break;
+        const int hit = __ffs(cm) - 1;
+        const float ss = __shfl_sync(full, s, hit);
+        const int64_t ts = chunk + 32 * g + hit;
+        if (lane == 0) {
+          EntryRec m{ss, (int32_t)ts, (int32_t)(ts + p.W), boost[ts], 1.0f};
+          mc.add(m);
+          hs = mc.has_space();
+          low = mc.lowest();
+          hasLast = mc.hasLast;
+          lastSim = mc.last.sim;
+          lastPi = mc.last.piOff;
+        }
+        hs = __shfl_sync(full, (int)hs, 0) != 0;
+        low = __shfl_sync(full, low, 0);
+        hasLast = __shfl_sync(full, hasLast, 0);
+        lastSim = __shfl_sync(full, lastSim, 0);
+        lastPi = __shfl_sync(full, lastPi, 0);
+        if (hs) marksValid = false;                // `low` may fall again: the marks are no superset any more
+        todo = hit == 31 ? 0u : (full << (hit + 1));
+        if (todo == 0u) break;
       }
     }
-    const int hit = __reduce_min_sync(full, first);
-    if (hit == (1 << 30)) { pos += 128; continue; }
-    const int64_t ts = pos + hit;
-    float ss = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; j++) if ((hit & 3) == j) ss = sv[j];
-    ss = __shfl_sync(full, ss, hit >> 2);
-    if (lane == 0) {
-      EntryRec m{ss, (int32_t)ts, (int32_t)(ts + p.W), boost[ts], 1.0f};
-      mc.add(m);
-      hs = mc.has_space();
-      low = mc.lowest();
-      hasLast = mc.hasLast;
-      lastSim = mc.last.sim;
-      lastPi = mc.last.piOff;
-    }
-    hs = __shfl_sync(full, (int)hs, 0) != 0;
-    low = __shfl_sync(full, low, 0);
-    hasLast = __shfl_sync(full, hasLast, 0);
-    lastSim = __shfl_sync(full, lastSim, 0);
-    lastPi = __shfl_sync(full, lastPi, 0);
-    pos = ts + 1;
+    if (lane == 0) { sLow = low; sHs = hs ? 1 : 0; }
   }
-  if (lane == 0) p.counts[job] = mc.n;
+  if (threadIdx.x == 0) p.counts[job] = mc.n;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -20,6 +20,27 @@ from typing import Dict, List, Optional
 import numpy as np
 
 _caps: Dict[str, int] = {}
+_bufs: Dict[tuple, tuple] = {}
+
+
+def _exchange_buffers(tag: str, cap: int, world: int, dev):
+    """Persistent buffers of one exchange: pinned host send / receive staging and the device send / receive tensors NCCL
+    works on, allocated once per (tag, capacity) -- a search runs the same two exchanges every time, and a fresh pageable
+    tensor per call costs a synchronous staged copy in each direction."""
+    import torch
+    key = (tag, cap, world, str(dev))
+    b = _bufs.get(key)
+    if b is None:
+        n = 8 + cap
+        if dev.type == "cuda":
+            b = (torch.zeros(n, dtype=torch.uint8, pin_memory=True), torch.empty(n, dtype=torch.uint8, device=dev),
+                 torch.empty(world * n, dtype=torch.uint8, device=dev), torch.empty(world * n, dtype=torch.uint8, pin_memory=True))
+        else:
+            b = (torch.zeros(n, dtype=torch.uint8), None, None, torch.empty(world * n, dtype=torch.uint8))
+        for k in [k for k in _bufs if k[0] == tag and k[2:] == key[2:]]:     # an outgrown capacity is not kept
+            del _bufs[k]
+        _bufs[key] = b
+    return b
 
 
 def allgather_bytes(arr: np.ndarray, device=None, group=None, tag: str = "default", initial_cap: int = 1 << 16):
@@ -34,17 +55,19 @@ def allgather_bytes(arr: np.ndarray, device=None, group=None, tag: str = "defaul
     dev = device if device is not None else torch.device("cpu")
     cap = _caps.get(tag, initial_cap)
     while True:
-        msg = np.zeros(8 + cap, np.uint8)
+        h_send, d_send, d_recv, h_recv = _exchange_buffers(tag, cap, world, dev)
+        msg = h_send.numpy()
         msg[:8] = np.frombuffer(np.int64(raw.shape[0]).tobytes(), np.uint8)
         n_send = min(raw.shape[0], cap)
         msg[8:8 + n_send] = raw[:n_send]
-        buf = torch.from_numpy(msg).to(dev)
-        out = torch.empty(world * (8 + cap), dtype=torch.uint8, device=dev)
         if dev.type == "cuda":
-            dist.all_gather_into_tensor(out, buf, group=group)
+            d_send.copy_(h_send, non_blocking=True)
+            dist.all_gather_into_tensor(d_recv, d_send, group=group)
+            h_recv.copy_(d_recv, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
         else:
-            dist.all_gather(list(out.view(world, 8 + cap).unbind(0)), buf, group=group)
-        host = out.cpu().numpy().reshape(world, 8 + cap)
+            dist.all_gather(list(h_recv.view(world, 8 + cap).unbind(0)), h_send, group=group)
+        host = h_recv.numpy().reshape(world, 8 + cap)
         sizes = [int(np.frombuffer(host[r, :8].tobytes(), np.int64)[0]) for r in range(world)]
         if max(sizes) <= cap:
             break
@@ -73,11 +96,32 @@ def sharded_search(job, device=None, group=None, trace: Optional[dict] = None) -
     rank = dist.get_rank(group)
     job.scan()
     mark("scan")
-    summary = job.local_summary()
-    mark("summary_download")
-    everything, counts = allgather_bytes(summary, device, group, tag="summary", initial_cap=1 << 17)
-    mark("summary_allgather")
-    job.set_global(everything, int(sum(counts[:rank])))
+    if getattr(job, "sparse_summary", False):
+        # punch-in only: the numMatches largest file maxima of every rank are all the thresholds need (strugatzki_b200.h);
+        # entry 0 of each rank's message carries its number of files
+        from . import _native as N
+        top, n_local = job.local_top()
+        msg = np.zeros(top.shape[0] + 1, N.ENTRY_DTYPE)
+        msg[0]["file"] = n_local
+        msg[1:] = top
+        mark("summary_download")
+        everything, counts = allgather_bytes(msg, device, group, tag="top", initial_cap=1 << 12)
+        mark("summary_allgather")
+        starts = np.concatenate([[0], np.cumsum(counts)])
+        n_files = [int(everything[starts[r]]["file"]) for r in range(len(counts))]
+        first = np.concatenate([[0], np.cumsum(n_files)])
+        parts = []
+        for r in range(len(counts)):
+            e = everything[starts[r] + 1:starts[r + 1]].copy()
+            e["file"] += first[r]
+            parts.append(e)
+        job.set_global_top(np.concatenate(parts), int(first[-1]), int(first[rank]))
+    else:
+        summary = job.local_summary()
+        mark("summary_download")
+        everything, counts = allgather_bytes(summary, device, group, tag="summary", initial_cap=1 << 17)
+        mark("summary_allgather")
+        job.set_global(everything, int(sum(counts[:rank])))
     mark("set_global")
     done = False
     rounds = 0

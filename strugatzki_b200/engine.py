@@ -182,6 +182,9 @@ class CorrelationJob:
         N.check(N.lib().sgz_corr_create(db._h, C.byref(cfg), N.fptr(a), C.c_int64(a.shape[0]), int(layout),
                                         C.byref(self._h)))
         self.cfg = cfg
+        # sharded searches: punch-in-only jobs exchange the numMatches largest file maxima per rank instead of one
+        # summary per file (sgz_corr_local_top / sgz_corr_set_global_top)
+        self.sparse_summary = not bool(cfg.hasPunchOut)
 
     def close(self):
         if self._h:
@@ -254,6 +257,19 @@ class CorrelationJob:
     def set_global(self, all_summaries: np.ndarray, my_first_file: int):
         a = np.ascontiguousarray(all_summaries, N.SUMMARY_DTYPE)
         N.check(N.lib().sgz_corr_set_global(self._h, N.fptr(a), a.shape[0], int(my_first_file)))
+
+    def local_top(self):
+        """(entries with LOCAL file indices, number of local files): the sparse summary of a punch-in-only search"""
+        n, nf = C.c_int32(), C.c_int32()
+        N.check(N.lib().sgz_corr_local_top(self._h, None, 0, C.byref(n), C.byref(nf)))
+        out = np.zeros(max(n.value, 1), N.ENTRY_DTYPE)
+        N.check(N.lib().sgz_corr_local_top(self._h, N.fptr(out), out.shape[0], C.byref(n), C.byref(nf)))
+        return out[:n.value], nf.value
+
+    def set_global_top(self, all_entries: np.ndarray, n_files_global: int, my_first_file: int):
+        a = np.ascontiguousarray(all_entries, N.ENTRY_DTYPE)
+        N.check(N.lib().sgz_corr_set_global_top(self._h, N.fptr(a) if a.shape[0] else None, a.shape[0], int(n_files_global),
+                                                int(my_first_file)))
 
     def select(self) -> np.ndarray:
         n = C.c_int32()

@@ -75,6 +75,32 @@ def _worker(rank, world, port, out_q):
         total = sum(r + 2 for r in range(world))
         assert job.all.shape[0] == total and job.first == sum(r + 2 for r in range(rank))
         assert job.rounds == 2 and job.calls == ["scan"]
+
+        # 3. the sparse summary of punch-in-only searches: every rank sends its file count and its top entries with LOCAL
+        # indices; the driver rebases them to the global file list
+        class SparseJob(FakeJob):
+            sparse_summary = True
+
+            def local_top(self):
+                e = np.zeros(1, N.ENTRY_DTYPE)              # only the best local file
+                e["file"] = self.n_local - 1
+                e["maxSim"] = 0.1 * (rank + 1) + 0.01 * (self.n_local - 1)
+                return e, self.n_local
+
+            def set_global_top(self, entries, n_files_global, my_first):
+                self.entries, self.n_global, self.first = entries.copy(), n_files_global, my_first
+                self.all = np.zeros(n_files_global, N.SUMMARY_DTYPE)
+                self.all["maxSim"] = -np.inf
+                self.all["maxSim"][entries["file"]] = entries["maxSim"]
+
+            def local_summary(self):
+                raise AssertionError("the dense summary must not be used")
+
+        sj = SparseJob()
+        res2 = sharded_search(sj)
+        assert sj.n_global == total and sj.first == sum(r + 2 for r in range(rank))
+        assert list(sj.entries["file"]) == [sum(q + 2 for q in range(r)) + r + 1 for r in range(world)]
+        assert np.allclose(sj.entries["maxSim"], [0.1 * (r + 1) + 0.01 * (r + 1) for r in range(world)])
         out_q.put((rank, res))
     finally:
         dist.destroy_process_group()
