@@ -605,11 +605,11 @@ int sgz_corr_scan(sgz_corr *job) {
     }
   }
   SGZ_TRY(job->simIn.alloc(n));
-  SGZ_TRY(job->boostIn.alloc(n));
+  if (!t2) SGZ_TRY(job->boostIn.alloc(n));   // the tensor-core scan writes no boost curve (BoostSrc, corr_fix.cuh)
   SGZ_TRY(job->dFileMax.alloc((size_t)std::max(db->numFiles(), 1)));
   if (job->hasOut) {
     SGZ_TRY(job->simOut.alloc(n));
-    SGZ_TRY(job->boostOut.alloc(n));
+    if (!t2) SGZ_TRY(job->boostOut.alloc(n));
     SGZ_TRY(job->dFileMaxOut.alloc((size_t)std::max(db->numFiles(), 1)));
   }
   const int tailIn = job->hasOut ? job->minPunchF : 0;
@@ -639,9 +639,9 @@ int sgz_corr_scan(sgz_corr *job) {
         if (end <= done && !last) continue;
         SGZ_CUDA(cudaStreamWaitEvent(ss, c.ev, 0));
         SGZ_TRY(db_ensure_planes(db, last ? -1 : c.uptoFrame, ss));
-        SGZ_TRY(run_scan_t2(job, job->qin, 0, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, done, end, ss, spare));
+        SGZ_TRY(run_scan_t2(job, job->qin, 0, tailIn, job->simIn.p, job->dFileMax.p, done, end, ss, spare));
         if (job->hasOut)
-          SGZ_TRY(run_scan_t2(job, job->qout, 1, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, done, end, ss, spare));
+          SGZ_TRY(run_scan_t2(job, job->qout, 1, 0, job->simOut.p, job->dFileMaxOut.p, done, end, ss, spare));
         done = std::max(done, end);
         continue;
       }
@@ -657,8 +657,8 @@ int sgz_corr_scan(sgz_corr *job) {
     }
     SGZ_CUDA(cudaStreamWaitEvent(ss, db->chunks.back().ev, 0));   // file table for the row maxima / later kernels
     if (t2 && db->usedFrames > 0) {
-      SGZ_TRY(run_fixup(job, job->qin, 0, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, ss));
-      if (job->hasOut) SGZ_TRY(run_fixup(job, job->qout, 1, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, ss));
+      SGZ_TRY(run_fixup(job, job->qin, 0, tailIn, job->simIn.p, job->dFileMax.p, ss));
+      if (job->hasOut) SGZ_TRY(run_fixup(job, job->qout, 1, 0, job->simOut.p, job->dFileMaxOut.p, ss));
     }
     if (job->hasOut && db->usedFrames > 0) {
       SGZ_TRY(job->rowMaxOut.alloc((size_t)db->usedFrames));
@@ -682,18 +682,18 @@ int sgz_corr_scan(sgz_corr *job) {
     if (t2) SGZ_CUDA(cudaMemsetAsync(job->dFixCount.p, 0, 2 * sizeof(uint32_t), ctx->stream));
     if (db->usedFrames > 0) {
       if (t2) {
-        SGZ_TRY(run_scan_t2(job, job->qin, 0, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, 0, job->numTilesT2,
+        SGZ_TRY(run_scan_t2(job, job->qin, 0, tailIn, job->simIn.p, job->dFileMax.p, 0, job->numTilesT2,
                             ctx->stream, 0));
-        SGZ_TRY(run_fixup(job, job->qin, 0, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, ctx->stream));
+        SGZ_TRY(run_fixup(job, job->qin, 0, tailIn, job->simIn.p, job->dFileMax.p, ctx->stream));
       } else if (tc) SGZ_TRY(run_scan_tc(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, ctx->stream));
       else
         SGZ_TRY(run_scan_one(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, 0, job->numTiles,
                              ctx->stream, 0));
       if (job->hasOut) {
         if (t2) {
-          SGZ_TRY(run_scan_t2(job, job->qout, 1, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, 0, job->numTilesT2,
+          SGZ_TRY(run_scan_t2(job, job->qout, 1, 0, job->simOut.p, job->dFileMaxOut.p, 0, job->numTilesT2,
                               ctx->stream, 0));
-          SGZ_TRY(run_fixup(job, job->qout, 1, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, ctx->stream));
+          SGZ_TRY(run_fixup(job, job->qout, 1, 0, job->simOut.p, job->dFileMaxOut.p, ctx->stream));
         } else if (tc) SGZ_TRY(run_scan_tc(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, ctx->stream));
         else
           SGZ_TRY(run_scan_one(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, 0, job->numTiles,
@@ -842,7 +842,7 @@ int sgz_corr_select(sgz_corr *job, int32_t *nRecords) {
       SGZ_CUDA(cudaMemcpyAsync(job->dFiles.p, files.data(), nj * sizeof(int32_t), cudaMemcpyHostToDevice,
                                ctx->stream));
       FillParams fp{};
-      fp.sim = job->simIn.p; fp.boost = job->boostIn.p; fp.fileStart = db->dFileStart.p;
+      fp.sim = job->simIn.p; fp.boost = boost_src(job, job->qin, job->boostIn.p); fp.fileStart = db->dFileStart.p;
       fp.files = job->dFiles.p; fp.numJobs = nj; fp.W = job->qin.W; fp.tailExtra = tail;
       fp.numPerFile = npf; fp.maxEntrySz = m; fp.minSpacing = job->cfg.minSpacing; fp.step = job->step;
       fp.entries = job->dEntries.p; fp.counts = job->dCounts.p;
@@ -905,7 +905,7 @@ int sgz_corr_select(sgz_corr *job, int32_t *nRecords) {
         SGZ_TRY(job->dRecs.alloc(cap));
         SGZ_CUDA(cudaMemsetAsync(job->dCounter.p, 0, sizeof(int), ctx->stream));
         CandParams cp{};
-        cp.sim = job->simIn.p; cp.boost = job->boostIn.p; cp.fileStart = db->dFileStart.p;
+        cp.sim = job->simIn.p; cp.boost = boost_src(job, job->qin, job->boostIn.p); cp.fileStart = db->dFileStart.p;
         cp.files = job->dFiles.p; cp.thresholds = job->dThr.p; cp.numJobs = nj; cp.W = job->qin.W;
         cp.tailExtra = tail; cp.fileBase = myLo; cp.out = job->dRecs.p; cp.cap = cap; cp.counter = job->dCounter.p;
         SGZ_TRY(ctx->begin_call());
@@ -1110,10 +1110,21 @@ int sgz_corr_curve(sgz_corr *job, int32_t which, int32_t file, int64_t first, in
               (long long)nValid);
   SGZ_TRY(job->ctx->bind());
   const float *s = (which == 0 ? job->simIn.p : job->simOut.p) + db->fileStart[file] + first;
-  const float *b = (which == 0 ? job->boostIn.p : job->boostOut.p) + db->fileStart[file] + first;
+  const float *bArr = which == 0 ? job->boostIn.p : job->boostOut.p;
   if (n > 0) {
     if (sim) SGZ_CUDA(cudaMemcpyAsync(sim, s, n * sizeof(float), cudaMemcpyDeviceToHost, job->ctx->stream));
-    if (boost) SGZ_CUDA(cudaMemcpyAsync(boost, b, n * sizeof(float), cudaMemcpyDeviceToHost, job->ctx->stream));
+    if (boost && bArr) {
+      SGZ_CUDA(cudaMemcpyAsync(boost, bArr + db->fileStart[file] + first, n * sizeof(float), cudaMemcpyDeviceToHost,
+                               job->ctx->stream));
+    } else if (boost) {   // tensor-core scan: the boost values are computed on demand
+      DevBuf<float> tmp;
+      SGZ_TRY(tmp.alloc((size_t)n));
+      k_boost_curve<<<(unsigned)ceil_div<int64_t>(n, 128), 128, 0, job->ctx->stream>>>(
+          boost_src(job, which == 0 ? job->qin : job->qout, nullptr), db->fileStart[file] + first, first, n, tmp.p);
+      SGZ_LAUNCH_CHECK(job->ctx);
+      SGZ_CUDA(cudaMemcpyAsync(boost, tmp.p, n * sizeof(float), cudaMemcpyDeviceToHost, job->ctx->stream));
+      SGZ_CUDA(cudaStreamSynchronize(job->ctx->stream));
+    }
     SGZ_CUDA(cudaStreamSynchronize(job->ctx->stream));
   }
   return SGZ_OK;

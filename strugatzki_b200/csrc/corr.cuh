@@ -331,12 +331,18 @@ inline int run_scan_tc(sgz_corr *job, PunchQuery &q, int tailExtra, float *sim, 
 
 // N = 64 tensor-core K1 over tiles [tileBegin, tileEnd) of 8192 offsets (corr_tc2.cuh); the planes of every frame the
 // tiles touch must have been enqueued on `st` (db_ensure_planes)
+// where the boost of an offset comes from: the curve a round-1 kernel wrote, or (tensor-core scan: arr = nullptr) the
+// loudness channel of the database
+inline BoostSrc boost_src(const sgz_corr *job, const PunchQuery &q, const float *arr) {
+  return BoostSrc{arr, job->db->dData.p, q.W, q.lnAvg};
+}
+
 constexpr uint32_t kFixCap = 1u << 20;
 
 // exact Double replay of the offsets the tensor-core scan flagged as ill-conditioned (corr_fix.cuh); `which` = 0 punch-in,
 // 1 punch-out curve.  Enqueued behind the K1 launches of that curve; costs one tiny launch when nothing was flagged.
-inline int run_fixup(sgz_corr *job, PunchQuery &q, int which, int tailExtra, float *sim, const float *boost,
-                     unsigned long long *fileMax, cudaStream_t st) {
+inline int run_fixup(sgz_corr *job, PunchQuery &q, int which, int tailExtra, float *sim, unsigned long long *fileMax,
+                     cudaStream_t st) {
   sgz_db *db = job->db;
   CorrFixParams fp{};
   fp.data = db->dData.p; fp.rowStride = db->capFrames; fp.usedFrames = db->usedFrames;
@@ -344,13 +350,13 @@ inline int run_fixup(sgz_corr *job, PunchQuery &q, int which, int tailExtra, flo
   fp.weight = q.weight; fp.maxBoost = job->cfg.maxBoost;
   fp.fileStart = db->dFileStart.p; fp.numFiles = db->numFiles(); fp.tailExtra = tailExtra;
   fp.list = job->dFixList[which].p; fp.count = job->dFixCount.p + which; fp.cap = kFixCap;
-  fp.sim = sim; fp.boost = boost; fp.fileMax = fileMax;
+  fp.sim = sim; fp.boost = boost_src(job, q, nullptr); fp.fileMax = fileMax;
   k_corr_fixup<<<(unsigned)job->ctx->smCount * 4, 128, 0, st>>>(fp);
   SGZ_LAUNCH_CHECK(job->ctx);
   return SGZ_OK;
 }
 
-inline int run_scan_t2(sgz_corr *job, PunchQuery &q, int which, int tailExtra, float *sim, float *boost,
+inline int run_scan_t2(sgz_corr *job, PunchQuery &q, int which, int tailExtra, float *sim,
                        unsigned long long *fileMax, int64_t tileBegin, int64_t tileEnd, cudaStream_t st, int spareSMs) {
   if (tileEnd <= tileBegin) return SGZ_OK;
   sgz_db *db = job->db;
@@ -364,22 +370,28 @@ inline int run_scan_t2(sgz_corr *job, PunchQuery &q, int which, int tailExtra, f
   tp.taps = q.dT2Taps.p;
   {
     T2Eval &E = tp.ev;
-    E.invW = 1.0 / (double)q.W; E.invNS = 1.0 / ((double)(db->numCh - 1) * (double)q.W);
-    E.negEps = -2e-3;
-    E.cT = (float)(E.invW / q.stdT); E.cS = (float)(E.invNS / q.stdS);
+    E.nT = (double)q.W; E.nS = (double)(db->numCh - 1) * (double)q.W;
+    E.negEpsT = -2e-3 * E.nT; E.negEpsS = -2e-3 * E.nS;
+    // boost = exp((lnAvgIn - ln avg) / 0.6) <= maxBoost  <=>  avg >= exp(lnAvgIn - 0.6 ln maxBoost); a NaN threshold
+    // (maxBoost < 0 or NaN) lets no offset pass, like the reference's comparison
+    const double avgMin = exp(q.lnAvg - 0.6 * log((double)job->cfg.maxBoost));
+    E.gateT1 = avgMin * E.nT;
+    E.invNT = (float)(1.0 / E.nT); E.invNS = (float)(1.0 / E.nS);
+    E.invNT2 = (float)(1.0 / (E.nT * E.nT)); E.invNS2 = (float)(1.0 / (E.nS * E.nS));
+    E.cT = (float)(1.0 / (E.nT * q.stdT)); E.cS = (float)(1.0 / (E.nS * q.stdS));
     E.kT = (float)q.rhoT * E.cT; E.kS = (float)q.rhoS * E.cS;
-    E.l2In = (float)(q.lnAvg * 1.4426950408889634);
-    E.wT = q.weight; E.wS = 1.0f - q.weight; E.maxBoost = job->cfg.maxBoost;
+    E.wT = q.weight; E.wS = 1.0f - q.weight;
     E.useT = q.weight > 0.f; E.useS = q.weight < 1.f;
   }
   tp.fileStart = db->dFileStart.p; tp.tileFile = job->dTileFileT2.p; tp.numFiles = db->numFiles(); tp.tailExtra = tailExtra;
   tp.tileBegin = tileBegin; tp.tileEnd = tileEnd;
-  tp.sim = sim; tp.boost = boost; tp.fileMax = fileMax;
+  tp.sim = sim; tp.fileMax = fileMax;
   tp.fixList = job->dFixList[which].p; tp.fixCount = job->dFixCount.p + which; tp.fixCap = kFixCap;
   tp.smemMax = (int)ctx->smemOptin;
   {
     static const int ahead = getenv("SGZ_T2_AHEAD") ? atoi(getenv("SGZ_T2_AHEAD")) : kT2Ahead;   // developer knob
     tp.ahead = ahead;
+    tp.dbg = getenv("SGZ_T2_DBG") ? atoi(getenv("SGZ_T2_DBG")) : 0;
   }
   const bool prof = getenv("SGZ_CORR_TC_PROF") != nullptr;   // developer probe: cycles per role and phase
   auto kern = prof ? k_corr_tc2<true> : k_corr_tc2<false>;

@@ -17,6 +17,29 @@ namespace sgz {
 
 constexpr uint32_t kFixSentinel = 0x7fc00badu;   // quiet NaN with a payload: "ill-conditioned, to be re-evaluated"
 
+// calcBoost (FeatureCorrelationImpl.scala:73-78) of the window that starts at global frame g (file-local offset tl).
+// The tensor-core K1 only evaluates the gate `boost <= maxBoost` per offset (a comparison of the loudness sum); the boost
+// VALUE is needed for the handful of offsets that end up in a result or are asked for, and is computed here like the
+// reference does: MathUtil.avg over ring positions 0 .. W-1 in Double -> Float, then exp((ln avgIn - ln avg) / 0.6).
+// The round-1 kernels still write a boost curve (`arr`).
+struct BoostSrc {
+  const float *arr;         // boost curve of the scan, or nullptr: compute from the loudness channel
+  const float2 *data;       // pair row 0 holds (loudness, first spectral channel)
+  int W;
+  double lnAvgIn;
+  __device__ float at(int64_t g, int64_t tl) const {
+    if (arr) return arr[g];
+    const int r0 = (int)(tl % W);
+    double sum = 0.0;
+    for (int pos = 0; pos < W; pos++) {
+      const int i = pos >= r0 ? pos - r0 : pos - r0 + W;
+      sum = __dadd_rn(sum, (double)data[g + i].x);
+    }
+    const float avg = (float)__ddiv_rn(sum, (double)W);
+    return (float)exp(__ddiv_rn(__dsub_rn(lnAvgIn, log((double)avg)), 0.6));
+  }
+};
+
 struct CorrFixParams {
   const float2 *data;       // normalised pair rows [numPairs][rowStride]
   int64_t rowStride, usedFrames;
@@ -30,7 +53,7 @@ struct CorrFixParams {
   const uint32_t *count;    // number of flagged offsets; > cap = the list overflowed: scan the curve for sentinels
   uint32_t cap;
   float *sim;
-  const float *boost;       // K1's boost (the loudness average is well conditioned)
+  BoostSrc boost;
   unsigned long long *fileMax;
 };
 
@@ -80,7 +103,7 @@ __device__ void fix_one(const CorrFixParams &p, int64_t g) {
     if (p.fileStart[mid] <= g) lo = mid; else hi = mid;
   }
   const int64_t tl = g - p.fileStart[lo];
-  const float boost = p.boost[g];
+  const float boost = p.boost.at(g, tl);
   float sim = 0.f;
   if (boost <= p.maxBoost) {                 // :199 (NaN boost: the comparison is false like the reference's)
     const float temporal = p.weight > 0.f ? fix_correlate(p, g, tl, 0, 1, p.stdT) : 0.f;
@@ -93,6 +116,12 @@ __device__ void fix_one(const CorrFixParams &p, int64_t g) {
                                    (unsigned long long)(0xffffffffu - (uint32_t)tl);
     atomicMax(p.fileMax + lo, key);
   }
+}
+
+// boost values of n consecutive offsets of one file (sgz_corr_curve)
+__global__ void k_boost_curve(BoostSrc b, int64_t g0, int64_t tl0, int64_t n, float *__restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = b.at(g0 + i, tl0 + i);
 }
 
 __global__ void __launch_bounds__(128) k_corr_fixup(const CorrFixParams p) {

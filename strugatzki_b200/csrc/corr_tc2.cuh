@@ -195,17 +195,27 @@ __global__ void __launch_bounds__(256) k_db_planes(const float2 *__restrict__ da
 // the kernel
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float t2_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float t2_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float t2_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// Double -> Float by truncation with integer instructions (F2F.F32.F64 and MUFU share the 16-lane conversion unit, and an
+// offset needed eight of them): for finite values of Float's normal range, 2^-23 relative; smaller magnitudes give 0.
+// Used for quantities whose last bit does not matter here (a variance on its way into rsqrt, a mean in a tiny correction).
+__device__ __forceinline__ float t2_d2f(double d) {
+  const uint32_t hi = (uint32_t)__double2hiint(d), lo = (uint32_t)__double2loint(d);
+  const uint32_t a = hi & 0x7fffffffu;
+  const uint32_t m = __funnelshift_l(lo, a - 0x38000000u, 3);
+  return __uint_as_float(a >= 0x38100000u ? (m | (hi & 0x80000000u)) : 0u);
+}
 
 // constants of one evaluated offset, prepared on the host (kernel parameters = constant bank operands)
 struct T2Eval {
-  double invW, invNS;       // 1 / W, 1 / ((numCh - 1) W)
-  double negEps;            // -2e-3: a window whose variance is below 2e-3 of its mean square is re-evaluated exactly (corr_fix.cuh)
-  float cT, cS;             // 1 / (W std_a) per group, (numCh - 1) folded into cS
+  double nT, nS;            // cells of a window per group: W, (numCh - 1) W
+  double negEpsT, negEpsS;  // -2e-3 n: a window whose variance is below 2e-3 of its mean square is re-evaluated exactly
+  double gateT1;            // boost <= maxBoost  <=>  loudness sum of the window >= gateT1 (calcBoost is monotone)
+  float invNT, invNS;       // 1 / n
+  float invNT2, invNS2;     // 1 / n^2
+  float cT, cS;             // 1 / (n std_a) per group
   float kT, kS;             // rho * c: correction for the rounded taps not summing to exactly zero
-  float l2In;               // log2 of the query's average loudness
-  float wT, wS, maxBoost;
+  float wT, wS;
   int useT, useS;
 };
 
@@ -224,13 +234,14 @@ struct CorrT2Params {
   const int32_t *tileFile;      // [numTiles + 1] file that holds frame 8192 * tile (clamped to the last file)
   int numFiles, tailExtra;
   int64_t tileBegin, tileEnd;
-  float *sim, *boost;
+  float *sim;
   unsigned long long *fileMax;
   uint32_t *fixList, *fixCount; // offsets whose windows are ill-conditioned (corr_fix.cuh)
   uint32_t fixCap;
   long long *prof;              // SGZ_CORR_TC_PROF: per CTA 24 cycle counters (k_corr_tc2<true>), or nullptr
   int smemMax;                  // the geometry (ring depths) is a function of (W, shared memory limit)
   int ahead;                    // channels between the L2 prefetch of a signal stage and its bulk copy (0: no prefetch)
+  int dbg;                      // developer knob (SGZ_T2_DBG, profiling build only): 1 = no MMAs, 2 = no per-offset work, 4 = no curve stores, 8 = no per-frame loads, 16 = no window slides, 32 = no evaluation
 };
 
 // pull a range into L2 without a destination: the ring in shared memory then waits for L2, not for HBM, so the HBM latency
@@ -248,29 +259,26 @@ __device__ __forceinline__ bool t2_test(uint64_t *bar, uint32_t parity) {   // n
   return done != 0;
 }
 
-// one evaluated offset: window sums -> boost and sim (FeatureCorrelationImpl.scala:73-78,198-210); branch free so that the
-// compiler can interleave the offsets of a thread
-__device__ __forceinline__ void t2_eval(const T2Eval &E, const D4 &win, float accT, float accS, float &sim, float &boost) {
+// one evaluated offset: window sums -> sim (FeatureCorrelationImpl.scala:73-78,198-210); branch free so that the compiler
+// can interleave the offsets of a thread.  n^2 var = n sum(x^2) - (sum x)^2 in FP64; the boost itself is not needed here,
+// only its gate (the few offsets that end up in a result get their boost from corr_boost, corr_fix.cuh)
+__device__ __forceinline__ float t2_eval(const T2Eval &E, const D4 &win, float accT, float accS) {
   const float qnan = __uint_as_float(kFixSentinel);
-  const double mT = win.t1 * E.invW;
-  const float mTf = (float)mT;                                             // MathUtil.avg -> Float
-  boost = t2_ex2((E.l2In - t2_lg2(mTf)) * (1.0f / 0.6f));                  // calcBoost
-  const double qT = win.t2 * E.invW;
-  const double varT = fma(-mT, mT, qT);
-  const float crT = fmaf(accT, E.cT, -mTf * E.kT);                         // (acc - mean_b * rho) / (W std_a)
-  float temporal = crT * t2_rsqrt((float)varT);
-  temporal = __double2hiint(fma(qT, E.negEps, varT)) > 0 ? temporal : qnan;   // var > 2e-3 q (positive and not NaN)
+  const double vT = fma(win.t2, E.nT, -(win.t1 * win.t1));
+  const float mT = t2_d2f(win.t1) * E.invNT;
+  const float crT = fmaf(accT, E.cT, -mT * E.kT);                          // (acc - mean_b * rho) / (W std_a)
+  float temporal = crT * t2_rsqrt(t2_d2f(vT) * E.invNT2);
+  temporal = __double2hiint(fma(win.t2, E.negEpsT, vT)) > 0 ? temporal : qnan;   // var > 2e-3 E[x^2] (positive, not NaN)
   temporal = E.useT ? temporal : 0.f;
-  const double mS = win.s1 * E.invNS;
-  const double qS = win.s2 * E.invNS;
-  const double varS = fma(-mS, mS, qS);
-  const float crS = fmaf(accS, E.cS, -(float)mS * E.kS);
-  float spectral = crS * t2_rsqrt((float)varS);
-  spectral = __double2hiint(fma(qS, E.negEps, varS)) > 0 ? spectral : qnan;
+  const double vS = fma(win.s2, E.nS, -(win.s1 * win.s1));
+  const float mS = t2_d2f(win.s1) * E.invNS;
+  const float crS = fmaf(accS, E.cS, -mS * E.kS);
+  float spectral = crS * t2_rsqrt(t2_d2f(vS) * E.invNS2);
+  spectral = __double2hiint(fma(win.s2, E.negEpsS, vS)) > 0 ? spectral : qnan;
   spectral = E.useS ? spectral : 0.f;
   const float blend = __fadd_rn(__fmul_rn(temporal, E.wT), __fmul_rn(spectral, E.wS));
   // an ill-conditioned group makes the blend NaN whatever the other group is; it is marked for the exact re-evaluation
-  sim = boost <= E.maxBoost ? (blend == blend ? blend : qnan) : 0.f;
+  return win.t1 >= E.gateT1 ? (blend == blend ? blend : qnan) : 0.f;
 }
 
 // warp 0: producer (bulk copies), warp 1: MMA issuer, warps 2-3: idle (they complete the first warpgroup, which hands most
@@ -384,6 +392,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
           // a1 t2 share the A operand through the collector
           uint64_t d1 = aHi, d2 = aLo, b1 = tHi, b2 = tLo;
           for (int k = 0; k < G.KS; k++, d1 += 2, d2 += 2, b1 += 32, b2 += 32) {
+            if ((kProf && p.dbg & 1)) break;
             tc_mma_fill(dMain, d1, b1, idesc, accMain | (uint32_t)(k > 0));
             tc_mma_lastuse(dCorr, d1, b2, idesc, accCorr | (uint32_t)(k > 0));
             tc_mma(dCorr, d2, b1, idesc, 1);
@@ -523,29 +532,40 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
       const uint32_t oNew = (uint32_t)((tile + (rowN >> 7)) * (int64_t)kT2Tile + (colN << 7) + (rowN & 127));
       const int eWrap = 64 - colN;
       const uint32_t dWrap = (uint32_t)(((rowN & 127) == 127 ? kT2Tile - 127 : 1) - (64 << 7));
-#pragma unroll
-      for (int blk = 0; blk < 4; blk++) {
-        // the frames that leave / enter the window during these four slides
-        uint2 oa[4], na[4];
-        uint32_t ob2[4], nb2[4];
+      // the frames that leave / enter the window during four slides, loaded one block of four AHEAD: the loads of block
+      // b + 1 are in flight while block b is evaluated (the latency of these loads was the largest stall of the epilogue)
+      uint2 oaN[4], naN[4];
+      uint32_t ob2N[4], nb2N[4];
+      auto load_block = [&](int blk) {
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const int jj = 4 * blk + e;
-          if (jj < 15) {
-            oa[e] = __ldg(p.sideA + (oOld + (uint32_t)(jj << 7))); ob2[e] = __ldg(p.sideB + (oOld + (uint32_t)(jj << 7)));
+          if ((kProf && p.dbg & 8)) { oaN[e] = make_uint2(0x3fe00000u + jj, 0x40100000u); naN[e] = oaN[e]; ob2N[e] = nb2N[e] = 0x40000000u; }
+          else if (jj < 15) {
+            oaN[e] = __ldg(p.sideA + (oOld + (uint32_t)(jj << 7))); ob2N[e] = __ldg(p.sideB + (oOld + (uint32_t)(jj << 7)));
             const uint32_t d = oNew + (uint32_t)(jj << 7) + (jj >= eWrap ? dWrap : 0u);
-            na[e] = __ldg(p.sideA + d); nb2[e] = __ldg(p.sideB + d);
+            naN[e] = __ldg(p.sideA + d); nb2N[e] = __ldg(p.sideB + d);
           }
         }
-        float simv[4], boostv[4];
+      };
+      if (!((kProf && p.dbg & 2))) load_block(0);
+#pragma unroll
+      for (int blk = 0; blk < 4; blk++) {
+        if ((kProf && p.dbg & 2)) break;
+        uint2 oa[4], na[4];
+        uint32_t ob2[4], nb2[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) { oa[e] = oaN[e]; na[e] = naN[e]; ob2[e] = ob2N[e]; nb2[e] = nb2N[e]; }
+        if (blk < 3) load_block(blk + 1);
+        float simv[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const int jj = 4 * blk + e;           // offset inside the thread's run; accumulator column 15 - jj of its group
-          t2_eval(E, win, accT[15 - jj], accS[15 - jj], simv[e], boostv[e]);
-          if (jj < 15) {
-            const double bo = t2_dbl(oa[e].x), bn = t2_dbl(na[e].x);
-            win.t1 += bn - bo;
-            win.t2 += fma(bn, bn, -(bo * bo));
+          simv[e] = ((kProf && p.dbg & 32)) ? accT[15 - jj] + accS[15 - jj] + (float)win.t1 : t2_eval(E, win, accT[15 - jj], accS[15 - jj]);
+          if (jj < 15 && !((kProf && p.dbg & 16))) {
+            const double bo = t2_dbl(oa[e].x), bn = t2_dbl(na[e].x), d = bn - bo;
+            win.t1 += d;
+            win.t2 = fma(d, bn + bo, win.t2);
             win.s1 += t2_dbl(na[e].y) - t2_dbl(oa[e].y);
             win.s2 += t2_dbl(nb2[e]) - t2_dbl(ob2[e]);
           }
@@ -570,10 +590,10 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
               fEnd = p.fileStart[f + 1];
             }
             const int64_t tl = g - fStart;
-            float sv = qnan, bv = qnan;
+            float sv = qnan;
 #pragma unroll
-            for (int kk = 0; kk < 4; kk++) if (kk == e) { sv = simv[kk]; bv = boostv[kk]; }
-            if (!(g < p.usedFrames && tl < (fEnd - fStart) - p.tailExtra - W + 1)) { sv = qnan; bv = qnan; }
+            for (int kk = 0; kk < 4; kk++) if (kk == e) sv = simv[kk];
+            if (!(g < p.usedFrames && tl < (fEnd - fStart) - p.tailExtra - W + 1)) sv = qnan;
             else if (sv == sv) {
               const unsigned long long key = ((unsigned long long)float_order_key(sv) << 32) |
                                              (unsigned long long)(0xffffffffu - (uint32_t)tl);
@@ -583,15 +603,32 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
               if (slot < p.fixCap) p.fixList[slot] = (uint32_t)g;
             }
 #pragma unroll
-            for (int kk = 0; kk < 4; kk++) if (kk == e) { simv[kk] = sv; boostv[kk] = bv; }
+            for (int kk = 0; kk < 4; kk++) if (kk == e) simv[kk] = sv;
           }
         }
-        *reinterpret_cast<float4 *>(p.sim + g0 + 4 * blk) = make_float4(simv[0], simv[1], simv[2], simv[3]);
-        *reinterpret_cast<float4 *>(p.boost + g0 + 4 * blk) = make_float4(boostv[0], boostv[1], boostv[2], boostv[3]);
+        if (kProf && (p.dbg & 4)) {     // no stores: keep the values alive through a branch that is never taken
+          if (simv[0] + simv[1] + simv[2] + simv[3] == 123.456f) p.sim[0] = 1.f;
+        } else {
+          *reinterpret_cast<float4 *>(p.sim + g0 + 4 * blk) = make_float4(simv[0], simv[1], simv[2], simv[3]);
+        }
       }
       if (bestJ >= 0)
         best = ((unsigned long long)float_order_key(bestS) << 32) | (unsigned long long)(0xffffffffu - (tl0 + (uint32_t)bestJ));
-      if (best != 0ull && p.fileMax) atomicMax(p.fileMax + f, best);
+      // one atomic per WARP where its 32 runs lie in one file (almost always): 512 atomics per tile on the same 8 bytes --
+      // and the neighbouring tiles on the same file -- serialise in L2 (0.28 ms of a 0.94 ms scan, tools/t2_ablate.py)
+      if (p.fileMax) {
+        const int f0 = __shfl_sync(0xffffffffu, f, 0);
+        if (__all_sync(0xffffffffu, f == f0)) {
+#pragma unroll
+          for (int d = 16; d >= 1; d >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
+            best = o > best ? o : best;
+          }
+          if (lane == 0 && best != 0ull) atomicMax(p.fileMax + f0, best);
+        } else if (best != 0ull) {
+          atomicMax(p.fileMax + f, best);
+        }
+      }
       if (kProf) eMain += clock64() - tE;
     }
     if (kProf && p.prof && ew == 0 && lane == 0) {

@@ -24,7 +24,8 @@
 namespace sgz {
 
 struct FillPoParams {
-  const float *simIn, *boostIn, *simOut, *boostOut, *rowMax;
+  const float *simIn, *simOut, *rowMax;
+  BoostSrc boostIn, boostOut;
   const int64_t *fileStart;
   const int32_t *files;
   int numJobs;
@@ -364,8 +365,8 @@ __global__ void __launch_bounds__(kFillThreads) k_replay_fill_po(const FillPoPar
     p.meta[job] = make_float4(metaM, metaV, __int_as_float(metaRow), 0.f);
     for (int i = 0; i < mc.n; i++) {
       EntryRec e = ent[i];
-      e.boostIn = p.boostIn[fs + e.piOff];
-      e.boostOut = p.boostOut[fs + e.stopOff];
+      e.boostIn = p.boostIn.at(fs + e.piOff, e.piOff);
+      e.boostOut = p.boostOut.at(fs + e.stopOff, e.stopOff);
       gEnt[i] = e;
     }
   }
@@ -375,7 +376,8 @@ __global__ void __launch_bounds__(kFillThreads) k_replay_fill_po(const FillPoPar
 }
 
 struct CandPoParams {
-  const float *simIn, *boostIn, *simOut, *boostOut, *rowMax;
+  const float *simIn, *simOut, *rowMax;
+  BoostSrc boostIn, boostOut;
   const int64_t *fileStart;
   const int32_t *files;
   const float *thresholds;
@@ -444,8 +446,8 @@ __global__ void k_candidates_po(const CandPoParams p) {
         const unsigned mask = __ballot_sync(full, hit);
         if (mask == 0u) continue;
         const float s = hit ? sim_of_prod(prod) : 0.f;
-        sgz_record rec{p.fileBase + f, 0, (int32_t)row, (int32_t)po, s, hit ? p.boostIn[fs + row] : 0.f,
-                       hit ? p.boostOut[fs + po] : 0.f, __float_as_int(inS)};
+        sgz_record rec{p.fileBase + f, 0, (int32_t)row, (int32_t)po, s, hit ? p.boostIn.at(fs + row, row) : 0.f,
+                       hit ? p.boostOut.at(fs + po, po) : 0.f, __float_as_int(inS)};
         emit_record(p, mask, lane, hit, rec);
       }
     }
@@ -478,7 +480,8 @@ inline int corr_select_punchout(sgz_corr *job, int32_t *nRecords) {
       SGZ_TRY(job->dEntries.alloc((size_t)nj * (npf + 1)));
       SGZ_CUDA(cudaMemcpyAsync(job->dFiles.p, files.data(), nj * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
       FillPoParams fp{};
-      fp.simIn = job->simIn.p; fp.boostIn = job->boostIn.p; fp.simOut = job->simOut.p; fp.boostOut = job->boostOut.p;
+      fp.simIn = job->simIn.p; fp.simOut = job->simOut.p;
+      fp.boostIn = boost_src(job, job->qin, job->boostIn.p); fp.boostOut = boost_src(job, job->qout, job->boostOut.p);
       fp.rowMax = job->rowMaxOut.p;
       fp.fileStart = db->dFileStart.p; fp.files = job->dFiles.p; fp.numJobs = nj;
       fp.Win = job->qin.W; fp.Wout = job->qout.W; fp.minPunchF = job->minPunchF; fp.maxPunchF = job->maxPunchF;
@@ -558,7 +561,8 @@ inline int corr_select_punchout(sgz_corr *job, int32_t *nRecords) {
         SGZ_TRY(job->dRecs.alloc(cap));
         SGZ_CUDA(cudaMemsetAsync(job->dCounter.p, 0, sizeof(int), ctx->stream));
         CandPoParams cp{};
-        cp.simIn = job->simIn.p; cp.boostIn = job->boostIn.p; cp.simOut = job->simOut.p; cp.boostOut = job->boostOut.p;
+        cp.simIn = job->simIn.p; cp.simOut = job->simOut.p;
+        cp.boostIn = boost_src(job, job->qin, job->boostIn.p); cp.boostOut = boost_src(job, job->qout, job->boostOut.p);
         cp.rowMax = job->rowMaxOut.p;
         cp.fileStart = db->dFileStart.p; cp.files = job->dFiles.p; cp.thresholds = job->dThr.p; cp.numJobs = nj;
         cp.Win = job->qin.W; cp.Wout = job->qout.W; cp.minPunchF = job->minPunchF; cp.maxPunchF = job->maxPunchF;

@@ -12,6 +12,7 @@
 //     pre-filter; the GPU emits only those candidates and the tiny ordered replay runs on them.
 #pragma once
 #include "common.cuh"
+#include "corr_fix.cuh"
 
 namespace sgz {
 
@@ -105,7 +106,7 @@ struct Machine {
 // ---------------------------------------------------------------------------------------------
 struct FillParams {
   const float *sim;
-  const float *boost;
+  BoostSrc boost;
   const int64_t *fileStart;
   const int32_t *files;     // local file indices to replay [numJobs]
   int numJobs;
@@ -139,7 +140,6 @@ __global__ void __launch_bounds__(kFillPiThreads) k_replay_fill(const FillParams
   const int64_t fs = p.fileStart[f];
   const int64_t nValid = (p.fileStart[f + 1] - fs) - p.tailExtra - p.W + 1;
   const float *sim = p.sim + fs;
-  const float *boost = p.boost + fs;
 
   Machine mc;
   mc.reset(p.entries + (size_t)job * (p.numPerFile + 1), p.numPerFile, p.maxEntrySz, 0, 0.f, p.minSpacing, p.step);
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kFillPiThreads) k_replay_fill(const FillParams
         const float ss = __shfl_sync(full, s, hit);
         const int64_t ts = chunk + 32 * g + hit;
         if (lane == 0) {
-          EntryRec m{ss, (int32_t)ts, (int32_t)(ts + p.W), boost[ts], 1.0f};
+          EntryRec m{ss, (int32_t)ts, (int32_t)(ts + p.W), 0.f, 1.0f};   // boost: filled in for the survivors
           mc.add(m);
           hs = mc.has_space();
           low = mc.lowest();
@@ -203,6 +203,12 @@ __global__ void __launch_bounds__(kFillPiThreads) k_replay_fill(const FillParams
     if (lane == 0) { sLow = low; sHs = hs ? 1 : 0; }
   }
   if (threadIdx.x == 0) p.counts[job] = mc.n;
+  if (warp == 0) {          // addMatch does not look at the boosts: computed for the entries that are left
+    EntryRec *e = p.entries + (size_t)job * (p.numPerFile + 1);
+    const int n = __shfl_sync(full, mc.n, 0);      // the machine lives in lane 0
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) e[i].boostIn = p.boost.at(fs + e[i].piOff, e[i].piOff);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -211,7 +217,7 @@ __global__ void __launch_bounds__(kFillPiThreads) k_replay_fill(const FillParams
 // ---------------------------------------------------------------------------------------------
 struct CandParams {
   const float *sim;
-  const float *boost;
+  BoostSrc boost;
   const int64_t *fileStart;
   const int32_t *files;       // local file indices [numJobs]
   const float *thresholds;    // [numJobs]
@@ -250,7 +256,7 @@ __global__ void k_candidates(const CandParams p) {
         r.piOff = (int32_t)t;
         r.poOff = -1;
         r.sim = s;
-        r.boostIn = p.boost[fs + t];
+        r.boostIn = p.boost.at(fs + t, t);
         r.boostOut = 1.0f;
         r.aux = 0;
         p.out[slot] = r;
