@@ -571,19 +571,13 @@ int sgz_corr_scan(sgz_corr *job) {
   if (t2) {
     n = std::max(n, (size_t)job->numTilesT2 * kT2Tile);
     if (!job->dTileFileT2.p) {
-      std::vector<int32_t> tf((size_t)job->numTilesT2 + 1);
-      int f = 0;
-      const int nf = db->numFiles();
-      for (int64_t t = 0; t <= job->numTilesT2; t++) {
-        const int64_t g = std::min<int64_t>(t * kT2Tile, std::max<int64_t>(db->usedFrames - 1, 0));
-        while (f + 1 < nf && db->fileStart[f + 1] <= g) f++;
-        tf[(size_t)t] = f;
-      }
-      SGZ_TRY(job->dTileFileT2.alloc(tf.size()));
-      // small pageable copy on the scan stream: inline, does not queue behind uploads in flight
-      SGZ_CUDA(cudaMemcpyAsync(job->dTileFileT2.p, tf.data(), tf.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
-                               ctx->scanStream));
-      SGZ_CUDA(cudaStreamSynchronize(ctx->scanStream));
+      // built on the device from the file table (151 KB for the 1000 h database: a host copy of that size would queue
+      // behind the uploads of a streaming scan)
+      SGZ_TRY(job->dTileFileT2.alloc((size_t)job->numTilesT2 + 1));
+      cudaStream_t tst = db->chunks.empty() ? ctx->stream : ctx->scanStream;
+      k_t2_tile_files<<<(unsigned)ceil_div<int64_t>(job->numTilesT2 + 1, 256), 256, 0, tst>>>(
+          db->dFileStart.p, db->numFiles(), db->usedFrames, job->numTilesT2, job->dTileFileT2.p);
+      SGZ_LAUNCH_CHECK(ctx);
     }
     SGZ_TRY(job->dFixCount.alloc(2));
     SGZ_TRY(job->dFixList[0].alloc(kFixCap));

@@ -18,8 +18,9 @@ struct PunchQuery {
   std::vector<uint16_t> tcTaps;
   DevBuf<uint16_t> dTcTaps;    // tensor-core path: hi/lo Toeplitz atoms (corr_tc.cuh), empty when not applicable
   DevBuf<unsigned char> dT2Taps;   // N = 64 tensor-core path (corr_tc2.cuh), empty when not applicable
-  std::vector<double> ac;          // centred query [numCh][W] in Double: a[c][i] + (-group mean), MathUtil.correlate's factor
-  DevBuf<double> dAc;              // ... for the exact re-evaluation of ill-conditioned windows (corr_fix.cuh)
+  DevBuf<float> dA;                // normalised query [numCh][W]
+  DevBuf<double> dAc;              // centred query in Double: a[c][i] + (-group mean), MathUtil.correlate's first factor, for
+                                   // the exact re-evaluation of ill-conditioned windows (corr_fix.cuh)
 };
 
 struct sgz_corr {
@@ -198,11 +199,11 @@ inline int prepare_query(const sgz_db *db, const float *inputPlanar /*[numCh][in
     SGZ_CUDA(cudaMemcpyAsync(q.dTcTaps.p, q.tcTaps.data(), q.tcTaps.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
   }
   if (t2_applicable(db->ctx, numCh, W)) {
-    q.ac.resize((size_t)numCh * W);
-    for (int c = 0; c < numCh; c++)
-      for (int i = 0; i < W; i++) q.ac[(size_t)c * W + i] = (double)a[(size_t)c * W + i] + (-(c == 0 ? meanT : meanS));
-    SGZ_TRY(q.dAc.alloc(q.ac.size()));
-    SGZ_CUDA(cudaMemcpyAsync(q.dAc.p, q.ac.data(), q.ac.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    SGZ_TRY(q.dA.alloc(a.size()));
+    SGZ_TRY(q.dAc.alloc(a.size()));
+    SGZ_CUDA(cudaMemcpyAsync(q.dA.p, a.data(), a.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    k_t2_query<<<ceil_div(numCh * W, 256), 256, 0, st>>>(q.dA.p, numCh, W, -meanT, -meanS, q.dAc.p);
+    SGZ_LAUNCH_CHECK(db->ctx);
     const T2Geom g = t2_geom(W, db->ctx->smemOptin);
     SGZ_TRY(q.dT2Taps.alloc((size_t)numCh * g.tapsBytes));
     k_t2_taps<<<numCh, 256, 0, st>>>(reinterpret_cast<const float2 *>(q.dTaps.p), numCh, q.Wq, W, q.dT2Taps.p);

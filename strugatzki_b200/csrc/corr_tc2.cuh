@@ -28,7 +28,7 @@ namespace sgz {
 
 constexpr int kT2P = 64, kT2M = 128, kT2Tile = kT2P * kT2M;
 constexpr int kT2Mains = 5;               // spectral main accumulators
-constexpr int kT2Ahead = 7;               // channels between the L2 prefetch of a signal stage and its bulk copy
+constexpr int kT2Ahead = 0;               // channels between an L2 prefetch of a signal stage and its bulk copy: 0 = none (measured: no gain, the ring itself keeps the bytes in flight)
 constexpr int kT2EpiWarps = 16, kT2Threads = (4 + kT2EpiWarps) * 32;
 
 struct T2Geom {
@@ -104,6 +104,29 @@ __global__ void k_t2_taps(const float2 *__restrict__ pairTaps, int numCh, int Wq
                            (size_t)(((kk >> 3) ^ ((cc >> 2) & 1)) << 4) + (size_t)(kk & 7) * 2;
     *reinterpret_cast<__half *>(out + byteOff) = v;
   }
+}
+
+// centred query in Double for the exact re-evaluation (corr_fix.cuh), built on the device from the normalised Float query
+// (same reason as the taps image: only a few KB cross PCIe at job creation): ac[c][i] = (double)a[c][i] + (-group mean)
+__global__ void k_t2_query(const float *__restrict__ a, int numCh, int W, double negMeanT, double negMeanS, double *__restrict__ ac) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < numCh * W) ac[i] = __dadd_rn((double)a[i], i < W ? negMeanT : negMeanS);
+}
+
+// tileFile[t] = file that holds frame min(8192 t, usedFrames - 1) (the file table is on the device already)
+__global__ void k_t2_tile_files(const int64_t *__restrict__ fileStart, int numFiles, int64_t usedFrames, int64_t numTiles,
+                                int32_t *__restrict__ tileFile) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t > numTiles) return;
+  int64_t g = t * kT2Tile;
+  if (g > usedFrames - 1) g = usedFrames - 1;
+  if (g < 0) g = 0;
+  int lo = 0, hi = numFiles;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (fileStart[mid] <= g) lo = mid; else hi = mid;
+  }
+  tileFile[t] = lo;
 }
 
 // ---------------------------------------------------------------------------------------------
