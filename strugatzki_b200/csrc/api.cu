@@ -212,12 +212,51 @@ static int db_mark_chunk(sgz_db *db, int64_t uptoFrame) {
   return SGZ_OK;
 }
 
-static int db_commit_file(sgz_db *db, int64_t nFrames) {
+static int db_commit_file(sgz_db *db, int64_t nFrames, bool mark = true) {
   db->usedFrames += nFrames;
   db->fileStart.push_back(db->usedFrames);
   // every writer of the pair rows runs on ctx->stream, so an event recorded now covers all frames so far
-  if (db->usedFrames - db->chunkMark >= chunk_frames()) SGZ_TRY(db_mark_chunk(db, db->usedFrames));
+  if (mark && db->usedFrames - db->chunkMark >= chunk_frames()) SGZ_TRY(db_mark_chunk(db, db->usedFrames));
   return db->numFiles() - 1;
+}
+
+// one host -> device copy + the prepare kernels of the files in it
+static int db_upload(sgz_db *db, const void *host, size_t bytes, const sgz_db::Pend *files, int nFiles, bool waitCopy) {
+  const int s = db->stageIdx;
+  db->stageIdx = (s + 1) % sgz_db::kStageSlots;
+  if (db->dStage[s].n < bytes) {
+    // staging buffer may still be read by an earlier prepare kernel
+    if (db->stageUsed[s]) SGZ_CUDA(cudaEventSynchronize(db->stageFree[s]));
+    SGZ_TRY(db->dStage[s].alloc(bytes + bytes / 4));
+    db->stageUsed[s] = false;
+  }
+  if (db->stageUsed[s]) SGZ_CUDA(cudaStreamWaitEvent(db->copyStream, db->stageFree[s], 0));
+  SGZ_CUDA(cudaMemcpyAsync(db->dStage[s].p, host, bytes, cudaMemcpyHostToDevice, db->copyStream));
+  SGZ_CUDA(cudaEventRecord(db->stageFull[s], db->copyStream));
+  SGZ_CUDA(cudaStreamWaitEvent(db->ctx->stream, db->stageFull[s], 0));
+  for (int i = 0; i < nFiles; i++)
+    SGZ_TRY(db_launch_prepare(db, (const float *)(db->dStage[s].p + files[i].off), files[i].layout, files[i].nFrames, files[i].dst));
+  SGZ_CUDA(cudaEventRecord(db->stageFree[s], db->ctx->stream));
+  db->stageUsed[s] = true;
+  if (waitCopy) SGZ_CUDA(cudaEventSynchronize(db->stageFull[s]));
+  return SGZ_OK;
+}
+
+// uploads the pending run of contiguous HOST_STABLE files (see sgz_db::pend)
+static int db_flush(sgz_db *db) {
+  if (db->pend.empty()) return SGZ_OK;
+  SGZ_TRY(db->ctx->bind());
+  SGZ_TRY(db_upload(db, db->pendPtr, db->pendBytes, db->pend.data(), (int)db->pend.size(), false));
+  const sgz_db::Pend &last = db->pend.back();
+  const int64_t upto = last.dst + last.nFrames;
+  db->pend.clear();
+  db->pendPtr = nullptr;
+  db->pendBytes = 0;
+  if (upto - db->chunkMark >= chunk_frames()) {
+    SGZ_TRY(db_mark_chunk(db, upto));
+    db->chunkMark = upto;
+  }
+  return SGZ_OK;
 }
 
 int sgz_db_add_file(sgz_db *db, const void *frames, int64_t nFrames, int32_t layout) {
@@ -227,28 +266,24 @@ int sgz_db_add_file(sgz_db *db, const void *frames, int64_t nFrames, int32_t lay
   const bool hostStable = (layout & SGZ_LAYOUT_HOST_STABLE) != 0;
   layout &= 0xff;
   SGZ_REQUIRE(layout >= 0 && layout <= 2, "unknown layout %d", layout);
+  const size_t bytes = (size_t)nFrames * db->numCh * sizeof(float);
+  if (hostStable && nFrames > 0) {
+    // deferred: joins the run if it continues it in host memory
+    const unsigned char *h = (const unsigned char *)frames;
+    if (!db->pend.empty() && !(h == db->pendPtr + db->pendBytes && db->pendBytes + bytes <= sgz_db::kRunBytes)) SGZ_TRY(db_flush(db));
+    if (db->pend.empty()) db->pendPtr = h;
+    db->pend.push_back(sgz_db::Pend{db->pendBytes, nFrames, layout, dst});
+    db->pendBytes += bytes;
+    return db_commit_file(db, nFrames, false);
+  }
+  SGZ_TRY(db_flush(db));
   if (nFrames > 0) {
-    const size_t bytes = (size_t)nFrames * db->numCh * sizeof(float);
-    const int s = db->stageIdx;
-    db->stageIdx = (s + 1) % sgz_db::kStageSlots;
-    if (db->dStage[s].n < bytes) {
-      // staging buffer may still be read by an earlier prepare kernel
-      if (db->stageUsed[s]) SGZ_CUDA(cudaEventSynchronize(db->stageFree[s]));
-      SGZ_TRY(db->dStage[s].alloc(bytes + bytes / 4));
-      db->stageUsed[s] = false;
-    }
-    if (db->stageUsed[s]) SGZ_CUDA(cudaStreamWaitEvent(db->copyStream, db->stageFree[s], 0));
-    SGZ_CUDA(cudaMemcpyAsync(db->dStage[s].p, frames, bytes, cudaMemcpyHostToDevice, db->copyStream));
-    SGZ_CUDA(cudaEventRecord(db->stageFull[s], db->copyStream));
-    SGZ_CUDA(cudaStreamWaitEvent(db->ctx->stream, db->stageFull[s], 0));
-    SGZ_TRY(db_launch_prepare(db, (const float *)db->dStage[s].p, layout, nFrames, dst));
-    SGZ_CUDA(cudaEventRecord(db->stageFree[s], db->ctx->stream));
-    db->stageUsed[s] = true;
+    const sgz_db::Pend one{0, nFrames, layout, dst};
     // the host buffer may be freed on return: pageable copies are staged by the driver before
     // cudaMemcpyAsync returns, pinned copies need the explicit wait
     cudaPointerAttributes attr;
-    if (!hostStable && cudaPointerGetAttributes(&attr, frames) == cudaSuccess && attr.type == cudaMemoryTypeHost)
-      SGZ_CUDA(cudaEventSynchronize(db->stageFull[s]));
+    const bool pinned = cudaPointerGetAttributes(&attr, frames) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    SGZ_TRY(db_upload(db, frames, bytes, &one, 1, pinned));
   }
   return db_commit_file(db, nFrames);
 }
@@ -256,6 +291,7 @@ int sgz_db_add_file(sgz_db *db, const void *frames, int64_t nFrames, int32_t lay
 int sgz_db_add_file_device(sgz_db *db, const void *dFrames, int64_t nFrames) {
   int64_t dst = 0;
   SGZ_TRY(db_begin_file(db, nFrames, &dst));
+  SGZ_TRY(db_flush(db));
   SGZ_REQUIRE(dFrames || nFrames == 0, "dFrames is NULL");
   SGZ_TRY(db_launch_prepare(db, (const float *)dFrames, SGZ_LAYOUT_INTERLEAVED_LE, nFrames, dst));
   return db_commit_file(db, nFrames);
@@ -265,6 +301,7 @@ int sgz_db_add_synth(sgz_db *db, uint64_t seed, uint32_t stream, int64_t nFrames
                      const float *sigma, float floor0) {
   int64_t dst = 0;
   SGZ_TRY(db_begin_file(db, nFrames, &dst));
+  SGZ_TRY(db_flush(db));
   SGZ_REQUIRE(mu && sigma, "mu / sigma is NULL");
   if (nFrames > 0) {
     DevBuf<float> ms;
@@ -286,6 +323,7 @@ int sgz_db_add_synth_many(sgz_db *db, uint64_t seed, uint32_t firstStream, int32
   SGZ_REQUIRE(numFiles >= 0 && nFramesEach >= 0, "negative file / frame count");
   int64_t dst = 0;
   SGZ_TRY(db_begin_file(db, (int64_t)numFiles * nFramesEach, &dst));
+  SGZ_TRY(db_flush(db));
   SGZ_REQUIRE(mu && sigma, "mu / sigma is NULL");
   const int first = db->numFiles();
   if (numFiles > 0 && nFramesEach > 0) {
@@ -314,6 +352,7 @@ int sgz_db_patch(sgz_db *db, int32_t file, int64_t frameOff, const float *frames
               (long long)frameOff, (long long)n, (long long)len);
   SGZ_TRY(db->ctx->bind());
   if (n == 0) return SGZ_OK;
+  SGZ_TRY(db_flush(db));
   DevBuf<float> tmp;
   SGZ_TRY(tmp.alloc((size_t)n * db->numCh));
   SGZ_CUDA(cudaMemcpyAsync(tmp.p, frames, (size_t)n * db->numCh * sizeof(float), cudaMemcpyHostToDevice,
@@ -326,6 +365,7 @@ int sgz_db_patch(sgz_db *db, int32_t file, int64_t frameOff, const float *frames
 
 // everything of finalize that is stream ordered: no host wait for the uploads
 static int db_finalize_enqueue(sgz_db *db) {
+  SGZ_TRY(db_flush(db));
   SGZ_TRY(db_grow(db, db->usedFrames));  // guarantees the slack even for an empty DB
   SGZ_CUDA(cudaMemset2DAsync(db->dData.p + db->usedFrames, (size_t)db->capFrames * sizeof(float2), 0,
                              (size_t)kDbSlack * sizeof(float2), (size_t)db->numPairs, db->ctx->stream));
@@ -444,6 +484,7 @@ int sgz_db_read(sgz_db *db, int32_t file, int64_t frameOff, int64_t n, float *ou
   SGZ_REQUIRE(frameOff >= 0 && n >= 0 && frameOff + n <= len, "read outside file");
   SGZ_TRY(db->ctx->bind());
   if (n == 0) return SGZ_OK;
+  SGZ_TRY(db_flush(db));
   DevBuf<float> tmp;
   SGZ_TRY(tmp.alloc((size_t)n * db->numCh));
   k_db_gather<<<(unsigned)ceil_div<int64_t>(n * db->numCh, 256), 256, 0, db->ctx->stream>>>(

@@ -42,6 +42,15 @@ struct sgz_db {
   struct Chunk { int64_t uptoFrame; cudaEvent_t ev; };
   std::vector<Chunk> chunks;
   int64_t chunkMark = 0;
+  // copy coalescing: HOST_STABLE files whose host buffers follow each other in memory (one arena, an mmap-ed database
+  // cache) are uploaded as ONE copy of up to kRunBytes -- file-sized copies (2.9 MB) reach 51 of the 55.5 GB/s PCIe gives
+  // a large copy (profiles/r01_pcie_probe.json).  The run is flushed by the next file that does not continue it and by
+  // everything that needs the frames on the device.
+  struct Pend { size_t off; int64_t nFrames; int layout; int64_t dst; };
+  static constexpr size_t kRunBytes = (size_t)32 << 20;
+  const unsigned char *pendPtr = nullptr;
+  size_t pendBytes = 0;
+  std::vector<Pend> pend;
 
   // tensor-core K1 (corr_tc2.cuh): pre-swizzled FP16 planes [numCh * 2][planeStrideBytes] and the tile-transposed
   // per-frame sums, built from the pair rows on demand (frames below planesUpto are done; a patch resets it)
