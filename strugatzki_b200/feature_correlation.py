@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _native as N
 from . import engine
-from .io import (FeatureExtractionConfig, Span, list_database, read_aiff, read_aiff_many, read_norm_file)
+from .io import (DatabaseCache, FeatureExtractionConfig, Span, list_database, read_aiff, read_aiff_many, read_norm_file)
 from .processor import Aborted, ProcessorFactory, ProcessorImpl
 
 verbose = False
@@ -147,6 +147,7 @@ class FeatureCorrelationImpl(ProcessorImpl):
     def __init__(self, config):
         super().__init__(config.build() if isinstance(config, ConfigBuilder) else config)
         self._job = None
+        self._cache_keepalive = None
 
     def _on_abort(self):
         if self._job is not None:
@@ -166,15 +167,30 @@ class FeatureCorrelationImpl(ProcessorImpl):
         ctx = engine.Context(self.device)
         db = engine.Database(ctx, num_ch, norm)
         try:
-            # reader threads run ahead of the upload; file order = order of extr_dbs (it fixes the file indices)
-            for e, (frames, spec) in zip(extr_dbs, read_aiff_many([e.feature_output for e in extr_dbs], raw=True)):
-                self.check_aborted()
-                if spec.num_channels != num_ch:
-                    raise IOError(f"{e.feature_output}: {spec.num_channels} channels, expected {num_ch}")
-                if spec.big_endian_f32:
-                    db.add_file(frames, N.LAYOUT_INTERLEAVED_BE)   # byte swap happens on the GPU
-                else:
-                    db.add_file(frames, N.LAYOUT_INTERLEAVED_LE)
+            # file order = order of extr_dbs (it fixes the file indices).  A database seen before comes from the on-disk
+            # cache of its decoded frames (one mapped file, contiguous -> uploaded in 32 MB copies); otherwise reader
+            # threads parse the AIFFs ahead of the upload and the cache is written on the way.
+            cache = DatabaseCache(cfg.databaseFolder, [e.feature_output for e in extr_dbs], num_ch)
+            hit = cache.load()
+            if hit is not None:
+                mm, counts = hit
+                self._cache_keepalive = mm
+                off = 0
+                for n in counts:
+                    self.check_aborted()
+                    db.add_file_ptr(mm.ctypes.data + off * num_ch * 4, n, N.LAYOUT_INTERLEAVED_LE | N.LAYOUT_HOST_STABLE)
+                    off += n
+            else:
+                with cache.writer() as w:
+                    for e, (frames, spec) in zip(extr_dbs, read_aiff_many([e.feature_output for e in extr_dbs], raw=True)):
+                        self.check_aborted()
+                        if spec.num_channels != num_ch:
+                            raise IOError(f"{e.feature_output}: {spec.num_channels} channels, expected {num_ch}")
+                        if spec.big_endian_f32:
+                            db.add_file(frames, N.LAYOUT_INTERLEAVED_BE)   # byte swap happens on the GPU
+                        else:
+                            db.add_file(frames, N.LAYOUT_INTERLEAVED_LE)
+                        w.add(frames)
             db.finalize()
             self._job = engine.CorrelationJob(db, native_config(cfg, step), inp)
             self._job.start()

@@ -288,3 +288,89 @@ def list_database(database_folder: str, meta_input: str, num_coeffs: int, step_s
         if e.num_coeffs == num_coeffs and e.fft_size // e.fft_overlap == step_size:
             out.append(e)
     return out
+
+
+class DatabaseCache:
+    """On-disk cache of a decoded feature database: `<folder>/.sgz_cache/db_<key>.f32` holds
+    the RAW float32 little-endian interleaved frames of all database files back to back, `db_<key>.json` their frame
+    counts.  The key covers name, size and mtime of every feature file and the channel count, so any change of the
+    database makes a new cache; normalisation stays on the GPU, so the norm file is not part of the key.  A search then
+    maps one file instead of parsing thousands of AIFFs (FeatureCorrelationImpl.scala:169,195 is what that replaces), and
+    the mapped frames are contiguous, so the engine uploads them in 32 MB copies.  SGZ_DB_CACHE=0 turns it off."""
+
+    def __init__(self, folder: str, feature_files: List[str], num_ch: int):
+        import hashlib
+        self.num_ch = num_ch
+        self.files = list(feature_files)
+        h = hashlib.sha1(f"sgz-db-cache-1 {num_ch}".encode())
+        for f in self.files:
+            st = os.stat(f)
+            h.update(f"{os.path.basename(f)} {st.st_size} {st.st_mtime_ns}\n".encode())
+        self.dir = os.path.join(folder, ".sgz_cache")
+        self.base = os.path.join(self.dir, f"db_{h.hexdigest()[:20]}")
+        self.enabled = os.environ.get("SGZ_DB_CACHE", "1") != "0"
+
+    def load(self):
+        """(memmap of float32 [total frames][num_ch], frame counts) or None"""
+        if not self.enabled:
+            return None
+        try:
+            import json
+            with open(self.base + ".json") as fh:
+                meta = json.load(fh)
+            counts = [int(c) for c in meta["frames"]]
+            if len(counts) != len(self.files) or meta["num_ch"] != self.num_ch:
+                return None
+            total = sum(counts)
+            if os.path.getsize(self.base + ".f32") != total * self.num_ch * 4:
+                return None
+            mm = np.memmap(self.base + ".f32", np.float32, "r", shape=(max(total, 1), self.num_ch)) if total else \
+                np.zeros((0, self.num_ch), np.float32)
+            return mm, counts
+        except (OSError, ValueError, KeyError):
+            return None
+
+    def writer(self):
+        """context manager with add(frames) -- frames as decoded by read_aiff_many(raw=True): big-endian payloads are
+        swapped here, once -- that publishes the cache atomically on exit; any I/O error just leaves no cache"""
+        cache = self
+
+        class _W:
+            def __enter__(self):
+                self.counts, self.fh = [], None
+                if cache.enabled:
+                    try:
+                        os.makedirs(cache.dir, exist_ok=True)
+                        self.fh = open(cache.base + ".f32.tmp", "wb")
+                    except OSError:
+                        self.fh = None
+                return self
+
+            def add(self, frames: np.ndarray):
+                self.counts.append(int(frames.shape[0]))
+                if self.fh is not None:
+                    try:
+                        self.fh.write(np.ascontiguousarray(frames, "<f4").tobytes())
+                    except OSError:
+                        self.fh.close()
+                        self.fh = None
+
+            def __exit__(self, et, ev, tb):
+                if self.fh is None:
+                    return False
+                self.fh.close()
+                try:
+                    if et is None and len(self.counts) == len(cache.files):
+                        import json
+                        with open(cache.base + ".json.tmp", "w") as fh:
+                            json.dump({"num_ch": cache.num_ch, "frames": self.counts,
+                                       "files": [os.path.basename(f) for f in cache.files]}, fh)
+                        os.replace(cache.base + ".f32.tmp", cache.base + ".f32")
+                        os.replace(cache.base + ".json.tmp", cache.base + ".json")
+                    else:
+                        os.remove(cache.base + ".f32.tmp")
+                except OSError:
+                    pass
+                return False
+
+        return _W()

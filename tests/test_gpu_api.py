@@ -130,3 +130,37 @@ def test_feature_stats_processor_writes_norm_file(ctx, tmp_path):
     from strugatzki_b200.io import read_norm_file
     norm = read_norm_file(folder, 14)
     assert np.array_equal(norm.view(np.uint32), want.astype(np.float32).view(np.uint32))
+
+
+def test_cli_correlate_prints_the_oracle_matches_and_reuses_the_database_cache(ctx, database, monkeypatch):
+    """`Strugatzki -c` (Strugatzki.scala:101-213) through strugatzki_b200.cli; the second run maps the on-disk cache of the
+    decoded database instead of parsing the AIFFs and must print the same matches"""
+    import io as _io
+    from strugatzki_b200 import cli
+    from strugatzki_b200 import io as sio
+    folder, meta_in, files, inp, norm = database
+    args = ["-c", "-d", folder, "--in-start", "0", "--in-stop", "2", "--dur-min", "1", "--dur-max", "8", "-m", "4",
+            "--num-per-file", "2", "--spacing", "0.5", "--sample-rate", "44100", meta_in]
+    want = O.corr_search(O.CorrParams(step_size=STEP, input=inp, punch_in=(0, 88200), norm=norm, num_matches=4,
+                                      num_per_file=2, min_spacing=22050), files)
+
+    def run():
+        out = _io.StringIO()
+        assert cli.main(args, out) == 0
+        return out.getvalue()
+
+    first = run()
+    assert "  Success." in first and first.count("#") == 25
+    blocks = [b for b in first.split("\n\n") if b.strip().startswith("File")]
+    assert len(blocks) == len(want) == 4
+    for b, w in zip(blocks, want):
+        lines = dict(l.split(None, 1) if l.startswith("File") else l.split(":", 1) for l in b.strip().split("\n"))
+        assert lines["File"].strip() == os.path.join(folder, f"file{w['file']:02d}.aif")
+        assert int(lines["Span start"]) == w["start"]
+        assert lines["Similarity"].strip() == cli.to_percent_str(w["sim"])
+        assert lines["Boost in  "].strip() == cli.to_db_str(w["boostIn"])
+    assert any(n.endswith(".f32") for n in os.listdir(os.path.join(folder, ".sgz_cache")))
+    calls = []
+    real = sio.read_aiff_many
+    monkeypatch.setattr("strugatzki_b200.feature_correlation.read_aiff_many", lambda *a, **k: calls.append(1) or real(*a, **k))
+    assert run() == first and calls == []                      # served from the cache, identical output
