@@ -287,6 +287,9 @@ def main():
     if rank == 0 and world == 1:
         secondary = run_secondary(ctx, engine, N, synth, norm)
 
+    if world > 1:
+        secondary = run_secondary_sharded(torch, dist, device, ctx, engine, N, synth, norm, rank, world)
+
     # ---- CPU baseline: the oracle port, one host thread (the reference is single-threaded) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -513,6 +516,39 @@ def run_secondary(ctx, engine, N, synth, norm):
                                                       "(BASELINE.json configs[1])"}
     except Exception as e:   # secondary numbers must never break the headline line
         out["error"] = repr(e)
+    return out
+
+
+def run_secondary_sharded(torch, dist, device, ctx, engine, N, synth, norm, rank, world):
+    """SelfSimilarity cells/s with the matrix sharded by column blocks over the ranks (BASELINE.json configs[3], the feature
+    file replicated on every GPU): every rank renders its block, the time is the max over ranks of the device time."""
+    from strugatzki_b200.distributed import selfsim_column_blocks
+    out = None
+    try:
+        frames = 155000
+        f = synth.regime_file(synth.BASE_SEED, 4, frames, 14, max(4, frames // 2000))[0]
+        cfg = N.SelfConfig(STEP, 0, 0, 0, 0, 44100, 1, 0.5, 0, 1.0, 1.0, None, 0, 0)
+        ext = engine.self_geometry(cfg, frames, frames)["imgExt"]
+        b, e = selfsim_column_blocks(ext, world)[rank]
+        ms = 0.0
+        if e > b:
+            engine.self_run(ctx, cfg, f, None, norm, b, e, download=False)
+            engine.self_run(ctx, cfg, f, None, norm, b, e, download=False)
+            ms, _ = ctx.last_timing()
+        cells = sum(ext - a for a in range(b, e))
+        t = torch.tensor([ms, float(cells)], dtype=torch.float64, device=device)
+        mx, sm = t.clone(), t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            out = {"selfsimilarity_gram_tc_config3_sharded": {
+                "metric": "SelfSimilarity cells/sec", "value": float(sm[1]) / (float(mx[0]) * 1e-3), "unit": "cells/s",
+                "cells": int(sm[1]), "imgExt": ext, "n_gpus": world, "kernel_ms_max_over_ranks": float(mx[0]),
+                "kernel": engine.self_last_kernel(ctx),
+                "workload": "155 000-frame synthetic feature file (BASELINE.json configs[3]), column blocks balanced by cell "
+                            "count, one per GPU; matrix only (image gather and PNG encode excluded)"}}
+    except Exception as ex:   # secondary numbers must never break the headline line
+        out = {"error": repr(ex)} if rank == 0 else None
     return out
 
 

@@ -168,18 +168,36 @@ def sharded_self_similarity(render, img_ext: int, device=None, group=None, dst: 
     """One SelfSimilarity image rendered by all ranks of `group`: rank r calls `render(col_begin, col_end)` -- e.g.
     `lambda b, e: engine.self_run(ctx, cfg, frames1, frames2, norm, b, e)[0]` with the feature file replicated on every
     GPU -- for its column block and gets an (img_ext, img_ext) int32 image that holds only that block's pixels and their
-    mirrors (everything else 0).  Blocks write disjoint pixels, so the image is the SUM of the partial images: one
-    reduce to rank `dst` (NCCL over NVLink on GPUs, gloo in the CPU tests).  Returns the image on `dst`, None elsewhere.
+    mirrors.  A block [b, e) touches two strips of the image and nothing else: its cells (a, c >= a) sit at
+    (row ext-1-c, column a), i.e. in COLUMNS [b, e), and their mirrors at (row ext-1-a, column c), i.e. in ROWS
+    [ext-e, ext-b).  Only these two strips travel to rank `dst` (point to point; NCCL over NVLink on GPUs, gloo in the CPU
+    tests), 2 x ext x (e - b) pixels per rank -- 8 ext^2 bytes in total whatever the number of ranks, where a reduce of whole
+    images moved 4 ext^2 bytes per rank and needed each of them on the device.  Returns the image on `dst`, None elsewhere.
     No other communication: the Gram tiles are independent (SelfSimilarityImpl.scala:127-155 has no cross-cell state)."""
     import torch
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    b, e = selfsim_column_blocks(img_ext, world)[rank]
-    part = render(b, e) if e > b else np.zeros((img_ext, img_ext), np.int32)
-    part = np.ascontiguousarray(part, np.int32)
-    assert part.shape == (img_ext, img_ext), part.shape
+    blocks = selfsim_column_blocks(img_ext, world)
+    b, e = blocks[rank]
     dev = device if device is not None else torch.device("cpu")
-    t = torch.from_numpy(part).to(dev)
-    dist.reduce(t, dst=dst, op=dist.ReduceOp.SUM, group=group)
-    return t.cpu().numpy() if rank == dst else None
+    part = None
+    if e > b:
+        part = np.ascontiguousarray(render(b, e), np.int32)
+        assert part.shape == (img_ext, img_ext), part.shape
+    if rank != dst:
+        if part is not None:
+            for strip in (part[:, b:e], part[img_ext - e:img_ext - b, :]):
+                dist.send(torch.from_numpy(np.ascontiguousarray(strip)).to(dev), dst, group=group)
+        return None
+    full = part if part is not None else np.zeros((img_ext, img_ext), np.int32)
+    for r, (rb, re) in enumerate(blocks):
+        if r == dst or re <= rb:
+            continue
+        v = torch.empty((img_ext, re - rb), dtype=torch.int32, device=dev)
+        h = torch.empty((re - rb, img_ext), dtype=torch.int32, device=dev)
+        dist.recv(v, r, group=group)
+        dist.recv(h, r, group=group)
+        full[:, rb:re] |= v.cpu().numpy()           # strips of different ranks cross, but no pixel is written twice
+        full[img_ext - re:img_ext - rb, :] |= h.cpu().numpy()
+    return full
