@@ -523,33 +523,34 @@ def run_secondary_sharded(torch, dist, device, ctx, engine, N, synth, norm, rank
     """SelfSimilarity cells/s with the matrix sharded by column blocks over the ranks (BASELINE.json configs[3], the feature
     file replicated on every GPU): every rank renders its block, the time is the max over ranks of the device time."""
     from strugatzki_b200.distributed import selfsim_column_blocks
-    out = None
+    ms, cells, ext, err = 0.0, 0, 0, None
     try:
         frames = 155000
         f = synth.regime_file(synth.BASE_SEED, 4, frames, 14, max(4, frames // 2000))[0]
         cfg = N.SelfConfig(STEP, 0, 0, 0, 0, 44100, 1, 0.5, 0, 1.0, 1.0, None, 0, 0)
         ext = engine.self_geometry(cfg, frames, frames)["imgExt"]
         b, e = selfsim_column_blocks(ext, world)[rank]
-        ms = 0.0
         if e > b:
             engine.self_run(ctx, cfg, f, None, norm, b, e, download=False)
             engine.self_run(ctx, cfg, f, None, norm, b, e, download=False)
             ms, _ = ctx.last_timing()
         cells = sum(ext - a for a in range(b, e))
-        t = torch.tensor([ms, float(cells)], dtype=torch.float64, device=device)
-        mx, sm = t.clone(), t.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        if rank == 0:
-            out = {"selfsimilarity_gram_tc_config3_sharded": {
-                "metric": "SelfSimilarity cells/sec", "value": float(sm[1]) / (float(mx[0]) * 1e-3), "unit": "cells/s",
-                "cells": int(sm[1]), "imgExt": ext, "n_gpus": world, "kernel_ms_max_over_ranks": float(mx[0]),
-                "kernel": engine.self_last_kernel(ctx),
-                "workload": "155 000-frame synthetic feature file (BASELINE.json configs[3]), column blocks balanced by cell "
-                            "count, one per GPU; matrix only (image gather and PNG encode excluded)"}}
-    except Exception as ex:   # secondary numbers must never break the headline line
-        out = {"error": repr(ex)} if rank == 0 else None
-    return out
+    except Exception as ex:   # secondary numbers must never break the headline line -- nor leave a rank out of the collective
+        err = repr(ex)
+    t = torch.tensor([ms, float(cells), 1.0 if err else 0.0], dtype=torch.float64, device=device)
+    mx, sm = t.clone(), t.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    if rank != 0:
+        return None
+    if float(mx[2]) > 0 or float(mx[0]) <= 0:
+        return {"error": err or "a rank failed"}
+    return {"selfsimilarity_gram_tc_config3_sharded": {
+        "metric": "SelfSimilarity cells/sec", "value": float(sm[1]) / (float(mx[0]) * 1e-3), "unit": "cells/s",
+        "cells": int(sm[1]), "imgExt": ext, "n_gpus": world, "kernel_ms_max_over_ranks": float(mx[0]),
+        "kernel": engine.self_last_kernel(ctx),
+        "workload": "155 000-frame synthetic feature file (BASELINE.json configs[3]), column blocks balanced by cell "
+                    "count, one per GPU; matrix only (image gather and PNG encode excluded)"}}
 
 
 def cpu_baseline(args, synth, norm, inp):
