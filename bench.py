@@ -40,12 +40,15 @@ def corr_config(N, num_matches=100, num_per_file=1, min_spacing=22050):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The process is started
+    before the warm-up (its start-up alone is longer than a short timed region), every row is stamped on arrival, and
+    only rows that arrived between mark_begin() and mark_end() count."""
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
+        self.rows = []      # (arrival time, fields)
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -53,7 +56,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -62,23 +65,35 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def in_window(self):
+        lo = self.t0 if self.t0 is not None else -1e300
+        hi = self.t1 if self.t1 is not None else 1e300
+        return [r for (t, r) in list(self.rows) if lo <= t <= hi and len(r) >= 7]
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        rows = self.in_window()
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower() == "active" for r in self.rows)]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower() == "active" for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm)}
 
 
 def host_threads() -> int:
@@ -236,12 +251,13 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(device)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()     # before the warm-up: nvidia-smi needs longer to start than a short timed region lasts
     for _ in range(args.warmup):
         res = step()
     sync_all()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     launches0 = ctx.launch_count
     phases.clear()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -258,7 +274,24 @@ def main():
     wall_ms = 1e3 * (time.perf_counter() - t_wall)
     dev_ms = ev0.elapsed_time(ev1)
     launches = ctx.launch_count - launches0
+    phases = dict(phases)   # the extra steps below must not count into the per-step phase times
+    # a timed region of K x 8 ms can fall between two nvidia-smi rows: the same steps keep running, untimed, until at
+    # least five rows have been taken under this load (every rank takes part: the steps are collective at N > 1)
+    extra = 0
+    for _ in range(40):
+        flag = torch.tensor([1.0 if (rank == 0 and len(sampler.in_window()) < 5) else 0.0], device=device)
+        if world > 1:
+            dist.broadcast(flag, 0)
+        if float(flag[0]) == 0.0:
+            break
+        for _ in range(max(args.steps, 10)):
+            sharded_search(job, device, None) if world > 1 else job.run()
+        sync_all()
+        extra += max(args.steps, 10)
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["extra_load_steps"] = extra   # identical untimed steps run behind the timed ones while sampling
 
     t = torch.tensor([dev_ms, wall_ms, float(n_off_local), float(np.mean(scan_ms))], dtype=torch.float64, device=device)
     if world > 1:

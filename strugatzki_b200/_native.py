@@ -128,10 +128,11 @@ def lib() -> C.CDLL:
     """The loaded C-ABI library; raises if it has not been built (no fallback)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("SGZ_LIB_PATH", LIB_PATH)   # developer knob: A/B a saved build against the in-tree one
+        if not os.path.exists(path):
             raise NativeError(ERR_STATE, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; "
                                          f"g.build()'` (there is no CPU fallback)")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         L.sgz_last_error.restype = C.c_char_p
         L.sgz_ctx_stream.restype = C.c_void_p
         L.sgz_ctx_launch_count.restype = C.c_int64

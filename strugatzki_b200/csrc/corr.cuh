@@ -372,15 +372,16 @@ inline int run_scan_t2(sgz_corr *job, PunchQuery &q, int which, int tailExtra, f
   {
     T2Eval &E = tp.ev;
     E.nT = (double)q.W; E.nS = (double)(db->numCh - 1) * (double)q.W;
-    E.negEpsT = -2e-3 * E.nT; E.negEpsS = -2e-3 * E.nS;
+    E.invNTd = 1.0 / E.nT; E.invNSd = 1.0 / E.nS;
+    E.nTf = (float)E.nT; E.nSf = (float)E.nS;
+    E.sqEps = (float)sqrt(2e-3 / (1.0 - 2e-3));
     // boost = exp((lnAvgIn - ln avg) / 0.6) <= maxBoost  <=>  avg >= exp(lnAvgIn - 0.6 ln maxBoost); a NaN threshold
     // (maxBoost < 0 or NaN) lets no offset pass, like the reference's comparison
     const double avgMin = exp(q.lnAvg - 0.6 * log((double)job->cfg.maxBoost));
-    E.gateT1 = avgMin * E.nT;
-    E.invNT = (float)(1.0 / E.nT); E.invNS = (float)(1.0 / E.nS);
+    E.gateNm = (float)(avgMin * E.nT);
     E.invNT2 = (float)(1.0 / (E.nT * E.nT)); E.invNS2 = (float)(1.0 / (E.nS * E.nS));
     E.cT = (float)(1.0 / (E.nT * q.stdT)); E.cS = (float)(1.0 / (E.nS * q.stdS));
-    E.kT = (float)q.rhoT * E.cT; E.kS = (float)q.rhoS * E.cS;
+    E.kTn = (float)(q.rhoT / (E.nT * E.nT * q.stdT)); E.kSn = (float)(q.rhoS / (E.nS * E.nS * q.stdS));
     E.wT = q.weight; E.wS = 1.0f - q.weight;
     E.useT = q.weight > 0.f; E.useS = q.weight < 1.f;
   }
@@ -393,6 +394,10 @@ inline int run_scan_t2(sgz_corr *job, PunchQuery &q, int which, int tailExtra, f
     static const int ahead = getenv("SGZ_T2_AHEAD") ? atoi(getenv("SGZ_T2_AHEAD")) : kT2Ahead;   // developer knob
     tp.ahead = ahead;
     tp.dbg = getenv("SGZ_T2_DBG") ? atoi(getenv("SGZ_T2_DBG")) : 0;
+    static const int split = getenv("SGZ_T2_SPLIT") ? atoi(getenv("SGZ_T2_SPLIT")) : 1;                 // developer knob
+    tp.splitRelease = split;
+    static const int l2hint = getenv("SGZ_T2_L2HINT") ? atoi(getenv("SGZ_T2_L2HINT")) : 1;             // developer knob
+    tp.l2hint = l2hint;
   }
   const bool prof = getenv("SGZ_CORR_TC_PROF") != nullptr;   // developer probe: cycles per role and phase
   auto kern = prof ? k_corr_tc2<true> : k_corr_tc2<false>;

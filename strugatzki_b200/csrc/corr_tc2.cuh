@@ -76,12 +76,6 @@ __host__ __device__ inline int64_t t2_side_index(int64_t g) {
   return (g & ~(int64_t)(kT2Tile - 1)) + ((g & 63) << 7) + ((g >> 6) & 127);
 }
 
-// per-frame statistics are kept as the high word of their Double, rounded to nearest (the carry may run into the exponent)
-__device__ __forceinline__ uint32_t t2_dhi(float x) {
-  return (uint32_t)(((unsigned long long)__double_as_longlong((double)x) + 0x80000000ull) >> 32);
-}
-__device__ __forceinline__ double t2_dbl(uint32_t hi) { return __hiloint2double((int)hi, 0); }
-
 // taps image of a taps stage: per channel [first-part atoms][second-part atoms], atom a = 8 rows (cc) x 16 k (kk) halves
 // holding q~[8 a + kk + cc - 63], SWIZZLE_32B chunk flip on rows 4..7.  Built on the device from the float taps (one block
 // per channel): the float taps are a few KB and reach the device as an inline copy even while database uploads occupy
@@ -134,12 +128,10 @@ __global__ void k_t2_tile_files(const int64_t *__restrict__ fileStart, int numFi
 // ---------------------------------------------------------------------------------------------
 // planes[(2 c + part)][planeStrideBytes]: part 0 = fp16(x), part 1 = fp16((x - part0) * 2^11), pre-swizzled (t2_plane_byte);
 // side arrays (tile transposed, t2_side_index): per frame b0 = loudness, s1 = sum over the spectral channels, s2 = sum of
-// their squares (FP32: s1 += x + y, s2 = fma(x, x, fma(y, y, s2)) pair by pair), each stored as the HIGH WORD of its
-// Double rounded to 20 mantissa bits -- the window statistics run in FP64, and the kernel gets its Double operand for free
-// (no Float -> Double conversion: 16 lanes per clock per SM, six per slide).  The rounding (2^-21 relative, unbiased) moves
-// a window variance by < 2e-7 relative; sideA = (b0, s1), sideB = s2;
-// b16[(4 q + cb)][rowsTotal]: FP64 sums of (b0, b0^2, s1, s2)[q] of the SAME rounded values over the aligned 16-frame
-// block cb of each 64-frame row.
+// their squares (accumulated in FP64, rounded once), each stored as a Float -- K1 slides its window statistics in FP32,
+// centred on the mean of the thread's first window (corr_tc2 epilogue); sideA = (b0, s1), sideB = s2;
+// b16[(4 q + cb)][rowsTotal]: FP64 sums of (b0, b0^2, s1, s2)[q] of the SAME Float values over the aligned 16-frame
+// block cb of each 64-frame row (exact: the window sums a thread starts from are the sums of what it slides with).
 constexpr int kPlaneFrames = 2048;     // frames per block (256 threads x 8 frames)
 __global__ void __launch_bounds__(256) k_db_planes(const float2 *__restrict__ data, int64_t rowStride, int numCh, int numPairs,
                                                    int64_t frameBegin, int64_t frameEnd, unsigned char *__restrict__ planes,
@@ -148,7 +140,8 @@ __global__ void __launch_bounds__(256) k_db_planes(const float2 *__restrict__ da
   __shared__ uint32_t sh[3][kPlaneFrames + 32];    // +1 per 64 frames against bank conflicts of the transposed read-out
   const int64_t f0 = frameBegin + (int64_t)blockIdx.x * kPlaneFrames;   // frameBegin is a multiple of 2048
   const int64_t g0 = f0 + 8 * (int64_t)threadIdx.x;
-  float b0[8], s1[8], s2[8];
+  float b0[8];
+  double s1[8], s2[8];
   for (int pr = 0; pr < numPairs; pr++) {
     const float4 *src = reinterpret_cast<const float4 *>(data + (int64_t)pr * rowStride + g0);
     float4 v[4];
@@ -159,10 +152,13 @@ __global__ void __launch_bounds__(256) k_db_planes(const float2 *__restrict__ da
     for (int k = 0; k < 4; k++) { x[2 * k] = v[k].x; y[2 * k] = v[k].y; x[2 * k + 1] = v[k].z; y[2 * k + 1] = v[k].w; }
     if (pr == 0) {
 #pragma unroll
-      for (int k = 0; k < 8; k++) { b0[k] = x[k]; s1[k] = y[k]; s2[k] = y[k] * y[k]; }
+      for (int k = 0; k < 8; k++) { b0[k] = x[k]; s1[k] = (double)y[k]; s2[k] = (double)y[k] * (double)y[k]; }
     } else {
 #pragma unroll
-      for (int k = 0; k < 8; k++) { s1[k] += x[k] + y[k]; s2[k] = fmaf(x[k], x[k], fmaf(y[k], y[k], s2[k])); }
+      for (int k = 0; k < 8; k++) {
+        const double xd = (double)x[k], yd = (double)y[k];    // a channel beyond numCh is zero
+        s1[k] += xd + yd; s2[k] = fma(xd, xd, fma(yd, yd, s2[k]));
+      }
     }
     uint32_t xh[4], xl[4], yh[4], yl[4];
 #pragma unroll
@@ -186,7 +182,7 @@ __global__ void __launch_bounds__(256) k_db_planes(const float2 *__restrict__ da
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     const int L = 8 * threadIdx.x + k, i = L + (L >> 6);
-    sh[0][i] = t2_dhi(b0[k]); sh[1][i] = t2_dhi(s1[k]); sh[2][i] = t2_dhi(s2[k]);
+    sh[0][i] = __float_as_uint(b0[k]); sh[1][i] = __float_as_uint((float)s1[k]); sh[2][i] = __float_as_uint((float)s2[k]);
   }
   __syncthreads();
   // transposed write-out: the block's 2048 frames are 32 rows x 64 columns of one tile; a warp writes 32 consecutive rows
@@ -204,10 +200,10 @@ __global__ void __launch_bounds__(256) k_db_planes(const float2 *__restrict__ da
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
 #pragma unroll
     for (int e = 0; e < 16; e += 2) {
-      const double x = t2_dbl(sh[0][i0 + e]), x2 = t2_dbl(sh[0][i0 + e + 1]);
+      const double x = (double)__uint_as_float(sh[0][i0 + e]), x2 = (double)__uint_as_float(sh[0][i0 + e + 1]);
       a0 += x; a1 += x * x; c0 += x2; c1 += x2 * x2;
-      a2 += t2_dbl(sh[1][i0 + e]); c2 += t2_dbl(sh[1][i0 + e + 1]);
-      a3 += t2_dbl(sh[2][i0 + e]); c3 += t2_dbl(sh[2][i0 + e + 1]);
+      a2 += (double)__uint_as_float(sh[1][i0 + e]); c2 += (double)__uint_as_float(sh[1][i0 + e + 1]);
+      a3 += (double)__uint_as_float(sh[2][i0 + e]); c3 += (double)__uint_as_float(sh[2][i0 + e + 1]);
     }
     double *dst = b16 + (int64_t)warp * rowsTotal + (f0 >> 6) + lane;
     dst[0] = a0 + c0; dst[4 * rowsTotal] = a1 + c1; dst[8 * rowsTotal] = a2 + c2; dst[12 * rowsTotal] = a3 + c3;
@@ -232,12 +228,14 @@ __device__ __forceinline__ float t2_d2f(double d) {
 // constants of one evaluated offset, prepared on the host (kernel parameters = constant bank operands)
 struct T2Eval {
   double nT, nS;            // cells of a window per group: W, (numCh - 1) W
-  double negEpsT, negEpsS;  // -2e-3 n: a window whose variance is below 2e-3 of its mean square is re-evaluated exactly
-  double gateT1;            // boost <= maxBoost  <=>  loudness sum of the window >= gateT1 (calcBoost is monotone)
-  float invNT, invNS;       // 1 / n
+  double invNTd, invNSd;    // 1 / n
+  float nTf, nSf;
+  float sqEps;              // sqrt(eps / (1 - eps)), eps = 2e-3: a window whose variance is below eps of its mean square
+                            // is re-evaluated exactly (corr_fix.cuh)
+  float gateNm;             // boost <= maxBoost  <=>  loudness sum of the window >= gateNm (calcBoost is monotone)
   float invNT2, invNS2;     // 1 / n^2
   float cT, cS;             // 1 / (n std_a) per group
-  float kT, kS;             // rho * c: correction for the rounded taps not summing to exactly zero
+  float kTn, kSn;           // rho / (n^2 std_a): correction for the rounded taps not summing to exactly zero
   float wT, wS;
   int useT, useS;
 };
@@ -264,6 +262,8 @@ struct CorrT2Params {
   long long *prof;              // SGZ_CORR_TC_PROF: per CTA 24 cycle counters (k_corr_tc2<true>), or nullptr
   int smemMax;                  // the geometry (ring depths) is a function of (W, shared memory limit)
   int ahead;                    // channels between the L2 prefetch of a signal stage and its bulk copy (0: no prefetch)
+  int l2hint;                   // bit 0: signal planes evict_first, bit 1: taps + block sums evict_last, bit 2: streaming curve stores
+  int splitRelease;             // 1: the epilogue hands the two temporal accumulators back before it reads the spectral ones
   int dbg;                      // developer knob (SGZ_T2_DBG, profiling build only): 1 = no MMAs, 2 = no per-offset work, 4 = no curve stores, 8 = no per-frame loads, 16 = no window slides, 32 = no evaluation
 };
 
@@ -282,26 +282,38 @@ __device__ __forceinline__ bool t2_test(uint64_t *bar, uint32_t parity) {   // n
   return done != 0;
 }
 
-// one evaluated offset: window sums -> sim (FeatureCorrelationImpl.scala:73-78,198-210); branch free so that the compiler
-// can interleave the offsets of a thread.  n^2 var = n sum(x^2) - (sum x)^2 in FP64; the boost itself is not needed here,
-// only its gate (the few offsets that end up in a result get their boost from corr_boost, corr_fix.cuh)
-__device__ __forceinline__ float t2_eval(const T2Eval &E, const D4 &win, float accT, float accS) {
+// Window statistics of a thread's run of 16 offsets, in FP32 and CENTRED on the mean mu of the run's first window (taken
+// from exact FP64 sums): c1 = sum (x - mu), c2 = sum (x - mu)^2 over the cells of the window.  n^2 var = n c2 - c1^2 then
+// cancels only by 1 + (mean - mu)^2 / var (the mean moves by a few frames out of W during 15 slides), where the raw sums
+// n sum x^2 - (sum x)^2 cancel by mean^2 / var; nmu = n mu, tmu = 2 mu.
+struct T2Win {
+  float c1T, c2T, c1S, c2S, nmuT, nmuS, tmuT, tmuS;
+};
+
+// one evaluated offset: centred window sums -> sim (FeatureCorrelationImpl.scala:73-78,198-210); branch free so that the
+// compiler can interleave the offsets of a thread.  The boost itself is not needed here, only its gate (the few offsets
+// that end up in a result get their boost from corr_boost, corr_fix.cuh).  A window is handed to the exact re-evaluation
+// (sentinel NaN) when its variance is below eps of its mean square (the split-FP16 products truncate at the scale of the
+// level) or when the centring has drifted (c1^2 above half of n c2: FP32 would cancel).
+__device__ __forceinline__ float t2_eval(const T2Eval &E, const T2Win &w, float accT, float accS) {
   const float qnan = __uint_as_float(kFixSentinel);
-  const double vT = fma(win.t2, E.nT, -(win.t1 * win.t1));
-  const float mT = t2_d2f(win.t1) * E.invNT;
-  const float crT = fmaf(accT, E.cT, -mT * E.kT);                          // (acc - mean_b * rho) / (W std_a)
-  float temporal = crT * t2_rsqrt(t2_d2f(vT) * E.invNT2);
-  temporal = __double2hiint(fma(win.t2, E.negEpsT, vT)) > 0 ? temporal : qnan;   // var > 2e-3 E[x^2] (positive, not NaN)
+  const float nmT = w.nmuT + w.c1T;                                     // n * window mean
+  const float qT = w.c1T * w.c1T, vT = fmaf(E.nTf, w.c2T, -qT);         // n^2 var
+  const float tT = nmT * E.sqEps;
+  const float crT = fmaf(accT, E.cT, -(nmT * E.kTn));                   // (acc - mean_b * rho) / (W std_a)
+  float temporal = crT * t2_rsqrt(vT * E.invNT2);
+  temporal = vT > fmaxf(tT * tT, qT) ? temporal : qnan;                 // (false for NaN)
   temporal = E.useT ? temporal : 0.f;
-  const double vS = fma(win.s2, E.nS, -(win.s1 * win.s1));
-  const float mS = t2_d2f(win.s1) * E.invNS;
-  const float crS = fmaf(accS, E.cS, -mS * E.kS);
-  float spectral = crS * t2_rsqrt(t2_d2f(vS) * E.invNS2);
-  spectral = __double2hiint(fma(win.s2, E.negEpsS, vS)) > 0 ? spectral : qnan;
+  const float nmS = w.nmuS + w.c1S;
+  const float qS = w.c1S * w.c1S, vS = fmaf(E.nSf, w.c2S, -qS);
+  const float tS = nmS * E.sqEps;
+  const float crS = fmaf(accS, E.cS, -(nmS * E.kSn));
+  float spectral = crS * t2_rsqrt(vS * E.invNS2);
+  spectral = vS > fmaxf(tS * tS, qS) ? spectral : qnan;
   spectral = E.useS ? spectral : 0.f;
   const float blend = __fadd_rn(__fmul_rn(temporal, E.wT), __fmul_rn(spectral, E.wS));
   // an ill-conditioned group makes the blend NaN whatever the other group is; it is marked for the exact re-evaluation
-  return win.t1 >= E.gateT1 ? (blend == blend ? blend : qnan) : 0.f;
+  return nmT >= E.gateNm ? (blend == blend ? blend : qnan) : 0.f;
 }
 
 // warp 0: producer (bulk copies), warp 1: MMA issuer, warps 2-3: idle (they complete the first warpgroup, which hands most
@@ -319,12 +331,14 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
   uint64_t *sigFull = bars, *sigFree = bars + 4, *tapFull = bars + 8, *tapFree = bars + 12;
   uint64_t *accFull = bars + 16, *accEmpty = bars + 17, *sumsFull = bars + 18, *sumsFree = bars + 19;
   uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(bars + 20);
+#define accEmptyT (accEmpty + 4)      // accumulators 0 and 1 (temporal channel) drained; accEmpty: 2..7 (spectral channels)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int s = 0; s < 4; s++) { mbar_init(sigFull + s, 1); mbar_init(sigFree + s, 1); mbar_init(tapFull + s, 1); mbar_init(tapFree + s, 1); }
     mbar_init(accFull, 1);
     mbar_init(accEmpty, kT2EpiWarps);
+    mbar_init(accEmptyT, kT2EpiWarps);
     mbar_init(sumsFull, 1);
     mbar_init(sumsFree, kT2EpiWarps);
     fence_mbar_init();
@@ -345,6 +359,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
     // =========================== producer ===========================
     if (lane == 0) {
       uint32_t it = 0, tileIt = 0;
+      // the planes stream through once (1.7 GB per 1000 h / 10): marked evict_first they leave the per-frame arrays (touched
+      // twice a tile apart), the taps and the block sums alone in L2
+      const uint64_t polSig = l2_policy_evict_first(), polKeep = l2_policy_evict_last();
       for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, tileIt++) {
         const unsigned char *src = p.planes + tile * (int64_t)(kT2Tile * 2);
         bool sumsPending = true;     // the block sums of this tile overwrite those of the previous one: once its windows are set up
@@ -372,12 +389,18 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
           const uint32_t s = it % (uint32_t)G.sigStages, u = it / (uint32_t)G.sigStages;
           if (u > 0) tc_wait(sigFree + s, (u - 1) & 1);
           mbar_expect_tx(sigFull + s, 2 * G.planeBytes);
-          bulk_g2s(sigBuf(s, 0), src + (int64_t)(2 * c) * p.planeStrideBytes, G.planeBytes, sigFull + s);
-          bulk_g2s(sigBuf(s, 1), src + (int64_t)(2 * c + 1) * p.planeStrideBytes, G.planeBytes, sigFull + s);
+          if (p.l2hint & 1) {
+            bulk_g2s_hint(sigBuf(s, 0), src + (int64_t)(2 * c) * p.planeStrideBytes, G.planeBytes, sigFull + s, polSig);
+            bulk_g2s_hint(sigBuf(s, 1), src + (int64_t)(2 * c + 1) * p.planeStrideBytes, G.planeBytes, sigFull + s, polSig);
+          } else {
+            bulk_g2s(sigBuf(s, 0), src + (int64_t)(2 * c) * p.planeStrideBytes, G.planeBytes, sigFull + s);
+            bulk_g2s(sigBuf(s, 1), src + (int64_t)(2 * c + 1) * p.planeStrideBytes, G.planeBytes, sigFull + s);
+          }
           const uint32_t t = it % (uint32_t)G.tapStages, v = it / (uint32_t)G.tapStages;
           if (v > 0) tc_wait(tapFree + t, (v - 1) & 1);
           mbar_expect_tx(tapFull + t, G.tapsBytes);
-          bulk_g2s(tapBuf(t), p.taps + (size_t)c * G.tapsBytes, G.tapsBytes, tapFull + t);
+          if (p.l2hint & 2) bulk_g2s_hint(tapBuf(t), p.taps + (size_t)c * G.tapsBytes, G.tapsBytes, tapFull + t, polKeep);
+          else bulk_g2s(tapBuf(t), p.taps + (size_t)c * G.tapsBytes, G.tapsBytes, tapFull + t);
           it++;
         }
       }
@@ -392,9 +415,16 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
     for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, tileIt++) {
       uint32_t started = 0;     // bit i: accumulator i holds a partial sum of this tile
       if (kProf) tA = clock64();
-      if (tileIt > 0) tc_wait<false>(accEmpty, (tileIt - 1) & 1);   // the epilogue has drained the accumulators
+      // the epilogue has drained the temporal accumulators (0, 1) of the previous tile; the spectral ones (2..7) are
+      // only written from channel 1 on, 3 KS MMAs later, so the read-out of a tile overlaps the first MMAs of the next
+      if (tileIt > 0) tc_wait<false>(accEmptyT, (tileIt - 1) & 1);
       if (kProf) cAcc += clock64() - tA;
       for (int c = 0; c < p.numCh; c++, it++) {
+        if (c == 1 && tileIt > 0) {
+          if (kProf) tA = clock64();
+          tc_wait<false>(accEmpty, (tileIt - 1) & 1);
+          if (kProf) cAcc += clock64() - tA;
+        }
         const uint32_t s = it % (uint32_t)G.sigStages, u = it / (uint32_t)G.sigStages;
         const uint32_t t = it % (uint32_t)G.tapStages, v = it / (uint32_t)G.tapStages;
         if (kProf) tA = clock64();
@@ -484,8 +514,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
           const int w = jb + sg0 + e, rr = r + (w >> 6);
           const int64_t o = (tile + (rr >> 7)) * (int64_t)kT2Tile + ((int64_t)(w & 63) << 7) + (rr & 127);
           const uint2 a = __ldg(p.sideA + o);
-          const double x = t2_dbl(a.x);
-          w2.t1 += x; w2.t2 += x * x; w2.s1 += t2_dbl(a.y); w2.s2 += t2_dbl(__ldg(p.sideB + o));
+          const double x = (double)__uint_as_float(a.x);
+          w2.t1 += x; w2.t2 += x * x; w2.s1 += (double)__uint_as_float(a.y); w2.s2 += (double)__uint_as_float(__ldg(p.sideB + o));
         }
         tc_wait(sumsFull, tileIt & 1);
         if (kProf) { eSt += clock64() - tE; tE = clock64(); }
@@ -508,6 +538,18 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
         win.t1 = (win.t1 + w3.t1) + sgn * w2.t1; win.t2 = (win.t2 + w3.t2) + sgn * w2.t2;
         win.s1 = (win.s1 + w3.s1) + sgn * w2.s1; win.s2 = (win.s2 + w3.s2) + sgn * w2.s2;
       }
+      // centre on the mean of this window: mu as a Float, the centred sums from the exact ones in FP64
+      T2Win cw;
+      {
+        const float muT = (float)(win.t1 * E.invNTd), muS = (float)(win.s1 * E.invNSd);
+        const double mT = (double)muT, mS = (double)muS;
+        cw.c1T = (float)fma(-E.nT, mT, win.t1);
+        cw.c2T = (float)fma(mT, fma(E.nT, mT, -2.0 * win.t1), win.t2);
+        cw.c1S = (float)fma(-E.nS, mS, win.s1);
+        cw.c2S = (float)fma(mS, fma(E.nS, mS, -2.0 * win.s1), win.s2);
+        cw.nmuT = E.nTf * muT; cw.nmuS = E.nSf * muS;
+        cw.tmuT = 2.f * muT; cw.tmuS = 2.f * muS;
+      }
       if (kProf) { eInit += clock64() - tE; tE = clock64(); }
 
       // ---- accumulators -> registers ----
@@ -523,6 +565,11 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
         tc_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; i++) accT[i] = fmaf(__uint_as_float(w[i]), 1.0f / kTcLoScale, __uint_as_float(u[i]));
+        if (p.splitRelease) {
+          asm volatile("tcgen05.fence::before_thread_sync;");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(accEmptyT);
+        }
         tc_ld16_nowait(laneAddr + 2 * 64, u);
         tc_ld16_nowait(laneAddr + 3 * 64, w);
         tc_ld_wait();
@@ -539,7 +586,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
       }
       asm volatile("tcgen05.fence::before_thread_sync;");
       __syncwarp();
-      if (lane == 0) mbar_arrive(accEmpty);
+      if (lane == 0) { mbar_arrive(accEmpty); if (!p.splitRelease) mbar_arrive(accEmptyT); }
       if (kProf) { eLd += clock64() - tE; tE = clock64(); }
 
       // ---- 16 offsets: evaluate, slide the window by one frame ----
@@ -563,7 +610,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const int jj = 4 * blk + e;
-          if ((kProf && p.dbg & 8)) { oaN[e] = make_uint2(0x3fe00000u + jj, 0x40100000u); naN[e] = oaN[e]; ob2N[e] = nb2N[e] = 0x40000000u; }
+          if ((kProf && p.dbg & 8)) { oaN[e] = make_uint2(0x3f000000u + jj, 0x40800000u); naN[e] = oaN[e]; ob2N[e] = nb2N[e] = 0x40000000u; }
           else if (jj < 15) {
             oaN[e] = __ldg(p.sideA + (oOld + (uint32_t)(jj << 7))); ob2N[e] = __ldg(p.sideB + (oOld + (uint32_t)(jj << 7)));
             const uint32_t d = oNew + (uint32_t)(jj << 7) + (jj >= eWrap ? dWrap : 0u);
@@ -584,13 +631,15 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const int jj = 4 * blk + e;           // offset inside the thread's run; accumulator column 15 - jj of its group
-          simv[e] = ((kProf && p.dbg & 32)) ? accT[15 - jj] + accS[15 - jj] + (float)win.t1 : t2_eval(E, win, accT[15 - jj], accS[15 - jj]);
+          simv[e] = ((kProf && p.dbg & 32)) ? accT[15 - jj] + accS[15 - jj] + cw.c1T : t2_eval(E, cw, accT[15 - jj], accS[15 - jj]);
           if (jj < 15 && !((kProf && p.dbg & 16))) {
-            const double bo = t2_dbl(oa[e].x), bn = t2_dbl(na[e].x), d = bn - bo;
-            win.t1 += d;
-            win.t2 = fma(d, bn + bo, win.t2);
-            win.s1 += t2_dbl(na[e].y) - t2_dbl(oa[e].y);
-            win.s2 += t2_dbl(nb2[e]) - t2_dbl(ob2[e]);
+            // (x - mu)^2 entering minus leaving = d (bn + bo - 2 mu); per frame sum_c (x - mu)^2 = s2 - 2 mu s1 + C mu^2
+            const float bo = __uint_as_float(oa[e].x), bn = __uint_as_float(na[e].x), d = bn - bo;
+            cw.c1T += d;
+            cw.c2T = fmaf(d, (bn + bo) - cw.tmuT, cw.c2T);
+            const float d1 = __uint_as_float(na[e].y) - __uint_as_float(oa[e].y);
+            cw.c1S += d1;
+            cw.c2S += fmaf(-cw.tmuS, d1, __uint_as_float(nb2[e]) - __uint_as_float(ob2[e]));
           }
         }
         if (plain) {
@@ -632,7 +681,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
         if (kProf && (p.dbg & 4)) {     // no stores: keep the values alive through a branch that is never taken
           if (simv[0] + simv[1] + simv[2] + simv[3] == 123.456f) p.sim[0] = 1.f;
         } else {
-          *reinterpret_cast<float4 *>(p.sim + g0 + 4 * blk) = make_float4(simv[0], simv[1], simv[2], simv[3]);
+          if (p.l2hint & 4) __stcs(reinterpret_cast<float4 *>(p.sim + g0 + 4 * blk), make_float4(simv[0], simv[1], simv[2], simv[3]));
+          else *reinterpret_cast<float4 *>(p.sim + g0 + 4 * blk) = make_float4(simv[0], simv[1], simv[2], simv[3]);
         }
       }
       if (bestJ >= 0)
@@ -664,4 +714,5 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
+#undef accEmptyT
 }  // namespace sgz
