@@ -561,13 +561,18 @@ int sgz_corr_create(sgz_db *db, const sgz_corr_config *cfg, const void *input, i
     if (const char *e = getenv("SGZ_CORR_NSLOT")) job->nslot = atoi(e) == 2 ? 2 : 3;   // tuning override
     if (job->ntg > 0 && corr_smem_layout(job->ntg, db->numPairs, wq, job->nslot).total > job->ctx->smemOptin) job->nslot = 2;
     if (job->ntg > 0 && corr_smem_layout(job->ntg, db->numPairs, wq, job->nslot).total > job->ctx->smemOptin) job->ntg = 0;
-    if (job->ntg == 0) {
-      set_error("punch window of %d feature frames does not fit the shared-memory tile", wq);
+    // windows that do not fit the FFMA2 kernel's shared-memory tile (> ~1500 frames) run on the tensor-core kernel alone
+    // (corr_tc2.cuh cuts long windows into passes: no length limit short of the zero slack behind the database)
+    const bool t2ok = job->qin.dT2Taps.p && (!job->hasOut || job->qout.dT2Taps.p) &&
+                      !(getenv("SGZ_CORR_TC") && atoi(getenv("SGZ_CORR_TC")) == 0) &&
+                      !(getenv("SGZ_CORR_TC2") && atoi(getenv("SGZ_CORR_TC2")) == 0);
+    if (job->ntg == 0 && !t2ok) {
+      set_error("punch window of %d feature frames does not fit any scan kernel", wq);
       rc = SGZ_ERR_INVALID;
     }
   }
   if (rc != SGZ_OK) { delete job; return rc; }
-  job->numTiles = ceil_div<int64_t>(std::max<int64_t>(db->usedFrames, 1), (int64_t)kR * job->ntg);
+  job->numTiles = job->ntg > 0 ? ceil_div<int64_t>(std::max<int64_t>(db->usedFrames, 1), (int64_t)kR * job->ntg) : 0;
   job->numTilesTc = ceil_div<int64_t>(std::max<int64_t>(db->usedFrames, 1), (int64_t)kTcTile);
   {
     // K1 on the tensor cores (corr_tc.cuh) wherever it applies (<= 14 channels, window <= 256 frames); the FFMA2
@@ -670,7 +675,7 @@ int sgz_corr_scan(sgz_corr *job) {
         const bool last = c.uptoFrame == INT64_MAX;
         const int64_t ready = last ? INT64_MAX : c.uptoFrame / kPlaneFrames * kPlaneFrames;
         const int64_t end = last ? job->numTilesT2
-                                 : std::min<int64_t>(job->numTilesT2, std::max<int64_t>(ready - std::max(320, wqMax + 32), 0) / kT2Tile);
+                                 : std::min<int64_t>(job->numTilesT2, std::max<int64_t>(ready - std::max(320, wqMax + 384), 0) / kT2Tile);
         if (end <= done && !last) continue;
         SGZ_CUDA(cudaStreamWaitEvent(ss, c.ev, 0));
         SGZ_TRY(db_ensure_planes(db, last ? -1 : c.uptoFrame, ss));

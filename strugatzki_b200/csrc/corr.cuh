@@ -99,12 +99,13 @@ inline bool tc_applicable(const sgz_ctx *ctx, int numCh, int W) {
   return numCh >= 2 && numCh <= 14 && W >= 1 && W <= 256 && tc_geom(W).smemBytes <= ctx->smemOptin;
 }
 
-// the N = 64 kernel takes any channel count (the spectral channels share five accumulators) and every window whose
-// operand / taps rings fit shared memory (W <~ 900 frames with the minimum of two stages each)
+// the N = 64 kernel takes any channel count (the spectral channels share five accumulators) and any window: beyond 257
+// frames it runs in passes of 16 K steps (T2Geom); the limit is the zero slack behind the database (kDbSlack) that the
+// tiles of the last file read into
 inline bool t2_applicable(const sgz_ctx *ctx, int numCh, int W) {
   // (32-bit element indices into the per-frame arrays: databases beyond 2^32 - 2^16 frames = 13 000 h per GPU are refused
   // by db_ensure_planes)
-  return numCh >= 2 && W >= 1 && W <= 4096 && t2_geom(W, ctx->smemOptin).smemBytes <= ctx->smemOptin;
+  return numCh >= 2 && W >= 1 && W <= 7680 && t2_geom(W, ctx->smemOptin).smemBytes <= ctx->smemOptin;
 }
 
 // FP16 planes and per-frame sums of the frames [db->planesUpto, upto) -- whole 2048-frame blocks; upto < 0 = everything
@@ -205,7 +206,7 @@ inline int prepare_query(const sgz_db *db, const float *inputPlanar /*[numCh][in
     k_t2_query<<<ceil_div(numCh * W, 256), 256, 0, st>>>(q.dA.p, numCh, W, -meanT, -meanS, q.dAc.p);
     SGZ_LAUNCH_CHECK(db->ctx);
     const T2Geom g = t2_geom(W, db->ctx->smemOptin);
-    SGZ_TRY(q.dT2Taps.alloc((size_t)numCh * g.tapsBytes));
+    SGZ_TRY(q.dT2Taps.alloc((size_t)numCh * g.tapsFullBytes));
     k_t2_taps<<<numCh, 256, 0, st>>>(reinterpret_cast<const float2 *>(q.dTaps.p), numCh, q.Wq, W, q.dT2Taps.p);
     SGZ_LAUNCH_CHECK(db->ctx);
   }
@@ -400,7 +401,7 @@ inline int run_scan_t2(sgz_corr *job, PunchQuery &q, int which, int tailExtra, f
     tp.l2hint = l2hint;
   }
   const bool prof = getenv("SGZ_CORR_TC_PROF") != nullptr;   // developer probe: cycles per role and phase
-  auto kern = prof ? k_corr_tc2<true> : k_corr_tc2<false>;
+  auto kern = G.NP > 1 ? (prof ? k_corr_tc2<true, true> : k_corr_tc2<false, true>) : (prof ? k_corr_tc2<true, false> : k_corr_tc2<false, false>);
   SGZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));
   const unsigned grid = (unsigned)std::min<int64_t>(tileEnd - tileBegin, std::max(ctx->smCount - spareSMs, 1));
   DevBuf<long long> dProf;

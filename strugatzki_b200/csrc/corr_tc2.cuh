@@ -31,11 +31,19 @@ constexpr int kT2Mains = 5;               // spectral main accumulators
 constexpr int kT2Ahead = 0;               // channels between an L2 prefetch of a signal stage and its bulk copy: 0 = none (measured: no gain, the ring itself keeps the bytes in flight)
 constexpr int kT2EpiWarps = 16, kT2Threads = (4 + kT2EpiWarps) * 32;
 
+constexpr int kT2PassKS = 16;             // K steps per pass of a long window (chains of <= 3 x 16 MMAs per accumulator)
+constexpr int kT2SinglePassKS = 20;       // windows up to 257 frames take one pass
+
 struct T2Geom {
   int W, KS, natom, rows, sumRows, sumPitch;
+  // long windows (more than kT2SinglePassKS K steps) are cut into NP passes of KS (= kT2PassKS) K steps, the last one of
+  // KSlast: pass j multiplies the signal shifted by 256 j frames with the taps atoms [32 j, 32 j + natom); the epilogue
+  // adds the accumulators of the passes in registers.  One pass: NP = 1, KS = KSlast = all K steps.
+  int NP, KSlast, natomFull;
   uint32_t planeBytes;      // one FP16 part of one channel of one tile (rows x 128 B)
   uint32_t planeStride;     // placement stride in shared memory (multiple of 1024)
-  uint32_t tapsBytes;       // taps of one channel: first-part atoms then second-part atoms
+  uint32_t tapsBytes;       // taps of one channel and pass: first-part atoms then second-part atoms
+  uint32_t tapsFullBytes;   // taps image of one channel in global memory: [natomFull first-part atoms][... second-part atoms]
   uint32_t tapsStride;
   uint32_t sumsBytes;
   int sigStages, tapStages;
@@ -45,12 +53,17 @@ struct T2Geom {
 __host__ __device__ inline T2Geom t2_geom(int W, size_t smemMax = 232448) {
   T2Geom g;
   g.W = W;
-  g.KS = (kT2P - 1 + W + 15) / 16;
+  const int ksAll = (kT2P - 1 + W + 15) / 16;
+  if (ksAll <= kT2SinglePassKS) { g.KS = ksAll; g.NP = 1; g.KSlast = ksAll; }
+  else { g.KS = kT2PassKS; g.NP = (ksAll + kT2PassKS - 1) / kT2PassKS; g.KSlast = ksAll - (g.NP - 1) * kT2PassKS; }
   g.natom = 2 * g.KS + 6;
+  g.natomFull = 2 * g.KS * g.NP + 6;
   g.rows = kT2M - 1 + (g.KS + 3) / 4;               // row 127 runs on for 16 KS halves
   g.planeBytes = (uint32_t)g.rows * 128u;
-  g.planeStride = (g.planeBytes + 1023u) / 1024u * 1024u;
+  // odd passes start 4 rows into the 8-row swizzle period of their source: they are placed 512 bytes into the stage
+  g.planeStride = (g.planeBytes + (g.NP > 1 ? 512u : 0u) + 1023u) / 1024u * 1024u;
   g.tapsBytes = (uint32_t)g.natom * 256u * 2u;
+  g.tapsFullBytes = (uint32_t)g.natomFull * 256u * 2u;
   g.tapsStride = (g.tapsBytes + 1023u) / 1024u * 1024u;
   g.sumRows = kT2M + (W + 63) / 64;                  // 64-frame rows that windows starting in the tile can touch
   g.sumPitch = (g.sumRows + 1) & ~1;                 // bulk copies move multiples of 16 bytes
@@ -81,11 +94,11 @@ __host__ __device__ inline int64_t t2_side_index(int64_t g) {
 // per channel): the float taps are a few KB and reach the device as an inline copy even while database uploads occupy
 // the copy engine (streaming scans)
 __global__ void k_t2_taps(const float2 *__restrict__ pairTaps, int numCh, int Wq, int W, unsigned char *__restrict__ out) {
-  const T2Geom g = t2_geom(W);   // natom / tapsBytes do not depend on the shared-memory limit
+  const T2Geom g = t2_geom(W);   // natomFull / tapsFullBytes do not depend on the shared-memory limit
   const int c = blockIdx.x;
   const float *tp = reinterpret_cast<const float *>(pairTaps + (size_t)(c >> 1) * Wq) + (c & 1);
-  for (int i = threadIdx.x; i < 2 * g.natom * 128; i += blockDim.x) {
-    const int part = i / (g.natom * 128), rem = i - part * g.natom * 128;
+  for (int i = threadIdx.x; i < 2 * g.natomFull * 128; i += blockDim.x) {
+    const int part = i / (g.natomFull * 128), rem = i - part * g.natomFull * 128;
     const int a = rem >> 7, cc = (rem >> 4) & 7, kk = rem & 15;
     const int q = 8 * a + kk + cc - (kT2P - 1);
     __half v = __float2half_rn(0.f);
@@ -94,7 +107,7 @@ __global__ void k_t2_taps(const float2 *__restrict__ pairTaps, int numCh, int Wq
       const __half t1 = __float2half_rn(t);
       v = part == 0 ? t1 : __float2half_rn((t - __half2float(t1)) * kTcLoScale);
     }
-    const size_t byteOff = (size_t)c * g.tapsBytes + (size_t)part * g.natom * 256 + (size_t)a * 256 + (size_t)cc * 32 +
+    const size_t byteOff = (size_t)c * g.tapsFullBytes + (size_t)part * g.natomFull * 256 + (size_t)a * 256 + (size_t)cc * 32 +
                            (size_t)(((kk >> 3) ^ ((cc >> 2) & 1)) << 4) + (size_t)(kk & 7) * 2;
     *reinterpret_cast<__half *>(out + byteOff) = v;
   }
@@ -260,7 +273,8 @@ struct CorrT2Params {
   uint32_t *fixList, *fixCount; // offsets whose windows are ill-conditioned (corr_fix.cuh)
   uint32_t fixCap;
   long long *prof;              // SGZ_CORR_TC_PROF: per CTA 24 cycle counters (k_corr_tc2<true>), or nullptr
-  int smemMax;                  // the geometry (ring depths) is a function of (W, shared memory limit)
+  int smemMax;                  // the geometry (ring depths) is a function of (W, shared memory limit); computed per thread --
+                                // passed as a parameter block it cost the epilogue more registers (ptxas)
   int ahead;                    // channels between the L2 prefetch of a signal stage and its bulk copy (0: no prefetch)
   int l2hint;                   // bit 0: signal planes evict_first, bit 1: taps + block sums evict_last, bit 2: streaming curve stores
   int splitRelease;             // 1: the epilogue hands the two temporal accumulators back before it reads the spectral ones
@@ -318,10 +332,12 @@ __device__ __forceinline__ float t2_eval(const T2Eval &E, const T2Win &w, float 
 
 // warp 0: producer (bulk copies), warp 1: MMA issuer, warps 2-3: idle (they complete the first warpgroup, which hands most
 // of its registers to the others: setmaxnreg), warps 4..19: epilogue
-template <bool kProf>
+// kMulti: long windows, several passes per tile (T2Geom::NP > 1)
+template <bool kProf, bool kMulti>
 __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p) {
   extern __shared__ __align__(1024) unsigned char smemRaw[];
   const T2Geom G = t2_geom(p.W, (size_t)p.smemMax);
+  const int NP = kMulti ? G.NP : 1;
   unsigned char *base = smemRaw + ((1024 - (smem_u32(smemRaw) & 1023)) & 1023);
   auto sigBuf = [&](int s, int part) { return base + (size_t)(2 * s + part) * G.planeStride; };
   unsigned char *tapsBase = base + (size_t)G.sigStages * 2 * G.planeStride;
@@ -365,8 +381,12 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
       for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, tileIt++) {
         const unsigned char *src = p.planes + tile * (int64_t)(kT2Tile * 2);
         bool sumsPending = true;     // the block sums of this tile overwrite those of the previous one: once its windows are set up
+        for (int j = 0; j < NP; j++) {
+        const bool lastPass = j == NP - 1;
+        const uint32_t shift = (uint32_t)j * (uint32_t)(G.KS * 32);   // pass j reads the signal 16 KS frames further on
+        const uint32_t dOff = (j & 1) ? 512u : 0u;                    // ... which starts 4 j rows into the swizzle period
         for (int c = 0; c <= p.numCh; c++) {
-          if (sumsPending && (c == p.numCh || tileIt == 0 || t2_test(sumsFree, (tileIt - 1) & 1))) {
+          if (sumsPending && ((c == p.numCh && lastPass) || tileIt == 0 || t2_test(sumsFree, (tileIt - 1) & 1))) {
             if (tileIt > 0) tc_wait(sumsFree, (tileIt - 1) & 1);
             mbar_expect_tx(sumsFull, G.sumsBytes);
             for (int k = 0; k < 16; k++)
@@ -389,19 +409,27 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
           const uint32_t s = it % (uint32_t)G.sigStages, u = it / (uint32_t)G.sigStages;
           if (u > 0) tc_wait(sigFree + s, (u - 1) & 1);
           mbar_expect_tx(sigFull + s, 2 * G.planeBytes);
-          if (p.l2hint & 1) {
-            bulk_g2s_hint(sigBuf(s, 0), src + (int64_t)(2 * c) * p.planeStrideBytes, G.planeBytes, sigFull + s, polSig);
-            bulk_g2s_hint(sigBuf(s, 1), src + (int64_t)(2 * c + 1) * p.planeStrideBytes, G.planeBytes, sigFull + s, polSig);
+          const unsigned char *s0 = src + (int64_t)(2 * c) * p.planeStrideBytes + shift, *s1 = s0 + p.planeStrideBytes;
+          if ((p.l2hint & 1) && lastPass) {     // earlier passes: the planes of this tile come again
+            bulk_g2s_hint(sigBuf(s, 0) + dOff, s0, G.planeBytes, sigFull + s, polSig);
+            bulk_g2s_hint(sigBuf(s, 1) + dOff, s1, G.planeBytes, sigFull + s, polSig);
           } else {
-            bulk_g2s(sigBuf(s, 0), src + (int64_t)(2 * c) * p.planeStrideBytes, G.planeBytes, sigFull + s);
-            bulk_g2s(sigBuf(s, 1), src + (int64_t)(2 * c + 1) * p.planeStrideBytes, G.planeBytes, sigFull + s);
+            bulk_g2s(sigBuf(s, 0) + dOff, s0, G.planeBytes, sigFull + s);
+            bulk_g2s(sigBuf(s, 1) + dOff, s1, G.planeBytes, sigFull + s);
           }
           const uint32_t t = it % (uint32_t)G.tapStages, v = it / (uint32_t)G.tapStages;
           if (v > 0) tc_wait(tapFree + t, (v - 1) & 1);
           mbar_expect_tx(tapFull + t, G.tapsBytes);
-          if (p.l2hint & 2) bulk_g2s_hint(tapBuf(t), p.taps + (size_t)c * G.tapsBytes, G.tapsBytes, tapFull + t, polKeep);
-          else bulk_g2s(tapBuf(t), p.taps + (size_t)c * G.tapsBytes, G.tapsBytes, tapFull + t);
+          const unsigned char *tsrc = p.taps + (size_t)c * G.tapsFullBytes + (size_t)j * (size_t)(2 * G.KS * 256);
+          if (!kMulti) {
+            if (p.l2hint & 2) bulk_g2s_hint(tapBuf(t), tsrc, G.tapsBytes, tapFull + t, polKeep);
+            else bulk_g2s(tapBuf(t), tsrc, G.tapsBytes, tapFull + t);
+          } else {   // the atoms [32 j, 32 j + natom) of both parts
+            bulk_g2s(tapBuf(t), tsrc, (uint32_t)G.natom * 256u, tapFull + t);
+            bulk_g2s(tapBuf(t) + (size_t)G.natom * 256, tsrc + (size_t)G.natomFull * 256, (uint32_t)G.natom * 256u, tapFull + t);
+          }
           it++;
+        }
         }
       }
     }
@@ -409,20 +437,23 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
     // =========================== MMA issuer ===========================
     // D = F32, A = B = F16, both K-major, N = 64, M = 128
     const uint32_t idesc = (1u << 4) | ((uint32_t)(kT2P >> 3) << 17) | ((uint32_t)(kT2M >> 4) << 24);
-    uint32_t it = 0, tileIt = 0;
+    uint32_t it = 0, tileIt = 0, passIt = 0;
     long long cAcc = 0, cSig = 0, cTap = 0, cIssue = 0, cTotal = 0, tA = 0;
     if (kProf) cTotal = clock64();
     for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, tileIt++) {
-      uint32_t started = 0;     // bit i: accumulator i holds a partial sum of this tile
+      for (int j = 0; j < NP; j++, passIt++) {
+      const int nk = j == NP - 1 ? G.KSlast : G.KS;
+      const uint32_t dOff = (j & 1) ? 512u : 0u;
+      uint32_t started = 0;     // bit i: accumulator i holds a partial sum of this pass
       if (kProf) tA = clock64();
-      // the epilogue has drained the temporal accumulators (0, 1) of the previous tile; the spectral ones (2..7) are
-      // only written from channel 1 on, 3 KS MMAs later, so the read-out of a tile overlaps the first MMAs of the next
-      if (tileIt > 0) tc_wait<false>(accEmptyT, (tileIt - 1) & 1);
+      // the epilogue has drained the temporal accumulators (0, 1) of the previous pass; the spectral ones (2..7) are
+      // only written from channel 1 on, 3 KS MMAs later, so the read-out of a pass overlaps the first MMAs of the next
+      if (passIt > 0) tc_wait<false>(accEmptyT, (passIt - 1) & 1);
       if (kProf) cAcc += clock64() - tA;
       for (int c = 0; c < p.numCh; c++, it++) {
-        if (c == 1 && tileIt > 0) {
+        if (c == 1 && passIt > 0) {
           if (kProf) tA = clock64();
-          tc_wait<false>(accEmpty, (tileIt - 1) & 1);
+          tc_wait<false>(accEmpty, (passIt - 1) & 1);
           if (kProf) cAcc += clock64() - tA;
         }
         const uint32_t s = it % (uint32_t)G.sigStages, u = it / (uint32_t)G.sigStages;
@@ -437,14 +468,14 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
         const uint32_t dMain = tmem + 64u * iMain, dCorr = tmem + 64u * iCorr;
         const uint32_t accMain = (started >> iMain) & 1u, accCorr = (started >> iCorr) & 1u;
         started |= (1u << iMain) | (1u << iCorr);
-        const uint64_t aHi = tc_desc(smem_u32(sigBuf(s, 0)), 1024, 2), aLo = tc_desc(smem_u32(sigBuf(s, 1)), 1024, 2);
+        const uint64_t aHi = tc_desc(smem_u32(sigBuf(s, 0)) + dOff, 1024, 2), aLo = tc_desc(smem_u32(sigBuf(s, 1)) + dOff, 1024, 2);
         const uint32_t tHiA = smem_u32(tapBuf(t));
         const uint64_t tHi = tc_desc(tHiA, 256, 6), tLo = tc_desc(tHiA + (uint32_t)G.natom * 256u, 256, 6);
         if (tc_elect()) {
           // one K step of 16: A start +32 B (2 descriptor units), taps start +2 atoms = 512 B (32 units); a1 t1 and
           // a1 t2 share the A operand through the collector
           uint64_t d1 = aHi, d2 = aLo, b1 = tHi, b2 = tLo;
-          for (int k = 0; k < G.KS; k++, d1 += 2, d2 += 2, b1 += 32, b2 += 32) {
+          for (int k = 0; k < nk; k++, d1 += 2, d2 += 2, b1 += 32, b2 += 32) {
             if ((kProf && p.dbg & 1)) break;
             tc_mma_fill(dMain, d1, b1, idesc, accMain | (uint32_t)(k > 0));
             tc_mma_lastuse(dCorr, d1, b2, idesc, accCorr | (uint32_t)(k > 0));
@@ -456,6 +487,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
         }
         __syncwarp();
         if (kProf) cIssue += clock64() - tA;
+      }
       }
     }
     if (kProf && p.prof && lane == 0) {
@@ -478,7 +510,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
     const int nb = W >> 4, left = W & 15;
     const int nbk = left > 8 ? nb + 1 : nb, nsg = left > 8 ? 16 - left : left, sg0 = left > 8 ? W : nb << 4;
     const double sgn = left > 8 ? -1.0 : 1.0;
-    uint32_t tileIt = 0;
+    uint32_t tileIt = 0, passIt = 0;
     long long eAcc = 0, eLd = 0, eSt = 0, eInit = 0, eMain = 0, tE = 0;
     for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, tileIt++) {
       const int64_t t0 = tile * kT2Tile;
@@ -552,19 +584,22 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
       }
       if (kProf) { eInit += clock64() - tE; tE = clock64(); }
 
-      // ---- accumulators -> registers ----
-      tc_wait(accFull, tileIt & 1);
-      if (kProf) { eAcc += clock64() - tE; tE = clock64(); }
-      asm volatile("tcgen05.fence::after_thread_sync;");
+      // ---- accumulators -> registers (long windows: the sum over the passes) ----
       const uint32_t laneAddr = tmem + ((uint32_t)(quarter * 32) << 16) + 16u * (uint32_t)jg;
       float accT[16], accS[16];
-      {
+      for (int j = 0; j < NP; j++, passIt++) {
+        tc_wait(accFull, passIt & 1);
+        if (kProf) { eAcc += clock64() - tE; tE = clock64(); }
+        asm volatile("tcgen05.fence::after_thread_sync;");
         uint32_t u[16], w[16];
         tc_ld16_nowait(laneAddr + 0 * 64, u);
         tc_ld16_nowait(laneAddr + 1 * 64, w);
         tc_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; i++) accT[i] = fmaf(__uint_as_float(w[i]), 1.0f / kTcLoScale, __uint_as_float(u[i]));
+        for (int i = 0; i < 16; i++) {
+          const float v = fmaf(__uint_as_float(w[i]), 1.0f / kTcLoScale, __uint_as_float(u[i]));
+          accT[i] = j == 0 ? v : accT[i] + v;
+        }
         if (p.splitRelease) {
           asm volatile("tcgen05.fence::before_thread_sync;");
           __syncwarp();
@@ -574,7 +609,10 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
         tc_ld16_nowait(laneAddr + 3 * 64, w);
         tc_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; i++) accS[i] = fmaf(__uint_as_float(u[i]), 1.0f / kTcLoScale, __uint_as_float(w[i]));
+        for (int i = 0; i < 16; i++) {
+          const float v = fmaf(__uint_as_float(u[i]), 1.0f / kTcLoScale, __uint_as_float(w[i]));
+          accS[i] = j == 0 ? v : accS[i] + v;
+        }
         const int nMain = min(p.numCh - 1, kT2Mains);
         for (int m = 1; m < nMain; m += 2) {
           tc_ld16_nowait(laneAddr + (uint32_t)(3 + m) * 64, u);
@@ -583,10 +621,11 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
 #pragma unroll
           for (int i = 0; i < 16; i++) accS[i] += __uint_as_float(u[i]) + (m + 1 < nMain ? __uint_as_float(w[i]) : 0.f);
         }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(accEmpty); if (!p.splitRelease) mbar_arrive(accEmptyT); }
+        if (kProf) tE = clock64();
       }
-      asm volatile("tcgen05.fence::before_thread_sync;");
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(accEmpty); if (!p.splitRelease) mbar_arrive(accEmptyT); }
       if (kProf) { eLd += clock64() - tE; tE = clock64(); }
 
       // ---- 16 offsets: evaluate, slide the window by one frame ----

@@ -293,6 +293,26 @@ def test_corr_edge_cases(ctx):
     assert_sims_close(sim, want, what="W=689 curve")
 
 
+@pytest.mark.parametrize("W", [258, 1723, 3000])
+def test_corr_long_windows_run_in_passes_on_the_tensor_cores(ctx, W):
+    """The reference accepts any punch span (FeatureCorrelationImpl.scala:83-98,154).  Beyond 257 frames the tensor-core
+    K1 cuts the window into passes of 16 K steps (corr_tc2.cuh, T2Geom): 258 is the first two-pass window, 1723 = 20 s and
+    3000 = 35 s do not fit the FFMA2 kernel's shared-memory tile at all (round 1 returned SGZ_ERR_INVALID there)."""
+    from strugatzki_b200 import engine
+    files, norm = make_db(3, [W + 1500, W + 40, 2 * W + 700])
+    inp = make_input(W + 300)
+    plant_needles(files, inp[:W], [(0, 1000), (2, W + 77)])
+    op, nc = corr_cfgs(inp, norm, punch_in=(0, W * STEP), num_matches=4, num_per_file=2)
+    job = engine.CorrelationJob(build_db(ctx, files, norm), nc, inp)
+    got = job.run()
+    assert_matches_equal(got, O.corr_search(op, files))
+    assert {(m["file"], m["start"]) for m in got[:2]} == {(0, 1000 * STEP), (2, (W + 77) * STEP)}
+    for i, f in enumerate(files):
+        want, _ = O.corr_curve(op, f)
+        sim, _ = job.curve(i, 0, 0, len(want))
+        assert_sims_close(sim, want, rel=1e-5, abs_tol=2e-6, what=f"W={W} file {i}")
+
+
 def test_corr_digital_silence_gives_nan_like_the_reference(ctx):
     """a constant loudness stretch has zero variance: the reference returns NaN sims (0/0) and, while the result
     list still has space, inserts them at the head; the engine must do the same"""
