@@ -363,8 +363,11 @@ inline int run_scan_t2(sgz_corr *job, PunchQuery &q, int which, int tailExtra, f
   if (tileEnd <= tileBegin) return SGZ_OK;
   sgz_db *db = job->db;
   sgz_ctx *ctx = job->ctx;
-  const T2Geom G = t2_geom(q.W, ctx->smemOptin);
+  static const int ring = getenv("SGZ_T2_RING") ? (int)strtol(getenv("SGZ_T2_RING"), nullptr, 16) : 0x43;   // developer knob
+  const T2Geom G = t2_geom(q.W, ctx->smemOptin, ring);
   CorrT2Params tp{};
+  tp.ring = ring;
+  tp.tapsFirst = getenv("SGZ_T2_TAPS_FIRST") ? atoi(getenv("SGZ_T2_TAPS_FIRST")) : 0;
   tp.planes = db->dPlanes.p; tp.planeStrideBytes = db->planeStrideBytes;
   tp.sideA = db->dSideA.p; tp.sideB = db->dSideB.p;
   tp.b16 = db->dB16.p; tp.rowsTotal = db->planeRows;
@@ -397,7 +400,7 @@ inline int run_scan_t2(sgz_corr *job, PunchQuery &q, int which, int tailExtra, f
     tp.dbg = getenv("SGZ_T2_DBG") ? atoi(getenv("SGZ_T2_DBG")) : 0;
     static const int split = getenv("SGZ_T2_SPLIT") ? atoi(getenv("SGZ_T2_SPLIT")) : 1;                 // developer knob
     tp.splitRelease = split;
-    static const int l2hint = getenv("SGZ_T2_L2HINT") ? atoi(getenv("SGZ_T2_L2HINT")) : 1;             // developer knob
+    static const int l2hint = getenv("SGZ_T2_L2HINT") ? atoi(getenv("SGZ_T2_L2HINT")) : 7;             // developer knob
     tp.l2hint = l2hint;
   }
   const bool prof = getenv("SGZ_CORR_TC_PROF") != nullptr;   // developer probe: cycles per role and phase

@@ -50,7 +50,7 @@ struct T2Geom {
   size_t smemBytes;
 };
 
-__host__ __device__ inline T2Geom t2_geom(int W, size_t smemMax = 232448) {
+__host__ __device__ inline T2Geom t2_geom(int W, size_t smemMax = 232448, int ring = 0x43) {
   T2Geom g;
   g.W = W;
   const int ksAll = (kT2P - 1 + W + 15) / 16;
@@ -68,8 +68,8 @@ __host__ __device__ inline T2Geom t2_geom(int W, size_t smemMax = 232448) {
   g.sumRows = kT2M + (W + 63) / 64;                  // 64-frame rows that windows starting in the tile can touch
   g.sumPitch = (g.sumRows + 1) & ~1;                 // bulk copies move multiples of 16 bytes
   g.sumsBytes = (uint32_t)(16 * g.sumPitch * 8);     // [4 quantities][4 column blocks][sumPitch] doubles
-  g.sigStages = 4;
-  g.tapStages = 3;
+  g.sigStages = ring >> 4;          // initial ring depths (signal, taps); reduced below until they fit
+  g.tapStages = ring & 15;
   for (;;) {
     g.smemBytes = (size_t)g.sigStages * 2 * g.planeStride + (size_t)g.tapStages * g.tapsStride + g.sumsBytes +
                   1024 /*alignment slack*/ + 256 /*barriers*/;
@@ -276,6 +276,8 @@ struct CorrT2Params {
   int smemMax;                  // the geometry (ring depths) is a function of (W, shared memory limit); computed per thread --
                                 // passed as a parameter block it cost the epilogue more registers (ptxas)
   int ahead;                    // channels between the L2 prefetch of a signal stage and its bulk copy (0: no prefetch)
+  int ring;                     // initial ring depths (signal << 4 | taps) of t2_geom
+  int tapsFirst;                // developer knob: request the taps of a channel before its planes
   int l2hint;                   // bit 0: signal planes evict_first, bit 1: taps + block sums evict_last, bit 2: streaming curve stores
   int splitRelease;             // 1: the epilogue hands the two temporal accumulators back before it reads the spectral ones
   int dbg;                      // developer knob (SGZ_T2_DBG, profiling build only): 1 = no MMAs, 2 = no per-offset work, 4 = no curve stores, 8 = no per-frame loads, 16 = no window slides, 32 = no evaluation
@@ -336,7 +338,7 @@ __device__ __forceinline__ float t2_eval(const T2Eval &E, const T2Win &w, float 
 template <bool kProf, bool kMulti>
 __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p) {
   extern __shared__ __align__(1024) unsigned char smemRaw[];
-  const T2Geom G = t2_geom(p.W, (size_t)p.smemMax);
+  const T2Geom G = t2_geom(p.W, (size_t)p.smemMax, p.ring);
   const int NP = kMulti ? G.NP : 1;
   unsigned char *base = smemRaw + ((1024 - (smem_u32(smemRaw) & 1023)) & 1023);
   auto sigBuf = [&](int s, int part) { return base + (size_t)(2 * s + part) * G.planeStride; };
@@ -344,14 +346,15 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
   auto tapBuf = [&](int s) { return tapsBase + (size_t)s * G.tapsStride; };
   double *B16 = reinterpret_cast<double *>(tapsBase + (size_t)G.tapStages * G.tapsStride);   // [q][cb][sumPitch]
   uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(B16) + G.sumsBytes);
-  uint64_t *sigFull = bars, *sigFree = bars + 4, *tapFull = bars + 8, *tapFree = bars + 12;
-  uint64_t *accFull = bars + 16, *accEmpty = bars + 17, *sumsFull = bars + 18, *sumsFree = bars + 19;
-  uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(bars + 20);
+  uint64_t *sigFull = bars, *sigFree = bars + 8, *tapFull = bars + 16, *tapFree = bars + 20;
+  uint64_t *accFull = bars + 24, *accEmpty = bars + 25, *sumsFull = bars + 26, *sumsFree = bars + 27;
+  uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(bars + 28);
 #define accEmptyT (accEmpty + 4)      // accumulators 0 and 1 (temporal channel) drained; accEmpty: 2..7 (spectral channels)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int s = 0; s < 4; s++) { mbar_init(sigFull + s, 1); mbar_init(sigFree + s, 1); mbar_init(tapFull + s, 1); mbar_init(tapFree + s, 1); }
+    for (int s = 0; s < 8; s++) { mbar_init(sigFull + s, 1); mbar_init(sigFree + s, 1); }
+    for (int s = 0; s < 4; s++) { mbar_init(tapFull + s, 1); mbar_init(tapFree + s, 1); }
     mbar_init(accFull, 1);
     mbar_init(accEmpty, kT2EpiWarps);
     mbar_init(accEmptyT, kT2EpiWarps);
@@ -406,28 +409,33 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
               for (int k = 0; k < 16; k++)
                 t2_prefetch_l2(p.b16 + (int64_t)k * p.rowsTotal + (tile + gridDim.x) * kT2M, (uint32_t)G.sumPitch * 8u);
           }
-          const uint32_t s = it % (uint32_t)G.sigStages, u = it / (uint32_t)G.sigStages;
-          if (u > 0) tc_wait(sigFree + s, (u - 1) & 1);
-          mbar_expect_tx(sigFull + s, 2 * G.planeBytes);
-          const unsigned char *s0 = src + (int64_t)(2 * c) * p.planeStrideBytes + shift, *s1 = s0 + p.planeStrideBytes;
-          if ((p.l2hint & 1) && lastPass) {     // earlier passes: the planes of this tile come again
-            bulk_g2s_hint(sigBuf(s, 0) + dOff, s0, G.planeBytes, sigFull + s, polSig);
-            bulk_g2s_hint(sigBuf(s, 1) + dOff, s1, G.planeBytes, sigFull + s, polSig);
-          } else {
-            bulk_g2s(sigBuf(s, 0) + dOff, s0, G.planeBytes, sigFull + s);
-            bulk_g2s(sigBuf(s, 1) + dOff, s1, G.planeBytes, sigFull + s);
-          }
-          const uint32_t t = it % (uint32_t)G.tapStages, v = it / (uint32_t)G.tapStages;
-          if (v > 0) tc_wait(tapFree + t, (v - 1) & 1);
-          mbar_expect_tx(tapFull + t, G.tapsBytes);
-          const unsigned char *tsrc = p.taps + (size_t)c * G.tapsFullBytes + (size_t)j * (size_t)(2 * G.KS * 256);
-          if (!kMulti) {
-            if (p.l2hint & 2) bulk_g2s_hint(tapBuf(t), tsrc, G.tapsBytes, tapFull + t, polKeep);
-            else bulk_g2s(tapBuf(t), tsrc, G.tapsBytes, tapFull + t);
-          } else {   // the atoms [32 j, 32 j + natom) of both parts
-            bulk_g2s(tapBuf(t), tsrc, (uint32_t)G.natom * 256u, tapFull + t);
-            bulk_g2s(tapBuf(t) + (size_t)G.natom * 256, tsrc + (size_t)G.natomFull * 256, (uint32_t)G.natom * 256u, tapFull + t);
-          }
+          auto issue_sig = [&]() {
+            const uint32_t s = it % (uint32_t)G.sigStages, u = it / (uint32_t)G.sigStages;
+            if (u > 0) tc_wait(sigFree + s, (u - 1) & 1);
+            mbar_expect_tx(sigFull + s, 2 * G.planeBytes);
+            const unsigned char *s0 = src + (int64_t)(2 * c) * p.planeStrideBytes + shift, *s1 = s0 + p.planeStrideBytes;
+            if ((p.l2hint & 1) && lastPass) {     // earlier passes: the planes of this tile come again
+              bulk_g2s_hint(sigBuf(s, 0) + dOff, s0, G.planeBytes, sigFull + s, polSig);
+              bulk_g2s_hint(sigBuf(s, 1) + dOff, s1, G.planeBytes, sigFull + s, polSig);
+            } else {
+              bulk_g2s(sigBuf(s, 0) + dOff, s0, G.planeBytes, sigFull + s);
+              bulk_g2s(sigBuf(s, 1) + dOff, s1, G.planeBytes, sigFull + s);
+            }
+          };
+          auto issue_taps = [&]() {
+            const uint32_t t = it % (uint32_t)G.tapStages, v = it / (uint32_t)G.tapStages;
+            if (v > 0) tc_wait(tapFree + t, (v - 1) & 1);
+            mbar_expect_tx(tapFull + t, G.tapsBytes);
+            const unsigned char *tsrc = p.taps + (size_t)c * G.tapsFullBytes + (size_t)j * (size_t)(2 * G.KS * 256);
+            if (!kMulti) {
+              if (p.l2hint & 2) bulk_g2s_hint(tapBuf(t), tsrc, G.tapsBytes, tapFull + t, polKeep);
+              else bulk_g2s(tapBuf(t), tsrc, G.tapsBytes, tapFull + t);
+            } else {   // the atoms [32 j, 32 j + natom) of both parts
+              bulk_g2s(tapBuf(t), tsrc, (uint32_t)G.natom * 256u, tapFull + t);
+              bulk_g2s(tapBuf(t) + (size_t)G.natom * 256, tsrc + (size_t)G.natomFull * 256, (uint32_t)G.natom * 256u, tapFull + t);
+            }
+          };
+          if (p.tapsFirst) { issue_taps(); issue_sig(); } else { issue_sig(); issue_taps(); }
           it++;
         }
         }

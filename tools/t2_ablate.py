@@ -17,8 +17,9 @@ inp = synth.synth_file(synth.BASE_SEED, 0, 900, mu, sigma, floor0)
 db.finalize()
 cfg = bench.corr_config(N)
 job = engine.CorrelationJob(db, cfg, inp)
-job.scan(); job.scan()
+for _ in range(int(os.environ.get("T2_ABLATE_WARM", "20"))):      # clocks ramp up under continuous load only
+    job.scan()
 ms = []
-for _ in range(3):
+for _ in range(int(os.environ.get("T2_ABLATE_REPS", "20"))):
     job.scan(); ms.append(job.timing()["scan_ms"])
 print("dbg", os.environ.get("SGZ_T2_DBG"), "scan_ms", float(np.median(ms)), flush=True)
