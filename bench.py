@@ -390,11 +390,13 @@ def main():
                         "frac": hbm["frac"] if intensity < ridge else flops / tensor_peak,
                         "peak_source": hbm_src if intensity < ridge else tensor["peak_source"],
                         "intensity_flop_per_byte": intensity, "ridge_flop_per_byte": ridge,
-                        "why_not_higher": "three split-FP16 products for FP32-grade precision: 630 M128xN64xK16 MMAs per 8192 "
-                                          "offsets fetch 2.9 MB of operands from shared memory, the ring is filled with 0.73 MB "
-                                          "and the epilogue moves another 0.9 MB -- 4.6 MB per tile through a 128 B/clock data "
-                                          "pipe is 36 k cycles (the measured tile time is 47 k); the HBM time of the same tile is "
-                                          "21 k cycles",
+                        "why_not_higher": "three split-FP16 products for FP32-grade precision: the 630 M128xN64xK16 MMAs of a "
+                                          "tile of 8192 offsets take 30 k cycles of the MMA pipe (47.6 cycles each: an MMA fetches "
+                                          "6 KB of operands from shared memory at 128 B/clock); the bulk copies that feed them "
+                                          "bring 74 B/offset from HBM (about 29 k cycles per tile at the measured HBM rate) and "
+                                          "overlap with the MMAs through a 4-deep ring: 42 k cycles per tile, of which the issuer "
+                                          "waits 6 k for operands (ring depth, L2 prefetch and copy order change nothing, "
+                                          "tools/t2_ablate.py); the epilogue (19 k) hides behind the MMAs of the next tile",
                         "tensor": tensor}
         else:
             roofline = {"kernel": "sgz::k_corr (K1 sliding-window Pearson correlation, FFMA2)", "bound": "fp32_ffma",
@@ -408,7 +410,7 @@ def main():
         line = {
             "metric": "FeatureCorrelation DB frame-offsets/sec", "value": value, "unit": "offsets/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16x2 split operands, f32 accumulate, f64 window sums",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16x2 split operands, f32 accumulate, window statistics f32 centred on exact f64 sums",
             "data": "synthetic (device-generated integer-hash features, planted needles)",
             "config": config_block(world, files),
             "roofline": roofline,
