@@ -218,7 +218,27 @@ static int self_fast_image(sgz_ctx *ctx, const sgz_self_config *cfg, sgz::SelfPa
   static const int oneMainMax = getenv("SGZ_SELF_TC_ONE_MAIN_MAX") ? atoi(getenv("SGZ_SELF_TC_ONE_MAIN_MAX")) : 60;
   const bool twoMain = chainAll > oneMainMax && numCh >= 3;
   const bool chainOk = (twoMain ? chainHalf : chainAll) <= 78 && 3 * G.nks <= 78;
-  bool tc = !tcOff && G.ok && numCh >= 2 && chainOk;
+  // Longer windows stay on the tensor cores in CHUNKS of 160 frames (10 K steps: 7 x 10 MMAs per main accumulator with
+  // twoMain), one launch per chunk: a launch adds the raw Gram sums of the earlier chunks from a scratch image and the
+  // last one applies the closed form of the whole window (SelfTcParams::recOff).  The scratch costs 16 B per cell and
+  // chunk of HBM traffic next to about 3 000 tensor-core flops per cell and chunk.
+  constexpr int kChunkH = 160;
+  static const bool chunkOff = getenv("SGZ_SELF_TC_CHUNKS") && atoi(getenv("SGZ_SELF_TC_CHUNKS")) == 0;
+  struct Chunk { int h0, Hc; SelfTcGeom G; bool twoMain; };
+  std::vector<Chunk> chunks;
+  if (chainOk && G.ok) chunks.push_back(Chunk{0, H, G, twoMain});
+  else if (!chunkOff && numCh >= 2) {
+    bool ok = true;
+    for (int h0 = 0; h0 < H && ok; h0 += kChunkH) {
+      const int Hc = std::min(kChunkH, H - h0);
+      const SelfTcGeom Gc = self_tc_geom(Hc, g.decim, ctx->smemOptin, !aDescOff);
+      const bool two = (numCh - 1) * Gc.nks > oneMainMax && numCh >= 3;
+      ok = Gc.ok && (two ? (numCh / 2) * Gc.nks : (numCh - 1) * Gc.nks) <= 78;
+      chunks.push_back(Chunk{h0, Hc, Gc, two});
+    }
+    if (!ok) chunks.clear();
+  }
+  bool tc = !tcOff && numCh >= 2 && !chunks.empty();
   if (tc) {
     k_self_absmax<<<ctx->smCount * 4, 256, 0, ctx->stream>>>(p.x1, p.stride1, need, numCh, dAmax.p);
     SGZ_LAUNCH_CHECK(ctx);
@@ -261,7 +281,9 @@ static int self_fast_image(sgz_ctx *ctx, const sgz_self_config *cfg, sgz::SelfPa
   }
   if (tc) {
     const int nT = ceil_div(ext, kGT);
-    const int64_t nRec = (int64_t)G.dp * kGT * (nT - 1) + G.span;
+    int64_t spanMax = 0;
+    for (const Chunk &ck : chunks) spanMax = std::max<int64_t>(spanMax, ck.G.span + ck.h0 / G.g);
+    const int64_t nRec = (int64_t)G.dp * kGT * (nT - 1) + spanMax;
     const int64_t recThreads = (int64_t)numCh * nRec;
     SGZ_TRY(rec1.alloc((size_t)2 * numCh * nRec));
     SGZ_TRY(wsA.alloc(ext));
@@ -290,41 +312,56 @@ static int self_fast_image(sgz_ctx *ctx, const sgz_self_config *cfg, sgz::SelfPa
     tp.wsB = cross ? wsB.p : wsA.p;
     tp.tiles = dTiles.p;
     tp.nTiles = (int)gt.size();
-    tp.nks = G.nks; tp.nSlab = G.nSlab; tp.slabKs = G.slabKs; tp.dp = G.dp; tp.kcStep = G.kcStep; tp.span = G.span;
-    tp.nStage = G.nStage; tp.nRecStage = G.nRecStage; tp.matBytes = G.matBytes; tp.stageBytes = G.stageBytes;
-    tp.recPartBytes = G.recPartBytes; tp.recStageBytes = G.recStageBytes; tp.tailBytes = G.tailBytes;
-    if (G.tailBytes) {   // in-place mode, H % 16 != 0: B's last K step, cut off at the window's end, for every window row
-      const int64_t nRows = (int64_t)nT * kGT;
-      SGZ_TRY(tail2.alloc((size_t)2 * numCh * 2 * nRows));
-      k_self_tail<<<(unsigned)ceil_div<int64_t>(2 * (int64_t)numCh * 2 * nRows, 256), 256, 0, ctx->stream>>>(
-          tp.rec2, numCh, nRec, G.kcStep, 2 * (G.nks - 1), H, nRows, tail2.p);
-      SGZ_LAUNCH_CHECK(ctx);
-      tp.tail2 = tail2.p;
-      tp.nTailRows = nRows;
-    }
     tp.simMat = simMat;
-    tp.aDesc = G.aDesc;
-    tp.twoMain = twoMain;
     static const int dumpEnv = getenv("SGZ_SELF_TC_DUMP") ? atoi(getenv("SGZ_SELF_TC_DUMP")) : -1;
-    tp.dump = dumpEnv >= 0 ? std::min(dumpEnv, G.dump) : G.dump;
-    SGZ_CUDA(cudaFuncSetAttribute(k_self_gram_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));
-    SGZ_CUDA(cudaFuncSetAttribute(k_self_gram_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));
-    SGZ_CUDA(cudaFuncSetAttribute(k_self_gram_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));
     const unsigned gridTc = (unsigned)std::min<size_t>(gt.size(), (size_t)ctx->smCount);
     DevBuf<long long> dProf;
-    DevBuf<float> dCorrT;
+    DevBuf<float> dCorrT, dGPart;
     const bool prof = getenv("SGZ_SELF_TC_PROF") != nullptr;   // developer probe: cycles per role
     // Both groups in play: one launch with three TMEM regions per tile (default; the epilogue of a tile is not overlapped
     // with the next tile's MMAs), or SGZ_SELF_TC_PASSES=2: temporal pass -> corrT, then the spectral pass with two tiles
     // in TMEM (see SelfTcParams).  Measured on B200 (30 000 frames, decim 1): 1.16e11 vs 1.06e11 cells/s -- the overlapped
     // epilogue runs at half speed next to the MMAs' shared-memory traffic and the extra pass costs 8 k cycles per tile.
-    static const bool onePass = !(getenv("SGZ_SELF_TC_PASSES") && atoi(getenv("SGZ_SELF_TC_PASSES")) == 2);
+    static const bool onePassEnv = !(getenv("SGZ_SELF_TC_PASSES") && atoi(getenv("SGZ_SELF_TC_PASSES")) == 2);
+    const bool onePass = onePassEnv || chunks.size() > 1;
     const bool useT = p.weight > 0.f, useS = p.weight < 1.f;
     const int nPass = useT && useS && !onePass ? 2 : 1;
     if (nPass == 2) {
       SGZ_TRY(dCorrT.alloc((size_t)ext * ext));
       tp.corrT = dCorrT.p;
     }
+    if (chunks.size() > 1) {
+      SGZ_TRY(dGPart.alloc((size_t)2 * ext * ext));
+      tp.gPart = dGPart.p;
+      tp.Hfull = H;
+    }
+    for (size_t ci = 0; ci < chunks.size(); ci++) {
+      const Chunk &ck = chunks[ci];
+      const SelfTcGeom &Gc = ck.G;
+      tp.f.base.H = ck.Hc;
+      tp.recOff = ck.h0 / Gc.g;
+      tp.storeG = ci + 1 < chunks.size();
+      tp.loadG = ci > 0;
+      tp.nks = Gc.nks; tp.nSlab = Gc.nSlab; tp.slabKs = Gc.slabKs; tp.dp = Gc.dp; tp.kcStep = Gc.kcStep; tp.span = Gc.span;
+      tp.nStage = Gc.nStage; tp.nRecStage = Gc.nRecStage; tp.matBytes = Gc.matBytes; tp.stageBytes = Gc.stageBytes;
+      tp.recPartBytes = Gc.recPartBytes; tp.recStageBytes = Gc.recStageBytes; tp.tailBytes = Gc.tailBytes;
+      tp.tail2 = nullptr; tp.nTailRows = 0;
+      if (Gc.tailBytes) {   // in-place mode, H % 16 != 0: B's last K step, cut off at the window's end, for every window row
+        const int64_t nRows = (int64_t)nT * kGT;
+        SGZ_TRY(tail2.alloc((size_t)2 * numCh * 2 * nRows));
+        // (the rows of a chunk start recOff records into the window; the channel stride stays nRec)
+        k_self_tail<<<(unsigned)ceil_div<int64_t>(2 * (int64_t)numCh * 2 * nRows, 256), 256, 0, ctx->stream>>>(
+            tp.rec2, numCh, nRec, Gc.kcStep, 2 * (Gc.nks - 1), ck.Hc, nRows, tail2.p, tp.recOff);
+        SGZ_LAUNCH_CHECK(ctx);
+        tp.tail2 = tail2.p;
+        tp.nTailRows = nRows;
+      }
+      tp.aDesc = Gc.aDesc;
+      tp.twoMain = ck.twoMain;
+      tp.dump = dumpEnv >= 0 ? std::min(dumpEnv, Gc.dump) : Gc.dump;
+      SGZ_CUDA(cudaFuncSetAttribute(k_self_gram_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gc.smemBytes));
+      SGZ_CUDA(cudaFuncSetAttribute(k_self_gram_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gc.smemBytes));
+      SGZ_CUDA(cudaFuncSetAttribute(k_self_gram_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gc.smemBytes));
     for (int pass = 0; pass < nPass; pass++) {
       const bool doT = nPass == 2 ? pass == 0 : useT, doS = nPass == 2 ? pass == 1 : useS;
       tp.storeT = nPass == 2 && pass == 0;
@@ -334,9 +371,9 @@ static int self_fast_image(sgz_ctx *ctx, const sgz_self_config *cfg, sgz::SelfPa
         SGZ_CUDA(cudaMemsetAsync(dProf.p, 0, (size_t)gridTc * 16 * sizeof(long long), ctx->stream));
         tp.prof = dProf.p;
       }
-      if (doT && doS) k_self_gram_tc<0><<<gridTc, kSgThreads, G.smemBytes, ctx->stream>>>(tp);
-      else if (doT) k_self_gram_tc<1><<<gridTc, kSgThreads, G.smemBytes, ctx->stream>>>(tp);
-      else k_self_gram_tc<2><<<gridTc, kSgThreads, G.smemBytes, ctx->stream>>>(tp);
+      if (doT && doS) k_self_gram_tc<0><<<gridTc, kSgThreads, Gc.smemBytes, ctx->stream>>>(tp);
+      else if (doT) k_self_gram_tc<1><<<gridTc, kSgThreads, Gc.smemBytes, ctx->stream>>>(tp);
+      else k_self_gram_tc<2><<<gridTc, kSgThreads, Gc.smemBytes, ctx->stream>>>(tp);
       SGZ_LAUNCH_CHECK(ctx);
       if (prof) {
         std::vector<long long> h((size_t)gridTc * 16);
@@ -345,12 +382,13 @@ static int self_fast_image(sgz_ctx *ctx, const sgz_self_config *cfg, sgz::SelfPa
         double a[16] = {0};
         for (unsigned bk = 0; bk < gridTc; bk++) for (int k = 0; k < 16; k++) a[k] += (double)h[(size_t)bk * 16 + k];
         const double tiles = a[5] > 0 ? a[5] : 1;
-        fprintf(stderr, "k_self_gram_tc pass %d/%d cycles per tile (aDesc %d, %d stages of %d K steps, %d record stages, %d parked batches): issuer total %.0f | "
+        fprintf(stderr, "k_self_gram_tc chunk %d/%d pass %d/%d cycles per tile (aDesc %d, %d stages of %d K steps, %d record stages, %d parked batches): issuer total %.0f | "
                         "records %.0f, wait accEmpty %.0f, wait full %.0f, issue %.0f || builder total %.0f | wait records %.0f, "
                         "wait empty %.0f, build %.0f || epilogue wait accFull %.0f, main %.0f\n",
-                pass + 1, nPass, tp.aDesc, tp.nStage, tp.slabKs, tp.nRecStage, tp.dump, a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles,
+                (int)ci + 1, (int)chunks.size(), pass + 1, nPass, tp.aDesc, tp.nStage, tp.slabKs, tp.nRecStage, tp.dump, a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles,
                 a[4] / tiles, a[8] / tiles, a[9] / tiles, a[10] / tiles, a[11] / tiles, a[12] / tiles, a[13] / tiles);
       }
+    }
     }
     SGZ_TRY(ctx->end_call());
     if (usedTc) *usedTc = 1;

@@ -136,6 +136,14 @@ struct SelfTcParams {
   int twoMain;               // long windows: the spectral main products alternate between two regions by channel parity,
                              // halving the chain (and the truncation bias) per accumulator; no spare region then
   float *corrT;              // [imgExt][imgExt], element [c][a] (column-major so that lanes = rows a are coalesced)
+  // Long windows (chains beyond the error budget of one accumulator): the window is cut into chunks of H frames, one
+  // launch per chunk.  A launch reads the records recOff further on (its chunk starts recOff * g frames into the window),
+  // adds the raw Gram sums of the earlier chunks (loadG) and either parks its own sums (storeG) or -- last chunk --
+  // applies the closed form with the window sums and the length Hfull of the WHOLE window.
+  int64_t recOff;
+  int Hfull;                 // 0: f.base.H is the whole window
+  float *gPart;              // [2][imgExt][imgExt] temporal / spectral partial Gram sums, element [c][a]
+  int storeG, loadG;
 };
 
 // max |x| per group (as float bits; |NaN| compares above everything) next to the means of k_self_means
@@ -175,13 +183,13 @@ __global__ void k_self_records(const float *__restrict__ x, int64_t stride, int6
 // In-place mode, H % 16 != 0: the last K step (chunks kc0 = 2 (nks - 1) and kc0 + 1) of every window row of file 2, cut
 // off at the window's end: tail[part][c][kcl][row] = record (row + kcStep (kc0 + kcl)) with the halves k >= H zeroed
 __global__ void k_self_tail(const uint4 *__restrict__ rec, int numCh, int64_t nRec, int kcStep, int kc0, int H, int64_t nRows,
-                            uint4 *__restrict__ tail) {
+                            uint4 *__restrict__ tail, int64_t recOff = 0) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (idx >= 2 * (int64_t)numCh * 2 * nRows) return;
   const int64_t row = idx % nRows;
   const int kcl = (int)((idx / nRows) & 1);
   const int64_t pc = idx / (2 * nRows);               // part * numCh + c
-  const int64_t rho = row + (int64_t)kcStep * (kc0 + kcl);
+  const int64_t rho = row + (int64_t)kcStep * (kc0 + kcl) + recOff;   // (chunked windows start recOff records in)
   uint4 v = rho < nRec ? rec[pc * nRec + rho] : make_uint4(0, 0, 0, 0);
   const int nv = H - 8 * (kc0 + kcl);
   if (nv < 8) {
@@ -343,8 +351,8 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
         if (tc_elect()) {
           unsigned char *dst = recBase + (size_t)rs * p.recStageBytes;
           mbar_expect_tx(recFull + rs, 4u * p.recPartBytes + p.tailBytes);
-          const uint4 *a0 = p.rec1 + (int64_t)c * chanRecs + (int64_t)p.dp * tl.x;
-          const uint4 *b0 = p.rec2 + (int64_t)c * chanRecs + (int64_t)p.dp * tl.y;
+          const uint4 *a0 = p.rec1 + (int64_t)c * chanRecs + (int64_t)p.dp * tl.x + p.recOff;
+          const uint4 *b0 = p.rec2 + (int64_t)c * chanRecs + (int64_t)p.dp * tl.y + p.recOff;
           bulk_g2s(dst, a0, p.recPartBytes, recFull + rs);
           bulk_g2s(dst + p.recPartBytes, a0 + partRecs, p.recPartBytes, recFull + rs);
           bulk_g2s(dst + 2 * p.recPartBytes, b0, p.recPartBytes, recFull + rs);
@@ -528,7 +536,8 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
     const int ew = warp - (kSgBuildWarps + 1), quarter = warp & 3, half = ew >> 2, et = ew * 32 + lane;
     int32_t *Pw = P + (size_t)ew * 32 * kSgPPitch;
     const int ext = b.imgExt;
-    const float invNT = (float)(1.0 / (4.0 * (double)H)), invNS = (float)(1.0 / (4.0 * (double)(b.numCh - 1) * (double)H));
+    const int Hf = p.Hfull > 0 ? p.Hfull : H;      // the closed form is that of the whole window
+    const float invNT = (float)(1.0 / (4.0 * (double)Hf)), invNS = (float)(1.0 / (4.0 * (double)(b.numCh - 1) * (double)Hf));
     const bool warpOne = b.colorWarp == 1.0f;
     const float wT = b.weight, wS = __fsub_rn(1.0f, b.weight);
     const bool useT = kDoT, useS = kDoS;
@@ -627,6 +636,23 @@ __global__ void __launch_bounds__(kSgThreads, 1) k_self_gram_tc(const SelfTcPara
         }
         const int c0 = tb + 64 * half + 16 * bt;
         const float4 *cw = colW + 64 * half + 16 * bt;
+        if (p.loadG || p.storeG) {    // chunked window: Gram sums of the chunks so far
+          float *gT = p.gPart, *gS = p.gPart + (int64_t)ext * ext;
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            const bool ok = interior || (a < ext && c0 + i < ext);
+            const int64_t o = (int64_t)(c0 + i) * ext + a;
+            if (p.loadG && ok) {
+              if (useT) uT[i] = __float_as_uint(__uint_as_float(uT[i]) + __ldcs(gT + o));
+              if (useS) uM[i] = __float_as_uint(__uint_as_float(uM[i]) + __ldcs(gS + o));
+            }
+            if (p.storeG && ok) {
+              if (useT) __stcs(gT + o, __uint_as_float(uT[i]));
+              if (useS) __stcs(gS + o, __uint_as_float(uM[i]));
+            }
+          }
+          if (p.storeG) continue;
+        }
         if (kMode == 1 && p.storeT) {
           // pass 1 of 2: the temporal coefficient of every cell of the tile -> corrT[c][a] (lanes = rows a: coalesced)
 #pragma unroll

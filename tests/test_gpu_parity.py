@@ -212,8 +212,10 @@ def test_selfsimilarity_image_identical(ctx, decim, weight, warp, ceil, inv, cro
     # by channel parity (7 x 7 and 7 x 10 MMAs), also with the spectral group alone and in expansion mode
     (1500, 49152, 1, 0.5, 1.0, False, False), (1500, 57344, 1, 0.5, 1.0, False, False), (1700, 81920, 1, 0.5, 1.0, False, True),
     (1700, 81920, 2, 0.0, 1.0, False, False), (2400, 65536, 3, 0.5, 1.0, False, False),
-    # long windows (32 and 64 K steps per channel): FFMA2 kernel
-    (1600, 262144, 1, 0.5, 1.0, False, False), (2600, 524288, 2, 0.4, 1.0, False, True),
+    # long windows (32 and 64 K steps per channel): chunks of 160 frames, one launch per chunk; 250 000 samples = H 488 with
+    # a last chunk of 8 frames (one K step with a pre-masked tail), in expansion mode too
+    (1600, 262144, 1, 0.5, 1.0, False, False), (2600, 524288, 2, 0.4, 1.0, False, True), (1500, 250000, 1, 0.5, 1.0, False, False),
+    (2200, 250000, 3, 0.5, 1.0, False, False),
 ])
 def test_selfsimilarity_fast_gram_within_tolerance(ctx, frames, corr_len, decim, weight, warp, inv, cross):
     """default (fast) path: Gram tiles (tensor cores, split FP16) + closed form with FP64-accumulated window sums: sims
@@ -227,9 +229,9 @@ def test_selfsimilarity_fast_gram_within_tolerance(ctx, frames, corr_len, decim,
     want = O.self_image(op, f1, f2)
     cfg = N.SelfConfig(STEP, 0, 0, 0, 0, corr_len, decim, weight, int(inv), warp, 1.0, None, 0, 0)   # precise = 0
     got, g = engine.self_run(ctx, cfg, f1, f2, norm)
-    # no silent fall-back to the FFMA2 kernel -- except for long windows, where the tensor core's truncating accumulation
-    # would exceed the error budget (chains of more than 78 MMAs into one accumulator even when split over two)
-    assert engine.self_last_kernel(ctx) == ("tc_gram" if corr_len <= 90112 else "ffma2_gram")
+    # no silent fall-back to the FFMA2 kernel: windows whose accumulation chains would exceed the error budget of the
+    # truncating tensor-core adder (more than 78 MMAs into one accumulator) run in chunks of 160 frames
+    assert engine.self_last_kernel(ctx) == "tc_gram"
     assert got.shape == want.shape and g["imgExt"] == want.shape[0] > 128      # several 128 x 128 tiles
     assert np.array_equal(got, got[::-1, ::-1].T)                              # mirrored like the reference
     dg = np.abs((got & 0xFF).astype(np.int64) - (want & 0xFF).astype(np.int64))
