@@ -378,7 +378,10 @@ inline int run_scan_t2(sgz_corr *job, PunchQuery &q, int which, int tailExtra, f
     E.nT = (double)q.W; E.nS = (double)(db->numCh - 1) * (double)q.W;
     E.invNTd = 1.0 / E.nT; E.invNSd = 1.0 / E.nS;
     E.nTf = (float)E.nT; E.nSf = (float)E.nS;
-    E.sqEps = (float)sqrt(2e-3 / (1.0 - 2e-3));
+    {
+      const double eT = std::min(0.5, std::max(2e-3, 0.25 / E.nT)), eS = std::min(0.5, std::max(2e-3, 0.25 / E.nS));
+      E.sqEpsT = (float)sqrt(eT / (1.0 - eT)); E.sqEpsS = (float)sqrt(eS / (1.0 - eS));
+    }
     // boost = exp((lnAvgIn - ln avg) / 0.6) <= maxBoost  <=>  avg >= exp(lnAvgIn - 0.6 ln maxBoost); a NaN threshold
     // (maxBoost < 0 or NaN) lets no offset pass, like the reference's comparison
     const double avgMin = exp(q.lnAvg - 0.6 * log((double)job->cfg.maxBoost));

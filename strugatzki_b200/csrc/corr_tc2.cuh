@@ -243,8 +243,10 @@ struct T2Eval {
   double nT, nS;            // cells of a window per group: W, (numCh - 1) W
   double invNTd, invNSd;    // 1 / n
   float nTf, nSf;
-  float sqEps;              // sqrt(eps / (1 - eps)), eps = 2e-3: a window whose variance is below eps of its mean square
-                            // is re-evaluated exactly (corr_fix.cuh)
+  float sqEpsT, sqEpsS;     // sqrt(eps / (1 - eps)) per group: a window whose variance is below eps of its mean square is
+                            // re-evaluated exactly (corr_fix.cuh); eps = max(2e-3, 0.25 / n) -- the truncation of the
+                            // split-FP16 products (2^-22 of the level per cell) averages out over the n cells of a window
+                            // only, so windows of a few cells need a larger spread
   float gateNm;             // boost <= maxBoost  <=>  loudness sum of the window >= gateNm (calcBoost is monotone)
   float invNT2, invNS2;     // 1 / n^2
   float cT, cS;             // 1 / (n std_a) per group
@@ -315,14 +317,14 @@ __device__ __forceinline__ float t2_eval(const T2Eval &E, const T2Win &w, float 
   const float qnan = __uint_as_float(kFixSentinel);
   const float nmT = w.nmuT + w.c1T;                                     // n * window mean
   const float qT = w.c1T * w.c1T, vT = fmaf(E.nTf, w.c2T, -qT);         // n^2 var
-  const float tT = nmT * E.sqEps;
+  const float tT = nmT * E.sqEpsT;
   const float crT = fmaf(accT, E.cT, -(nmT * E.kTn));                   // (acc - mean_b * rho) / (W std_a)
   float temporal = crT * t2_rsqrt(vT * E.invNT2);
   temporal = vT > fmaxf(tT * tT, qT) ? temporal : qnan;                 // (false for NaN)
   temporal = E.useT ? temporal : 0.f;
   const float nmS = w.nmuS + w.c1S;
   const float qS = w.c1S * w.c1S, vS = fmaf(E.nSf, w.c2S, -qS);
-  const float tS = nmS * E.sqEps;
+  const float tS = nmS * E.sqEpsS;
   const float crS = fmaf(accS, E.cS, -(nmS * E.kSn));
   float spectral = crS * t2_rsqrt(vS * E.invNS2);
   spectral = vS > fmaxf(tS * tS, qS) ? spectral : qnan;

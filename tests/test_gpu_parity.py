@@ -295,6 +295,29 @@ def test_corr_edge_cases(ctx):
     assert_sims_close(sim, want, what="W=689 curve")
 
 
+@pytest.mark.parametrize("W,weight", [(2, 0.5), (5, 0.5), (16, 0.3), (31, 1.0), (40, 0.0)])
+def test_corr_short_windows_and_level_steps(ctx, W, weight):
+    """K1 slides its window statistics in FP32 centred on the mean of a thread's first window (corr_tc2.cuh, T2Win).  With
+    a window of a few frames the mean moves by a whole window within the 15 slides of a run, and a file whose level jumps
+    (quiet -> loud, a factor of 40) moves it by many standard deviations: such windows must be recognised (c1^2 against
+    n c2) and re-evaluated exactly, so that the curve still meets the contract everywhere."""
+    from strugatzki_b200 import engine
+    files, norm = make_db(3, [1500, 700, 2100])
+    inp = make_input(300)
+    f = files[2]
+    f[500:900] = (f[500:900] * np.float32(0.025)).astype(np.float32)       # a quiet stretch with hard edges
+    f[1200:1210] = f[1200]                                                 # ten constant frames: exactly constant windows for W <= 10
+    plant_needles(files, inp[:W], [(0, 333), (2, 1700)])
+    op, nc = corr_cfgs(inp, norm, punch_in=(0, W * STEP), w_in=weight, num_matches=6, num_per_file=2, max_boost=1e9)
+    job = engine.CorrelationJob(build_db(ctx, files, norm), nc, inp)
+    got = job.run()
+    assert_matches_equal(got, O.corr_search(op, files))
+    for i, fl in enumerate(files):
+        want, _ = O.corr_curve(op, fl)
+        sim, _ = job.curve(i, 0, 0, len(want))
+        assert_sims_close(sim, want, rel=1e-5, abs_tol=2e-6, what=f"W={W} file {i}")
+
+
 @pytest.mark.parametrize("W", [258, 1723, 3000])
 def test_corr_long_windows_run_in_passes_on_the_tensor_cores(ctx, W):
     """The reference accepts any punch span (FeatureCorrelationImpl.scala:83-98,154).  Beyond 257 frames the tensor-core
