@@ -605,6 +605,8 @@ int sgz_corr_destroy(sgz_corr *job) {
   return SGZ_OK;
 }
 
+static int enqueue_summary_download(sgz_corr *job, cudaStream_t st);
+
 int sgz_corr_scan(sgz_corr *job) {
   SGZ_REQUIRE(job, "job is NULL");
   sgz_ctx *ctx = job->ctx;
@@ -647,6 +649,15 @@ int sgz_corr_scan(sgz_corr *job) {
   SGZ_TRY(job->simIn.alloc(n));
   if (!t2) SGZ_TRY(job->boostIn.alloc(n));   // the tensor-core scan writes no boost curve (BoostSrc, corr_fix.cuh)
   SGZ_TRY(job->dFileMax.alloc((size_t)std::max(db->numFiles(), 1)));
+  {
+    static const bool directOff = getenv("SGZ_DIRECT_SELECT") && atoi(getenv("SGZ_DIRECT_SELECT")) == 0;   // developer knob
+    job->direct = t2 && !job->hasOut && job->cfg.numPerFile == 1 && !directOff;
+    job->keysCached = false;
+    if (job->direct) {
+      SGZ_TRY(job->dFileNaN.alloc((size_t)std::max(db->numFiles(), 1)));
+      SGZ_TRY(job->dFileBoost.alloc((size_t)std::max(db->numFiles(), 1)));
+    }
+  }
   if (job->hasOut) {
     SGZ_TRY(job->simOut.alloc(n));
     if (!t2) SGZ_TRY(job->boostOut.alloc(n));
@@ -657,6 +668,7 @@ int sgz_corr_scan(sgz_corr *job) {
     // ---- streaming scan: the database is still being uploaded (sgz_db_finalize_async).  K1 runs on its own
     // stream, range by range behind the upload markers, and leaves a few SMs to the prepare kernels. ----
     cudaStream_t ss = ctx->scanStream;
+    job->summaryPrefetched = false;
     const int64_t launches0 = ctx->launches;
     const int64_t T = (int64_t)kR * job->ntg;
     const int wqMax = std::max(job->qin.Wq, job->hasOut ? job->qout.Wq : 0);
@@ -666,6 +678,7 @@ int sgz_corr_scan(sgz_corr *job) {
     if (job->hasOut)
       SGZ_CUDA(cudaMemsetAsync(job->dFileMaxOut.p, 0, job->dFileMaxOut.n * sizeof(unsigned long long), ss));
     if (t2) SGZ_CUDA(cudaMemsetAsync(job->dFixCount.p, 0, 2 * sizeof(uint32_t), ss));
+    if (job->direct) SGZ_CUDA(cudaMemsetAsync(job->dFileNaN.p, 0, job->dFileNaN.n * sizeof(uint32_t), ss));
     int64_t done = 0;
     for (const auto &c : db->chunks) {
       if (db->usedFrames == 0) continue;
@@ -699,6 +712,11 @@ int sgz_corr_scan(sgz_corr *job) {
     if (t2 && db->usedFrames > 0) {
       SGZ_TRY(run_fixup(job, job->qin, 0, tailIn, job->simIn.p, job->dFileMax.p, ss));
       if (job->hasOut) SGZ_TRY(run_fixup(job, job->qout, 1, 0, job->simOut.p, job->dFileMaxOut.p, ss));
+      if (job->direct) {
+        k_filemax_boost<<<ceil_div(db->numFiles(), 128), 128, 0, ss>>>(boost_src(job, job->qin, nullptr), db->dFileStart.p,
+                                                                      job->dFileMax.p, db->numFiles(), job->dFileBoost.p);
+        SGZ_LAUNCH_CHECK(ctx);
+      }
     }
     if (job->hasOut && db->usedFrames > 0) {
       SGZ_TRY(job->rowMaxOut.alloc((size_t)db->usedFrames));
@@ -720,11 +738,17 @@ int sgz_corr_scan(sgz_corr *job) {
     if (job->hasOut)
       SGZ_CUDA(cudaMemsetAsync(job->dFileMaxOut.p, 0, job->dFileMaxOut.n * sizeof(unsigned long long), ctx->stream));
     if (t2) SGZ_CUDA(cudaMemsetAsync(job->dFixCount.p, 0, 2 * sizeof(uint32_t), ctx->stream));
+    if (job->direct) SGZ_CUDA(cudaMemsetAsync(job->dFileNaN.p, 0, job->dFileNaN.n * sizeof(uint32_t), ctx->stream));
     if (db->usedFrames > 0) {
       if (t2) {
         SGZ_TRY(run_scan_t2(job, job->qin, 0, tailIn, job->simIn.p, job->dFileMax.p, 0, job->numTilesT2,
                             ctx->stream, 0));
         SGZ_TRY(run_fixup(job, job->qin, 0, tailIn, job->simIn.p, job->dFileMax.p, ctx->stream));
+        if (job->direct) {
+          k_filemax_boost<<<ceil_div(db->numFiles(), 128), 128, 0, ctx->stream>>>(
+              boost_src(job, job->qin, nullptr), db->dFileStart.p, job->dFileMax.p, db->numFiles(), job->dFileBoost.p);
+          SGZ_LAUNCH_CHECK(ctx);
+        }
       } else if (tc) SGZ_TRY(run_scan_tc(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, ctx->stream));
       else
         SGZ_TRY(run_scan_one(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, 0, job->numTiles,
@@ -744,7 +768,12 @@ int sgz_corr_scan(sgz_corr *job) {
         ctx->launches++;
       }
     }
-    SGZ_TRY(ctx->end_call());
+    job->summaryPrefetched = false;
+    SGZ_TRY(ctx->end_call_async());
+    SGZ_TRY(enqueue_summary_download(job, ctx->stream));     // the per-file results ride on the scan's own wait
+    SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    SGZ_TRY(ctx->collect_call());
+    job->summaryPrefetched = true;
   }
   job->scanMs = ctx->lastMs;
   job->scanLaunches = ctx->lastLaunches;
@@ -759,6 +788,25 @@ int sgz_corr_scan(sgz_corr *job) {
   return SGZ_OK;
 }
 
+// downloads of the per-file results of a scan into the job's pinned scratch, enqueued on `st` (no wait):
+// [keys in][keys out][NaN flags][boosts], nf entries each
+static int enqueue_summary_download(sgz_corr *job, cudaStream_t st) {
+  const int nf = job->db->numFiles();
+  SGZ_TRY(job->pin((size_t)std::max(nf, 1) * (2 * sizeof(unsigned long long) + 8)));
+  unsigned long long *keys = reinterpret_cast<unsigned long long *>(job->hPin), *keysOut = keys + std::max(nf, 1);
+  uint32_t *nanFlags = reinterpret_cast<uint32_t *>(keysOut + std::max(nf, 1));
+  float *boosts = reinterpret_cast<float *>(nanFlags + std::max(nf, 1));
+  if (nf == 0) return SGZ_OK;
+  if (job->direct && job->db->usedFrames > 0) {
+    SGZ_CUDA(cudaMemcpyAsync(nanFlags, job->dFileNaN.p, nf * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SGZ_CUDA(cudaMemcpyAsync(boosts, job->dFileBoost.p, nf * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  SGZ_CUDA(cudaMemcpyAsync(keys, job->dFileMax.p, nf * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  if (job->hasOut)
+    SGZ_CUDA(cudaMemcpyAsync(keysOut, job->dFileMaxOut.p, nf * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  return SGZ_OK;
+}
+
 int sgz_corr_local_summary(sgz_corr *job, sgz_file_summary *out, int32_t cap, int32_t *n) {
   SGZ_REQUIRE(job && n, "NULL argument");
   if (!job->scanned) { set_error("sgz_corr_local_summary before scan"); return SGZ_ERR_STATE; }
@@ -768,16 +816,22 @@ int sgz_corr_local_summary(sgz_corr *job, sgz_file_summary *out, int32_t cap, in
   *n = nf;
   if (!out) return SGZ_OK;
   SGZ_REQUIRE(cap >= nf, "summary buffer too small (%d < %d)", cap, nf);
-  SGZ_TRY(job->pin((size_t)std::max(nf, 1) * 2 * sizeof(unsigned long long)));
-  unsigned long long *keys = reinterpret_cast<unsigned long long *>(job->hPin), *keysOut = keys + std::max(nf, 1);
-  if (nf > 0) {
-    SGZ_CUDA(cudaMemcpyAsync(keys, job->dFileMax.p, nf * sizeof(unsigned long long), cudaMemcpyDeviceToHost, job->ctx->stream));
-    if (job->hasOut)
-      SGZ_CUDA(cudaMemcpyAsync(keysOut, job->dFileMaxOut.p, nf * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                               job->ctx->stream));
-    SGZ_CUDA(cudaStreamSynchronize(job->ctx->stream));
+  if (!job->summaryPrefetched) {     // (a resident scan has fetched them behind its kernels: one wait less per search)
+    SGZ_TRY(enqueue_summary_download(job, job->ctx->stream));
+    if (nf > 0) SGZ_CUDA(cudaStreamSynchronize(job->ctx->stream));
+    job->summaryPrefetched = true;     // the pinned copy stays valid until the next selection round uses the scratch
   }
+  unsigned long long *keys = reinterpret_cast<unsigned long long *>(job->hPin), *keysOut = keys + std::max(nf, 1);
+  uint32_t *nanFlags = reinterpret_cast<uint32_t *>(keysOut + std::max(nf, 1));
+  float *boosts = reinterpret_cast<float *>(nanFlags + std::max(nf, 1));
+  const bool direct = job->direct && db->usedFrames > 0;
   if (!job->hasOut) memset(keysOut, 0, (size_t)std::max(nf, 1) * sizeof(unsigned long long));
+  if (direct) {
+    job->hKeys.assign(keys, keys + nf);
+    job->hNaN.assign(nanFlags, nanFlags + nf);
+    job->hBoost.assign(boosts, boosts + nf);
+    job->keysCached = true;
+  }
   const int tail = job->hasOut ? job->minPunchF : 0;
   for (int f = 0; f < nf; f++) {
     int64_t nv = (db->fileStart[f + 1] - db->fileStart[f]) - tail - job->qin.W + 1;
@@ -857,12 +911,25 @@ int sgz_corr_select(sgz_corr *job, int32_t *nRecords) {
   SGZ_TRY(ctx->bind());
   job->localRecords.clear();
   *nRecords = 0;
+  job->summaryPrefetched = false;    // the selection rounds reuse the pinned scratch
   if (job->finished) return SGZ_OK;
   if (job->hasOut) return corr_select_punchout(job, nRecords);
   const int K = job->cfg.numMatches, npf = job->cfg.numPerFile;
   const int room = K - (int)job->allPrio.size();
   const int myLo = job->myFirst, myHi = job->myFirst + db->numFiles();
   const int tail = 0;
+  // numPerFile = 1 on the tensor-core scan: the entry of a file is its maximum at its first position (addMatch keeps one
+  // match per file and replaces it only by a strictly larger sim, FeatureCorrelationImpl.scala:135-150), which the scan left
+  // in fileMax together with its boost -- no replay, no candidate kernel, no device round trip.  Exception: a file with a NaN
+  // window in a FILLING round (NaN enters an entry that still has space and then blocks it, :120-129) keeps the replay.
+  const bool direct = job->direct && job->keysCached && (int)job->hKeys.size() == db->numFiles();
+  auto direct_record = [&](int f) {
+    const unsigned long long key = job->hKeys[(size_t)f];
+    if (key == 0ull) return;                               // no valid offset in this file
+    const sgz_record r{myLo + f, 1, (int32_t)(0xffffffffu - (uint32_t)key), -1, float_from_order_key((uint32_t)(key >> 32)),
+                       job->hBoost[(size_t)f], 1.0f, 0};
+    job->localRecords.push_back(r);
+  };
   if (room > 0) {
     // ---- filling round: files whose maxEntrySz is known without looking at their results ----
     const int nb = room >= npf ? room / npf : 1;
@@ -871,9 +938,13 @@ int sgz_corr_select(sgz_corr *job, int32_t *nRecords) {
     job->roundFirst = job->nextFile;
     job->roundCount = std::min(nb, job->nFilesGlobal - job->nextFile);
     job->roundMaxEntrySz = m;
-    std::vector<int32_t> files;
+    std::vector<int32_t> files, directFiles;
     for (int g = job->roundFirst; g < job->roundFirst + job->roundCount; g++)
-      if (g >= myLo && g < myHi) files.push_back(g - myLo);
+      if (g >= myLo && g < myHi) {
+        if (direct && !job->hNaN[(size_t)(g - myLo)]) directFiles.push_back(g - myLo);
+        else files.push_back(g - myLo);
+      }
+    for (int f : directFiles) direct_record(f);
     if (!files.empty()) {
       const int nj = (int)files.size();
       SGZ_TRY(job->dFiles.alloc(nj));
@@ -926,7 +997,10 @@ int sgz_corr_select(sgz_corr *job, int32_t *nRecords) {
       if (!(bound == bound)) break;  // allPrio.last is NaN: `sim > NaN` never holds -> nothing more is accepted
       const float mx = job->globalSummary[g].maxSim;
       if (mx > bound) {
-        if (g >= myLo && g < myHi) { files.push_back(g - myLo); thr.push_back(bound); }
+        if (g >= myLo && g < myHi) {
+          if (direct) direct_record(g - myLo);             // (a NaN never passes `sim > bound`: the maximum is all it takes)
+          else { files.push_back(g - myLo); thr.push_back(bound); }
+        }
         auto it = std::lower_bound(top.begin(), top.end(), mx);
         if (it == top.end() || *it != mx) top.insert(it, mx);
         if ((int)top.size() > K) top.erase(top.begin());

@@ -42,6 +42,17 @@ struct sgz_corr {
   int64_t numOffsets = 0;
   DevBuf<float> simIn, boostIn, simOut, boostOut, rowMaxOut;
   DevBuf<unsigned long long> dFileMax, dFileMaxOut;
+  // numPerFile = 1, punch-in only, tensor-core scan: the entry of a file is its maximum, which K1 leaves in dFileMax with
+  // its first position; the scan adds the boost of that offset and a flag for files that hold a NaN window (whose entry
+  // the reference decides by its NaN-first rule: those files keep the replay kernel).  Host copies from local_summary.
+  DevBuf<uint32_t> dFileNaN;
+  DevBuf<float> dFileBoost;
+  std::vector<unsigned long long> hKeys;
+  std::vector<uint32_t> hNaN;
+  std::vector<float> hBoost;
+  bool direct = false;      // this scan prepared the three arrays
+  bool keysCached = false;  // ... and local_summary has fetched them
+  bool summaryPrefetched = false;   // the pinned scratch holds the per-file results of the last scan
   bool scanned = false;
 
   // global (all ranks) view
@@ -353,6 +364,7 @@ inline int run_fixup(sgz_corr *job, PunchQuery &q, int which, int tailExtra, flo
   fp.fileStart = db->dFileStart.p; fp.numFiles = db->numFiles(); fp.tailExtra = tailExtra;
   fp.list = job->dFixList[which].p; fp.count = job->dFixCount.p + which; fp.cap = kFixCap;
   fp.sim = sim; fp.boost = boost_src(job, q, nullptr); fp.fileMax = fileMax;
+  fp.fileNaN = (which == 0 && job->direct) ? job->dFileNaN.p : nullptr;
   k_corr_fixup<<<(unsigned)job->ctx->smCount * 4, 128, 0, st>>>(fp);
   SGZ_LAUNCH_CHECK(job->ctx);
   return SGZ_OK;

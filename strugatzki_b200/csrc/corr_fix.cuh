@@ -55,6 +55,7 @@ struct CorrFixParams {
   float *sim;
   BoostSrc boost;
   unsigned long long *fileMax;
+  uint32_t *fileNaN;        // [numFiles] set when a window of the file is NaN in the reference (exactly constant), or nullptr
 };
 
 __device__ __forceinline__ float fix_value(const CorrFixParams &p, int ch, int64_t g) {
@@ -111,11 +112,24 @@ __device__ void fix_one(const CorrFixParams &p, int64_t g) {
     sim = __fadd_rn(__fmul_rn(temporal, p.weight), __fmul_rn(spectral, __fsub_rn(1.0f, p.weight)));
   }
   p.sim[g] = sim;
+  if (sim != sim && p.fileNaN) p.fileNaN[lo] = 1u;
   if (sim == sim && p.fileMax) {
     const unsigned long long key = ((unsigned long long)float_order_key(sim) << 32) |
                                    (unsigned long long)(0xffffffffu - (uint32_t)tl);
     atomicMax(p.fileMax + lo, key);
   }
+}
+
+// boost of the offset that holds each file's maximum (fileMax key: order key of the sim << 32 | ~offset; 0 = no offset).
+// With numPerFile = 1 the entry of a file IS that maximum, so a punch-in search needs no selection kernel at all.
+__global__ void k_filemax_boost(BoostSrc b, const int64_t *__restrict__ fileStart, const unsigned long long *__restrict__ fileMax,
+                                int numFiles, float *__restrict__ out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= numFiles) return;
+  const unsigned long long key = fileMax[f];
+  if (key == 0ull) { out[f] = 1.0f; return; }
+  const int64_t tl = (int64_t)(0xffffffffu - (uint32_t)key);
+  out[f] = b.at(fileStart[f] + tl, tl);
 }
 
 // boost values of n consecutive offsets of one file (sgz_corr_curve)
