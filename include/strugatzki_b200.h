@@ -279,6 +279,19 @@ typedef struct {
   float   maxSim;
 } sgz_file_entry;
 int sgz_corr_local_top(sgz_corr *job, sgz_file_entry *out, int32_t cap, int32_t *n, int32_t *numFiles);
+
+/* numPerFile = 1, punch-in only: the entry of a file is its maximum at its first position (addMatch keeps one match per
+ * file and replaces it only by a strictly larger sim, FeatureCorrelationImpl.scala:135-150), and allPrio always holds the
+ * numMatches largest entries seen so far (:120-129, :399-400) -- so the entries of each rank's numMatches best files are ALL a
+ * search needs, and ONE exchange per search replaces the summary / record rounds above.
+ * sgz_corr_local_best returns those entries as records (kind 1, LOCAL file index, punch-in offset, sim, boostIn) and says
+ * whether the shortcut applies on this rank: *ok = 0 when the scan did not prepare it (another kernel, numPerFile > 1, a
+ * punch-out search) or when a file of this rank holds a NaN window (whose entry the reference decides by its NaN-first
+ * rule while allPrio still has space).  If every rank says ok, the host rebases the file indices, hands all records of
+ * all ranks to sgz_corr_finish_from_best on every rank -- the search is then finished, sgz_corr_result is valid -- else it
+ * continues with sgz_corr_local_top as before. */
+int sgz_corr_local_best(sgz_corr *job, sgz_record *out, int32_t cap, int32_t *n, int32_t *numFiles, int32_t *ok);
+int sgz_corr_finish_from_best(sgz_corr *job, const sgz_record *all, int32_t nAll, int32_t nFilesGlobal);
 int sgz_corr_set_global_top(sgz_corr *job, const sgz_file_entry *all, int32_t nAll, int32_t nFilesGlobal,
                             int32_t myFirstFile);
 

@@ -30,7 +30,7 @@ SYMBOLS = [
     "sgz_db_add_synth", "sgz_db_add_synth_many", "sgz_db_patch", "sgz_db_finalize", "sgz_db_finalize_async", "sgz_db_stats", "sgz_db_info", "sgz_db_file_frames", "sgz_db_read",
     "sgz_corr_create", "sgz_corr_destroy", "sgz_corr_run", "sgz_corr_start", "sgz_corr_poll", "sgz_corr_abort",
     "sgz_corr_wait", "sgz_corr_result", "sgz_corr_num_offsets", "sgz_corr_timing", "sgz_corr_curve",
-    "sgz_corr_scan", "sgz_corr_local_summary", "sgz_corr_set_global", "sgz_corr_local_top", "sgz_corr_set_global_top", "sgz_corr_select", "sgz_corr_records",
+    "sgz_corr_scan", "sgz_corr_local_summary", "sgz_corr_set_global", "sgz_corr_local_top", "sgz_corr_set_global_top", "sgz_corr_local_best", "sgz_corr_finish_from_best", "sgz_corr_select", "sgz_corr_records",
     "sgz_corr_merge",
     "sgz_segm_run", "sgz_self_geometry_of", "sgz_self_run", "sgz_self_cells", "sgz_cross_num_outputs",
     "sgz_cross_run", "sgz_measure_peak",

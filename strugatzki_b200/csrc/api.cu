@@ -885,6 +885,77 @@ int sgz_corr_local_top(sgz_corr *job, sgz_file_entry *out, int32_t cap, int32_t 
   return SGZ_OK;
 }
 
+int sgz_corr_local_best(sgz_corr *job, sgz_record *out, int32_t cap, int32_t *n, int32_t *numFiles, int32_t *ok) {
+  SGZ_REQUIRE(job && n && numFiles && ok, "NULL argument");
+  if (!job->scanned) { set_error("sgz_corr_local_best before scan"); return SGZ_ERR_STATE; }
+  sgz_db *db = job->db;
+  const int nf = db->numFiles();
+  *numFiles = nf;
+  const int k = std::min(nf, std::max(job->cfg.numMatches, 0));
+  *n = k;
+  *ok = 0;
+  if (!out) return SGZ_OK;
+  SGZ_REQUIRE(cap >= k, "record buffer too small (%d < %d)", cap, k);
+  job->localSummary.resize((size_t)std::max(nf, 1));
+  int32_t got = 0;
+  SGZ_TRY(sgz_corr_local_summary(job, job->localSummary.data(), nf, &got));   // (fetches keys, NaN flags and boosts)
+  const bool direct = job->direct && (nf == 0 || db->usedFrames == 0 || (job->keysCached && (int)job->hKeys.size() == nf));
+  bool anyNaN = false;
+  if (direct && job->keysCached)
+    for (int f = 0; f < nf; f++) anyNaN |= job->hNaN[(size_t)f] != 0;
+  *ok = direct && !anyNaN;
+  std::vector<int32_t> idx((size_t)nf);
+  for (int f = 0; f < nf; f++) idx[(size_t)f] = f;
+  auto greater = [&](int32_t a, int32_t b) {
+    const float x = job->localSummary[(size_t)a].maxSim, y = job->localSummary[(size_t)b].maxSim;
+    return x != y ? x > y : a < b;
+  };
+  if (k < nf) std::nth_element(idx.begin(), idx.begin() + k, idx.end(), greater);
+  std::sort(idx.begin(), idx.begin() + k);
+  for (int i = 0; i < k; i++) {
+    const int f = idx[(size_t)i];
+    sgz_record r{f, 0, -1, -1, job->localSummary[(size_t)f].maxSim, 1.0f, 1.0f, 0};
+    if (*ok && job->keysCached && job->hKeys[(size_t)f] != 0ull) {
+      r.kind = 1;                                            // the file has an entry
+      r.piOff = (int32_t)(0xffffffffu - (uint32_t)job->hKeys[(size_t)f]);
+      r.boostIn = job->hBoost[(size_t)f];
+    }
+    out[i] = r;
+  }
+  return SGZ_OK;
+}
+
+int sgz_corr_finish_from_best(sgz_corr *job, const sgz_record *all, int32_t nAll, int32_t nFilesGlobal) {
+  SGZ_REQUIRE(job && (all || nAll == 0), "NULL argument");
+  if (!job->scanned) { set_error("sgz_corr_finish_from_best before scan"); return SGZ_ERR_STATE; }
+  SGZ_REQUIRE(!job->hasOut && job->cfg.numPerFile == 1, "sgz_corr_finish_from_best is for punch-in searches with numPerFile = 1");
+  const int K = job->cfg.numMatches, step = job->step, W = job->qin.W;
+  std::vector<sgz_record> recs(all, all + nAll);
+  std::stable_sort(recs.begin(), recs.end(), [](const sgz_record &a, const sgz_record &b) { return a.file < b.file; });
+  job->allPrio.clear();
+  if (K > 0)
+    for (const sgz_record &r : recs) {                       // the files in list order, FeatureCorrelationImpl.scala:160-165
+      SGZ_REQUIRE(r.file >= 0 && r.file < nFilesGlobal, "record names file %d of %d", r.file, nFilesGlobal);
+      if (r.kind != 1) continue;                             // no valid offset in that file
+      // entryHasSpace || sim > lowestSim (:120-129) with an empty entryPrio, then allPrio ++= entryPrio; take(numMatches)
+      if ((int)job->allPrio.size() < K || r.sim > job->allPrio.back().sim) {
+        sgz_match m;
+        m.sim = r.sim; m.file = r.file;
+        m.start = feat_to_full(r.piOff, step);
+        m.stop = feat_to_full(r.piOff + W, step);
+        m.boostIn = r.boostIn; m.boostOut = 1.0f;
+        allprio_add(job->allPrio, m);
+        if ((int)job->allPrio.size() > K) job->allPrio.resize(K);
+      }
+    }
+  job->nFilesGlobal = nFilesGlobal;
+  job->nextFile = nFilesGlobal;
+  job->globalSet = true;
+  job->finished = true;
+  job->progress = 1.0f;
+  return SGZ_OK;
+}
+
 int sgz_corr_set_global_top(sgz_corr *job, const sgz_file_entry *all, int32_t nAll, int32_t nFilesGlobal, int32_t myFirstFile) {
   SGZ_REQUIRE(job && (all || nAll == 0), "NULL argument");
   if (!job->scanned) { set_error("sgz_corr_set_global_top before scan"); return SGZ_ERR_STATE; }

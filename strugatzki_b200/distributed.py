@@ -96,7 +96,42 @@ def sharded_search(job, device=None, group=None, trace: Optional[dict] = None) -
     rank = dist.get_rank(group)
     job.scan()
     mark("scan")
-    if getattr(job, "sparse_summary", False):
+    if getattr(job, "one_exchange", False):
+        # punch-in only, one match per file: the entries of every rank's numMatches best files are all the search needs
+        # (strugatzki_b200.h, sgz_corr_local_best); record 0 of a rank's message carries its number of files and whether
+        # the shortcut applies there.  Every rank sees the same gathered bytes, so all take the same branch.
+        from . import _native as N
+        recs, n_local, ok = job.local_best()
+        msg = np.zeros(recs.shape[0] + 1, N.RECORD_DTYPE)
+        msg[0]["file"] = n_local
+        msg[0]["kind"] = 1 if ok else 0
+        msg[1:] = recs
+        mark("summary_download")
+        everything, counts = allgather_bytes(msg, device, group, tag="best", initial_cap=1 << 13)
+        mark("summary_allgather")
+        starts = np.concatenate([[0], np.cumsum(counts)])
+        n_files = [int(everything[starts[r]]["file"]) for r in range(len(counts))]
+        all_ok = all(int(everything[starts[r]]["kind"]) == 1 for r in range(len(counts)))
+        first = np.concatenate([[0], np.cumsum(n_files)])
+        parts = []
+        for r in range(len(counts)):
+            e = everything[starts[r] + 1:starts[r + 1]].copy()
+            e["file"] += first[r]
+            parts.append(e)
+        best = np.concatenate(parts) if parts else np.zeros(0, N.RECORD_DTYPE)
+        if all_ok:
+            job.finish_from_best(best, int(first[-1]))
+            mark("merge")
+            if trace is not None:
+                trace["rounds"] = trace.get("rounds", 0)
+            res = job.result()
+            mark("result")
+            return res
+        entries = np.zeros(best.shape[0], N.ENTRY_DTYPE)       # some rank holds NaN windows: the round protocol
+        entries["file"] = best["file"]
+        entries["maxSim"] = best["sim"]
+        job.set_global_top(entries, int(first[-1]), int(first[rank]))
+    elif getattr(job, "sparse_summary", False):
         # punch-in only: the numMatches largest file maxima of every rank are all the thresholds need (strugatzki_b200.h);
         # entry 0 of each rank's message carries its number of files
         from . import _native as N

@@ -6,6 +6,7 @@ device memory never crosses this layer.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -185,6 +186,8 @@ class CorrelationJob:
         # sharded searches: punch-in-only jobs exchange the numMatches largest file maxima per rank instead of one
         # summary per file (sgz_corr_local_top / sgz_corr_set_global_top)
         self.sparse_summary = not bool(cfg.hasPunchOut)
+        # ... and with one match per file the whole search is ONE exchange (sgz_corr_local_best / finish_from_best)
+        self.one_exchange = self.sparse_summary and int(cfg.numPerFile) == 1 and os.environ.get("SGZ_ONE_EXCHANGE", "1") != "0"
 
     def close(self):
         if self._h:
@@ -270,6 +273,19 @@ class CorrelationJob:
         a = np.ascontiguousarray(all_entries, N.ENTRY_DTYPE)
         N.check(N.lib().sgz_corr_set_global_top(self._h, N.fptr(a) if a.shape[0] else None, a.shape[0], int(n_files_global),
                                                 int(my_first_file)))
+
+    def local_best(self):
+        """(records of this rank's numMatches best files with LOCAL file indices, number of local files, ok): the ONE
+        message of a punch-in search with numPerFile = 1 (sgz_corr_local_best); ok = False -> use local_top / select"""
+        n, nf, ok = C.c_int32(), C.c_int32(), C.c_int32()
+        N.check(N.lib().sgz_corr_local_best(self._h, None, 0, C.byref(n), C.byref(nf), C.byref(ok)))
+        out = np.zeros(max(n.value, 1), N.RECORD_DTYPE)
+        N.check(N.lib().sgz_corr_local_best(self._h, N.fptr(out), out.shape[0], C.byref(n), C.byref(nf), C.byref(ok)))
+        return out[:n.value], nf.value, bool(ok.value)
+
+    def finish_from_best(self, all_records: np.ndarray, n_files_global: int):
+        a = np.ascontiguousarray(all_records, N.RECORD_DTYPE)
+        N.check(N.lib().sgz_corr_finish_from_best(self._h, N.fptr(a) if a.shape[0] else None, a.shape[0], int(n_files_global)))
 
     def select(self) -> np.ndarray:
         n = C.c_int32()

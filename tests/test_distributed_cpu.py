@@ -101,6 +101,37 @@ def _worker(rank, world, port, out_q):
         assert sj.n_global == total and sj.first == sum(r + 2 for r in range(rank))
         assert list(sj.entries["file"]) == [sum(q + 2 for q in range(r)) + r + 1 for r in range(world)]
         assert np.allclose(sj.entries["maxSim"], [0.1 * (r + 1) + 0.01 * (r + 1) for r in range(world)])
+        # 4. one match per file: ONE exchange of every rank's best entries; rank 1 once reports a NaN file (ok = False) and
+        # everybody must then continue with the round protocol on the same gathered bytes
+        class BestJob(SparseJob):
+            one_exchange = True
+            nan_rank = -1
+
+            def local_best(self):
+                r = np.zeros(1, N.RECORD_DTYPE)
+                r["file"], r["kind"], r["piOff"] = self.n_local - 1, 1, 7 + rank
+                r["sim"] = 0.1 * (rank + 1) + 0.01 * (self.n_local - 1)
+                return r, self.n_local, rank != self.nan_rank
+
+            def finish_from_best(self, best, n_files_global):
+                self.finished_with = best.copy()
+                self.n_global = n_files_global
+                self.best = sorted(((float(x), int(f)) for x, f in zip(best["sim"], best["file"])), reverse=True)[:3]
+
+            def local_top(self):
+                raise AssertionError("the top entries travel inside the best records")
+
+        bj = BestJob()
+        res3 = sharded_search(bj)
+        assert bj.rounds == 0 and bj.n_global == total                       # no selection round at all
+        assert list(bj.finished_with["file"]) == [sum(q + 2 for q in range(r)) + r + 1 for r in range(world)]
+        assert list(bj.finished_with["piOff"]) == [7 + r for r in range(world)]
+        fb = BestJob()
+        fb.nan_rank = 1
+        sharded_search(fb)
+        assert not hasattr(fb, "finished_with") and fb.rounds == 2            # fell back: set_global_top + rounds
+        assert list(fb.entries["file"]) == list(bj.finished_with["file"])
+        assert np.allclose(fb.entries["maxSim"], bj.finished_with["sim"])
         out_q.put((rank, res))
     finally:
         dist.destroy_process_group()

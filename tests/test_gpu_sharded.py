@@ -66,6 +66,81 @@ def test_sharded_equals_single(ctx, punch_out, num_matches, num_per_file, split)
         assert all((f, off * STEP) in found for f, off in plants)   # every planted needle is recovered
 
 
+def drive_one_exchange(jobs):
+    """what distributed.sharded_search does with job.one_exchange: ONE gather of every shard's best entries"""
+    for j in jobs:
+        j.scan()
+    msgs = [j.local_best() for j in jobs]
+    first = np.cumsum([0] + [nf for _, nf, _ in msgs])
+    parts = []
+    for (recs, _, _), f0 in zip(msgs, first):
+        e = recs.copy()
+        e["file"] += f0
+        parts.append(e)
+    best = np.concatenate(parts)
+    all_ok = all(ok for _, _, ok in msgs)
+    if all_ok:
+        for j in jobs:
+            j.finish_from_best(best, int(first[-1]))
+        rounds = 0
+    else:
+        entries = np.zeros(best.shape[0], N.ENTRY_DTYPE)
+        entries["file"], entries["maxSim"] = best["file"], best["sim"]
+        for j, f0 in zip(jobs, first):
+            j.set_global_top(entries, int(first[-1]), int(f0))
+        done, rounds = False, 0
+        while not done:
+            recs = np.concatenate([j.select() for j in jobs])
+            done = all([j.merge(recs) for j in jobs])
+            rounds += 1
+            assert rounds < 1000
+    res = [j.result() for j in jobs]
+    assert all(r == res[0] for r in res)
+    return res[0], rounds, all_ok
+
+
+@pytest.mark.parametrize("num_matches,split,silence", [
+    (100, (70, 140), False), (7, (5, 100), False), (250, (100,), False), (30, (60, 150), True), (3, (1, 2, 3, 199), False),
+])
+def test_one_exchange_equals_single_and_oracle(ctx, num_matches, split, silence):
+    """numPerFile = 1, punch-in only: the entries of each shard's numMatches best files decide the search (one exchange,
+    no selection kernels).  More matches than files with offsets, shards of a single file, and a shard with digital silence
+    (NaN windows: that shard reports ok = False and everybody falls back to the round protocol) -- always the single-GPU
+    result, which on a database small enough is the oracle's."""
+    from strugatzki_b200 import engine
+    mu, sigma, floor0, norm = synth.default_profile(14)
+    n_files, frames = 200, 1500
+    inp = make_input(900)
+    rng = np.random.default_rng(17)
+    files = [synth.synth_file(synth.BASE_SEED, 1 + g, frames if g % 17 else 120, mu, sigma, floor0) for g in range(n_files)]
+    for k in range(12):
+        f, off = int(rng.integers(0, n_files)), int(rng.integers(0, frames - 400))
+        if files[f].shape[0] >= frames:
+            files[f][off:off + 172] = synth.plant(inp[:172], 3, k)
+    if silence:
+        files[65][200:700] = files[65][200]          # constant stretch: NaN windows in the second shard
+    op, cfg = corr_cfgs(inp, norm, num_matches=num_matches, num_per_file=1, min_spacing=22050)
+
+    def build(lo, hi):
+        db = engine.Database(ctx, 14, norm)
+        for g in range(lo, hi):
+            db.add_file(files[g])
+        db.finalize()
+        return db
+
+    single = engine.CorrelationJob(build(0, n_files), cfg, inp).run()
+    assert_matches_equal(single, O.corr_search(op, files))
+    bounds = (0,) + tuple(split) + (n_files,)
+    jobs = [engine.CorrelationJob(build(a, b), cfg, inp) for a, b in zip(bounds, bounds[1:])]
+    assert all(j.one_exchange for j in jobs)
+    sharded, rounds, all_ok = drive_one_exchange(jobs)
+    # same files, spans and boosts; the sims agree to the kernel's rounding -- the order in which the tensor cores add an
+    # offset's products, and the frame a thread's run of 16 offsets is centred on, depend on the offset's position in the
+    # DATABASE modulo 64 (bit-identical when the shards begin on multiples of 64 frames, as in test_sharded_equals_single)
+    assert_matches_equal(sharded, single, rel=1e-6)
+    assert all_ok == (not silence) and (rounds == 0) == all_ok
+
+
 def test_search_is_idempotent_and_order_sensitive(ctx):
     """same job run twice -> identical result; the DB order is part of the semantics (Q3): reversing it may change
     which equal-rank matches survive, but never the best match"""
