@@ -109,16 +109,15 @@ def sharded_search(job, device=None, group=None, trace: Optional[dict] = None) -
         mark("summary_download")
         everything, counts = allgather_bytes(msg, device, group, tag="best", initial_cap=1 << 13)
         mark("summary_allgather")
-        starts = np.concatenate([[0], np.cumsum(counts)])
-        n_files = [int(everything[starts[r]]["file"]) for r in range(len(counts))]
-        all_ok = all(int(everything[starts[r]]["kind"]) == 1 for r in range(len(counts)))
-        first = np.concatenate([[0], np.cumsum(n_files)])
-        parts = []
-        for r in range(len(counts)):
-            e = everything[starts[r] + 1:starts[r + 1]].copy()
-            e["file"] += first[r]
-            parts.append(e)
-        best = np.concatenate(parts) if parts else np.zeros(0, N.RECORD_DTYPE)
+        cnt = np.asarray(counts, np.int64)
+        starts = np.concatenate([[0], np.cumsum(cnt)])
+        hdr = everything[starts[:-1]]                           # record 0 of every rank
+        all_ok = bool((hdr["kind"] == 1).all())
+        first = np.concatenate([[0], np.cumsum(hdr["file"].astype(np.int64))])
+        keep = np.ones(everything.shape[0], bool)
+        keep[starts[:-1]] = False
+        best = everything[keep]                                 # (a copy) all entries, rank order = file order
+        best["file"] += first[np.repeat(np.arange(cnt.shape[0]), cnt - 1)].astype(np.int32)
         if all_ok:
             job.finish_from_best(best, int(first[-1]))
             mark("merge")
