@@ -647,7 +647,8 @@ int sgz_corr_scan(sgz_corr *job) {
     }
   }
   SGZ_TRY(job->simIn.alloc(n));
-  if (!t2) SGZ_TRY(job->boostIn.alloc(n));   // the tensor-core scan writes no boost curve (BoostSrc, corr_fix.cuh)
+  // the tensor-core scan writes no boost curve (BoostSrc, corr_fix.cuh); punch-out searches get one from k_boost_all
+  if (!t2 || job->hasOut) SGZ_TRY(job->boostIn.alloc(n));
   SGZ_TRY(job->dFileMax.alloc((size_t)std::max(db->numFiles(), 1)));
   {
     static const bool directOff = getenv("SGZ_DIRECT_SELECT") && atoi(getenv("SGZ_DIRECT_SELECT")) == 0;   // developer knob
@@ -660,7 +661,7 @@ int sgz_corr_scan(sgz_corr *job) {
   }
   if (job->hasOut) {
     SGZ_TRY(job->simOut.alloc(n));
-    if (!t2) SGZ_TRY(job->boostOut.alloc(n));
+    SGZ_TRY(job->boostOut.alloc(n));
     SGZ_TRY(job->dFileMaxOut.alloc((size_t)std::max(db->numFiles(), 1)));
   }
   const int tailIn = job->hasOut ? job->minPunchF : 0;
@@ -712,6 +713,7 @@ int sgz_corr_scan(sgz_corr *job) {
     if (t2 && db->usedFrames > 0) {
       SGZ_TRY(run_fixup(job, job->qin, 0, tailIn, job->simIn.p, job->dFileMax.p, ss));
       if (job->hasOut) SGZ_TRY(run_fixup(job, job->qout, 1, 0, job->simOut.p, job->dFileMaxOut.p, ss));
+      if (job->hasOut) SGZ_TRY(run_boost_curves(job, ss));
       if (job->direct) {
         k_filemax_boost<<<ceil_div(db->numFiles(), 128), 128, 0, ss>>>(boost_src(job, job->qin, nullptr), db->dFileStart.p,
                                                                       job->dFileMax.p, db->numFiles(), job->dFileBoost.p);
@@ -758,6 +760,7 @@ int sgz_corr_scan(sgz_corr *job) {
           SGZ_TRY(run_scan_t2(job, job->qout, 1, 0, job->simOut.p, job->dFileMaxOut.p, 0, job->numTilesT2,
                               ctx->stream, 0));
           SGZ_TRY(run_fixup(job, job->qout, 1, 0, job->simOut.p, job->dFileMaxOut.p, ctx->stream));
+          SGZ_TRY(run_boost_curves(job, ctx->stream));
         } else if (tc) SGZ_TRY(run_scan_tc(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, ctx->stream));
         else
           SGZ_TRY(run_scan_one(job, job->qout, 0, job->simOut.p, job->boostOut.p, job->dFileMaxOut.p, 0, job->numTiles,

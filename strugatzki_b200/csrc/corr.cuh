@@ -370,6 +370,18 @@ inline int run_fixup(sgz_corr *job, PunchQuery &q, int which, int tailExtra, flo
   return SGZ_OK;
 }
 
+// boost curves of both punch windows of a punch-out search on the tensor-core scan (k_boost_all, corr_fix.cuh)
+inline int run_boost_curves(sgz_corr *job, cudaStream_t st) {
+  sgz_db *db = job->db;
+  if (db->usedFrames <= 0) return SGZ_OK;
+  const unsigned blocks = (unsigned)ceil_div<int64_t>(ceil_div<int64_t>(db->usedFrames, kBoostRun), 128);
+  k_boost_all<<<blocks, 128, 0, st>>>(db->dData.p, db->usedFrames, job->qin.W, job->qin.lnAvg, job->boostIn.p);
+  SGZ_LAUNCH_CHECK(job->ctx);
+  k_boost_all<<<blocks, 128, 0, st>>>(db->dData.p, db->usedFrames, job->qout.W, job->qout.lnAvg, job->boostOut.p);
+  SGZ_LAUNCH_CHECK(job->ctx);
+  return SGZ_OK;
+}
+
 inline int run_scan_t2(sgz_corr *job, PunchQuery &q, int which, int tailExtra, float *sim,
                        unsigned long long *fileMax, int64_t tileBegin, int64_t tileEnd, cudaStream_t st, int spareSMs) {
   if (tileEnd <= tileBegin) return SGZ_OK;

@@ -132,6 +132,23 @@ __global__ void k_filemax_boost(BoostSrc b, const int64_t *__restrict__ fileStar
   out[f] = b.at(fileStart[f] + tl, tl);
 }
 
+// Boost CURVE of a punch window for every global frame (punch-out searches: the grid kernels look a boost up per candidate
+// CELL, thousands per file, where a punch-in search needs a handful).  A thread slides the Double loudness sum over a run
+// of 32 offsets; the sum differs from the reference's ring-order sum in its last bits only (the boost is compared at 1e-5).
+constexpr int kBoostRun = 32;
+__global__ void k_boost_all(const float2 *__restrict__ data, int64_t usedFrames, int W, double lnAvgIn, float *__restrict__ out) {
+  const int64_t g0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * kBoostRun;
+  if (g0 >= usedFrames) return;
+  double sum = 0.0;
+  for (int i = 0; i < W; i++) sum += (double)data[g0 + i].x;          // (the zero slack behind the database is readable)
+  const int n = (int)min((int64_t)kBoostRun, usedFrames - g0);
+  for (int j = 0; j < n; j++) {
+    const float avg = (float)(sum / (double)W);
+    out[g0 + j] = expf(((float)lnAvgIn - logf(avg)) * (1.0f / 0.6f));      // (1e-6 relative; the contract is 1e-5)
+    sum += (double)data[g0 + j + W].x - (double)data[g0 + j].x;
+  }
+}
+
 // boost values of n consecutive offsets of one file (sgz_corr_curve)
 __global__ void k_boost_curve(BoostSrc b, int64_t g0, int64_t tl0, int64_t n, float *__restrict__ out) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
