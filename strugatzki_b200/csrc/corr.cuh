@@ -429,6 +429,8 @@ inline int run_scan_t2(sgz_corr *job, PunchQuery &q, int which, int tailExtra, f
     tp.splitRelease = split;
     static const int l2hint = getenv("SGZ_T2_L2HINT") ? atoi(getenv("SGZ_T2_L2HINT")) : 7;             // developer knob
     tp.l2hint = l2hint;
+    static const int narrow = getenv("SGZ_T2_NARROW") ? atoi(getenv("SGZ_T2_NARROW")) : 1;               // developer knob
+    tp.narrow = narrow;
   }
   const bool prof = getenv("SGZ_CORR_TC_PROF") != nullptr;   // developer probe: cycles per role and phase
   auto kern = G.NP > 1 ? (prof ? k_corr_tc2<true, true> : k_corr_tc2<false, true>) : (prof ? k_corr_tc2<true, false> : k_corr_tc2<false, false>);

@@ -280,6 +280,7 @@ struct CorrT2Params {
   int ahead;                    // channels between the L2 prefetch of a signal stage and its bulk copy (0: no prefetch)
   int ring;                     // initial ring depths (signal << 4 | taps) of t2_geom
   int tapsFirst;                // developer knob: request the taps of a channel before its planes
+  int narrow;                   // 1: band-limited MMAs (narrower N) in the first / last K steps of a window
   int l2hint;                   // bit 0: signal planes evict_first, bit 1: taps + block sums evict_last, bit 2: streaming curve stores
   int splitRelease;             // 1: the epilogue hands the two temporal accumulators back before it reads the spectral ones
   int dbg;                      // developer knob (SGZ_T2_DBG, profiling build only): 1 = no MMAs, 2 = no per-offset work, 4 = no curve stores, 8 = no per-frame loads, 16 = no window slides, 32 = no evaluation
@@ -445,8 +446,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    // D = F32, A = B = F16, both K-major, N = 64, M = 128
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(kT2P >> 3) << 17) | ((uint32_t)(kT2M >> 4) << 24);
+    // D = F32, A = B = F16, both K-major, M = 128, N = 64 (narrower at the edges of the taps band, see below)
+    auto make_idesc = [](uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((uint32_t)(kT2M >> 4) << 24); };
+    const uint32_t idesc = make_idesc(kT2P), id16 = make_idesc(16), id32 = make_idesc(32), id48 = make_idesc(48);
     uint32_t it = 0, tileIt = 0, passIt = 0;
     long long cAcc = 0, cSig = 0, cTap = 0, cIssue = 0, cTotal = 0, tA = 0;
     if (kProf) cTotal = clock64();
@@ -483,13 +485,36 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
         const uint64_t tHi = tc_desc(tHiA, 256, 6), tLo = tc_desc(tHiA + (uint32_t)G.natom * 256u, 256, 6);
         if (tc_elect()) {
           // one K step of 16: A start +32 B (2 descriptor units), taps start +2 atoms = 512 B (32 units); a1 t1 and
-          // a1 t2 share the A operand through the collector
-          uint64_t d1 = aHi, d2 = aLo, b1 = tHi, b2 = tLo;
-          for (int k = 0; k < nk; k++, d1 += 2, d2 += 2, b1 += 32, b2 += 32) {
-            if ((kProf && p.dbg & 1)) break;
-            tc_mma_fill(dMain, d1, b1, idesc, accMain | (uint32_t)(k > 0));
-            tc_mma_lastuse(dCorr, d1, b2, idesc, accCorr | (uint32_t)(k > 0));
-            tc_mma(dCorr, d2, b1, idesc, 1);
+          // a1 t2 share the A operand through the collector.
+          // The taps matrix is a band: in K step S only the columns c with 0 <= 16 S + kk + c - 63 < W hold taps, i.e.
+          // c in [48 - 16 S, 62 + W - 16 S].  The first three and the last three K steps of a window therefore run as
+          // narrower MMAs -- N = 16, 32, 48 on columns 48.., 32.., 16.. at the head, N = 48, 32, 16 on columns 0.. at the
+          // tail: a fifth of the tensor work at W = 172 -- and the K step issued FIRST is a full one (k = 3), because it
+          // may have to overwrite the accumulator.  (One-pass windows of at least 7 K steps; the issue loop is the
+          // critical path of the kernel, so the six narrow steps are written out with constant geometry.)
+          auto kstep = [&](uint32_t k, uint32_t c0, uint32_t id, uint32_t acc) {
+            const uint64_t d1 = aHi + 2u * k, d2 = aLo + 2u * k, b1 = tHi + 32u * k + 2u * c0, b2 = tLo + 32u * k + 2u * c0;
+            tc_mma_fill(dMain + c0, d1, b1, id, accMain | acc);
+            tc_mma_lastuse(dCorr + c0, d1, b2, id, accCorr | acc);
+            tc_mma(dCorr + c0, d2, b1, id, 1);
+          };
+          if (!kMulti && p.narrow && nk >= 7 && !(kProf && p.dbg & 1)) {
+            uint64_t d1 = aHi + 6, d2 = aLo + 6, b1 = tHi + 96, b2 = tLo + 96;
+            for (int k = 3; k <= nk - 4; k++, d1 += 2, d2 += 2, b1 += 32, b2 += 32) {
+              tc_mma_fill(dMain, d1, b1, idesc, accMain | (uint32_t)(k > 3));
+              tc_mma_lastuse(dCorr, d1, b2, idesc, accCorr | (uint32_t)(k > 3));
+              tc_mma(dCorr, d2, b1, idesc, 1);
+            }
+            kstep(0u, 48u, id16, 1u); kstep(1u, 32u, id32, 1u); kstep(2u, 16u, id48, 1u);
+            kstep((uint32_t)nk - 3u, 0u, id48, 1u); kstep((uint32_t)nk - 2u, 0u, id32, 1u); kstep((uint32_t)nk - 1u, 0u, id16, 1u);
+          } else {
+            uint64_t d1 = aHi, d2 = aLo, b1 = tHi, b2 = tLo;
+            for (int k = 0; k < nk; k++, d1 += 2, d2 += 2, b1 += 32, b2 += 32) {
+              if ((kProf && p.dbg & 1)) break;
+              tc_mma_fill(dMain, d1, b1, idesc, accMain | (uint32_t)(k > 0));
+              tc_mma_lastuse(dCorr, d1, b2, idesc, accCorr | (uint32_t)(k > 0));
+              tc_mma(dCorr, d2, b1, idesc, 1);
+            }
           }
           tc_commit(sigFree + s);
           tc_commit(tapFree + t);
