@@ -397,13 +397,16 @@ def main():
                         "frac": hbm["frac"] if intensity < ridge else flops / tensor_peak,
                         "peak_source": hbm_src if intensity < ridge else tensor["peak_source"],
                         "intensity_flop_per_byte": intensity, "ridge_flop_per_byte": ridge,
-                        "why_not_higher": "three split-FP16 products for FP32-grade precision: the 630 M128xN64xK16 MMAs of a "
-                                          "tile of 8192 offsets take 30 k cycles of the MMA pipe (47.6 cycles each: an MMA fetches "
-                                          "6 KB of operands from shared memory at 128 B/clock); the bulk copies that feed them "
-                                          "bring 74 B/offset from HBM (about 29 k cycles per tile at the measured HBM rate) and "
-                                          "overlap with the MMAs through a 4-deep ring: 42 k cycles per tile, of which the issuer "
-                                          "waits 6 k for operands (ring depth, L2 prefetch and copy order change nothing, "
-                                          "tools/t2_ablate.py); the epilogue (19 k) hides behind the MMAs of the next tile",
+                        "why_not_higher": "power: with the tensor cores, HBM and 16 epilogue warps busy at once the GPU sits at its "
+                                          "1000 W cap and the SM clock averages 1.48 GHz INSIDE the kernel (clock64 / %globaltimer per "
+                                          "CTA; 1.96 GHz with the MMAs ablated; nvidia-smi's samples between launches read higher) -- "
+                                          "a tile of 8192 offsets takes 40.8 k cycles (20.8 us at 1.965 GHz = frac 0.57, 27.6 us at the "
+                                          "capped clock).  In cycles: three split-FP16 products for FP32-grade precision = 630 MMAs per "
+                                          "tile, 28.9 k cycles of MMA issue (an M128xN64xK16 MMA fetches 6 KB of operands from shared "
+                                          "memory at 128 B/clock; the band of the taps matrix already runs as N = 16/32/48 MMAs at its "
+                                          "edges), 7 k cycles waiting for operands / accumulators, the epilogue (25 k) hidden behind "
+                                          "the next tile's MMAs; data movement alone takes 25 k cycles per tile at full clock "
+                                          "(profiles/r02_k_corr_tc2_power_ablation.txt)",
                         "tensor": tensor}
         else:
             roofline = {"kernel": "sgz::k_corr (K1 sliding-window Pearson correlation, FFMA2)", "bound": "fp32_ffma",

@@ -455,6 +455,23 @@ inline int run_scan_t2(sgz_corr *job, PunchQuery &q, int which, int tailExtra, f
                     "|| epilogue singles + wait sums %.0f, window init %.0f, wait accFull %.0f, tmem read %.0f, 16 offsets %.0f\n",
             a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles, a[4] / tiles, a[8] / tiles, a[9] / tiles, a[10] / tiles,
             a[11] / tiles, a[12] / tiles);
+    // per CTA: a static round-robin of tiles ends with the slowest SM
+    std::vector<double> cyc, ns;
+    for (unsigned b = 0; b < grid; b++)
+      if (h[(size_t)b * 24 + 5] > 0) {
+        cyc.push_back((double)h[(size_t)b * 24] / (double)h[(size_t)b * 24 + 5]);
+        ns.push_back((double)h[(size_t)b * 24 + 6]);
+      }
+    if (!cyc.empty()) {
+      std::vector<double> c2 = cyc, n2 = ns;
+      std::sort(c2.begin(), c2.end()); std::sort(n2.begin(), n2.end());
+      fprintf(stderr, "k_corr_tc2 per CTA: cycles per tile min %.0f, median %.0f, max %.0f | issuer wall ns min %.0f, median %.0f, max %.0f | mean clock %.3f GHz\n",
+              c2.front(), c2[c2.size() / 2], c2.back(), n2.front(), n2[n2.size() / 2], n2.back(), a[0] / std::max(a[6], 1.0));
+      if (getenv("SGZ_T2_PROF_CTAS")) {
+        for (size_t b = 0; b < cyc.size(); b++) fprintf(stderr, "%s%.0f", b ? " " : "k_corr_tc2 cycles per tile by CTA: ", cyc[b]);
+        fprintf(stderr, "\n");
+      }
+    }
   }
   return SGZ_OK;
 }

@@ -451,7 +451,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
     const uint32_t idesc = make_idesc(kT2P), id16 = make_idesc(16), id32 = make_idesc(32), id48 = make_idesc(48);
     uint32_t it = 0, tileIt = 0, passIt = 0;
     long long cAcc = 0, cSig = 0, cTap = 0, cIssue = 0, cTotal = 0, tA = 0;
-    if (kProf) cTotal = clock64();
+    unsigned long long nsTotal = 0;
+    if (kProf) { cTotal = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(nsTotal)); }
     for (int64_t tile = p.tileBegin + blockIdx.x; tile < p.tileEnd; tile += gridDim.x, tileIt++) {
       for (int j = 0; j < NP; j++, passIt++) {
       const int nk = j == NP - 1 ? G.KSlast : G.KS;
@@ -527,7 +528,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
     }
     if (kProf && p.prof && lane == 0) {
       long long *o = p.prof + 24 * blockIdx.x;
-      o[0] = clock64() - cTotal; o[1] = cAcc; o[2] = cSig; o[3] = cTap; o[4] = cIssue; o[5] = tileIt;
+      unsigned long long nsEnd;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(nsEnd));
+      o[0] = clock64() - cTotal; o[1] = cAcc; o[2] = cSig; o[3] = cTap; o[4] = cIssue; o[5] = tileIt; o[6] = (long long)(nsEnd - nsTotal);
     }
   }
   } else {
