@@ -217,7 +217,10 @@ int sgz_corr_result(sgz_corr *job, sgz_match *out, int32_t cap, int32_t *n);
 int sgz_corr_num_offsets(sgz_corr *job, int64_t *n);
 
 /* device time (CUDA events on the context stream) of the last scan (K1) and of the selection
- * kernels (K2) accumulated since that scan, plus the number of kernels the scan launched */
+ * kernels (K2) accumulated since that scan, plus the number of kernels the scan launched.
+ * Punch-in searches on the tensor-core scan: scanMs is the K1 launch alone; what follows it inside
+ * sgz_corr_scan (exact re-evaluation of ill-conditioned and of decisive offsets, per-file boosts)
+ * is the first part of selectMs. */
 int sgz_corr_timing(sgz_corr *job, float *scanMs, float *selectMs, int64_t *scanLaunches);
 
 /* Debug / parity access to the ungated curves in HBM: which = 0 punch-in, 1 punch-out.

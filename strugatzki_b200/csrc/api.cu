@@ -65,6 +65,7 @@ int sgz_ctx_create(int32_t device, sgz_ctx **out) {
   SGZ_CUDA(cudaStreamCreateWithFlags(&c->scanStream, cudaStreamNonBlocking));
   SGZ_CUDA(cudaEventCreate(&c->ev0));
   SGZ_CUDA(cudaEventCreate(&c->ev1));
+  SGZ_CUDA(cudaEventCreate(&c->evMid));
   *out = c;
   return SGZ_OK;
 }
@@ -75,6 +76,7 @@ static void ctx_free(sgz_ctx *ctx) {
   cudaStreamSynchronize(ctx->scanStream);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
+  cudaEventDestroy(ctx->evMid);
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->scanStream);
   delete ctx;
@@ -613,6 +615,7 @@ int sgz_corr_scan(sgz_corr *job) {
   sgz_db *db = job->db;
   SGZ_TRY(ctx->bind());
   if (job->abortFlag) return SGZ_ERR_ABORTED;
+  job->tailMs = 0.f;
   size_t n = (size_t)job->numTiles * kR * job->ntg;
   const bool t2 = job->useT2;
   const bool tc = !t2 && job->useTc && db->chunks.empty();   // round-1 kernels: a streaming scan takes the FFMA2 path
@@ -654,6 +657,15 @@ int sgz_corr_scan(sgz_corr *job) {
     static const bool directOff = getenv("SGZ_DIRECT_SELECT") && atoi(getenv("SGZ_DIRECT_SELECT")) == 0;   // developer knob
     job->direct = t2 && !job->hasOut && job->cfg.numPerFile == 1 && !directOff;
     job->keysCached = false;
+    static const bool refineOff = getenv("SGZ_REFINE") && atoi(getenv("SGZ_REFINE")) == 0;   // developer knob
+    job->refine = t2 && !job->hasOut && !refineOff;
+    if (job->refine) {
+      SGZ_TRY(job->dRefList.alloc(kRefineCap));
+      SGZ_TRY(job->dRefCount.alloc(2));
+      SGZ_TRY(job->dRefCand.alloc((size_t)std::max(db->numFiles(), 1)));
+      SGZ_TRY(job->dRefThr.alloc(1));
+      SGZ_TRY(job->dFileMaxExact.alloc((size_t)std::max(db->numFiles(), 1)));
+    }
     if (job->direct) {
       SGZ_TRY(job->dFileNaN.alloc((size_t)std::max(db->numFiles(), 1)));
       SGZ_TRY(job->dFileBoost.alloc((size_t)std::max(db->numFiles(), 1)));
@@ -712,12 +724,11 @@ int sgz_corr_scan(sgz_corr *job) {
     SGZ_CUDA(cudaStreamWaitEvent(ss, db->chunks.back().ev, 0));   // file table for the row maxima / later kernels
     if (t2 && db->usedFrames > 0) {
       SGZ_TRY(run_fixup(job, job->qin, 0, tailIn, job->simIn.p, job->dFileMax.p, ss));
+      if (job->refine) SGZ_TRY(run_refine(job, ss));
       if (job->hasOut) SGZ_TRY(run_fixup(job, job->qout, 1, 0, job->simOut.p, job->dFileMaxOut.p, ss));
       if (job->hasOut) SGZ_TRY(run_boost_curves(job, ss));
       if (job->direct) {
-        k_filemax_boost<<<ceil_div(db->numFiles(), 128), 128, 0, ss>>>(boost_src(job, job->qin, nullptr), db->dFileStart.p,
-                                                                      job->dFileMax.p, db->numFiles(), job->dFileBoost.p);
-        SGZ_LAUNCH_CHECK(ctx);
+        SGZ_TRY(run_filemax_boost(job, ss));
       }
     }
     if (job->hasOut && db->usedFrames > 0) {
@@ -735,6 +746,7 @@ int sgz_corr_scan(sgz_corr *job) {
   } else {
     // once per database (a property of the database like its normalisation, not of the search): FP16 planes + frame sums
     if (t2 && db->usedFrames > 0) SGZ_TRY(db_ensure_planes(db, -1, ctx->stream));
+    bool midRecorded = false;
     SGZ_TRY(ctx->begin_call());
     SGZ_CUDA(cudaMemsetAsync(job->dFileMax.p, 0, job->dFileMax.n * sizeof(unsigned long long), ctx->stream));
     if (job->hasOut)
@@ -745,11 +757,11 @@ int sgz_corr_scan(sgz_corr *job) {
       if (t2) {
         SGZ_TRY(run_scan_t2(job, job->qin, 0, tailIn, job->simIn.p, job->dFileMax.p, 0, job->numTilesT2,
                             ctx->stream, 0));
+        if (!job->hasOut) { SGZ_CUDA(cudaEventRecord(ctx->evMid, ctx->stream)); midRecorded = true; }
         SGZ_TRY(run_fixup(job, job->qin, 0, tailIn, job->simIn.p, job->dFileMax.p, ctx->stream));
+        if (job->refine) SGZ_TRY(run_refine(job, ctx->stream));
         if (job->direct) {
-          k_filemax_boost<<<ceil_div(db->numFiles(), 128), 128, 0, ctx->stream>>>(
-              boost_src(job, job->qin, nullptr), db->dFileStart.p, job->dFileMax.p, db->numFiles(), job->dFileBoost.p);
-          SGZ_LAUNCH_CHECK(ctx);
+          SGZ_TRY(run_filemax_boost(job, ctx->stream));
         }
       } else if (tc) SGZ_TRY(run_scan_tc(job, job->qin, tailIn, job->simIn.p, job->boostIn.p, job->dFileMax.p, ctx->stream));
       else
@@ -777,6 +789,12 @@ int sgz_corr_scan(sgz_corr *job) {
     SGZ_CUDA(cudaStreamSynchronize(ctx->stream));
     SGZ_TRY(ctx->collect_call());
     job->summaryPrefetched = true;
+    if (midRecorded) {   // punch-in scan on the tensor cores: the K1 launch on its own, what follows it counts as selection
+      float k1 = 0.f;
+      SGZ_CUDA(cudaEventElapsedTime(&k1, ctx->ev0, ctx->evMid));
+      job->tailMs = ctx->lastMs - k1;
+      ctx->lastMs = k1;
+    }
   }
   job->scanMs = ctx->lastMs;
   job->scanLaunches = ctx->lastLaunches;
@@ -787,7 +805,7 @@ int sgz_corr_scan(sgz_corr *job) {
   job->nextFile = 0;
   job->finished = false;
   job->globalSet = false;
-  job->selectMs = 0.f;
+  job->selectMs = job->tailMs;
   return SGZ_OK;
 }
 

@@ -119,7 +119,7 @@ struct sgz_ctx {
   size_t smemOptin = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t scanStream = nullptr;   // K1 launches of a streaming scan (overlaps the uploads queued on `stream`)
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evMid = nullptr;   // evMid: end of the K1 launches of a punch-in scan
   int64_t launches = 0;        // total kernels launched on this context
   int64_t callLaunches0 = 0;   // snapshot at begin_call
   float lastMs = 0.f;

@@ -6,6 +6,7 @@
 #include "corr_kernel.cuh"
 #include "corr_tc.cuh"
 #include "corr_tc2.cuh"
+#include "corr_refine.cuh"
 #include "db.cuh"
 #include "select.cuh"
 
@@ -38,6 +39,13 @@ struct sgz_corr {
   DevBuf<int32_t> dTileFile;   // [numTilesTc + 1] file holding the first frame of each tensor-core tile
   DevBuf<int32_t> dTileFileT2; // the same for the 8192-offset tiles of corr_tc2.cuh
   DevBuf<uint32_t> dFixList[2], dFixCount;   // ill-conditioned offsets of the punch-in / punch-out scan (corr_fix.cuh)
+  // exact re-evaluation of the decisive offsets of a punch-in search (corr_refine.cuh)
+  DevBuf<uint32_t> dRefList, dRefCount;
+  DevBuf<int32_t> dRefCand;
+  DevBuf<float> dRefThr;
+  DevBuf<unsigned long long> dFileMaxExact;
+  bool refine = false;      // this scan re-evaluates them
+  float tailMs = 0.f;       // device time of a scan behind its K1 launches (re-evaluations, per-file boosts)
   int64_t numTiles = 0;
   int64_t numOffsets = 0;
   DevBuf<float> simIn, boostIn, simOut, boostOut, rowMaxOut;
@@ -366,6 +374,68 @@ inline int run_fixup(sgz_corr *job, PunchQuery &q, int which, int tailExtra, flo
   fp.sim = sim; fp.boost = boost_src(job, q, nullptr); fp.fileMax = fileMax;
   fp.fileNaN = (which == 0 && job->direct) ? job->dFileNaN.p : nullptr;
   k_corr_fixup<<<(unsigned)job->ctx->smCount * 4, 128, 0, st>>>(fp);
+  SGZ_LAUNCH_CHECK(job->ctx);
+  return SGZ_OK;
+}
+
+// exact sims for every offset that can reach the result of a punch-in search, file maxima rebuilt from them
+// (corr_refine.cuh); enqueued behind run_fixup, before anything reads the curve or the maxima
+inline int run_refine(sgz_corr *job, cudaStream_t st) {
+  sgz_db *db = job->db;
+  const int nf = db->numFiles();
+  if (nf == 0 || db->usedFrames <= 0) return SGZ_OK;
+  PunchQuery &q = job->qin;
+  SGZ_CUDA(cudaMemsetAsync(job->dRefCount.p, 0, 2 * sizeof(uint32_t), st));     // [offsets listed, files listed]
+  SGZ_CUDA(cudaMemsetAsync(job->dFileMaxExact.p, 0, (size_t)nf * sizeof(unsigned long long), st));
+  k_refine_threshold<<<1, kRefineThrThreads, 0, st>>>(job->dFileMax.p, nf, job->cfg.numMatches, kRefineMargin, kRefineTieTol,
+                                         job->dRefThr.p, job->dRefCand.p, job->dRefCount.p + 1);
+  SGZ_LAUNCH_CHECK(job->ctx);
+  k_refine_collect<<<(unsigned)job->ctx->smCount * 8, 256, 0, st>>>(
+      job->simIn.p, db->dFileStart.p, job->dFileMax.p, q.W, 0, job->dRefThr.p, kRefineMargin, job->cfg.numPerFile == 1 ? 1 : 0,
+      job->dRefCand.p, job->dRefCount.p + 1, job->dRefList.p, job->dRefCount.p, kRefineCap);
+  SGZ_LAUNCH_CHECK(job->ctx);
+  CorrFixParams fp{};
+  fp.data = db->dData.p; fp.rowStride = db->capFrames; fp.usedFrames = db->usedFrames;
+  fp.a = q.dAc.p; fp.numCh = db->numCh; fp.W = q.W; fp.stdT = q.stdT; fp.stdS = q.stdS;
+  fp.weight = q.weight; fp.maxBoost = job->cfg.maxBoost;
+  fp.fileStart = db->dFileStart.p; fp.numFiles = nf; fp.tailExtra = 0;
+  fp.list = job->dRefList.p; fp.count = job->dRefCount.p; fp.cap = kRefineCap;
+  fp.sim = job->simIn.p; fp.boost = boost_src(job, q, nullptr); fp.fileMax = job->dFileMaxExact.p;
+  fp.fileNaN = nullptr; fp.listOnly = 1;
+  // a warp per offset with the window in shared memory (k_corr_exact); windows too long for that: a thread per offset
+  const size_t perWarp = kExactBytesPerValue * (size_t)db->numCh * (size_t)q.W;
+  const int warps = (int)std::min<size_t>(4, ((size_t)200 << 10) / perWarp);
+  if (warps >= 1) {
+    const size_t smem = (size_t)warps * perWarp;
+    if (smem > ((size_t)48 << 10))
+      SGZ_CUDA(cudaFuncSetAttribute(k_corr_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_corr_exact<<<(unsigned)job->ctx->smCount * 8, 32 * warps, smem, st>>>(fp);
+  } else {
+    k_corr_fixup<<<(unsigned)job->ctx->smCount * 4, 128, 0, st>>>(fp);
+  }
+  SGZ_LAUNCH_CHECK(job->ctx);
+  k_refine_merge<<<ceil_div(nf, 256), 256, 0, st>>>(job->dFileMaxExact.p, job->dFileMax.p, nf);
+  SGZ_LAUNCH_CHECK(job->ctx);
+  if (getenv("SGZ_REFINE_DEBUG")) {   // developer probe: how much was re-evaluated
+    uint32_t h[2];
+    float t;
+    SGZ_CUDA(cudaMemcpyAsync(h, job->dRefCount.p, sizeof h, cudaMemcpyDeviceToHost, st));
+    SGZ_CUDA(cudaMemcpyAsync(&t, job->dRefThr.p, sizeof t, cudaMemcpyDeviceToHost, st));
+    SGZ_CUDA(cudaStreamSynchronize(st));
+    fprintf(stderr, "refine: threshold %.7g, %u files listed, %u offsets re-evaluated%s\n", t, h[1], h[0],
+            h[0] > kRefineCap ? " (list overflowed: none)" : "");
+  }
+  return SGZ_OK;
+}
+
+// boost of every file's best offset (numPerFile = 1 searches take their entries from the file maxima)
+inline int run_filemax_boost(sgz_corr *job, cudaStream_t st) {
+  sgz_db *db = job->db;
+  const int nf = db->numFiles();
+  if (nf == 0) return SGZ_OK;
+  const int warps = (size_t)job->qin.W * 16 <= ((size_t)48 << 10) ? 4 : 1;
+  k_filemax_boost_warp<<<ceil_div(nf, warps), 32 * warps, (size_t)warps * job->qin.W * sizeof(float), st>>>(
+      boost_src(job, job->qin, nullptr), db->dFileStart.p, job->dFileMax.p, nf, job->dFileBoost.p);
   SGZ_LAUNCH_CHECK(job->ctx);
   return SGZ_OK;
 }

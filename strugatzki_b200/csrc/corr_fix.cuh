@@ -56,6 +56,7 @@ struct CorrFixParams {
   BoostSrc boost;
   unsigned long long *fileMax;
   uint32_t *fileNaN;        // [numFiles] set when a window of the file is NaN in the reference (exactly constant), or nullptr
+  int listOnly;             // 1: a list that overflowed is left alone (corr_refine.cuh) instead of scanning the curve for sentinels
 };
 
 __device__ __forceinline__ float fix_value(const CorrFixParams &p, int ch, int64_t g) {
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(128) k_corr_fixup(const CorrFixParams p) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x, t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (n <= p.cap) {
     for (int64_t i = t; i < (int64_t)n; i += stride) fix_one(p, (int64_t)p.list[i]);
-  } else {
+  } else if (!p.listOnly) {
     for (int64_t g = t; g < p.usedFrames; g += stride)
       if (__float_as_uint(p.sim[g]) == kFixSentinel) fix_one(p, g);
   }

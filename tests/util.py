@@ -75,11 +75,16 @@ def assert_sims_close(got, want, rel=1e-5, abs_tol=2e-6, what="sim") -> int:
     return int(np.count_nonzero(err > rel * np.abs(want[ok])))
 
 
-def assert_matches_equal(got: List[dict], want: List[dict], rel=1e-5):
+def assert_matches_equal(got: List[dict], want: List[dict], rel=1e-5, exact_sim=False):
+    """same files and spans in the same order; sims and boosts within rel (absolute floor 2e-6).  exact_sim: the sims are
+    the oracle's bit for bit (punch-in searches: the decisive offsets are re-evaluated in Double, corr_refine.cuh)"""
     assert len(got) == len(want), f"{len(got)} matches, oracle has {len(want)}\n got={got}\nwant={want}"
     for i, (g, w) in enumerate(zip(got, want)):
         assert (g["file"], g["start"], g["stop"]) == (w["file"], w["start"], w["stop"]), \
             f"match {i}: got {g}, oracle {w}"
+        if exact_sim:
+            a, b = np.float32(g["sim"]), np.float32(w["sim"])
+            assert a.tobytes() == b.tobytes() or (np.isnan(a) and np.isnan(b)), f"match {i} sim: got {a!r}, oracle {b!r}"
         for key in ("sim", "boostIn", "boostOut"):
             a, b = float(g[key]), float(w[key])
             if np.isnan(b):

@@ -16,7 +16,7 @@ for files in sizes:
     db.add_synth_many(synth.BASE_SEED, 1, files, F, mu, sigma, float(floor0))
     db.finalize()
     job = engine.CorrelationJob(db, bench.corr_config(N), inp)
-    for _ in range(max(reps, 430000 // files)):      # about half a second of load: clocks ramp up (and the power cap sets in) under continuous load only
+    for _ in range(int(os.environ.get("T2_WARM", max(reps, 430000 // files)))):      # about half a second of load: clocks ramp up (and the power cap sets in) under continuous load only
         job.scan()
     ms = []
     for _ in range(reps):
