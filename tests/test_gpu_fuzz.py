@@ -107,3 +107,29 @@ def test_fuzz_punch_in_search(ctx, seed):
 @pytest.mark.parametrize("seed", range(200, 280))
 def test_fuzz_punch_out_search(ctx, seed):
     run_case(ctx, seed, punch_out=True)
+
+
+@pytest.mark.parametrize("num_matches,num_per_file", [(1, 1), (20, 1), (100, 1), (224, 1), (230, 2), (60, 3)])
+def test_many_files_exact_result(ctx, num_matches, num_per_file):
+    """more files than matches: the threshold of the exact re-evaluation comes from the numMatches-th largest DISTINCT file
+    maximum (k_refine_threshold).  Files that occur two and three
+    times take ONE place each in the reference's TreeSet, so the threshold has to reach further down than their copies."""
+    from strugatzki_b200 import engine
+    rng = np.random.default_rng(5)
+    mu, sigma, floor0, norm = synth.default_profile(14)
+    n_files, w = 700, 43
+    inp = synth.synth_file(synth.BASE_SEED, 0, 120, mu, sigma, floor0)
+    files = [synth.synth_file(synth.BASE_SEED, 1 + i, int(rng.integers(150, 420)), mu, sigma, floor0) for i in range(n_files)]
+    for k in range(40):                                  # needles of graded quality
+        f = int(rng.integers(0, n_files))
+        a = int(rng.integers(0, files[f].shape[0] - w))
+        files[f][a:a + w] = synth.plant(inp[10:10 + w], 91, k, 0.01 + 0.01 * k)
+    for k in range(30):                                  # repeated files, some of them among the best
+        src, dst = int(rng.integers(0, n_files)), int(rng.integers(0, n_files))
+        files[dst] = files[src].copy()
+    op, nc = corr_cfgs(inp, norm, punch_in=(10 * STEP, (10 + w) * STEP), num_matches=num_matches, num_per_file=num_per_file,
+                       min_spacing=4 * STEP)
+    want = O.corr_search(op, files)
+    got = engine.CorrelationJob(build_db(ctx, files, norm), nc, inp).run()
+    assert_matches_equal(got, want, exact_sim=True)
+    assert len(got) == min(num_matches, len(want)) and len(got) >= min(num_matches, 200)
