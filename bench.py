@@ -425,6 +425,9 @@ def main():
             "config": config_block(world, files),
             "roofline": roofline,
             "breakdown_ms": {"k1_scan": float(np.mean(scan_ms)), "k2_select_kernels": float(np.mean(select_ms)),
+                             "note": "k1_scan = the k_corr_tc2 launch alone (an event sits right behind it); k2_select_kernels = "
+                                     "what follows it on the device: exact Double re-evaluation of the offsets that can reach "
+                                     "the result (the returned sims are the reference's bit for bit), per-file boosts",
                              "wall_per_step": wall_ms / args.steps,
                              "rank0_host_phases": {k: (v / args.steps if k == "rounds" else 1e3 * v / args.steps)
                                                    for k, v in phases.items()} if world > 1 else None},
