@@ -26,7 +26,7 @@ if mode == "launches":
     allms = sum(v[1] for v in tot.values())
     ks = [{"kernel": k, "launches": v[0], "total_ms": round(v[1], 4), "share_of_all": round(v[1] / allms, 4)}
           for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1])]
-    search = {k: v[1] for k, v in tot.items() if k.startswith(("k_corr", "k_replay", "k_candidates"))}
+    search = {k: v[1] for k, v in tot.items() if k.startswith(("k_corr", "k_replay", "k_candidates", "k_refine", "k_filemax"))}
     s = sum(search.values())
     json.dump({"source": sys.argv[2], "note": "per-launch times under ncu are serialised and cold-cache: compare SHARES, not absolutes",
                "kernels": ks, "search_step_shares": {k: round(v / s, 4) for k, v in sorted(search.items(), key=lambda kv: -kv[1])}},
