@@ -8,3 +8,7 @@ timeout 300 ncu --set full --clock-control none -k regex:k_segm_pick_warp -s 1 -
 timeout 300 ncu --set full --clock-control none -k regex:k_cross -s 1 -c 1 -f -o gpurun_out/r02_k_cross python tools/cross_probe.py > gpurun_out/ncu_cross.log 2>&1; echo rc=$?
 timeout 300 ncu --set full --clock-control none -k regex:k_stats_hist -s 1 -c 1 -f -o gpurun_out/r02_k_stats_hist python tools/stats_probe.py > gpurun_out/ncu_stats.log 2>&1; echo rc=$?
 ls -la gpurun_out/
+# k_corr_tc2 under sustained load: role counters, per-CTA wall clock and mean SM clock per ablation; power / clock trace
+bash tools/t2_power_ablate.sh > gpurun_out/r02_k_corr_tc2_power_ablation.txt 2>&1; echo rc=$?
+bash tools/t2_power_watch.sh; cp gpurun_out/power_watch.csv gpurun_out/r02_k_corr_tc2_power_watch.csv
+python tools/t2_size_probe.py > gpurun_out/size_probe.log 2>&1; echo rc=$?
