@@ -202,7 +202,12 @@ int sgz_corr_create(sgz_db *db, const sgz_corr_config *cfg, const void *input,
                     int64_t inputFrames, int32_t layout, sgz_corr **out);
 int sgz_corr_destroy(sgz_corr *job);
 
-/* One-call synchronous search on this context's shard: scan + select + merge. */
+/* One-call synchronous search on this context's shard: scan + select + merge.
+ * Punch-in searches (no punch-out): the matches are the reference's with the reference's sims BIT FOR BIT -- every
+ * offset that can reach the result is re-evaluated in the reference's Double arithmetic (MathUtil.stat / correlate,
+ * :29-62,177-196) before the queues of addMatch (:120-150) are replayed, so equal sims of repeated material are one
+ * entry like in the TreeSet and the result does not depend on how the database is sharded.  Punch-out searches:
+ * same files and spans, sims within 1e-5 relative. */
 int sgz_corr_run(sgz_corr *job);
 /* Asynchronous variant: runs on a worker thread; poll/abort from the host loop
  * (reference: checkAborted() / progress_=, FeatureCorrelationImpl.scala:164,192,402). */
