@@ -659,6 +659,11 @@ int sgz_corr_scan(sgz_corr *job) {
     job->keysCached = false;
     static const bool refineOff = getenv("SGZ_REFINE") && atoi(getenv("SGZ_REFINE")) == 0;   // developer knob
     job->refine = t2 && !job->hasOut && !refineOff;
+    // filter mode (opt-in): one FP16 product instead of three in K1, the exact re-evaluation makes up for it -- only where
+    // the result is decided by the re-evaluated offsets alone (numPerFile = 1 punch-in searches on a resident database)
+    static const bool fastOn = getenv("SGZ_FAST") && atoi(getenv("SGZ_FAST")) == 1;   // developer knob
+    job->fast = fastOn && job->refine && job->cfg.numPerFile == 1 && db->chunks.empty() &&
+                t2_geom(job->qin.W, ctx->smemOptin).NP == 1;
     if (job->refine) {
       SGZ_TRY(job->dRefList.alloc(kRefineCap));
       SGZ_TRY(job->dRefCount.alloc(2));

@@ -15,6 +15,7 @@ struct PunchQuery {
   float weight = 0.5f;
   std::vector<float> taps;  // [numCh][Wq]
   double stdT = 0, stdS = 0, rhoT = 0, rhoS = 0, lnAvg = 0;
+  double rhoTFast = 0, rhoSFast = 0;   // sums of the taps rounded to FP16 (filter mode of k_corr_tc2: first parts only)
   DevBuf<float> dTaps;
   std::vector<uint16_t> tcTaps;
   DevBuf<uint16_t> dTcTaps;    // tensor-core path: hi/lo Toeplitz atoms (corr_tc.cuh), empty when not applicable
@@ -45,6 +46,7 @@ struct sgz_corr {
   DevBuf<float> dRefThr;
   DevBuf<unsigned long long> dFileMaxExact;
   bool refine = false;      // this scan re-evaluates them
+  bool fast = false;        // SGZ_FAST=1: K1 in filter mode (first-part product only), the re-evaluation with wider margins
   float tailMs = 0.f;       // device time of a scan behind its K1 launches (re-evaluations, per-file boosts)
   int64_t numTiles = 0;
   int64_t numOffsets = 0;
@@ -200,13 +202,14 @@ inline int prepare_query(const sgz_db *db, const float *inputPlanar /*[numCh][in
   }
   // taps in the kernel's pair layout: [pair p][tap i] = float2(channel 2p, channel 2p+1), zero padded
   q.taps.assign((size_t)db->numPairs * q.Wq * 2, 0.f);
-  q.rhoT = q.rhoS = 0.0;
+  q.rhoT = q.rhoS = q.rhoTFast = q.rhoSFast = 0.0;
   for (int c = 0; c < numCh; c++) {
     double mean = c == 0 ? meanT : meanS;
     for (int i = 0; i < W; i++) {
       float tp = (float)((double)a[(size_t)c * W + i] - mean);
       q.taps[((size_t)(c >> 1) * q.Wq + i) * 2 + (c & 1)] = tp;
       (c == 0 ? q.rhoT : q.rhoS) += (double)tp;
+      (c == 0 ? q.rhoTFast : q.rhoSFast) += (double)__half2float(__float2half_rn(tp));
     }
   }
   SGZ_TRY(q.dTaps.alloc(q.taps.size()));
@@ -387,11 +390,18 @@ inline int run_refine(sgz_corr *job, cudaStream_t st) {
   PunchQuery &q = job->qin;
   SGZ_CUDA(cudaMemsetAsync(job->dRefCount.p, 0, 2 * sizeof(uint32_t), st));     // [offsets listed, files listed]
   SGZ_CUDA(cudaMemsetAsync(job->dFileMaxExact.p, 0, (size_t)nf * sizeof(unsigned long long), st));
-  k_refine_threshold<<<1, kRefineThrThreads, 0, st>>>(job->dFileMax.p, nf, job->cfg.numMatches, kRefineMargin, kRefineTieTol,
+  // filter mode: FP16 signal and taps -- a sim is off by about 1.4e-4 x (level / spread) / sqrt(cells of the window)
+  float margin = kRefineMargin, tieTol = kRefineTieTol;
+  if (job->fast) {
+    const float err = std::min(0.05f, 2.5e-4f * sqrtf(172.f / (float)q.W));
+    margin = 4.f * err;
+    tieTol = 2.f * err;
+  }
+  k_refine_threshold<<<1, kRefineThrThreads, 0, st>>>(job->dFileMax.p, nf, job->cfg.numMatches, margin, tieTol,
                                          job->dRefThr.p, job->dRefCand.p, job->dRefCount.p + 1);
   SGZ_LAUNCH_CHECK(job->ctx);
   k_refine_collect<<<(unsigned)job->ctx->smCount * 8, 256, 0, st>>>(
-      job->simIn.p, db->dFileStart.p, job->dFileMax.p, q.W, 0, job->dRefThr.p, kRefineMargin, job->cfg.numPerFile == 1 ? 1 : 0,
+      job->simIn.p, db->dFileStart.p, job->dFileMax.p, q.W, 0, job->dRefThr.p, margin, job->cfg.numPerFile == 1 ? 1 : 0,
       job->dRefCand.p, job->dRefCount.p + 1, job->dRefList.p, job->dRefCount.p, kRefineCap);
   SGZ_LAUNCH_CHECK(job->ctx);
   CorrFixParams fp{};
@@ -482,7 +492,9 @@ inline int run_scan_t2(sgz_corr *job, PunchQuery &q, int which, int tailExtra, f
     E.gateNm = (float)(avgMin * E.nT);
     E.invNT2 = (float)(1.0 / (E.nT * E.nT)); E.invNS2 = (float)(1.0 / (E.nS * E.nS));
     E.cT = (float)(1.0 / (E.nT * q.stdT)); E.cS = (float)(1.0 / (E.nS * q.stdS));
-    E.kTn = (float)(q.rhoT / (E.nT * E.nT * q.stdT)); E.kSn = (float)(q.rhoS / (E.nS * E.nS * q.stdS));
+    const bool fastRho = job->fast && which == 0 && G.NP == 1;
+    E.kTn = (float)((fastRho ? q.rhoTFast : q.rhoT) / (E.nT * E.nT * q.stdT));
+    E.kSn = (float)((fastRho ? q.rhoSFast : q.rhoS) / (E.nS * E.nS * q.stdS));
     E.wT = q.weight; E.wS = 1.0f - q.weight;
     E.useT = q.weight > 0.f; E.useS = q.weight < 1.f;
   }
@@ -504,6 +516,7 @@ inline int run_scan_t2(sgz_corr *job, PunchQuery &q, int which, int tailExtra, f
   }
   const bool prof = getenv("SGZ_CORR_TC_PROF") != nullptr;   // developer probe: cycles per role and phase
   auto kern = G.NP > 1 ? (prof ? k_corr_tc2<true, true> : k_corr_tc2<false, true>) : (prof ? k_corr_tc2<true, false> : k_corr_tc2<false, false>);
+  if (job->fast && which == 0 && G.NP == 1) kern = prof ? k_corr_tc2<true, false, true> : k_corr_tc2<false, false, true>;
   SGZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smemBytes));
   const unsigned grid = (unsigned)std::min<int64_t>(tileEnd - tileBegin, std::max(ctx->smCount - spareSMs, 1));
   DevBuf<long long> dProf;

@@ -338,7 +338,11 @@ __device__ __forceinline__ float t2_eval(const T2Eval &E, const T2Win &w, float 
 // warp 0: producer (bulk copies), warp 1: MMA issuer, warps 2-3: idle (they complete the first warpgroup, which hands most
 // of its registers to the others: setmaxnreg), warps 4..19: epilogue
 // kMulti: long windows, several passes per tile (T2Geom::NP > 1)
-template <bool kProf, bool kMulti>
+// kFast: FILTER mode (one-pass windows only) -- the first-part product a1 t1 alone: one MMA of three, the first-part plane
+// and taps alone (44 instead of 75 B/offset).  The sims are then accurate to a few 1e-4 instead of 1e-6; a punch-in search
+// with numPerFile = 1 still returns the reference's matches bit for bit, because everything within the (wider) margin of
+// the threshold is re-evaluated exactly afterwards (corr_refine.cuh).  Opt-in (SGZ_FAST=1).
+template <bool kProf, bool kMulti, bool kFast = false>
 __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p) {
   extern __shared__ __align__(1024) unsigned char smemRaw[];
   const T2Geom G = t2_geom(p.W, (size_t)p.smemMax, p.ring);
@@ -415,24 +419,25 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
           auto issue_sig = [&]() {
             const uint32_t s = it % (uint32_t)G.sigStages, u = it / (uint32_t)G.sigStages;
             if (u > 0) tc_wait(sigFree + s, (u - 1) & 1);
-            mbar_expect_tx(sigFull + s, 2 * G.planeBytes);
+            mbar_expect_tx(sigFull + s, (kFast ? 1u : 2u) * G.planeBytes);
             const unsigned char *s0 = src + (int64_t)(2 * c) * p.planeStrideBytes + shift, *s1 = s0 + p.planeStrideBytes;
             if ((p.l2hint & 1) && lastPass) {     // earlier passes: the planes of this tile come again
               bulk_g2s_hint(sigBuf(s, 0) + dOff, s0, G.planeBytes, sigFull + s, polSig);
-              bulk_g2s_hint(sigBuf(s, 1) + dOff, s1, G.planeBytes, sigFull + s, polSig);
+              if (!kFast) bulk_g2s_hint(sigBuf(s, 1) + dOff, s1, G.planeBytes, sigFull + s, polSig);
             } else {
               bulk_g2s(sigBuf(s, 0) + dOff, s0, G.planeBytes, sigFull + s);
-              bulk_g2s(sigBuf(s, 1) + dOff, s1, G.planeBytes, sigFull + s);
+              if (!kFast) bulk_g2s(sigBuf(s, 1) + dOff, s1, G.planeBytes, sigFull + s);
             }
           };
           auto issue_taps = [&]() {
             const uint32_t t = it % (uint32_t)G.tapStages, v = it / (uint32_t)G.tapStages;
             if (v > 0) tc_wait(tapFree + t, (v - 1) & 1);
-            mbar_expect_tx(tapFull + t, G.tapsBytes);
+            const uint32_t tapBytes = kFast ? (uint32_t)G.natom * 256u : G.tapsBytes;     // filter mode: the first-part atoms
+            mbar_expect_tx(tapFull + t, tapBytes);
             const unsigned char *tsrc = p.taps + (size_t)c * G.tapsFullBytes + (size_t)j * (size_t)(2 * G.KS * 256);
             if (!kMulti) {
-              if (p.l2hint & 2) bulk_g2s_hint(tapBuf(t), tsrc, G.tapsBytes, tapFull + t, polKeep);
-              else bulk_g2s(tapBuf(t), tsrc, G.tapsBytes, tapFull + t);
+              if (p.l2hint & 2) bulk_g2s_hint(tapBuf(t), tsrc, tapBytes, tapFull + t, polKeep);
+              else bulk_g2s(tapBuf(t), tsrc, tapBytes, tapFull + t);
             } else {   // the atoms [32 j, 32 j + natom) of both parts
               bulk_g2s(tapBuf(t), tsrc, (uint32_t)G.natom * 256u, tapFull + t);
               bulk_g2s(tapBuf(t) + (size_t)G.natom * 256, tsrc + (size_t)G.natomFull * 256, (uint32_t)G.natom * 256u, tapFull + t);
@@ -495,6 +500,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
           // critical path of the kernel, so the six narrow steps are written out with constant geometry.)
           auto kstep = [&](uint32_t k, uint32_t c0, uint32_t id, uint32_t acc) {
             const uint64_t d1 = aHi + 2u * k, d2 = aLo + 2u * k, b1 = tHi + 32u * k + 2u * c0, b2 = tLo + 32u * k + 2u * c0;
+            if (kFast) { tc_mma(dMain + c0, d1, b1, id, accMain | acc); return; }
             tc_mma_fill(dMain + c0, d1, b1, id, accMain | acc);
             tc_mma_lastuse(dCorr + c0, d1, b2, id, accCorr | acc);
             tc_mma(dCorr + c0, d2, b1, id, 1);
@@ -502,6 +508,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
           if (!kMulti && p.narrow && nk >= 7 && !(kProf && p.dbg & 1)) {
             uint64_t d1 = aHi + 6, d2 = aLo + 6, b1 = tHi + 96, b2 = tLo + 96;
             for (int k = 3; k <= nk - 4; k++, d1 += 2, d2 += 2, b1 += 32, b2 += 32) {
+              if (kFast) { tc_mma(dMain, d1, b1, idesc, accMain | (uint32_t)(k > 3)); continue; }
               tc_mma_fill(dMain, d1, b1, idesc, accMain | (uint32_t)(k > 3));
               tc_mma_lastuse(dCorr, d1, b2, idesc, accCorr | (uint32_t)(k > 3));
               tc_mma(dCorr, d2, b1, idesc, 1);
@@ -512,6 +519,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
             uint64_t d1 = aHi, d2 = aLo, b1 = tHi, b2 = tLo;
             for (int k = 0; k < nk; k++, d1 += 2, d2 += 2, b1 += 32, b2 += 32) {
               if ((kProf && p.dbg & 1)) break;
+              if (kFast) { tc_mma(dMain, d1, b1, idesc, accMain | (uint32_t)(k > 0)); continue; }
               tc_mma_fill(dMain, d1, b1, idesc, accMain | (uint32_t)(k > 0));
               tc_mma_lastuse(dCorr, d1, b2, idesc, accCorr | (uint32_t)(k > 0));
               tc_mma(dCorr, d2, b1, idesc, 1);
@@ -631,11 +639,11 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
         asm volatile("tcgen05.fence::after_thread_sync;");
         uint32_t u[16], w[16];
         tc_ld16_nowait(laneAddr + 0 * 64, u);
-        tc_ld16_nowait(laneAddr + 1 * 64, w);
+        if (!kFast) tc_ld16_nowait(laneAddr + 1 * 64, w);     // (filter mode: the correction accumulators are never written)
         tc_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; i++) {
-          const float v = fmaf(__uint_as_float(w[i]), 1.0f / kTcLoScale, __uint_as_float(u[i]));
+          const float v = kFast ? __uint_as_float(u[i]) : fmaf(__uint_as_float(w[i]), 1.0f / kTcLoScale, __uint_as_float(u[i]));
           accT[i] = j == 0 ? v : accT[i] + v;
         }
         if (p.splitRelease) {
@@ -643,12 +651,12 @@ __global__ void __launch_bounds__(kT2Threads, 1) k_corr_tc2(const CorrT2Params p
           __syncwarp();
           if (lane == 0) mbar_arrive(accEmptyT);
         }
-        tc_ld16_nowait(laneAddr + 2 * 64, u);
+        if (!kFast) tc_ld16_nowait(laneAddr + 2 * 64, u);
         tc_ld16_nowait(laneAddr + 3 * 64, w);
         tc_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; i++) {
-          const float v = fmaf(__uint_as_float(u[i]), 1.0f / kTcLoScale, __uint_as_float(w[i]));
+          const float v = kFast ? __uint_as_float(w[i]) : fmaf(__uint_as_float(u[i]), 1.0f / kTcLoScale, __uint_as_float(w[i]));
           accS[i] = j == 0 ? v : accS[i] + v;
         }
         const int nMain = min(p.numCh - 1, kT2Mains);

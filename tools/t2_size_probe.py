@@ -18,11 +18,11 @@ for files in sizes:
     job = engine.CorrelationJob(db, bench.corr_config(N), inp)
     for _ in range(int(os.environ.get("T2_WARM", max(reps, 430000 // files)))):      # about half a second of load: clocks ramp up (and the power cap sets in) under continuous load only
         job.scan()
-    ms = []
+    ms, tail = [], []
     for _ in range(reps):
-        job.scan(); ms.append(job.timing()["scan_ms"])
+        job.scan(); ms.append(job.timing()["scan_ms"]); tail.append(job.timing()["select_ms"])
     m = float(np.median(ms))
     tiles = files * F / 8192.0
     print("files", files, "scan_ms", round(m, 4), "min", round(float(np.min(ms)), 4), "us_per_tile_per_sm", round(m * 1e3 / (tiles / 148.0), 3),
-          "offsets_per_s", "%.4g" % (files * F / (m * 1e-3)), flush=True)
+          "offsets_per_s", "%.4g" % (files * F / (m * 1e-3)), "tail_ms", round(float(np.median(tail)), 4), flush=True)
     del job, db
