@@ -1,0 +1,57 @@
+"""The oracle's match queues against a second, independently written restatement (tests/queue_model.py): both replay
+FeatureCorrelationImpl.body() (FeatureCorrelationImpl.scala:113-150, 190-246, 250-400) on the same similarity curves and
+must return the same matches bit for bit -- over the randomly drawn configurations of the GPU differential tests (ragged and
+too-short files, repeated files = equal sims, silence = NaN sims, quiet files = gated sims, any numMatches / numPerFile /
+minSpacing, punch-in only and punch-in + punch-out)."""
+import numpy as np
+import pytest
+
+import queue_model
+from test_gpu_fuzz import draw_case
+from util import O, STEP, corr_cfgs, make_db, make_input, synth
+
+
+def same(model, oracle):
+    assert len(model) == len(oracle), (len(model), len(oracle))
+    for i, (a, b) in enumerate(zip(model, oracle)):
+        for key in ("file", "start", "stop"):
+            assert a[key] == b[key], (i, key, a, b)
+        for key in ("sim", "boostIn", "boostOut"):
+            x, y = np.float32(a[key]), np.float32(b[key])
+            assert x.tobytes() == y.tobytes() or (np.isnan(x) and np.isnan(y)), (i, key, a, b)
+
+
+@pytest.mark.parametrize("block", range(8))
+def test_punch_in_queues(block):
+    for seed in range(15 * block, 15 * block + 15):
+        inp, files, norm, cfg = draw_case(seed, False)
+        op, _ = corr_cfgs(inp, norm, **cfg)
+        same(queue_model.search(O, op, files), O.corr_search(op, files))
+
+
+@pytest.mark.parametrize("block", range(8))
+def test_punch_out_queues(block):
+    n = 0
+    for seed in range(200 + 10 * block, 200 + 10 * block + 10):
+        inp, files, norm, cfg = draw_case(seed, True)
+        op, _ = corr_cfgs(inp, norm, **cfg)
+        want = O.corr_search(op, files)
+        same(queue_model.search(O, op, files), want)
+        n += len(want)
+    assert n > 0
+
+
+def test_repeated_files_silence_and_spacing():
+    """equal sims (a file three times), NaN sims (a constant stretch) and a tight minSpacing in one search, with and
+    without punch-out"""
+    files, norm = make_db(6, [900, 700, 900, 650, 900, 300])
+    inp = make_input(700)
+    files[2] = files[0].copy()
+    files[4] = files[0].copy()
+    files[1][100:420] = files[1][100]
+    files[3][50:222] = synth.plant(inp[:172], 5, 1)
+    for po in (None, (345 * STEP, 517 * STEP)):
+        for nm, npf, sp in ((4, 2, 0), (10, 3, 30 * STEP), (3, 1, 10 ** 7), (50, 50, 0)):
+            op, _ = corr_cfgs(inp, norm, punch_out=po, num_matches=nm, num_per_file=npf, min_spacing=sp,
+                              min_punch=40 * STEP, max_punch=300 * STEP)
+            same(queue_model.search(O, op, files), O.corr_search(op, files))
