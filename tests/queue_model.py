@@ -166,3 +166,51 @@ def search(O, op, files) -> List[dict]:
 
     return [dict(sim=float(m.sim), file=m.file, start=m.start, stop=m.stop, boostIn=float(m.boost_in),
                  boostOut=float(m.boost_out)) for m in all_prio.items]
+
+
+class MaxOrdSet(MinOrdSet):
+    """SortedSet[Break](BreakMaxOrd): iteration from the SMALLEST sim up (FeatureSegmentation.scala:60-62); `last` is the
+    largest.  Implemented on the descending list of MinOrdSet read backwards."""
+
+    def last(self):
+        return self.items[0]
+
+    def ascending(self):
+        return self.items[::-1]
+
+
+def segmentation(O, sp, file) -> List[dict]:
+    """FeatureSegmentationImpl.body() (:52-142) on the oracle's similarity curve: entryHasSpace / highestSim / addBreak"""
+    step = sp.step_size
+
+    def full_to_feat(x):
+        return (x + step // 2) // step
+
+    half = full_to_feat(sp.corr_len)
+    win = 2 * half
+    n = file.shape[0]
+    af_start = max(0, full_to_feat(sp.span_start)) if sp.span_start is not None else 0
+    af_stop = min(n, full_to_feat(sp.span_stop)) if sp.span_stop is not None else n
+    af_len = af_stop - af_start
+    _, curve = O.segm_run(sp, file, want_curve=True)
+    prio = MaxOrdSet()
+    last = None
+    # the first read takes min(left, winLen) frames, every later one a single frame (:103-107): a span shorter than the
+    # window still yields ONE offset, evaluated on the freshly allocated (zero-filled) rest of the buffer
+    n_off = af_len - win + 1 if af_len >= win else (1 if af_len > 0 else 0)
+    for off in range(n_off):
+        sim = F32(curve[off])
+        highest = prio.last().sim if len(prio) else F32(0.0)
+        if len(prio) < sp.num_breaks or sim < highest:
+            b = Match(sim, 0, (af_start + off + half) * step, 0, 0, 0)      # Break(sim, pos): pos in `start`
+            if last is not None and (b.start - last.start) < sp.min_spacing:
+                if last.sim > b.sim:
+                    prio.remove(last)
+                    prio.add(b)
+                    last = b
+            else:
+                prio.add(b)
+                if len(prio) > sp.num_breaks:
+                    prio.remove(prio.last())
+                last = b
+    return [dict(sim=float(b.sim), pos=b.start) for b in prio.ascending()]

@@ -55,3 +55,33 @@ def test_repeated_files_silence_and_spacing():
             op, _ = corr_cfgs(inp, norm, punch_out=po, num_matches=nm, num_per_file=npf, min_spacing=sp,
                               min_punch=40 * STEP, max_punch=300 * STEP)
             same(queue_model.search(O, op, files), O.corr_search(op, files))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_segmentation_break_queue(seed):
+    """FeatureSegmentationImpl's break queue (:52-82) restated on the oracle's curve: same breaks bit for bit"""
+    rng = np.random.default_rng(400 + seed)
+    num_ch = int(rng.choice([3, 14]))
+    _, _, _, norm = synth.default_profile(num_ch)
+    n = int(rng.integers(40, 1500))
+    if seed % 3 == 0:
+        f, _ = synth.regime_file(synth.BASE_SEED, 30 + seed, n, num_ch, int(rng.integers(2, 9)))
+    else:
+        mu, sigma, floor0, _ = synth.default_profile(num_ch)
+        f = synth.synth_file(synth.BASE_SEED, 30 + seed, n, mu, sigma, floor0)
+    if seed % 5 == 1 and n > 300:
+        f[100:260] = f[100]                               # silence: NaN sims
+    half = int(rng.choice([1, 2, 7, 43, 86]))
+    use_span = bool(rng.integers(0, 2))
+    sp = O.SegmParams(step_size=STEP, corr_len=half * STEP + int(rng.integers(-200, 200)), temporal_weight=float(rng.choice([0, 1, 0.5, 0.3])),
+                      norm=norm if rng.integers(0, 3) else None, num_breaks=int(rng.choice([1, 2, 5, 20, 100])),
+                      min_spacing=int(rng.choice([0, 1, 512, 22050, 10 ** 6])),
+                      span_start=int(rng.integers(0, n // 3)) * STEP + 17 if use_span else None,
+                      span_stop=int(rng.integers(2 * n // 3, n + 50)) * STEP - 23 if use_span else None)
+    want = O.segm_run(sp, f)
+    got = queue_model.segmentation(O, sp, f)
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert a["pos"] == b["pos"], (a, b)
+        x, y = np.float32(a["sim"]), np.float32(b["sim"])
+        assert x.tobytes() == y.tobytes() or (np.isnan(x) and np.isnan(y)), (a, b)
