@@ -1,0 +1,108 @@
+"""The arithmetic of one FeatureCorrelation offset, restated a second time -- test infrastructure, like the oracle.
+
+Pure-Python loops over IEEE doubles (Python's float) and numpy.float32 scalars, written from MathUtil.scala (stat :29-62, avg
+:109-118, normalize :132-152, correlate :177-196) and FeatureCorrelationImpl.scala (readInBuffer :83-98, calcBoost :73-78, the
+loop body :190-211): same conversion points, same order of every addition (stat walks the ring buffer in PHYSICAL order,
+correlate in logical order), Float arithmetic where the Scala has Floats.  tests/test_queue_model.py compares the curves it
+produces with the oracle's bit for bit on small cases; together with queue_model.py (the queues) every part of the oracle's
+FeatureCorrelation has an independently written twin."""
+import math
+
+import numpy as np
+
+F32 = np.float32
+
+
+def normalize(norm, b):
+    """MathUtil.normalize: Float arithmetic, in place; b = [ch][frames] of np.float32"""
+    if norm is None:
+        return
+    for ch in range(len(b)):
+        mn, mx = F32(norm[ch][0]), F32(norm[ch][1])
+        d = F32(mx - mn)
+        for i in range(len(b[ch])):
+            b[ch][i] = F32(F32(b[ch][i] - mn) / d)
+
+
+def stat(mat, frame_len, chan_off, chan_len):
+    """MathUtil.stat over ring positions 0 .. frame_len-1 of rows chan_off .. : (mean, stddev) in Double"""
+    s = 0.0
+    for ch in range(chan_off, chan_off + chan_len):
+        for i in range(frame_len):
+            s += float(mat[ch][i])
+    size = frame_len * chan_len
+    mean = s / size
+    s = 0.0
+    for ch in range(chan_off, chan_off + chan_len):
+        for i in range(frame_len):
+            d = float(mat[ch][i]) - mean
+            s += d * d
+    return mean, math.sqrt(s / size)
+
+
+def avg(row, n):
+    s = 0.0
+    for i in range(n):
+        s += float(row[i])
+    return F32(s / n)
+
+
+def correlate(a, a_mean, a_std, num_frames, num_ch, b, b_mean, b_std, b_frame_off, b_chan_off):
+    a_add, b_add = -a_mean, -b_mean
+    s = 0.0
+    for ch in range(num_ch):
+        ca, cb = a[ch], b[ch + b_chan_off]
+        for i in range(num_frames):
+            s += (float(ca[i]) + a_add) * (float(cb[(i + b_frame_off) % len(cb)]) + b_add)
+    # (IEEE division: 0 / 0 = NaN for a constant window, where Python's float raises)
+    return F32(np.float64(s) / np.float64(a_std * b_std * (num_ch * num_frames)))
+
+
+def curve(inp, start_frame, w, norm, weight, max_boost, file):
+    """(sim, boost) of every offset of `file` for the punch window inp[start_frame : start_frame + w] (loop A, no gate by
+    the queues): inp, file = [frames][ch] float32 arrays"""
+    num_ch = inp.shape[1]
+    a = [[F32(inp[start_frame + i][ch]) for i in range(w)] for ch in range(num_ch)]
+    normalize(norm, a)
+    t_mean, t_std = stat(a, w, 0, 1)
+    s_mean, s_std = stat(a, w, 1, num_ch - 1)
+    ln_avg_in = math.log(float(avg(a[0], w)))
+    wt = F32(weight)
+    n = file.shape[0]
+    ring = [[F32(0.0)] * w for _ in range(num_ch)]
+    sims, boosts = [], []
+    left, read_sz, read_off, logical = n, w, 0, 0
+    pos = 0
+    if left < w:
+        return sims, boosts                       # (no offset)
+    while left > 0:
+        chunk = min(left, read_sz)
+        fresh = [[F32(file[pos + k][ch]) for k in range(chunk)] for ch in range(num_ch)]
+        normalize(norm, fresh)
+        for ch in range(num_ch):
+            for k in range(chunk):
+                ring[ch][read_off + k] = fresh[ch][k]
+        pos += chunk
+        off = logical % w
+        boost = F32(math.exp((ln_avg_in - math.log(float(avg(ring[0], w)))) / 0.6))
+        if boost <= F32(max_boost):
+            if wt > 0:
+                b_mean, b_std = stat(ring, w, 0, 1)
+                temporal = correlate(a[0:1], t_mean, t_std, w, 1, ring, b_mean, b_std, off, 0)
+            else:
+                temporal = F32(0.0)
+            if wt < 1:
+                b_mean, b_std = stat(ring, w, 1, num_ch - 1)
+                spectral = correlate(a[1:], s_mean, s_std, w, num_ch - 1, ring, b_mean, b_std, off, 1)
+            else:
+                spectral = F32(0.0)
+            sim = F32(F32(temporal * wt) + F32(spectral * F32(F32(1.0) - wt)))
+        else:
+            sim = F32(0.0)
+        sims.append(sim)
+        boosts.append(boost)
+        left -= chunk
+        read_off = (read_off + chunk) % w
+        logical += 1
+        read_sz = 1
+    return sims, boosts

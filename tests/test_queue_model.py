@@ -85,3 +85,32 @@ def test_segmentation_break_queue(seed):
         assert a["pos"] == b["pos"], (a, b)
         x, y = np.float32(a["sim"]), np.float32(b["sim"])
         assert x.tobytes() == y.tobytes() or (np.isnan(x) and np.isnan(y)), (a, b)
+
+
+@pytest.mark.parametrize("num_ch,w,weight,use_norm,max_boost", [
+    (14, 43, 0.5, True, 8.0), (5, 16, 0.3, True, 8.0), (2, 3, 1.0, False, 8.0), (3, 7, 0.0, True, 1.05), (14, 20, 0.7, False, 2.0),
+])
+def test_offset_arithmetic_restated(num_ch, w, weight, use_norm, max_boost):
+    """tests/arith_model.py (normalize, stat in ring order, correlate in logical order, calcBoost, the Float blend) gives the
+    oracle's similarity curve BIT FOR BIT, silence (0 / 0 = NaN) and gated offsets (boost > maxBoost -> 0f) included"""
+    import warnings
+
+    import arith_model
+    mu, sigma, floor0, norm = synth.default_profile(num_ch)
+    inp = synth.synth_file(synth.BASE_SEED, 0, w + 9, mu, sigma, floor0)
+    f = synth.synth_file(synth.BASE_SEED, 77, 140, mu, sigma, floor0)
+    f[60:60 + w + 5] = f[60]                                   # a constant stretch: NaN sims
+    f[115:, 0] *= np.float32(0.6)                              # a quieter stretch: boosts above a tight maxBoost
+    norm = norm if use_norm else None
+    op, _ = corr_cfgs(inp, norm, punch_in=(4 * STEP, (4 + w) * STEP), w_in=weight, max_boost=max_boost)
+    want_sim, want_boost = O.corr_curve(op, f, 0, 0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                        # 0 / 0 in numpy scalars warns
+        got_sim, got_boost = arith_model.curve(inp, 4, w, norm, weight, max_boost, f)
+    assert len(got_sim) == len(want_sim) == 140 - w + 1
+    a, b = np.array(got_sim, np.float32), np.asarray(want_sim, np.float32)
+    assert np.array_equal(np.isnan(a), np.isnan(b)) and (np.isnan(b).any() or weight == 0.0)
+    assert np.array_equal(a[~np.isnan(a)].view(np.uint32), b[~np.isnan(b)].view(np.uint32))
+    assert np.array_equal(np.array(got_boost, np.float32).view(np.uint32), np.asarray(want_boost, np.float32).view(np.uint32))
+    if max_boost < 2:
+        assert (b == 0).any()
