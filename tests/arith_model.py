@@ -106,3 +106,43 @@ def curve(inp, start_frame, w, norm, weight, max_boost, file):
         logical += 1
         read_sz = 1
     return sims, boosts
+
+
+def correlate_half(num_ch, half, a, frame_off, chan_off):
+    """MathUtil.correlateHalf (:80-99): the two halves of the ring buffer against each other"""
+    num_frames = half << 1
+    mean, std = stat(a, num_frames, chan_off, num_ch)
+    add = -mean
+    s = 0.0
+    for ch in range(num_ch):
+        ca = a[ch + chan_off]
+        for i in range(frame_off, frame_off + half):
+            s += (float(ca[i % num_frames]) + add) * (float(ca[(i + half) % num_frames]) + add)
+    return F32(np.float64(s) / np.float64(std * std * (num_ch * half)))
+
+
+def segm_curve(file, half, norm, weight, af_start, af_stop):
+    """the similarity of every offset of FeatureSegmentationImpl.body()'s loop (:103-127): file = [frames][ch] float32"""
+    num_ch = file.shape[1]
+    win = 2 * half
+    wt = F32(weight)
+    ring = [[F32(0.0)] * win for _ in range(num_ch)]      # eInBuf: freshly allocated, zero-filled
+    left, read_sz, read_off, logical, pos = af_stop - af_start, win, 0, 0, af_start
+    sims = []
+    while left > 0:
+        chunk = min(left, read_sz)
+        fresh = [[F32(file[pos + k][ch]) for k in range(chunk)] for ch in range(num_ch)]
+        normalize(norm, fresh)
+        for ch in range(num_ch):
+            for k in range(chunk):
+                ring[ch][read_off + k] = fresh[ch][k]
+        pos += chunk
+        off = logical % win
+        temporal = correlate_half(1, half, ring, off, 0) if wt > 0 else F32(0.0)
+        spectral = correlate_half(num_ch - 1, half, ring, off, 1) if wt < 1 else F32(0.0)
+        sims.append(F32(F32(temporal * wt) + F32(spectral * F32(F32(1.0) - wt))))
+        left -= chunk
+        read_off = (read_off + chunk) % win
+        logical += 1
+        read_sz = 1
+    return sims

@@ -114,3 +114,31 @@ def test_offset_arithmetic_restated(num_ch, w, weight, use_norm, max_boost):
     assert np.array_equal(np.array(got_boost, np.float32).view(np.uint32), np.asarray(want_boost, np.float32).view(np.uint32))
     if max_boost < 2:
         assert (b == 0).any()
+
+
+@pytest.mark.parametrize("num_ch,half,weight,use_norm,n,span", [
+    (14, 21, 0.5, True, 130, None), (3, 2, 1.0, False, 60, (5, 50)), (5, 8, 0.0, True, 90, None), (14, 43, 0.3, True, 70, (0, 70)),
+])
+def test_segmentation_arithmetic_restated(num_ch, half, weight, use_norm, n, span):
+    """tests/arith_model.py: correlateHalf over the rotating buffer gives the oracle's segmentation curve bit for bit (a
+    span shorter than the window -- the last case -- yields the one offset on the zero-filled rest of the buffer)"""
+    import warnings
+
+    import arith_model
+    mu, sigma, floor0, norm = synth.default_profile(num_ch)
+    f = synth.synth_file(synth.BASE_SEED, 55, n, mu, sigma, floor0)
+    if n > 100:
+        f[40:40 + 2 * half + 4] = f[40]                        # silence: 0 / 0
+    norm = norm if use_norm else None
+    sp = O.SegmParams(step_size=STEP, corr_len=half * STEP, temporal_weight=weight, norm=norm, num_breaks=3, min_spacing=0,
+                      span_start=None if span is None else span[0] * STEP, span_stop=None if span is None else span[1] * STEP)
+    _, want = O.segm_run(sp, f, want_curve=True)
+    a0, a1 = (0, n) if span is None else span
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = np.array(arith_model.segm_curve(f, half, norm, weight, a0, a1), np.float32)
+    want = np.asarray(want[:len(got)], np.float32)
+    assert len(got) == (a1 - a0 - 2 * half + 1 if a1 - a0 >= 2 * half else 1)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.array_equal(got[ok].view(np.uint32), want[ok].view(np.uint32))
