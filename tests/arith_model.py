@@ -146,3 +146,52 @@ def segm_curve(file, half, norm, weight, af_start, af_stop):
         logical += 1
         read_sz = 1
     return sims
+
+
+def self_image(file1, file2, half, decimation, norm, weight, color_inv, color_warp, color_ceil, af_start, af_stop):
+    """SelfSimilarityImpl.body() (:64-167), GrayScale: the image as a list of rows of 0xRRGGBB ints"""
+    num_ch = file1.shape[1]
+    win = 2 * half
+    af_len = af_stop - af_start
+    num_corrs = max(0, af_len - win + 1)
+    i = num_corrs // decimation
+    if i <= 0xB504:
+        decim, ext = decimation, i
+    else:
+        decim = (num_corrs + 0xB503) // 0xB504
+        ext = num_corrs // decim
+    wt = F32(weight)
+    scale = F32(F32(1.0) / F32(color_ceil))
+    img = [[0] * ext for _ in range(ext)]
+    stop = num_corrs // decim * decim
+    buf = [[F32(0.0)] * win for _ in range(num_ch)]
+
+    def read(f, at, dst):
+        fresh = [[F32(f[at + k][ch]) for k in range(half)] for ch in range(num_ch)]
+        normalize(norm, fresh)
+        for ch in range(num_ch):
+            for k in range(half):
+                buf[ch][dst + k] = fresh[ch][k]
+
+    left = 0
+    while left < stop:
+        read(file1, left + af_start, 0)
+        right = left
+        while right < stop:
+            read(file2, right + af_start, half)
+            temporal = correlate_half(1, half, buf, 0, 0) if wt > 0 else F32(0.0)
+            spectral = correlate_half(num_ch - 1, half, buf, 0, 1) if wt < 1 else F32(0.0)
+            sim = F32(F32(temporal * wt) + F32(spectral * F32(F32(1.0) - wt)))
+            # colorFun(math.pow(math.max(0f, sim), colorWarp).toFloat * colorScale); math.max(0f, NaN) = NaN
+            base = sim if (sim > 0 or np.isnan(sim)) else F32(0.0)
+            v = F32(F32(math.pow(float(base), float(F32(color_warp)))) * scale)
+            x = F32(F32(1.0) - v) if color_inv else v
+            d = float(F32(x * F32(255))) + 0.5                    # Float * Int -> Float, + 0.5 -> Double
+            g = 0 if math.isnan(d) else int(max(-2147483648.0, min(2147483647.0, math.trunc(d))))      # Double.toInt
+            g = max(0, min(255, g))
+            colr = (g << 16) | (g << 8) | g
+            img[(ext - 1 - right // decim)][left // decim] = colr
+            img[(ext - 1 - left // decim)][right // decim] = colr
+            right += decim
+        left += decim
+    return img

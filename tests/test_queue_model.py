@@ -142,3 +142,25 @@ def test_segmentation_arithmetic_restated(num_ch, half, weight, use_norm, n, spa
     assert np.array_equal(np.isnan(got), np.isnan(want))
     ok = ~np.isnan(want)
     assert np.array_equal(got[ok].view(np.uint32), want[ok].view(np.uint32))
+
+
+@pytest.mark.parametrize("num_ch,half,decim,weight,inv,warp,ceil,n", [
+    (14, 6, 1, 0.5, False, 1.0, 1.0, 60), (5, 3, 2, 0.3, True, 0.5, 0.8, 50), (3, 4, 3, 1.0, False, 2.0, 1.0, 47), (14, 5, 1, 0.0, True, 1.0, 2.0, 40),
+])
+def test_self_similarity_restated(num_ch, half, decim, weight, inv, warp, ceil, n):
+    """tests/arith_model.py: SelfSimilarityImpl's cell loop, decimation, mirror pixels and GrayScale colour function
+    (:76-150) give the oracle's image pixel for pixel"""
+    import warnings
+
+    import arith_model
+    mu, sigma, floor0, norm = synth.default_profile(num_ch)
+    f = synth.synth_file(synth.BASE_SEED, 66, n, mu, sigma, floor0)
+    f[20:20 + 2 * half + 3] = f[20]                            # silence: NaN sims -> (NaN * 255 + 0.5).toInt = 0
+    p = O.SelfParams(step_size=STEP, corr_len=half * STEP, decimation=decim, temporal_weight=weight, norm=norm,
+                     color_inv=inv, color_warp=warp, color_ceil=ceil)
+    want = O.self_image(p, f)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = np.array(arith_model.self_image(f, f, half, decim, norm, weight, inv, warp, ceil, 0, n), np.int64)
+    assert got.shape == want.shape and got.shape[0] == (n - 2 * half + 1) // decim
+    assert np.array_equal(got, want.astype(np.int64) & 0xFFFFFF)
