@@ -195,3 +195,55 @@ def self_image(file1, file2, half, decimation, norm, weight, color_inv, color_wa
             right += decim
         left += decim
     return img
+
+
+def feature_stats(files):
+    """FeatureStatsImpl.body() / body1() (:30-135): per file the 1st and 99th percentile of every channel through a skewed
+    2048-bin histogram; over the files the minimum of the former and the maximum of the latter.  files = [frames][ch]"""
+    all_mins = all_maxs = None
+    per_file = []
+    for f in files:
+        n, num_ch = f.shape
+        mins = [F32(np.inf)] * num_ch
+        maxs = [F32(-np.inf)] * num_ch
+        sums = [0.0] * num_ch
+        for ch in range(num_ch):
+            for i in range(n):
+                v = F32(f[i][ch])
+                if v < mins[ch]:
+                    mins[ch] = v
+                if v > maxs[ch]:
+                    maxs[ch] = v
+                sums[ch] += float(v)
+        log05 = math.log(0.5)
+        p01, p99 = [0.0] * num_ch, [0.0] * num_ch
+        for ch in range(num_ch):
+            mean = sums[ch] / n
+            d = F32(maxs[ch] - mins[ch])                       # Float - Float
+            mn = (mean - float(mins[ch])) / float(d)
+            skew = log05 / math.log(mn)
+            hist = [0] * 2048
+            mn_f = mins[ch]
+            for i in range(n):
+                v = F32(f[i][ch])
+                x = float(F32(F32(v - mn_f) / d))              # (f - min) / d in Float, widened for math.pow
+                hist[int(math.pow(x, skew) * 2047 + 0.5)] += 1
+            p01n, p99n = int(n * 0.01), int(n * 0.99)
+            skewr = 1.0 / skew
+            cnt = i = 0
+            while cnt < p01n:
+                cnt += hist[i]
+                i += 1
+            p01[ch] = math.pow(i / 2048, skewr) * float(d) + float(mn_f)
+            while cnt < p99n:
+                cnt += hist[i]
+                i += 1
+            p99[ch] = math.pow(i / 2048, skewr) * float(d) + float(mn_f)
+        per_file.append((p01, p99))
+        if all_mins is None:
+            all_mins, all_maxs = list(p01), list(p99)
+        else:
+            for ch in range(num_ch):
+                all_mins[ch] = min(all_mins[ch], p01[ch])
+                all_maxs[ch] = max(all_maxs[ch], p99[ch])
+    return all_mins, all_maxs, per_file

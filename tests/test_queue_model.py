@@ -164,3 +164,17 @@ def test_self_similarity_restated(num_ch, half, decim, weight, inv, warp, ceil, 
         got = np.array(arith_model.self_image(f, f, half, decim, norm, weight, inv, warp, ceil, 0, n), np.int64)
     assert got.shape == want.shape and got.shape[0] == (n - 2 * half + 1) // decim
     assert np.array_equal(got, want.astype(np.int64) & 0xFFFFFF)
+
+
+def test_feature_stats_restated():
+    """tests/arith_model.py: FeatureStatsImpl's two passes (min / max / mean, skewed 2048-bin histogram, percentiles) give the
+    oracle's normalisation ranges to the last bit of the Doubles"""
+    import arith_model
+    mu, sigma, floor0, _ = synth.default_profile(5)
+    files = [synth.synth_file(synth.BASE_SEED, 90 + i, n, mu, sigma, floor0) for i, n in enumerate((700, 1500, 333))]
+    files[1][:, 2] *= np.float32(3.0)
+    want, per = O.stats_run(files, want_per_file=True)
+    mins, maxs, per_file = arith_model.feature_stats(files)
+    assert np.array_equal(np.array(mins), want[:, 0]) and np.array_equal(np.array(maxs), want[:, 1])
+    for i, (p01, p99) in enumerate(per_file):
+        assert np.array_equal(np.array(p01), per[i, :, 0]) and np.array_equal(np.array(p99), per[i, :, 1])
