@@ -1,4 +1,5 @@
-"""The arithmetic of one FeatureCorrelation offset, restated a second time -- test infrastructure, like the oracle.
+"""The arithmetic of the five processes, restated a second time -- test infrastructure, like the oracle
+(FeatureCorrelation's offset, FeatureSegmentation's correlateHalf, the SelfSimilarity image, CrossSimilarity, FeatureStats).
 
 Pure-Python loops over IEEE doubles (Python's float) and numpy.float32 scalars, written from MathUtil.scala (stat :29-62, avg
 :109-118, normalize :132-152, correlate :177-196) and FeatureCorrelationImpl.scala (readInBuffer :83-98, calcBoost :73-78, the
@@ -247,3 +248,49 @@ def feature_stats(files):
                 all_mins[ch] = min(all_mins[ch], p01[ch])
                 all_maxs[ch] = max(all_maxs[ch], p99[ch])
     return all_mins, all_maxs, per_file
+
+
+def cross_curve(file1, file2, norm, weight, max_boost):
+    """CrossSimilarityImpl.body() (:83-176) for Span.All inputs: the shorter file is the template, the longer one runs
+    through the 8192-frame buffer -- whose first read takes 8192 frames at once, whose write position wraps at the TEMPLATE
+    length and whose read index wraps at the BUFFER length, exactly as the reference has it"""
+    f_in1, f_in2 = (file1, file2) if file1.shape[0] < file2.shape[0] else (file2, file1)
+    len1, len2, num_ch = f_in1.shape[0], f_in2.shape[0], f_in1.shape[1]
+    a = [[F32(f_in1[i][ch]) for i in range(len1)] for ch in range(num_ch)]
+    normalize(norm, a)
+    t_mean, t_std = stat(a, len1, 0, 1)
+    s_mean, s_std = stat(a, len1, 1, num_ch - 1)
+    ln_avg_in = math.log(float(avg(a[0], len1)))
+    wt = F32(weight)
+    buf_sz = 8192
+    ring = [[F32(0.0)] * buf_sz for _ in range(num_ch)]
+    left, read_sz, read_off, logical, pos = len2, buf_sz, 0, 0, 0
+    out = []
+    while left > 0:
+        chunk = min(left, read_sz)
+        fresh = [[F32(f_in2[pos + k][ch]) for k in range(chunk)] for ch in range(num_ch)]
+        normalize(norm, fresh)
+        for ch in range(num_ch):
+            ring[ch][read_off:read_off + chunk] = fresh[ch]
+        pos += chunk
+        off = logical % len1
+        boost = F32(math.exp((ln_avg_in - math.log(float(avg(ring[0], len1)))) / 0.6))
+        if boost <= F32(max_boost):
+            if wt > 0:
+                b_mean, b_std = stat(ring, len1, 0, 1)
+                temporal = correlate(a[0:1], t_mean, t_std, len1, 1, ring, b_mean, b_std, off, 0)
+            else:
+                temporal = F32(0.0)
+            if wt < 1:
+                b_mean, b_std = stat(ring, len1, 1, num_ch - 1)
+                spectral = correlate(a[1:], s_mean, s_std, len1, num_ch - 1, ring, b_mean, b_std, off, 1)
+            else:
+                spectral = F32(0.0)
+            out.append(F32(F32(temporal * wt) + F32(spectral * F32(F32(1.0) - wt))))
+        else:
+            out.append(F32(0.0))
+        left -= chunk
+        read_off = (read_off + chunk) % len1
+        logical += 1
+        read_sz = 1
+    return out

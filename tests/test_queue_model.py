@@ -178,3 +178,22 @@ def test_feature_stats_restated():
     assert np.array_equal(np.array(mins), want[:, 0]) and np.array_equal(np.array(maxs), want[:, 1])
     for i, (p01, p99) in enumerate(per_file):
         assert np.array_equal(np.array(p01), per[i, :, 0]) and np.array_equal(np.array(p99), per[i, :, 1])
+
+
+@pytest.mark.parametrize("n1,n2,num_ch,weight", [(25, 8192 + 120, 5, 0.5), (8192 + 60, 17, 3, 0.3), (40, 300, 14, 1.0)])
+def test_cross_similarity_restated(n1, n2, num_ch, weight):
+    """tests/arith_model.py: CrossSimilarityImpl's loop with its 8192-frame buffer quirks gives the oracle's curve bit for bit"""
+    import warnings
+
+    import arith_model
+    mu, sigma, floor0, norm = synth.default_profile(num_ch)
+    f1 = synth.synth_file(synth.BASE_SEED, 41, n1, mu, sigma, floor0)
+    f2 = synth.synth_file(synth.BASE_SEED, 42, n2, mu, sigma, floor0)
+    want = O.cross_run(O.CrossParams(step_size=STEP, norm=norm, temporal_weight=weight), f1, f2)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = np.array(arith_model.cross_curve(f1, f2, norm, weight, 8.0), np.float32)
+    assert got.shape == want.shape == (1 + max(n1, n2) - min(max(n1, n2), 8192),)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.array_equal(got[ok].view(np.uint32), want[ok].view(np.uint32))
